@@ -1,0 +1,218 @@
+/*
+ * tsdrgpu.h -- C-ABI of the B200 (sm_100a) implementation of TempestSDR's IQ->raster DSP path.
+ *
+ * This is the drop-in boundary below the reference's own C host code: plain C, plain pointers and sizes, no
+ * C++ or torch types.  Every entry point names the reference function(s) it replaces
+ * (paths relative to /root/reference/TempestSDR/src).  The tsdr_* / tsdrplugin_* ABI above it is declared
+ * unchanged in TSDRLibrary.h / TSDRPlugin.h / TSDRCodes.h beside this file.
+ *
+ * Conventions
+ *   - every function returns TSDRGPU_OK (0) or a negative TSDRGPU_E* code; tsdrgpu_last_error() gives text;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls are asynchronous on
+ *     that stream unless the comment says "synchronises";
+ *   - pointers named d_* are device pointers on the context's device, h_* are host pointers;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with TSDRGPU_ENODEVICE.
+ */
+#ifndef TSDRGPU_H_
+#define TSDRGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TSDRGPU_API __attribute__((visibility("default")))
+#else
+#define TSDRGPU_API
+#endif
+
+enum {
+	TSDRGPU_OK        = 0,
+	TSDRGPU_ENODEVICE = -1,   /* no usable CUDA device / wrong architecture */
+	TSDRGPU_ECUDA     = -2,   /* a CUDA runtime call failed (text in tsdrgpu_last_error) */
+	TSDRGPU_EINVAL    = -3,   /* bad argument */
+	TSDRGPU_ENOMEM    = -4,
+	TSDRGPU_ECAPACITY = -5    /* caller's output buffer too small */
+};
+
+typedef struct tsdrgpu_ctx tsdrgpu_ctx_t;
+
+/* ------------------------------------------------------------------------------------------------ context */
+TSDRGPU_API int         tsdrgpu_device_count(void);
+TSDRGPU_API int         tsdrgpu_create(tsdrgpu_ctx_t **ctx, int device);
+TSDRGPU_API void        tsdrgpu_destroy(tsdrgpu_ctx_t *ctx);
+TSDRGPU_API const char *tsdrgpu_last_error(tsdrgpu_ctx_t *ctx);      /* ctx may be NULL (creation errors) */
+TSDRGPU_API int         tsdrgpu_sm_count(tsdrgpu_ctx_t *ctx);
+/* number of kernels this library has launched through ctx since creation (bench.py's gpu_launches) */
+TSDRGPU_API uint64_t    tsdrgpu_launch_count(tsdrgpu_ctx_t *ctx);
+
+/* plumbing for C hosts that do not bring their own allocator (Python callers use torch tensors instead) */
+TSDRGPU_API int tsdrgpu_malloc(tsdrgpu_ctx_t *ctx, size_t bytes, void **d_ptr);
+TSDRGPU_API int tsdrgpu_free(tsdrgpu_ctx_t *ctx, void *d_ptr);
+TSDRGPU_API int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr);   /* pinned */
+TSDRGPU_API int tsdrgpu_free_host(tsdrgpu_ctx_t *ctx, void *h_ptr);
+TSDRGPU_API int tsdrgpu_memcpy_h2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *h_src, size_t bytes);
+TSDRGPU_API int tsdrgpu_memcpy_d2h(tsdrgpu_ctx_t *ctx, void *stream, void *h_dst, const void *d_src, size_t bytes);
+TSDRGPU_API int tsdrgpu_memset(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, int value, size_t bytes);
+TSDRGPU_API int tsdrgpu_stream_create(tsdrgpu_ctx_t *ctx, void **stream);
+TSDRGPU_API int tsdrgpu_stream_destroy(tsdrgpu_ctx_t *ctx, void *stream);
+TSDRGPU_API int tsdrgpu_stream_sync(tsdrgpu_ctx_t *ctx, void *stream);                 /* synchronises */
+
+/* ---------------------------------------------------------------------------- host-only scalar helpers (no GPU needed)
+ * a4: set_internal_samplerate's geometry (TSDRLibrary.c:540-550). */
+TSDRGPU_API void tsdrgpu_geometry(uint32_t samplerate, int height, double refreshrate, int *width, double *pixelrate,
+                                  double *pixeltimeoversampletime);
+/* one decimator block as the device sees it (40 bytes, no padding) */
+typedef struct {
+	uint64_t in_start;    /* first sample of the block in the input stream (sample index, not float index) */
+	uint64_t out_start;   /* first pixel of the block in the output stream */
+	uint32_t size;        /* samples in the block                            (dsp.c:261) */
+	uint32_t n_out;       /* output_samples                                  (dsp.c:262) */
+	double   r;           /* sampletimeoverpixel = upsample_by/downsample_by (dsp.c:258) */
+	double   phase;       /* offset_sample = -offset * r                     (dsp.c:272) */
+} tsdrgpu_rs_block_t;
+/* the per-call phase recurrence of dsp_resample_process (dsp.c:258-262,272,306) for nblocks consecutive calls:
+ * advances *offset, returns the total of the reference's output_samples (UINT64_MAX if a block yields none:
+ * the reference asserts there, extbuffer.c:48).  `blocks` may be NULL (count only). */
+TSDRGPU_API uint64_t tsdrgpu_plan_resample(double *offset, const uint32_t *sizes, uint32_t uniform, uint32_t nblocks,
+                                           double upsample_by, double downsample_by, tsdrgpu_rs_block_t *blocks);
+/* the normalised 5-tap Gaussian of gaussian.c:16-30 */
+TSDRGPU_API void tsdrgpu_gauss_taps(float taps[5]);
+
+/* ---------------------------------------------------------------------------- a2  AM demodulation
+ * replaces am_demod (TSDRLibrary.c:244-262): out[k] = sqrtf(I*I + Q*Q), bit-exact (no FMA, IEEE sqrt). */
+TSDRGPU_API int tsdrgpu_am_demod(tsdrgpu_ctx_t *ctx, void *stream, const float *d_iq, uint64_t pairs, float *d_out);
+
+/* ---------------------------------------------------------------------------- a6  resampler (+ fused a2)
+ * replaces dsp_resample_init / dsp_resample_process / dsp_resample_t (dsp.c:250-307, dsp.h:79-82), optionally
+ * fused with am_demod.  The object carries the reference's {contrib, offset} across calls; `offset` lives on
+ * the host (it depends only on sizes and rates), `contrib` on the device (it depends on the data).
+ *
+ * One run processes `nblocks` CONSECUTIVE decimator blocks (the reference's decimatingthread calls
+ * dsp_resample_process once per 0.1 frame, TSDRLibrary.c:335-340); the per-block phase recurrence
+ * (dsp.c:262,272,306) is replayed on the host in C, the pixels are computed on the GPU, bit-exact.
+ * Deviation: a slot the reference leaves stale because its loop writes one pixel fewer than output_samples
+ * (exact-integer landings, e.g. r == 2.0) is written as 0.0f.
+ */
+typedef struct tsdrgpu_resampler tsdrgpu_resampler_t;
+TSDRGPU_API int  tsdrgpu_resampler_create(tsdrgpu_ctx_t *ctx, tsdrgpu_resampler_t **r);
+TSDRGPU_API void tsdrgpu_resampler_destroy(tsdrgpu_resampler_t *r);
+TSDRGPU_API int  tsdrgpu_resampler_reset(tsdrgpu_resampler_t *r, void *stream);                 /* dsp_resample_init */
+TSDRGPU_API int  tsdrgpu_resampler_get_state(tsdrgpu_resampler_t *r, void *stream, double *contrib, double *offset); /* synchronises */
+TSDRGPU_API int  tsdrgpu_resampler_set_state(tsdrgpu_resampler_t *r, void *stream, double contrib, double offset);
+/* host-only: pixels the next run would produce (sum of the reference's output_samples), state untouched.
+ * block_sizes may be NULL: then every block has `uniform_block` samples. */
+TSDRGPU_API uint64_t tsdrgpu_resampler_plan(tsdrgpu_resampler_t *r, const uint32_t *block_sizes, uint32_t uniform_block,
+                                            uint32_t nblocks, double upsample_by, double downsample_by);
+/* d_in: IQ pairs (in_is_iq != 0, 2 floats per sample) or magnitudes (1 float per sample), blocks back to back.
+ * Writes *h_n_out pixels to d_out (blocks back to back) and advances the state. */
+TSDRGPU_API int  tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream, const float *d_in, int in_is_iq,
+                                       const uint32_t *block_sizes, uint32_t uniform_block, uint32_t nblocks,
+                                       double upsample_by, double downsample_by, int nearest_neighbour,
+                                       float *d_out, uint64_t out_capacity, uint64_t *h_n_out);
+
+/* ---------------------------------------------------------------------------- a7-a15  frame stage
+ * replaces dsp_post_process + dsp_postprocess_t (dsp.c:112-239), dsp_autogain_run (:41-94),
+ * dsp_timelowpass_run (:22-33), dsp_average_v_h (:96-110), syncdetector_run / findthesweetspot / findbestfit /
+ * frameratepll state (syncdetector.c:26-226) and gaussianblur (gaussian.c:18-79), for a BATCH of consecutive
+ * frames.  Pixel outputs and all integer sync results are bit-exact; `snr` (never announced by the reference,
+ * dsp.c:234) is computed with parallel double sums, ~1e-12 relative.
+ * The PLL's write-back to refreshrate (syncdetector.c:141-152) is the HOST's job: the per-frame results carry
+ * vx / avg_speed / state so the caller applies it between batches (geometry is constant inside one batch).
+ */
+typedef struct tsdrgpu_framestage tsdrgpu_framestage_t;
+
+typedef struct {
+	int32_t x_dx, x_vx, x_absvx, x_stripsize;     /* sweetspot_data_t db_x (syncdetector.h:16-22) */
+	int32_t y_dx, y_vx, y_absvx, y_stripsize;     /* db_y */
+	double  avg_speed;                            /* syncdetector_t.avg_speed after this frame */
+	int32_t pll_state;                            /* 1 = locked */
+	float   lastmax, lastmin, snr;                /* dsp_autogain_t after this frame */
+	int32_t autogain_report;                      /* 1 when dsp.c:231-235 would announce min/max */
+	int32_t reserved;
+} tsdrgpu_frame_result_t;
+
+enum {                                            /* flags for tsdrgpu_framestage_run */
+	TSDRGPU_FS_AUTOSHIFT            = 1,          /* PARAM_INT_AUTOSHIFT */
+	TSDRGPU_FS_LOWPASS_BEFORE_SYNC  = 2,          /* PARAM_LOW_PASS_BEFORE_SYNC */
+	TSDRGPU_FS_AUTOGAIN_AFTER_PROC  = 4,          /* PARAM_AUTOGAIN_AFTER_PROCESSING */
+	TSDRGPU_FS_SUPERRESOLUTION      = 8,          /* PARAM_AUTOCORR_SUPERRESOLUTION (suppresses the green lines) */
+	TSDRGPU_FS_COMPUTE_SNR          = 16          /* also fill .snr (costs one more reduction) */
+};
+
+TSDRGPU_API int  tsdrgpu_framestage_create(tsdrgpu_ctx_t *ctx, tsdrgpu_framestage_t **fs);
+TSDRGPU_API void tsdrgpu_framestage_destroy(tsdrgpu_framestage_t *fs);
+TSDRGPU_API int  tsdrgpu_framestage_reset(tsdrgpu_framestage_t *fs, void *stream);          /* dsp_post_process_init */
+/* d_frames_in / d_frames_out: nframes * width * height floats, frames back to back (in != out).
+ * h_results (nframes entries, may be NULL) is filled when the call returns: this call synchronises `stream`
+ * only if h_results != NULL. */
+TSDRGPU_API int  tsdrgpu_framestage_run(tsdrgpu_framestage_t *fs, void *stream, const float *d_frames_in, int nframes,
+                                        int width, int height, float motionblur, float lowpasscoeff, unsigned flags,
+                                        float *d_frames_out, tsdrgpu_frame_result_t *h_results);
+
+/* stage-level entry points (same arithmetic as the kernels inside tsdrgpu_framestage_run) */
+TSDRGPU_API int tsdrgpu_autogain(tsdrgpu_ctx_t *ctx, void *stream, float *h_lastmax, float *h_lastmin, float *h_snr,
+                                 int n, const float *d_in, float *d_out, float norm);        /* synchronises */
+TSDRGPU_API int tsdrgpu_timelowpass(tsdrgpu_ctx_t *ctx, void *stream, float coeff, int n, const float *d_in, float *d_screen);
+TSDRGPU_API int tsdrgpu_average_v_h(tsdrgpu_ctx_t *ctx, void *stream, int width, int height, const float *d_in,
+                                    float *d_wbuf, float *d_hbuf);
+TSDRGPU_API int tsdrgpu_gaussianblur(tsdrgpu_ctx_t *ctx, void *stream, float *d_data, int n);
+
+/* ---------------------------------------------------------------------------- a16 host pixel rule (next-row item)
+ * the JNI glue's float->ARGB mapping (JavaGUI/jni/TSDRLibraryNDK.c:222-283), bit-exact; transparent (2048.0f)
+ * pixels keep the previous content of d_argb. */
+TSDRGPU_API int tsdrgpu_pixels_argb(tsdrgpu_ctx_t *ctx, void *stream, const float *d_frame, int n, int inverted, int32_t *d_argb);
+
+/* ---------------------------------------------------------------------------- a19/a20  FFT and correlations
+ * replace fft_perform, fft_autocorrelation, fft_crosscorrelation (fft.c:49-176).  Same definitions as the
+ * reference (forward divides by N, inverse does not; N = largest power of two <= size; "autocorrelation" is
+ * IFFT(|FFT(x)|/N)), computed by a float32 Stockham FFT with double-derived twiddles: results agree with the
+ * reference's float-storage/double-arithmetic radix-2 code to ~1e-6 of the spectrum's peak (tolerance-based).
+ */
+TSDRGPU_API uint32_t tsdrgpu_fft_getrealsize(uint32_t size);                                   /* fft.c:5-11 */
+TSDRGPU_API int tsdrgpu_fft(tsdrgpu_ctx_t *ctx, void *stream, float *d_iq, uint32_t size, int inverse);   /* in place */
+TSDRGPU_API int tsdrgpu_autocorrelation(tsdrgpu_ctx_t *ctx, void *stream, float *d_answer, const float *d_real, uint32_t size);
+TSDRGPU_API int tsdrgpu_crosscorrelation(tsdrgpu_ctx_t *ctx, void *stream, float *d_a_out, float *d_b_tmp, uint32_t samples);
+
+/* ---------------------------------------------------------------------------- a17/a18  frame-rate detector
+ * replaces frameratedetector_runontodata / accummulate (frameratedetector.c:34-126) and the two extbuffer
+ * running means: one capture in, the two lag-window plots out. */
+typedef struct tsdrgpu_frd tsdrgpu_frd_t;
+TSDRGPU_API int  tsdrgpu_frd_create(tsdrgpu_ctx_t *ctx, tsdrgpu_frd_t **frd);
+TSDRGPU_API void tsdrgpu_frd_destroy(tsdrgpu_frd_t *frd);
+TSDRGPU_API int  tsdrgpu_frd_reset(tsdrgpu_frd_t *frd);                      /* extbuffer_cleartozero on all three */
+TSDRGPU_API uint32_t tsdrgpu_frd_capture_size(uint32_t samplerate);          /* frameratedetector.c:160 */
+TSDRGPU_API void tsdrgpu_frd_windows(uint32_t samplerate, int *frame_min, int *frame_max, int *line_min, int *line_max);
+/* d_capture: `size` demodulated samples.  The running means stay on the device; pass h_* (may be NULL) to copy
+ * them out (then the call synchronises).  *calls = captures accumulated so far. */
+TSDRGPU_API int  tsdrgpu_frd_run(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
+                                 double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls);
+TSDRGPU_API int  tsdrgpu_accumulate(tsdrgpu_ctx_t *ctx, void *stream, double *d_out, uint64_t calls,
+                                    const float *d_in_complex, int startid, int length);
+
+/* ---------------------------------------------------------------------------- a22  superbandwidth
+ * replace complex_to_abs_diff, superb_bestfit, superb_ondataready (superbandwidth.c:67-152). */
+TSDRGPU_API int tsdrgpu_complex_to_abs_diff(tsdrgpu_ctx_t *ctx, void *stream, float *d_data, int size_floats);
+/* alignment lag in floats (2 * argmax over the first half of |xcorr|), exact integer.  synchronises */
+TSDRGPU_API int tsdrgpu_superb_bestfit(tsdrgpu_ctx_t *ctx, void *stream, const float *d_hop0, const float *d_hopi,
+                                       int size_floats, int samples_in_frame, int *h_best_offset);
+/* single-GPU stitch of nhops hops (each count_pairs IQ pairs, d_hops[i] device pointers in a HOST array);
+ * d_out holds nhops * N * 2 floats, N = fft_getrealsize(count_pairs).  synchronises (lags are read back). */
+TSDRGPU_API int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream, float *const *d_hops, int nhops, int count_pairs,
+                                      int samples_in_frame, float *d_out, int *h_best_offsets, int *h_total_samples);
+/* multi-GPU building blocks (one hop per rank; the all-gather between them is the caller's NCCL call):
+ *   rotate hop by best_offset floats and forward-FFT it into d_spectrum (N complex);
+ *   then, given the gathered [X0..X_{H-1}] (H*N complex), produce this rank's share of the H*N-point inverse:
+ *   the strided residue s of the output (y[H*p + s], p < N) -- see DESIGN.md "superbandwidth decomposition". */
+TSDRGPU_API int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream, const float *d_hop, int count_pairs,
+                                            int best_offset_floats, float *d_spectrum);
+TSDRGPU_API int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream, const float *d_gathered, int nhops, uint32_t n,
+                                            int residue, float *d_out_residue);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,116 @@
+"""ctypes loader of tempestsdr_b200/lib/libtsdrgpu.so (the C-ABI of include/tsdrgpu.h).
+
+There is no fallback of any kind: a missing library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtsdrgpu.so")
+
+OK = 0
+
+
+class FrameResult(C.Structure):
+    """tsdrgpu_frame_result_t"""
+    _fields_ = [("x_dx", C.c_int32), ("x_vx", C.c_int32), ("x_absvx", C.c_int32), ("x_stripsize", C.c_int32),
+                ("y_dx", C.c_int32), ("y_vx", C.c_int32), ("y_absvx", C.c_int32), ("y_stripsize", C.c_int32),
+                ("avg_speed", C.c_double), ("pll_state", C.c_int32),
+                ("lastmax", C.c_float), ("lastmin", C.c_float), ("snr", C.c_float),
+                ("autogain_report", C.c_int32), ("reserved", C.c_int32)]
+
+
+FS_AUTOSHIFT, FS_LOWPASS_BEFORE_SYNC, FS_AUTOGAIN_AFTER_PROC, FS_SUPERRESOLUTION, FS_COMPUTE_SNR = 1, 2, 4, 8, 16
+
+_SIGS = {
+    "tsdrgpu_device_count": (C.c_int, []),
+    "tsdrgpu_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "tsdrgpu_destroy": (None, [C.c_void_p]),
+    "tsdrgpu_last_error": (C.c_char_p, [C.c_void_p]),
+    "tsdrgpu_sm_count": (C.c_int, [C.c_void_p]),
+    "tsdrgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "tsdrgpu_malloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_malloc_host": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_free_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tsdrgpu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tsdrgpu_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "tsdrgpu_stream_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_stream_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_stream_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_geometry": (None, [C.c_uint32, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tsdrgpu_plan_resample": (C.c_uint64, [C.POINTER(C.c_double), C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_void_p]),
+    "tsdrgpu_gauss_taps": (None, [C.POINTER(C.c_float * 5)]),
+    "tsdrgpu_am_demod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tsdrgpu_resampler_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_resampler_destroy": (None, [C.c_void_p]),
+    "tsdrgpu_resampler_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_resampler_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tsdrgpu_resampler_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "tsdrgpu_resampler_plan": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_double]),
+    "tsdrgpu_resampler_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32,
+                                        C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_framestage_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_framestage_destroy": (None, [C.c_void_p]),
+    "tsdrgpu_framestage_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_framestage_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                         C.c_uint, C.c_void_p, C.POINTER(FrameResult)]),
+    "tsdrgpu_autogain": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_float]),
+    "tsdrgpu_timelowpass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "tsdrgpu_average_v_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tsdrgpu_gaussianblur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "tsdrgpu_pixels_argb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tsdrgpu_fft_getrealsize": (C.c_uint32, [C.c_uint32]),
+    "tsdrgpu_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
+    "tsdrgpu_autocorrelation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "tsdrgpu_crosscorrelation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "tsdrgpu_frd_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_frd_destroy": (None, [C.c_void_p]),
+    "tsdrgpu_frd_reset": (C.c_int, [C.c_void_p]),
+    "tsdrgpu_frd_capture_size": (C.c_uint32, [C.c_uint32]),
+    "tsdrgpu_frd_windows": (None, [C.c_uint32] + [C.POINTER(C.c_int)] * 4),
+    "tsdrgpu_frd_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]),
+    "tsdrgpu_complex_to_abs_diff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "tsdrgpu_superb_bestfit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "tsdrgpu_superb_stitch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tsdrgpu_superb_hop_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tsdrgpu_superb_residue_ifft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
+}
+
+#: every symbol include/tsdrgpu.h declares (tests check the built library exports all of them)
+DECLARED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded libtsdrgpu.so.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C tempestsdr_b200/csrc` "
+                               "(or __graft_entry__.build()).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class TsdrGpuError(RuntimeError):
+    pass
+
+
+def check(rc: int, ctx=None) -> None:
+    if rc != OK:
+        msg = lib().tsdrgpu_last_error(ctx)
+        raise TsdrGpuError(f"libtsdrgpu error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,71 @@
+// common.cuh -- shared plumbing of libtsdrgpu (context, error handling, exact-arithmetic helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+
+#include "../../include/tsdrgpu.h"
+
+struct tsdrgpu_ctx {
+	int device;
+	int sm_count;
+	char err[512];
+	uint64_t launches;
+	// scratch owned by the context (grown on demand, reused across calls on the same stream)
+	void *scratch[4];
+	size_t scratch_bytes[4];
+	void *pinned;            // small pinned staging area for descriptor uploads / scalar read-backs
+	size_t pinned_bytes;
+	std::mutex mu;
+};
+
+extern thread_local char g_tsdrgpu_err[512];
+
+static inline int tsdrgpu_fail(tsdrgpu_ctx_t *ctx, int code, const char *what, cudaError_t e, const char *file, int line) {
+	char *dst = ctx ? ctx->err : g_tsdrgpu_err;
+	if (e != cudaSuccess) snprintf(dst, 512, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+	else snprintf(dst, 512, "%s (%s:%d)", what, file, line);
+	return code;
+}
+
+#define CU_TRY(ctx, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+	return tsdrgpu_fail((ctx), TSDRGPU_ECUDA, #expr, e_, __FILE__, __LINE__); } while (0)
+#define ARG_TRY(ctx, cond) do { if (!(cond)) \
+	return tsdrgpu_fail((ctx), TSDRGPU_EINVAL, "invalid argument: " #cond, cudaSuccess, __FILE__, __LINE__); } while (0)
+#define LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+	return tsdrgpu_fail((ctx), TSDRGPU_ECUDA, "kernel launch", e_, __FILE__, __LINE__); } while (0)
+
+static inline int tsdrgpu_bind(tsdrgpu_ctx_t *ctx) {
+	if (!ctx) return tsdrgpu_fail(NULL, TSDRGPU_EINVAL, "null context", cudaSuccess, __FILE__, __LINE__);
+	CU_TRY(ctx, cudaSetDevice(ctx->device));
+	return TSDRGPU_OK;
+}
+#define BIND(ctx) do { int rc_ = tsdrgpu_bind(ctx); if (rc_ != TSDRGPU_OK) return rc_; } while (0)
+
+// grow-only scratch slot
+int tsdrgpu_scratch(tsdrgpu_ctx_t *ctx, int slot, size_t bytes, void **out);
+int tsdrgpu_pinned(tsdrgpu_ctx_t *ctx, size_t bytes, void **out);
+
+// ---- exact single-precision magnitude: fl(sqrt(fl(fl(I*I) + fl(Q*Q)))), no contraction (TSDRLibrary.c:260)
+__device__ __forceinline__ float mag_exact(float i, float q) {
+	return __fsqrt_rn(__fadd_rn(__fmul_rn(i, i), __fmul_rn(q, q)));
+}
+
+__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p) {
+	float2 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
+	float4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+	             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *p) {
+	float v;
+	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+	return v;
+}

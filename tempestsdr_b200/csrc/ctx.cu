@@ -1,0 +1,116 @@
+// ctx.cu -- context, memory and stream plumbing of libtsdrgpu (include/tsdrgpu.h, "context" section).
+#include "common.cuh"
+
+thread_local char g_tsdrgpu_err[512] = "";
+
+extern "C" {
+
+int tsdrgpu_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int tsdrgpu_create(tsdrgpu_ctx_t **out, int device) {
+	if (!out) return tsdrgpu_fail(NULL, TSDRGPU_EINVAL, "null out pointer", cudaSuccess, __FILE__, __LINE__);
+	*out = NULL;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return tsdrgpu_fail(NULL, TSDRGPU_ENODEVICE, "no CUDA device visible (this library has no CPU fallback)", e, __FILE__, __LINE__);
+	}
+	if (device < 0 || device >= n) return tsdrgpu_fail(NULL, TSDRGPU_EINVAL, "device index out of range", cudaSuccess, __FILE__, __LINE__);
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess) return tsdrgpu_fail(NULL, TSDRGPU_ECUDA, "cudaGetDeviceProperties", e, __FILE__, __LINE__);
+	if (prop.major != 10) {
+		char msg[160];
+		snprintf(msg, sizeof msg, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+		return tsdrgpu_fail(NULL, TSDRGPU_ENODEVICE, msg, cudaSuccess, __FILE__, __LINE__);
+	}
+	tsdrgpu_ctx_t *c = new tsdrgpu_ctx();
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	c->err[0] = 0;
+	c->launches = 0;
+	for (int i = 0; i < 4; i++) { c->scratch[i] = NULL; c->scratch_bytes[i] = 0; }
+	c->pinned = NULL; c->pinned_bytes = 0;
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) { delete c; return tsdrgpu_fail(NULL, TSDRGPU_ECUDA, "cudaSetDevice", e, __FILE__, __LINE__); }
+	*out = c;
+	return TSDRGPU_OK;
+}
+
+void tsdrgpu_destroy(tsdrgpu_ctx_t *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	for (int i = 0; i < 4; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+	if (ctx->pinned) cudaFreeHost(ctx->pinned);
+	delete ctx;
+}
+
+const char *tsdrgpu_last_error(tsdrgpu_ctx_t *ctx) { return ctx ? ctx->err : g_tsdrgpu_err; }
+int tsdrgpu_sm_count(tsdrgpu_ctx_t *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t tsdrgpu_launch_count(tsdrgpu_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+int tsdrgpu_malloc(tsdrgpu_ctx_t *ctx, size_t bytes, void **d_ptr) {
+	BIND(ctx); ARG_TRY(ctx, d_ptr != NULL);
+	CU_TRY(ctx, cudaMalloc(d_ptr, bytes ? bytes : 1));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_free(tsdrgpu_ctx_t *ctx, void *d_ptr) { BIND(ctx); CU_TRY(ctx, cudaFree(d_ptr)); return TSDRGPU_OK; }
+int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr) {
+	BIND(ctx); ARG_TRY(ctx, h_ptr != NULL);
+	CU_TRY(ctx, cudaMallocHost(h_ptr, bytes ? bytes : 1));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_free_host(tsdrgpu_ctx_t *ctx, void *h_ptr) { BIND(ctx); CU_TRY(ctx, cudaFreeHost(h_ptr)); return TSDRGPU_OK; }
+int tsdrgpu_memcpy_h2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *h_src, size_t bytes) {
+	BIND(ctx);
+	CU_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_memcpy_d2h(tsdrgpu_ctx_t *ctx, void *stream, void *h_dst, const void *d_src, size_t bytes) {
+	BIND(ctx);
+	CU_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_memset(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, int value, size_t bytes) {
+	BIND(ctx);
+	CU_TRY(ctx, cudaMemsetAsync(d_dst, value, bytes, (cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_stream_create(tsdrgpu_ctx_t *ctx, void **stream) {
+	BIND(ctx); ARG_TRY(ctx, stream != NULL);
+	cudaStream_t s;
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	*stream = (void *) s;
+	return TSDRGPU_OK;
+}
+int tsdrgpu_stream_destroy(tsdrgpu_ctx_t *ctx, void *stream) { BIND(ctx); CU_TRY(ctx, cudaStreamDestroy((cudaStream_t) stream)); return TSDRGPU_OK; }
+int tsdrgpu_stream_sync(tsdrgpu_ctx_t *ctx, void *stream) { BIND(ctx); CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t) stream)); return TSDRGPU_OK; }
+
+}  // extern "C"
+
+int tsdrgpu_scratch(tsdrgpu_ctx_t *ctx, int slot, size_t bytes, void **out) {
+	if (ctx->scratch_bytes[slot] < bytes) {
+		if (ctx->scratch[slot]) { CU_TRY(ctx, cudaDeviceSynchronize()); CU_TRY(ctx, cudaFree(ctx->scratch[slot])); ctx->scratch[slot] = NULL; ctx->scratch_bytes[slot] = 0; }
+		size_t want = bytes + (bytes >> 2) + 256;
+		CU_TRY(ctx, cudaMalloc(&ctx->scratch[slot], want));
+		ctx->scratch_bytes[slot] = want;
+	}
+	*out = ctx->scratch[slot];
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_pinned(tsdrgpu_ctx_t *ctx, size_t bytes, void **out) {
+	if (ctx->pinned_bytes < bytes) {
+		if (ctx->pinned) { CU_TRY(ctx, cudaDeviceSynchronize()); CU_TRY(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = NULL; ctx->pinned_bytes = 0; }
+		size_t want = bytes * 2 + 4096;
+		CU_TRY(ctx, cudaMallocHost(&ctx->pinned, want));
+		ctx->pinned_bytes = want;
+	}
+	*out = ctx->pinned;
+	return TSDRGPU_OK;
+}

@@ -1,0 +1,581 @@
+// fft.cu -- a18..a20, a22: FFT, "autocorrelation", cross-correlation, the frame-rate detector's running means and
+// the superbandwidth stitch.
+//
+// Replaces fft_perform / fft_autocorrelation / fft_crosscorrelation (fft.c:49-176), accummulate and
+// frameratedetector_runontodata (frameratedetector.c:34-126), complex_to_abs_diff / superb_bestfit /
+// superb_ondataready (superbandwidth.c:67-152).
+//
+// FFT design (no tensor cores: nothing here is a dense contraction; the bound is HBM / L2 bandwidth):
+//   N = 2^m is factored into 1, 2 or 3 line lengths L_i <= 2048 (Cooley-Tukey index maps).  One CTA transforms a
+//   BUNDLE of C adjacent lines entirely in shared memory (in-place radix-4/2 Stockham stages, natural order in and
+//   out), multiplies by the inter-pass twiddle and writes the bundle back.  Bundling makes every global access a
+//   run of >= C consecutive complex values (>= 64..128 B) even on the strided passes, so each pass is one
+//   coalesced read + one coalesced write of the array: 16 N bytes per pass, 2 passes up to N = 2^22, 3 above.
+//   The transposing last pass writes to the other buffer (scratch <-> data), so no extra copy pass exists.
+//   Real->complex widening and |X|/N are fused into the first / last pass of the forward transform of the
+//   autocorrelation.
+// Numerics: float32 data, twiddles from a double-computed table (intra-line) and sincospif of an exactly reduced
+// argument (inter-pass).  The reference keeps float32 storage between its radix-2 stages too (fft.c:150-155), so
+// both carry ~1e-7*sqrt(log2 N) relative noise; results agree to ~1e-6 of the spectrum's peak (not bit-exact).
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+
+namespace {
+
+constexpr int FFT_MAX_LOG2L = 11;            // longest line transformed inside one CTA: 2048
+constexpr int FFT_TABLE = 1 << FFT_MAX_LOG2L;
+constexpr int FFT_MAX_ELEMS = 16384;         // complex elements per CTA bundle (128 KB of shared memory)
+
+struct FftPass {
+	int log2L, C, c_fast_in, c_fast_out;
+	unsigned G_lo;
+	long long in_hi, in_lo, in_cs, in_js;
+	long long out_hi, out_lo, out_cs, out_ks;
+	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
+	float scale;
+	int in_real, out_abs;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// W^{q}_{2048} (forward sign); inverse conjugates
+__device__ __forceinline__ float2 tw_lookup(const float2 *__restrict__ table, unsigned q, bool inverse) {
+	float2 w = __ldg(table + (q & (FFT_TABLE - 1)));
+	if (inverse) w.y = -w.y;
+	return w;
+}
+
+__global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
+                                                        const float2 *__restrict__ table, int inverse) {
+	extern __shared__ float2 s[];
+	const int L = 1 << P.log2L, C = P.C, LP = L + 1, total = C * L;
+	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g % P.G_lo;
+	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo;
+	const long long out_base = (long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo;
+
+	// ---- load the bundle
+	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+		int c, j;
+		if (P.c_fast_in) { c = idx % C; j = idx / C; } else { j = idx & (L - 1); c = idx >> P.log2L; }
+		const long long src = in_base + (long long) c * P.in_cs + (long long) j * P.in_js;
+		float2 v;
+		if (P.in_real) v = make_float2(reinterpret_cast<const float *>(in)[src], 0.0f); else v = in[src];
+		s[c * LP + j] = v;
+	}
+	__syncthreads();
+
+	// ---- Stockham stages, in place: every thread reads its butterflies, barrier, writes, barrier.
+	// A CTA holds at most FFT_MAX_ELEMS points and has >= elems/16 threads (launch_pass), so a thread owns at
+	// most 4 radix-4 or 8 radix-2 butterflies: 16 complex registers either way.
+	int p = 1, stage_log = 0;
+	float2 r[16];
+	while (stage_log < P.log2L) {
+		const bool radix4 = ((P.log2L - stage_log) & 1) == 0;       // one radix-2 stage first when log2 L is odd
+		if (radix4) {
+			const int per_line = L >> 2, work = C * per_line;
+			#pragma unroll
+			for (int it = 0; it < 4; it++) {
+				const int widx = threadIdx.x + it * blockDim.x;
+				if (widx < work) {
+					const int c = widx / per_line, i = widx - c * per_line;
+					const int k = i & (p - 1);
+					const float2 *line = s + c * LP;
+					const unsigned tq = (unsigned) k * (unsigned) (FFT_TABLE / (4 * p));
+					float2 u0 = line[i], u1 = line[i + per_line], u2 = line[i + 2 * per_line], u3 = line[i + 3 * per_line];
+					if (k) { u1 = cmul(u1, tw_lookup(table, tq, inverse)); u2 = cmul(u2, tw_lookup(table, 2 * tq, inverse)); u3 = cmul(u3, tw_lookup(table, 3 * tq, inverse)); }
+					const float2 a0 = make_float2(u0.x + u2.x, u0.y + u2.y), a1 = make_float2(u0.x - u2.x, u0.y - u2.y);
+					const float2 a2 = make_float2(u1.x + u3.x, u1.y + u3.y);
+					float2 a3 = make_float2(u1.x - u3.x, u1.y - u3.y);
+					a3 = inverse ? make_float2(-a3.y, a3.x) : make_float2(a3.y, -a3.x);     // * (+i) inverse, * (-i) forward
+					r[it * 4 + 0] = make_float2(a0.x + a2.x, a0.y + a2.y); r[it * 4 + 1] = make_float2(a1.x + a3.x, a1.y + a3.y);
+					r[it * 4 + 2] = make_float2(a0.x - a2.x, a0.y - a2.y); r[it * 4 + 3] = make_float2(a1.x - a3.x, a1.y - a3.y);
+				}
+			}
+			__syncthreads();
+			#pragma unroll
+			for (int it = 0; it < 4; it++) {
+				const int widx = threadIdx.x + it * blockDim.x;
+				if (widx < work) {
+					const int c = widx / per_line, i = widx - c * per_line;
+					const int k = i & (p - 1);
+					const int j = ((i - k) << 2) + k;
+					float2 *line = s + c * LP;
+					line[j] = r[it * 4 + 0]; line[j + p] = r[it * 4 + 1]; line[j + 2 * p] = r[it * 4 + 2]; line[j + 3 * p] = r[it * 4 + 3];
+				}
+			}
+			__syncthreads();
+			p <<= 2; stage_log += 2;
+		} else {
+			const int per_line = L >> 1, work = C * per_line;
+			#pragma unroll
+			for (int it = 0; it < 8; it++) {
+				const int widx = threadIdx.x + it * blockDim.x;
+				if (widx < work) {
+					const int c = widx / per_line, i = widx - c * per_line;
+					const int k = i & (p - 1);
+					const float2 *line = s + c * LP;
+					const float2 u0 = line[i];
+					float2 u1 = line[i + per_line];
+					if (k) u1 = cmul(u1, tw_lookup(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), inverse));
+					r[it * 2 + 0] = make_float2(u0.x + u1.x, u0.y + u1.y); r[it * 2 + 1] = make_float2(u0.x - u1.x, u0.y - u1.y);
+				}
+			}
+			__syncthreads();
+			#pragma unroll
+			for (int it = 0; it < 8; it++) {
+				const int widx = threadIdx.x + it * blockDim.x;
+				if (widx < work) {
+					const int c = widx / per_line, i = widx - c * per_line;
+					const int k = i & (p - 1);
+					const int j = ((i - k) << 1) + k;
+					float2 *line = s + c * LP;
+					line[j] = r[it * 2 + 0]; line[j + p] = r[it * 2 + 1];
+				}
+			}
+			__syncthreads();
+			p <<= 1; stage_log += 1;
+		}
+	}
+
+	// ---- inter-pass twiddle, scaling, optional |.|, store
+	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+		int c, k;
+		if (P.c_fast_out) { c = idx % C; k = idx / C; } else { k = idx & (L - 1); c = idx >> P.log2L; }
+		float2 v = s[c * LP + k];
+		if (P.tw_M) {
+			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
+			const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
+			float sn, cs;
+			if (P.tw_M <= (1ull << 24)) sincospif(2.0f * ((float) e / (float) P.tw_M), &sn, &cs);      // exact argument
+			else { double dsn, dcs; sincospi(2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); sn = (float) dsn; cs = (float) dcs; }
+			v = cmul(v, make_float2(cs, inverse ? sn : -sn));
+		}
+		v.x *= P.scale; v.y *= P.scale;
+		if (P.out_abs) v = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))), 0.0f);
+		out[out_base + (long long) c * P.out_cs + (long long) k * P.out_ks] = v;
+	}
+}
+
+__global__ void fft_table_kernel(float2 *table) {
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < FFT_TABLE) {
+		double sn, cs;
+		sincospi(-2.0 * (double) q / (double) FFT_TABLE, &sn, &cs);
+		table[q] = make_float2((float) cs, (float) sn);
+	}
+}
+
+// ---- small elementwise helpers -----------------------------------------------------------------------------
+__global__ void k_scale(float2 *d, unsigned long long n, float scale) {
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+		float2 v = d[i]; v.x *= scale; v.y *= scale; d[i] = v;
+	}
+}
+// answer[2i] = real[i], answer[2i+1] = 0 for i in [from, to)          (fft.c:14-22)
+__global__ void k_real_to_complex(float2 *answer, const float *real, unsigned long long from, unsigned long long to) {
+	for (unsigned long long i = from + (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (unsigned long long) gridDim.x * blockDim.x)
+		answer[i] = make_float2(real[i], 0.0f);
+}
+// answer[i] = (|answer[i]|, 0)                                          (fft.c:34-45)
+__global__ void k_abs(float2 *answer, unsigned long long from, unsigned long long to) {
+	for (unsigned long long i = from + (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < to; i += (unsigned long long) gridDim.x * blockDim.x) {
+		const float2 v = answer[i];
+		answer[i] = make_float2(mag_exact(v.x, v.y), 0.0f);
+	}
+}
+// a = (aI*bI + aQ*bQ, aI*bQ - aQ*bI)                                   (fft.c:80-89)
+__global__ void k_conj_mul(float2 *a, const float2 *b, unsigned long long n) {
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+		const float2 x = a[i], y = b[i];
+		a[i] = make_float2(__fadd_rn(__fmul_rn(x.x, y.x), __fmul_rn(x.y, y.y)), __fsub_rn(__fmul_rn(x.x, y.y), __fmul_rn(x.y, y.x)));
+	}
+}
+// running mean of lag magnitudes in double                             (frameratedetector.c:34-62)
+__global__ void k_accumulate(double *out, unsigned long long calls, const float2 *in, int startid, int length) {
+	const double now_n = (double) calls, before_n = (double) (calls - 1);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < length; i += gridDim.x * blockDim.x) {
+		const float2 v = in[(size_t) startid + i];
+		const double re = (double) v.x, im = (double) v.y;
+		const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+		out[i] = (calls == 0) ? mag : __ddiv_rn(__dadd_rn(__dmul_rn(out[i], before_n), mag), now_n);
+	}
+}
+// first difference of magnitudes, out of place                          (superbandwidth.c:67-81)
+__global__ void k_abs_diff(const float2 *src, float2 *dst, unsigned long long pairs) {
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (unsigned long long) gridDim.x * blockDim.x) {
+		const float2 v = src[i];
+		const float cur = mag_exact(v.x, v.y);
+		float prev;
+		if (i == 0) prev = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));    // seed without the square root
+		else { const float2 u = src[i - 1]; prev = mag_exact(u.x, u.y); }
+		dst[i] = make_float2(__fsub_rn(cur, prev), 0.0f);
+	}
+}
+// rotate left by `shift` complex elements
+__global__ void k_rotate(const float2 *src, float2 *dst, unsigned long long n, unsigned long long shift) {
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+		unsigned long long s = i + shift; if (s >= n) s -= n;
+		dst[i] = src[s];
+	}
+}
+// argmax of |x| over [0, n): first maximum wins                         (superbandwidth.c:100-116)
+__global__ void __launch_bounds__(1024) k_argmax_mag(const float2 *x, unsigned n, int *result) {
+	__shared__ float s_v[32]; __shared__ unsigned s_i[32];
+	float best = -1.0f; unsigned bi = 0xffffffffu;
+	for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+		const float2 v = x[i];
+		const float m = mag_exact(v.x, v.y);
+		if (m > best) { best = m; bi = i; }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		const float ov = __shfl_xor_sync(0xffffffffu, best, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
+		if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+	}
+	if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < (int) (blockDim.x >> 5); w++) if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) { best = s_v[w]; bi = s_i[w]; }
+		// the reference starts from element 0 and only moves on a strict '>' (NaN never wins)
+		*result = (bi == 0xffffffffu) ? 0 : (int) bi;
+	}
+}
+// U_s[m] = e^{+2 pi i m s/(H N)} * sum_q e^{+2 pi i q s / H} X_q[m]     (superbandwidth decomposition)
+__global__ void k_residue_mix(const float2 *gathered, int H, unsigned n, int s, float2 *dst) {
+	for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+		double accr = 0.0, acci = 0.0;
+		for (int q = 0; q < H; q++) {
+			double sn, cs;
+			sincospi(2.0 * (double) ((q * s) % H) / (double) H, &sn, &cs);
+			const float2 v = gathered[(size_t) q * n + m];
+			accr += cs * v.x - sn * v.y; acci += cs * v.y + sn * v.x;
+		}
+		double sn, cs;
+		sincospi(2.0 * ((double) m * (double) s) / ((double) H * (double) n), &sn, &cs);
+		dst[m] = make_float2((float) (accr * cs - acci * sn), (float) (accr * sn + acci * cs));
+	}
+}
+
+inline unsigned grid1d(unsigned long long n, int sm_count) {
+	const unsigned long long want = (n + 255) / 256, cap = (unsigned long long) sm_count * 8;
+	return (unsigned) (want < cap ? (want ? want : 1) : cap);
+}
+
+float2 *g_table[64] = {0};          // per device
+
+int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
+	if (g_table[ctx->device]) return TSDRGPU_OK;
+	float2 *t;
+	CU_TRY(ctx, cudaMalloc(&t, sizeof(float2) * FFT_TABLE));
+	fft_table_kernel<<<FFT_TABLE / 256, 256, 0, stream>>>(t);
+	LAUNCH_CHECK(ctx);
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	g_table[ctx->device] = t;
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(float2) * (FFT_MAX_ELEMS + 64))));
+	return TSDRGPU_OK;
+}
+
+int bundle_for(int log2L, unsigned long long lines) {
+	const int L = 1 << log2L;
+	int C = 4096 / L; if (C < 8) C = 8;
+	while ((long long) C * L > FFT_MAX_ELEMS) C >>= 1;
+	while ((unsigned long long) C > lines) C >>= 1;
+	return C < 1 ? 1 : C;
+}
+
+int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, const FftPass &P, unsigned bundles, int inverse) {
+	const int L = 1 << P.log2L, total = P.C * L;
+	int threads = (total / 16 + 31) / 32 * 32;           // <= 4 radix-4 (8 radix-2) butterflies per thread
+	if (threads < 64) threads = 64;
+	if (total / 4 >= 256 && threads < 256) threads = 256;
+	if (threads > 1024) threads = 1024;
+	const size_t smem = sizeof(float2) * (size_t) P.C * (L + 1);
+	fft_pass_kernel<<<bundles, threads, smem, stream>>>(in, out, P, g_table[ctx->device], inverse);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+struct FftOpts { const float *real_in; bool out_abs; float scale; };
+
+// N-point transform of `data` (complex, natural order) through `scratch`; result lands in `data`.
+// With opts.real_in the input is read from a real array instead (data is output only).
+int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scratch, unsigned log2N, int inverse, FftOpts o) {
+	const unsigned long long N = 1ull << log2N;
+	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : data;
+	FftPass P; memset(&P, 0, sizeof P);
+	if (log2N <= FFT_MAX_LOG2L) {                       // one pass, one CTA
+		P.log2L = (int) log2N; P.C = 1; P.G_lo = 1; P.in_js = 1; P.out_ks = 1; P.scale = o.scale;
+		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs;
+		return launch_pass(ctx, stream, src0, data, P, 1, inverse);
+	}
+	int rc;
+	if (log2N <= 2 * FFT_MAX_LOG2L) {                   // N = N1 * N2 ; n = N2*n1 + n2 ; k = k1 + N1*k2
+		const unsigned l1 = (log2N + 1) / 2, l2 = log2N - l1;
+		const unsigned long long N1 = 1ull << l1, N2 = 1ull << l2;
+		P.log2L = (int) l1; P.C = bundle_for((int) l1, N2); P.c_fast_in = P.c_fast_out = 1;
+		P.G_lo = (unsigned) (N2 / P.C);
+		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N2;
+		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N2;
+		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
+		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse))) return rc;
+		FftPass Q; memset(&Q, 0, sizeof Q);
+		Q.log2L = (int) l2; Q.C = bundle_for((int) l2, N1); Q.c_fast_in = 0; Q.c_fast_out = 1;
+		Q.G_lo = (unsigned) (N1 / Q.C);
+		Q.in_lo = (long long) Q.C * (long long) N2; Q.in_cs = (long long) N2; Q.in_js = 1;
+		Q.out_lo = Q.C; Q.out_cs = 1; Q.out_ks = (long long) N1;
+		Q.scale = o.scale; Q.out_abs = o.out_abs;
+		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse);
+	}
+	// N = N1*N2*N3 ; n = N2N3 n1 + N3 n2 + n3 ; k = k1 + N1 k2 + N1N2 k3
+	const unsigned l1 = (log2N + 2) / 3, l2 = (log2N - l1 + 1) / 2, l3 = log2N - l1 - l2;
+	if (l1 > (unsigned) FFT_MAX_LOG2L) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT too long", cudaSuccess, __FILE__, __LINE__);
+	const unsigned long long N1 = 1ull << l1, N2 = 1ull << l2, N3 = 1ull << l3, N23 = N2 * N3;
+	{   // pass A: length N1 along stride N2N3, bundle over adjacent columns m
+		P.log2L = (int) l1; P.C = bundle_for((int) l1, N23); P.c_fast_in = P.c_fast_out = 1;
+		P.G_lo = (unsigned) (N23 / P.C);
+		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N23;
+		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N23;
+		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
+		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse))) return rc;
+	}
+	{   // pass B: for every k1, length N2 along stride N3, bundle over adjacent n3 (in place in scratch)
+		FftPass B; memset(&B, 0, sizeof B);
+		B.log2L = (int) l2; B.C = bundle_for((int) l2, N3); B.c_fast_in = B.c_fast_out = 1;
+		B.G_lo = (unsigned) (N3 / B.C);
+		B.in_hi = (long long) N23; B.in_lo = B.C; B.in_cs = 1; B.in_js = (long long) N3;
+		B.out_hi = (long long) N23; B.out_lo = B.C; B.out_cs = 1; B.out_ks = (long long) N3;
+		B.tw_M = N23; B.tw_lo = B.C; B.tw_cs = 1; B.scale = 1.0f;
+		if ((rc = launch_pass(ctx, stream, scratch, scratch, B, (unsigned) (N1 * B.G_lo), inverse))) return rc;
+	}
+	{   // pass C: contiguous lines of N3 at (k1,k2); bundle over adjacent k1; output k1 + N1 k2 + N1N2 k3
+		FftPass Cc; memset(&Cc, 0, sizeof Cc);
+		Cc.log2L = (int) l3; Cc.C = bundle_for((int) l3, N1); Cc.c_fast_in = 0; Cc.c_fast_out = 1;
+		Cc.G_lo = (unsigned) (N1 / Cc.C);                // g = k2 * G_lo + (k1 / C)
+		Cc.in_hi = (long long) N3; Cc.in_lo = (long long) Cc.C * (long long) N23; Cc.in_cs = (long long) N23; Cc.in_js = 1;
+		Cc.out_hi = (long long) N1; Cc.out_lo = Cc.C; Cc.out_cs = 1; Cc.out_ks = (long long) (N1 * N2);
+		Cc.scale = o.scale; Cc.out_abs = o.out_abs;
+		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse);
+	}
+}
+
+unsigned ilog2(unsigned long long n) { unsigned m = 0; while ((n >>= 1) != 0) m++; return m; }
+
+}  // namespace
+
+// internal entry used by other translation units
+int tsdrgpu_fft_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, unsigned long long n_pow2, int inverse) {
+	int rc = ensure_table(ctx, stream);
+	if (rc) return rc;
+	if (n_pow2 <= 1) return TSDRGPU_OK;
+	void *scratch;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * n_pow2, &scratch))) return rc;
+	FftOpts o; o.real_in = NULL; o.out_abs = false; o.scale = inverse ? 1.0f : 1.0f / (float) n_pow2;
+	return fft_run(ctx, stream, data, (float2 *) scratch, ilog2(n_pow2), inverse, o);
+}
+
+struct tsdrgpu_frd {
+	tsdrgpu_ctx_t *ctx;
+	float *d_big; size_t big_cap;                 // extbuff (2*size floats)
+	double *d_p1, *d_p2; size_t p1_cap, p2_cap;   // the two running means
+	uint64_t calls; int fresh;
+};
+
+extern "C" {
+
+uint32_t tsdrgpu_fft_getrealsize(uint32_t size) {          // fft.c:5-11
+	uint32_t m = 0;
+	while ((size /= 2) != 0) m++;
+	return 1u << m;
+}
+
+int tsdrgpu_fft(tsdrgpu_ctx_t *ctx, void *stream, float *d_iq, uint32_t size, int inverse) {
+	BIND(ctx); ARG_TRY(ctx, d_iq != NULL);
+	if (size == 0) return TSDRGPU_OK;
+	return tsdrgpu_fft_internal(ctx, (cudaStream_t) stream, reinterpret_cast<float2 *>(d_iq), tsdrgpu_fft_getrealsize(size), inverse);
+}
+
+int tsdrgpu_autocorrelation(tsdrgpu_ctx_t *ctx, void *stream_, float *d_answer, const float *d_real, uint32_t size) {
+	BIND(ctx); ARG_TRY(ctx, d_answer != NULL && d_real != NULL);
+	if (size == 0) return TSDRGPU_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	int rc = ensure_table(ctx, stream);
+	if (rc) return rc;
+	const unsigned long long N = tsdrgpu_fft_getrealsize(size);
+	float2 *ans = reinterpret_cast<float2 *>(d_answer);
+	void *scratch;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N, &scratch))) return rc;
+	if (N == 1) {
+		k_real_to_complex<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, d_real, 0, size); LAUNCH_CHECK(ctx);
+		k_abs<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, 0, size); LAUNCH_CHECK(ctx);
+		return TSDRGPU_OK;
+	}
+	// forward transform of the first N samples, real input widened on load, |X|/N on store
+	FftOpts f; f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N;
+	if ((rc = fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 0, f))) return rc;
+	if (size > N) {                                       // the tail never enters a transform (fft.c:52-60)
+		k_real_to_complex<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, d_real, N, size); LAUNCH_CHECK(ctx);
+		k_abs<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, N, size); LAUNCH_CHECK(ctx);
+	}
+	FftOpts b; b.real_in = NULL; b.out_abs = false; b.scale = 1.0f;
+	return fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 1, b);
+}
+
+int tsdrgpu_crosscorrelation(tsdrgpu_ctx_t *ctx, void *stream_, float *d_a, float *d_b, uint32_t samples) {
+	BIND(ctx); ARG_TRY(ctx, d_a != NULL && d_b != NULL);
+	if (samples == 0) return TSDRGPU_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const unsigned long long N = tsdrgpu_fft_getrealsize(samples);
+	int rc;
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_a), N, 0))) return rc;
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_b), N, 0))) return rc;
+	k_conj_mul<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<float2 *>(d_a), reinterpret_cast<const float2 *>(d_b), N);
+	LAUNCH_CHECK(ctx);
+	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_a), N, 1);
+}
+
+int tsdrgpu_accumulate(tsdrgpu_ctx_t *ctx, void *stream, double *d_out, uint64_t calls, const float *d_in, int startid, int length) {
+	BIND(ctx); ARG_TRY(ctx, d_out != NULL && d_in != NULL && length >= 0 && startid >= 0);
+	if (length == 0) return TSDRGPU_OK;
+	k_accumulate<<<grid1d((unsigned long long) length, ctx->sm_count), 256, 0, (cudaStream_t) stream>>>(d_out, calls, reinterpret_cast<const float2 *>(d_in), startid, length);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+// ---- frame-rate detector ---------------------------------------------------------------------------------------
+int tsdrgpu_frd_create(tsdrgpu_ctx_t *ctx, tsdrgpu_frd_t **out) {
+	BIND(ctx); ARG_TRY(ctx, out != NULL);
+	tsdrgpu_frd *f = new tsdrgpu_frd();
+	memset(f, 0, sizeof *f);
+	f->ctx = ctx; f->fresh = 1;
+	*out = f;
+	return TSDRGPU_OK;
+}
+void tsdrgpu_frd_destroy(tsdrgpu_frd_t *f) {
+	if (!f) return;
+	cudaSetDevice(f->ctx->device); cudaDeviceSynchronize();
+	if (f->d_big) cudaFree(f->d_big);
+	if (f->d_p1) cudaFree(f->d_p1);
+	if (f->d_p2) cudaFree(f->d_p2);
+	delete f;
+}
+int tsdrgpu_frd_reset(tsdrgpu_frd_t *f) { if (!f) return TSDRGPU_EINVAL; f->fresh = 1; return TSDRGPU_OK; }
+
+uint32_t tsdrgpu_frd_capture_size(uint32_t samplerate) { return (uint32_t) (3.1 * samplerate / (double) (55)); }   // frameratedetector.c:160
+void tsdrgpu_frd_windows(uint32_t samplerate, int *frame_min, int *frame_max, int *line_min, int *line_max) {
+	*frame_max = (int) (samplerate / (double) (55));               // frameratedetector.c:91-95
+	*frame_min = (int) (samplerate / (double) (87));
+	*line_max = (int) (samplerate / (double) (590 * 55));
+	*line_min = (int) (samplerate / (double) (1500 * 87));
+}
+
+int tsdrgpu_frd_run(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, const float *d_capture, uint32_t size,
+                    double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
+	tsdrgpu_ctx_t *ctx = f->ctx;
+	BIND(ctx); ARG_TRY(ctx, d_capture != NULL && size > 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	int fmin, fmax, lmin, lmax;
+	tsdrgpu_frd_windows(samplerate, &fmin, &fmax, &lmin, &lmax);
+	const int flen = fmax - fmin, llen = lmax - lmin;
+	ARG_TRY(ctx, (uint64_t) fmax <= (uint64_t) size && flen >= 0 && llen >= 0);
+	if (f->big_cap < 2ull * size) {
+		CU_TRY(ctx, cudaStreamSynchronize(stream));
+		if (f->d_big) CU_TRY(ctx, cudaFree(f->d_big));
+		CU_TRY(ctx, cudaMalloc(&f->d_big, sizeof(float) * 2ull * size)); f->big_cap = 2ull * size;
+	}
+	if (f->p1_cap < (size_t) flen || f->fresh) {
+		if (f->p1_cap < (size_t) flen) { CU_TRY(ctx, cudaStreamSynchronize(stream)); if (f->d_p1) CU_TRY(ctx, cudaFree(f->d_p1)); CU_TRY(ctx, cudaMalloc(&f->d_p1, sizeof(double) * (flen + 1))); f->p1_cap = flen; }
+		CU_TRY(ctx, cudaMemsetAsync(f->d_p1, 0, sizeof(double) * (flen + 1), stream));
+	}
+	if (f->p2_cap < (size_t) llen || f->fresh) {
+		if (f->p2_cap < (size_t) llen) { CU_TRY(ctx, cudaStreamSynchronize(stream)); if (f->d_p2) CU_TRY(ctx, cudaFree(f->d_p2)); CU_TRY(ctx, cudaMalloc(&f->d_p2, sizeof(double) * (llen + 1))); f->p2_cap = llen; }
+		CU_TRY(ctx, cudaMemsetAsync(f->d_p2, 0, sizeof(double) * (llen + 1), stream));
+	}
+	if (f->fresh) { f->calls = 0; f->fresh = 0; }
+	f->calls++;                                           // extbuffer.c:81, one prepare per capture
+	int rc;
+	if ((rc = tsdrgpu_autocorrelation(ctx, stream, f->d_big, d_capture, size))) return rc;
+	if ((rc = tsdrgpu_accumulate(ctx, stream, f->d_p1, f->calls, f->d_big, fmin, flen))) return rc;
+	if ((rc = tsdrgpu_accumulate(ctx, stream, f->d_p2, f->calls, f->d_big, lmin, llen))) return rc;
+	if (calls) *calls = f->calls;
+	if (h_frame_plot || h_line_plot) {
+		if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
+		if (h_line_plot) CU_TRY(ctx, cudaMemcpyAsync(h_line_plot, f->d_p2, sizeof(double) * (size_t) (llen < line_cap ? llen : line_cap), cudaMemcpyDeviceToHost, stream));
+		CU_TRY(ctx, cudaStreamSynchronize(stream));
+	}
+	return TSDRGPU_OK;
+}
+
+// ---- superbandwidth ----------------------------------------------------------------------------------------------
+int tsdrgpu_complex_to_abs_diff(tsdrgpu_ctx_t *ctx, void *stream_, float *d_data, int size_floats) {
+	BIND(ctx); ARG_TRY(ctx, d_data != NULL && size_floats >= 0 && (size_floats & 1) == 0);
+	if (size_floats == 0) return TSDRGPU_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const unsigned long long pairs = (unsigned long long) size_floats / 2;
+	void *tmp; int rc;
+	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * pairs, &tmp))) return rc;
+	k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_data), (float2 *) tmp, pairs); LAUNCH_CHECK(ctx);
+	CU_TRY(ctx, cudaMemcpyAsync(d_data, tmp, sizeof(float2) * pairs, cudaMemcpyDeviceToDevice, stream));
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_superb_bestfit(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop0, const float *d_hopi, int size_floats,
+                           int samples_in_frame, int *h_best_offset) {
+	BIND(ctx); ARG_TRY(ctx, d_hop0 && d_hopi && h_best_offset && size_floats > 0 && samples_in_frame > 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	int size = (size_floats / samples_in_frame) * samples_in_frame;      // superbandwidth.c:84-86
+	ARG_TRY(ctx, size >= 2);
+	size = (int) tsdrgpu_fft_getrealsize((uint32_t) size);
+	const unsigned long long pairs = (unsigned long long) size / 2;
+	void *wa, *wb; int rc;
+	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * pairs + 256, &wa))) return rc;
+	if ((rc = tsdrgpu_scratch(ctx, 2, sizeof(float2) * pairs + 256, &wb))) return rc;
+	k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), (float2 *) wa, pairs); LAUNCH_CHECK(ctx);
+	k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hopi), (float2 *) wb, pairs); LAUNCH_CHECK(ctx);
+	if ((rc = tsdrgpu_crosscorrelation(ctx, stream, (float *) wa, (float *) wb, (uint32_t) pairs))) return rc;
+	int *d_res = reinterpret_cast<int *>((char *) wb);    // wb is free again after the cross-correlation
+	k_argmax_mag<<<1, 1024, 0, stream>>>((const float2 *) wa, (unsigned) pairs, d_res); LAUNCH_CHECK(ctx);
+	int lag = 0;
+	CU_TRY(ctx, cudaMemcpyAsync(&lag, d_res, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	*h_best_offset = 2 * lag;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop, int count_pairs, int best_offset_floats, float *d_spectrum) {
+	BIND(ctx); ARG_TRY(ctx, d_hop && d_spectrum && count_pairs > 0 && best_offset_floats >= 0 && (best_offset_floats & 1) == 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
+	ARG_TRY(ctx, (unsigned long long) best_offset_floats / 2 < N);
+	k_rotate<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), reinterpret_cast<float2 *>(d_spectrum), N, (unsigned long long) best_offset_floats / 2);
+	LAUNCH_CHECK(ctx);
+	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_spectrum), N, 0);
+}
+
+int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream_, float *const *d_hops, int nhops, int count_pairs, int samples_in_frame,
+                          float *d_out, int *h_best_offsets, int *h_total_samples) {
+	BIND(ctx); ARG_TRY(ctx, d_hops && nhops > 0 && count_pairs > 0 && d_out && h_best_offsets);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
+	int rc;
+	h_best_offsets[0] = 0;
+	for (int i = 1; i < nhops; i++)
+		if ((rc = tsdrgpu_superb_bestfit(ctx, stream, d_hops[0], d_hops[i], (int) (2 * N), samples_in_frame, &h_best_offsets[i]))) return rc;
+	for (int i = 0; i < nhops; i++)
+		if ((rc = tsdrgpu_superb_hop_spectrum(ctx, stream, d_hops[i], count_pairs, h_best_offsets[i], d_out + (size_t) i * 2 * N))) return rc;
+	const unsigned long long total = N * (unsigned long long) nhops;
+	const unsigned long long tp = 1ull << ilog2(total);            // fft_perform transforms the largest power of two (fft.c:101-105)
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_out), tp, 1))) return rc;
+	if (h_total_samples) *h_total_samples = (int) total;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_gathered, int nhops, uint32_t n, int residue, float *d_out) {
+	BIND(ctx); ARG_TRY(ctx, d_gathered && d_out && nhops > 0 && n > 0 && residue >= 0 && residue < nhops && (n & (n - 1)) == 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	k_residue_mix<<<grid1d(n, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_gathered), nhops, n, residue, reinterpret_cast<float2 *>(d_out));
+	LAUNCH_CHECK(ctx);
+	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_out), n, 1);
+}
+
+}  // extern "C"

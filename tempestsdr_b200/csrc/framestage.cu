@@ -1,0 +1,752 @@
+// framestage.cu -- a7..a15: the per-frame stage of the reference, for a batch of consecutive frames.
+//
+// Replaces dsp_post_process (dsp.c:134-239) and everything it calls: dsp_autogain_run (:41-94),
+// dsp_timelowpass_run (:22-33), dsp_average_v_h (:96-110), syncdetector_run / findthesweetspot / findbestfit /
+// frameratepll (syncdetector.c:26-226), gaussianblur (gaussian.c:18-79).
+//
+// The reference processes one frame at a time; frames depend on each other only through
+//   (1) two scalars of the auto-gain IIR (lastmin/lastmax),
+//   (2) the per-pixel temporal IIR (screenbuffer),
+//   (3) the sync detector's small integer state.
+// So a batch of F frames is processed stage by stage with F as an extra (parallel) grid dimension, the scalar
+// recurrences run in one-thread epilogues, and only the sync search (inherently sequential double-precision
+// sliding sums over <= a few thousand strip elements) walks the frames one after another inside a single CTA.
+// All pixel values and all integer results are bit-identical to the reference: every float/double operation is
+// issued as an individual IEEE round-to-nearest instruction in the reference's order; the order-sensitive
+// single-precision row/column sums are accumulated in exactly the reference's order (one owner thread per
+// row / per column).  Only `snr` (dead in the reference, dsp.c:234) uses tree-ordered double sums.
+//
+// Every kernel here is HBM-bound elementwise/reduction work: coalesced loads, grid sized by pixels x frames.
+#include "common.cuh"
+#include "host_plan.h"
+#include <math.h>
+
+namespace {
+
+constexpr int FS_MAX_STRIP = 8192;      // longest width/height the in-CTA sync search supports
+constexpr int FS_MM_CHUNKS = 64;        // partial reductions per frame
+constexpr int FS_SYNC_THREADS = 512;
+
+__device__ __forceinline__ bool px_is_marker(float v) { return v > 250.0f || v < -250.0f; }   // dsp.c:57
+
+struct SyncState {                      // device-resident syncdetector_t + dsp_autogain_t
+	int x_dx, x_vx, x_absvx, x_strip;
+	int y_dx, y_vx, y_absvx, y_strip;
+	double avg_speed;
+	int pll_state;
+	float lastmax, lastmin, snr;
+};
+
+struct FrameParams {                    // per frame, produced by the auto-gain epilogue
+	float lastmin, span, lastmax, snr;
+	double mean;
+};
+
+// ---------------------------------------------------------------- auto-gain pass 1: min / max / sum (dsp.c:50-61)
+template <bool SNR>
+__global__ void __launch_bounds__(256) fs_minmax(const float *__restrict__ in, size_t n, float *__restrict__ pmin,
+                                                 float *__restrict__ pmax, double *__restrict__ psum) {
+	const int f = blockIdx.y;
+	const float *src = in + (size_t) f * n;
+	float lo = INFINITY, hi = -INFINITY;
+	double sum = 0.0;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		const float v = __ldg(src + i);
+		if (px_is_marker(v)) continue;
+		hi = (v > hi) ? v : hi;
+		lo = (v < lo) ? v : lo;
+		if (SNR) sum += (double) v;
+	}
+	__shared__ float s_lo[8], s_hi[8];
+	__shared__ double s_sum[8];
+	for (int o = 16; o > 0; o >>= 1) {
+		const float olo = __shfl_xor_sync(0xffffffffu, lo, o), ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+		lo = (olo < lo) ? olo : lo; hi = (ohi > hi) ? ohi : hi;
+		if (SNR) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+	}
+	if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; if (SNR) s_sum[threadIdx.x >> 5] = sum; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < 8; w++) { lo = (s_lo[w] < lo) ? s_lo[w] : lo; hi = (s_hi[w] > hi) ? s_hi[w] : hi; if (SNR) sum += s_sum[w]; }
+		pmin[f * gridDim.x + blockIdx.x] = lo; pmax[f * gridDim.x + blockIdx.x] = hi;
+		if (SNR) psum[f * gridDim.x + blockIdx.x] = sum;
+	}
+}
+
+// epilogue: finish the reductions, then run the lastmin/lastmax IIR over the frames in order (dsp.c:63-68)
+__global__ void __launch_bounds__(256) fs_autogain_iir(const float *__restrict__ in, size_t n, int nframes, int chunks,
+                                                       const float *__restrict__ pmin, const float *__restrict__ pmax,
+                                                       const double *__restrict__ psum, bool snr, float norm,
+                                                       SyncState *state, FrameParams *params) {
+	__shared__ float s_lo[1024], s_hi[1024];
+	__shared__ double s_mean[1024];
+	for (int base = 0; base < nframes; base += 1024) {
+		const int cnt = min(1024, nframes - base);
+		for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+			const int f = base + t;
+			const float first = in[(size_t) f * n];      // min = max = screenbuffer[0], marker or not (dsp.c:50-51)
+			float lo = first, hi = first;
+			double sum = 0.0;
+			for (int c = 0; c < chunks; c++) {
+				const float a = pmin[f * chunks + c], b = pmax[f * chunks + c];
+				lo = (a < lo) ? a : lo; hi = (b > hi) ? b : hi;
+				if (snr) sum += psum[f * chunks + c];
+			}
+			s_lo[t] = lo; s_hi[t] = hi; s_mean[t] = sum / (double) n;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			float lastmax = state->lastmax, lastmin = state->lastmin;
+			const float keep = __fsub_rn(1.0f, norm);
+			for (int t = 0; t < cnt; t++) {
+				lastmax = __fadd_rn(__fmul_rn(keep, lastmax), __fmul_rn(norm, s_hi[t]));
+				lastmin = __fadd_rn(__fmul_rn(keep, lastmin), __fmul_rn(norm, s_lo[t]));
+				FrameParams p;
+				p.lastmin = lastmin; p.lastmax = lastmax;
+				p.span = (lastmax == lastmin) ? 1.0f : __fsub_rn(lastmax, lastmin);
+				p.mean = s_mean[t]; p.snr = state->snr;
+				params[base + t] = p;
+			}
+			state->lastmax = lastmax; state->lastmin = lastmin;
+		}
+		__syncthreads();
+	}
+}
+
+// auto-gain pass 2: normalise (dsp.c:72-79).  Optionally the SNR sums of the same loop.
+template <bool SNR>
+__global__ void __launch_bounds__(256) fs_normalise(const float *__restrict__ in, float *__restrict__ out, size_t n,
+                                                    const FrameParams *__restrict__ params, double *__restrict__ psq,
+                                                    double *__restrict__ plin) {
+	const int f = blockIdx.y;
+	const FrameParams P = params[f];
+	const float *src = in + (size_t) f * n;
+	float *dst = out + (size_t) f * n;
+	double sq = 0.0, lin = 0.0;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		const float v = __ldg(src + i);
+		dst[i] = px_is_marker(v) ? v : __fdiv_rn(__fsub_rn(v, P.lastmin), P.span);
+		if (SNR) { const double d = (double) v - P.mean; sq += d * d; lin += d; }
+	}
+	if (SNR) {
+		__shared__ double s_a[8], s_b[8];
+		for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); lin += __shfl_xor_sync(0xffffffffu, lin, o); }
+		if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = sq; s_b[threadIdx.x >> 5] = lin; }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			for (int w = 1; w < 8; w++) { sq += s_a[w]; lin += s_b[w]; }
+			psq[f * gridDim.x + blockIdx.x] = sq; plin[f * gridDim.x + blockIdx.x] = lin;
+		}
+	}
+}
+
+__global__ void fs_snr_finish(int nframes, int chunks, size_t n, const double *__restrict__ psq, const double *__restrict__ plin,
+                              FrameParams *params, SyncState *state) {
+	for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
+		double sq = 0.0, lin = 0.0;
+		for (int c = 0; c < chunks; c++) { sq += psq[f * chunks + c]; lin += plin[f * chunks + c]; }
+		const double stdev = sqrt((sq - lin * lin / (double) n) / (double) (n - 1));   // dsp.c:91
+		params[f].snr = (float) (params[f].mean / stdev);
+		if (f == nframes - 1) state->snr = params[f].snr;
+	}
+}
+
+// ---------------------------------------------------------------- temporal IIR over the batch (dsp.c:22-33)
+// one thread per pixel carries the screen value through the F frames in order
+__global__ void __launch_bounds__(256) fs_timelowpass(const float *__restrict__ in, float *out, float *screen,
+                                                      size_t n, int nframes, float coeff, double fresh) {
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		float s = screen[i];
+		#pragma unroll 4
+		for (int f = 0; f < nframes; f++) {
+			const float v = __ldg(in + (size_t) f * n + i);
+			const float old = __fmul_rn(s, coeff);
+			s = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
+			out[(size_t) f * n + i] = s;
+		}
+		screen[i] = s;
+	}
+}
+
+// ---------------------------------------------------------------- row / column collapse (dsp.c:96-110)
+// Sequential single-precision accumulation in raster order == per column: top to bottom; per row: left to right.
+// grid.x = column CTAs (128 columns each) followed by row CTAs (64 rows each); grid.y = frame.
+constexpr int CL_COLS = 128, CL_ROWS = 64, CL_TILE = 128;
+__global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in, int w, int h, float *__restrict__ wbuf,
+                                                   float *__restrict__ hbuf, int col_ctas) {
+	__shared__ float tile[CL_ROWS][CL_TILE + 1];
+	const int f = blockIdx.y;
+	const float *src = in + (size_t) f * w * h;
+	if ((int) blockIdx.x < col_ctas) {
+		const int x = blockIdx.x * CL_COLS + threadIdx.x;
+		if (threadIdx.x < CL_COLS && x < w) {
+			float acc = 0.0f;
+			#pragma unroll 8
+			for (int y = 0; y < h; y++) acc = __fadd_rn(acc, __ldg(src + (size_t) y * w + x));
+			wbuf[(size_t) f * w + x] = acc;
+		}
+		return;
+	}
+	const int y0 = ((int) blockIdx.x - col_ctas) * CL_ROWS;
+	const int rows = min(CL_ROWS, h - y0);
+	float acc = 0.0f;
+	for (int x0 = 0; x0 < w; x0 += CL_TILE) {
+		const int cols = min(CL_TILE, w - x0);
+		for (int idx = threadIdx.x; idx < rows * CL_TILE; idx += blockDim.x) {
+			const int ry = idx / CL_TILE, cx = idx % CL_TILE;
+			if (cx < cols) tile[ry][cx] = __ldg(src + (size_t) (y0 + ry) * w + x0 + cx);
+		}
+		__syncthreads();
+		if ((int) threadIdx.x < rows) {
+			for (int cx = 0; cx < cols; cx++) acc = __fadd_rn(acc, tile[threadIdx.x][cx]);
+		}
+		__syncthreads();
+	}
+	if ((int) threadIdx.x < rows) hbuf[(size_t) f * h + y0 + threadIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------- sync search (syncdetector.c:26-153, gaussian.c)
+struct SweetIn { int size, minsize; double lowpass; };
+
+// exact 5-tap circular blur, out of place (gaussian.c:18-79); n < 5 replayed literally by one thread
+__device__ void blur_strip(const float *__restrict__ src, float *__restrict__ dst, int n, const float *c) {
+	if (n >= 5) {
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			const int a = (j + n - 2) % n, b = (j + n - 1) % n, d = (j + 1) % n, e = (j + 2) % n;
+			float acc = __fmul_rn(src[a], c[0]);
+			acc = __fadd_rn(acc, __fmul_rn(src[b], c[1]));
+			acc = __fadd_rn(acc, __fmul_rn(src[j], c[2]));
+			acc = __fadd_rn(acc, __fmul_rn(src[d], c[3]));
+			acc = __fadd_rn(acc, __fmul_rn(src[e], c[4]));
+			dst[j] = acc;
+		}
+	} else if (threadIdx.x == 0) {
+		for (int j = 0; j < n; j++) dst[j] = src[j];
+		float w0 = dst[0], w1 = dst[1 % n], w2 = dst[2 % n], w3 = dst[3 % n], w4 = dst[4 % n];
+		const float k2 = w2, k3 = w3, k4 = w4;
+		for (int i = 0; i < n; i++) {
+			const int upd = (i < n - 2) ? (i + 2) : (i - (n - 2));
+			const int nxt = (i < n - 5) ? (i + 5) : (i - (n - 5));
+			float acc = __fmul_rn(w0, c[0]);
+			acc = __fadd_rn(acc, __fmul_rn(w1, c[1]));
+			acc = __fadd_rn(acc, __fmul_rn(w2, c[2]));
+			acc = __fadd_rn(acc, __fmul_rn(w3, c[3]));
+			acc = __fadd_rn(acc, __fmul_rn(w4, c[4]));
+			dst[upd] = acc;
+			w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+			if (nxt < 2 || nxt >= 5) w4 = dst[nxt]; else w4 = (nxt == 2) ? k2 : (nxt == 3 ? k3 : k4);
+		}
+	}
+}
+
+// the serial part of findbestfit: window sums for every start position, written to `cs` (global scratch).
+// cs[0] = sum of the first `strip` elements; cs[e] = window sum after the e-th slide (syncdetector.c:31-49)
+__device__ void window_sums(const float *__restrict__ data, int size, int strip, double *__restrict__ cs) {
+	double cur = 0.0;
+	for (int i = 0; i < strip; i++) cur = __dadd_rn(cur, (double) data[i]);
+	cs[0] = cur;
+	const int wrap_at = size - strip;
+	for (int i = 0; i < size - 1; i++) {
+		const int enter = (i < wrap_at) ? (i + strip) : (i - wrap_at);
+		cur = __dadd_rn(__dsub_rn(cur, (double) data[i]), (double) data[enter]);
+		cs[i + 1] = cur;
+	}
+}
+
+__device__ __forceinline__ double fit_score(double total, double cs, double n_out, double n_in) {
+	const double contrast = __dsub_rn(__ddiv_rn(__dsub_rn(total, cs), n_out), __ddiv_rn(cs, n_in));
+	return __dmul_rn(contrast, contrast);
+}
+
+struct Best { double score; int e; };
+// first maximum in e-order (the reference updates only on a strict '>')
+__device__ __forceinline__ Best best_merge(Best a, Best b) {
+	if (b.score > a.score || (b.score == a.score && b.e < a.e)) return b;
+	return a;
+}
+
+__global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
+                                                           int w, int h, int minsize_x, int minsize_y, int nframes,
+                                                           float c0, float c1, float c2, float c3, float c4,
+                                                           SyncState *state, double *__restrict__ chain_scratch,
+                                                           const FrameParams *__restrict__ params, tsdrgpu_frame_result_t *results) {
+	extern __shared__ float smem[];
+	float *raw_x = smem, *blur_x = raw_x + w, *raw_y = blur_x + w, *blur_y = raw_y + h;
+	__shared__ int cand[2][5];           // strip sizes tried per axis, -1 = skipped
+	__shared__ float totalf[2];
+	__shared__ Best warp_best[FS_SYNC_THREADS / 32];
+	__shared__ Best cand_best[2][5];
+	__shared__ SyncState st;
+	const float taps[5] = {c0, c1, c2, c3, c4};
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) st = *state;
+	__syncthreads();
+
+	for (int f = 0; f < nframes; f++) {
+		for (int i = threadIdx.x; i < w; i += blockDim.x) raw_x[i] = wstrips[(size_t) f * w + i];
+		for (int i = threadIdx.x; i < h; i += blockDim.x) raw_y[i] = hstrips[(size_t) f * h + i];
+		if (threadIdx.x == 0) {
+			// clamp the carried strip size and list the sizes to try (syncdetector.c:73-77, 60-69, 88-93)
+			for (int ax = 0; ax < 2; ax++) {
+				const int size = ax ? h : w;
+				int minsize = ax ? minsize_y : minsize_x;
+				if (minsize < 1) minsize = 1;
+				const int half = size >> 1;
+				int &cur = ax ? st.y_strip : st.x_strip;
+				if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
+				const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
+				cand[ax][0] = cur;
+				for (int t = 1; t < 5; t++) cand[ax][t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
+			}
+		}
+		__syncthreads();
+		blur_strip(raw_x, blur_x, w, taps);
+		blur_strip(raw_y, blur_y, h, taps);
+		__syncthreads();
+		// serial chains, one per warp (lane 0): 2 totals + up to 10 window-sum chains
+		if (lane == 0 && warp < 12) {
+			if (warp < 2) {
+				const float *d = warp ? blur_y : blur_x; const int size = warp ? h : w;
+				double tot = 0.0;
+				for (int i = 0; i < size; i++) tot = __dadd_rn(tot, (double) d[i]);
+				totalf[warp] = __double2float_rn(tot);          // findbestfit takes a float (syncdetector.c:26)
+			} else {
+				const int ax = (warp - 2) / 5, t = (warp - 2) % 5;
+				const int strip = cand[ax][t];
+				if (strip > 0) window_sums(ax ? blur_y : blur_x, ax ? h : w, strip, chain_scratch + (size_t) (warp - 2) * FS_MAX_STRIP);
+			}
+		}
+		__syncthreads();
+		// score every window of every candidate in parallel; keep the first maximum
+		for (int ci = 0; ci < 10; ci++) {
+			const int ax = ci / 5, t = ci % 5;
+			const int strip = cand[ax][t];
+			if (strip <= 0) { if (threadIdx.x == 0) { cand_best[ax][t].score = -1.0; cand_best[ax][t].e = -1; } continue; }
+			const int size = ax ? h : w;
+			const double total = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
+			const double *cs = chain_scratch + (size_t) ci * FS_MAX_STRIP;
+			Best b; b.score = -INFINITY; b.e = 0x7fffffff;
+			for (int e = threadIdx.x; e < size; e += blockDim.x) {
+				const double s = fit_score(total, cs[e], n_out, n_in);
+				if (s > b.score) { b.score = s; b.e = e; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
+				b = best_merge(b, other);
+			}
+			if (lane == 0) warp_best[warp] = b;
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				Best r = warp_best[0];
+				for (int k = 1; k < FS_SYNC_THREADS / 32; k++) r = best_merge(r, warp_best[k]);
+				// e = 0 is the starting value of the reference's running maximum even when it is NaN
+				const double s0 = fit_score(total, cs[0], n_out, n_in);
+				if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
+				cand_best[ax][t] = r;
+			}
+			__syncthreads();
+		}
+		if (threadIdx.x == 0) {
+			for (int ax = 0; ax < 2; ax++) {
+				const int size = ax ? h : w;
+				const double lowpass = ax ? 0.1 : 0.9;          // FRAMERATE_DX_LOWPASS_COEFF_* (syncdetector.c:15-16)
+				int &dx = ax ? st.y_dx : st.x_dx; int &vx = ax ? st.y_vx : st.x_vx;
+				int &absvx = ax ? st.y_absvx : st.x_absvx; int &cur = ax ? st.y_strip : st.x_strip;
+				// pick among candidates in the reference's order, strict '>' (syncdetector.c:60-69)
+				Best best = cand_best[ax][0];
+				int best_size = cand[ax][0];
+				for (int t = 1; t < 5; t++) {
+					if (cand[ax][t] <= 0) continue;
+					if (cand_best[ax][t].score > best.score) { best = cand_best[ax][t]; best_size = cand[ax][t]; }
+				}
+				const int best_start = (best.e == 0) ? 0 : best.e - 1;   // index recorded before the slide
+				cur = best_size;
+				const int h2 = size / 2;
+				int centre = (best_start + best_size / 2) % size;
+				const int jump = centre - dx;
+				if (jump > h2) dx += size; else if (jump < -h2) centre += size;
+				const int before = dx;
+				const double mixed = __dadd_rn(__dmul_rn((double) centre, lowpass), __dmul_rn(__dsub_rn(1.0, lowpass), (double) dx));
+				dx = (int) (((long long) round(mixed)) % ((long long) size));
+				const int moved = dx - before;
+				vx = (moved > h2) ? (size - moved) : ((moved < -h2) ? (-size - moved) : moved);
+				absvx = (vx >= 0) ? vx : -vx;
+			}
+			// frameratepll bookkeeping (syncdetector.c:134-139); the refreshrate write-back is the host's
+			st.avg_speed = __dadd_rn(__dmul_rn(st.avg_speed, 0.99), __dmul_rn(0.01, (double) st.x_vx));
+			st.pll_state = (st.avg_speed < 0.5 && st.avg_speed > -0.5) ? 1 : 0;
+			tsdrgpu_frame_result_t r;
+			r.x_dx = st.x_dx; r.x_vx = st.x_vx; r.x_absvx = st.x_absvx; r.x_stripsize = st.x_strip;
+			r.y_dx = st.y_dx; r.y_vx = st.y_vx; r.y_absvx = st.y_absvx; r.y_stripsize = st.y_strip;
+			r.avg_speed = st.avg_speed; r.pll_state = st.pll_state;
+			r.lastmax = params ? params[f].lastmax : st.lastmax;
+			r.lastmin = params ? params[f].lastmin : st.lastmin;
+			r.snr = params ? params[f].snr : st.snr;
+			r.autogain_report = 0; r.reserved = 0;
+			results[f] = r;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		// auto-gain fields of the state are owned by the auto-gain epilogue: write back the sync part only
+		state->x_dx = st.x_dx; state->x_vx = st.x_vx; state->x_absvx = st.x_absvx; state->x_strip = st.x_strip;
+		state->y_dx = st.y_dx; state->y_vx = st.y_vx; state->y_absvx = st.y_absvx; state->y_strip = st.y_strip;
+		state->avg_speed = st.avg_speed; state->pll_state = st.pll_state;
+	}
+}
+
+// refresh the auto-gain fields of already written results (auto-gain-after-processing order)
+__global__ void fs_results_autogain(int nframes, const FrameParams *__restrict__ params, tsdrgpu_frame_result_t *results) {
+	for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
+		results[f].lastmax = params[f].lastmax; results[f].lastmin = params[f].lastmin; results[f].snr = params[f].snr;
+	}
+}
+
+// ---------------------------------------------------------------- circular 2-D re-centre (syncdetector.c:187-207)
+__global__ void __launch_bounds__(256) fs_shift(const float *__restrict__ in, float *__restrict__ out, int w, int h,
+                                                const tsdrgpu_frame_result_t *__restrict__ results) {
+	const int f = blockIdx.y;
+	const int dx = results[f].x_dx, dy = results[f].y_dx;
+	const size_t n = (size_t) w * h;
+	const float *src = in + (size_t) f * n;
+	float *dst = out + (size_t) f * n;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		const int y = (int) (i / w), x = (int) (i - (size_t) y * w);
+		int sy = y + dy; if (sy >= h) sy -= h;
+		int sx = x + dx; if (sx >= w) sx -= w;
+		dst[i] = __ldg(src + (size_t) sy * w + sx);
+	}
+}
+
+// green marker lines (syncdetector.c:121-131, 209-220): copy (if out != in) then draw
+__global__ void __launch_bounds__(256) fs_copy(const float *__restrict__ in, float *__restrict__ out, size_t total) {
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) out[i] = in[i];
+}
+__global__ void __launch_bounds__(256) fs_greenlines(float *frames, int w, int h, const tsdrgpu_frame_result_t *__restrict__ results) {
+	const int f = blockIdx.y;
+	float *d = frames + (size_t) f * w * h;
+	const int dx = results[f].x_dx, dy = results[f].y_dx;
+	// vertical line first, then the horizontal one (its pixels win at the crossing; both are 512.0 anyway)
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < h + w; i += gridDim.x * blockDim.x) {
+		if (i < h) d[dx + (size_t) w * i] = 512.0f; else d[(i - h) + (size_t) w * dy] = 512.0f;
+	}
+}
+
+__global__ void __launch_bounds__(256) fs_argb(const float *__restrict__ frame, int n, int inverted, int *__restrict__ argb) {
+	const int white = 255 | (255 << 8) | (255 << 16);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float v = frame[i];
+		int px;
+		if (v > 0.0f && v <= 1.0f) {
+			int g = (int) __fmul_rn(v, 255.0f);
+			if (inverted) g = 255 - g;
+			px = g | (g << 8) | (g << 16);
+		} else if (v <= 0.0f) px = inverted ? white : 0;
+		else if (v == 256.0f) px = 255 << 16;
+		else if (v == 512.0f) px = 255 << 8;
+		else if (v == 1024.0f) px = 255;
+		else if (v == 2048.0f) continue;                 // transparent: slot left untouched
+		else px = inverted ? 0 : white;
+		argb[i] = px;
+	}
+}
+
+__global__ void fs_blur_kernel(float *data, int n, float c0, float c1, float c2, float c3, float c4) {
+	extern __shared__ float smem[];
+	float *src = smem, *dst = smem + n;
+	const float taps[5] = {c0, c1, c2, c3, c4};
+	for (int i = threadIdx.x; i < n; i += blockDim.x) src[i] = data[i];
+	__syncthreads();
+	blur_strip(src, dst, n, taps);
+	__syncthreads();
+	for (int i = threadIdx.x; i < n; i += blockDim.x) data[i] = dst[i];
+}
+
+inline unsigned grid_for(size_t n, int sm_count, int per_sm = 8) {
+	const size_t want = (n + 255) / 256;
+	const size_t cap = (size_t) sm_count * per_sm;
+	return (unsigned) (want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------------------------
+struct tsdrgpu_framestage {
+	tsdrgpu_ctx_t *ctx;
+	float *d_screen; size_t screen_cap;          // dsp_postprocess_t.screenbuffer / bufsize
+	int w, h; size_t n;                          // current geometry (pp->width/height/sizetopoll)
+	int lp_before_sync;                          // pp->lowpass_before_sync
+	int runs;                                    // pp->runs
+	SyncState *d_state;
+	// batch temporaries
+	float *d_t1, *d_t2; size_t t_cap;
+	float *d_wstrips, *d_hstrips; size_t strips_cap;
+	float *d_pmin, *d_pmax; double *d_psum, *d_psq, *d_plin; FrameParams *d_params; tsdrgpu_frame_result_t *d_results; int batch_cap;
+	double *d_chain;
+	float taps[5];
+};
+
+static int fs_reserve(tsdrgpu_framestage *fs, int nframes, size_t n, int w, int h) {
+	tsdrgpu_ctx_t *ctx = fs->ctx;
+	const size_t need = (size_t) nframes * n;
+	if (fs->t_cap < need) {
+		CU_TRY(ctx, cudaDeviceSynchronize());
+		if (fs->d_t1) CU_TRY(ctx, cudaFree(fs->d_t1));
+		if (fs->d_t2) CU_TRY(ctx, cudaFree(fs->d_t2));
+		CU_TRY(ctx, cudaMalloc(&fs->d_t1, sizeof(float) * need));
+		CU_TRY(ctx, cudaMalloc(&fs->d_t2, sizeof(float) * need));
+		fs->t_cap = need;
+	}
+	const size_t sneed = (size_t) nframes * (size_t) (w > h ? w : h);
+	if (fs->strips_cap < sneed) {
+		CU_TRY(ctx, cudaDeviceSynchronize());
+		if (fs->d_wstrips) CU_TRY(ctx, cudaFree(fs->d_wstrips));
+		if (fs->d_hstrips) CU_TRY(ctx, cudaFree(fs->d_hstrips));
+		CU_TRY(ctx, cudaMalloc(&fs->d_wstrips, sizeof(float) * sneed));
+		CU_TRY(ctx, cudaMalloc(&fs->d_hstrips, sizeof(float) * sneed));
+		fs->strips_cap = sneed;
+	}
+	if (fs->batch_cap < nframes) {
+		CU_TRY(ctx, cudaDeviceSynchronize());
+		void *ptrs[] = {fs->d_pmin, fs->d_pmax, fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results};
+		for (void *p : ptrs) if (p) CU_TRY(ctx, cudaFree(p));
+		const size_t pc = (size_t) nframes * FS_MM_CHUNKS;
+		CU_TRY(ctx, cudaMalloc(&fs->d_pmin, sizeof(float) * pc));
+		CU_TRY(ctx, cudaMalloc(&fs->d_pmax, sizeof(float) * pc));
+		CU_TRY(ctx, cudaMalloc(&fs->d_psum, sizeof(double) * pc));
+		CU_TRY(ctx, cudaMalloc(&fs->d_psq, sizeof(double) * pc));
+		CU_TRY(ctx, cudaMalloc(&fs->d_plin, sizeof(double) * pc));
+		CU_TRY(ctx, cudaMalloc(&fs->d_params, sizeof(FrameParams) * nframes));
+		CU_TRY(ctx, cudaMalloc(&fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes));
+		fs->batch_cap = nframes;
+	}
+	return TSDRGPU_OK;
+}
+
+// auto-gain of a batch: in -> out, state updated, params[f] filled
+static int fs_autogain_batch(tsdrgpu_framestage *fs, cudaStream_t stream, const float *in, float *out, int nframes, size_t n,
+                             float norm, bool snr) {
+	tsdrgpu_ctx_t *ctx = fs->ctx;
+	const int chunks = (int) ((n + 4095) / 4096 < FS_MM_CHUNKS ? (n + 4095) / 4096 : FS_MM_CHUNKS);
+	dim3 grid(chunks, nframes);
+	if (snr) fs_minmax<true><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum);
+	else fs_minmax<false><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum);
+	LAUNCH_CHECK(ctx);
+	fs_autogain_iir<<<1, 256, 0, stream>>>(in, n, nframes, chunks, fs->d_pmin, fs->d_pmax, fs->d_psum, snr, norm, fs->d_state, fs->d_params);
+	LAUNCH_CHECK(ctx);
+	const unsigned gx = grid_for(n, ctx->sm_count, 4);
+	dim3 grid2(snr ? (gx < (unsigned) FS_MM_CHUNKS ? gx : FS_MM_CHUNKS) : gx, nframes);
+	if (snr) fs_normalise<true><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin);
+	else fs_normalise<false><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin);
+	LAUNCH_CHECK(ctx);
+	if (snr) {
+		fs_snr_finish<<<1, 256, 0, stream>>>(nframes, (int) grid2.x, n, fs->d_psq, fs->d_plin, fs->d_params, fs->d_state);
+		LAUNCH_CHECK(ctx);
+	}
+	return TSDRGPU_OK;
+}
+
+extern "C" {
+
+int tsdrgpu_framestage_create(tsdrgpu_ctx_t *ctx, tsdrgpu_framestage_t **out) {
+	BIND(ctx); ARG_TRY(ctx, out != NULL);
+	tsdrgpu_framestage *fs = new tsdrgpu_framestage();
+	memset(fs, 0, sizeof(*fs));
+	fs->ctx = ctx;
+	tsdrgpu_gauss_taps(fs->taps);
+	CU_TRY(ctx, cudaMalloc(&fs->d_state, sizeof(SyncState)));
+	CU_TRY(ctx, cudaMalloc(&fs->d_chain, sizeof(double) * 10 * FS_MAX_STRIP));
+	*out = fs;
+	return tsdrgpu_framestage_reset(fs, NULL);
+}
+
+void tsdrgpu_framestage_destroy(tsdrgpu_framestage_t *fs) {
+	if (!fs) return;
+	cudaSetDevice(fs->ctx->device);
+	cudaDeviceSynchronize();
+	void *ptrs[] = {fs->d_screen, fs->d_state, fs->d_t1, fs->d_t2, fs->d_wstrips, fs->d_hstrips, fs->d_pmin, fs->d_pmax,
+	                fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results, fs->d_chain};
+	for (void *p : ptrs) if (p) cudaFree(p);
+	delete fs;
+}
+
+int tsdrgpu_framestage_reset(tsdrgpu_framestage_t *fs, void *stream) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
+	BIND(fs->ctx);
+	SyncState s; memset(&s, 0, sizeof s);
+	s.snr = 1.0f;                                        // dsp_autogain_init (dsp.c:35-39)
+	CU_TRY(fs->ctx, cudaMemcpyAsync(fs->d_state, &s, sizeof s, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	CU_TRY(fs->ctx, cudaStreamSynchronize((cudaStream_t) stream));
+	if (fs->d_screen) { CU_TRY(fs->ctx, cudaFree(fs->d_screen)); fs->d_screen = NULL; }
+	fs->screen_cap = 0; fs->w = 0; fs->h = 0; fs->n = 0; fs->lp_before_sync = 0; fs->runs = 0;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_framestage_run(tsdrgpu_framestage_t *fs, void *stream_, const float *d_in, int nframes, int w, int h,
+                           float motionblur, float lowpasscoeff, unsigned flags, float *d_out, tsdrgpu_frame_result_t *h_results) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
+	tsdrgpu_ctx_t *ctx = fs->ctx;
+	BIND(ctx);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	if (nframes == 0) return TSDRGPU_OK;
+	ARG_TRY(ctx, nframes > 0 && w > 0 && h > 0 && d_in != NULL && d_out != NULL && d_in != d_out);
+	ARG_TRY(ctx, w <= FS_MAX_STRIP && h <= FS_MAX_STRIP);
+	const size_t n = (size_t) w * h;
+	const bool autoshift = flags & TSDRGPU_FS_AUTOSHIFT, lpbs = flags & TSDRGPU_FS_LOWPASS_BEFORE_SYNC;
+	const bool aap = flags & TSDRGPU_FS_AUTOGAIN_AFTER_PROC, superres = flags & TSDRGPU_FS_SUPERRESOLUTION;
+	const bool snr = flags & TSDRGPU_FS_COMPUTE_SNR;
+
+	// buffer (re)sizing exactly as dsp.c:152-186
+	if (h != fs->h || w != fs->w) {
+		fs->h = h; fs->w = w; fs->n = n;
+		if (n > fs->screen_cap) {
+			float *nb;
+			CU_TRY(ctx, cudaStreamSynchronize(stream));
+			CU_TRY(ctx, cudaMalloc(&nb, sizeof(float) * n));
+			if (fs->d_screen) CU_TRY(ctx, cudaFree(fs->d_screen));
+			fs->d_screen = nb; fs->screen_cap = n;
+			CU_TRY(ctx, cudaMemsetAsync(fs->d_screen, 0, sizeof(float) * n, stream));
+		}
+	}
+	if (fs->lp_before_sync != (int) lpbs) {
+		fs->lp_before_sync = lpbs;
+		CU_TRY(ctx, cudaMemsetAsync(fs->d_screen, 0, sizeof(float) * n, stream));
+	}
+	{ int rc = fs_reserve(fs, nframes, n, w, h); if (rc != TSDRGPU_OK) return rc; }
+
+	const double fresh = 1.0 - (double) motionblur;      // dsp.c:29
+	const int minsize_x = (int) (w * 0.05f), minsize_y = (int) (h * 0.01f);   // syncdetector.c:178-179
+	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
+	const size_t sync_smem = sizeof(float) * 2 * ((size_t) w + h);
+	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(float) * 4 * FS_MAX_STRIP)));
+	const unsigned gx = grid_for(n, ctx->sm_count, 4);
+	const size_t total = (size_t) nframes * n;
+
+	auto collapse_sync = [&](const float *src, bool with_params) -> int {
+		fs_collapse<<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips, fs->d_hstrips, col_ctas);
+		LAUNCH_CHECK(ctx);
+		fs_sync<<<1, FS_SYNC_THREADS, sync_smem, stream>>>(fs->d_wstrips, fs->d_hstrips, w, h, minsize_x, minsize_y, nframes,
+			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain,
+			with_params ? fs->d_params : NULL, fs->d_results);
+		LAUNCH_CHECK(ctx);
+		return TSDRGPU_OK;
+	};
+	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed
+	auto emit = [&](float *src, float *dst, bool greenlines, bool may_modify, float **result) -> int {
+		if (autoshift) {
+			fs_shift<<<dim3(gx, nframes), 256, 0, stream>>>(src, dst, w, h, fs->d_results); LAUNCH_CHECK(ctx);
+			*result = dst;
+		} else if (greenlines && may_modify) {
+			fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(src, w, h, fs->d_results); LAUNCH_CHECK(ctx);
+			*result = src;
+		} else if (greenlines) {
+			fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, dst, total); LAUNCH_CHECK(ctx);
+			fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(dst, w, h, fs->d_results); LAUNCH_CHECK(ctx);
+			*result = dst;
+		} else *result = src;
+		return TSDRGPU_OK;
+	};
+	auto copy_to_out = [&](const float *src) -> int {
+		if (src != d_out) { fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, d_out, total); LAUNCH_CHECK(ctx); }
+		return TSDRGPU_OK;
+	};
+	int rc;
+	float *res = NULL;
+	if (lpbs) {                                          // dsp.c:201-212
+		const float *lp_in = d_in;
+		if (!aap) { if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc; lp_in = fs->d_t1; }
+		fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, fs->d_t2, fs->d_screen, n, nframes, motionblur, fresh); LAUNCH_CHECK(ctx);
+		if ((rc = collapse_sync(fs->d_t2, !aap))) return rc;
+		float *dst = aap ? fs->d_t1 : d_out;
+		if ((rc = emit(fs->d_t2, dst, !superres, false, &res))) return rc;
+		if (aap) {
+			if ((rc = fs_autogain_batch(fs, stream, res, d_out, nframes, n, lowpasscoeff, snr))) return rc;
+			fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results); LAUNCH_CHECK(ctx);
+		} else if ((rc = copy_to_out(res))) return rc;
+	} else {                                             // dsp.c:214-226
+		float *work = fs->d_t1;
+		if (!aap) { if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc; }
+		else { fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(d_in, fs->d_t1, total); LAUNCH_CHECK(ctx); }
+		if ((rc = collapse_sync(work, !aap))) return rc;
+		if ((rc = emit(work, fs->d_t2, (motionblur == 0.0f) && !superres, true, &res))) return rc;
+		float *lp_out = aap ? ((res == fs->d_t1) ? fs->d_t2 : fs->d_t1) : d_out;
+		fs_timelowpass<<<gx, 256, 0, stream>>>(res, lp_out, fs->d_screen, n, nframes, motionblur, fresh); LAUNCH_CHECK(ctx);
+		if (aap) {
+			if ((rc = fs_autogain_batch(fs, stream, lp_out, d_out, nframes, n, lowpasscoeff, snr))) return rc;
+			fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results); LAUNCH_CHECK(ctx);
+		}
+	}
+	if (h_results) {
+		CU_TRY(ctx, cudaMemcpyAsync(h_results, fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes, cudaMemcpyDeviceToHost, stream));
+		CU_TRY(ctx, cudaStreamSynchronize(stream));
+		for (int f = 0; f < nframes; f++) {
+			h_results[f].autogain_report = 0;
+			if (fs->runs++ > 5) { fs->runs = 0; h_results[f].autogain_report = 1; }     // dsp.c:231-235
+		}
+	} else {
+		for (int f = 0; f < nframes; f++) if (fs->runs++ > 5) fs->runs = 0;
+	}
+	return TSDRGPU_OK;
+}
+
+// ---- stage-level entry points -------------------------------------------------------------------------------
+int tsdrgpu_autogain(tsdrgpu_ctx_t *ctx, void *stream_, float *h_lastmax, float *h_lastmin, float *h_snr,
+                     int n, const float *d_in, float *d_out, float norm) {
+	BIND(ctx);
+	ARG_TRY(ctx, n > 0 && d_in && d_out && h_lastmax && h_lastmin);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	tsdrgpu_framestage_t *fs;
+	int rc = tsdrgpu_framestage_create(ctx, &fs);
+	if (rc) return rc;
+	SyncState s; memset(&s, 0, sizeof s);
+	s.lastmax = *h_lastmax; s.lastmin = *h_lastmin; s.snr = h_snr ? *h_snr : 1.0f;
+	CU_TRY(ctx, cudaMemcpy(fs->d_state, &s, sizeof s, cudaMemcpyHostToDevice));
+	if ((rc = fs_reserve(fs, 1, 1, 1, 1))) { tsdrgpu_framestage_destroy(fs); return rc; }
+	rc = fs_autogain_batch(fs, stream, d_in, d_out, 1, (size_t) n, norm, h_snr != NULL);
+	if (rc == TSDRGPU_OK) {
+		CU_TRY(ctx, cudaStreamSynchronize(stream));
+		CU_TRY(ctx, cudaMemcpy(&s, fs->d_state, sizeof s, cudaMemcpyDeviceToHost));
+		*h_lastmax = s.lastmax; *h_lastmin = s.lastmin; if (h_snr) *h_snr = s.snr;
+	}
+	tsdrgpu_framestage_destroy(fs);
+	return rc;
+}
+
+int tsdrgpu_timelowpass(tsdrgpu_ctx_t *ctx, void *stream, float coeff, int n, const float *d_in, float *d_screen) {
+	BIND(ctx);
+	ARG_TRY(ctx, n > 0 && d_in && d_screen);
+	// single frame: the per-frame output IS the screen buffer
+	fs_timelowpass<<<grid_for((size_t) n, ctx->sm_count, 4), 256, 0, (cudaStream_t) stream>>>(d_in, d_screen, d_screen, (size_t) n, 1, coeff, 1.0 - (double) coeff);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_average_v_h(tsdrgpu_ctx_t *ctx, void *stream, int w, int h, const float *d_in, float *d_wbuf, float *d_hbuf) {
+	BIND(ctx);
+	ARG_TRY(ctx, w > 0 && h > 0 && d_in && d_wbuf && d_hbuf);
+	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
+	fs_collapse<<<dim3(col_ctas + row_ctas, 1), 256, 0, (cudaStream_t) stream>>>(d_in, w, h, d_wbuf, d_hbuf, col_ctas);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_gaussianblur(tsdrgpu_ctx_t *ctx, void *stream, float *d_data, int n) {
+	BIND(ctx);
+	ARG_TRY(ctx, n > 0 && n <= 2 * FS_MAX_STRIP && d_data);
+	float t[5];
+	tsdrgpu_gauss_taps(t);
+	CU_TRY(ctx, cudaFuncSetAttribute(fs_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(float) * 4 * FS_MAX_STRIP)));
+	fs_blur_kernel<<<1, 256, sizeof(float) * 2 * n, (cudaStream_t) stream>>>(d_data, n, t[0], t[1], t[2], t[3], t[4]);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_pixels_argb(tsdrgpu_ctx_t *ctx, void *stream, const float *d_frame, int n, int inverted, int32_t *d_argb) {
+	BIND(ctx);
+	ARG_TRY(ctx, n > 0 && d_frame && d_argb);
+	fs_argb<<<grid_for((size_t) n, ctx->sm_count), 256, 0, (cudaStream_t) stream>>>(d_frame, n, inverted, d_argb);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+}  // extern "C"

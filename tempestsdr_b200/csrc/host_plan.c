@@ -1,0 +1,45 @@
+/* host_plan.c -- host-side scalar planning for libtsdrgpu.  Plain C on purpose ("host code stays C"): these are
+ * the data-independent scalar recurrences of the reference, replayed with the reference's operand types and
+ * operation order so the device kernels receive bit-identical parameters. */
+#include "host_plan.h"
+#include <math.h>
+
+uint64_t tsdrgpu_plan_resample(double *offset, const uint32_t *sizes, uint32_t uniform, uint32_t nblocks,
+                               double upsample_by, double downsample_by, tsdrgpu_rs_block_t *blocks) {
+	const double r = upsample_by / downsample_by;          /* dsp.c:258 */
+	const double rinv = downsample_by / upsample_by;       /* dsp.c:259 */
+	double off = *offset;
+	uint64_t in_pos = 0, out_pos = 0;
+	for (uint32_t b = 0; b < nblocks; b++) {
+		const uint32_t size = sizes ? sizes[b] : uniform;
+		const uint32_t n_out = (uint32_t) (int) ((size - off) * r);      /* dsp.c:262 */
+		if (n_out == 0) return UINT64_MAX;
+		if (blocks) {
+			blocks[b].in_start = in_pos; blocks[b].out_start = out_pos;
+			blocks[b].size = size; blocks[b].n_out = n_out;
+			blocks[b].r = r; blocks[b].phase = -off * r;                  /* dsp.c:272 */
+		}
+		off += n_out * rinv - size;                                       /* dsp.c:306 */
+		in_pos += size; out_pos += n_out;
+	}
+	*offset = off;
+	return out_pos;
+}
+
+void tsdrgpu_geometry(uint32_t samplerate, int height, double refreshrate, int *width, double *pixelrate,
+                      double *pixeltimeoversampletime) {
+	const double real_width = samplerate / (refreshrate * height);
+	const int w = (int) (2 * real_width);
+	const double pr = w * height * refreshrate;
+	*width = w; *pixelrate = pr;
+	*pixeltimeoversampletime = (samplerate != 0 && pr != 0) ? ((double) samplerate) / pr : 0.0;
+}
+
+void tsdrgpu_gauss_taps(float taps[5]) {
+	/* CALC_GAUSSCOEFF(N,i) = expf(-2.0f*ALPHA*ALPHA*i*i/(N*N)) with textual i in {-2,-1,0,1,2}, N = 5 */
+	const float e2 = expf(-2.0f * 1.0f * 1.0f * -2 * -2 / (5 * 5));
+	const float e1 = expf(-2.0f * 1.0f * 1.0f * -1 * -1 / (5 * 5));
+	const float e0 = expf(-2.0f * 1.0f * 1.0f * 0 * 0 / (5 * 5));
+	const float norm = e2 + e1 + e0 + e1 + e2;
+	taps[0] = e2 / norm; taps[1] = e1 / norm; taps[2] = e0 / norm; taps[3] = e1 / norm; taps[4] = e2 / norm;
+}

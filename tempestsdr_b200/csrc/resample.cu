@@ -1,0 +1,385 @@
+// resample.cu -- a2 + a6: AM demodulation fused with the reference's area-weighted box resampler.
+//
+// Replaces am_demod (TSDRLibrary.c:244-262) and dsp_resample_process (dsp.c:256-307), bit-exact.
+//
+// How a serial loop becomes a data-parallel kernel
+// ------------------------------------------------
+// The reference walks samples k = 0..size-1 keeping `pid`, the next pixel to complete.  Sample k covers
+//     lo_k = fl(fl(k*r) + phase),  hi_k = fl(lo_k + r),  c_k = fl(hi_k - 1)           (dsp.c:282-284)
+// on the pixel axis.  After sample k, pid == P(k) := max(0, ceil(c_k)) -- a closed form, because c_k is
+// monotone in k.  So sample k emits pixels P(k-1) .. P(k)-1:
+//     the first one is an "A" pixel,  float(bank + v_k*((1-lo_k)+p)),   iff p < lo_k && p < c_k  (dsp.c:288-292)
+//     all others are "B" pixels,      v_k                                                    (dsp.c:294-297)
+// and then banks t_k = (P(k) < hi_k && P(k) > lo_k) ? (hi_k-P(k))*v_k : r*v_k               (dsp.c:299-302).
+// `bank` before sample k is the left-to-right double sum of t_j since the last A pixel (where it is zeroed):
+// for r > 1 that is just t_{k-1}; the general case walks back until it meets an A sample.  Everything except
+// the sample values is data-independent, and all double operations are issued as separate IEEE
+// round-to-nearest instructions (no FMA contraction), so every pixel is bit-identical to gcc's x86-64 result.
+//
+// Only one pixel per decimator block cannot be produced locally: the first A pixel, whose bank reaches back
+// into the previous block (or into the carried `contrib` state).  A small second kernel (rs_fixup) resolves
+// those, fills slots the reference leaves stale, and writes the new `contrib`.
+//
+// Memory plan: 8 B read per IQ pair (ld.global.nc, L1 no-allocate), magnitudes staged once in shared memory,
+// pixels assembled in shared memory and written back as full contiguous runs.  Algorithmic traffic:
+// 8 B + 4*r B per sample (~16 B at r ~ 2).  Bound: HBM.
+#include "common.cuh"
+#include "host_plan.h"
+
+namespace {
+
+constexpr int RS_TILE = 2048;        // samples per CTA tile
+constexpr int RS_THREADS = 256;
+constexpr int RS_HALO = 8;           // samples before the tile kept in smem for short bank chains
+constexpr int RS_OUT_CAP = 3 * RS_TILE + 16;   // pixels staged per tile (r <= 3); larger ratios store directly
+
+struct RsBlock { unsigned long long in_start, out_start; unsigned size, n_out; double r, phase; };
+static_assert(sizeof(RsBlock) == sizeof(tsdrgpu_rs_block_t), "device/host block layout");
+
+struct Geo { double lo, hi, c; };
+
+__device__ __forceinline__ Geo rs_geo(unsigned k, double r, double phase) {
+	Geo g;
+	g.lo = __dadd_rn(__dmul_rn((double) k, r), phase);
+	g.hi = __dadd_rn(g.lo, r);
+	g.c = __dadd_rn(g.hi, -1.0);
+	return g;
+}
+// pid after a sample whose c is `c`, as a double holding an exact non-negative integer
+__device__ __forceinline__ double rs_P(double c) { return fmax(0.0, ceil(c)); }
+
+template <bool IQ>
+__device__ __forceinline__ float rs_load(const float *in, unsigned long long idx) {
+	if (IQ) { const float2 v = ldg_stream_f2(reinterpret_cast<const float2 *>(in) + idx); return mag_exact(v.x, v.y); }
+	return ldg_stream_f1(in + idx);
+}
+
+// what sample k leaves in the bank (dsp.c:299-302)
+__device__ __forceinline__ double rs_t(const Geo &g, double Pk, double r, double v) {
+	if (Pk < g.hi && Pk > g.lo) return __dmul_rn(__dsub_rn(g.hi, Pk), v);
+	return __dmul_rn(r, v);
+}
+// does sample k emit an A pixel?  (dsp.c:288)
+__device__ __forceinline__ bool rs_isA(const Geo &g, double Pkm1) { return Pkm1 < g.lo && Pkm1 < g.c; }
+
+// -------------------------------------------------------------------------------------------------------------
+template <bool IQ>
+__global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ in, float *__restrict__ out,
+                                                      const RsBlock *__restrict__ blocks,
+                                                      const unsigned *__restrict__ tile_prefix, unsigned nblocks) {
+	__shared__ float s_mag[RS_HALO + RS_TILE];
+	__shared__ float s_out[RS_OUT_CAP];
+	__shared__ unsigned s_b;
+
+	const unsigned tile = blockIdx.x;
+	if (threadIdx.x == 0) {
+		unsigned lo = 0, hi = nblocks;
+		while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (tile_prefix[mid] <= tile) lo = mid; else hi = mid; }
+		s_b = lo;
+	}
+	__syncthreads();
+	const unsigned b = s_b;
+	const RsBlock B = blocks[b];
+	const unsigned s0 = (tile - tile_prefix[b]) * RS_TILE;
+	const unsigned s1 = min(s0 + (unsigned) RS_TILE, B.size);
+	const unsigned halo = min((unsigned) RS_HALO, s0);
+	const double r = B.r, phase = B.phase;
+
+	// stage magnitudes (demod fused): s_mag[RS_HALO + (k - s0)] = |x_k|
+	for (unsigned i = threadIdx.x; i < (s1 - s0) + halo; i += RS_THREADS) {
+		const unsigned k = s0 - halo + i;
+		s_mag[RS_HALO - halo + i] = rs_load<IQ>(in, B.in_start + k);
+	}
+	const double pbase_d = (s0 == 0) ? 0.0 : rs_P(rs_geo(s0 - 1, r, phase).c);
+	const double pend_d = rs_P(rs_geo(s1 - 1, r, phase).c);
+	const unsigned pbase = (unsigned) pbase_d;
+	const unsigned pend = (unsigned) pend_d;
+	const bool staged = (pend - pbase) <= (unsigned) RS_OUT_CAP;
+	float *gout = out + B.out_start;
+	__syncthreads();
+
+	for (unsigned k = s0 + threadIdx.x; k < s1; k += RS_THREADS) {
+		const Geo g = rs_geo(k, r, phase);
+		const double Pk = rs_P(g.c);
+		const double Pkm1 = (k == 0) ? 0.0 : rs_P(rs_geo(k - 1, r, phase).c);
+		const float vf = s_mag[RS_HALO + (k - s0)];
+		const double v = (double) vf;
+		unsigned p = (unsigned) Pkm1;
+		const unsigned pstop = (unsigned) Pk;
+		if (rs_isA(g, Pkm1)) {
+			// bank = t_L + ... + t_{k-1}, L = latest earlier sample that emitted an A pixel
+			long long L = (long long) k - 1;
+			while (L >= 0) {
+				const Geo gl = rs_geo((unsigned) L, r, phase);
+				const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, r, phase).c);
+				if (rs_isA(gl, Plm1)) break;
+				L--;
+			}
+			if (L >= 0) {
+				double bank = 0.0;
+				for (unsigned j = (unsigned) L; j < k; j++) {
+					const Geo gj = rs_geo(j, r, phase);
+					const float vj = (j + RS_HALO >= s0) ? s_mag[RS_HALO + j - s0] : rs_load<IQ>(in, B.in_start + j);
+					bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) vj));
+				}
+				const double w = __dadd_rn(__dsub_rn(1.0, g.lo), Pkm1);
+				const float px = __double2float_rn(__dadd_rn(bank, __dmul_rn(v, w)));
+				if (staged) s_out[p - pbase] = px; else if (p < B.n_out) gout[p] = px;
+			}   // else: the bank reaches past the block start -> rs_fixup writes this pixel
+			p++;
+		}
+		for (; p < pstop; p++) {
+			if (staged) s_out[p - pbase] = vf; else if (p < B.n_out) gout[p] = vf;
+		}
+	}
+	if (!staged) return;
+	__syncthreads();
+	const unsigned pe = min(pend, B.n_out);
+	for (unsigned q = pbase + threadIdx.x; q < pe; q += RS_THREADS) gout[q] = s_out[q - pbase];
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// One CTA.  Resolves the per-block quantities that cross block boundaries (see header comment).
+template <bool IQ>
+__global__ void __launch_bounds__(256) rs_fixup(const float *__restrict__ in, float *__restrict__ out,
+                                                const RsBlock *__restrict__ blocks, unsigned nblocks,
+                                                double *__restrict__ bank_in /* nblocks+1 */, int *__restrict__ has_a,
+                                                double *contrib_state) {
+	// 1. per block: bank left at the end of the block, if the block contains an A sample
+	for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x) {
+		const RsBlock B = blocks[b];
+		long long L = (long long) B.size - 1;
+		while (L >= 0) {
+			const Geo gl = rs_geo((unsigned) L, B.r, B.phase);
+			const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, B.r, B.phase).c);
+			if (rs_isA(gl, Plm1)) break;
+			L--;
+		}
+		if (L >= 0) {
+			double bank = 0.0;
+			for (unsigned j = (unsigned) L; j < B.size; j++) {
+				const Geo gj = rs_geo(j, B.r, B.phase);
+				bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), B.r, (double) rs_load<IQ>(in, B.in_start + j)));
+			}
+			bank_in[b + 1] = bank;
+			has_a[b] = 1;
+		} else has_a[b] = 0;
+	}
+	if (threadIdx.x == 0) bank_in[0] = *contrib_state;
+	__syncthreads();
+	// 2. blocks without any A sample pass the incoming bank through (serial, practically never taken)
+	if (threadIdx.x == 0) {
+		for (unsigned b = 0; b < nblocks; b++) {
+			if (has_a[b]) continue;
+			const RsBlock B = blocks[b];
+			double bank = bank_in[b];
+			for (unsigned j = 0; j < B.size; j++) {
+				const Geo gj = rs_geo(j, B.r, B.phase);
+				bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), B.r, (double) rs_load<IQ>(in, B.in_start + j)));
+			}
+			bank_in[b + 1] = bank;
+		}
+		*contrib_state = bank_in[nblocks];
+	}
+	__syncthreads();
+	// 3. first A pixel of every block, and slots the reference's loop never writes
+	for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x) {
+		const RsBlock B = blocks[b];
+		double bank = bank_in[b];
+		for (unsigned k = 0; k < B.size; k++) {
+			const Geo g = rs_geo(k, B.r, B.phase);
+			const double Pkm1 = (k == 0) ? 0.0 : rs_P(rs_geo(k - 1, B.r, B.phase).c);
+			const double v = (double) rs_load<IQ>(in, B.in_start + k);
+			if (rs_isA(g, Pkm1)) {
+				const double w = __dadd_rn(__dsub_rn(1.0, g.lo), Pkm1);
+				const unsigned p = (unsigned) Pkm1;
+				if (p < B.n_out) out[B.out_start + p] = __double2float_rn(__dadd_rn(bank, __dmul_rn(v, w)));
+				break;
+			}
+			bank = __dadd_rn(bank, rs_t(g, rs_P(g.c), B.r, v));
+		}
+		const unsigned emitted = (unsigned) rs_P(rs_geo(B.size - 1, B.r, B.phase).c);
+		for (unsigned p = emitted; p < B.n_out; p++) out[B.out_start + p] = 0.0f;   // stale in the reference
+	}
+}
+
+// nearest-neighbour mode (dsp.c:274-276): out[p] = x[(size*p)/output_samples]
+template <bool IQ>
+__global__ void __launch_bounds__(256) rs_nearest(const float *__restrict__ in, float *__restrict__ out,
+                                                  const RsBlock *__restrict__ blocks) {
+	const RsBlock B = blocks[blockIdx.y];
+	for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < B.n_out; p += gridDim.x * blockDim.x) {
+		const unsigned long long src = ((unsigned long long) B.size * p) / B.n_out;
+		out[B.out_start + p] = rs_load<IQ>(in, B.in_start + src);
+	}
+}
+
+__global__ void __launch_bounds__(256) demod_kernel(const float2 *__restrict__ iq, float *__restrict__ out, unsigned long long pairs) {
+	const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+		const float2 v = ldg_stream_f2(iq + i);
+		out[i] = mag_exact(v.x, v.y);
+	}
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+struct tsdrgpu_resampler {
+	tsdrgpu_ctx_t *ctx;
+	double offset;             // host: data-independent phase state (dsp_resample_t.offset)
+	double *d_contrib;         // device: dsp_resample_t.contrib
+	// descriptor staging: pinned ring + device copies, one slot per in-flight run
+	static constexpr int SLOTS = 4;
+	void *h_desc[SLOTS]; void *d_desc[SLOTS]; size_t desc_bytes[SLOTS]; cudaEvent_t ev[SLOTS]; int next;
+	double *d_bank; int *d_has_a; size_t bank_cap;
+};
+
+extern "C" {
+
+int tsdrgpu_am_demod(tsdrgpu_ctx_t *ctx, void *stream, const float *d_iq, uint64_t pairs, float *d_out) {
+	BIND(ctx);
+	if (pairs == 0) return TSDRGPU_OK;
+	ARG_TRY(ctx, d_iq != NULL && d_out != NULL);
+	const unsigned long long want = (pairs + 255) / 256;
+	const unsigned grid = (unsigned) (want < (unsigned long long) ctx->sm_count * 16 ? want : (unsigned long long) ctx->sm_count * 16);
+	demod_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(reinterpret_cast<const float2 *>(d_iq), d_out, pairs);
+	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_resampler_create(tsdrgpu_ctx_t *ctx, tsdrgpu_resampler_t **out) {
+	BIND(ctx); ARG_TRY(ctx, out != NULL);
+	tsdrgpu_resampler *r = new tsdrgpu_resampler();
+	memset(r, 0, sizeof(*r));
+	r->ctx = ctx;
+	CU_TRY(ctx, cudaMalloc(&r->d_contrib, sizeof(double)));
+	CU_TRY(ctx, cudaMemset(r->d_contrib, 0, sizeof(double)));
+	for (int i = 0; i < tsdrgpu_resampler::SLOTS; i++) CU_TRY(ctx, cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming));
+	*out = r;
+	return TSDRGPU_OK;
+}
+
+void tsdrgpu_resampler_destroy(tsdrgpu_resampler_t *r) {
+	if (!r) return;
+	cudaSetDevice(r->ctx->device);
+	cudaDeviceSynchronize();
+	cudaFree(r->d_contrib);
+	for (int i = 0; i < tsdrgpu_resampler::SLOTS; i++) {
+		if (r->h_desc[i]) cudaFreeHost(r->h_desc[i]);
+		if (r->d_desc[i]) cudaFree(r->d_desc[i]);
+		cudaEventDestroy(r->ev[i]);
+	}
+	if (r->d_bank) cudaFree(r->d_bank);
+	if (r->d_has_a) cudaFree(r->d_has_a);
+	delete r;
+}
+
+int tsdrgpu_resampler_reset(tsdrgpu_resampler_t *r, void *stream) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, r != NULL);
+	BIND(r->ctx);
+	r->offset = 0.0;
+	CU_TRY(r->ctx, cudaMemsetAsync(r->d_contrib, 0, sizeof(double), (cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_resampler_get_state(tsdrgpu_resampler_t *r, void *stream, double *contrib, double *offset) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, r != NULL);
+	BIND(r->ctx);
+	if (contrib) {
+		CU_TRY(r->ctx, cudaMemcpyAsync(contrib, r->d_contrib, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+		CU_TRY(r->ctx, cudaStreamSynchronize((cudaStream_t) stream));
+	}
+	if (offset) *offset = r->offset;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_resampler_set_state(tsdrgpu_resampler_t *r, void *stream, double contrib, double offset) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, r != NULL);
+	BIND(r->ctx);
+	r->offset = offset;
+	CU_TRY(r->ctx, cudaMemcpyAsync(r->d_contrib, &contrib, sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t) stream));
+	CU_TRY(r->ctx, cudaStreamSynchronize((cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+
+uint64_t tsdrgpu_resampler_plan(tsdrgpu_resampler_t *r, const uint32_t *block_sizes, uint32_t uniform_block,
+                                uint32_t nblocks, double upsample_by, double downsample_by) {
+	if (!r) return 0;
+	double off = r->offset;
+	const uint64_t n = tsdrgpu_plan_resample(&off, block_sizes, uniform_block, nblocks, upsample_by, downsample_by, NULL);
+	return n == UINT64_MAX ? 0 : n;
+}
+
+int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_in, int in_is_iq,
+                          const uint32_t *block_sizes, uint32_t uniform_block, uint32_t nblocks,
+                          double upsample_by, double downsample_by, int nearest,
+                          float *d_out, uint64_t out_capacity, uint64_t *h_n_out) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, r != NULL);
+	tsdrgpu_ctx_t *ctx = r->ctx;
+	BIND(ctx);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	if (h_n_out) *h_n_out = 0;
+	if (nblocks == 0) return TSDRGPU_OK;
+	ARG_TRY(ctx, d_in != NULL && d_out != NULL);
+	ARG_TRY(ctx, upsample_by > 0 && downsample_by > 0);
+	ARG_TRY(ctx, nblocks <= 65535u);
+
+	// descriptor slot: [RsBlock x nblocks][tile_prefix x (nblocks+1)]
+	const size_t need = sizeof(tsdrgpu_rs_block_t) * nblocks + sizeof(unsigned) * (nblocks + 1);
+	const int slot = r->next; r->next = (r->next + 1) % tsdrgpu_resampler::SLOTS;
+	CU_TRY(ctx, cudaEventSynchronize(r->ev[slot]));
+	if (r->desc_bytes[slot] < need) {
+		if (r->h_desc[slot]) CU_TRY(ctx, cudaFreeHost(r->h_desc[slot]));
+		if (r->d_desc[slot]) CU_TRY(ctx, cudaFree(r->d_desc[slot]));
+		const size_t cap = need * 2;
+		CU_TRY(ctx, cudaMallocHost(&r->h_desc[slot], cap));
+		CU_TRY(ctx, cudaMalloc(&r->d_desc[slot], cap));
+		r->desc_bytes[slot] = cap;
+	}
+	tsdrgpu_rs_block_t *hb = (tsdrgpu_rs_block_t *) r->h_desc[slot];
+	unsigned *hp = (unsigned *) (hb + nblocks);
+
+	double off = r->offset;
+	const uint64_t total = tsdrgpu_plan_resample(&off, block_sizes, uniform_block, nblocks, upsample_by, downsample_by, hb);
+	if (total == UINT64_MAX)
+		return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "a block would produce no pixel (the reference asserts here, extbuffer.c:48)", cudaSuccess, __FILE__, __LINE__);
+	if (total > out_capacity)
+		return tsdrgpu_fail(ctx, TSDRGPU_ECAPACITY, "resampler output buffer too small", cudaSuccess, __FILE__, __LINE__);
+	unsigned tiles = 0, max_out = 0;
+	for (uint32_t b = 0; b < nblocks; b++) {
+		hp[b] = tiles;
+		tiles += (hb[b].size + RS_TILE - 1) / RS_TILE;
+		if (hb[b].n_out > max_out) max_out = hb[b].n_out;
+	}
+	hp[nblocks] = tiles;
+	CU_TRY(ctx, cudaMemcpyAsync(r->d_desc[slot], r->h_desc[slot], need, cudaMemcpyHostToDevice, stream));
+	CU_TRY(ctx, cudaEventRecord(r->ev[slot], stream));
+	const RsBlock *db = (const RsBlock *) r->d_desc[slot];
+	const unsigned *dp = (const unsigned *) (db + nblocks);
+
+	if (nearest) {
+		dim3 grid((max_out + 1023) / 1024, nblocks);
+		if (in_is_iq) rs_nearest<true><<<grid, 256, 0, stream>>>(d_in, d_out, db);
+		else rs_nearest<false><<<grid, 256, 0, stream>>>(d_in, d_out, db);
+		LAUNCH_CHECK(ctx);
+	} else {
+		if (r->bank_cap < (size_t) nblocks + 1) {
+			if (r->d_bank) { CU_TRY(ctx, cudaStreamSynchronize(stream)); CU_TRY(ctx, cudaFree(r->d_bank)); CU_TRY(ctx, cudaFree(r->d_has_a)); }
+			r->bank_cap = (size_t) nblocks * 2 + 2;
+			CU_TRY(ctx, cudaMalloc(&r->d_bank, sizeof(double) * r->bank_cap));
+			CU_TRY(ctx, cudaMalloc(&r->d_has_a, sizeof(int) * r->bank_cap));
+		}
+		if (in_is_iq) rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks);
+		else rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks);
+		LAUNCH_CHECK(ctx);
+		if (in_is_iq) rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib);
+		else rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib);
+		LAUNCH_CHECK(ctx);
+	}
+	r->offset = off;
+	if (h_n_out) *h_n_out = total;
+	return TSDRGPU_OK;
+}
+
+}  // extern "C"

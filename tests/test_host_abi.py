@@ -1,0 +1,78 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads without a GPU, exports every symbol the
+header declares, fails loudly (no fallback) when no device exists, and its host-side scalar planning agrees with the
+oracle bit for bit."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tempestsdr_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols(path):
+    txt = open(path).read()
+    return sorted(set(re.findall(r"\b(tsdrgpu_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.lib()
+    declared = header_symbols(os.path.join(ROOT, "include", "tsdrgpu.h"))
+    assert len(declared) > 40
+    for s in declared:
+        assert hasattr(lib, s), f"libtsdrgpu.so does not export {s}"
+    assert sorted(_native.DECLARED_SYMBOLS) == declared, "python binding table out of sync with the header"
+
+
+def test_no_silent_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _native.lib()
+    assert lib.tsdrgpu_device_count() == 0
+    h = C.c_void_p()
+    rc = lib.tsdrgpu_create(C.byref(h), 0)
+    assert rc == -1 and not h.value                      # TSDRGPU_ENODEVICE
+    assert b"no CPU fallback" in lib.tsdrgpu_last_error(None)
+    from tempestsdr_b200 import api
+    with pytest.raises(api.TsdrGpuError):
+        api.Context(0)
+
+
+@pytest.mark.parametrize("fs,h,fv", [(8_000_000, 525, 60.0), (25_000_000, 1125, 60.0), (50_000_000, 1125, 60.0),
+                                     (100_000_000, 2250, 60.0), (1_000_000, 100, 50.0), (2_400_000, 313, 59.94)])
+def test_host_geometry_and_resample_plan(fs, h, fv):
+    lib = _native.lib()
+    P = orc.port()
+    w, pr, pt = C.c_int(0), C.c_double(0), C.c_double(0)
+    lib.tsdrgpu_geometry(fs, h, fv, C.byref(w), C.byref(pr), C.byref(pt))
+    assert (w.value, pr.value, pt.value) == P.geometry(fs, h, fv)
+    # the phase recurrence over 200 decimator blocks equals the oracle's resampler state block by block
+    block = int(0.1 * fs / fv)
+    up = w.value * h * fv
+    rs = P.resampler()
+    off = C.c_double(0.0)
+    x = np.zeros(block, np.float32)
+    for k in range(200):
+        n = lib.tsdrgpu_plan_resample(C.byref(off), None, block, 1, up, float(fs), None)
+        assert n == rs.run(x, up, float(fs)).size
+        assert off.value == rs.state[1]
+    # and in one call of 200 blocks
+    off2 = C.c_double(0.0)
+    blocks = (C.c_byte * (40 * 200))()
+    total = lib.tsdrgpu_plan_resample(C.byref(off2), None, block, 200, up, float(fs), blocks)
+    assert off2.value == off.value and total > 0
+    assert lib.tsdrgpu_plan_resample(C.byref(C.c_double(0.0)), None, 1, 1, 0.1, 1.0, None) == 2**64 - 1
+
+
+def test_gauss_taps_match_oracle():
+    lib = _native.lib()
+    taps = (C.c_float * 5)()
+    lib.tsdrgpu_gauss_taps(C.byref(taps))
+    imp = np.zeros(11, np.float32); imp[5] = 1.0
+    blurred = orc.port().gaussianblur(imp)
+    assert np.array_equal(np.array(taps[:], np.float32)[::-1].view(np.uint32), blurred[3:8].view(np.uint32))
