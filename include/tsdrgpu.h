@@ -153,6 +153,13 @@ TSDRGPU_API int  tsdrgpu_framestage_run(tsdrgpu_framestage_t *fs, void *stream, 
                                         int width, int height, float motionblur, float lowpasscoeff, unsigned flags,
                                         float *d_frames_out, tsdrgpu_frame_result_t *h_results);
 
+/* same, but never synchronises: h_results_pinned (page-locked, nframes entries, may be NULL) is valid once the
+ * stream has passed this call; h_autogain_report (nframes ints, may be NULL) is filled on return. */
+TSDRGPU_API int  tsdrgpu_framestage_run_async(tsdrgpu_framestage_t *fs, void *stream, const float *d_frames_in, int nframes,
+                                              int width, int height, float motionblur, float lowpasscoeff, unsigned flags,
+                                              float *d_frames_out, tsdrgpu_frame_result_t *h_results_pinned,
+                                              int32_t *h_autogain_report);
+
 /* stage-level entry points (same arithmetic as the kernels inside tsdrgpu_framestage_run) */
 TSDRGPU_API int tsdrgpu_autogain(tsdrgpu_ctx_t *ctx, void *stream, float *h_lastmax, float *h_lastmin, float *h_snr,
                                  int n, const float *d_in, float *d_out, float norm);        /* synchronises */
@@ -190,6 +197,9 @@ TSDRGPU_API void tsdrgpu_frd_windows(uint32_t samplerate, int *frame_min, int *f
  * them out (then the call synchronises).  *calls = captures accumulated so far. */
 TSDRGPU_API int  tsdrgpu_frd_run(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
                                  double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls);
+/* same without the final synchronisation; the h_* buffers must be page-locked */
+TSDRGPU_API int  tsdrgpu_frd_run_async(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
+                                       double *h_frame_plot_pinned, int frame_cap, double *h_line_plot_pinned, int line_cap, uint64_t *calls);
 TSDRGPU_API int  tsdrgpu_accumulate(tsdrgpu_ctx_t *ctx, void *stream, double *d_out, uint64_t calls,
                                     const float *d_in_complex, int startid, int length);
 
@@ -211,6 +221,57 @@ TSDRGPU_API int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream, co
                                             int best_offset_floats, float *d_spectrum);
 TSDRGPU_API int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream, const float *d_gathered, int nhops, uint32_t n,
                                             int residue, float *d_out_residue);
+
+/* ---------------------------------------------------------------------------- a1, a3, a5, a16, a17  streaming pipeline
+ * replaces the body of process() (TSDRLibrary.c:264-298), decimatingthread / postprocessingthread /
+ * videodecodingthread (TSDRLibrary.c:300-418) with their three rings (circbuff.c), dsp_dropped_compensation_*
+ * (dsp.c:313-368) and the frame-rate detector's capture loop (frameratedetector.c:128-187, 215-230).
+ * HOST buffers in (the plugin's), HOST frame / plot buffers out (valid during the callback only), callbacks on an
+ * internal delivery thread.  The C host library (tempestsdr_b200/host) forwards the reference's process() here.
+ */
+typedef struct tsdrgpu_pipeline tsdrgpu_pipeline_t;
+
+enum {                                   /* indices of params_int: TSDRLibrary.h:32-41 */
+	TSDRGPU_PARAM_INT_AUTOSHIFT = 0, TSDRGPU_PARAM_INT_FRAMERATE_PLL = 1, TSDRGPU_PARAM_AUTOCORR_PLOTS_RESET = 2,
+	TSDRGPU_PARAM_AUTOCORR_PLOTS_OFF = 3, TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION = 4,
+	TSDRGPU_PARAM_NEAREST_NEIGHBOUR_RESAMPLING = 5, TSDRGPU_PARAM_LOW_PASS_BEFORE_SYNC = 6,
+	TSDRGPU_PARAM_AUTOGAIN_AFTER_PROCESSING = 7, TSDRGPU_PARAM_AUTOCORR_DUMP = 8
+};
+
+typedef struct {
+	uint32_t samplerate;                 /* tsdrplugin_getsamplerate() */
+	int      height;                     /* tsdr_setresolution */
+	double   refreshrate;
+	float    motionblur;                 /* tsdr_motionblur */
+	uint32_t params_int[9];              /* tsdr_setparameter_int */
+	int      batch_frames;               /* frames per frame-stage launch (>= 1; 1 = lowest latency) */
+	int      batch_blocks;               /* decimator blocks (0.1 frame each) per resampler launch (>= 1; default 10) */
+	int      block_when_busy;            /* 1: wait for the frame callback instead of dropping a batch */
+} tsdrgpu_pipeline_config_t;
+
+typedef struct {
+	uint64_t samples_in, samples_dropped_upstream, samples_resampled;
+	uint64_t frames_processed, frames_delivered, frames_dropped, captures, plots_delivered;
+	uint64_t h2d_bytes, d2h_bytes, gpu_launches;
+} tsdrgpu_pipeline_stats_t;
+
+typedef void (*tsdrgpu_frame_cb)(float *buf, int width, int height, void *user);                  /* tsdr_readasync_function */
+typedef void (*tsdrgpu_value_cb)(int value_id, double arg0, double arg1, void *user);             /* tsdr_value_changed_callback */
+typedef void (*tsdrgpu_plot_cb)(int plot_id, int offset, double *values, int size, uint32_t samplerate, void *user);
+
+TSDRGPU_API int  tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t *cfg, tsdrgpu_frame_cb frame_cb,
+                                         tsdrgpu_value_cb value_cb, tsdrgpu_plot_cb plot_cb, void *user, tsdrgpu_pipeline_t **p);
+TSDRGPU_API void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p);
+/* == process(buf, items_count, ctx, samples_dropped): returns once h_iq has been read (it may then be reused) */
+TSDRGPU_API int  tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped);
+TSDRGPU_API int  tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p);            /* waits for the GPU and for every pending callback */
+TSDRGPU_API int  tsdrgpu_pipeline_set_param_int(tsdrgpu_pipeline_t *p, int id, uint32_t value);
+TSDRGPU_API int  tsdrgpu_pipeline_set_resolution(tsdrgpu_pipeline_t *p, int height, double refreshrate);
+TSDRGPU_API int  tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate);
+TSDRGPU_API int  tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff);
+TSDRGPU_API int  tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels);   /* tsdr_sync: syncoffset += pixels */
+TSDRGPU_API int  tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate);
+TSDRGPU_API int  tsdrgpu_pipeline_stats(tsdrgpu_pipeline_t *p, tsdrgpu_pipeline_stats_t *out);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,7 @@ uint32_t refh_resample_run(void *h, const float *in, uint32_t size, double upsam
 	{
 		const double r_ = upsample_by / downsample_by;
 		const uint32_t want = (uint32_t) (int) ((size - r->res.offset) * r_);
+		if (want == 0) return 0;   /* the reference would abort in extbuffer_preparetohandle's assert(size > 0) */
 		if (want > 0 && r->out.buffer_max_size >= want && r->out.buffer_max_size <= (want << 1)) {
 			/* no realloc will happen inside; make sure one element of slack exists */
 			r->out.buffer = (float *) realloc(r->out.buffer, sizeof(float) * ((size_t) r->out.buffer_max_size + 8));

@@ -22,6 +22,23 @@ class FrameResult(C.Structure):
                 ("autogain_report", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PipelineConfig(C.Structure):
+    """tsdrgpu_pipeline_config_t"""
+    _fields_ = [("samplerate", C.c_uint32), ("height", C.c_int), ("refreshrate", C.c_double), ("motionblur", C.c_float),
+                ("params_int", C.c_uint32 * 9), ("batch_frames", C.c_int), ("batch_blocks", C.c_int), ("block_when_busy", C.c_int)]
+
+
+class PipelineStats(C.Structure):
+    """tsdrgpu_pipeline_stats_t"""
+    _fields_ = [(n, C.c_uint64) for n in ("samples_in", "samples_dropped_upstream", "samples_resampled", "frames_processed",
+                                          "frames_delivered", "frames_dropped", "captures", "plots_delivered",
+                                          "h2d_bytes", "d2h_bytes", "gpu_launches")]
+
+
+FRAME_CB = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p)
+VALUE_CB = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_double, C.c_void_p)
+PLOT_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_uint32, C.c_void_p)
+
 FS_AUTOSHIFT, FS_LOWPASS_BEFORE_SYNC, FS_AUTOGAIN_AFTER_PROC, FS_SUPERRESOLUTION, FS_COMPUTE_SNR = 1, 2, 4, 8, 16
 
 _SIGS = {
@@ -58,6 +75,8 @@ _SIGS = {
     "tsdrgpu_framestage_reset": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_framestage_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                          C.c_uint, C.c_void_p, C.POINTER(FrameResult)]),
+    "tsdrgpu_framestage_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                               C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tsdrgpu_autogain": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_float]),
     "tsdrgpu_timelowpass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
@@ -75,6 +94,8 @@ _SIGS = {
     "tsdrgpu_frd_windows": (None, [C.c_uint32] + [C.POINTER(C.c_int)] * 4),
     "tsdrgpu_frd_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_frd_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "tsdrgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]),
     "tsdrgpu_complex_to_abs_diff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "tsdrgpu_superb_bestfit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
@@ -82,6 +103,17 @@ _SIGS = {
                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tsdrgpu_superb_hop_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tsdrgpu_superb_residue_ifft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
+    "tsdrgpu_pipeline_create": (C.c_int, [C.c_void_p, C.POINTER(PipelineConfig), FRAME_CB, VALUE_CB, PLOT_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_pipeline_destroy": (None, [C.c_void_p]),
+    "tsdrgpu_pipeline_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]),
+    "tsdrgpu_pipeline_flush": (C.c_int, [C.c_void_p]),
+    "tsdrgpu_pipeline_set_param_int": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
+    "tsdrgpu_pipeline_set_resolution": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "tsdrgpu_pipeline_set_samplerate": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "tsdrgpu_pipeline_set_motionblur": (C.c_int, [C.c_void_p, C.c_float]),
+    "tsdrgpu_pipeline_sync": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsdrgpu_pipeline_get_geometry": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "tsdrgpu_pipeline_stats": (C.c_int, [C.c_void_p, C.POINTER(PipelineStats)]),
 }
 
 #: every symbol include/tsdrgpu.h declares (tests check the built library exports all of them)

@@ -468,8 +468,8 @@ void tsdrgpu_frd_windows(uint32_t samplerate, int *frame_min, int *frame_max, in
 	*line_min = (int) (samplerate / (double) (1500 * 87));
 }
 
-int tsdrgpu_frd_run(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, const float *d_capture, uint32_t size,
-                    double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls) {
+static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, const float *d_capture, uint32_t size,
+                        double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls, bool synchronise) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
 	tsdrgpu_ctx_t *ctx = f->ctx;
 	BIND(ctx); ARG_TRY(ctx, d_capture != NULL && size > 0);
@@ -501,9 +501,18 @@ int tsdrgpu_frd_run(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, const 
 	if (h_frame_plot || h_line_plot) {
 		if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
 		if (h_line_plot) CU_TRY(ctx, cudaMemcpyAsync(h_line_plot, f->d_p2, sizeof(double) * (size_t) (llen < line_cap ? llen : line_cap), cudaMemcpyDeviceToHost, stream));
-		CU_TRY(ctx, cudaStreamSynchronize(stream));
+		if (synchronise) CU_TRY(ctx, cudaStreamSynchronize(stream));
 	}
 	return TSDRGPU_OK;
+}
+
+int tsdrgpu_frd_run(tsdrgpu_frd_t *f, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
+                    double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls) {
+	return frd_run_impl(f, stream, samplerate, d_capture, size, h_frame_plot, frame_cap, h_line_plot, line_cap, calls, true);
+}
+int tsdrgpu_frd_run_async(tsdrgpu_frd_t *f, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
+                          double *h_frame_plot_pinned, int frame_cap, double *h_line_plot_pinned, int line_cap, uint64_t *calls) {
+	return frd_run_impl(f, stream, samplerate, d_capture, size, h_frame_plot_pinned, frame_cap, h_line_plot_pinned, line_cap, calls, false);
 }
 
 // ---- superbandwidth ----------------------------------------------------------------------------------------------

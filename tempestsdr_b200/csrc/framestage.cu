@@ -582,8 +582,9 @@ int tsdrgpu_framestage_reset(tsdrgpu_framestage_t *fs, void *stream) {
 	return TSDRGPU_OK;
 }
 
-int tsdrgpu_framestage_run(tsdrgpu_framestage_t *fs, void *stream_, const float *d_in, int nframes, int w, int h,
-                           float motionblur, float lowpasscoeff, unsigned flags, float *d_out, tsdrgpu_frame_result_t *h_results) {
+static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const float *d_in, int nframes, int w, int h,
+                           float motionblur, float lowpasscoeff, unsigned flags, float *d_out, tsdrgpu_frame_result_t *h_results,
+                           bool synchronise, int32_t *h_report) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
 	tsdrgpu_ctx_t *ctx = fs->ctx;
 	BIND(ctx);
@@ -676,17 +677,26 @@ int tsdrgpu_framestage_run(tsdrgpu_framestage_t *fs, void *stream_, const float 
 			fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results); LAUNCH_CHECK(ctx);
 		}
 	}
-	if (h_results) {
-		CU_TRY(ctx, cudaMemcpyAsync(h_results, fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes, cudaMemcpyDeviceToHost, stream));
-		CU_TRY(ctx, cudaStreamSynchronize(stream));
-		for (int f = 0; f < nframes; f++) {
-			h_results[f].autogain_report = 0;
-			if (fs->runs++ > 5) { fs->runs = 0; h_results[f].autogain_report = 1; }     // dsp.c:231-235
-		}
-	} else {
-		for (int f = 0; f < nframes; f++) if (fs->runs++ > 5) fs->runs = 0;
+	if (h_results) CU_TRY(ctx, cudaMemcpyAsync(h_results, fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes, cudaMemcpyDeviceToHost, stream));
+	if (h_results && synchronise) CU_TRY(ctx, cudaStreamSynchronize(stream));
+	for (int f = 0; f < nframes; f++) {
+		int report = 0;
+		if (fs->runs++ > 5) { fs->runs = 0; report = 1; }                              // dsp.c:231-235
+		if (h_report) h_report[f] = report;
+		if (h_results && synchronise) h_results[f].autogain_report = report;
 	}
 	return TSDRGPU_OK;
+}
+
+int tsdrgpu_framestage_run(tsdrgpu_framestage_t *fs, void *stream, const float *d_in, int nframes, int w, int h,
+                           float motionblur, float lowpasscoeff, unsigned flags, float *d_out, tsdrgpu_frame_result_t *h_results) {
+	return framestage_run_impl(fs, stream, d_in, nframes, w, h, motionblur, lowpasscoeff, flags, d_out, h_results, true, NULL);
+}
+
+int tsdrgpu_framestage_run_async(tsdrgpu_framestage_t *fs, void *stream, const float *d_in, int nframes, int w, int h,
+                                 float motionblur, float lowpasscoeff, unsigned flags, float *d_out,
+                                 tsdrgpu_frame_result_t *h_results_pinned, int32_t *h_autogain_report) {
+	return framestage_run_impl(fs, stream, d_in, nframes, w, h, motionblur, lowpasscoeff, flags, d_out, h_results_pinned, false, h_autogain_report);
 }
 
 // ---- stage-level entry points -------------------------------------------------------------------------------

@@ -1,0 +1,519 @@
+// pipeline.cu -- a1, a3, a5, a16, a17: the streaming glue between the plugin callback and the frame callback.
+//
+// Replaces the body of process() (TSDRLibrary.c:264-298), decimatingthread / postprocessingthread /
+// videodecodingthread (TSDRLibrary.c:300-418), the three CircBuff rings between them (circbuff.c) and the
+// frame-rate detector thread's capture loop (frameratedetector.c:128-187, 215-230).  Host buffers in, host frame
+// and plot buffers out: this is the object the C host library (tempestsdr_b200/host/TSDRLibrary.c) drives from
+// the reference's own process() callback, and the one bench.py times end to end.
+//
+// Data movement per IQ block: one H2D copy of the plugin's buffer (pinned if the pointer could be registered),
+// everything else stays in HBM: IQ -> (fused demod+resample) -> pixel stream -> (frame stage, batches of frames)
+// -> one D2H copy of the finished frames into page-locked slots -> frame callback on the delivery thread.
+// The reference's rings, which copy every sample 2x per stage under a mutex, do not exist here; what is kept
+// is their observable behaviour: whole-block dropping with frame-aligned resynchronisation (dsp.c:313-368),
+// purge of the autocorrelation capture on any drop (frameratedetector.c:221-224).
+//
+// Ordering differences to the (timing-dependent) threaded reference, both deterministic here:
+//   * geometry changes made by the PLL take effect at the next batch boundary;
+//   * tsdr_sync offsets are applied between batches of decimator blocks rather than between single blocks.
+#include "common.cuh"
+#include <math.h>
+#include <pthread.h>
+#include <deque>
+#include <vector>
+
+struct tsdrgpu_frd;
+struct tsdrgpu_resampler;
+struct tsdrgpu_framestage;
+
+namespace {
+
+constexpr int PL_SLOTS = 4;
+
+struct FrameJob {
+	int kind;                 // 0 = frames, 1 = plots, 2 = barrier
+	int slot, nframes, w, h;
+	cudaEvent_t ev;
+	uint32_t samplerate;      // plots
+	int foff, flen, loff, llen; uint64_t calls; int reset_announce;
+};
+
+// block-aligned dropping, dsp.c:313-368 (integer bookkeeping, host side)
+struct DropComp {
+	int64_t difference = 0;
+	static uint64_t debt(int block, int dropped) { const uint64_t whole = (uint64_t) (dropped / block); return ((whole + 1) * block - dropped) % block; }
+	void shift_with(uint32_t block, int64_t syncoffset) {
+		if (syncoffset >= 0) difference -= syncoffset % block; else difference -= block + syncoffset % block;
+		if (difference < 0) difference = (int64_t) debt((int) block, (int) -difference);
+	}
+	bool will_drop_all(uint32_t size) const { return size <= difference; }
+	// returns elements forwarded; *skip = leading elements discarded.  accepted = downstream took the block
+	uint32_t add(uint32_t size, uint32_t block, bool accepted, uint32_t *skip) {
+		*skip = 0;
+		if (size <= difference) { difference -= size; *skip = size; return 0; }
+		if (accepted) { const uint32_t lead = (uint32_t) difference; difference = 0; *skip = lead; return size - lead; }
+		difference -= size % block;
+		if (difference < 0) difference = (int64_t) debt((int) block, (int) -difference);
+		return 0;
+	}
+};
+
+__global__ void pl_copy_f32(const float *__restrict__ src, float *__restrict__ dst, size_t n) {
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace
+
+struct tsdrgpu_pipeline {
+	tsdrgpu_ctx_t *ctx;
+	tsdrgpu_pipeline_config_t cfg;
+	tsdrgpu_frame_cb frame_cb; tsdrgpu_value_cb value_cb; tsdrgpu_plot_cb plot_cb; void *user;
+	cudaStream_t s_main, s_copy;
+	cudaEvent_t ev_h2d[2], ev_used[2]; int stage_slot;
+
+	// live geometry (set_internal_samplerate)
+	pthread_mutex_t geo_mu;
+	uint32_t samplerate; int height, width; double refreshrate, pixelrate, ptos;
+	float motionblur; volatile int syncoffset;
+	uint32_t params[9];
+
+	// stage 0: H2D staging of the plugin's buffer
+	float *d_stage[2]; size_t stage_cap[2];           // floats; double-buffered so H2D overlaps the kernels
+	std::vector<void *> registered;
+	// stage 1: decimator input (IQ pairs waiting for whole blocks)
+	float *d_decim; size_t decim_cap, decim_fill;     // pairs
+	DropComp dev_drop;
+	// stage 2: pixels waiting for whole frames
+	tsdrgpu_resampler *rs;
+	float *d_pix; size_t pix_cap, pix_read, pix_fill;
+	DropComp pix_drop;
+	// stage 3: frames
+	tsdrgpu_framestage *fs;
+	float *d_frames; size_t frames_cap;
+	float *h_frames[PL_SLOTS]; tsdrgpu_frame_result_t *h_results[PL_SLOTS]; int32_t *h_report[PL_SLOTS]; size_t slot_cap;
+	int slot_busy[PL_SLOTS];
+	// autocorrelation side path
+	tsdrgpu_frd *frd; float *d_capture; size_t cap_size, cap_fill; uint32_t cap_rate;
+	double *h_plot_frame[2], *h_plot_line[2]; size_t plot_cap; int plot_slot; int plot_busy[2];
+	// delivery
+	pthread_t thread; pthread_mutex_t mu; pthread_cond_t cv_job, cv_done;
+	std::deque<FrameJob> jobs; int stop; uint64_t submitted, delivered;
+	tsdrgpu_pipeline_stats_t stats;
+	int last_w, last_h;
+};
+
+extern "C" {
+int tsdrgpu_resampler_create(tsdrgpu_ctx_t *, tsdrgpu_resampler **);
+}
+
+static void geometry_locked(tsdrgpu_pipeline *p) {      // set_internal_samplerate, TSDRLibrary.c:540-550
+	double pr, pt; int w;
+	tsdrgpu_geometry(p->samplerate, p->height, p->refreshrate, &w, &pr, &pt);
+	p->width = w; p->pixelrate = pr;
+	if (p->samplerate != 0 && pr != 0) p->ptos = pt;
+}
+
+static void *delivery_main(void *arg) {
+	tsdrgpu_pipeline *p = (tsdrgpu_pipeline *) arg;
+	cudaSetDevice(p->ctx->device);
+	for (;;) {
+		pthread_mutex_lock(&p->mu);
+		while (p->jobs.empty() && !p->stop) pthread_cond_wait(&p->cv_job, &p->mu);
+		if (p->jobs.empty() && p->stop) { pthread_mutex_unlock(&p->mu); break; }
+		FrameJob j = p->jobs.front(); p->jobs.pop_front();
+		pthread_mutex_unlock(&p->mu);
+		cudaEventSynchronize(j.ev);
+		if (j.kind == 0) {
+			const size_t n = (size_t) j.w * j.h;
+			for (int f = 0; f < j.nframes; f++) {
+				const tsdrgpu_frame_result_t &r = p->h_results[j.slot][f];
+				// frameratepll's write-back (syncdetector.c:141-152): refreshrate moves, geometry follows
+				if (p->params[TSDRGPU_PARAM_INT_FRAMERATE_PLL] && r.x_vx != 0) {
+					const double diff = (r.pll_state == 0) ? r.x_vx * 0.00001 : r.avg_speed * 0.000001;
+					pthread_mutex_lock(&p->geo_mu);
+					p->refreshrate -= diff;
+					geometry_locked(p);
+					const double rr = p->refreshrate;
+					pthread_mutex_unlock(&p->geo_mu);
+					if (p->value_cb) p->value_cb(0 /* VALUE_ID_PLL_FRAMERATE */, rr, 0, p->user);
+				}
+				if (p->h_report[j.slot][f] && p->value_cb) p->value_cb(3 /* VALUE_ID_AUTOGAIN_VALUES */, r.lastmin, r.lastmax, p->user);
+				if (p->frame_cb) p->frame_cb(p->h_frames[j.slot] + f * n, j.w, j.h, p->user);
+			}
+			pthread_mutex_lock(&p->mu);
+			p->slot_busy[j.slot] = 0; p->stats.frames_delivered += j.nframes;
+			pthread_mutex_unlock(&p->mu);
+		} else if (j.kind == 1) {
+			if (j.reset_announce && p->value_cb) p->value_cb(1 /* VALUE_ID_AUTOCORRECT_RESET */, 0, 0, p->user);
+			if (p->plot_cb) {
+				p->plot_cb(0 /* PLOT_ID_FRAME */, j.foff, p->h_plot_frame[j.slot], j.flen, j.samplerate, p->user);
+				p->plot_cb(1 /* PLOT_ID_LINE */, j.loff, p->h_plot_line[j.slot], j.llen, j.samplerate, p->user);
+			}
+			if (p->value_cb) p->value_cb(2 /* VALUE_ID_AUTOCORRECT_FRAMES_COUNT */, 0, (double) j.calls, p->user);
+			pthread_mutex_lock(&p->mu);
+			p->plot_busy[j.slot] = 0; p->stats.plots_delivered++;
+			pthread_mutex_unlock(&p->mu);
+		}
+		cudaEventDestroy(j.ev);
+		pthread_mutex_lock(&p->mu);
+		p->delivered++;
+		pthread_cond_broadcast(&p->cv_done);
+		pthread_mutex_unlock(&p->mu);
+	}
+	return NULL;
+}
+
+static int submit(tsdrgpu_pipeline *p, FrameJob &j) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	CU_TRY(ctx, cudaEventCreateWithFlags(&j.ev, cudaEventDisableTiming));
+	CU_TRY(ctx, cudaEventRecord(j.ev, p->s_main));
+	pthread_mutex_lock(&p->mu);
+	p->jobs.push_back(j); p->submitted++;
+	pthread_cond_signal(&p->cv_job);
+	pthread_mutex_unlock(&p->mu);
+	return TSDRGPU_OK;
+}
+
+static int grow(tsdrgpu_ctx_t *ctx, cudaStream_t s, float **buf, size_t *cap, size_t need, size_t keep_floats) {
+	if (*cap >= need) return TSDRGPU_OK;
+	float *nb;
+	const size_t ncap = need + need / 2 + 1024;
+	CU_TRY(ctx, cudaMalloc(&nb, sizeof(float) * ncap));
+	if (*buf && keep_floats) CU_TRY(ctx, cudaMemcpyAsync(nb, *buf, sizeof(float) * keep_floats, cudaMemcpyDeviceToDevice, s));
+	CU_TRY(ctx, cudaStreamSynchronize(s));
+	if (*buf) CU_TRY(ctx, cudaFree(*buf));
+	*buf = nb; *cap = ncap;
+	return TSDRGPU_OK;
+}
+
+// ---- autocorrelation side path: append demodulated samples, fire a capture when full (frameratedetector.c:128-230)
+static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, bool dropped) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	if (p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_OFF]) return TSDRGPU_OK;
+	if (dropped) { p->cap_fill = 0; return TSDRGPU_OK; }              // cb_purge on any drop
+	if (p->cap_rate != p->samplerate) { p->cap_rate = p->samplerate; p->cap_fill = 0; }
+	const size_t want = tsdrgpu_frd_capture_size(p->samplerate);
+	if (want == 0) return TSDRGPU_OK;
+	int rc;
+	if (p->cap_size < want) { if ((rc = grow(ctx, p->s_main, &p->d_capture, &p->cap_size, want, p->cap_fill))) return rc; }
+	uint64_t done = 0;
+	while (done < pairs) {
+		const uint64_t take = (want - p->cap_fill) < (pairs - done) ? (want - p->cap_fill) : (pairs - done);
+		if ((rc = tsdrgpu_am_demod(ctx, p->s_main, d_iq + 2 * done, take, p->d_capture + p->cap_fill))) return rc;
+		p->cap_fill += take; done += take;
+		if (p->cap_fill == want) {
+			p->cap_fill = 0;
+			int reset_announce = 0;
+			if (p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_RESET]) {          // frameratedetector.c:97-104
+				reset_announce = (p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_RESET] == 1);
+				p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_RESET] = 0;
+				tsdrgpu_frd_reset(p->frd);
+			}
+			int fmin, fmax, lmin, lmax;
+			tsdrgpu_frd_windows(p->samplerate, &fmin, &fmax, &lmin, &lmax);
+			const size_t need = (size_t) (fmax - fmin) + 8;
+			// pick a free plot slot; when the host is slower than the GPU the capture is still accumulated on
+			// the device, only this particular plot delivery is skipped
+			pthread_mutex_lock(&p->mu);
+			int slot = -1;
+			for (int s = 0; s < 2; s++) if (!p->plot_busy[s]) { slot = s; break; }
+			if (slot >= 0) p->plot_busy[slot] = 1;
+			pthread_mutex_unlock(&p->mu);
+			if (p->plot_cap < need) {
+				CU_TRY(ctx, cudaStreamSynchronize(p->s_main));
+				pthread_mutex_lock(&p->mu);
+				while (p->delivered < p->submitted) pthread_cond_wait(&p->cv_done, &p->mu);
+				pthread_mutex_unlock(&p->mu);
+				for (int s = 0; s < 2; s++) {
+					if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
+					CU_TRY(ctx, cudaMallocHost(&p->h_plot_frame[s], sizeof(double) * need));
+					CU_TRY(ctx, cudaMallocHost(&p->h_plot_line[s], sizeof(double) * need));
+				}
+				p->plot_cap = need;
+			}
+			uint64_t calls = 0;
+			if ((rc = tsdrgpu_frd_run_async(p->frd, p->s_main, p->samplerate, p->d_capture, (uint32_t) want,
+			                                slot >= 0 ? p->h_plot_frame[slot] : NULL, fmax - fmin,
+			                                slot >= 0 ? p->h_plot_line[slot] : NULL, lmax - lmin, &calls))) return rc;
+			p->stats.captures++;
+			if (slot >= 0) {
+				FrameJob j; memset(&j, 0, sizeof j);
+				j.kind = 1; j.slot = slot; j.samplerate = p->samplerate; j.foff = fmin; j.flen = fmax - fmin; j.loff = lmin; j.llen = lmax - lmin;
+				j.calls = calls; j.reset_announce = reset_announce;
+				if ((rc = submit(p, j))) return rc;
+			}
+		}
+	}
+	return TSDRGPU_OK;
+}
+
+// ---- pixels -> frames (postprocessingthread + videodecodingthread)
+static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	const size_t n = (size_t) w * h;
+	int rc;
+	const int batch = p->cfg.batch_frames > 0 ? p->cfg.batch_frames : 1;
+	while (p->pix_fill - p->pix_read >= n * (size_t) batch) {
+		const int nf = batch;
+		// a free delivery slot, or the batch is dropped whole (frames stay aligned), as a full ring would (circbuff.c:95-104)
+		pthread_mutex_lock(&p->mu);
+		int slot = -1;
+		for (int s = 0; s < PL_SLOTS; s++) if (!p->slot_busy[s]) { slot = s; break; }
+		if (slot >= 0) p->slot_busy[slot] = 1;
+		pthread_mutex_unlock(&p->mu);
+		if (slot < 0 && p->cfg.block_when_busy) {
+			pthread_mutex_lock(&p->mu);
+			while (slot < 0) {
+				for (int s = 0; s < PL_SLOTS; s++) if (!p->slot_busy[s]) { slot = s; break; }
+				if (slot < 0) pthread_cond_wait(&p->cv_done, &p->mu);
+			}
+			p->slot_busy[slot] = 1;
+			pthread_mutex_unlock(&p->mu);
+		}
+		if (slot < 0) { p->pix_read += n * nf; p->stats.frames_dropped += nf; continue; }
+		if (p->slot_cap < n * nf) {
+			CU_TRY(ctx, cudaStreamSynchronize(p->s_main));
+			pthread_mutex_lock(&p->mu);
+			while (p->delivered < p->submitted) pthread_cond_wait(&p->cv_done, &p->mu);
+			pthread_mutex_unlock(&p->mu);
+			for (int s = 0; s < PL_SLOTS; s++) {
+				if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
+				CU_TRY(ctx, cudaMallocHost(&p->h_frames[s], sizeof(float) * n * nf));
+				CU_TRY(ctx, cudaMallocHost(&p->h_results[s], sizeof(tsdrgpu_frame_result_t) * nf));
+				CU_TRY(ctx, cudaMallocHost(&p->h_report[s], sizeof(int32_t) * nf));
+			}
+			p->slot_cap = n * nf;
+		}
+		if ((rc = grow(ctx, p->s_main, &p->d_frames, &p->frames_cap, n * nf, 0))) return rc;
+		unsigned flags = 0;
+		if (p->params[TSDRGPU_PARAM_INT_AUTOSHIFT]) flags |= TSDRGPU_FS_AUTOSHIFT;
+		if (p->params[TSDRGPU_PARAM_LOW_PASS_BEFORE_SYNC]) flags |= TSDRGPU_FS_LOWPASS_BEFORE_SYNC;
+		if (p->params[TSDRGPU_PARAM_AUTOGAIN_AFTER_PROCESSING]) flags |= TSDRGPU_FS_AUTOGAIN_AFTER_PROC;
+		if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION]) flags |= TSDRGPU_FS_SUPERRESOLUTION;
+		if ((rc = tsdrgpu_framestage_run_async(p->fs, p->s_main, p->d_pix + p->pix_read, nf, w, h, p->motionblur,
+		                                       0.1f /* NORMALISATION_LOWPASS_COEFF, TSDRLibrary.c:37 */, flags, p->d_frames,
+		                                       p->h_results[slot], p->h_report[slot]))) return rc;
+		CU_TRY(ctx, cudaMemcpyAsync(p->h_frames[slot], p->d_frames, sizeof(float) * n * nf, cudaMemcpyDeviceToHost, p->s_main));
+		p->stats.d2h_bytes += sizeof(float) * n * nf;
+		p->pix_read += n * nf;
+		p->stats.frames_processed += nf;
+		FrameJob j; memset(&j, 0, sizeof j);
+		j.kind = 0; j.slot = slot; j.nframes = nf; j.w = w; j.h = h;
+		if ((rc = submit(p, j))) return rc;
+	}
+	// compact the pixel buffer when the consumed prefix is large
+	if (p->pix_read > 0 && p->pix_read >= (p->pix_fill - p->pix_read)) {
+		const size_t left = p->pix_fill - p->pix_read;
+		if (left) {
+			pl_copy_f32<<<(unsigned) ((left + 255) / 256 < 1024 ? (left + 255) / 256 : 1024), 256, 0, p->s_main>>>(p->d_pix + p->pix_read, p->d_pix, left);
+			LAUNCH_CHECK(ctx);
+		}
+		p->pix_read = 0; p->pix_fill = left;
+	}
+	return TSDRGPU_OK;
+}
+
+// ---- samples -> pixels (decimatingthread)
+static int drain_blocks(tsdrgpu_pipeline *p) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	int rc;
+	pthread_mutex_lock(&p->geo_mu);
+	const int w = p->width, h = p->height; const double fv = p->refreshrate; const uint32_t fs_ = p->samplerate;
+	pthread_mutex_unlock(&p->geo_mu);
+	if (w <= 0 || h <= 0) return TSDRGPU_OK;
+	if (w != p->last_w || h != p->last_h) {            // postprocessingthread purges downstream on a size change
+		p->last_w = w; p->last_h = h;
+	}
+	const uint32_t block = (uint32_t) (0.1 * fs_ / fv);                 // FRAMES_TO_POLL, TSDRLibrary.c:41,335
+	if (block == 0) return TSDRGPU_OK;
+	const uint32_t min_blocks = p->cfg.batch_blocks > 0 ? (uint32_t) p->cfg.batch_blocks : 10;
+	while (p->decim_fill / block >= min_blocks) {
+		const uint32_t nb = (uint32_t) (p->decim_fill / block) > 4096 ? 4096 : (uint32_t) (p->decim_fill / block);
+		const double up = (double) (w * h) * fv;        // width*height*refreshrate, TSDRLibrary.c:340
+		const uint64_t npix = tsdrgpu_resampler_plan(p->rs, NULL, block, nb, up, (double) fs_);
+		if (npix == 0) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "resampler plan produced no pixels", cudaSuccess, __FILE__, __LINE__);
+		if ((rc = grow(ctx, p->s_main, &p->d_pix, &p->pix_cap, p->pix_fill + npix + 64, p->pix_fill))) return rc;
+		uint64_t n_out = 0;
+		if ((rc = tsdrgpu_resampler_run(p->rs, p->s_main, p->d_decim, 1, NULL, block, nb, up, (double) fs_,
+		                                (int) p->params[TSDRGPU_PARAM_NEAREST_NEIGHBOUR_RESAMPLING], p->d_pix + p->pix_fill,
+		                                p->pix_cap - p->pix_fill, &n_out))) return rc;
+		// pixel-level alignment (dsp.c:326-346 on the pixel ring) and manual sync (TSDRLibrary.c:344-346)
+		const uint32_t totalpixels = (uint32_t) (w * h);
+		uint32_t skip = 0;
+		const uint32_t fwd = p->pix_drop.add((uint32_t) n_out, totalpixels, true, &skip);
+		if (skip && fwd) {                               // rare (after drops / manual sync): shift through scratch, ranges overlap
+			void *tmp;
+			if ((rc = tsdrgpu_scratch(ctx, 3, sizeof(float) * fwd, &tmp))) return rc;
+			const unsigned g = (unsigned) ((fwd + 255) / 256 < 1024 ? (fwd + 255) / 256 : 1024);
+			pl_copy_f32<<<g, 256, 0, p->s_main>>>(p->d_pix + p->pix_fill + skip, (float *) tmp, fwd); LAUNCH_CHECK(ctx);
+			pl_copy_f32<<<g, 256, 0, p->s_main>>>((const float *) tmp, p->d_pix + p->pix_fill, fwd); LAUNCH_CHECK(ctx);
+		}
+		p->pix_fill += fwd;
+		const int so = p->syncoffset; p->syncoffset = 0;
+		p->pix_drop.shift_with(totalpixels, -(int64_t) so);
+		// consume the blocks: move the tail to the front
+		const size_t used = (size_t) nb * block, left = p->decim_fill - used;
+		if (left) { pl_copy_f32<<<(unsigned) ((2 * left + 255) / 256 < 1024 ? (2 * left + 255) / 256 : 1024), 256, 0, p->s_main>>>(p->d_decim + 2 * used, p->d_decim, 2 * left); LAUNCH_CHECK(ctx); }
+		p->decim_fill = left;
+		p->stats.samples_resampled += used;
+		if ((rc = drain_frames(p, w, h))) return rc;
+	}
+	return TSDRGPU_OK;
+}
+
+extern "C" {
+
+int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t *cfg, tsdrgpu_frame_cb frame_cb,
+                            tsdrgpu_value_cb value_cb, tsdrgpu_plot_cb plot_cb, void *user, tsdrgpu_pipeline_t **out) {
+	BIND(ctx); ARG_TRY(ctx, cfg != NULL && out != NULL);
+	ARG_TRY(ctx, cfg->samplerate > 0 && cfg->height > 0 && cfg->refreshrate > 0);
+	tsdrgpu_pipeline *p = new tsdrgpu_pipeline();
+	p->ctx = ctx; p->cfg = *cfg; p->frame_cb = frame_cb; p->value_cb = value_cb; p->plot_cb = plot_cb; p->user = user;
+	p->samplerate = cfg->samplerate; p->height = cfg->height; p->refreshrate = cfg->refreshrate; p->motionblur = cfg->motionblur;
+	p->width = 0; p->pixelrate = 0; p->ptos = 0; p->syncoffset = 0;
+	for (int i = 0; i < 9; i++) p->params[i] = cfg->params_int[i];
+	pthread_mutex_init(&p->geo_mu, NULL); pthread_mutex_init(&p->mu, NULL);
+	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
+	geometry_locked(p);
+	p->d_stage[0] = p->d_stage[1] = NULL; p->stage_cap[0] = p->stage_cap[1] = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
+	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames = NULL; p->frames_cap = 0;
+	p->slot_cap = 0; p->d_capture = NULL; p->cap_size = 0; p->cap_fill = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
+	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
+	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
+	p->stop = 0; p->submitted = 0; p->delivered = 0; p->last_w = 0; p->last_h = 0;
+	memset(&p->stats, 0, sizeof p->stats);
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking));
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
+		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_used[i], cudaEventDisableTiming));
+	}
+	int rc;
+	if ((rc = tsdrgpu_resampler_create(ctx, &p->rs))) return rc;
+	if ((rc = tsdrgpu_framestage_create(ctx, &p->fs))) return rc;
+	if ((rc = tsdrgpu_frd_create(ctx, &p->frd))) return rc;
+	pthread_create(&p->thread, NULL, delivery_main, p);
+	*out = p;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
+	BIND(p->ctx);
+	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_copy));
+	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_main));
+	pthread_mutex_lock(&p->mu);
+	while (p->delivered < p->submitted) pthread_cond_wait(&p->cv_done, &p->mu);
+	pthread_mutex_unlock(&p->mu);
+	return TSDRGPU_OK;
+}
+
+void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
+	if (!p) return;
+	tsdrgpu_pipeline_flush(p);
+	pthread_mutex_lock(&p->mu); p->stop = 1; pthread_cond_broadcast(&p->cv_job); pthread_mutex_unlock(&p->mu);
+	pthread_join(p->thread, NULL);
+	cudaSetDevice(p->ctx->device);
+	tsdrgpu_resampler_destroy(p->rs); tsdrgpu_framestage_destroy(p->fs); tsdrgpu_frd_destroy(p->frd);
+	for (void *h : p->registered) cudaHostUnregister(h);
+	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_decim, p->d_pix, p->d_frames, p->d_capture};
+	for (float *d : dev) if (d) cudaFree(d);
+	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
+	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
+	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy);
+	for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_h2d[i]); cudaEventDestroy(p->ev_used[i]); }
+	pthread_mutex_destroy(&p->mu); pthread_mutex_destroy(&p->geo_mu); pthread_cond_destroy(&p->cv_job); pthread_cond_destroy(&p->cv_done);
+	delete p;
+}
+
+int tsdrgpu_pipeline_set_param_int(tsdrgpu_pipeline_t *p, int id, uint32_t value) {
+	if (!p || id < 0 || id >= 9) return TSDRGPU_EINVAL;
+	p->params[id] = value;
+	return TSDRGPU_OK;
+}
+int tsdrgpu_pipeline_set_resolution(tsdrgpu_pipeline_t *p, int height, double refreshrate) {
+	if (!p || height <= 0 || refreshrate <= 0) return TSDRGPU_EINVAL;
+	pthread_mutex_lock(&p->geo_mu);
+	p->height = height; p->refreshrate = refreshrate;
+	geometry_locked(p);
+	pthread_mutex_unlock(&p->geo_mu);
+	return TSDRGPU_OK;
+}
+int tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate) {
+	if (!p || samplerate == 0) return TSDRGPU_EINVAL;
+	pthread_mutex_lock(&p->geo_mu);
+	p->samplerate = samplerate;
+	geometry_locked(p);
+	pthread_mutex_unlock(&p->geo_mu);
+	return TSDRGPU_OK;
+}
+int tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff) { if (!p) return TSDRGPU_EINVAL; p->motionblur = coeff; return TSDRGPU_OK; }
+int tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels) { if (!p) return TSDRGPU_EINVAL; p->syncoffset += pixels; return TSDRGPU_OK; }
+int tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate) {
+	if (!p) return TSDRGPU_EINVAL;
+	pthread_mutex_lock(&p->geo_mu);
+	if (width) *width = p->width; if (height) *height = p->height; if (refreshrate) *refreshrate = p->refreshrate;
+	pthread_mutex_unlock(&p->geo_mu);
+	return TSDRGPU_OK;
+}
+int tsdrgpu_pipeline_stats(tsdrgpu_pipeline_t *p, tsdrgpu_pipeline_stats_t *out) {
+	if (!p || !out) return TSDRGPU_EINVAL;
+	pthread_mutex_lock(&p->mu); *out = p->stats; pthread_mutex_unlock(&p->mu);
+	out->gpu_launches = p->ctx->launches;
+	return TSDRGPU_OK;
+}
+
+// the body of the reference's process() (TSDRLibrary.c:264-298), normal (non-superbandwidth) mode
+int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	BIND(ctx);
+	ARG_TRY(ctx, (items_count & 1) == 0);                     // assert at TSDRLibrary.c:265
+	const uint64_t size2 = items_count >> 1;
+	pthread_mutex_lock(&p->geo_mu);
+	const int w = p->width, h = p->height; const double ptos = p->ptos;
+	pthread_mutex_unlock(&p->geo_mu);
+	p->stats.samples_in += size2;
+	if (samples_dropped > 0) p->stats.samples_dropped_upstream += (uint64_t) samples_dropped;
+	if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION])
+		return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "superbandwidth mode is driven through tsdrgpu_superb_* (not the streaming pipeline)", cudaSuccess, __FILE__, __LINE__);
+	const int block = (int) round((double) ((w * h) << 1) * ptos);           // TSDRLibrary.c:284
+	if (block <= 0) return TSDRGPU_OK;
+	p->dev_drop.shift_with((uint32_t) block, samples_dropped);
+	const bool drop_all = p->dev_drop.will_drop_all((uint32_t) size2);
+	const bool plots_on = !p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_OFF];
+	int rc;
+	const bool need_data = size2 > 0 && (!drop_all || (plots_on && samples_dropped != 0));
+	const int ss = p->stage_slot;
+	float *stage = NULL;
+	if (need_data) {
+		ARG_TRY(ctx, h_iq != NULL);
+		p->stage_slot ^= 1;
+		if ((rc = grow(ctx, p->s_main, &p->d_stage[ss], &p->stage_cap[ss], items_count, 0))) return rc;
+		stage = p->d_stage[ss];
+		// the plugin's buffer is only valid during this call: copy it on the copy stream (after the kernels that
+		// read this staging slot two calls ago), let the main stream wait for the copy, and return once the
+		// host buffer has been read.  With two slots the copy of block k+1 overlaps the kernels of block k.
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->ev_used[ss], 0));
+		CU_TRY(ctx, cudaMemcpyAsync(stage, h_iq, sizeof(float) * items_count, cudaMemcpyHostToDevice, p->s_copy));
+		CU_TRY(ctx, cudaEventRecord(p->ev_h2d[ss], p->s_copy));
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_h2d[ss], 0));
+		p->stats.h2d_bytes += sizeof(float) * items_count;
+		if ((rc = feed_capture(p, stage, size2, samples_dropped != 0))) return rc;
+	} else if (plots_on && samples_dropped != 0) p->cap_fill = 0;
+	uint32_t skip = 0;
+	const uint32_t fwd = p->dev_drop.add((uint32_t) size2, (uint32_t) block, true, &skip);
+	if (fwd) {
+		if ((rc = grow(ctx, p->s_main, &p->d_decim, &p->decim_cap, 2 * (p->decim_fill + fwd), 2 * p->decim_fill))) return rc;
+		pl_copy_f32<<<(unsigned) ((2ull * fwd + 255) / 256 < 2048 ? (2ull * fwd + 255) / 256 : 2048), 256, 0, p->s_main>>>(stage + 2ull * skip, p->d_decim + 2 * p->decim_fill, 2ull * fwd);
+		LAUNCH_CHECK(ctx);
+		p->decim_fill += fwd;
+	}
+	if (need_data) {
+		CU_TRY(ctx, cudaEventRecord(p->ev_used[ss], p->s_main));           // the slot may be overwritten after this point
+		CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));                     // the host buffer has been read
+	}
+	return drain_blocks(p);
+}
+
+}  // extern "C"

@@ -108,7 +108,7 @@ def test_resample_stream(gpu, O, name, nearest, fused):
 @pytest.mark.parametrize("ratio", [0.37, 0.9999, 1.0, 1.5, 2.0, 3.25, 7.5])
 def test_resample_general_ratio(gpu, O, ratio):
     rng = np.random.default_rng(11)
-    sizes = [1000 + 37 * k for k in range(9)] + [1, 2, 4100]
+    sizes = [1000 + 37 * k for k in range(9)] + [7, 11, 4100]     # every block must yield >= 1 pixel (the reference asserts)
     x = rng.standard_normal(sum(sizes)).astype(np.float32)
     P = {"rs": orc.port().resampler()}
     want, state, stale = _oracle_stream(O, x, sizes, ratio * 1e6, 1e6, False, P)

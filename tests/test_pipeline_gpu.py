@@ -1,0 +1,112 @@
+"""GPU: the streaming pipeline (process() -> frames) against the oracle driven stage by stage on one thread."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tempestsdr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_oracle_stream(O, iq_blocks, fs, h, fv, plots=True):
+    """Single-threaded replay of process() -> decimatingthread -> postprocessingthread with the reference stages."""
+    w, _, _ = O.geometry(fs, h, fv)
+    n = w * h
+    block = int(0.1 * fs / fv)
+    rs = O.resampler(); pp = O.postprocessor(fs, h, fv, 1, 0)
+    decim = np.zeros(0, np.float32); pix = np.zeros(0, np.float32)
+    frames = []
+    for iq in iq_blocks:
+        decim = np.concatenate([decim, O.am_demod(iq)])
+        while decim.size >= 10 * block:
+            for k in range(10):
+                pix = np.concatenate([pix, rs.run(decim[k * block:(k + 1) * block], w * h * fv, fs)])
+            decim = decim[10 * block:]
+            while pix.size >= n:
+                out, res = pp.run(pix[:n], w, h, 0.0, 0.1, 1, 0)
+                frames.append(out); pix = pix[n:]
+    return w, frames
+
+
+def test_pipeline_matches_stagewise_oracle():
+    from tempestsdr_b200 import pipeline
+    O = orc.best()
+    fs, h, fv = 2_000_000, 125, 60.0
+    w, _, _ = O.geometry(fs, h, fv)
+    nblk, items = 24, 65536
+    iq_all = synth.video_like_iq(nblk * items // 2, fs, w, h, fv, seed=21)
+    blocks = [iq_all[k * items:(k + 1) * items].copy() for k in range(nblk)]
+    _, want = run_oracle_stream(O, blocks, fs, h, fv)
+    got, plots, values = [], [], []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=1, block_when_busy=True,
+                          params={"autoshift": 1, "lowpass_before_sync": 1},
+                          on_frame=lambda f, ww, hh: got.append(f.copy()),
+                          on_plot=lambda pid, off, v, sr: plots.append((pid, off, v.copy())),
+                          on_value=lambda vid, a, b: values.append((vid, a, b)))
+    for b in blocks:
+        p.process(b, 0)
+    p.flush()
+    st = p.stats()
+    assert st.frames_dropped == 0 and st.frames_delivered == len(want) > 3
+    for k, (g, wv) in enumerate(zip(got, want)):
+        assert np.array_equal(g.view(np.uint32), wv.view(np.uint32)), f"frame {k}"
+    # autocorrelation plots: capture size 3.1*fs/55 = 112727 samples -> several captures
+    cap = int(3.1 * fs / 55.0)
+    assert st.captures == (nblk * items // 2) // cap and len(plots) == 2 * st.captures
+    mag = O.am_demod(iq_all)
+    det = O.framerate_detector()
+    for c in range(st.captures):
+        (fo, fp), (lo, lp), calls = det.run(fs, mag[c * cap:(c + 1) * cap])
+    last_frame = [v for pid, off, v in plots if pid == 0][-1]
+    assert np.max(np.abs(last_frame - fp)) <= 1e-5 * np.max(np.abs(fp))      # tolerance: 1e-5 of the plot peak
+    assert (2, 0.0, float(st.captures)) in values
+    p.close()
+
+
+def test_pipeline_drop_resync_and_manual_sync():
+    """Upstream sample drops discard up to the next multiple of `block` (dsp.c:313-368) so frames stay aligned."""
+    from tempestsdr_b200 import pipeline
+    O = orc.best()
+    fs, h, fv = 2_000_000, 125, 60.0
+    w, _, pt = O.geometry(fs, h, fv)[0], None, O.geometry(fs, h, fv)[2]
+    items = 65536
+    iq_all = synth.video_like_iq(30 * items // 2, fs, w, h, fv, seed=22)
+    blocks = [iq_all[k * items:(k + 1) * items].copy() for k in range(30)]
+    block = int(round(((w * h) << 1) * pt))
+    got = []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=1, block_when_busy=True,
+                          params={"autoshift": 0, "autocorr_plots_off": 1}, on_frame=lambda f, ww, hh: got.append(f.copy()))
+    dropped = 12345
+    diff = 0
+    fed = []
+    for k, b in enumerate(blocks):
+        d = dropped if k == 7 else 0
+        # oracle bookkeeping for what the decimator receives
+        diff = O.dropcomp_shift_with(diff, block, d)
+        diff, fwd, skip = O.dropcomp_add(diff, items // 2, block, True)
+        if fwd:
+            fed.append(b[2 * skip:])
+        p.process(b, d)
+    p.flush()
+    _, want = run_oracle_stream_flat(O, np.concatenate(fed), fs, h, fv)
+    assert len(got) == len(want) > 3
+    for k, (g, wv) in enumerate(zip(got, want)):
+        assert np.array_equal(g.view(np.uint32), wv.view(np.uint32)), f"frame {k}"
+    p.close()
+
+
+def run_oracle_stream_flat(O, iq, fs, h, fv):
+    w, _, _ = O.geometry(fs, h, fv)
+    n = w * h
+    block = int(0.1 * fs / fv)
+    mag = O.am_demod(iq)
+    rs = O.resampler(); pp = O.postprocessor(fs, h, fv, 0, 0)
+    pix = []
+    for k in range(mag.size // (10 * block) * 10):
+        pix.append(rs.run(mag[k * block:(k + 1) * block], w * h * fv, fs))
+    pix = np.concatenate(pix)
+    frames = [pp.run(pix[k * n:(k + 1) * n], w, h, 0.0, 0.1, 0, 0)[0] for k in range(pix.size // n)]
+    return w, frames
