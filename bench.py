@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE configs[1] -- 1080p60 geometry (1125 total lines, the GUI's convention;
+W = 740), 25 MS/s float32 IQ.  One step = one batch of 64 frames' worth of synthetic IQ (640 decimator blocks of
+41666 pairs = 26.7 M pairs = 213 MB, larger than L2) through the whole hot path:
+    fused demod+resample -> pixel stream -> frame stage (auto-gain, temporal IIR, collapse, sync search, re-centre)
+    and, beside it, the frame-rate detector: every capture of 3.1*fs/55 samples is demodulated, autocorrelated
+    (2^20-point FFT + IFFT) and accumulated into the two lag plots.
+`value`   MS/s with the IQ already resident in HBM (CUDA events around exactly K steps, max over ranks).
+`e2e`     the same metric through the reference-facing call: tsdrgpu_pipeline_process() == the plugin's process()
+          callback with HOST buffers (pinned), H2D of every block and D2H of every finished frame inside the timed
+          region (host wall clock bracketed by device synchronisation, max over ranks).
+N > 1     N independent streams, one per GPU (the path has no cross-stream exchange: replicas, weak scaling).
+--impl reference   the reference's own threaded CPU pipeline (oracle/_ref: libTSDRLibrary.so + its RawFile plugin
+          with pacing off) on this box's host cores, same geometry; falls back to the pinned C port when the
+          reference binary is absent.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS, HEIGHT, FV = 25_000_000, 1125, 60.0
+FRAMES_PER_STEP = 64
+METRIC = "IQ MS/s ingested -> 1080p60 frames (demod+resample+frame stage+autocorrelation), whole job"
+
+
+def geometry():
+    from tempestsdr_b200 import _native as N
+    w, pr, pt = C.c_int(0), C.c_double(0), C.c_double(0)
+    N.lib().tsdrgpu_geometry(FS, HEIGHT, FV, C.byref(w), C.byref(pr), C.byref(pt))
+    return w.value
+
+
+def make_iq(pairs: int, seed: int) -> np.ndarray:
+    """Video-like synthetic IQ, generated for one frame period and tiled (cheap, deterministic)."""
+    from tempestsdr_b200 import synth
+    per_frame = int(FS / FV)
+    base = synth.video_like_iq(4 * per_frame, FS, 2576, 1125, FV, seed=seed, snr_db=25.0)
+    reps = (2 * pairs + base.size - 1) // base.size
+    return np.ascontiguousarray(np.tile(base, reps)[: 2 * pairs])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                sm.append(float(p[1])); mx.append(float(p[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# --------------------------------------------------------------------------------------------------- our arm
+class DeviceStep:
+    """One step of the hot path with the IQ resident in HBM."""
+
+    def __init__(self, gpu, iq_dev, w):
+        import torch
+        from tempestsdr_b200.api import FrameRateDetector, PostProcessFlags
+        self.torch, self.gpu, self.iq, self.w = torch, gpu, iq_dev, w
+        self.block = int(0.1 * FS / FV)
+        self.nblocks = FRAMES_PER_STEP * 10
+        self.n = w * HEIGHT
+        self.up = w * HEIGHT * FV
+        self.rs = gpu.resampler()
+        self.pp = gpu.post_processor()
+        self.frd = gpu.framerate_detector()
+        self.flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True)     # the GUI's defaults
+        self.cap = FrameRateDetector.capture_size(FS)
+        max_pix = int(self.rs.plan((self.block, self.nblocks), self.up, float(FS))) + 1024
+        self.pix = torch.empty(max_pix + self.n + 1024, dtype=torch.float32, device=iq_dev.device)
+        self.pix_fill = 0
+        self.frames_out = torch.empty(FRAMES_PER_STEP * self.n, dtype=torch.float32, device=iq_dev.device)
+        self.capture = torch.empty(self.cap, dtype=torch.float32, device=iq_dev.device)
+        self.cap_fill = 0
+        self.frames = 0
+        self.captures = 0
+        self.pairs = self.block * self.nblocks
+
+    def __call__(self):
+        torch, gpu = self.torch, self.gpu
+        # samples -> pixels (fused demod + resample), appended behind the pixels left over from the last step
+        out = self.rs.process(self.iq, (self.block, self.nblocks), self.up, float(FS), in_is_iq=True, out=self.pix[self.pix_fill:])
+        self.pix_fill += out.numel()
+        nf = min(self.pix_fill // self.n, FRAMES_PER_STEP)
+        self.pp.process(self.pix[: nf * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=self.frames_out[: nf * self.n], want_results=False)
+        left = self.pix_fill - nf * self.n
+        if left:
+            self.pix[:left].copy_(self.pix[nf * self.n: self.pix_fill].clone() if left > nf * self.n else self.pix[nf * self.n: self.pix_fill])
+        self.pix_fill = left
+        self.frames += nf
+        # frame-rate detector: every capture of the stream
+        pos = 0
+        while pos < self.pairs:
+            take = min(self.cap - self.cap_fill, self.pairs - pos)
+            gpu.chk(gpu._lib.tsdrgpu_am_demod(gpu._h, gpu.stream, self.iq.data_ptr() + 8 * pos, take, self.capture.data_ptr() + 4 * self.cap_fill))
+            self.cap_fill += take; pos += take
+            if self.cap_fill == self.cap:
+                self.frd.run(FS, self.capture, copy_out=False)
+                self.cap_fill = 0; self.captures += 1
+
+
+def collect_profile(gpu):
+    names = C.create_string_buffer(48 * 48)
+    tot = (C.c_double * 48)(); cnt = (C.c_uint64 * 48)(); n = C.c_int(0)
+    gpu.chk(gpu._lib.tsdrgpu_profile_collect(gpu._h, names, tot, cnt, 48, C.byref(n)))
+    out = {}
+    for i in range(n.value):
+        nm = names.raw[48 * i: 48 * (i + 1)].split(b"\0")[0].decode()
+        out[nm] = (tot[i], cnt[i])
+    return out
+
+
+def cpu_baseline(w, seconds_budget=25.0):
+    """The same work as one GPU step on ONE host core: the compiled reference's stage functions driven serially
+    (oracle/_ref when present, else the pinned C port).  Bounded sample: 8 frames of IQ + 2 autocorrelation captures."""
+    from oracle import oracle as orc
+    O = orc.best()
+    block = int(0.1 * FS / FV)
+    nframes = 8
+    pairs = block * 10 * nframes
+    iq = make_iq(pairs, seed=77)
+    cap = int(3.1 * FS / 55.0)
+    t0 = time.perf_counter()
+    mag = O.am_demod(iq)
+    rs = O.resampler()
+    pix = np.concatenate([rs.run(mag[k * block:(k + 1) * block], w * HEIGHT * FV, float(FS)) for k in range(10 * nframes)])
+    pp = O.postprocessor(FS, HEIGHT, FV, 1, 0)
+    n = w * HEIGHT
+    for k in range(pix.size // n):
+        pp.run(pix[k * n:(k + 1) * n], w, HEIGHT, 0.0, 0.1, 1, 0)
+    t_stream = time.perf_counter() - t0
+    det = O.framerate_detector()
+    ncap = 2
+    capdata = np.tile(mag, (ncap * cap + mag.size - 1) // mag.size)[: ncap * cap]
+    t1 = time.perf_counter()
+    for c in range(ncap):
+        det.run(FS, capdata[c * cap:(c + 1) * cap])
+    t_cap = (time.perf_counter() - t1) / ncap
+    # one GPU step does pairs_step samples of the stream path and pairs_step/cap captures
+    per_sample = t_stream / pairs + t_cap / cap
+    return {"value": 1e-6 / per_sample, "unit": "MS/s", "cores": 1, "kind": "reference" if O.kind == "reference" else "port",
+            "sample": f"{nframes} frames ({pairs} IQ pairs) through demod+resample+frame stage: {t_stream:.2f} s; "
+                      f"{ncap} captures of {cap} samples autocorrelated: {t_cap:.2f} s each; stages driven serially on one thread"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tempestsdr_b200 import api, pipeline
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gpu = api.Context(local)
+    w = geometry()
+    block = int(0.1 * FS / FV)
+    pairs = block * 10 * FRAMES_PER_STEP
+    iq_host = make_iq(pairs, seed=1000 + rank)
+    iq_pinned = torch.from_numpy(iq_host).pin_memory()
+    iq_dev = iq_pinned.cuda(non_blocking=True)
+    step = DeviceStep(gpu, iq_dev, w)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = gpu.launches
+    frames0, caps0 = step.frames, step.captures
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    launches = gpu.launches - launches0
+    frames_done, caps_done = step.frames - frames0, step.captures - caps0
+
+    # ---- per-kernel timing pass (separate from the timed region above): CUDA events on the launching stream
+    gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
+    collect_profile(gpu)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        step()
+    prof = collect_profile(gpu)
+    gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
+
+    # ---- e2e through the C-ABI pipeline with host buffers
+    chunk = 512 * 1024 * 8                     # floats per process() call (8x the RawFile plugin's block)
+    pl = pipeline.Pipeline(samplerate=FS, height=HEIGHT, refreshrate=FV, batch_frames=16, batch_blocks=160, block_when_busy=True,
+                           device=local, params={"autoshift": 1, "lowpass_before_sync": 1})
+    host = iq_pinned.numpy()
+    base_ptr = iq_pinned.data_ptr()
+
+    def feed_once():
+        pos = 0
+        while pos < host.size:
+            n = min(chunk, host.size - pos)
+            pl.process_ptr(base_ptr + 4 * pos, n, 0)
+            pos += n
+
+    e2e_steps = max(2, min(args.steps, 6))
+    feed_once(); pl.flush()
+    barrier()
+    s0 = pl.stats()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        feed_once()
+    pl.flush()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    s1 = pl.stats()
+    e2e_val = world * e2e_steps * pairs / t_e2e.item() / 1e6
+    h2d = (s1.h2d_bytes - s0.h2d_bytes) // e2e_steps
+    d2h = (s1.d2h_bytes - s0.d2h_bytes) // e2e_steps
+    e2e_frames = s1.frames_delivered - s0.frames_delivered
+    pl.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (by total device time in the profiled steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+    ratio = w * HEIGHT * FV / FS
+    # algorithmic bytes per launch (DESIGN.md "algorithmic bytes"), per kernel
+    n_pix = step.n * FRAMES_PER_STEP
+    alg = {
+        "rs_main": pairs * (8 + 4 * ratio),                      # 8 B per IQ pair in + 4 B per pixel out
+        "fs_minmax": 4 * n_pix, "fs_normalise": 8 * n_pix, "fs_timelowpass": 8 * n_pix, "fs_collapse": 4 * n_pix, "fs_shift": 8 * n_pix,
+        "demod_kernel": None, "fft_pass_kernel": 16 * (1 << 20),
+    }
+    total_prof = sum(t for t, _ in prof.values()) or 1.0
+    kernels = {k: {"ms_per_step": t / prof_steps, "launches_per_step": c / prof_steps, "share": t / total_prof} for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    dom = next(iter(kernels))
+    roof_k = "rs_main"                                           # the kernel BASELINE configs[1] names
+    t_rs, c_rs = prof.get(roof_k, (0.0, 0))
+    achieved = alg[roof_k] / (t_rs / c_rs * 1e-3) / 1e9 if c_rs else None
+    roofline = {"kernel": "rs_main<IQ> (fused demod+resample)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[roof_k], "avg_launch_ms": (t_rs / c_rs) if c_rs else None,
+                "dominant_kernel_by_time": dom,
+                "per_kernel": {k: dict(v, **({"achieved_gbs": alg[k] * v["launches_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9} if alg.get(k) else {})) for k, v in kernels.items()}}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        roofline["traffic"] = tr.get("rs_main_dram_bytes_per_launch")
+    except Exception:
+        pass
+    value = world * args.steps * pairs / (ms_total * 1e-3) / 1e6
+    cpu = cpu_baseline(w)
+    line = {
+        "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (f64 accumulators where the reference uses them)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 1080p60 geometry (1125 total lines -> 740x1125 px frames), 25 MS/s float32 IQ, "
+                               f"{FRAMES_PER_STEP} frames per step ({pairs} IQ pairs, {8 * pairs / 1e6:.0f} MB > L2, so no L2 flush is needed)",
+                   "frames_per_step": frames_done / args.steps, "autocorr_captures_per_step": caps_done / args.steps,
+                   "frames_per_s": world * frames_done / (ms_total * 1e-3), "parallelism": f"replicas x{world}" if world > 1 else "single stream",
+                   "flags": "AUTOSHIFT=1, LOW_PASS_BEFORE_SYNC=1, AUTOGAIN_AFTER=0, motionblur 0 (GUI defaults), PLL write-back off"},
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "frames_delivered": int(e2e_frames), "how": "tsdrgpu_pipeline_process() on pinned host IQ in 16 MiB calls, "
+                "frames copied back to pinned host slots; host wall clock between device synchronisations"},
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    w = geometry()
+    ncores = os.cpu_count() or 1
+    if not orc.have_ref():
+        cpu = cpu_baseline(w)
+        cpu["sample"] = "reference binary absent: pinned C port, " + cpu["sample"]
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "higher_is_better": True, "data": "synthetic", "cpu_baseline": cpu,
+                          "config": {"workload": "BASELINE configs[1] geometry, C port of the reference stages, one thread"},
+                          "e2e": {"value": cpu["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    # the reference's own threaded pipeline: tsdr_readasync + RawFile (pacing off) on a file of synthetic IQ
+    lib = C.CDLL(orc.REF_LIB_SO)
+    per_frame = int(FS / FV)
+    iq = make_iq(16 * per_frame, seed=1000)
+    tmp = tempfile.NamedTemporaryFile(prefix="tsdr_iq_", suffix=".raw", delete=False)
+    iq.tofile(tmp); tmp.close()
+    FRAME_CB = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p)
+    VALUE_CB = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_double, C.c_void_p)
+    PLOT_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_uint32, C.c_void_p)
+    count = {"frames": 0, "plots": 0}
+    fcb = FRAME_CB(lambda b, ww, hh, c: count.__setitem__("frames", count["frames"] + 1))
+    vcb = VALUE_CB(lambda i, a, b, c: None)
+    pcb = PLOT_CB(lambda p, o, v, s, sr, c: count.__setitem__("plots", count["plots"] + 1))
+    t = C.c_void_p()
+    lib.tsdr_init(C.byref(t), vcb, pcb, None)
+    lib.tsdr_setresolution.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.tsdr_motionblur.argtypes = [C.c_void_p, C.c_float]
+    lib.tsdr_setgain.argtypes = [C.c_void_p, C.c_float]
+    lib.tsdr_setparameter_int.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    lib.tsdr_loadplugin.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    lib.tsdr_readasync.argtypes = [C.c_void_p, FRAME_CB, C.c_void_p]
+    lib.tsdr_stop.argtypes = [C.c_void_p]
+    lib.tsdr_setresolution(t, HEIGHT, FV); lib.tsdr_motionblur(t, 0.0); lib.tsdr_setgain(t, 0.5)
+    for pid, v in ((0, 1), (1, 0), (6, 1)):          # AUTOSHIFT=1, PLL=0, LOW_PASS_BEFORE_SYNC=1
+        lib.tsdr_setparameter_int(t, pid, v)
+    rc = lib.tsdr_loadplugin(t, orc.REF_RAWFILE_NOPACE_SO.encode(), f'"{tmp.name}" {FS} float'.encode())
+    assert rc == 0, f"tsdr_loadplugin rc={rc}"
+    th = threading.Thread(target=lambda: lib.tsdr_readasync(t, fcb, None), daemon=True)
+    th.start()
+    seconds = 4.0
+    time.sleep(1.0)                                  # warm-up: rings grow, first frames arrive
+    results = []
+    for s in range(args.warmup + args.steps):
+        f0, p0, t0 = count["frames"], count["plots"], time.perf_counter()
+        time.sleep(seconds)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            results.append(((count["frames"] - f0) / dt, (count["plots"] - p0) / 2 / dt))
+    lib.tsdr_stop(t)
+    th.join(timeout=10)
+    os.unlink(tmp.name)
+    fps = statistics.mean(r[0] for r in results)
+    caps = statistics.mean(r[1] for r in results)
+    value = fps * per_frame / 1e6
+    cpu = {"value": value, "unit": "MS/s", "cores": min(ncores, 6), "kind": "reference",
+           "sample": f"the reference's own threaded pipeline (plugin + decimate + post-process + video + autocorr threads) for "
+                     f"{args.steps} x {seconds:.0f} s on {ncores} host cores; counts FRAMES DELIVERED x samples per frame "
+                     f"(it drops whole blocks when a ring is full); {fps:.1f} frames/s, {caps:.2f} autocorrelation captures/s"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "cpu_baseline": cpu,
+                      "config": {"workload": "BASELINE configs[1]: 1080p60 geometry (1125 lines), 25 MS/s float32 IQ from a file through "
+                                             "TSDRPlugin_RawFile (pacing off) and the unmodified reference library", "frames_per_s": fps},
+                      "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

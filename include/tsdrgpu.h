@@ -49,6 +49,12 @@ TSDRGPU_API int         tsdrgpu_sm_count(tsdrgpu_ctx_t *ctx);
 /* number of kernels this library has launched through ctx since creation (bench.py's gpu_launches) */
 TSDRGPU_API uint64_t    tsdrgpu_launch_count(tsdrgpu_ctx_t *ctx);
 
+/* per-kernel timing for roofline reporting: when enabled, the library brackets its main kernel launches with CUDA
+ * events on the launching stream.  collect() synchronises the device, returns per-name totals (names: cap x 48
+ * chars) and resets.  Not for production paths (adds two event records per launch). */
+TSDRGPU_API int tsdrgpu_profile_enable(tsdrgpu_ctx_t *ctx, int on);
+TSDRGPU_API int tsdrgpu_profile_collect(tsdrgpu_ctx_t *ctx, char *names, double *total_ms, uint64_t *counts, int cap, int *n);
+
 /* plumbing for C hosts that do not bring their own allocator (Python callers use torch tensors instead) */
 TSDRGPU_API int tsdrgpu_malloc(tsdrgpu_ctx_t *ctx, size_t bytes, void **d_ptr);
 TSDRGPU_API int tsdrgpu_free(tsdrgpu_ctx_t *ctx, void *d_ptr);

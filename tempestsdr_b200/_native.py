@@ -48,6 +48,8 @@ _SIGS = {
     "tsdrgpu_last_error": (C.c_char_p, [C.c_void_p]),
     "tsdrgpu_sm_count": (C.c_int, [C.c_void_p]),
     "tsdrgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "tsdrgpu_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsdrgpu_profile_collect": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),
     "tsdrgpu_malloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "tsdrgpu_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_malloc_host": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),

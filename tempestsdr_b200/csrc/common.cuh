@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <vector>
 
 #include "../../include/tsdrgpu.h"
 
@@ -19,7 +20,20 @@ struct tsdrgpu_ctx {
 	void *pinned;            // small pinned staging area for descriptor uploads / scalar read-backs
 	size_t pinned_bytes;
 	std::mutex mu;
+	// optional per-kernel timing (bench.py's roofline): CUDA events on the launching stream around named launches
+	bool profiling;
+	struct ProfRec { int id; cudaEvent_t a, b; };
+	std::vector<ProfRec> prof_recs;
+	std::vector<cudaEvent_t> prof_pool;
+	char prof_names[48][48];
+	int prof_nnames;
 };
+
+void tsdrgpu_prof_begin(tsdrgpu_ctx_t *ctx, const char *name, cudaStream_t stream);
+void tsdrgpu_prof_end(tsdrgpu_ctx_t *ctx, cudaStream_t stream);
+// wrap a kernel launch: KL(ctx, "name", stream, kernel<<<...>>>(...));
+#define KL(ctx, name, stream, ...) do { if ((ctx)->profiling) tsdrgpu_prof_begin((ctx), (name), (stream)); __VA_ARGS__; \
+	if ((ctx)->profiling) tsdrgpu_prof_end((ctx), (stream)); LAUNCH_CHECK(ctx); } while (0)
 
 extern thread_local char g_tsdrgpu_err[512];
 

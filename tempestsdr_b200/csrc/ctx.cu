@@ -36,6 +36,7 @@ int tsdrgpu_create(tsdrgpu_ctx_t **out, int device) {
 	c->launches = 0;
 	for (int i = 0; i < 4; i++) { c->scratch[i] = NULL; c->scratch_bytes[i] = 0; }
 	c->pinned = NULL; c->pinned_bytes = 0;
+	c->profiling = false; c->prof_nnames = 0;
 	e = cudaSetDevice(device);
 	if (e != cudaSuccess) { delete c; return tsdrgpu_fail(NULL, TSDRGPU_ECUDA, "cudaSetDevice", e, __FILE__, __LINE__); }
 	*out = c;
@@ -47,6 +48,8 @@ void tsdrgpu_destroy(tsdrgpu_ctx_t *ctx) {
 	cudaSetDevice(ctx->device);
 	for (int i = 0; i < 4; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
+	for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+	for (auto e : ctx->prof_pool) cudaEventDestroy(e);
 	delete ctx;
 }
 
@@ -91,7 +94,47 @@ int tsdrgpu_stream_create(tsdrgpu_ctx_t *ctx, void **stream) {
 int tsdrgpu_stream_destroy(tsdrgpu_ctx_t *ctx, void *stream) { BIND(ctx); CU_TRY(ctx, cudaStreamDestroy((cudaStream_t) stream)); return TSDRGPU_OK; }
 int tsdrgpu_stream_sync(tsdrgpu_ctx_t *ctx, void *stream) { BIND(ctx); CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t) stream)); return TSDRGPU_OK; }
 
+int tsdrgpu_profile_enable(tsdrgpu_ctx_t *ctx, int on) {
+	BIND(ctx);
+	ctx->profiling = on != 0;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_profile_collect(tsdrgpu_ctx_t *ctx, char *names, double *total_ms, uint64_t *counts, int cap, int *n) {
+	BIND(ctx); ARG_TRY(ctx, names && total_ms && counts && n && cap > 0);
+	CU_TRY(ctx, cudaDeviceSynchronize());
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	const int m = ctx->prof_nnames < cap ? ctx->prof_nnames : cap;
+	for (int i = 0; i < m; i++) { strncpy(names + 48 * i, ctx->prof_names[i], 48); total_ms[i] = 0.0; counts[i] = 0; }
+	for (auto &r : ctx->prof_recs) {
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.id < m) { total_ms[r.id] += ms; counts[r.id]++; }
+		ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b);
+	}
+	ctx->prof_recs.clear();
+	*n = m;
+	return TSDRGPU_OK;
+}
+
 }  // extern "C"
+
+static cudaEvent_t prof_event(tsdrgpu_ctx_t *ctx) {
+	if (!ctx->prof_pool.empty()) { cudaEvent_t e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); return e; }
+	cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void tsdrgpu_prof_begin(tsdrgpu_ctx_t *ctx, const char *name, cudaStream_t stream) {
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	int id = -1;
+	for (int i = 0; i < ctx->prof_nnames; i++) if (!strcmp(ctx->prof_names[i], name)) { id = i; break; }
+	if (id < 0) { if (ctx->prof_nnames >= 48) return; id = ctx->prof_nnames++; strncpy(ctx->prof_names[id], name, 47); ctx->prof_names[id][47] = 0; }
+	tsdrgpu_ctx::ProfRec r; r.id = id; r.a = prof_event(ctx); r.b = prof_event(ctx);
+	cudaEventRecord(r.a, stream);
+	ctx->prof_recs.push_back(r);
+}
+void tsdrgpu_prof_end(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!ctx->prof_recs.empty()) cudaEventRecord(ctx->prof_recs.back().b, stream);
+}
 
 int tsdrgpu_scratch(tsdrgpu_ctx_t *ctx, int slot, size_t bytes, void **out) {
 	if (ctx->scratch_bytes[slot] < bytes) {

@@ -290,8 +290,7 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	if (total / 4 >= 256 && threads < 256) threads = 256;
 	if (threads > 1024) threads = 1024;
 	const size_t smem = sizeof(float2) * (size_t) P.C * (L + 1);
-	fft_pass_kernel<<<bundles, threads, smem, stream>>>(in, out, P, g_table[ctx->device], inverse);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<<<bundles, threads, smem, stream>>>(in, out, P, g_table[ctx->device], inverse));
 	return TSDRGPU_OK;
 }
 
@@ -405,16 +404,16 @@ int tsdrgpu_autocorrelation(tsdrgpu_ctx_t *ctx, void *stream_, float *d_answer, 
 	void *scratch;
 	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N, &scratch))) return rc;
 	if (N == 1) {
-		k_real_to_complex<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, d_real, 0, size); LAUNCH_CHECK(ctx);
-		k_abs<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, 0, size); LAUNCH_CHECK(ctx);
+		KL(ctx, "k_real_to_complex", stream, k_real_to_complex<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, d_real, 0, size));
+		KL(ctx, "k_abs", stream, k_abs<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, 0, size));
 		return TSDRGPU_OK;
 	}
 	// forward transform of the first N samples, real input widened on load, |X|/N on store
 	FftOpts f; f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N;
 	if ((rc = fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 0, f))) return rc;
 	if (size > N) {                                       // the tail never enters a transform (fft.c:52-60)
-		k_real_to_complex<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, d_real, N, size); LAUNCH_CHECK(ctx);
-		k_abs<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, N, size); LAUNCH_CHECK(ctx);
+		KL(ctx, "k_real_to_complex", stream, k_real_to_complex<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, d_real, N, size));
+		KL(ctx, "k_abs", stream, k_abs<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, N, size));
 	}
 	FftOpts b; b.real_in = NULL; b.out_abs = false; b.scale = 1.0f;
 	return fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 1, b);
@@ -428,16 +427,14 @@ int tsdrgpu_crosscorrelation(tsdrgpu_ctx_t *ctx, void *stream_, float *d_a, floa
 	int rc;
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_a), N, 0))) return rc;
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_b), N, 0))) return rc;
-	k_conj_mul<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<float2 *>(d_a), reinterpret_cast<const float2 *>(d_b), N);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "k_conj_mul", stream, k_conj_mul<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<float2 *>(d_a), reinterpret_cast<const float2 *>(d_b), N));
 	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_a), N, 1);
 }
 
 int tsdrgpu_accumulate(tsdrgpu_ctx_t *ctx, void *stream, double *d_out, uint64_t calls, const float *d_in, int startid, int length) {
 	BIND(ctx); ARG_TRY(ctx, d_out != NULL && d_in != NULL && length >= 0 && startid >= 0);
 	if (length == 0) return TSDRGPU_OK;
-	k_accumulate<<<grid1d((unsigned long long) length, ctx->sm_count), 256, 0, (cudaStream_t) stream>>>(d_out, calls, reinterpret_cast<const float2 *>(d_in), startid, length);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "k_accumulate", (cudaStream_t) stream, k_accumulate<<<grid1d((unsigned long long) length, ctx->sm_count), 256, 0, (cudaStream_t) stream>>>(d_out, calls, reinterpret_cast<const float2 *>(d_in), startid, length));
 	return TSDRGPU_OK;
 }
 
@@ -523,7 +520,7 @@ int tsdrgpu_complex_to_abs_diff(tsdrgpu_ctx_t *ctx, void *stream_, float *d_data
 	const unsigned long long pairs = (unsigned long long) size_floats / 2;
 	void *tmp; int rc;
 	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * pairs, &tmp))) return rc;
-	k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_data), (float2 *) tmp, pairs); LAUNCH_CHECK(ctx);
+	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_data), (float2 *) tmp, pairs));
 	CU_TRY(ctx, cudaMemcpyAsync(d_data, tmp, sizeof(float2) * pairs, cudaMemcpyDeviceToDevice, stream));
 	return TSDRGPU_OK;
 }
@@ -539,11 +536,11 @@ int tsdrgpu_superb_bestfit(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop
 	void *wa, *wb; int rc;
 	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * pairs + 256, &wa))) return rc;
 	if ((rc = tsdrgpu_scratch(ctx, 2, sizeof(float2) * pairs + 256, &wb))) return rc;
-	k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), (float2 *) wa, pairs); LAUNCH_CHECK(ctx);
-	k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hopi), (float2 *) wb, pairs); LAUNCH_CHECK(ctx);
+	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), (float2 *) wa, pairs));
+	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hopi), (float2 *) wb, pairs));
 	if ((rc = tsdrgpu_crosscorrelation(ctx, stream, (float *) wa, (float *) wb, (uint32_t) pairs))) return rc;
 	int *d_res = reinterpret_cast<int *>((char *) wb);    // wb is free again after the cross-correlation
-	k_argmax_mag<<<1, 1024, 0, stream>>>((const float2 *) wa, (unsigned) pairs, d_res); LAUNCH_CHECK(ctx);
+	KL(ctx, "k_argmax_mag", stream, k_argmax_mag<<<1, 1024, 0, stream>>>((const float2 *) wa, (unsigned) pairs, d_res));
 	int lag = 0;
 	CU_TRY(ctx, cudaMemcpyAsync(&lag, d_res, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
@@ -556,8 +553,7 @@ int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream_, const float *
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
 	ARG_TRY(ctx, (unsigned long long) best_offset_floats / 2 < N);
-	k_rotate<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), reinterpret_cast<float2 *>(d_spectrum), N, (unsigned long long) best_offset_floats / 2);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "k_rotate", stream, k_rotate<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), reinterpret_cast<float2 *>(d_spectrum), N, (unsigned long long) best_offset_floats / 2));
 	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_spectrum), N, 0);
 }
 
@@ -582,8 +578,7 @@ int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream_, float *const *d_hop
 int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_gathered, int nhops, uint32_t n, int residue, float *d_out) {
 	BIND(ctx); ARG_TRY(ctx, d_gathered && d_out && nhops > 0 && n > 0 && residue >= 0 && residue < nhops && (n & (n - 1)) == 0);
 	cudaStream_t stream = (cudaStream_t) stream_;
-	k_residue_mix<<<grid1d(n, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_gathered), nhops, n, residue, reinterpret_cast<float2 *>(d_out));
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "k_residue_mix", stream, k_residue_mix<<<grid1d(n, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_gathered), nhops, n, residue, reinterpret_cast<float2 *>(d_out)));
 	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_out), n, 1);
 }
 

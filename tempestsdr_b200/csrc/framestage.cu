@@ -529,19 +529,15 @@ static int fs_autogain_batch(tsdrgpu_framestage *fs, cudaStream_t stream, const 
 	tsdrgpu_ctx_t *ctx = fs->ctx;
 	const int chunks = (int) ((n + 4095) / 4096 < FS_MM_CHUNKS ? (n + 4095) / 4096 : FS_MM_CHUNKS);
 	dim3 grid(chunks, nframes);
-	if (snr) fs_minmax<true><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum);
-	else fs_minmax<false><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum);
-	LAUNCH_CHECK(ctx);
-	fs_autogain_iir<<<1, 256, 0, stream>>>(in, n, nframes, chunks, fs->d_pmin, fs->d_pmax, fs->d_psum, snr, norm, fs->d_state, fs->d_params);
-	LAUNCH_CHECK(ctx);
+	if (snr) KL(ctx, "fs_minmax", stream, fs_minmax<true><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum));
+	else KL(ctx, "fs_minmax", stream, fs_minmax<false><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum));
+	KL(ctx, "fs_autogain_iir", stream, fs_autogain_iir<<<1, 256, 0, stream>>>(in, n, nframes, chunks, fs->d_pmin, fs->d_pmax, fs->d_psum, snr, norm, fs->d_state, fs->d_params));
 	const unsigned gx = grid_for(n, ctx->sm_count, 4);
 	dim3 grid2(snr ? (gx < (unsigned) FS_MM_CHUNKS ? gx : FS_MM_CHUNKS) : gx, nframes);
-	if (snr) fs_normalise<true><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin);
-	else fs_normalise<false><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin);
-	LAUNCH_CHECK(ctx);
+	if (snr) KL(ctx, "fs_normalise", stream, fs_normalise<true><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin));
+	else KL(ctx, "fs_normalise", stream, fs_normalise<false><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin));
 	if (snr) {
-		fs_snr_finish<<<1, 256, 0, stream>>>(nframes, (int) grid2.x, n, fs->d_psq, fs->d_plin, fs->d_params, fs->d_state);
-		LAUNCH_CHECK(ctx);
+		KL(ctx, "fs_snr_finish", stream, fs_snr_finish<<<1, 256, 0, stream>>>(nframes, (int) grid2.x, n, fs->d_psq, fs->d_plin, fs->d_params, fs->d_state));
 	}
 	return TSDRGPU_OK;
 }
@@ -624,31 +620,29 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	const size_t total = (size_t) nframes * n;
 
 	auto collapse_sync = [&](const float *src, bool with_params) -> int {
-		fs_collapse<<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips, fs->d_hstrips, col_ctas);
-		LAUNCH_CHECK(ctx);
-		fs_sync<<<1, FS_SYNC_THREADS, sync_smem, stream>>>(fs->d_wstrips, fs->d_hstrips, w, h, minsize_x, minsize_y, nframes,
+		KL(ctx, "fs_collapse", stream, fs_collapse<<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips, fs->d_hstrips, col_ctas));
+		KL(ctx, "fs_sync", stream, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, stream>>>(fs->d_wstrips, fs->d_hstrips, w, h, minsize_x, minsize_y, nframes,
 			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain,
-			with_params ? fs->d_params : NULL, fs->d_results);
-		LAUNCH_CHECK(ctx);
+			with_params ? fs->d_params : NULL, fs->d_results));
 		return TSDRGPU_OK;
 	};
 	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed
 	auto emit = [&](float *src, float *dst, bool greenlines, bool may_modify, float **result) -> int {
 		if (autoshift) {
-			fs_shift<<<dim3(gx, nframes), 256, 0, stream>>>(src, dst, w, h, fs->d_results); LAUNCH_CHECK(ctx);
+			KL(ctx, "fs_shift", stream, fs_shift<<<dim3(gx, nframes), 256, 0, stream>>>(src, dst, w, h, fs->d_results));
 			*result = dst;
 		} else if (greenlines && may_modify) {
-			fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(src, w, h, fs->d_results); LAUNCH_CHECK(ctx);
+			KL(ctx, "fs_greenlines", stream, fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(src, w, h, fs->d_results));
 			*result = src;
 		} else if (greenlines) {
-			fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, dst, total); LAUNCH_CHECK(ctx);
-			fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(dst, w, h, fs->d_results); LAUNCH_CHECK(ctx);
+			KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, dst, total));
+			KL(ctx, "fs_greenlines", stream, fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(dst, w, h, fs->d_results));
 			*result = dst;
 		} else *result = src;
 		return TSDRGPU_OK;
 	};
 	auto copy_to_out = [&](const float *src) -> int {
-		if (src != d_out) { fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, d_out, total); LAUNCH_CHECK(ctx); }
+		if (src != d_out) { KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, d_out, total)); }
 		return TSDRGPU_OK;
 	};
 	int rc;
@@ -656,25 +650,25 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	if (lpbs) {                                          // dsp.c:201-212
 		const float *lp_in = d_in;
 		if (!aap) { if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc; lp_in = fs->d_t1; }
-		fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, fs->d_t2, fs->d_screen, n, nframes, motionblur, fresh); LAUNCH_CHECK(ctx);
+		KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, fs->d_t2, fs->d_screen, n, nframes, motionblur, fresh));
 		if ((rc = collapse_sync(fs->d_t2, !aap))) return rc;
 		float *dst = aap ? fs->d_t1 : d_out;
 		if ((rc = emit(fs->d_t2, dst, !superres, false, &res))) return rc;
 		if (aap) {
 			if ((rc = fs_autogain_batch(fs, stream, res, d_out, nframes, n, lowpasscoeff, snr))) return rc;
-			fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results); LAUNCH_CHECK(ctx);
+			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results));
 		} else if ((rc = copy_to_out(res))) return rc;
 	} else {                                             // dsp.c:214-226
 		float *work = fs->d_t1;
 		if (!aap) { if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc; }
-		else { fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(d_in, fs->d_t1, total); LAUNCH_CHECK(ctx); }
+		else { KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(d_in, fs->d_t1, total)); }
 		if ((rc = collapse_sync(work, !aap))) return rc;
 		if ((rc = emit(work, fs->d_t2, (motionblur == 0.0f) && !superres, true, &res))) return rc;
 		float *lp_out = aap ? ((res == fs->d_t1) ? fs->d_t2 : fs->d_t1) : d_out;
-		fs_timelowpass<<<gx, 256, 0, stream>>>(res, lp_out, fs->d_screen, n, nframes, motionblur, fresh); LAUNCH_CHECK(ctx);
+		KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(res, lp_out, fs->d_screen, n, nframes, motionblur, fresh));
 		if (aap) {
 			if ((rc = fs_autogain_batch(fs, stream, lp_out, d_out, nframes, n, lowpasscoeff, snr))) return rc;
-			fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results); LAUNCH_CHECK(ctx);
+			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results));
 		}
 	}
 	if (h_results) CU_TRY(ctx, cudaMemcpyAsync(h_results, fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes, cudaMemcpyDeviceToHost, stream));
@@ -726,8 +720,7 @@ int tsdrgpu_timelowpass(tsdrgpu_ctx_t *ctx, void *stream, float coeff, int n, co
 	BIND(ctx);
 	ARG_TRY(ctx, n > 0 && d_in && d_screen);
 	// single frame: the per-frame output IS the screen buffer
-	fs_timelowpass<<<grid_for((size_t) n, ctx->sm_count, 4), 256, 0, (cudaStream_t) stream>>>(d_in, d_screen, d_screen, (size_t) n, 1, coeff, 1.0 - (double) coeff);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "fs_timelowpass", (cudaStream_t) stream, fs_timelowpass<<<grid_for((size_t) n, ctx->sm_count, 4), 256, 0, (cudaStream_t) stream>>>(d_in, d_screen, d_screen, (size_t) n, 1, coeff, 1.0 - (double) coeff));
 	return TSDRGPU_OK;
 }
 
@@ -735,8 +728,7 @@ int tsdrgpu_average_v_h(tsdrgpu_ctx_t *ctx, void *stream, int w, int h, const fl
 	BIND(ctx);
 	ARG_TRY(ctx, w > 0 && h > 0 && d_in && d_wbuf && d_hbuf);
 	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
-	fs_collapse<<<dim3(col_ctas + row_ctas, 1), 256, 0, (cudaStream_t) stream>>>(d_in, w, h, d_wbuf, d_hbuf, col_ctas);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "fs_collapse", (cudaStream_t) stream, fs_collapse<<<dim3(col_ctas + row_ctas, 1), 256, 0, (cudaStream_t) stream>>>(d_in, w, h, d_wbuf, d_hbuf, col_ctas));
 	return TSDRGPU_OK;
 }
 

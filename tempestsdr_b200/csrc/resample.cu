@@ -243,8 +243,7 @@ int tsdrgpu_am_demod(tsdrgpu_ctx_t *ctx, void *stream, const float *d_iq, uint64
 	ARG_TRY(ctx, d_iq != NULL && d_out != NULL);
 	const unsigned long long want = (pairs + 255) / 256;
 	const unsigned grid = (unsigned) (want < (unsigned long long) ctx->sm_count * 16 ? want : (unsigned long long) ctx->sm_count * 16);
-	demod_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(reinterpret_cast<const float2 *>(d_iq), d_out, pairs);
-	LAUNCH_CHECK(ctx);
+	KL(ctx, "demod_kernel", (cudaStream_t) stream, demod_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(reinterpret_cast<const float2 *>(d_iq), d_out, pairs));
 	return TSDRGPU_OK;
 }
 
@@ -360,9 +359,8 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 
 	if (nearest) {
 		dim3 grid((max_out + 1023) / 1024, nblocks);
-		if (in_is_iq) rs_nearest<true><<<grid, 256, 0, stream>>>(d_in, d_out, db);
-		else rs_nearest<false><<<grid, 256, 0, stream>>>(d_in, d_out, db);
-		LAUNCH_CHECK(ctx);
+		if (in_is_iq) KL(ctx, "rs_nearest", stream, rs_nearest<true><<<grid, 256, 0, stream>>>(d_in, d_out, db));
+		else KL(ctx, "rs_nearest", stream, rs_nearest<false><<<grid, 256, 0, stream>>>(d_in, d_out, db));
 	} else {
 		if (r->bank_cap < (size_t) nblocks + 1) {
 			if (r->d_bank) { CU_TRY(ctx, cudaStreamSynchronize(stream)); CU_TRY(ctx, cudaFree(r->d_bank)); CU_TRY(ctx, cudaFree(r->d_has_a)); }
@@ -370,12 +368,10 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			CU_TRY(ctx, cudaMalloc(&r->d_bank, sizeof(double) * r->bank_cap));
 			CU_TRY(ctx, cudaMalloc(&r->d_has_a, sizeof(int) * r->bank_cap));
 		}
-		if (in_is_iq) rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks);
-		else rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks);
-		LAUNCH_CHECK(ctx);
-		if (in_is_iq) rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib);
-		else rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib);
-		LAUNCH_CHECK(ctx);
+		if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks));
+		else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks));
+		if (in_is_iq) KL(ctx, "rs_fixup", stream, rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
+		else KL(ctx, "rs_fixup", stream, rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 	}
 	r->offset = off;
 	if (h_n_out) *h_n_out = total;
