@@ -328,7 +328,11 @@ static int drain_blocks(tsdrgpu_pipeline *p) {
 	if (block == 0) return TSDRGPU_OK;
 	const uint32_t min_blocks = p->cfg.batch_blocks > 0 ? (uint32_t) p->cfg.batch_blocks : 10;
 	while (p->decim_fill / block >= min_blocks) {
-		const uint32_t nb = (uint32_t) (p->decim_fill / block) > 4096 ? 4096 : (uint32_t) (p->decim_fill / block);
+		// whole multiples of the batch size, so the grouping (and with it every result) does not depend on how the
+		// plugin happened to cut the stream into process() calls
+		uint32_t nb = (uint32_t) ((p->decim_fill / block / min_blocks) * min_blocks);
+		if (nb > 4000) nb = (4000 / min_blocks) * min_blocks;
+		if (nb == 0) nb = min_blocks;
 		const double up = (double) (w * h) * fv;        // width*height*refreshrate, TSDRLibrary.c:340
 		const uint64_t npix = tsdrgpu_resampler_plan(p->rs, NULL, block, nb, up, (double) fs_);
 		if (npix == 0) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "resampler plan produced no pixels", cudaSuccess, __FILE__, __LINE__);

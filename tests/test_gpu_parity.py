@@ -233,8 +233,21 @@ def test_fft(gpu, O, logn):
         want = O.fft(x, inv)
         d = dev(x)
         gpu.fft_perform(d, n, inv)
-        # tolerance: 2e-6 of the peak bin (both sides keep float32 between stages; see fft.cu header)
-        _close(d, want, 2e-6 if logn <= 20 else 4e-6, f"fft 2^{logn} inv={inv}")
+        # tolerance: 2e-6 of the peak bin up to 2^20 (both sides keep float32 between stages; see fft.cu header).
+        # Above that the REFERENCE itself drifts from the true DFT: its stage twiddles come from the half-angle
+        # recurrence c2 = sqrt((1-c1)/2) (fft.c:161), which cancels catastrophically for small angles -- the
+        # relative error of sin(pi/2^l) grows 4x per stage (~3e-6 at 2^20, ~5e-5 at 2^23).  So the bound scales
+        # 4x per doubling, and the CUDA result must be the one closer to a float64 DFT.
+        tol = 2e-6 if logn <= 20 else 2e-6 * 4 ** (logn - 20) * 1.5
+        err, _ = _close(d, want, tol, f"fft 2^{logn} inv={inv}")
+        if logn >= 20:
+            xc = x[0::2].astype(np.float64) + 1j * x[1::2].astype(np.float64)
+            true = np.fft.ifft(xc) * n if inv else np.fft.fft(xc) / n
+            t = np.empty(2 * n); t[0::2] = true.real; t[1::2] = true.imag
+            peak = np.max(np.abs(t))
+            e_gpu = np.max(np.abs(d.cpu().numpy() - t)) / peak
+            e_ref = np.max(np.abs(want - t)) / peak
+            assert e_gpu <= 2e-6 and e_gpu <= e_ref + 1e-7, (e_gpu, e_ref)
 
 
 @pytest.mark.parametrize("size", [1, 5, 1000, 4096, 70_001, 450_909])
