@@ -117,40 +117,49 @@ class DeviceStep:
         self.up = w * HEIGHT * FV
         self.rs = gpu.resampler()
         self.pp = gpu.post_processor()
+        self.pp.set_overlap(True)                 # sync search + re-centring of batch k under the kernels of batch k+1
         self.frd = gpu.framerate_detector()
         self.flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True)     # the GUI's defaults
         self.cap = FrameRateDetector.capture_size(FS)
         max_pix = int(self.rs.plan((self.block, self.nblocks), self.up, float(FS))) + 1024
         self.pix = torch.empty(max_pix + self.n + 1024, dtype=torch.float32, device=iq_dev.device)
         self.pix_fill = 0
-        self.frames_out = torch.empty(FRAMES_PER_STEP * self.n, dtype=torch.float32, device=iq_dev.device)
-        self.capture = torch.empty(self.cap, dtype=torch.float32, device=iq_dev.device)
-        self.cap_fill = 0
+        self.frames_out = [torch.empty(FRAMES_PER_STEP * self.n, dtype=torch.float32, device=iq_dev.device) for _ in range(2)]
+        self.pairs = self.block * self.nblocks
+        self.mag = torch.empty(self.cap + self.pairs, dtype=torch.float32, device=iq_dev.device)   # demodulated stream, capture-aligned
+        self.mag_fill = 0
         self.frames = 0
         self.captures = 0
-        self.pairs = self.block * self.nblocks
+        self.k = 0
 
     def __call__(self):
-        torch, gpu = self.torch, self.gpu
+        gpu = self.gpu
         # samples -> pixels (fused demod + resample), appended behind the pixels left over from the last step
         out = self.rs.process(self.iq, (self.block, self.nblocks), self.up, float(FS), in_is_iq=True, out=self.pix[self.pix_fill:])
         self.pix_fill += out.numel()
         nf = min(self.pix_fill // self.n, FRAMES_PER_STEP)
-        self.pp.process(self.pix[: nf * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=self.frames_out[: nf * self.n], want_results=False)
+        self.pp.process(self.pix[: nf * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=self.frames_out[self.k & 1][: nf * self.n], want_results=False)
+        self.k += 1
         left = self.pix_fill - nf * self.n
         if left:
-            self.pix[:left].copy_(self.pix[nf * self.n: self.pix_fill].clone() if left > nf * self.n else self.pix[nf * self.n: self.pix_fill])
+            self.pix[:left].copy_(self.pix[nf * self.n: self.pix_fill])      # left << nf*n: the ranges do not overlap
         self.pix_fill = left
         self.frames += nf
-        # frame-rate detector: every capture of the stream
-        pos = 0
-        while pos < self.pairs:
-            take = min(self.cap - self.cap_fill, self.pairs - pos)
-            gpu.chk(gpu._lib.tsdrgpu_am_demod(gpu._h, gpu.stream, self.iq.data_ptr() + 8 * pos, take, self.capture.data_ptr() + 4 * self.cap_fill))
-            self.cap_fill += take; pos += take
-            if self.cap_fill == self.cap:
-                self.frd.run(FS, self.capture, copy_out=False)
-                self.cap_fill = 0; self.captures += 1
+        # frame-rate detector: the whole stream is demodulated once; every complete capture of 3.1*fs/55 samples is
+        # autocorrelated (batched FFTs) and accumulated in order
+        gpu.chk(gpu._lib.tsdrgpu_am_demod(gpu._h, gpu.stream, self.iq.data_ptr(), self.pairs, self.mag.data_ptr() + 4 * self.mag_fill))
+        self.mag_fill += self.pairs
+        ncap = self.mag_fill // self.cap
+        if ncap:
+            self.frd.run_batch(FS, self.mag, self.cap, ncap, self.cap)
+            rest = self.mag_fill - ncap * self.cap
+            if rest:
+                self.mag[:rest].copy_(self.mag[ncap * self.cap: self.mag_fill])
+            self.mag_fill = rest
+            self.captures += ncap
+
+    def join(self):
+        self.pp.join()
 
 
 def collect_profile(gpu):
@@ -233,6 +242,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    step.join()                                   # the side stream's tail (last sync search + re-centring) is inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

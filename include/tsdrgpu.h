@@ -166,6 +166,13 @@ TSDRGPU_API int  tsdrgpu_framestage_run_async(tsdrgpu_framestage_t *fs, void *st
                                               float *d_frames_out, tsdrgpu_frame_result_t *h_results_pinned,
                                               int32_t *h_autogain_report);
 
+/* Overlap mode (off by default).  When on, and for the default stage order (LOWPASS_BEFORE_SYNC set,
+ * AUTOGAIN_AFTER_PROC clear), the latency-bound sync search and the re-centring of batch k run on an internal side
+ * stream while `stream` already works on batch k+1.  d_frames_out / h_results_pinned of a run are then valid only
+ * after tsdrgpu_framestage_join(fs, s) has made stream `s` wait for the side stream (or after a device sync). */
+TSDRGPU_API int  tsdrgpu_framestage_set_overlap(tsdrgpu_framestage_t *fs, int on);
+TSDRGPU_API int  tsdrgpu_framestage_join(tsdrgpu_framestage_t *fs, void *stream);
+
 /* stage-level entry points (same arithmetic as the kernels inside tsdrgpu_framestage_run) */
 TSDRGPU_API int tsdrgpu_autogain(tsdrgpu_ctx_t *ctx, void *stream, float *h_lastmax, float *h_lastmin, float *h_snr,
                                  int n, const float *d_in, float *d_out, float norm);        /* synchronises */
@@ -188,6 +195,10 @@ TSDRGPU_API int tsdrgpu_pixels_argb(tsdrgpu_ctx_t *ctx, void *stream, const floa
 TSDRGPU_API uint32_t tsdrgpu_fft_getrealsize(uint32_t size);                                   /* fft.c:5-11 */
 TSDRGPU_API int tsdrgpu_fft(tsdrgpu_ctx_t *ctx, void *stream, float *d_iq, uint32_t size, int inverse);   /* in place */
 TSDRGPU_API int tsdrgpu_autocorrelation(tsdrgpu_ctx_t *ctx, void *stream, float *d_answer, const float *d_real, uint32_t size);
+/* `batch` independent autocorrelations in one set of launches: input b at d_reals + b*real_stride (floats), output b at
+ * d_answers + b*2*size (floats).  size must be even. */
+TSDRGPU_API int tsdrgpu_autocorrelation_batch(tsdrgpu_ctx_t *ctx, void *stream, float *d_answers, const float *d_reals, uint32_t size,
+                                              uint32_t batch, uint64_t real_stride);
 TSDRGPU_API int tsdrgpu_crosscorrelation(tsdrgpu_ctx_t *ctx, void *stream, float *d_a_out, float *d_b_tmp, uint32_t samples);
 
 /* ---------------------------------------------------------------------------- a17/a18  frame-rate detector
@@ -206,6 +217,13 @@ TSDRGPU_API int  tsdrgpu_frd_run(tsdrgpu_frd_t *frd, void *stream, uint32_t samp
 /* same without the final synchronisation; the h_* buffers must be page-locked */
 TSDRGPU_API int  tsdrgpu_frd_run_async(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
                                        double *h_frame_plot_pinned, int frame_cap, double *h_line_plot_pinned, int line_cap, uint64_t *calls);
+/* `batch` consecutive captures (capture b at d_captures + b*capture_stride floats) accumulated in order, as if
+ * tsdrgpu_frd_run had been called batch times; asynchronous, plots stay on the device. */
+TSDRGPU_API int  tsdrgpu_frd_run_batch(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_captures, uint32_t size,
+                                       uint32_t batch, uint64_t capture_stride, uint64_t *calls);
+/* copies the current running means (device-resident) to host buffers; synchronises */
+TSDRGPU_API int  tsdrgpu_frd_get_plots(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, double *h_frame_plot, int frame_cap,
+                                       double *h_line_plot, int line_cap);
 TSDRGPU_API int  tsdrgpu_accumulate(tsdrgpu_ctx_t *ctx, void *stream, double *d_out, uint64_t calls,
                                     const float *d_in_complex, int startid, int length);
 

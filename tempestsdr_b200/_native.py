@@ -79,6 +79,8 @@ _SIGS = {
                                          C.c_uint, C.c_void_p, C.POINTER(FrameResult)]),
     "tsdrgpu_framestage_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                                C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tsdrgpu_framestage_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsdrgpu_framestage_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_autogain": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_float]),
     "tsdrgpu_timelowpass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
@@ -88,6 +90,7 @@ _SIGS = {
     "tsdrgpu_fft_getrealsize": (C.c_uint32, [C.c_uint32]),
     "tsdrgpu_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
     "tsdrgpu_autocorrelation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "tsdrgpu_autocorrelation_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]),
     "tsdrgpu_crosscorrelation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "tsdrgpu_frd_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_frd_destroy": (None, [C.c_void_p]),
@@ -98,6 +101,8 @@ _SIGS = {
                                   C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "tsdrgpu_frd_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_frd_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_frd_get_plots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "tsdrgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]),
     "tsdrgpu_complex_to_abs_diff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "tsdrgpu_superb_bestfit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),

@@ -265,6 +265,14 @@ class PostProcessor:
     def reset(self):
         self.ctx.chk(self.ctx._lib.tsdrgpu_framestage_reset(self._h, self.ctx.stream))
 
+    def set_overlap(self, on: bool):
+        """Run the sync search + re-centring of batch k on a side stream under batch k+1 (see tsdrgpu.h); outputs are
+        valid after :meth:`join`."""
+        self.ctx.chk(self.ctx._lib.tsdrgpu_framestage_set_overlap(self._h, int(on)))
+
+    def join(self):
+        self.ctx.chk(self.ctx._lib.tsdrgpu_framestage_join(self._h, self.ctx.stream))
+
     def process(self, frames: torch.Tensor, width: int, height: int, motionblur: float = 0.0, lowpasscoeff: float = 0.1,
                 flags: PostProcessFlags = PostProcessFlags(), out: Optional[torch.Tensor] = None, want_results: bool = True):
         """frames: nframes*width*height float32, frames back to back.  Returns (frames_out, [FrameResult])."""
@@ -307,6 +315,21 @@ class FrameRateDetector:
         v = [C.c_int(0) for _ in range(4)]
         N.lib().tsdrgpu_frd_windows(samplerate, *[C.byref(x) for x in v])
         return tuple(x.value for x in v)
+
+    def run_batch(self, samplerate: int, captures: torch.Tensor, size: int, batch: int, stride: Optional[int] = None) -> int:
+        """`batch` consecutive captures of `size` samples (capture b at captures[b*stride:]) accumulated in order;
+        asynchronous, the plots stay on the device (see :meth:`plots`)."""
+        calls = C.c_uint64(0)
+        self.ctx.chk(self.ctx._lib.tsdrgpu_frd_run_batch(self._h, self.ctx.stream, samplerate, _f32(captures).data_ptr(), size, batch,
+                                                         stride if stride is not None else size, C.byref(calls)))
+        return calls.value
+
+    def plots(self, samplerate: int):
+        fmin, fmax, lmin, lmax = self.windows(samplerate)
+        fp, lp = np.zeros(fmax - fmin), np.zeros(lmax - lmin)
+        self.ctx.chk(self.ctx._lib.tsdrgpu_frd_get_plots(self._h, self.ctx.stream, samplerate, fp.ctypes.data_as(C.c_void_p), fp.size,
+                                                         lp.ctypes.data_as(C.c_void_p), lp.size))
+        return (fmin, fp), (lmin, lp)
 
     def run(self, samplerate: int, capture: torch.Tensor, copy_out: bool = True):
         fmin, fmax, lmin, lmax = self.windows(samplerate)

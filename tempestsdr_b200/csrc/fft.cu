@@ -28,7 +28,8 @@ constexpr int FFT_TABLE = 1 << FFT_MAX_LOG2L;
 constexpr int FFT_MAX_ELEMS = 16384;         // complex elements per CTA bundle (128 KB of shared memory)
 
 struct FftPass {
-	int log2L, C, c_fast_in, c_fast_out;
+	int log2L, C, log2C, c_fast_in, c_fast_out;
+	long long in_bs, out_bs;                            // batch strides (blockIdx.y), in elements of the in / out type
 	unsigned G_lo;
 	long long in_hi, in_lo, in_cs, in_js;
 	long long out_hi, out_lo, out_cs, out_ks;
@@ -51,13 +52,14 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 	extern __shared__ float2 s[];
 	const int L = 1 << P.log2L, C = P.C, LP = L + 1, total = C * L;
 	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g % P.G_lo;
-	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo;
-	const long long out_base = (long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo;
+	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs;
+	const long long out_base = (long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo + (long long) blockIdx.y * P.out_bs;
+	const int log2C = P.log2C;
 
 	// ---- load the bundle
 	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
 		int c, j;
-		if (P.c_fast_in) { c = idx % C; j = idx / C; } else { j = idx & (L - 1); c = idx >> P.log2L; }
+		if (P.c_fast_in) { c = idx & (C - 1); j = idx >> log2C; } else { j = idx & (L - 1); c = idx >> P.log2L; }
 		const long long src = in_base + (long long) c * P.in_cs + (long long) j * P.in_js;
 		float2 v;
 		if (P.in_real) v = make_float2(reinterpret_cast<const float *>(in)[src], 0.0f); else v = in[src];
@@ -73,12 +75,12 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 	while (stage_log < P.log2L) {
 		const bool radix4 = ((P.log2L - stage_log) & 1) == 0;       // one radix-2 stage first when log2 L is odd
 		if (radix4) {
-			const int per_line = L >> 2, work = C * per_line;
+			const int per_line = L >> 2, work = C * per_line, pl_log = P.log2L - 2;
 			#pragma unroll
 			for (int it = 0; it < 4; it++) {
 				const int widx = threadIdx.x + it * blockDim.x;
 				if (widx < work) {
-					const int c = widx / per_line, i = widx - c * per_line;
+					const int c = widx >> pl_log, i = widx & (per_line - 1);
 					const int k = i & (p - 1);
 					const float2 *line = s + c * LP;
 					const unsigned tq = (unsigned) k * (unsigned) (FFT_TABLE / (4 * p));
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 			for (int it = 0; it < 4; it++) {
 				const int widx = threadIdx.x + it * blockDim.x;
 				if (widx < work) {
-					const int c = widx / per_line, i = widx - c * per_line;
+					const int c = widx >> pl_log, i = widx & (per_line - 1);
 					const int k = i & (p - 1);
 					const int j = ((i - k) << 2) + k;
 					float2 *line = s + c * LP;
@@ -107,12 +109,12 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 			__syncthreads();
 			p <<= 2; stage_log += 2;
 		} else {
-			const int per_line = L >> 1, work = C * per_line;
+			const int per_line = L >> 1, work = C * per_line, pl_log = P.log2L - 1;
 			#pragma unroll
 			for (int it = 0; it < 8; it++) {
 				const int widx = threadIdx.x + it * blockDim.x;
 				if (widx < work) {
-					const int c = widx / per_line, i = widx - c * per_line;
+					const int c = widx >> pl_log, i = widx & (per_line - 1);
 					const int k = i & (p - 1);
 					const float2 *line = s + c * LP;
 					const float2 u0 = line[i];
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 			for (int it = 0; it < 8; it++) {
 				const int widx = threadIdx.x + it * blockDim.x;
 				if (widx < work) {
-					const int c = widx / per_line, i = widx - c * per_line;
+					const int c = widx >> pl_log, i = widx & (per_line - 1);
 					const int k = i & (p - 1);
 					const int j = ((i - k) << 1) + k;
 					float2 *line = s + c * LP;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 	// ---- inter-pass twiddle, scaling, optional |.|, store
 	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
 		int c, k;
-		if (P.c_fast_out) { c = idx % C; k = idx / C; } else { k = idx & (L - 1); c = idx >> P.log2L; }
+		if (P.c_fast_out) { c = idx & (C - 1); k = idx >> log2C; } else { k = idx & (L - 1); c = idx >> P.log2L; }
 		float2 v = s[c * LP + k];
 		if (P.tw_M) {
 			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
@@ -199,6 +201,21 @@ __global__ void k_accumulate(double *out, unsigned long long calls, const float2
 		const double re = (double) v.x, im = (double) v.y;
 		const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
 		out[i] = (calls == 0) ? mag : __ddiv_rn(__dadd_rn(__dmul_rn(out[i], before_n), mag), now_n);
+	}
+}
+// the same running mean for `batch` consecutive captures in order (one launch instead of `batch`)
+__global__ void k_accumulate_batch(double *out, unsigned long long first_calls, const float2 *in, long long in_stride, unsigned batch,
+                                   int startid, int length) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < length; i += gridDim.x * blockDim.x) {
+		double acc = out[i];
+		for (unsigned b = 0; b < batch; b++) {
+			const unsigned long long calls = first_calls + b;
+			const float2 v = in[(size_t) b * in_stride + startid + i];
+			const double re = (double) v.x, im = (double) v.y;
+			const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+			acc = (calls == 0) ? mag : __ddiv_rn(__dadd_rn(__dmul_rn(acc, (double) (calls - 1)), mag), (double) calls);
+		}
+		out[i] = acc;
 	}
 }
 // first difference of magnitudes, out of place                          (superbandwidth.c:67-81)
@@ -283,29 +300,37 @@ int bundle_for(int log2L, unsigned long long lines) {
 	return C < 1 ? 1 : C;
 }
 
-int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, const FftPass &P, unsigned bundles, int inverse) {
+int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, FftPass P, unsigned bundles, int inverse,
+                unsigned batch, long long in_bs, long long out_bs) {
+	P.in_bs = in_bs; P.out_bs = out_bs;
+	P.log2C = 0; while ((1 << P.log2C) < P.C) P.log2C++;
 	const int L = 1 << P.log2L, total = P.C * L;
 	int threads = (total / 16 + 31) / 32 * 32;           // <= 4 radix-4 (8 radix-2) butterflies per thread
 	if (threads < 64) threads = 64;
 	if (total / 4 >= 256 && threads < 256) threads = 256;
 	if (threads > 1024) threads = 1024;
 	const size_t smem = sizeof(float2) * (size_t) P.C * (L + 1);
-	KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<<<bundles, threads, smem, stream>>>(in, out, P, g_table[ctx->device], inverse));
+	KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<<<dim3(bundles, batch), threads, smem, stream>>>(in, out, P, g_table[ctx->device], inverse));
 	return TSDRGPU_OK;
 }
 
-struct FftOpts { const float *real_in; bool out_abs; float scale; };
+struct FftOpts {
+	const float *real_in; bool out_abs; float scale;
+	unsigned batch;                 // independent transforms (grid.y)
+	long long data_bs, scratch_bs, real_bs;   // distance between consecutive transforms in data (complex), scratch (complex), real_in (floats)
+};
 
 // N-point transform of `data` (complex, natural order) through `scratch`; result lands in `data`.
 // With opts.real_in the input is read from a real array instead (data is output only).
 int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scratch, unsigned log2N, int inverse, FftOpts o) {
 	const unsigned long long N = 1ull << log2N;
 	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : data;
+	const long long in0_bs = o.real_in ? o.real_bs : o.data_bs;
 	FftPass P; memset(&P, 0, sizeof P);
 	if (log2N <= FFT_MAX_LOG2L) {                       // one pass, one CTA
 		P.log2L = (int) log2N; P.C = 1; P.G_lo = 1; P.in_js = 1; P.out_ks = 1; P.scale = o.scale;
 		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs;
-		return launch_pass(ctx, stream, src0, data, P, 1, inverse);
+		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs);
 	}
 	int rc;
 	if (log2N <= 2 * FFT_MAX_LOG2L) {                   // N = N1 * N2 ; n = N2*n1 + n2 ; k = k1 + N1*k2
@@ -316,14 +341,14 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N2;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N2;
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
-		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse))) return rc;
+		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs))) return rc;
 		FftPass Q; memset(&Q, 0, sizeof Q);
 		Q.log2L = (int) l2; Q.C = bundle_for((int) l2, N1); Q.c_fast_in = 0; Q.c_fast_out = 1;
 		Q.G_lo = (unsigned) (N1 / Q.C);
 		Q.in_lo = (long long) Q.C * (long long) N2; Q.in_cs = (long long) N2; Q.in_js = 1;
 		Q.out_lo = Q.C; Q.out_cs = 1; Q.out_ks = (long long) N1;
 		Q.scale = o.scale; Q.out_abs = o.out_abs;
-		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse);
+		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse, o.batch, o.scratch_bs, o.data_bs);
 	}
 	// N = N1*N2*N3 ; n = N2N3 n1 + N3 n2 + n3 ; k = k1 + N1 k2 + N1N2 k3
 	const unsigned l1 = (log2N + 2) / 3, l2 = (log2N - l1 + 1) / 2, l3 = log2N - l1 - l2;
@@ -335,7 +360,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N23;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N23;
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
-		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse))) return rc;
+		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs))) return rc;
 	}
 	{   // pass B: for every k1, length N2 along stride N3, bundle over adjacent n3 (in place in scratch)
 		FftPass B; memset(&B, 0, sizeof B);
@@ -344,7 +369,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		B.in_hi = (long long) N23; B.in_lo = B.C; B.in_cs = 1; B.in_js = (long long) N3;
 		B.out_hi = (long long) N23; B.out_lo = B.C; B.out_cs = 1; B.out_ks = (long long) N3;
 		B.tw_M = N23; B.tw_lo = B.C; B.tw_cs = 1; B.scale = 1.0f;
-		if ((rc = launch_pass(ctx, stream, scratch, scratch, B, (unsigned) (N1 * B.G_lo), inverse))) return rc;
+		if ((rc = launch_pass(ctx, stream, scratch, scratch, B, (unsigned) (N1 * B.G_lo), inverse, o.batch, o.scratch_bs, o.scratch_bs))) return rc;
 	}
 	{   // pass C: contiguous lines of N3 at (k1,k2); bundle over adjacent k1; output k1 + N1 k2 + N1N2 k3
 		FftPass Cc; memset(&Cc, 0, sizeof Cc);
@@ -353,7 +378,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		Cc.in_hi = (long long) N3; Cc.in_lo = (long long) Cc.C * (long long) N23; Cc.in_cs = (long long) N23; Cc.in_js = 1;
 		Cc.out_hi = (long long) N1; Cc.out_lo = Cc.C; Cc.out_cs = 1; Cc.out_ks = (long long) (N1 * N2);
 		Cc.scale = o.scale; Cc.out_abs = o.out_abs;
-		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse);
+		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse, o.batch, o.scratch_bs, o.data_bs);
 	}
 }
 
@@ -368,7 +393,7 @@ int tsdrgpu_fft_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, 
 	if (n_pow2 <= 1) return TSDRGPU_OK;
 	void *scratch;
 	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * n_pow2, &scratch))) return rc;
-	FftOpts o; o.real_in = NULL; o.out_abs = false; o.scale = inverse ? 1.0f : 1.0f / (float) n_pow2;
+	FftOpts o; memset(&o, 0, sizeof o); o.batch = 1; o.scale = inverse ? 1.0f : 1.0f / (float) n_pow2;
 	return fft_run(ctx, stream, data, (float2 *) scratch, ilog2(n_pow2), inverse, o);
 }
 
@@ -393,30 +418,48 @@ int tsdrgpu_fft(tsdrgpu_ctx_t *ctx, void *stream, float *d_iq, uint32_t size, in
 	return tsdrgpu_fft_internal(ctx, (cudaStream_t) stream, reinterpret_cast<float2 *>(d_iq), tsdrgpu_fft_getrealsize(size), inverse);
 }
 
-int tsdrgpu_autocorrelation(tsdrgpu_ctx_t *ctx, void *stream_, float *d_answer, const float *d_real, uint32_t size) {
-	BIND(ctx); ARG_TRY(ctx, d_answer != NULL && d_real != NULL);
-	if (size == 0) return TSDRGPU_OK;
-	cudaStream_t stream = (cudaStream_t) stream_;
+// batch of independent autocorrelations: transform b reads d_real + b*real_stride (floats) and writes
+// d_answer + b*answer_stride (floats, 2*size each).  skip_tail leaves answer[2N .. 2*size) untouched (the
+// frame-rate detector never reads lags >= N).
+static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float *d_answer, long long answer_stride,
+                                 const float *d_real, long long real_stride, uint32_t size, unsigned batch, bool skip_tail) {
 	int rc = ensure_table(ctx, stream);
 	if (rc) return rc;
 	const unsigned long long N = tsdrgpu_fft_getrealsize(size);
 	float2 *ans = reinterpret_cast<float2 *>(d_answer);
 	void *scratch;
-	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N, &scratch))) return rc;
-	if (N == 1) {
-		KL(ctx, "k_real_to_complex", stream, k_real_to_complex<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, d_real, 0, size));
-		KL(ctx, "k_abs", stream, k_abs<<<grid1d(size, ctx->sm_count), 256, 0, stream>>>(ans, 0, size));
-		return TSDRGPU_OK;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N * batch, &scratch))) return rc;
+	if (N == 1 || !skip_tail) {
+		for (unsigned b = 0; b < batch; b++) {       // the part that never enters a transform (fft.c:52-60): (|x|, 0)
+			const unsigned long long from = (N == 1) ? 0 : N;
+			if (from >= size) break;
+			float2 *a = reinterpret_cast<float2 *>(d_answer + (long long) b * answer_stride);
+			KL(ctx, "k_real_to_complex", stream, k_real_to_complex<<<grid1d(size - from, ctx->sm_count), 256, 0, stream>>>(a, d_real + (long long) b * real_stride, from, size));
+			KL(ctx, "k_abs", stream, k_abs<<<grid1d(size - from, ctx->sm_count), 256, 0, stream>>>(a, from, size));
+		}
+		if (N == 1) return TSDRGPU_OK;
 	}
 	// forward transform of the first N samples, real input widened on load, |X|/N on store
-	FftOpts f; f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N;
+	FftOpts f; memset(&f, 0, sizeof f);
+	f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N; f.batch = batch;
+	f.data_bs = answer_stride / 2; f.scratch_bs = (long long) N; f.real_bs = real_stride;
 	if ((rc = fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 0, f))) return rc;
-	if (size > N) {                                       // the tail never enters a transform (fft.c:52-60)
-		KL(ctx, "k_real_to_complex", stream, k_real_to_complex<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, d_real, N, size));
-		KL(ctx, "k_abs", stream, k_abs<<<grid1d(size - N, ctx->sm_count), 256, 0, stream>>>(ans, N, size));
-	}
-	FftOpts b; b.real_in = NULL; b.out_abs = false; b.scale = 1.0f;
-	return fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 1, b);
+	FftOpts g; memset(&g, 0, sizeof g);
+	g.scale = 1.0f; g.batch = batch; g.data_bs = answer_stride / 2; g.scratch_bs = (long long) N;
+	return fft_run(ctx, stream, ans, (float2 *) scratch, ilog2(N), 1, g);
+}
+
+int tsdrgpu_autocorrelation(tsdrgpu_ctx_t *ctx, void *stream, float *d_answer, const float *d_real, uint32_t size) {
+	BIND(ctx); ARG_TRY(ctx, d_answer != NULL && d_real != NULL);
+	if (size == 0) return TSDRGPU_OK;
+	return autocorrelation_batch(ctx, (cudaStream_t) stream, d_answer, 2ll * size, d_real, size, size, 1, false);
+}
+
+int tsdrgpu_autocorrelation_batch(tsdrgpu_ctx_t *ctx, void *stream, float *d_answers, const float *d_reals, uint32_t size,
+                                  uint32_t batch, uint64_t real_stride) {
+	BIND(ctx); ARG_TRY(ctx, d_answers != NULL && d_reals != NULL && (size & 1) == 0);
+	if (size == 0 || batch == 0) return TSDRGPU_OK;
+	return autocorrelation_batch(ctx, (cudaStream_t) stream, d_answers, 2ll * size, d_reals, (long long) real_stride, size, batch, false);
 }
 
 int tsdrgpu_crosscorrelation(tsdrgpu_ctx_t *ctx, void *stream_, float *d_a, float *d_b, uint32_t samples) {
@@ -466,19 +509,23 @@ void tsdrgpu_frd_windows(uint32_t samplerate, int *frame_min, int *frame_max, in
 }
 
 static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, const float *d_capture, uint32_t size,
+                        uint32_t batch, uint64_t capture_stride,
                         double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls, bool synchronise) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
 	tsdrgpu_ctx_t *ctx = f->ctx;
-	BIND(ctx); ARG_TRY(ctx, d_capture != NULL && size > 0);
+	BIND(ctx); ARG_TRY(ctx, d_capture != NULL && size > 0 && batch > 0);
 	cudaStream_t stream = (cudaStream_t) stream_;
 	int fmin, fmax, lmin, lmax;
 	tsdrgpu_frd_windows(samplerate, &fmin, &fmax, &lmin, &lmax);
 	const int flen = fmax - fmin, llen = lmax - lmin;
+	const uint32_t N = tsdrgpu_fft_getrealsize(size);
 	ARG_TRY(ctx, (uint64_t) fmax <= (uint64_t) size && flen >= 0 && llen >= 0);
-	if (f->big_cap < 2ull * size) {
+	const bool skip_tail = (uint32_t) fmax <= N;               // always true for the detector's own capture size
+	const size_t big_need = 2ull * size * batch;
+	if (f->big_cap < big_need) {
 		CU_TRY(ctx, cudaStreamSynchronize(stream));
 		if (f->d_big) CU_TRY(ctx, cudaFree(f->d_big));
-		CU_TRY(ctx, cudaMalloc(&f->d_big, sizeof(float) * 2ull * size)); f->big_cap = 2ull * size;
+		CU_TRY(ctx, cudaMalloc(&f->d_big, sizeof(float) * big_need)); f->big_cap = big_need;
 	}
 	if (f->p1_cap < (size_t) flen || f->fresh) {
 		if (f->p1_cap < (size_t) flen) { CU_TRY(ctx, cudaStreamSynchronize(stream)); if (f->d_p1) CU_TRY(ctx, cudaFree(f->d_p1)); CU_TRY(ctx, cudaMalloc(&f->d_p1, sizeof(double) * (flen + 1))); f->p1_cap = flen; }
@@ -489,11 +536,12 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 		CU_TRY(ctx, cudaMemsetAsync(f->d_p2, 0, sizeof(double) * (llen + 1), stream));
 	}
 	if (f->fresh) { f->calls = 0; f->fresh = 0; }
-	f->calls++;                                           // extbuffer.c:81, one prepare per capture
+	const uint64_t first_calls = f->calls + 1;                  // extbuffer.c:81, one prepare per capture
+	f->calls += batch;
 	int rc;
-	if ((rc = tsdrgpu_autocorrelation(ctx, stream, f->d_big, d_capture, size))) return rc;
-	if ((rc = tsdrgpu_accumulate(ctx, stream, f->d_p1, f->calls, f->d_big, fmin, flen))) return rc;
-	if ((rc = tsdrgpu_accumulate(ctx, stream, f->d_p2, f->calls, f->d_big, lmin, llen))) return rc;
+	if ((rc = autocorrelation_batch(ctx, stream, f->d_big, 2ll * size, d_capture, (long long) capture_stride, size, batch, skip_tail))) return rc;
+	if (flen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) flen, ctx->sm_count), 256, 0, stream>>>(f->d_p1, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, fmin, flen));
+	if (llen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) llen, ctx->sm_count), 256, 0, stream>>>(f->d_p2, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, lmin, llen));
 	if (calls) *calls = f->calls;
 	if (h_frame_plot || h_line_plot) {
 		if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
@@ -505,11 +553,31 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 
 int tsdrgpu_frd_run(tsdrgpu_frd_t *f, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
                     double *h_frame_plot, int frame_cap, double *h_line_plot, int line_cap, uint64_t *calls) {
-	return frd_run_impl(f, stream, samplerate, d_capture, size, h_frame_plot, frame_cap, h_line_plot, line_cap, calls, true);
+	return frd_run_impl(f, stream, samplerate, d_capture, size, 1, size, h_frame_plot, frame_cap, h_line_plot, line_cap, calls, true);
+}
+int tsdrgpu_frd_run_batch(tsdrgpu_frd_t *f, void *stream, uint32_t samplerate, const float *d_captures, uint32_t size, uint32_t batch,
+                          uint64_t capture_stride, uint64_t *calls) {
+	return frd_run_impl(f, stream, samplerate, d_captures, size, batch, capture_stride, NULL, 0, NULL, 0, calls, false);
 }
 int tsdrgpu_frd_run_async(tsdrgpu_frd_t *f, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size,
                           double *h_frame_plot_pinned, int frame_cap, double *h_line_plot_pinned, int line_cap, uint64_t *calls) {
-	return frd_run_impl(f, stream, samplerate, d_capture, size, h_frame_plot_pinned, frame_cap, h_line_plot_pinned, line_cap, calls, false);
+	return frd_run_impl(f, stream, samplerate, d_capture, size, 1, size, h_frame_plot_pinned, frame_cap, h_line_plot_pinned, line_cap, calls, false);
+}
+
+int tsdrgpu_frd_get_plots(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, double *h_frame_plot, int frame_cap,
+                          double *h_line_plot, int line_cap) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
+	tsdrgpu_ctx_t *ctx = f->ctx;
+	BIND(ctx);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	int fmin, fmax, lmin, lmax;
+	tsdrgpu_frd_windows(samplerate, &fmin, &fmax, &lmin, &lmax);
+	const int flen = fmax - fmin, llen = lmax - lmin;
+	ARG_TRY(ctx, f->p1_cap >= (size_t) flen && f->p2_cap >= (size_t) llen);
+	if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
+	if (h_line_plot) CU_TRY(ctx, cudaMemcpyAsync(h_line_plot, f->d_p2, sizeof(double) * (size_t) (llen < line_cap ? llen : line_cap), cudaMemcpyDeviceToHost, stream));
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	return TSDRGPU_OK;
 }
 
 // ---- superbandwidth ----------------------------------------------------------------------------------------------

@@ -239,18 +239,54 @@ __device__ void blur_strip(const float *__restrict__ src, float *__restrict__ ds
 	}
 }
 
-// the serial part of findbestfit: window sums for every start position, written to `cs` (global scratch).
-// cs[0] = sum of the first `strip` elements; cs[e] = window sum after the e-th slide (syncdetector.c:31-49)
-__device__ void window_sums(const float *__restrict__ data, int size, int strip, double *__restrict__ cs) {
+// the serial part of findbestfit: window sums for every start position (syncdetector.c:31-49).
+// cs[0] = sum of the first `strip` elements; cs[e] = window sum after the e-th slide.  `data` already holds the
+// blurred strip widened to double (exact), so the dependent chain is two DADDs per step; the operands of the next
+// 8 steps are fetched before the chain needs them (a warp issues in order: without this every step would also
+// wait for a shared-memory load).
+__device__ void window_sums(const double *__restrict__ data, int size, int strip, double *__restrict__ cs) {
 	double cur = 0.0;
-	for (int i = 0; i < strip; i++) cur = __dadd_rn(cur, (double) data[i]);
+	int i = 0;
+	for (; i + 8 <= strip; i += 8) {
+		double v[8];
+		#pragma unroll
+		for (int u = 0; u < 8; u++) v[u] = data[i + u];
+		#pragma unroll
+		for (int u = 0; u < 8; u++) cur = __dadd_rn(cur, v[u]);
+	}
+	for (; i < strip; i++) cur = __dadd_rn(cur, data[i]);
 	cs[0] = cur;
-	const int wrap_at = size - strip;
-	for (int i = 0; i < size - 1; i++) {
-		const int enter = (i < wrap_at) ? (i + strip) : (i - wrap_at);
-		cur = __dadd_rn(__dsub_rn(cur, (double) data[i]), (double) data[enter]);
+	const int wrap_at = size - strip, last = size - 1;
+	i = 0;
+	for (; i + 8 <= last; i += 8) {
+		double rem[8], add[8];
+		#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const int k = i + u;
+			rem[u] = data[k];
+			add[u] = data[(k < wrap_at) ? (k + strip) : (k - wrap_at)];
+		}
+		#pragma unroll
+		for (int u = 0; u < 8; u++) { cur = __dadd_rn(__dsub_rn(cur, rem[u]), add[u]); cs[i + u + 1] = cur; }
+	}
+	for (; i < last; i++) {
+		cur = __dadd_rn(__dsub_rn(cur, data[i]), data[(i < wrap_at) ? (i + strip) : (i - wrap_at)]);
 		cs[i + 1] = cur;
 	}
+}
+
+__device__ double strip_total(const double *__restrict__ data, int size) {       // syncdetector.c:81-82
+	double tot = 0.0;
+	int i = 0;
+	for (; i + 8 <= size; i += 8) {
+		double v[8];
+		#pragma unroll
+		for (int u = 0; u < 8; u++) v[u] = data[i + u];
+		#pragma unroll
+		for (int u = 0; u < 8; u++) tot = __dadd_rn(tot, v[u]);
+	}
+	for (; i < size; i++) tot = __dadd_rn(tot, data[i]);
+	return tot;
 }
 
 __device__ __forceinline__ double fit_score(double total, double cs, double n_out, double n_in) {
@@ -265,87 +301,100 @@ __device__ __forceinline__ Best best_merge(Best a, Best b) {
 	return a;
 }
 
+// exact 5-tap circular blur of one strip straight from global memory into a double array (gaussian.c:18-79)
+__device__ void blur_to_double(const float *__restrict__ src, double *__restrict__ dst, int n, const float *c, float *tmp) {
+	if (n >= 5) {
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			const int a = (j + n - 2) % n, b = (j + n - 1) % n, d = (j + 1) % n, e = (j + 2) % n;
+			float acc = __fmul_rn(__ldg(src + a), c[0]);
+			acc = __fadd_rn(acc, __fmul_rn(__ldg(src + b), c[1]));
+			acc = __fadd_rn(acc, __fmul_rn(__ldg(src + j), c[2]));
+			acc = __fadd_rn(acc, __fmul_rn(__ldg(src + d), c[3]));
+			acc = __fadd_rn(acc, __fmul_rn(__ldg(src + e), c[4]));
+			dst[j] = (double) acc;
+		}
+	} else {                          // degenerate strips: literal replay through the float helper
+		if (threadIdx.x < n) tmp[threadIdx.x] = src[threadIdx.x];
+		__syncthreads();
+		blur_strip(tmp, tmp + 8, n, c);
+		__syncthreads();
+		if (threadIdx.x < n) dst[threadIdx.x] = (double) tmp[8 + threadIdx.x];
+	}
+}
+
+// One CTA walks the frames of the batch in order (the strip size and dx carry from frame to frame).
+// Per frame: blur both strips (all threads) | 12 serial double chains in 12 warps (2 totals, <=10 window-sum chains)
+// | 10 warps score one candidate each, first-max reduce | thread 0: pick the strip size, update dx/vx, PLL average.
 __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
                                                            int w, int h, int minsize_x, int minsize_y, int nframes,
                                                            float c0, float c1, float c2, float c3, float c4,
-                                                           SyncState *state, double *__restrict__ chain_scratch,
-                                                           const FrameParams *__restrict__ params, tsdrgpu_frame_result_t *results) {
-	extern __shared__ float smem[];
-	float *raw_x = smem, *blur_x = raw_x + w, *raw_y = blur_x + w, *blur_y = raw_y + h;
+                                                           SyncState *state, double *__restrict__ chain_scratch, int chains_in_smem,
+                                                           tsdrgpu_frame_result_t *results) {
+	extern __shared__ double smem_d[];
+	double *dbl_x = smem_d, *dbl_y = dbl_x + w;
+	double *cs_base = chains_in_smem ? (dbl_y + h) : chain_scratch;
+	const int cs_stride = chains_in_smem ? max(w, h) : FS_MAX_STRIP;
 	__shared__ int cand[2][5];           // strip sizes tried per axis, -1 = skipped
 	__shared__ float totalf[2];
-	__shared__ Best warp_best[FS_SYNC_THREADS / 32];
 	__shared__ Best cand_best[2][5];
 	__shared__ SyncState st;
+	__shared__ float tiny[16];
 	const float taps[5] = {c0, c1, c2, c3, c4};
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	if (threadIdx.x == 0) st = *state;
-	__syncthreads();
+
+	auto list_candidates = [&]() {       // clamp the carried strip size, list the sizes to try (syncdetector.c:73-77, 60-69, 88-93)
+		for (int ax = 0; ax < 2; ax++) {
+			const int size = ax ? h : w;
+			int minsize = ax ? minsize_y : minsize_x;
+			if (minsize < 1) minsize = 1;
+			const int half = size >> 1;
+			int &cur = ax ? st.y_strip : st.x_strip;
+			if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
+			const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
+			cand[ax][0] = cur;
+			for (int t = 1; t < 5; t++) cand[ax][t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
+		}
+	};
+	if (threadIdx.x == 0) { st = *state; list_candidates(); }
 
 	for (int f = 0; f < nframes; f++) {
-		for (int i = threadIdx.x; i < w; i += blockDim.x) raw_x[i] = wstrips[(size_t) f * w + i];
-		for (int i = threadIdx.x; i < h; i += blockDim.x) raw_y[i] = hstrips[(size_t) f * h + i];
-		if (threadIdx.x == 0) {
-			// clamp the carried strip size and list the sizes to try (syncdetector.c:73-77, 60-69, 88-93)
-			for (int ax = 0; ax < 2; ax++) {
-				const int size = ax ? h : w;
-				int minsize = ax ? minsize_y : minsize_x;
-				if (minsize < 1) minsize = 1;
-				const int half = size >> 1;
-				int &cur = ax ? st.y_strip : st.x_strip;
-				if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
-				const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
-				cand[ax][0] = cur;
-				for (int t = 1; t < 5; t++) cand[ax][t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
-			}
-		}
+		blur_to_double(wstrips + (size_t) f * w, dbl_x, w, taps, tiny);
+		blur_to_double(hstrips + (size_t) f * h, dbl_y, h, taps, tiny);
 		__syncthreads();
-		blur_strip(raw_x, blur_x, w, taps);
-		blur_strip(raw_y, blur_y, h, taps);
-		__syncthreads();
-		// serial chains, one per warp (lane 0): 2 totals + up to 10 window-sum chains
 		if (lane == 0 && warp < 12) {
-			if (warp < 2) {
-				const float *d = warp ? blur_y : blur_x; const int size = warp ? h : w;
-				double tot = 0.0;
-				for (int i = 0; i < size; i++) tot = __dadd_rn(tot, (double) d[i]);
-				totalf[warp] = __double2float_rn(tot);          // findbestfit takes a float (syncdetector.c:26)
-			} else {
+			if (warp < 2) totalf[warp] = __double2float_rn(strip_total(warp ? dbl_y : dbl_x, warp ? h : w));   // findbestfit takes a float
+			else {
 				const int ax = (warp - 2) / 5, t = (warp - 2) % 5;
 				const int strip = cand[ax][t];
-				if (strip > 0) window_sums(ax ? blur_y : blur_x, ax ? h : w, strip, chain_scratch + (size_t) (warp - 2) * FS_MAX_STRIP);
+				if (strip > 0) window_sums(ax ? dbl_y : dbl_x, ax ? h : w, strip, cs_base + (size_t) (warp - 2) * cs_stride);
 			}
 		}
 		__syncthreads();
-		// score every window of every candidate in parallel; keep the first maximum
-		for (int ci = 0; ci < 10; ci++) {
-			const int ax = ci / 5, t = ci % 5;
+		if (warp < 10) {                 // one warp scores one candidate
+			const int ax = warp / 5, t = warp % 5;
 			const int strip = cand[ax][t];
-			if (strip <= 0) { if (threadIdx.x == 0) { cand_best[ax][t].score = -1.0; cand_best[ax][t].e = -1; } continue; }
-			const int size = ax ? h : w;
-			const double total = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
-			const double *cs = chain_scratch + (size_t) ci * FS_MAX_STRIP;
-			Best b; b.score = -INFINITY; b.e = 0x7fffffff;
-			for (int e = threadIdx.x; e < size; e += blockDim.x) {
-				const double s = fit_score(total, cs[e], n_out, n_in);
-				if (s > b.score) { b.score = s; b.e = e; }
-			}
-			for (int o = 16; o > 0; o >>= 1) {
-				Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
-				b = best_merge(b, other);
-			}
-			if (lane == 0) warp_best[warp] = b;
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				Best r = warp_best[0];
-				for (int k = 1; k < FS_SYNC_THREADS / 32; k++) r = best_merge(r, warp_best[k]);
+			Best b; b.score = -1.0; b.e = -1;
+			if (strip > 0) {
+				const int size = ax ? h : w;
+				const double total = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
+				const double *cs = cs_base + (size_t) warp * cs_stride;
+				b.score = -INFINITY; b.e = 0x7fffffff;
+				#pragma unroll 4
+				for (int e = lane; e < size; e += 32) {
+					const double sc = fit_score(total, cs[e], n_out, n_in);
+					if (sc > b.score) { b.score = sc; b.e = e; }
+				}
+				for (int o = 16; o > 0; o >>= 1) {
+					Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
+					b = best_merge(b, other);
+				}
 				// e = 0 is the starting value of the reference's running maximum even when it is NaN
 				const double s0 = fit_score(total, cs[0], n_out, n_in);
-				if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
-				cand_best[ax][t] = r;
+				if (!(s0 == s0) || b.e == 0x7fffffff) { b.score = s0; b.e = 0; }
 			}
-			__syncthreads();
+			if (lane == 0) cand_best[ax][t] = b;
 		}
+		__syncthreads();
 		if (threadIdx.x == 0) {
 			for (int ax = 0; ax < 2; ax++) {
 				const int size = ax ? h : w;
@@ -375,15 +424,12 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restri
 			// frameratepll bookkeeping (syncdetector.c:134-139); the refreshrate write-back is the host's
 			st.avg_speed = __dadd_rn(__dmul_rn(st.avg_speed, 0.99), __dmul_rn(0.01, (double) st.x_vx));
 			st.pll_state = (st.avg_speed < 0.5 && st.avg_speed > -0.5) ? 1 : 0;
-			tsdrgpu_frame_result_t r;
-			r.x_dx = st.x_dx; r.x_vx = st.x_vx; r.x_absvx = st.x_absvx; r.x_stripsize = st.x_strip;
-			r.y_dx = st.y_dx; r.y_vx = st.y_vx; r.y_absvx = st.y_absvx; r.y_stripsize = st.y_strip;
-			r.avg_speed = st.avg_speed; r.pll_state = st.pll_state;
-			r.lastmax = params ? params[f].lastmax : st.lastmax;
-			r.lastmin = params ? params[f].lastmin : st.lastmin;
-			r.snr = params ? params[f].snr : st.snr;
-			r.autogain_report = 0; r.reserved = 0;
-			results[f] = r;
+			tsdrgpu_frame_result_t *r = results + f;   // the auto-gain fields of the record belong to fs_results_autogain
+			r->x_dx = st.x_dx; r->x_vx = st.x_vx; r->x_absvx = st.x_absvx; r->x_stripsize = st.x_strip;
+			r->y_dx = st.y_dx; r->y_vx = st.y_vx; r->y_absvx = st.y_absvx; r->y_stripsize = st.y_strip;
+			r->avg_speed = st.avg_speed; r->pll_state = st.pll_state;
+			r->autogain_report = 0; r->reserved = 0;
+			list_candidates();                                  // for the next frame
 		}
 		__syncthreads();
 	}
@@ -396,9 +442,11 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restri
 }
 
 // refresh the auto-gain fields of already written results (auto-gain-after-processing order)
-__global__ void fs_results_autogain(int nframes, const FrameParams *__restrict__ params, tsdrgpu_frame_result_t *results) {
+__global__ void fs_results_autogain(int nframes, const FrameParams *__restrict__ params, const SyncState *__restrict__ state,
+                                    tsdrgpu_frame_result_t *results) {
 	for (int f = threadIdx.x; f < nframes; f += blockDim.x) {
-		results[f].lastmax = params[f].lastmax; results[f].lastmin = params[f].lastmin; results[f].snr = params[f].snr;
+		if (params) { results[f].lastmax = params[f].lastmax; results[f].lastmin = params[f].lastmin; results[f].snr = params[f].snr; }
+		else { results[f].lastmax = state->lastmax; results[f].lastmin = state->lastmin; results[f].snr = state->snr; }
 	}
 }
 
@@ -478,12 +526,18 @@ struct tsdrgpu_framestage {
 	int lp_before_sync;                          // pp->lowpass_before_sync
 	int runs;                                    // pp->runs
 	SyncState *d_state;
-	// batch temporaries
-	float *d_t1, *d_t2; size_t t_cap;
-	float *d_wstrips, *d_hstrips; size_t strips_cap;
-	float *d_pmin, *d_pmax; double *d_psum, *d_psq, *d_plin; FrameParams *d_params; tsdrgpu_frame_result_t *d_results; int batch_cap;
+	// batch temporaries.  The sync search + re-centre of batch k may run on the side stream while the main stream
+	// already produces batch k+1, so everything they read is double-buffered ("phase" = batch parity).
+	float *d_t1, *d_t2[2]; size_t t_cap;
+	float *d_wstrips[2], *d_hstrips[2]; size_t strips_cap;
+	float *d_pmin, *d_pmax; double *d_psum, *d_psq, *d_plin; FrameParams *d_params; int batch_cap;
+	tsdrgpu_frame_result_t *d_results[2];
 	double *d_chain;
 	float taps[5];
+	int overlap, phase, side_pending;
+	cudaStream_t s_side;
+	cudaEvent_t ev_ready[2];                     // main: collapse of this phase done -> side may start
+	cudaEvent_t ev_done[2];                      // side: sync + emit of this phase done -> buffers of the phase are free
 };
 
 static int fs_reserve(tsdrgpu_framestage *fs, int nframes, size_t n, int w, int h) {
@@ -491,24 +545,20 @@ static int fs_reserve(tsdrgpu_framestage *fs, int nframes, size_t n, int w, int 
 	const size_t need = (size_t) nframes * n;
 	if (fs->t_cap < need) {
 		CU_TRY(ctx, cudaDeviceSynchronize());
-		if (fs->d_t1) CU_TRY(ctx, cudaFree(fs->d_t1));
-		if (fs->d_t2) CU_TRY(ctx, cudaFree(fs->d_t2));
-		CU_TRY(ctx, cudaMalloc(&fs->d_t1, sizeof(float) * need));
-		CU_TRY(ctx, cudaMalloc(&fs->d_t2, sizeof(float) * need));
+		float **bufs[] = {&fs->d_t1, &fs->d_t2[0], &fs->d_t2[1]};
+		for (float **b : bufs) { if (*b) CU_TRY(ctx, cudaFree(*b)); CU_TRY(ctx, cudaMalloc(b, sizeof(float) * need)); }
 		fs->t_cap = need;
 	}
 	const size_t sneed = (size_t) nframes * (size_t) (w > h ? w : h);
 	if (fs->strips_cap < sneed) {
 		CU_TRY(ctx, cudaDeviceSynchronize());
-		if (fs->d_wstrips) CU_TRY(ctx, cudaFree(fs->d_wstrips));
-		if (fs->d_hstrips) CU_TRY(ctx, cudaFree(fs->d_hstrips));
-		CU_TRY(ctx, cudaMalloc(&fs->d_wstrips, sizeof(float) * sneed));
-		CU_TRY(ctx, cudaMalloc(&fs->d_hstrips, sizeof(float) * sneed));
+		float **bufs[] = {&fs->d_wstrips[0], &fs->d_wstrips[1], &fs->d_hstrips[0], &fs->d_hstrips[1]};
+		for (float **b : bufs) { if (*b) CU_TRY(ctx, cudaFree(*b)); CU_TRY(ctx, cudaMalloc(b, sizeof(float) * sneed)); }
 		fs->strips_cap = sneed;
 	}
 	if (fs->batch_cap < nframes) {
 		CU_TRY(ctx, cudaDeviceSynchronize());
-		void *ptrs[] = {fs->d_pmin, fs->d_pmax, fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results};
+		void *ptrs[] = {fs->d_pmin, fs->d_pmax, fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results[0], fs->d_results[1]};
 		for (void *p : ptrs) if (p) CU_TRY(ctx, cudaFree(p));
 		const size_t pc = (size_t) nframes * FS_MM_CHUNKS;
 		CU_TRY(ctx, cudaMalloc(&fs->d_pmin, sizeof(float) * pc));
@@ -517,7 +567,10 @@ static int fs_reserve(tsdrgpu_framestage *fs, int nframes, size_t n, int w, int 
 		CU_TRY(ctx, cudaMalloc(&fs->d_psq, sizeof(double) * pc));
 		CU_TRY(ctx, cudaMalloc(&fs->d_plin, sizeof(double) * pc));
 		CU_TRY(ctx, cudaMalloc(&fs->d_params, sizeof(FrameParams) * nframes));
-		CU_TRY(ctx, cudaMalloc(&fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes));
+		for (int i = 0; i < 2; i++) {
+			CU_TRY(ctx, cudaMalloc(&fs->d_results[i], sizeof(tsdrgpu_frame_result_t) * nframes));
+			CU_TRY(ctx, cudaMemset(fs->d_results[i], 0, sizeof(tsdrgpu_frame_result_t) * nframes));
+		}
 		fs->batch_cap = nframes;
 	}
 	return TSDRGPU_OK;
@@ -536,9 +589,7 @@ static int fs_autogain_batch(tsdrgpu_framestage *fs, cudaStream_t stream, const 
 	dim3 grid2(snr ? (gx < (unsigned) FS_MM_CHUNKS ? gx : FS_MM_CHUNKS) : gx, nframes);
 	if (snr) KL(ctx, "fs_normalise", stream, fs_normalise<true><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin));
 	else KL(ctx, "fs_normalise", stream, fs_normalise<false><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin));
-	if (snr) {
-		KL(ctx, "fs_snr_finish", stream, fs_snr_finish<<<1, 256, 0, stream>>>(nframes, (int) grid2.x, n, fs->d_psq, fs->d_plin, fs->d_params, fs->d_state));
-	}
+	if (snr) KL(ctx, "fs_snr_finish", stream, fs_snr_finish<<<1, 256, 0, stream>>>(nframes, (int) grid2.x, n, fs->d_psq, fs->d_plin, fs->d_params, fs->d_state));
 	return TSDRGPU_OK;
 }
 
@@ -552,6 +603,11 @@ int tsdrgpu_framestage_create(tsdrgpu_ctx_t *ctx, tsdrgpu_framestage_t **out) {
 	tsdrgpu_gauss_taps(fs->taps);
 	CU_TRY(ctx, cudaMalloc(&fs->d_state, sizeof(SyncState)));
 	CU_TRY(ctx, cudaMalloc(&fs->d_chain, sizeof(double) * 10 * FS_MAX_STRIP));
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&fs->s_side, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CU_TRY(ctx, cudaEventCreateWithFlags(&fs->ev_ready[i], cudaEventDisableTiming));
+		CU_TRY(ctx, cudaEventCreateWithFlags(&fs->ev_done[i], cudaEventDisableTiming));
+	}
 	*out = fs;
 	return tsdrgpu_framestage_reset(fs, NULL);
 }
@@ -560,27 +616,49 @@ void tsdrgpu_framestage_destroy(tsdrgpu_framestage_t *fs) {
 	if (!fs) return;
 	cudaSetDevice(fs->ctx->device);
 	cudaDeviceSynchronize();
-	void *ptrs[] = {fs->d_screen, fs->d_state, fs->d_t1, fs->d_t2, fs->d_wstrips, fs->d_hstrips, fs->d_pmin, fs->d_pmax,
-	                fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results, fs->d_chain};
+	void *ptrs[] = {fs->d_screen, fs->d_state, fs->d_t1, fs->d_t2[0], fs->d_t2[1], fs->d_wstrips[0], fs->d_wstrips[1], fs->d_hstrips[0],
+	                fs->d_hstrips[1], fs->d_pmin, fs->d_pmax, fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results[0],
+	                fs->d_results[1], fs->d_chain};
 	for (void *p : ptrs) if (p) cudaFree(p);
+	cudaStreamDestroy(fs->s_side);
+	for (int i = 0; i < 2; i++) { cudaEventDestroy(fs->ev_ready[i]); cudaEventDestroy(fs->ev_done[i]); }
 	delete fs;
 }
 
 int tsdrgpu_framestage_reset(tsdrgpu_framestage_t *fs, void *stream) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
 	BIND(fs->ctx);
+	CU_TRY(fs->ctx, cudaStreamSynchronize(fs->s_side));
 	SyncState s; memset(&s, 0, sizeof s);
 	s.snr = 1.0f;                                        // dsp_autogain_init (dsp.c:35-39)
 	CU_TRY(fs->ctx, cudaMemcpyAsync(fs->d_state, &s, sizeof s, cudaMemcpyHostToDevice, (cudaStream_t) stream));
 	CU_TRY(fs->ctx, cudaStreamSynchronize((cudaStream_t) stream));
 	if (fs->d_screen) { CU_TRY(fs->ctx, cudaFree(fs->d_screen)); fs->d_screen = NULL; }
-	fs->screen_cap = 0; fs->w = 0; fs->h = 0; fs->n = 0; fs->lp_before_sync = 0; fs->runs = 0;
+	fs->screen_cap = 0; fs->w = 0; fs->h = 0; fs->n = 0; fs->lp_before_sync = 0; fs->runs = 0; fs->side_pending = 0;
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_framestage_set_overlap(tsdrgpu_framestage_t *fs, int on) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
+	fs->overlap = on != 0;
+	return TSDRGPU_OK;
+}
+
+// make `stream` wait for everything this object has queued on its side stream
+int tsdrgpu_framestage_join(tsdrgpu_framestage_t *fs, void *stream) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
+	BIND(fs->ctx);
+	if (fs->side_pending) {
+		CU_TRY(fs->ctx, cudaStreamWaitEvent((cudaStream_t) stream, fs->ev_done[0], 0));
+		CU_TRY(fs->ctx, cudaStreamWaitEvent((cudaStream_t) stream, fs->ev_done[1], 0));
+		fs->side_pending = 0;
+	}
 	return TSDRGPU_OK;
 }
 
 static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const float *d_in, int nframes, int w, int h,
-                           float motionblur, float lowpasscoeff, unsigned flags, float *d_out, tsdrgpu_frame_result_t *h_results,
-                           bool synchronise, int32_t *h_report) {
+                               float motionblur, float lowpasscoeff, unsigned flags, float *d_out, tsdrgpu_frame_result_t *h_results,
+                               bool synchronise, int32_t *h_report) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
 	tsdrgpu_ctx_t *ctx = fs->ctx;
 	BIND(ctx);
@@ -592,9 +670,14 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	const bool autoshift = flags & TSDRGPU_FS_AUTOSHIFT, lpbs = flags & TSDRGPU_FS_LOWPASS_BEFORE_SYNC;
 	const bool aap = flags & TSDRGPU_FS_AUTOGAIN_AFTER_PROC, superres = flags & TSDRGPU_FS_SUPERRESOLUTION;
 	const bool snr = flags & TSDRGPU_FS_COMPUTE_SNR;
+	// the side stream is used for the default order only (low-pass before sync, auto-gain first); anything else is serial
+	const bool overlapped = fs->overlap && lpbs && !aap && !(h_results && synchronise);
+	int rc;
+	if (!overlapped && (rc = tsdrgpu_framestage_join(fs, stream))) return rc;
 
 	// buffer (re)sizing exactly as dsp.c:152-186
 	if (h != fs->h || w != fs->w) {
+		if ((rc = tsdrgpu_framestage_join(fs, stream))) return rc;
 		fs->h = h; fs->w = w; fs->n = n;
 		if (n > fs->screen_cap) {
 			float *nb;
@@ -606,73 +689,97 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 		}
 	}
 	if (fs->lp_before_sync != (int) lpbs) {
+		if ((rc = tsdrgpu_framestage_join(fs, stream))) return rc;
 		fs->lp_before_sync = lpbs;
 		CU_TRY(ctx, cudaMemsetAsync(fs->d_screen, 0, sizeof(float) * n, stream));
 	}
-	{ int rc = fs_reserve(fs, nframes, n, w, h); if (rc != TSDRGPU_OK) return rc; }
+	if (fs->t_cap < (size_t) nframes * n || fs->batch_cap < nframes) { if ((rc = tsdrgpu_framestage_join(fs, stream))) return rc; }
+	if ((rc = fs_reserve(fs, nframes, n, w, h))) return rc;
 
+	const int ph = fs->phase; fs->phase ^= 1;
+	float *T2 = fs->d_t2[ph];
+	tsdrgpu_frame_result_t *d_results = fs->d_results[ph];
 	const double fresh = 1.0 - (double) motionblur;      // dsp.c:29
 	const int minsize_x = (int) (w * 0.05f), minsize_y = (int) (h * 0.01f);   // syncdetector.c:178-179
 	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
-	const size_t sync_smem = sizeof(float) * 2 * ((size_t) w + h);
-	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(float) * 4 * FS_MAX_STRIP)));
+	const size_t chains_bytes = sizeof(double) * 10 * (size_t) (w > h ? w : h);
+	const size_t strips_bytes = sizeof(double) * ((size_t) w + h);
+	const int chains_in_smem = (strips_bytes + chains_bytes) <= 200 * 1024;
+	const size_t sync_smem = strips_bytes + (chains_in_smem ? chains_bytes : 0);
+	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 	const unsigned gx = grid_for(n, ctx->sm_count, 4);
 	const size_t total = (size_t) nframes * n;
 
-	auto collapse_sync = [&](const float *src, bool with_params) -> int {
-		KL(ctx, "fs_collapse", stream, fs_collapse<<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips, fs->d_hstrips, col_ctas));
-		KL(ctx, "fs_sync", stream, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, stream>>>(fs->d_wstrips, fs->d_hstrips, w, h, minsize_x, minsize_y, nframes,
-			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain,
-			with_params ? fs->d_params : NULL, fs->d_results));
+	// collapse on `stream`, then sync search on `s2` (== stream unless overlapped)
+	auto collapse_sync = [&](const float *src, cudaStream_t s2) -> int {
+		KL(ctx, "fs_collapse", stream, fs_collapse<<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
+		if (s2 != stream) {
+			CU_TRY(ctx, cudaEventRecord(fs->ev_ready[ph], stream));
+			CU_TRY(ctx, cudaStreamWaitEvent(s2, fs->ev_ready[ph], 0));
+		}
+		KL(ctx, "fs_sync", s2, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, s2>>>(fs->d_wstrips[ph], fs->d_hstrips[ph], w, h, minsize_x, minsize_y, nframes,
+			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain, chains_in_smem, d_results));
 		return TSDRGPU_OK;
 	};
 	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed
-	auto emit = [&](float *src, float *dst, bool greenlines, bool may_modify, float **result) -> int {
+	auto emit = [&](float *src, float *dst, bool greenlines, bool may_modify, float **result, cudaStream_t s2) -> int {
 		if (autoshift) {
-			KL(ctx, "fs_shift", stream, fs_shift<<<dim3(gx, nframes), 256, 0, stream>>>(src, dst, w, h, fs->d_results));
+			KL(ctx, "fs_shift", s2, fs_shift<<<dim3(gx, nframes), 256, 0, s2>>>(src, dst, w, h, d_results));
 			*result = dst;
 		} else if (greenlines && may_modify) {
-			KL(ctx, "fs_greenlines", stream, fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(src, w, h, fs->d_results));
+			KL(ctx, "fs_greenlines", s2, fs_greenlines<<<dim3(8, nframes), 256, 0, s2>>>(src, w, h, d_results));
 			*result = src;
 		} else if (greenlines) {
-			KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, dst, total));
-			KL(ctx, "fs_greenlines", stream, fs_greenlines<<<dim3(8, nframes), 256, 0, stream>>>(dst, w, h, fs->d_results));
+			KL(ctx, "fs_copy", s2, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, s2>>>(src, dst, total));
+			KL(ctx, "fs_greenlines", s2, fs_greenlines<<<dim3(8, nframes), 256, 0, s2>>>(dst, w, h, d_results));
 			*result = dst;
 		} else *result = src;
 		return TSDRGPU_OK;
 	};
-	auto copy_to_out = [&](const float *src) -> int {
-		if (src != d_out) { KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(src, d_out, total)); }
+	auto copy_to_out = [&](const float *src, cudaStream_t s2) -> int {
+		if (src != d_out) KL(ctx, "fs_copy", s2, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, s2>>>(src, d_out, total));
 		return TSDRGPU_OK;
 	};
-	int rc;
 	float *res = NULL;
+	cudaStream_t tail = stream;                          // the stream the results / output become valid on
 	if (lpbs) {                                          // dsp.c:201-212
 		const float *lp_in = d_in;
-		if (!aap) { if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc; lp_in = fs->d_t1; }
-		KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, fs->d_t2, fs->d_screen, n, nframes, motionblur, fresh));
-		if ((rc = collapse_sync(fs->d_t2, !aap))) return rc;
+		if (overlapped) CU_TRY(ctx, cudaStreamWaitEvent(stream, fs->ev_done[ph], 0));      // this phase's buffers are free again
+		if (!aap) {
+			if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc;
+			lp_in = fs->d_t1;
+			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
+		}
+		KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, T2, fs->d_screen, n, nframes, motionblur, fresh));
+		if (overlapped) tail = fs->s_side;
+		if ((rc = collapse_sync(T2, tail))) return rc;
 		float *dst = aap ? fs->d_t1 : d_out;
-		if ((rc = emit(fs->d_t2, dst, !superres, false, &res))) return rc;
+		if ((rc = emit(T2, dst, !superres, false, &res, tail))) return rc;
 		if (aap) {
 			if ((rc = fs_autogain_batch(fs, stream, res, d_out, nframes, n, lowpasscoeff, snr))) return rc;
-			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results));
-		} else if ((rc = copy_to_out(res))) return rc;
+			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
+		} else if ((rc = copy_to_out(res, tail))) return rc;
 	} else {                                             // dsp.c:214-226
 		float *work = fs->d_t1;
-		if (!aap) { if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc; }
-		else { KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(d_in, fs->d_t1, total)); }
-		if ((rc = collapse_sync(work, !aap))) return rc;
-		if ((rc = emit(work, fs->d_t2, (motionblur == 0.0f) && !superres, true, &res))) return rc;
-		float *lp_out = aap ? ((res == fs->d_t1) ? fs->d_t2 : fs->d_t1) : d_out;
+		if (!aap) {
+			if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc;
+			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
+		} else KL(ctx, "fs_copy", stream, fs_copy<<<grid_for(total, ctx->sm_count), 256, 0, stream>>>(d_in, fs->d_t1, total));
+		if ((rc = collapse_sync(work, stream))) return rc;
+		if ((rc = emit(work, T2, (motionblur == 0.0f) && !superres, true, &res, stream))) return rc;
+		float *lp_out = aap ? ((res == fs->d_t1) ? T2 : fs->d_t1) : d_out;
 		KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(res, lp_out, fs->d_screen, n, nframes, motionblur, fresh));
 		if (aap) {
 			if ((rc = fs_autogain_batch(fs, stream, lp_out, d_out, nframes, n, lowpasscoeff, snr))) return rc;
-			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_results));
+			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
 		}
 	}
-	if (h_results) CU_TRY(ctx, cudaMemcpyAsync(h_results, fs->d_results, sizeof(tsdrgpu_frame_result_t) * nframes, cudaMemcpyDeviceToHost, stream));
-	if (h_results && synchronise) CU_TRY(ctx, cudaStreamSynchronize(stream));
+	if (h_results) CU_TRY(ctx, cudaMemcpyAsync(h_results, d_results, sizeof(tsdrgpu_frame_result_t) * nframes, cudaMemcpyDeviceToHost, tail));
+	if (overlapped) {
+		CU_TRY(ctx, cudaEventRecord(fs->ev_done[ph], fs->s_side));
+		fs->side_pending = 1;
+	}
+	if (h_results && synchronise) CU_TRY(ctx, cudaStreamSynchronize(tail));
 	for (int f = 0; f < nframes; f++) {
 		int report = 0;
 		if (fs->runs++ > 5) { fs->runs = 0; report = 1; }                              // dsp.c:231-235

@@ -68,7 +68,8 @@ struct tsdrgpu_pipeline {
 	tsdrgpu_ctx_t *ctx;
 	tsdrgpu_pipeline_config_t cfg;
 	tsdrgpu_frame_cb frame_cb; tsdrgpu_value_cb value_cb; tsdrgpu_plot_cb plot_cb; void *user;
-	cudaStream_t s_main, s_copy;
+	cudaStream_t s_main, s_copy, s_out;
+	cudaEvent_t ev_out[2]; int out_phase;
 	cudaEvent_t ev_h2d[2], ev_used[2]; int stage_slot;
 
 	// live geometry (set_internal_samplerate)
@@ -89,7 +90,7 @@ struct tsdrgpu_pipeline {
 	DropComp pix_drop;
 	// stage 3: frames
 	tsdrgpu_framestage *fs;
-	float *d_frames; size_t frames_cap;
+	float *d_frames[2]; size_t frames_cap[2];          // double-buffered: D2H of batch k overlaps the kernels of batch k+1
 	float *h_frames[PL_SLOTS]; tsdrgpu_frame_result_t *h_results[PL_SLOTS]; int32_t *h_report[PL_SLOTS]; size_t slot_cap;
 	int slot_busy[PL_SLOTS];
 	// autocorrelation side path
@@ -163,10 +164,10 @@ static void *delivery_main(void *arg) {
 	return NULL;
 }
 
-static int submit(tsdrgpu_pipeline *p, FrameJob &j) {
+static int submit(tsdrgpu_pipeline *p, FrameJob &j, cudaStream_t on) {
 	tsdrgpu_ctx_t *ctx = p->ctx;
 	CU_TRY(ctx, cudaEventCreateWithFlags(&j.ev, cudaEventDisableTiming));
-	CU_TRY(ctx, cudaEventRecord(j.ev, p->s_main));
+	CU_TRY(ctx, cudaEventRecord(j.ev, on));
 	pthread_mutex_lock(&p->mu);
 	p->jobs.push_back(j); p->submitted++;
 	pthread_cond_signal(&p->cv_job);
@@ -240,7 +241,7 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 				FrameJob j; memset(&j, 0, sizeof j);
 				j.kind = 1; j.slot = slot; j.samplerate = p->samplerate; j.foff = fmin; j.flen = fmax - fmin; j.loff = lmin; j.llen = lmax - lmin;
 				j.calls = calls; j.reset_announce = reset_announce;
-				if ((rc = submit(p, j))) return rc;
+				if ((rc = submit(p, j, p->s_main))) return rc;
 			}
 		}
 	}
@@ -284,22 +285,27 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 			}
 			p->slot_cap = n * nf;
 		}
-		if ((rc = grow(ctx, p->s_main, &p->d_frames, &p->frames_cap, n * nf, 0))) return rc;
+		const int op = p->out_phase; p->out_phase ^= 1;
+		if ((rc = grow(ctx, p->s_main, &p->d_frames[op], &p->frames_cap[op], n * nf, 0))) return rc;
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_out[op], 0));       // the D2H that last read this buffer is done
 		unsigned flags = 0;
 		if (p->params[TSDRGPU_PARAM_INT_AUTOSHIFT]) flags |= TSDRGPU_FS_AUTOSHIFT;
 		if (p->params[TSDRGPU_PARAM_LOW_PASS_BEFORE_SYNC]) flags |= TSDRGPU_FS_LOWPASS_BEFORE_SYNC;
 		if (p->params[TSDRGPU_PARAM_AUTOGAIN_AFTER_PROCESSING]) flags |= TSDRGPU_FS_AUTOGAIN_AFTER_PROC;
 		if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION]) flags |= TSDRGPU_FS_SUPERRESOLUTION;
 		if ((rc = tsdrgpu_framestage_run_async(p->fs, p->s_main, p->d_pix + p->pix_read, nf, w, h, p->motionblur,
-		                                       0.1f /* NORMALISATION_LOWPASS_COEFF, TSDRLibrary.c:37 */, flags, p->d_frames,
+		                                       0.1f /* NORMALISATION_LOWPASS_COEFF, TSDRLibrary.c:37 */, flags, p->d_frames[op],
 		                                       p->h_results[slot], p->h_report[slot]))) return rc;
-		CU_TRY(ctx, cudaMemcpyAsync(p->h_frames[slot], p->d_frames, sizeof(float) * n * nf, cudaMemcpyDeviceToHost, p->s_main));
+		// the frames become valid on the frame stage's side stream: copy them out on the output stream behind it
+		if ((rc = tsdrgpu_framestage_join(p->fs, p->s_out))) return rc;
+		CU_TRY(ctx, cudaMemcpyAsync(p->h_frames[slot], p->d_frames[op], sizeof(float) * n * nf, cudaMemcpyDeviceToHost, p->s_out));
+		CU_TRY(ctx, cudaEventRecord(p->ev_out[op], p->s_out));
 		p->stats.d2h_bytes += sizeof(float) * n * nf;
 		p->pix_read += n * nf;
 		p->stats.frames_processed += nf;
 		FrameJob j; memset(&j, 0, sizeof j);
 		j.kind = 0; j.slot = slot; j.nframes = nf; j.w = w; j.h = h;
-		if ((rc = submit(p, j))) return rc;
+		if ((rc = submit(p, j, p->s_out))) return rc;
 	}
 	// compact the pixel buffer when the consumed prefix is large
 	if (p->pix_read > 0 && p->pix_read >= (p->pix_fill - p->pix_read)) {
@@ -380,7 +386,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
 	geometry_locked(p);
 	p->d_stage[0] = p->d_stage[1] = NULL; p->stage_cap[0] = p->stage_cap[1] = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
-	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames = NULL; p->frames_cap = 0;
+	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
 	p->slot_cap = 0; p->d_capture = NULL; p->cap_size = 0; p->cap_fill = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
 	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
@@ -388,6 +394,8 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	memset(&p->stats, 0, sizeof p->stats);
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking));
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
 	for (int i = 0; i < 2; i++) {
 		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
 		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_used[i], cudaEventDisableTiming));
@@ -395,6 +403,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	int rc;
 	if ((rc = tsdrgpu_resampler_create(ctx, &p->rs))) return rc;
 	if ((rc = tsdrgpu_framestage_create(ctx, &p->fs))) return rc;
+	tsdrgpu_framestage_set_overlap(p->fs, 1);
 	if ((rc = tsdrgpu_frd_create(ctx, &p->frd))) return rc;
 	pthread_create(&p->thread, NULL, delivery_main, p);
 	*out = p;
@@ -406,6 +415,7 @@ int tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p) {
 	BIND(p->ctx);
 	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_copy));
 	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_main));
+	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_out));
 	pthread_mutex_lock(&p->mu);
 	while (p->delivered < p->submitted) pthread_cond_wait(&p->cv_done, &p->mu);
 	pthread_mutex_unlock(&p->mu);
@@ -420,11 +430,12 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	cudaSetDevice(p->ctx->device);
 	tsdrgpu_resampler_destroy(p->rs); tsdrgpu_framestage_destroy(p->fs); tsdrgpu_frd_destroy(p->frd);
 	for (void *h : p->registered) cudaHostUnregister(h);
-	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_decim, p->d_pix, p->d_frames, p->d_capture};
+	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture};
 	for (float *d : dev) if (d) cudaFree(d);
 	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
 	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
-	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy);
+	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
+	for (int i = 0; i < 2; i++) cudaEventDestroy(p->ev_out[i]);
 	for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_h2d[i]); cudaEventDestroy(p->ev_used[i]); }
 	pthread_mutex_destroy(&p->mu); pthread_mutex_destroy(&p->geo_mu); pthread_cond_destroy(&p->cv_job); pthread_cond_destroy(&p->cv_done);
 	delete p;

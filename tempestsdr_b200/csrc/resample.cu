@@ -98,30 +98,56 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 	float *gout = out + B.out_start;
 	__syncthreads();
 
-	for (unsigned k = s0 + threadIdx.x; k < s1; k += RS_THREADS) {
-		const Geo g = rs_geo(k, r, phase);
+	// One warp owns 32 CONSECUTIVE samples per round, so everything sample k needs from sample k-1 (its pid, whether it
+	// emitted an A pixel, what it banked) arrives by one warp shuffle instead of being recomputed in double precision.
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	for (unsigned base = s0 + warp * 32u; base < s1; base += RS_THREADS) {
+		const unsigned k = base + lane;
+		const bool live = k < s1;
+		const unsigned kk = live ? k : (s1 - 1);                 // idle lanes shadow the last sample (results unused)
+		const Geo g = rs_geo(kk, r, phase);
 		const double Pk = rs_P(g.c);
-		const double Pkm1 = (k == 0) ? 0.0 : rs_P(rs_geo(k - 1, r, phase).c);
-		const float vf = s_mag[RS_HALO + (k - s0)];
+		const float vf = s_mag[RS_HALO + (kk - s0)];
 		const double v = (double) vf;
+		const double tk = rs_t(g, Pk, r, v);
+		double Pkm1 = __shfl_up_sync(0xffffffffu, Pk, 1);
+		if (lane == 0) Pkm1 = (kk == 0) ? 0.0 : rs_P(rs_geo(kk - 1, r, phase).c);
+		const bool isA = rs_isA(g, Pkm1);
+		int prevA = __shfl_up_sync(0xffffffffu, (int) isA, 1);
+		double prevT = __shfl_up_sync(0xffffffffu, tk, 1);
+		if (lane == 0 && isA && kk > 0) {                        // the neighbour lives in another warp: recompute it
+			const Geo gp = rs_geo(kk - 1, r, phase);
+			const double Ppm1 = (kk == 1) ? 0.0 : rs_P(rs_geo(kk - 2, r, phase).c);
+			prevA = rs_isA(gp, Ppm1);
+			const float vp = (kk - 1 + RS_HALO >= s0) ? s_mag[RS_HALO + (kk - 1) - s0] : rs_load<IQ>(in, B.in_start + kk - 1);
+			prevT = rs_t(gp, rs_P(gp.c), r, (double) vp);
+		}
+		if (!live) continue;
 		unsigned p = (unsigned) Pkm1;
 		const unsigned pstop = (unsigned) Pk;
-		if (rs_isA(g, Pkm1)) {
-			// bank = t_L + ... + t_{k-1}, L = latest earlier sample that emitted an A pixel
-			long long L = (long long) k - 1;
-			while (L >= 0) {
-				const Geo gl = rs_geo((unsigned) L, r, phase);
-				const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, r, phase).c);
-				if (rs_isA(gl, Plm1)) break;
-				L--;
-			}
-			if (L >= 0) {
-				double bank = 0.0;
-				for (unsigned j = (unsigned) L; j < k; j++) {
-					const Geo gj = rs_geo(j, r, phase);
-					const float vj = (j + RS_HALO >= s0) ? s_mag[RS_HALO + j - s0] : rs_load<IQ>(in, B.in_start + j);
-					bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) vj));
+		if (isA) {
+			double bank = 0.0;
+			bool have = false;
+			if (k > 0 && prevA) { bank = __dadd_rn(0.0, prevT); have = true; }      // the common case for r > 1
+			else if (k > 0) {
+				// general case: bank = t_L + ... + t_{k-1}, L = latest earlier sample that emitted an A pixel
+				long long L = (long long) k - 2;
+				while (L >= 0) {
+					const Geo gl = rs_geo((unsigned) L, r, phase);
+					const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, r, phase).c);
+					if (rs_isA(gl, Plm1)) break;
+					L--;
 				}
+				if (L >= 0) {
+					for (unsigned j = (unsigned) L; j < k; j++) {
+						const Geo gj = rs_geo(j, r, phase);
+						const float vj = (j + RS_HALO >= s0) ? s_mag[RS_HALO + j - s0] : rs_load<IQ>(in, B.in_start + j);
+						bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) vj));
+					}
+					have = true;
+				}
+			}
+			if (have) {
 				const double w = __dadd_rn(__dsub_rn(1.0, g.lo), Pkm1);
 				const float px = __double2float_rn(__dadd_rn(bank, __dmul_rn(v, w)));
 				if (staged) s_out[p - pbase] = px; else if (p < B.n_out) gout[p] = px;
