@@ -253,6 +253,12 @@ def run_ours(args):
     launches = gpu.launches - launches0
     frames_done, caps_done = step.frames - frames0, step.captures - caps0
 
+    if os.environ.get("BENCH_QUICK"):                 # used under ncu: the timed steps only
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": world * args.steps * pairs / (ms_total * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": ms_total / args.steps}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- per-kernel timing pass (separate from the timed region above): CUDA events on the launching stream
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
     collect_profile(gpu)

@@ -69,7 +69,7 @@ struct tsdrgpu_pipeline {
 	tsdrgpu_pipeline_config_t cfg;
 	tsdrgpu_frame_cb frame_cb; tsdrgpu_value_cb value_cb; tsdrgpu_plot_cb plot_cb; void *user;
 	cudaStream_t s_main, s_copy, s_out;
-	cudaEvent_t ev_out[2]; int out_phase;
+	cudaEvent_t ev_out[2], ev_main; int out_phase;
 	cudaEvent_t ev_h2d[2], ev_used[2]; int stage_slot;
 
 	// live geometry (set_internal_samplerate)
@@ -297,7 +297,9 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 		                                       0.1f /* NORMALISATION_LOWPASS_COEFF, TSDRLibrary.c:37 */, flags, p->d_frames[op],
 		                                       p->h_results[slot], p->h_report[slot]))) return rc;
 		// the frames become valid on the frame stage's side stream: copy them out on the output stream behind it
-		if ((rc = tsdrgpu_framestage_join(p->fs, p->s_out))) return rc;
+		CU_TRY(ctx, cudaEventRecord(p->ev_main, p->s_main));
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_out, p->ev_main, 0));             // serial stage orders finish on the main stream
+		if ((rc = tsdrgpu_framestage_join(p->fs, p->s_out))) return rc;        // the overlapped order finishes on the side stream
 		CU_TRY(ctx, cudaMemcpyAsync(p->h_frames[slot], p->d_frames[op], sizeof(float) * n * nf, cudaMemcpyDeviceToHost, p->s_out));
 		CU_TRY(ctx, cudaEventRecord(p->ev_out[op], p->s_out));
 		p->stats.d2h_bytes += sizeof(float) * n * nf;
@@ -396,6 +398,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_main, cudaEventDisableTiming));
 	for (int i = 0; i < 2; i++) {
 		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
 		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_used[i], cudaEventDisableTiming));
@@ -436,6 +439,7 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
 	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
 	for (int i = 0; i < 2; i++) cudaEventDestroy(p->ev_out[i]);
+	cudaEventDestroy(p->ev_main);
 	for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_h2d[i]); cudaEventDestroy(p->ev_used[i]); }
 	pthread_mutex_destroy(&p->mu); pthread_mutex_destroy(&p->geo_mu); pthread_cond_destroy(&p->cv_job); pthread_cond_destroy(&p->cv_done);
 	delete p;
