@@ -25,7 +25,7 @@ namespace {
 
 constexpr int FFT_MAX_LOG2L = 11;            // longest line transformed inside one CTA: 2048
 constexpr int FFT_TABLE = 1 << FFT_MAX_LOG2L;
-constexpr int FFT_MAX_ELEMS = 16384;         // complex elements per CTA bundle (128 KB of shared memory)
+constexpr int FFT_MAX_ELEMS = 8192;          // complex elements per CTA bundle: 1024 threads x 8 (68 KB of shared memory)
 
 struct FftPass {
 	int log2L, C, log2C, c_fast_in, c_fast_out;
@@ -47,104 +47,115 @@ __device__ __forceinline__ float2 tw_lookup(const float2 *__restrict__ table, un
 	return w;
 }
 
+// ---- in-register small DFTs (natural order in, natural order out) -------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+__device__ __forceinline__ float2 rot90(float2 a, bool inverse) { return inverse ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+__device__ __forceinline__ void dft2(float2 &a, float2 &b) { const float2 t = a; a = cadd(t, b); b = csub(t, b); }
+__device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3, bool inverse) {
+	const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = rot90(csub(v1, v3), inverse);
+	v0 = cadd(a0, a2); v1 = cadd(a1, a3); v2 = csub(a0, a2); v3 = csub(a1, a3);
+}
+__device__ __forceinline__ void dft8(float2 (&v)[8], bool inverse) {
+	// even / odd halves as two 4-point DFTs, then the W8^k twiddles
+	dft4(v[0], v[2], v[4], v[6], inverse);
+	dft4(v[1], v[3], v[5], v[7], inverse);
+	const float h = 0.70710678118654752440f;
+	const float2 o0 = v[1];
+	const float2 t1 = v[3];            // * W8^1 = (1 -+ i)/sqrt2
+	const float2 o1 = inverse ? make_float2(h * (t1.x - t1.y), h * (t1.x + t1.y)) : make_float2(h * (t1.x + t1.y), h * (t1.y - t1.x));
+	const float2 o2 = rot90(v[5], inverse);
+	const float2 t3 = v[7];            // * W8^3 = (-1 -+ i)/sqrt2
+	const float2 o3 = inverse ? make_float2(-h * (t3.x + t3.y), h * (t3.x - t3.y)) : make_float2(h * (t3.y - t3.x), -h * (t3.x + t3.y));
+	const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+	v[0] = cadd(e0, o0); v[1] = cadd(e1, o1); v[2] = cadd(e2, o2); v[3] = cadd(e3, o3);
+	v[4] = csub(e0, o0); v[5] = csub(e1, o1); v[6] = csub(e2, o2); v[7] = csub(e3, o3);
+}
+
+// shared-memory index with one pad element per 16 (keeps the stride-R Stockham writes spread over the banks)
+__device__ __forceinline__ int padq(int q) { return q + (q >> 4); }
+
+// One Stockham stage of radix R on every line of the bundle.  Each thread owns `8/R` butterflies (8 elements):
+// read -> barrier -> write -> barrier (in place).
+template <int R, int LOG2L>
+__device__ __forceinline__ void stockham_stage(float2 *s, int LP, int C, int p, const float2 *__restrict__ table, bool inverse) {
+	constexpr int L = 1 << LOG2L, PER_LINE = L / R, LOGPL = LOG2L - (R == 8 ? 3 : (R == 4 ? 2 : 1)), NB = 8 / R;
+	const int work = C * PER_LINE;
+	float2 v[8];
+	#pragma unroll
+	for (int it = 0; it < NB; it++) {
+		const int widx = threadIdx.x + it * blockDim.x;
+		if (widx < work) {
+			const int c = widx >> LOGPL, i = widx & (PER_LINE - 1);
+			const int k = i & (p - 1);
+			const float2 *line = s + c * LP;
+			#pragma unroll
+			for (int m = 0; m < R; m++) v[it * R + m] = line[padq(i + m * PER_LINE)];
+			if (k) {
+				const unsigned tq = (unsigned) k * (unsigned) (FFT_TABLE / (R * p));
+				#pragma unroll
+				for (int m = 1; m < R; m++) v[it * R + m] = cmul(v[it * R + m], tw_lookup(table, m * tq, inverse));
+			}
+			if (R == 8) {
+				float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
+				dft8(u, inverse);
+			} else if (R == 4) dft4(v[it * 4 + 0], v[it * 4 + 1], v[it * 4 + 2], v[it * 4 + 3], inverse);
+			else dft2(v[it * 2 + 0], v[it * 2 + 1]);
+		}
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int it = 0; it < NB; it++) {
+		const int widx = threadIdx.x + it * blockDim.x;
+		if (widx < work) {
+			const int c = widx >> LOGPL, i = widx & (PER_LINE - 1);
+			const int k = i & (p - 1);
+			const int j = (i - k) * R + k;
+			float2 *line = s + c * LP;
+			#pragma unroll
+			for (int m = 0; m < R; m++) line[padq(j + m * p)] = v[it * R + m];
+		}
+	}
+	__syncthreads();
+}
+
+template <int LOG2L>
 __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
-                                                        const float2 *__restrict__ table, int inverse) {
+                                                        const float2 *__restrict__ table, int inverse_) {
 	extern __shared__ float2 s[];
-	const int L = 1 << P.log2L, C = P.C, LP = L + 1, total = C * L;
-	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g % P.G_lo;
+	constexpr int L = 1 << LOG2L;
+	const bool inverse = inverse_ != 0;
+	const int C = P.C, LP = padq(L) + 1, total = C * L, log2C = P.log2C;
+	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g - g_hi * P.G_lo;
 	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs;
 	const long long out_base = (long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo + (long long) blockIdx.y * P.out_bs;
-	const int log2C = P.log2C;
 
-	// ---- load the bundle
+	// ---- load the bundle (runs of C consecutive values on strided passes, whole lines on contiguous ones)
 	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
 		int c, j;
-		if (P.c_fast_in) { c = idx & (C - 1); j = idx >> log2C; } else { j = idx & (L - 1); c = idx >> P.log2L; }
+		if (P.c_fast_in) { c = idx & (C - 1); j = idx >> log2C; } else { j = idx & (L - 1); c = idx >> LOG2L; }
 		const long long src = in_base + (long long) c * P.in_cs + (long long) j * P.in_js;
 		float2 v;
-		if (P.in_real) v = make_float2(reinterpret_cast<const float *>(in)[src], 0.0f); else v = in[src];
-		s[c * LP + j] = v;
+		if (P.in_real) v = make_float2(__ldg(reinterpret_cast<const float *>(in) + src), 0.0f); else v = __ldg(in + src);
+		s[c * LP + padq(j)] = v;
 	}
 	__syncthreads();
 
-	// ---- Stockham stages, in place: every thread reads its butterflies, barrier, writes, barrier.
-	// A CTA holds at most FFT_MAX_ELEMS points and has >= elems/16 threads (launch_pass), so a thread owns at
-	// most 4 radix-4 or 8 radix-2 butterflies: 16 complex registers either way.
-	int p = 1, stage_log = 0;
-	float2 r[16];
-	while (stage_log < P.log2L) {
-		const bool radix4 = ((P.log2L - stage_log) & 1) == 0;       // one radix-2 stage first when log2 L is odd
-		if (radix4) {
-			const int per_line = L >> 2, work = C * per_line, pl_log = P.log2L - 2;
-			#pragma unroll
-			for (int it = 0; it < 4; it++) {
-				const int widx = threadIdx.x + it * blockDim.x;
-				if (widx < work) {
-					const int c = widx >> pl_log, i = widx & (per_line - 1);
-					const int k = i & (p - 1);
-					const float2 *line = s + c * LP;
-					const unsigned tq = (unsigned) k * (unsigned) (FFT_TABLE / (4 * p));
-					float2 u0 = line[i], u1 = line[i + per_line], u2 = line[i + 2 * per_line], u3 = line[i + 3 * per_line];
-					if (k) { u1 = cmul(u1, tw_lookup(table, tq, inverse)); u2 = cmul(u2, tw_lookup(table, 2 * tq, inverse)); u3 = cmul(u3, tw_lookup(table, 3 * tq, inverse)); }
-					const float2 a0 = make_float2(u0.x + u2.x, u0.y + u2.y), a1 = make_float2(u0.x - u2.x, u0.y - u2.y);
-					const float2 a2 = make_float2(u1.x + u3.x, u1.y + u3.y);
-					float2 a3 = make_float2(u1.x - u3.x, u1.y - u3.y);
-					a3 = inverse ? make_float2(-a3.y, a3.x) : make_float2(a3.y, -a3.x);     // * (+i) inverse, * (-i) forward
-					r[it * 4 + 0] = make_float2(a0.x + a2.x, a0.y + a2.y); r[it * 4 + 1] = make_float2(a1.x + a3.x, a1.y + a3.y);
-					r[it * 4 + 2] = make_float2(a0.x - a2.x, a0.y - a2.y); r[it * 4 + 3] = make_float2(a1.x - a3.x, a1.y - a3.y);
-				}
-			}
-			__syncthreads();
-			#pragma unroll
-			for (int it = 0; it < 4; it++) {
-				const int widx = threadIdx.x + it * blockDim.x;
-				if (widx < work) {
-					const int c = widx >> pl_log, i = widx & (per_line - 1);
-					const int k = i & (p - 1);
-					const int j = ((i - k) << 2) + k;
-					float2 *line = s + c * LP;
-					line[j] = r[it * 4 + 0]; line[j + p] = r[it * 4 + 1]; line[j + 2 * p] = r[it * 4 + 2]; line[j + 3 * p] = r[it * 4 + 3];
-				}
-			}
-			__syncthreads();
-			p <<= 2; stage_log += 2;
-		} else {
-			const int per_line = L >> 1, work = C * per_line, pl_log = P.log2L - 1;
-			#pragma unroll
-			for (int it = 0; it < 8; it++) {
-				const int widx = threadIdx.x + it * blockDim.x;
-				if (widx < work) {
-					const int c = widx >> pl_log, i = widx & (per_line - 1);
-					const int k = i & (p - 1);
-					const float2 *line = s + c * LP;
-					const float2 u0 = line[i];
-					float2 u1 = line[i + per_line];
-					if (k) u1 = cmul(u1, tw_lookup(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), inverse));
-					r[it * 2 + 0] = make_float2(u0.x + u1.x, u0.y + u1.y); r[it * 2 + 1] = make_float2(u0.x - u1.x, u0.y - u1.y);
-				}
-			}
-			__syncthreads();
-			#pragma unroll
-			for (int it = 0; it < 8; it++) {
-				const int widx = threadIdx.x + it * blockDim.x;
-				if (widx < work) {
-					const int c = widx >> pl_log, i = widx & (per_line - 1);
-					const int k = i & (p - 1);
-					const int j = ((i - k) << 1) + k;
-					float2 *line = s + c * LP;
-					line[j] = r[it * 2 + 0]; line[j + p] = r[it * 2 + 1];
-				}
-			}
-			__syncthreads();
-			p <<= 1; stage_log += 1;
-		}
-	}
+	// ---- Stockham stages: the odd radix (2 or 4) first, where all twiddles are 1, then radix 8
+	int p = 1;
+	constexpr int FIRST = (LOG2L % 3 == 0) ? 8 : ((LOG2L % 3 == 1) ? 2 : 4);
+	if (FIRST == 2) { stockham_stage<2, LOG2L>(s, LP, C, p, table, inverse); p = 2; }
+	else if (FIRST == 4) { stockham_stage<4, LOG2L>(s, LP, C, p, table, inverse); p = 4; }
+	#pragma unroll
+	for (int st = 0; st < LOG2L / 3; st++) { stockham_stage<8, (LOG2L >= 3 ? LOG2L : 3)>(s, LP, C, p, table, inverse); p <<= 3; }
 
 	// ---- inter-pass twiddle, scaling, optional |.|, store
 	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
 		int c, k;
-		if (P.c_fast_out) { c = idx & (C - 1); k = idx >> log2C; } else { k = idx & (L - 1); c = idx >> P.log2L; }
-		float2 v = s[c * LP + k];
+		if (P.c_fast_out) { c = idx & (C - 1); k = idx >> log2C; } else { k = idx & (L - 1); c = idx >> LOG2L; }
+		float2 v = s[c * LP + padq(k)];
 		if (P.tw_M) {
 			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
 			const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
@@ -288,7 +299,10 @@ int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	LAUNCH_CHECK(ctx);
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
 	g_table[ctx->device] = t;
-	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(float2) * (FFT_MAX_ELEMS + 64))));
+	const int max_smem = (int) (sizeof(float2) * (FFT_MAX_ELEMS + FFT_MAX_ELEMS / 16 + 64));
+#define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+	SET_ATTR(1); SET_ATTR(2); SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
+#undef SET_ATTR
 	return TSDRGPU_OK;
 }
 
@@ -305,12 +319,19 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	P.in_bs = in_bs; P.out_bs = out_bs;
 	P.log2C = 0; while ((1 << P.log2C) < P.C) P.log2C++;
 	const int L = 1 << P.log2L, total = P.C * L;
-	int threads = (total / 16 + 31) / 32 * 32;           // <= 4 radix-4 (8 radix-2) butterflies per thread
-	if (threads < 64) threads = 64;
-	if (total / 4 >= 256 && threads < 256) threads = 256;
-	if (threads > 1024) threads = 1024;
-	const size_t smem = sizeof(float2) * (size_t) P.C * (L + 1);
-	KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<<<dim3(bundles, batch), threads, smem, stream>>>(in, out, P, g_table[ctx->device], inverse));
+	int threads = (total / 8 + 31) / 32 * 32;            // one radix-8 butterfly (8 elements) per thread and stage
+	if (threads < 32) threads = 32;
+	if (threads > 1024) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT bundle too large", cudaSuccess, __FILE__, __LINE__);
+	const int LP = L + (L >> 4) + 1;
+	const size_t smem = sizeof(float2) * (size_t) P.C * LP;
+	const dim3 grid(bundles, batch);
+	const float2 *tab = g_table[ctx->device];
+	switch (P.log2L) {
+#define CASE(l) case l: KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break
+	CASE(1); CASE(2); CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
+#undef CASE
+	default: return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "unsupported FFT line length", cudaSuccess, __FILE__, __LINE__);
+	}
 	return TSDRGPU_OK;
 }
 

@@ -20,12 +20,13 @@
 #include "common.cuh"
 #include "host_plan.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int FS_MAX_STRIP = 8192;      // longest width/height the in-CTA sync search supports
 constexpr int FS_MM_CHUNKS = 64;        // partial reductions per frame
-constexpr int FS_SYNC_THREADS = 512;
+constexpr int FS_SYNC_THREADS = 1024;
 
 __device__ __forceinline__ bool px_is_marker(float v) { return v > 250.0f || v < -250.0f; }   // dsp.c:57
 
@@ -322,25 +323,79 @@ __device__ void blur_to_double(const float *__restrict__ src, double *__restrict
 	}
 }
 
+// ---- exact window sums without the serial chain ------------------------------------------------------------------
+// findbestfit's sliding sum cur = (cur - d[i]) + d[i+s] is a serial chain of ~2n dependent double additions per strip
+// size.  But the strip holds floats widened to double; when the exponents of its non-zero entries span less than
+// 29 - log2(n) binades, EVERY partial sum of up to n entries is an integer multiple of the smallest ulp and smaller than
+// 2^53 of them: it is exactly representable, so no addition or subtraction in the chain ever rounds and the chain's
+// values equal the exact real-number window sums -- in any association.  Then cs[e] = S[e+s] - S[e] from one exclusive
+// prefix scan S (also exact) is bit-identical to the reference's chain, for every strip size at once.  The certificate
+// is checked per strip per frame; if it fails (denormals, infinities, > ~2^17 dynamic range) the serial chains run.
+struct ExpRange { int lo, hi, bad; };
+__device__ __forceinline__ void exp_range_add(ExpRange &r, float v) {
+	const unsigned bits = __float_as_uint(v), e = (bits >> 23) & 0xffu, m = bits & 0x7fffffu;
+	if (e == 0) { if (m) r.bad = 1; return; }            // zero is harmless, a denormal is not covered
+	if (e == 255) { r.bad = 1; return; }
+	r.lo = min(r.lo, (int) e); r.hi = max(r.hi, (int) e);
+}
+
+// exclusive prefix sums of data[0..n) into S[0..n] IN PLACE over the same storage shifted by one:
+// on entry buf[1..n] = data, on exit buf[i] = sum_{j<i} data[j] (buf[0] = 0).  All threads of the CTA take part.
+__device__ void exact_prefix(double *buf, int n, double *warp_tot /* >= 32 */) {
+	const int T = blockDim.x, chunk = (n + T - 1) / T;
+	const int i0 = min((int) threadIdx.x * chunk, n), i1 = min(i0 + chunk, n);
+	double v[8];                                         // n <= 8 * blockDim.x (checked by the caller)
+	double local = 0.0;
+	#pragma unroll
+	for (int u = 0; u < 8; u++) if (i0 + u < i1) { v[u] = buf[1 + i0 + u]; local += v[u]; }
+	// exclusive scan of `local` across the CTA
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	double incl = local;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+	if (lane == 31) warp_tot[warp] = incl;
+	__syncthreads();                                     // also: every thread has read its chunk
+	if (warp == 0) {
+		double w = (lane < (T >> 5)) ? warp_tot[lane] : 0.0, wi = w;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += up; }
+		warp_tot[lane] = wi - w;                         // exclusive
+	}
+	__syncthreads();
+	double run = warp_tot[warp] + (incl - local);
+	if (threadIdx.x == 0) buf[0] = 0.0;
+	#pragma unroll
+	for (int u = 0; u < 8; u++) if (i0 + u < i1) { run += v[u]; buf[1 + i0 + u] = run; }
+	__syncthreads();
+}
+
+__device__ __forceinline__ double window_from_prefix(const double *S, int n, int e, int strip) {
+	const int end = e + strip;
+	if (end <= n) return S[end] - S[e];
+	return (S[n] - S[e]) + S[end - n];
+}
+
 // One CTA walks the frames of the batch in order (the strip size and dx carry from frame to frame).
-// Per frame: blur both strips (all threads) | 12 serial double chains in 12 warps (2 totals, <=10 window-sum chains)
-// | 10 warps score one candidate each, first-max reduce | thread 0: pick the strip size, update dx/vx, PLL average.
+// Per frame: blur both strips into double (all threads) + exactness certificate | exact prefix scans (or, when the
+// certificate fails, the serial chains) | every thread scores a slice of the windows of every candidate strip size,
+// first-max reduce | thread 0: pick the strip size, update dx/vx, PLL average.
 __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
                                                            int w, int h, int minsize_x, int minsize_y, int nframes,
                                                            float c0, float c1, float c2, float c3, float c4,
-                                                           SyncState *state, double *__restrict__ chain_scratch, int chains_in_smem,
+                                                           SyncState *state, double *__restrict__ chain_scratch, int force_serial,
                                                            tsdrgpu_frame_result_t *results) {
 	extern __shared__ double smem_d[];
-	double *dbl_x = smem_d, *dbl_y = dbl_x + w;
-	double *cs_base = chains_in_smem ? (dbl_y + h) : chain_scratch;
-	const int cs_stride = chains_in_smem ? max(w, h) : FS_MAX_STRIP;
+	double *buf_x = smem_d, *buf_y = buf_x + (w + 1);    // buf[1..n] = blurred strip, later buf[0..n] = prefix sums
 	__shared__ int cand[2][5];           // strip sizes tried per axis, -1 = skipped
 	__shared__ float totalf[2];
+	__shared__ Best warp_best[10][FS_SYNC_THREADS / 32];
 	__shared__ Best cand_best[2][5];
 	__shared__ SyncState st;
 	__shared__ float tiny[16];
+	__shared__ double warp_tot[32];
+	__shared__ int range_lo[2], range_hi[2], range_bad[2], exact_ok[2];
 	const float taps[5] = {c0, c1, c2, c3, c4};
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
 	auto list_candidates = [&]() {       // clamp the carried strip size, list the sizes to try (syncdetector.c:73-77, 60-69, 88-93)
 		for (int ax = 0; ax < 2; ax++) {
@@ -358,41 +413,81 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restri
 	if (threadIdx.x == 0) { st = *state; list_candidates(); }
 
 	for (int f = 0; f < nframes; f++) {
-		blur_to_double(wstrips + (size_t) f * w, dbl_x, w, taps, tiny);
-		blur_to_double(hstrips + (size_t) f * h, dbl_y, h, taps, tiny);
+		if (threadIdx.x < 2) { range_lo[threadIdx.x] = 255; range_hi[threadIdx.x] = 0; range_bad[threadIdx.x] = 0; }
+		blur_to_double(wstrips + (size_t) f * w, buf_x + 1, w, taps, tiny);
+		blur_to_double(hstrips + (size_t) f * h, buf_y + 1, h, taps, tiny);
 		__syncthreads();
-		if (lane == 0 && warp < 12) {
-			if (warp < 2) totalf[warp] = __double2float_rn(strip_total(warp ? dbl_y : dbl_x, warp ? h : w));   // findbestfit takes a float
+		// exactness certificate (see above)
+		for (int ax = 0; ax < 2; ax++) {
+			const int n = ax ? h : w; const double *d = (ax ? buf_y : buf_x) + 1;
+			ExpRange r; r.lo = 255; r.hi = 0; r.bad = 0;
+			for (int i = threadIdx.x; i < n; i += blockDim.x) exp_range_add(r, (float) d[i]);
+			for (int o = 16; o > 0; o >>= 1) {
+				r.lo = min(r.lo, __shfl_xor_sync(0xffffffffu, r.lo, o)); r.hi = max(r.hi, __shfl_xor_sync(0xffffffffu, r.hi, o));
+				r.bad |= __shfl_xor_sync(0xffffffffu, r.bad, o);
+			}
+			if (lane == 0) { atomicMin(&range_lo[ax], r.lo); atomicMax(&range_hi[ax], r.hi); if (r.bad) atomicOr(&range_bad[ax], 1); }
+		}
+		__syncthreads();
+		if (threadIdx.x < 2) {
+			const int ax = threadIdx.x, n = ax ? h : w;
+			int lg = 0; while ((1 << lg) < n) lg++;
+			const int span = (range_hi[ax] >= range_lo[ax]) ? (range_hi[ax] - range_lo[ax]) : 0;
+			exact_ok[ax] = !force_serial && !range_bad[ax] && n <= 8 * (int) blockDim.x && (span < 29 - lg);
+		}
+		__syncthreads();
+		const bool ok_x = exact_ok[0], ok_y = exact_ok[1];
+		// serial fallback for strips that fail the certificate (window sums go to the global scratch)
+		if ((!ok_x || !ok_y) && lane == 0 && warp < 12) {
+			if (warp < 2) { if (!(warp ? ok_y : ok_x)) totalf[warp] = __double2float_rn(strip_total((warp ? buf_y : buf_x) + 1, warp ? h : w)); }
 			else {
 				const int ax = (warp - 2) / 5, t = (warp - 2) % 5;
 				const int strip = cand[ax][t];
-				if (strip > 0) window_sums(ax ? dbl_y : dbl_x, ax ? h : w, strip, cs_base + (size_t) (warp - 2) * cs_stride);
+				if (strip > 0 && !(ax ? ok_y : ok_x)) window_sums((ax ? buf_y : buf_x) + 1, ax ? h : w, strip, chain_scratch + (size_t) (warp - 2) * FS_MAX_STRIP);
 			}
 		}
+		if (ok_x) exact_prefix(buf_x, w, warp_tot);
+		if (ok_y) exact_prefix(buf_y, h, warp_tot);
+		if (threadIdx.x < 2 && exact_ok[threadIdx.x]) totalf[threadIdx.x] = __double2float_rn(threadIdx.x ? buf_y[h] : buf_x[w]);   // findbestfit takes a float
 		__syncthreads();
-		if (warp < 10) {                 // one warp scores one candidate
-			const int ax = warp / 5, t = warp % 5;
+		// score every window of every candidate; every thread owns a slice of the start positions
+		for (int ci = 0; ci < 10; ci++) {
+			const int ax = ci / 5, t = ci % 5;
 			const int strip = cand[ax][t];
-			Best b; b.score = -1.0; b.e = -1;
+			if (strip <= 0) continue;
+			const int size = ax ? h : w;
+			const bool ok = ax ? ok_y : ok_x;
+			const double *S = ax ? buf_y : buf_x;
+			const double *cs = chain_scratch + (size_t) ci * FS_MAX_STRIP;
+			const double total = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
+			Best b; b.score = -INFINITY; b.e = 0x7fffffff;
+			for (int e = threadIdx.x; e < size; e += blockDim.x) {
+				const double c = ok ? window_from_prefix(S, size, e, strip) : cs[e];
+				const double sc = fit_score(total, c, n_out, n_in);
+				if (sc > b.score) { b.score = sc; b.e = e; }
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
+				b = best_merge(b, other);
+			}
+			if (lane == 0) warp_best[ci][warp] = b;
+		}
+		__syncthreads();
+		if (threadIdx.x < 10) {
+			const int ci = threadIdx.x, ax = ci / 5, t = ci % 5;
+			const int strip = cand[ax][t];
+			Best r; r.score = -1.0; r.e = -1;
 			if (strip > 0) {
 				const int size = ax ? h : w;
-				const double total = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
-				const double *cs = cs_base + (size_t) warp * cs_stride;
-				b.score = -INFINITY; b.e = 0x7fffffff;
-				#pragma unroll 4
-				for (int e = lane; e < size; e += 32) {
-					const double sc = fit_score(total, cs[e], n_out, n_in);
-					if (sc > b.score) { b.score = sc; b.e = e; }
-				}
-				for (int o = 16; o > 0; o >>= 1) {
-					Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
-					b = best_merge(b, other);
-				}
+				r = warp_best[ci][0];
+				for (int k = 1; k < nwarps; k++) r = best_merge(r, warp_best[ci][k]);
 				// e = 0 is the starting value of the reference's running maximum even when it is NaN
-				const double s0 = fit_score(total, cs[0], n_out, n_in);
-				if (!(s0 == s0) || b.e == 0x7fffffff) { b.score = s0; b.e = 0; }
+				const bool ok = ax ? ok_y : ok_x;
+				const double c0s = ok ? window_from_prefix(ax ? buf_y : buf_x, size, 0, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP];
+				const double s0 = fit_score((double) totalf[ax], c0s, (double) (size - strip), (double) strip);
+				if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
 			}
-			if (lane == 0) cand_best[ax][t] = b;
+			cand_best[ax][t] = r;
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) {
@@ -702,11 +797,9 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	const double fresh = 1.0 - (double) motionblur;      // dsp.c:29
 	const int minsize_x = (int) (w * 0.05f), minsize_y = (int) (h * 0.01f);   // syncdetector.c:178-179
 	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
-	const size_t chains_bytes = sizeof(double) * 10 * (size_t) (w > h ? w : h);
-	const size_t strips_bytes = sizeof(double) * ((size_t) w + h);
-	const int chains_in_smem = (strips_bytes + chains_bytes) <= 200 * 1024;
-	const size_t sync_smem = strips_bytes + (chains_in_smem ? chains_bytes : 0);
-	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	const size_t sync_smem = sizeof(double) * ((size_t) w + h + 2);
+	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(double) * (2 * FS_MAX_STRIP + 2))));
+	const int force_serial = getenv("TSDRGPU_SYNC_SERIAL") ? 1 : 0;      // test hook: always take the serial-chain path
 	const unsigned gx = grid_for(n, ctx->sm_count, 4);
 	const size_t total = (size_t) nframes * n;
 
@@ -718,7 +811,7 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 			CU_TRY(ctx, cudaStreamWaitEvent(s2, fs->ev_ready[ph], 0));
 		}
 		KL(ctx, "fs_sync", s2, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, s2>>>(fs->d_wstrips[ph], fs->d_hstrips[ph], w, h, minsize_x, minsize_y, nframes,
-			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain, chains_in_smem, d_results));
+			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain, force_serial, d_results));
 		return TSDRGPU_OK;
 	};
 	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed

@@ -195,6 +195,34 @@ def test_post_process_sequence(gpu, O, lpbs, aap, autoshift, mb, batches):
         k += nb
 
 
+@pytest.mark.parametrize("mode", ["forced_serial", "wide_dynamic_range", "denormals"])
+def test_sync_search_serial_fallback(gpu, O, mode, monkeypatch):
+    """The sync search replaces the reference's serial sliding sums by exact prefix sums when a per-strip exactness
+    certificate holds; these inputs make it fail (or force the serial chains) -- results must still be bit-identical."""
+    from tempestsdr_b200.api import PostProcessFlags
+    w, h = 253, 105
+    po = O.postprocessor(800_000, h, 60.0, 1, 0)
+    pg = gpu.post_processor()
+    if mode == "forced_serial":
+        monkeypatch.setenv("TSDRGPU_SYNC_SERIAL", "1")
+    frames = []
+    for k in range(5):
+        f = synth.video_like_frame(w, h, seed=70 + k, shift_x=20 + 7 * k, shift_y=5 + k).reshape(h, w)
+        if mode == "wide_dynamic_range":
+            f[:, ::7] *= 1e-9; f[::5, :] *= 3e4                # column/row sums now span > 2^17
+        if mode == "denormals":
+            f[:, 3] = 0.0; f[0, 3] = 1e-44                      # a denormal column sum
+        frames.append(np.ascontiguousarray(f.reshape(-1)))
+    # auto-gain after processing so the (extreme) raw values reach the collapse unchanged
+    fl = PostProcessFlags(lowpass_before_sync=True, autogain_after_proc=True)
+    out, res = pg.process(dev(np.concatenate(frames)), w, h, 0.0, 0.1, fl)
+    out = out.cpu().numpy().reshape(5, -1)
+    for k in range(5):
+        wf, wr = po.run(frames[k], w, h, 0.0, 0.1, 1, 1)
+        assert _results_tuple(res[k]) == wr.x.astuple() + wr.y.astuple(), f"{mode} frame {k}"
+        assert_same_bits(out[k], wf, f"{mode} frame {k}")
+
+
 def test_post_process_resize_and_flag_flip(gpu, O):
     from tempestsdr_b200.api import PostProcessFlags
     po = O.postprocessor(8_000_000, 525, 60.0)
