@@ -243,6 +243,15 @@ TSDRGPU_API int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream, float *c
  *   the strided residue s of the output (y[H*p + s], p < N) -- see DESIGN.md "superbandwidth decomposition". */
 TSDRGPU_API int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream, const float *d_hop, int count_pairs,
                                             int best_offset_floats, float *d_spectrum);
+/* the same with ONE exchange in total: every rank sends [FFT_N(raw hop) | FFT_nd(first
+ * difference of |hop|)] (n + nd complex, returned in *h_n / *h_nd), one all-gather, then every rank derives the
+ * integer alignment lags itself (tsdrgpu_superb_lags, exact) and applies them as spectral phase ramps while mixing. */
+TSDRGPU_API int tsdrgpu_superb_local_spectra(tsdrgpu_ctx_t *ctx, void *stream, const float *d_hop, int count_pairs, int samples_in_frame,
+                                             float *d_block, uint32_t *h_n, uint32_t *h_nd);
+TSDRGPU_API int tsdrgpu_superb_lags(tsdrgpu_ctx_t *ctx, void *stream, const float *d_gathered, int nhops, uint64_t block_stride_complex,
+                                    uint32_t n, uint32_t nd, int *h_lags);
+TSDRGPU_API int tsdrgpu_superb_residue_ifft_lag(tsdrgpu_ctx_t *ctx, void *stream, const float *d_gathered, int nhops,
+                                                uint64_t block_stride_complex, uint32_t n, int residue, const int *h_lags, float *d_out_residue);
 TSDRGPU_API int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream, const float *d_gathered, int nhops, uint32_t n,
                                             int residue, float *d_out_residue);
 

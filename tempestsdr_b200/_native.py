@@ -109,6 +109,9 @@ _SIGS = {
     "tsdrgpu_superb_stitch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tsdrgpu_superb_hop_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tsdrgpu_superb_local_spectra": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "tsdrgpu_superb_lags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]),
+    "tsdrgpu_superb_residue_ifft_lag": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "tsdrgpu_superb_residue_ifft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
     "tsdrgpu_pipeline_create": (C.c_int, [C.c_void_p, C.POINTER(PipelineConfig), FRAME_CB, VALUE_CB, PLOT_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_pipeline_destroy": (None, [C.c_void_p]),

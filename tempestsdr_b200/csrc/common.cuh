@@ -69,17 +69,17 @@ __device__ __forceinline__ float mag_exact(float i, float q) {
 
 __device__ __forceinline__ float2 ldg_stream_f2(const float2 *p) {
 	float2 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+	asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
 	return v;
 }
 __device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
 	float4 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+	asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
 	             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
 	return v;
 }
 __device__ __forceinline__ float ldg_stream_f1(const float *p) {
 	float v;
-	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+	asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
 	return v;
 }

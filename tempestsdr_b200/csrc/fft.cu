@@ -34,6 +34,7 @@ struct FftPass {
 	long long in_hi, in_lo, in_cs, in_js;
 	long long out_hi, out_lo, out_cs, out_ks;
 	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
+	const float2 *tab_lo, *tab_hi;                      // W_M^e = tab_lo[e & 4095] * tab_hi[e >> 12]  (forward sign)
 	float scale;
 	int in_real, out_abs;
 };
@@ -159,15 +160,23 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 		if (P.tw_M) {
 			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
 			const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
-			float sn, cs;
-			if (P.tw_M <= (1ull << 24)) sincospif(2.0f * ((float) e / (float) P.tw_M), &sn, &cs);      // exact argument
-			else { double dsn, dcs; sincospi(2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); sn = (float) dsn; cs = (float) dcs; }
-			v = cmul(v, make_float2(cs, inverse ? sn : -sn));
+			float2 tw = __ldg(P.tab_lo + (unsigned) (e & 4095ull));                 // two-level table, both factors from double
+			if (P.tw_M > 4096ull) tw = cmul(tw, __ldg(P.tab_hi + (unsigned) (e >> 12)));
+			if (inverse) tw.y = -tw.y;
+			v = cmul(v, tw);
 		}
 		v.x *= P.scale; v.y *= P.scale;
 		if (P.out_abs) v = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))), 0.0f);
 		out[out_base + (long long) c * P.out_cs + (long long) k * P.out_ks] = v;
 	}
+}
+
+// inter-pass twiddle tables for modulus M: lo[q] = e^{-2 pi i q / M} (q < 4096), hi[q] = e^{-2 pi i q 4096 / M} (q < M/4096)
+__global__ void fft_tw_table_kernel(float2 *lo, float2 *hi, unsigned long long M) {
+	const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+	double sn, cs;
+	if (q < 4096) { sincospi(-2.0 * ((double) (q % M)) / (double) M, &sn, &cs); lo[q] = make_float2((float) cs, (float) sn); }
+	if (M > 4096 && q < (unsigned) (M >> 12)) { sincospi(-2.0 * (double) q * 4096.0 / (double) M, &sn, &cs); hi[q] = make_float2((float) cs, (float) sn); }
 }
 
 __global__ void fft_table_kernel(float2 *table) {
@@ -284,12 +293,54 @@ __global__ void k_residue_mix(const float2 *gathered, int H, unsigned n, int s, 
 	}
 }
 
+// multi-GPU stitch with the alignment folded into the spectrum: rotating hop q left by lag_q samples multiplies its
+// spectrum by e^{+2 pi i m lag_q / N}, so ranks exchange RAW spectra and apply the ramp after the gather:
+// U_s[m] = e^{+2 pi i m s/(H N)} * sum_q e^{+2 pi i (q s / H + m lag_q / N)} X_q[m]
+struct LagSet { int lag[16]; };
+__global__ void k_residue_mix_lag(const float2 *gathered, long long block_stride, int H, unsigned n, int s, LagSet lags, float2 *dst) {
+	for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+		float accr = 0.0f, acci = 0.0f;
+		for (int q = 0; q < H; q++) {
+			// phase = 2 pi (q s / H + m lag / N): both terms reduced exactly in integers before the division
+			const unsigned long long e = ((unsigned long long) m * (unsigned long long) lags.lag[q]) & (unsigned long long) (n - 1);
+			const double frac = (double) e / (double) n + (double) ((q * s) % H) / (double) H;
+			float sn, cs;
+			sincospif((float) (2.0 * (frac - floor(frac))), &sn, &cs);
+			const float2 v = gathered[(size_t) q * block_stride + m];
+			accr += cs * v.x - sn * v.y; acci += cs * v.y + sn * v.x;
+		}
+		double dsn, dcs;
+		sincospi(2.0 * ((double) m * (double) s) / ((double) H * (double) n), &dsn, &dcs);
+		const float sn = (float) dsn, cs = (float) dcs;
+		dst[m] = make_float2(accr * cs - acci * sn, accr * sn + acci * cs);
+	}
+}
+
 inline unsigned grid1d(unsigned long long n, int sm_count) {
 	const unsigned long long want = (n + 255) / 256, cap = (unsigned long long) sm_count * 8;
 	return (unsigned) (want < cap ? (want ? want : 1) : cap);
 }
 
 float2 *g_table[64] = {0};          // per device
+struct TwTab { int device; unsigned long long M; float2 *lo, *hi; };
+std::vector<TwTab> g_twtabs;
+std::mutex g_tw_mu;
+
+int tw_tables(tsdrgpu_ctx_t *ctx, cudaStream_t stream, unsigned long long M, const float2 **lo, const float2 **hi) {
+	std::lock_guard<std::mutex> lock(g_tw_mu);
+	for (auto &t : g_twtabs) if (t.device == ctx->device && t.M == M) { *lo = t.lo; *hi = t.hi; return TSDRGPU_OK; }
+	TwTab t; t.device = ctx->device; t.M = M;
+	const unsigned long long nhi = (M > 4096) ? (M >> 12) : 1;
+	CU_TRY(ctx, cudaMalloc(&t.lo, sizeof(float2) * 4096));
+	CU_TRY(ctx, cudaMalloc(&t.hi, sizeof(float2) * nhi));
+	const unsigned long long threads = nhi > 4096 ? nhi : 4096;
+	fft_tw_table_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, stream>>>(t.lo, t.hi, M);
+	LAUNCH_CHECK(ctx);
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	g_twtabs.push_back(t);
+	*lo = t.lo; *hi = t.hi;
+	return TSDRGPU_OK;
+}
 
 int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	if (g_table[ctx->device]) return TSDRGPU_OK;
@@ -317,6 +368,8 @@ int bundle_for(int log2L, unsigned long long lines) {
 int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, FftPass P, unsigned bundles, int inverse,
                 unsigned batch, long long in_bs, long long out_bs) {
 	P.in_bs = in_bs; P.out_bs = out_bs;
+	P.tab_lo = P.tab_hi = NULL;
+	if (P.tw_M) { int rc = tw_tables(ctx, stream, P.tw_M, &P.tab_lo, &P.tab_hi); if (rc) return rc; }
 	P.log2C = 0; while ((1 << P.log2C) < P.C) P.log2C++;
 	const int L = 1 << P.log2L, total = P.C * L;
 	int threads = (total / 8 + 31) / 32 * 32;            // one radix-8 butterfly (8 elements) per thread and stage
@@ -662,6 +715,58 @@ int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream_, float *const *d_hop
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_out), tp, 1))) return rc;
 	if (h_total_samples) *h_total_samples = (int) total;
 	return TSDRGPU_OK;
+}
+
+// ---- one hop per GPU -------------------------------------------------------------------------------------------------
+// what a rank contributes to the single all-gather: [ X = FFT_N(raw hop) | D = FFT_nd(first difference of |hop|) ]
+int tsdrgpu_superb_local_spectra(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop, int count_pairs, int samples_in_frame,
+                                 float *d_block, uint32_t *h_n, uint32_t *h_nd) {
+	BIND(ctx); ARG_TRY(ctx, d_hop && d_block && count_pairs > 0 && samples_in_frame > 0 && h_n && h_nd);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
+	int size = (int) ((2 * N / samples_in_frame) * samples_in_frame);          // superbandwidth.c:84-86 with bufsize = 2N floats
+	ARG_TRY(ctx, size >= 2);
+	size = (int) tsdrgpu_fft_getrealsize((uint32_t) size);
+	const unsigned long long nd = (unsigned long long) size / 2;
+	float2 *X = reinterpret_cast<float2 *>(d_block), *D = X + N;
+	CU_TRY(ctx, cudaMemcpyAsync(X, d_hop, sizeof(float2) * N, cudaMemcpyDeviceToDevice, stream));
+	int rc;
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, X, N, 0))) return rc;
+	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), D, nd));
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, D, nd, 0))) return rc;
+	*h_n = (uint32_t) N; *h_nd = (uint32_t) nd;
+	return TSDRGPU_OK;
+}
+
+// after the all-gather: the alignment lag of every hop against hop 0 (pairs), exact integers.  synchronises
+int tsdrgpu_superb_lags(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_gathered, int nhops, uint64_t block_stride_complex,
+                        uint32_t n, uint32_t nd, int *h_lags) {
+	BIND(ctx); ARG_TRY(ctx, d_gathered && nhops > 0 && nhops <= 16 && h_lags && nd > 0 && (nd & (nd - 1)) == 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const float2 *G = reinterpret_cast<const float2 *>(d_gathered);
+	void *wa, *res; int rc;
+	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * nd + 256, &wa))) return rc;
+	if ((rc = tsdrgpu_scratch(ctx, 2, sizeof(int) * 16 + 256, &res))) return rc;
+	h_lags[0] = 0;
+	for (int q = 1; q < nhops; q++) {
+		CU_TRY(ctx, cudaMemcpyAsync(wa, G + n, sizeof(float2) * nd, cudaMemcpyDeviceToDevice, stream));            // D_0
+		KL(ctx, "k_conj_mul", stream, k_conj_mul<<<grid1d(nd, ctx->sm_count), 256, 0, stream>>>((float2 *) wa, G + (size_t) q * block_stride_complex + n, nd));
+		if ((rc = tsdrgpu_fft_internal(ctx, stream, (float2 *) wa, nd, 1))) return rc;
+		KL(ctx, "k_argmax_mag", stream, k_argmax_mag<<<1, 1024, 0, stream>>>((const float2 *) wa, nd, (int *) res + q));
+	}
+	CU_TRY(ctx, cudaMemcpyAsync(h_lags + 1, (int *) res + 1, sizeof(int) * (nhops - 1), cudaMemcpyDeviceToHost, stream));
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	return TSDRGPU_OK;
+}
+
+// this rank's strided residue of the H*N-point inverse, from the gathered RAW spectra and the lags
+int tsdrgpu_superb_residue_ifft_lag(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_gathered, int nhops, uint64_t block_stride_complex,
+                                    uint32_t n, int residue, const int *h_lags, float *d_out) {
+	BIND(ctx); ARG_TRY(ctx, d_gathered && d_out && h_lags && nhops > 0 && nhops <= 16 && n > 0 && residue >= 0 && residue < nhops && (n & (n - 1)) == 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	LagSet ls; for (int q = 0; q < 16; q++) ls.lag[q] = q < nhops ? h_lags[q] : 0;
+	KL(ctx, "k_residue_mix", stream, k_residue_mix_lag<<<grid1d(n, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_gathered), (long long) block_stride_complex, nhops, n, residue, ls, reinterpret_cast<float2 *>(d_out)));
+	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_out), n, 1);
 }
 
 int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_gathered, int nhops, uint32_t n, int residue, float *d_out) {

@@ -169,6 +169,28 @@ __global__ void __launch_bounds__(256) fs_timelowpass(const float *__restrict__ 
 	}
 }
 
+// auto-gain pass 2 fused with the temporal IIR (default stage order): out[f][i] = screen_f[i] where
+// screen_f = lowpass(screen_{f-1}, normalise_f(in[f][i])).  Saves one write + one read of the normalised frames.
+__global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__ in, float *out, float *screen, size_t n, int nframes,
+                                                       const FrameParams *__restrict__ params, float coeff, double fresh) {
+	extern __shared__ float2 s_par[];                    // (lastmin, span) per frame
+	for (int f = threadIdx.x; f < nframes; f += blockDim.x) s_par[f] = make_float2(params[f].lastmin, params[f].span);
+	__syncthreads();
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		float s = screen[i];
+		#pragma unroll 4
+		for (int f = 0; f < nframes; f++) {
+			const float raw = __ldg(in + (size_t) f * n + i);
+			const float2 p = s_par[f];
+			const float v = px_is_marker(raw) ? raw : __fdiv_rn(__fsub_rn(raw, p.x), p.y);
+			const float old = __fmul_rn(s, coeff);
+			s = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
+			out[(size_t) f * n + i] = s;
+		}
+		screen[i] = s;
+	}
+}
+
 // ---------------------------------------------------------------- row / column collapse (dsp.c:96-110)
 // Sequential single-precision accumulation in raster order == per column: top to bottom; per row: left to right.
 // grid.x = column CTAs (128 columns each) followed by row CTAs (64 rows each); grid.y = frame.
@@ -680,6 +702,7 @@ static int fs_autogain_batch(tsdrgpu_framestage *fs, cudaStream_t stream, const 
 	if (snr) KL(ctx, "fs_minmax", stream, fs_minmax<true><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum));
 	else KL(ctx, "fs_minmax", stream, fs_minmax<false><<<grid, 256, 0, stream>>>(in, n, fs->d_pmin, fs->d_pmax, fs->d_psum));
 	KL(ctx, "fs_autogain_iir", stream, fs_autogain_iir<<<1, 256, 0, stream>>>(in, n, nframes, chunks, fs->d_pmin, fs->d_pmax, fs->d_psum, snr, norm, fs->d_state, fs->d_params));
+	if (!out) return TSDRGPU_OK;                     // statistics only: the caller fuses the normalisation elsewhere
 	const unsigned gx = grid_for(n, ctx->sm_count, 4);
 	dim3 grid2(snr ? (gx < (unsigned) FS_MM_CHUNKS ? gx : FS_MM_CHUNKS) : gx, nframes);
 	if (snr) KL(ctx, "fs_normalise", stream, fs_normalise<true><<<grid2, 256, 0, stream>>>(in, out, n, fs->d_params, fs->d_psq, fs->d_plin));
@@ -838,12 +861,14 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	if (lpbs) {                                          // dsp.c:201-212
 		const float *lp_in = d_in;
 		if (overlapped) CU_TRY(ctx, cudaStreamWaitEvent(stream, fs->ev_done[ph], 0));      // this phase's buffers are free again
+		const bool fuse = !aap && !snr && nframes <= 4096;
 		if (!aap) {
-			if ((rc = fs_autogain_batch(fs, stream, d_in, fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc;
+			if ((rc = fs_autogain_batch(fs, stream, d_in, fuse ? NULL : fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc;
 			lp_in = fs->d_t1;
 			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
 		}
-		KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, T2, fs->d_screen, n, nframes, motionblur, fresh));
+		if (fuse) KL(ctx, "fs_norm_lowpass", stream, fs_norm_lowpass<<<gx, 256, sizeof(float2) * nframes, stream>>>(d_in, T2, fs->d_screen, n, nframes, fs->d_params, motionblur, fresh));
+		else KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, T2, fs->d_screen, n, nframes, motionblur, fresh));
 		if (overlapped) tail = fs->s_side;
 		if ((rc = collapse_sync(T2, tail))) return rc;
 		float *dst = aap ? fs->d_t1 : d_out;

@@ -66,29 +66,24 @@ __device__ __forceinline__ bool rs_isA(const Geo &g, double Pkm1) { return Pkm1 
 template <bool IQ>
 __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ in, float *__restrict__ out,
                                                       const RsBlock *__restrict__ blocks,
-                                                      const unsigned *__restrict__ tile_prefix, unsigned nblocks) {
+                                                      const uint2 *__restrict__ tile_info /* {block, first sample} per tile */) {
 	__shared__ float s_mag[RS_HALO + RS_TILE];
-	__shared__ float s_out[RS_OUT_CAP];
-	__shared__ unsigned s_b;
+	__shared__ __align__(16) float s_out[RS_OUT_CAP + 8];
 
-	const unsigned tile = blockIdx.x;
-	if (threadIdx.x == 0) {
-		unsigned lo = 0, hi = nblocks;
-		while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (tile_prefix[mid] <= tile) lo = mid; else hi = mid; }
-		s_b = lo;
-	}
-	__syncthreads();
-	const unsigned b = s_b;
-	const RsBlock B = blocks[b];
-	const unsigned s0 = (tile - tile_prefix[b]) * RS_TILE;
+	const uint2 ti = tile_info[blockIdx.x];
+	const RsBlock B = blocks[ti.x];
+	const unsigned s0 = ti.y;
 	const unsigned s1 = min(s0 + (unsigned) RS_TILE, B.size);
 	const unsigned halo = min((unsigned) RS_HALO, s0);
 	const double r = B.r, phase = B.phase;
 
-	// stage magnitudes (demod fused): s_mag[RS_HALO + (k - s0)] = |x_k|
-	for (unsigned i = threadIdx.x; i < (s1 - s0) + halo; i += RS_THREADS) {
-		const unsigned k = s0 - halo + i;
-		s_mag[RS_HALO - halo + i] = rs_load<IQ>(in, B.in_start + k);
+	// stage magnitudes (demod fused): s_mag[RS_HALO + (k - s0)] = |x_k|.  Loads are issued 8 deep per thread.
+	{
+		const unsigned n_load = (s1 - s0) + halo;
+		const unsigned long long first = B.in_start + s0 - halo;
+		float *dst = s_mag + (RS_HALO - halo);
+		#pragma unroll 8
+		for (unsigned i = threadIdx.x; i < n_load; i += RS_THREADS) dst[i] = rs_load<IQ>(in, first + i);
 	}
 	const double pbase_d = (s0 == 0) ? 0.0 : rs_P(rs_geo(s0 - 1, r, phase).c);
 	const double pend_d = rs_P(rs_geo(s1 - 1, r, phase).c);
@@ -96,72 +91,102 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 	const unsigned pend = (unsigned) pend_d;
 	const bool staged = (pend - pbase) <= (unsigned) RS_OUT_CAP;
 	float *gout = out + B.out_start;
+	// staging index = (p - pbase) + aoff, chosen so that shared and global addresses are congruent modulo 16 bytes
+	const unsigned aoff = (unsigned) ((reinterpret_cast<unsigned long long>(gout + pbase) >> 2) & 3ull);
+	float *sq = s_out + aoff;
 	__syncthreads();
 
-	// One warp owns 32 CONSECUTIVE samples per round, so everything sample k needs from sample k-1 (its pid, whether it
-	// emitted an A pixel, what it banked) arrives by one warp shuffle instead of being recomputed in double precision.
+	// One warp owns 256 CONSECUTIVE samples, 32 per round: what sample k needs from sample k-1 (its pid, whether it emitted
+	// an A pixel, what it banked) arrives by warp shuffle, or from the previous round's lane 31.
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	for (unsigned base = s0 + warp * 32u; base < s1; base += RS_THREADS) {
-		const unsigned k = base + lane;
-		const bool live = k < s1;
-		const unsigned kk = live ? k : (s1 - 1);                 // idle lanes shadow the last sample (results unused)
-		const Geo g = rs_geo(kk, r, phase);
-		const double Pk = rs_P(g.c);
-		const float vf = s_mag[RS_HALO + (kk - s0)];
-		const double v = (double) vf;
-		const double tk = rs_t(g, Pk, r, v);
-		double Pkm1 = __shfl_up_sync(0xffffffffu, Pk, 1);
-		if (lane == 0) Pkm1 = (kk == 0) ? 0.0 : rs_P(rs_geo(kk - 1, r, phase).c);
-		const bool isA = rs_isA(g, Pkm1);
-		int prevA = __shfl_up_sync(0xffffffffu, (int) isA, 1);
-		double prevT = __shfl_up_sync(0xffffffffu, tk, 1);
-		if (lane == 0 && isA && kk > 0) {                        // the neighbour lives in another warp: recompute it
-			const Geo gp = rs_geo(kk - 1, r, phase);
-			const double Ppm1 = (kk == 1) ? 0.0 : rs_P(rs_geo(kk - 2, r, phase).c);
-			prevA = rs_isA(gp, Ppm1);
-			const float vp = (kk - 1 + RS_HALO >= s0) ? s_mag[RS_HALO + (kk - 1) - s0] : rs_load<IQ>(in, B.in_start + kk - 1);
-			prevT = rs_t(gp, rs_P(gp.c), r, (double) vp);
+	const unsigned wbase = s0 + warp * (RS_TILE / (RS_THREADS / 32));
+	if (wbase < s1) {
+		double carryP = 0.0, carryT = 0.0; int carryA = 0;
+		if (wbase > 0) {                                         // the sample just before this warp's range (once per warp)
+			const unsigned kp = wbase - 1;
+			const Geo gp = rs_geo(kp, r, phase);
+			carryP = rs_P(gp.c);
+			const double Ppm1 = (kp == 0) ? 0.0 : rs_P(rs_geo(kp - 1, r, phase).c);
+			carryA = rs_isA(gp, Ppm1);
+			const float vp = (kp + RS_HALO >= s0) ? s_mag[RS_HALO + kp - s0] : rs_load<IQ>(in, B.in_start + kp);
+			carryT = rs_t(gp, carryP, r, (double) vp);
 		}
-		if (!live) continue;
-		unsigned p = (unsigned) Pkm1;
-		const unsigned pstop = (unsigned) Pk;
-		if (isA) {
-			double bank = 0.0;
-			bool have = false;
-			if (k > 0 && prevA) { bank = __dadd_rn(0.0, prevT); have = true; }      // the common case for r > 1
-			else if (k > 0) {
-				// general case: bank = t_L + ... + t_{k-1}, L = latest earlier sample that emitted an A pixel
-				long long L = (long long) k - 2;
-				while (L >= 0) {
-					const Geo gl = rs_geo((unsigned) L, r, phase);
-					const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, r, phase).c);
-					if (rs_isA(gl, Plm1)) break;
-					L--;
-				}
-				if (L >= 0) {
-					for (unsigned j = (unsigned) L; j < k; j++) {
-						const Geo gj = rs_geo(j, r, phase);
-						const float vj = (j + RS_HALO >= s0) ? s_mag[RS_HALO + j - s0] : rs_load<IQ>(in, B.in_start + j);
-						bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) vj));
+		for (unsigned base = wbase; base < min(wbase + (unsigned) (RS_TILE / (RS_THREADS / 32)), s1); base += 32) {
+			const unsigned k = base + lane;
+			const bool live = k < s1;
+			const unsigned kk = live ? k : (s1 - 1);             // idle lanes shadow the last sample (results unused)
+			const Geo g = rs_geo(kk, r, phase);
+			const double Pk = rs_P(g.c);
+			const float vf = s_mag[RS_HALO + (kk - s0)];
+			const double v = (double) vf;
+			const double tk = rs_t(g, Pk, r, v);
+			double Pkm1 = __shfl_up_sync(0xffffffffu, Pk, 1);
+			if (lane == 0) Pkm1 = carryP;
+			const bool isA = rs_isA(g, Pkm1);
+			int prevA = __shfl_up_sync(0xffffffffu, (int) isA, 1);
+			double prevT = __shfl_up_sync(0xffffffffu, tk, 1);
+			if (lane == 0) { prevA = carryA; prevT = carryT; }
+			carryP = __shfl_sync(0xffffffffu, Pk, 31); carryA = __shfl_sync(0xffffffffu, (int) isA, 31); carryT = __shfl_sync(0xffffffffu, tk, 31);
+			if (!live) continue;
+			const unsigned p0 = (unsigned) Pkm1, cnt = (unsigned) Pk - p0;
+			float first = vf;
+			bool write_first = true;
+			if (isA) {
+				double bank = 0.0;
+				bool have = false;
+				if (k > 0 && prevA) { bank = __dadd_rn(0.0, prevT); have = true; }      // the common case for r > 1
+				else if (k > 0) {
+					// general case: bank = t_L + ... + t_{k-1}, L = latest earlier sample that emitted an A pixel
+					long long L = (long long) k - 2;
+					while (L >= 0) {
+						const Geo gl = rs_geo((unsigned) L, r, phase);
+						const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, r, phase).c);
+						if (rs_isA(gl, Plm1)) break;
+						L--;
 					}
-					have = true;
+					if (L >= 0) {
+						for (unsigned j = (unsigned) L; j < k; j++) {
+							const Geo gj = rs_geo(j, r, phase);
+							const float vj = (j + RS_HALO >= s0) ? s_mag[RS_HALO + j - s0] : rs_load<IQ>(in, B.in_start + j);
+							bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) vj));
+						}
+						have = true;
+					}
+				}
+				if (have) {
+					const double w = __dadd_rn(__dsub_rn(1.0, g.lo), Pkm1);
+					first = __double2float_rn(__dadd_rn(bank, __dmul_rn(v, w)));
+				} else write_first = false;      // the bank reaches past the block start -> rs_fixup writes this pixel
+			}
+			if (staged) {
+				float *d = sq + (p0 - pbase);
+				if (cnt > 0 && write_first) d[0] = first;
+				if (cnt > 1) d[1] = vf;
+				if (cnt > 2) d[2] = vf;
+				for (unsigned c = 3; c < cnt; c++) d[c] = vf;
+			} else {
+				for (unsigned c = 0; c < cnt; c++) {
+					const unsigned p = p0 + c;
+					if (p < B.n_out && (c > 0 || write_first)) gout[p] = c ? vf : first;
 				}
 			}
-			if (have) {
-				const double w = __dadd_rn(__dsub_rn(1.0, g.lo), Pkm1);
-				const float px = __double2float_rn(__dadd_rn(bank, __dmul_rn(v, w)));
-				if (staged) s_out[p - pbase] = px; else if (p < B.n_out) gout[p] = px;
-			}   // else: the bank reaches past the block start -> rs_fixup writes this pixel
-			p++;
-		}
-		for (; p < pstop; p++) {
-			if (staged) s_out[p - pbase] = vf; else if (p < B.n_out) gout[p] = vf;
 		}
 	}
 	if (!staged) return;
 	__syncthreads();
+	// write the assembled run of pixels: scalar head to a 16-byte boundary, float4 body, scalar tail
 	const unsigned pe = min(pend, B.n_out);
-	for (unsigned q = pbase + threadIdx.x; q < pe; q += RS_THREADS) gout[q] = s_out[q - pbase];
+	if (pe <= pbase) return;
+	const unsigned count = pe - pbase;
+	float *gdst = gout + pbase;
+	const unsigned head = min((4u - aoff) & 3u, count);
+	if (threadIdx.x < head) gdst[threadIdx.x] = sq[threadIdx.x];
+	const unsigned body4 = (count - head) >> 2;
+	const float4 *s4 = reinterpret_cast<const float4 *>(sq + head);
+	float4 *g4 = reinterpret_cast<float4 *>(gdst + head);
+	for (unsigned q = threadIdx.x; q < body4; q += RS_THREADS) g4[q] = s4[q];
+	const unsigned done = head + (body4 << 2);
+	if (threadIdx.x < count - done) gdst[done + threadIdx.x] = sq[done + threadIdx.x];
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -350,8 +375,10 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 	ARG_TRY(ctx, upsample_by > 0 && downsample_by > 0);
 	ARG_TRY(ctx, nblocks <= 65535u);
 
-	// descriptor slot: [RsBlock x nblocks][tile_prefix x (nblocks+1)]
-	const size_t need = sizeof(tsdrgpu_rs_block_t) * nblocks + sizeof(unsigned) * (nblocks + 1);
+	// descriptor slot: [RsBlock x nblocks][{block, first sample} x tiles]
+	size_t max_tiles = 0;
+	for (uint32_t b = 0; b < nblocks; b++) max_tiles += ((size_t) (block_sizes ? block_sizes[b] : uniform_block) + RS_TILE - 1) / RS_TILE;
+	const size_t need = sizeof(tsdrgpu_rs_block_t) * nblocks + sizeof(uint2) * (max_tiles + 1);
 	const int slot = r->next; r->next = (r->next + 1) % tsdrgpu_resampler::SLOTS;
 	CU_TRY(ctx, cudaEventSynchronize(r->ev[slot]));
 	if (r->desc_bytes[slot] < need) {
@@ -363,7 +390,7 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 		r->desc_bytes[slot] = cap;
 	}
 	tsdrgpu_rs_block_t *hb = (tsdrgpu_rs_block_t *) r->h_desc[slot];
-	unsigned *hp = (unsigned *) (hb + nblocks);
+	uint2 *hp = (uint2 *) (hb + nblocks);
 
 	double off = r->offset;
 	const uint64_t total = tsdrgpu_plan_resample(&off, block_sizes, uniform_block, nblocks, upsample_by, downsample_by, hb);
@@ -373,15 +400,13 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 		return tsdrgpu_fail(ctx, TSDRGPU_ECAPACITY, "resampler output buffer too small", cudaSuccess, __FILE__, __LINE__);
 	unsigned tiles = 0, max_out = 0;
 	for (uint32_t b = 0; b < nblocks; b++) {
-		hp[b] = tiles;
-		tiles += (hb[b].size + RS_TILE - 1) / RS_TILE;
+		for (unsigned s0 = 0; s0 < hb[b].size; s0 += RS_TILE) hp[tiles++] = make_uint2(b, s0);
 		if (hb[b].n_out > max_out) max_out = hb[b].n_out;
 	}
-	hp[nblocks] = tiles;
 	CU_TRY(ctx, cudaMemcpyAsync(r->d_desc[slot], r->h_desc[slot], need, cudaMemcpyHostToDevice, stream));
 	CU_TRY(ctx, cudaEventRecord(r->ev[slot], stream));
 	const RsBlock *db = (const RsBlock *) r->d_desc[slot];
-	const unsigned *dp = (const unsigned *) (db + nblocks);
+	const uint2 *dp = (const uint2 *) (db + nblocks);
 
 	if (nearest) {
 		dim3 grid((max_out + 1023) / 1024, nblocks);
@@ -394,8 +419,8 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			CU_TRY(ctx, cudaMalloc(&r->d_bank, sizeof(double) * r->bank_cap));
 			CU_TRY(ctx, cudaMalloc(&r->d_has_a, sizeof(int) * r->bank_cap));
 		}
-		if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks));
-		else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, nblocks));
+		if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp));
+		else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp));
 		if (in_is_iq) KL(ctx, "rs_fixup", stream, rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 		else KL(ctx, "rs_fixup", stream, rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 	}

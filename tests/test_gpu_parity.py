@@ -339,6 +339,11 @@ def test_superbandwidth(gpu, O):
     for s in range(4):
         full[s::4] = gpu.superb_residue_ifft(specs, 4, n, s).cpu().numpy().reshape(-1, 2)
     _close(full.reshape(-1), want, 6e-6, "residue decomposition")
+    # the one-exchange dataflow (raw spectra + difference spectra gathered once, lags applied as phase ramps)
+    from tempestsdr_b200 import superband
+    sim, sim_offs = superband.stitch_simulated(gpu, [dev(h) for h in hops], sif)
+    assert list(sim_offs) == list(offs)
+    _close(sim, want, 8e-6, "one-exchange stitch")
 
 
 # ------------------------------------------------------------------------------------------------ golden vectors
