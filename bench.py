@@ -117,7 +117,7 @@ class DeviceStep:
         self.up = w * HEIGHT * FV
         self.rs = gpu.resampler()
         self.pp = gpu.post_processor()
-        self.pp.set_overlap(True)                 # sync search + re-centring of batch k under the kernels of batch k+1
+        self.pp.set_overlap(not os.environ.get("BENCH_NO_OVERLAP"))   # sync search + re-centring of batch k under the kernels of batch k+1
         self.frd = gpu.framerate_detector()
         self.flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True)     # the GUI's defaults
         self.cap = FrameRateDetector.capture_size(FS)
@@ -301,6 +301,26 @@ def run_ours(args):
     e2e_frames = s1.frames_delivered - s0.frames_delivered
     pl.close()
 
+    # ---- N > 1 only: the path's one real exchange, the superbandwidth stitch with one hop per GPU (configs[3])
+    superb = None
+    if world > 1:
+        from tempestsdr_b200 import superband
+        hop_pairs = 10 * int(FS / FV)                        # SUPER_SAMPLES_TO_RECORD frames per hop -> N = 2^22
+        hop = iq_dev[: 2 * hop_pairs].contiguous()
+        for _ in range(2):
+            superband.stitch_distributed(gpu, hop, int(FS / FV))
+        barrier()
+        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        s0e.record()
+        for _ in range(reps):
+            res, lags, n_fft = superband.stitch_distributed(gpu, hop, int(FS / FV))
+        s1e.record()
+        barrier()
+        tms = torch.tensor([s0e.elapsed_time(s1e) / reps], device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        superb = {"hops": world, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": world * n_fft / (tms.item() * 1e-3) / 1e6,
+                  "allgather_bytes_per_rank": 8 * (n_fft + n_fft // 2), "collective": "one NCCL all_gather_into_tensor per stitch"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -353,6 +373,8 @@ def run_ours(args):
                 "frames copied back to pinned host slots; host wall clock between device synchronisations"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }
+    if superb:
+        line["superbandwidth"] = superb
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

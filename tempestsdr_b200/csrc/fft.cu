@@ -19,13 +19,14 @@
 // both carry ~1e-7*sqrt(log2 N) relative noise; results agree to ~1e-6 of the spectrum's peak (not bit-exact).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
 
 constexpr int FFT_MAX_LOG2L = 11;            // longest line transformed inside one CTA: 2048
 constexpr int FFT_TABLE = 1 << FFT_MAX_LOG2L;
-constexpr int FFT_MAX_ELEMS = 8192;          // complex elements per CTA bundle: 1024 threads x 8 (68 KB of shared memory)
+constexpr int FFT_MAX_ELEMS = 4096;          // complex elements per CTA bundle: 512 threads x 8 (35 KB of shared memory, >= 3 CTAs/SM)
 
 struct FftPass {
 	int log2L, C, log2C, c_fast_in, c_fast_out;
@@ -123,7 +124,7 @@ __device__ __forceinline__ void stockham_stage(float2 *s, int LP, int C, int p, 
 }
 
 template <int LOG2L>
-__global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
+__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
                                                         const float2 *__restrict__ table, int inverse_) {
 	extern __shared__ float2 s[];
 	constexpr int L = 1 << LOG2L;
@@ -160,8 +161,12 @@ __global__ void __launch_bounds__(1024) fft_pass_kernel(const float2 *in, float2
 		if (P.tw_M) {
 			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
 			const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
-			float2 tw = __ldg(P.tab_lo + (unsigned) (e & 4095ull));                 // two-level table, both factors from double
-			if (P.tw_M > 4096ull) tw = cmul(tw, __ldg(P.tab_hi + (unsigned) (e >> 12)));
+			float2 tw;
+			if (P.tab_lo) {                                   // two-level table (opt-in: scattered lookups measured slower)
+				tw = __ldg(P.tab_lo + (unsigned) (e & 4095ull));
+				if (P.tw_M > 4096ull) tw = cmul(tw, __ldg(P.tab_hi + (unsigned) (e >> 12)));
+			} else if (P.tw_M <= (1ull << 24)) { float sn, cs; sincospif(-2.0f * ((float) e / (float) P.tw_M), &sn, &cs); tw = make_float2(cs, sn); }   // exact argument
+			else { double dsn, dcs; sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); tw = make_float2((float) dcs, (float) dsn); }
 			if (inverse) tw.y = -tw.y;
 			v = cmul(v, tw);
 		}
@@ -369,12 +374,13 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
                 unsigned batch, long long in_bs, long long out_bs) {
 	P.in_bs = in_bs; P.out_bs = out_bs;
 	P.tab_lo = P.tab_hi = NULL;
-	if (P.tw_M) { int rc = tw_tables(ctx, stream, P.tw_M, &P.tab_lo, &P.tab_hi); if (rc) return rc; }
+	static const bool use_tables = getenv("TSDRGPU_FFT_TWIDDLE_TABLES") != NULL;
+	if (P.tw_M && use_tables) { int rc = tw_tables(ctx, stream, P.tw_M, &P.tab_lo, &P.tab_hi); if (rc) return rc; }
 	P.log2C = 0; while ((1 << P.log2C) < P.C) P.log2C++;
 	const int L = 1 << P.log2L, total = P.C * L;
 	int threads = (total / 8 + 31) / 32 * 32;            // one radix-8 butterfly (8 elements) per thread and stage
 	if (threads < 32) threads = 32;
-	if (threads > 1024) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT bundle too large", cudaSuccess, __FILE__, __LINE__);
+	if (threads > 512) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT bundle too large", cudaSuccess, __FILE__, __LINE__);
 	const int LP = L + (L >> 4) + 1;
 	const size_t smem = sizeof(float2) * (size_t) P.C * LP;
 	const dim3 grid(bundles, batch);
@@ -407,7 +413,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs);
 	}
 	int rc;
-	if (log2N <= 2 * FFT_MAX_LOG2L) {                   // N = N1 * N2 ; n = N2*n1 + n2 ; k = k1 + N1*k2
+	if (log2N <= 20) {                                  // N = N1 * N2 (lines <= 1024) ; n = N2*n1 + n2 ; k = k1 + N1*k2
 		const unsigned l1 = (log2N + 1) / 2, l2 = log2N - l1;
 		const unsigned long long N1 = 1ull << l1, N2 = 1ull << l2;
 		P.log2L = (int) l1; P.C = bundle_for((int) l1, N2); P.c_fast_in = P.c_fast_out = 1;

@@ -26,7 +26,7 @@ namespace {
 
 constexpr int FS_MAX_STRIP = 8192;      // longest width/height the in-CTA sync search supports
 constexpr int FS_MM_CHUNKS = 64;        // partial reductions per frame
-constexpr int FS_SYNC_THREADS = 1024;
+constexpr int FS_SYNC_THREADS = 512;       // half an SM's registers: it must find room beside the main stream's CTAs
 
 __device__ __forceinline__ bool px_is_marker(float v) { return v > 250.0f || v < -250.0f; }   // dsp.c:57
 
@@ -366,10 +366,8 @@ __device__ __forceinline__ void exp_range_add(ExpRange &r, float v) {
 __device__ void exact_prefix(double *buf, int n, double *warp_tot /* >= 32 */) {
 	const int T = blockDim.x, chunk = (n + T - 1) / T;
 	const int i0 = min((int) threadIdx.x * chunk, n), i1 = min(i0 + chunk, n);
-	double v[8];                                         // n <= 8 * blockDim.x (checked by the caller)
-	double local = 0.0;
-	#pragma unroll
-	for (int u = 0; u < 8; u++) if (i0 + u < i1) { v[u] = buf[1 + i0 + u]; local += v[u]; }
+	double local = 0.0;                                  // every thread owns one contiguous chunk (n <= 16 * blockDim.x)
+	for (int i = i0; i < i1; i++) local += buf[1 + i];
 	// exclusive scan of `local` across the CTA
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	double incl = local;
@@ -386,8 +384,7 @@ __device__ void exact_prefix(double *buf, int n, double *warp_tot /* >= 32 */) {
 	__syncthreads();
 	double run = warp_tot[warp] + (incl - local);
 	if (threadIdx.x == 0) buf[0] = 0.0;
-	#pragma unroll
-	for (int u = 0; u < 8; u++) if (i0 + u < i1) { run += v[u]; buf[1 + i0 + u] = run; }
+	for (int i = i0; i < i1; i++) { run += buf[1 + i]; buf[1 + i] = run; }      // in place: a thread only touches its own chunk
 	__syncthreads();
 }
 
@@ -401,7 +398,7 @@ __device__ __forceinline__ double window_from_prefix(const double *S, int n, int
 // Per frame: blur both strips into double (all threads) + exactness certificate | exact prefix scans (or, when the
 // certificate fails, the serial chains) | every thread scores a slice of the windows of every candidate strip size,
 // first-max reduce | thread 0: pick the strip size, update dx/vx, PLL average.
-__global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
+__global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
                                                            int w, int h, int minsize_x, int minsize_y, int nframes,
                                                            float c0, float c1, float c2, float c3, float c4,
                                                            SyncState *state, double *__restrict__ chain_scratch, int force_serial,
@@ -455,7 +452,7 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync(const float *__restri
 			const int ax = threadIdx.x, n = ax ? h : w;
 			int lg = 0; while ((1 << lg) < n) lg++;
 			const int span = (range_hi[ax] >= range_lo[ax]) ? (range_hi[ax] - range_lo[ax]) : 0;
-			exact_ok[ax] = !force_serial && !range_bad[ax] && n <= 8 * (int) blockDim.x && (span < 29 - lg);
+			exact_ok[ax] = !force_serial && !range_bad[ax] && n <= 16 * (int) blockDim.x && (span < 29 - lg);
 		}
 		__syncthreads();
 		const bool ok_x = exact_ok[0], ok_y = exact_ok[1];
@@ -721,7 +718,11 @@ int tsdrgpu_framestage_create(tsdrgpu_ctx_t *ctx, tsdrgpu_framestage_t **out) {
 	tsdrgpu_gauss_taps(fs->taps);
 	CU_TRY(ctx, cudaMalloc(&fs->d_state, sizeof(SyncState)));
 	CU_TRY(ctx, cudaMalloc(&fs->d_chain, sizeof(double) * 10 * FS_MAX_STRIP));
-	CU_TRY(ctx, cudaStreamCreateWithFlags(&fs->s_side, cudaStreamNonBlocking));
+	{   // highest priority: its single CTA should be placed as soon as an SM has room, ahead of the main stream's queued CTAs
+		int lo = 0, hi = 0;
+		CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CU_TRY(ctx, cudaStreamCreateWithPriority(&fs->s_side, cudaStreamNonBlocking, hi));
+	}
 	for (int i = 0; i < 2; i++) {
 		CU_TRY(ctx, cudaEventCreateWithFlags(&fs->ev_ready[i], cudaEventDisableTiming));
 		CU_TRY(ctx, cudaEventCreateWithFlags(&fs->ev_done[i], cudaEventDisableTiming));
@@ -861,7 +862,8 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	if (lpbs) {                                          // dsp.c:201-212
 		const float *lp_in = d_in;
 		if (overlapped) CU_TRY(ctx, cudaStreamWaitEvent(stream, fs->ev_done[ph], 0));      // this phase's buffers are free again
-		const bool fuse = !aap && !snr && nframes <= 4096;
+		static const bool no_fuse = getenv("TSDRGPU_NO_FUSE") != NULL;
+		const bool fuse = !aap && !snr && nframes <= 4096 && !no_fuse;
 		if (!aap) {
 			if ((rc = fs_autogain_batch(fs, stream, d_in, fuse ? NULL : fs->d_t1, nframes, n, lowpasscoeff, snr))) return rc;
 			lp_in = fs->d_t1;

@@ -68,9 +68,10 @@ struct tsdrgpu_pipeline {
 	tsdrgpu_ctx_t *ctx;
 	tsdrgpu_pipeline_config_t cfg;
 	tsdrgpu_frame_cb frame_cb; tsdrgpu_value_cb value_cb; tsdrgpu_plot_cb plot_cb; void *user;
-	cudaStream_t s_main, s_copy, s_out;
+	cudaStream_t s_main, s_copy, s_out, s_ingest;      // heavy kernels | H2D | D2H | light per-block kernels
+	cudaEvent_t ev_ingest, ev_decim, ev_cap_used[2];
 	cudaEvent_t ev_out[2], ev_main; int out_phase;
-	cudaEvent_t ev_h2d[2], ev_used[2]; int stage_slot;
+	cudaEvent_t ev_h2d[4], ev_used[4]; int stage_slot;
 
 	// live geometry (set_internal_samplerate)
 	pthread_mutex_t geo_mu;
@@ -79,7 +80,7 @@ struct tsdrgpu_pipeline {
 	uint32_t params[9];
 
 	// stage 0: H2D staging of the plugin's buffer
-	float *d_stage[2]; size_t stage_cap[2];           // floats; double-buffered so H2D overlaps the kernels
+	float *d_stage[4]; size_t stage_cap[4];           // floats; 4 slots so H2D runs ahead of the kernels
 	std::vector<void *> registered;
 	// stage 1: decimator input (IQ pairs waiting for whole blocks)
 	float *d_decim; size_t decim_cap, decim_fill;     // pairs
@@ -94,7 +95,7 @@ struct tsdrgpu_pipeline {
 	float *h_frames[PL_SLOTS]; tsdrgpu_frame_result_t *h_results[PL_SLOTS]; int32_t *h_report[PL_SLOTS]; size_t slot_cap;
 	int slot_busy[PL_SLOTS];
 	// autocorrelation side path
-	tsdrgpu_frd *frd; float *d_capture; size_t cap_size, cap_fill; uint32_t cap_rate;
+	tsdrgpu_frd *frd; float *d_capture[2]; size_t cap_size[2], cap_fill; int cap_phase; uint32_t cap_rate;
 	double *h_plot_frame[2], *h_plot_line[2]; size_t plot_cap; int plot_slot; int plot_busy[2];
 	// delivery
 	pthread_t thread; pthread_mutex_t mu; pthread_cond_t cv_job, cv_done;
@@ -196,14 +197,22 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 	const size_t want = tsdrgpu_frd_capture_size(p->samplerate);
 	if (want == 0) return TSDRGPU_OK;
 	int rc;
-	if (p->cap_size < want) { if ((rc = grow(ctx, p->s_main, &p->d_capture, &p->cap_size, want, p->cap_fill))) return rc; }
+	for (int i = 0; i < 2; i++) if (p->cap_size[i] < want) {
+		CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest));
+		if ((rc = grow(ctx, p->s_main, &p->d_capture[i], &p->cap_size[i], want, (i == p->cap_phase) ? p->cap_fill : 0))) return rc;
+	}
 	uint64_t done = 0;
 	while (done < pairs) {
 		const uint64_t take = (want - p->cap_fill) < (pairs - done) ? (want - p->cap_fill) : (pairs - done);
-		if ((rc = tsdrgpu_am_demod(ctx, p->s_main, d_iq + 2 * done, take, p->d_capture + p->cap_fill))) return rc;
+		float *cap = p->d_capture[p->cap_phase];
+		if (p->cap_fill == 0) CU_TRY(ctx, cudaStreamWaitEvent(p->s_ingest, p->ev_cap_used[p->cap_phase], 0));   // the FFT that last read it is done
+		if ((rc = tsdrgpu_am_demod(ctx, p->s_ingest, d_iq + 2 * done, take, cap + p->cap_fill))) return rc;
 		p->cap_fill += take; done += take;
 		if (p->cap_fill == want) {
 			p->cap_fill = 0;
+			const int cph = p->cap_phase; p->cap_phase ^= 1;
+			CU_TRY(ctx, cudaEventRecord(p->ev_ingest, p->s_ingest));
+			CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_ingest, 0));
 			int reset_announce = 0;
 			if (p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_RESET]) {          // frameratedetector.c:97-104
 				reset_announce = (p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_RESET] == 1);
@@ -233,9 +242,10 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 				p->plot_cap = need;
 			}
 			uint64_t calls = 0;
-			if ((rc = tsdrgpu_frd_run_async(p->frd, p->s_main, p->samplerate, p->d_capture, (uint32_t) want,
+			if ((rc = tsdrgpu_frd_run_async(p->frd, p->s_main, p->samplerate, cap, (uint32_t) want,
 			                                slot >= 0 ? p->h_plot_frame[slot] : NULL, fmax - fmin,
 			                                slot >= 0 ? p->h_plot_line[slot] : NULL, lmax - lmin, &calls))) return rc;
+			CU_TRY(ctx, cudaEventRecord(p->ev_cap_used[cph], p->s_main));
 			p->stats.captures++;
 			if (slot >= 0) {
 				FrameJob j; memset(&j, 0, sizeof j);
@@ -366,6 +376,7 @@ static int drain_blocks(tsdrgpu_pipeline *p) {
 		// consume the blocks: move the tail to the front
 		const size_t used = (size_t) nb * block, left = p->decim_fill - used;
 		if (left) { pl_copy_f32<<<(unsigned) ((2 * left + 255) / 256 < 1024 ? (2 * left + 255) / 256 : 1024), 256, 0, p->s_main>>>(p->d_decim + 2 * used, p->d_decim, 2 * left); LAUNCH_CHECK(ctx); }
+		CU_TRY(ctx, cudaEventRecord(p->ev_decim, p->s_main));                // later appends (ingest stream) must come after this
 		p->decim_fill = left;
 		p->stats.samples_resampled += used;
 		if ((rc = drain_frames(p, w, h))) return rc;
@@ -387,9 +398,9 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	pthread_mutex_init(&p->geo_mu, NULL); pthread_mutex_init(&p->mu, NULL);
 	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
 	geometry_locked(p);
-	p->d_stage[0] = p->d_stage[1] = NULL; p->stage_cap[0] = p->stage_cap[1] = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
+	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; } p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
 	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
-	p->slot_cap = 0; p->d_capture = NULL; p->cap_size = 0; p->cap_fill = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
+	p->slot_cap = 0; p->d_capture[0] = p->d_capture[1] = NULL; p->cap_size[0] = p->cap_size[1] = 0; p->cap_fill = 0; p->cap_phase = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
 	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
 	p->stop = 0; p->submitted = 0; p->delivered = 0; p->last_w = 0; p->last_h = 0;
@@ -399,10 +410,14 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; i++) CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
 	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_main, cudaEventDisableTiming));
-	for (int i = 0; i < 2; i++) {
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_ingest, cudaStreamNonBlocking));
+	for (int i = 0; i < 4; i++) {
 		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
 		CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_used[i], cudaEventDisableTiming));
 	}
+	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_ingest, cudaEventDisableTiming));
+	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_decim, cudaEventDisableTiming));
+	for (int i = 0; i < 2; i++) CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_cap_used[i], cudaEventDisableTiming));
 	int rc;
 	if ((rc = tsdrgpu_resampler_create(ctx, &p->rs))) return rc;
 	if ((rc = tsdrgpu_framestage_create(ctx, &p->fs))) return rc;
@@ -417,6 +432,7 @@ int tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
 	BIND(p->ctx);
 	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_copy));
+	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_ingest));
 	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_main));
 	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_out));
 	pthread_mutex_lock(&p->mu);
@@ -433,14 +449,15 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	cudaSetDevice(p->ctx->device);
 	tsdrgpu_resampler_destroy(p->rs); tsdrgpu_framestage_destroy(p->fs); tsdrgpu_frd_destroy(p->frd);
 	for (void *h : p->registered) cudaHostUnregister(h);
-	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture};
+	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_stage[2], p->d_stage[3], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture[0], p->d_capture[1]};
 	for (float *d : dev) if (d) cudaFree(d);
 	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
 	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
 	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
 	for (int i = 0; i < 2; i++) cudaEventDestroy(p->ev_out[i]);
 	cudaEventDestroy(p->ev_main);
-	for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_h2d[i]); cudaEventDestroy(p->ev_used[i]); }
+	for (int i = 0; i < 4; i++) { cudaEventDestroy(p->ev_h2d[i]); cudaEventDestroy(p->ev_used[i]); }
+	cudaEventDestroy(p->ev_ingest); cudaEventDestroy(p->ev_decim); cudaEventDestroy(p->ev_cap_used[0]); cudaEventDestroy(p->ev_cap_used[1]); cudaStreamDestroy(p->s_ingest);
 	pthread_mutex_destroy(&p->mu); pthread_mutex_destroy(&p->geo_mu); pthread_cond_destroy(&p->cv_job); pthread_cond_destroy(&p->cv_done);
 	delete p;
 }
@@ -507,31 +524,37 @@ int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t 
 	float *stage = NULL;
 	if (need_data) {
 		ARG_TRY(ctx, h_iq != NULL);
-		p->stage_slot ^= 1;
+		p->stage_slot = (p->stage_slot + 1) & 3;
+		if (p->stage_cap[ss] < items_count) { CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest)); CU_TRY(ctx, cudaStreamSynchronize(p->s_copy)); }
 		if ((rc = grow(ctx, p->s_main, &p->d_stage[ss], &p->stage_cap[ss], items_count, 0))) return rc;
 		stage = p->d_stage[ss];
-		// the plugin's buffer is only valid during this call: copy it on the copy stream (after the kernels that
-		// read this staging slot two calls ago), let the main stream wait for the copy, and return once the
-		// host buffer has been read.  With two slots the copy of block k+1 overlaps the kernels of block k.
+		// The plugin's buffer is only valid during this call: copy it on the copy stream into one of four staging slots
+		// (after the ingest kernels that read the slot four calls ago) and return once the host buffer has been read.
+		// The light per-block kernels (capture demod, append to the decimator input) run on their own stream, so the
+		// copy of block k+1..k+3 never waits behind the heavy resample / frame / FFT kernels of earlier blocks.
 		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->ev_used[ss], 0));
 		CU_TRY(ctx, cudaMemcpyAsync(stage, h_iq, sizeof(float) * items_count, cudaMemcpyHostToDevice, p->s_copy));
 		CU_TRY(ctx, cudaEventRecord(p->ev_h2d[ss], p->s_copy));
-		CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_h2d[ss], 0));
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_ingest, p->ev_h2d[ss], 0));
 		p->stats.h2d_bytes += sizeof(float) * items_count;
 		if ((rc = feed_capture(p, stage, size2, samples_dropped != 0))) return rc;
 	} else if (plots_on && samples_dropped != 0) p->cap_fill = 0;
 	uint32_t skip = 0;
 	const uint32_t fwd = p->dev_drop.add((uint32_t) size2, (uint32_t) block, true, &skip);
 	if (fwd) {
+		if (p->decim_cap < 2 * (p->decim_fill + fwd)) { CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest)); }
 		if ((rc = grow(ctx, p->s_main, &p->d_decim, &p->decim_cap, 2 * (p->decim_fill + fwd), 2 * p->decim_fill))) return rc;
-		pl_copy_f32<<<(unsigned) ((2ull * fwd + 255) / 256 < 2048 ? (2ull * fwd + 255) / 256 : 2048), 256, 0, p->s_main>>>(stage + 2ull * skip, p->d_decim + 2 * p->decim_fill, 2ull * fwd);
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_ingest, p->ev_decim, 0));       // the last compaction of the decimator input is done
+		pl_copy_f32<<<(unsigned) ((2ull * fwd + 255) / 256 < 2048 ? (2ull * fwd + 255) / 256 : 2048), 256, 0, p->s_ingest>>>(stage + 2ull * skip, p->d_decim + 2 * p->decim_fill, 2ull * fwd);
 		LAUNCH_CHECK(ctx);
 		p->decim_fill += fwd;
 	}
 	if (need_data) {
-		CU_TRY(ctx, cudaEventRecord(p->ev_used[ss], p->s_main));           // the slot may be overwritten after this point
+		CU_TRY(ctx, cudaEventRecord(p->ev_used[ss], p->s_ingest));         // the slot may be overwritten after this point
 		CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));                     // the host buffer has been read
 	}
+	CU_TRY(ctx, cudaEventRecord(p->ev_ingest, p->s_ingest));
+	CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_ingest, 0));          // the resampler may read what was appended
 	return drain_blocks(p);
 }
 

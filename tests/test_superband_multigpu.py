@@ -1,0 +1,56 @@
+"""Multi-GPU superbandwidth stitch (one hop per GPU, one NCCL all-gather): needs >= 2 GPUs, skipped otherwise.
+Run with:  gpurun --gpus 2 -- python -m pytest tests/test_superband_multigpu.py -m gpu -q"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import oracle as orc
+    from tempestsdr_b200 import api, superband, synth
+    fs, fv = 400_000, 50.0
+    sif = int(fs / fv)
+    pairs = 10 * sif
+    base = synth.video_like_iq(pairs + 5000, fs, 200, 160, fv, seed=9, snr_db=25)
+    lags_true = (0, 1234, 77, 3999, 55, 640, 2222, 9)[:world]
+    hops = [base[2 * l: 2 * (l + pairs)].copy() + synth.noise_iq(pairs, seed=100 + i, scale=0.01) for i, l in enumerate(lags_true)]
+    ctx = api.Context(rank)
+    res, lags, n = superband.stitch_distributed(ctx, torch.from_numpy(hops[rank]).cuda(), sif)
+    ok, msg = True, ""
+    if world in (2, 4):      # the reference stitches `world` hops into a world*N-point inverse (needs a power of two)
+        want, offs = orc.best().superb_ondataready(hops, sif)
+        ok = [2 * l for l in lags] == list(offs)
+        got = res.cpu().numpy().reshape(-1, 2)
+        ref = want.reshape(-1, 2)[rank::world]
+        err = float(np.max(np.abs(got - ref)) / np.max(np.abs(want)))
+        ok = ok and err <= 8e-6          # tolerance 8e-6 of the peak (float FFT, see test_gpu_parity)
+        msg = f"err={err:.3g} lags={lags} offs={list(offs)}"
+    q.put((rank, ok, msg))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_one_hop_per_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29741 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+    assert all(ok for _, ok, _ in results), results
