@@ -124,7 +124,7 @@ __device__ __forceinline__ void stockham_stage(float2 *s, int LP, int C, int p, 
 }
 
 template <int LOG2L>
-__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
+__global__ void __launch_bounds__(512, 3) fft_pass_small(const float2 *in, float2 *out, FftPass P,
                                                         const float2 *__restrict__ table, int inverse_) {
 	extern __shared__ float2 s[];
 	constexpr int L = 1 << LOG2L;
@@ -173,6 +173,125 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 		v.x *= P.scale; v.y *= P.scale;
 		if (P.out_abs) v = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))), 0.0f);
 		out[out_base + (long long) c * P.out_cs + (long long) k * P.out_ks] = v;
+	}
+}
+
+// ---- the pass kernel for lines of length L >= 8 --------------------------------------------------------------------
+// Each thread owns 8 points per stage.  The first radix-8 butterfly is fed straight from global memory and the last
+// butterfly (radix 8, 4 or 2) stores straight to global memory (through the inter-pass twiddle / scale / |.| epilogue),
+// so a 1024-point line makes 3 trips through shared memory instead of 5 + load + store, with one barrier each
+// (ping-pong buffers).  Thread -> (line, butterfly) maps are chosen per pass so that the global accesses of a warp are
+// runs of consecutive complex values: line-fastest on strided passes, butterfly-fastest on contiguous lines.
+template <int R>
+__device__ __forceinline__ void apply_stage_twiddles(float2 *v, unsigned tq, const float2 *__restrict__ table, bool inverse) {
+	#pragma unroll
+	for (int m = 1; m < R; m++) v[m] = cmul(v[m], tw_lookup(table, m * tq, inverse));
+}
+
+template <int LOG2L>
+__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
+                                                          const float2 *__restrict__ table, int inverse_) {
+	extern __shared__ float2 s[];
+	constexpr int L = 1 << LOG2L, NST8 = LOG2L / 3, RL = LOG2L % 3;
+	constexpr int RLAST = (RL == 0) ? 8 : ((RL == 1) ? 2 : 4);
+	constexpr int NSTAGES = NST8 + (RL ? 1 : 0);
+	constexpr int NMID = NSTAGES - 2;                    // radix-8 stages between the first and the last one
+	constexpr int L8 = L / 8, LOG2L8 = LOG2L - 3;
+	const bool inverse = inverse_ != 0;
+	const int C = P.C, log2C = P.log2C, LP = padq(L) + 1;
+	const int tid = threadIdx.x;
+	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g - g_hi * P.G_lo;
+	const float2 *gin = in + ((long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs);
+	const float *gin_real = reinterpret_cast<const float *>(in) + ((long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs);
+	float2 *gout = out + ((long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo + (long long) blockIdx.y * P.out_bs);
+	const bool active = tid < C * L8;                    // tiny bundles leave part of the last warp idle
+	float2 v[8];
+
+	// ---- stage 0: radix 8, p = 1 (all twiddles are 1), inputs x[i + m L/8] from global memory
+	{
+		int c, i;
+		if (P.c_fast_in) { c = tid & (C - 1); i = tid >> log2C; } else { i = tid & (L8 - 1); c = tid >> LOG2L8; }
+		if (active) {
+			const int off = c * (int) P.in_cs + i * (int) P.in_js, step = L8 * (int) P.in_js;
+			if (P.in_real) {
+				#pragma unroll
+				for (int m = 0; m < 8; m++) v[m] = make_float2(__ldg(gin_real + off + m * step), 0.0f);
+			} else {
+				#pragma unroll
+				for (int m = 0; m < 8; m++) v[m] = __ldg(gin + off + m * step);
+			}
+			float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
+			dft8(u, inverse);
+		}
+		if (NSTAGES > 1) {
+			if (active) {
+				float2 *line = s + c * LP;
+				#pragma unroll
+				for (int m = 0; m < 8; m++) line[padq(8 * i + m)] = v[m];
+			}
+			__syncthreads();
+		}
+	}
+	float2 *src = s, *dst = s + C * LP;
+	int p = 8;
+	// ---- middle radix-8 stages (shared -> shared, ping-pong)
+	#pragma unroll
+	for (int st = 0; st < (NMID > 0 ? NMID : 0); st++) {
+		const int i = tid & (L8 - 1), c = tid >> LOG2L8;
+		if (active) {
+			const float2 *line = src + c * LP;
+			#pragma unroll
+			for (int m = 0; m < 8; m++) v[m] = line[padq(i + m * L8)];
+			const int k = i & (p - 1);
+			if (k) apply_stage_twiddles<8>(v, (unsigned) k * (unsigned) (FFT_TABLE / (8 * p)), table, inverse);
+			float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
+			dft8(u, inverse);
+			float2 *lo = dst + c * LP;
+			const int j = ((i - k) << 3) + k;
+			#pragma unroll
+			for (int m = 0; m < 8; m++) lo[padq(j + m * p)] = v[m];
+		}
+		__syncthreads();
+		float2 *t = src; src = dst; dst = t;
+		p <<= 3;
+	}
+	// ---- last stage: radix RLAST with p = L / RLAST, results X[i + m p] go to global memory
+	constexpr int NB = 8 / RLAST, PL = L / RLAST, LOG2PL = LOG2L - (RLAST == 8 ? 3 : (RLAST == 4 ? 2 : 1));
+	const int T = blockDim.x;
+	#pragma unroll
+	for (int it = 0; it < NB; it++) {
+		const int widx = tid + it * T;
+		if (widx >= C * PL) continue;
+		int c, i;
+		if (P.c_fast_out) { c = widx & (C - 1); i = widx >> log2C; } else { i = widx & (PL - 1); c = widx >> LOG2PL; }
+		float2 *w = v + it * RLAST;
+		if (NSTAGES > 1) {
+			const float2 *line = src + c * LP;
+			#pragma unroll
+			for (int m = 0; m < RLAST; m++) w[m] = line[padq(i + m * PL)];
+			if (i) apply_stage_twiddles<RLAST>(w, (unsigned) i * (unsigned) (FFT_TABLE / L), table, inverse);
+			if (RLAST == 8) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&w[0]); dft8(u, inverse); }
+			else if (RLAST == 4) dft4(w[0], w[1], w[2], w[3], inverse);
+			else dft2(w[0], w[1]);
+		}
+		const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
+		float2 *o = gout + c * (int) P.out_cs;
+		#pragma unroll
+		for (int m = 0; m < RLAST; m++) {
+			const int k = i + m * PL;
+			float2 x = w[m];
+			if (P.tw_M) {
+				const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
+				float2 tw;
+				if (P.tw_M <= (1ull << 24)) { float sn, cs; sincospif(-2.0f * ((float) e / (float) P.tw_M), &sn, &cs); tw = make_float2(cs, sn); }   // exact argument
+				else { double dsn, dcs; sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); tw = make_float2((float) dcs, (float) dsn); }
+				if (inverse) tw.y = -tw.y;
+				x = cmul(x, tw);
+			}
+			x.x *= P.scale; x.y *= P.scale;
+			if (P.out_abs) x = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y))), 0.0f);
+			o[(long long) k * P.out_ks] = x;
+		}
 	}
 }
 
@@ -355,9 +474,9 @@ int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	LAUNCH_CHECK(ctx);
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
 	g_table[ctx->device] = t;
-	const int max_smem = (int) (sizeof(float2) * (FFT_MAX_ELEMS + FFT_MAX_ELEMS / 16 + 64));
+	const int max_smem = (int) (2 * sizeof(float2) * (FFT_MAX_ELEMS + FFT_MAX_ELEMS / 16 + 64));     // ping-pong
 #define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
-	SET_ATTR(1); SET_ATTR(2); SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
+	SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
 #undef SET_ATTR
 	return TSDRGPU_OK;
 }
@@ -382,12 +501,15 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	if (threads < 32) threads = 32;
 	if (threads > 512) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT bundle too large", cudaSuccess, __FILE__, __LINE__);
 	const int LP = L + (L >> 4) + 1;
-	const size_t smem = sizeof(float2) * (size_t) P.C * LP;
+	const int nstages = P.log2L / 3 + ((P.log2L % 3) ? 1 : 0);
+	const size_t smem = sizeof(float2) * (size_t) P.C * LP * (P.log2L >= 3 ? (nstages >= 3 ? 2 : 1) : 1);
 	const dim3 grid(bundles, batch);
 	const float2 *tab = g_table[ctx->device];
 	switch (P.log2L) {
+	case 1: KL(ctx, "fft_pass_kernel", stream, fft_pass_small<1><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break;
+	case 2: KL(ctx, "fft_pass_kernel", stream, fft_pass_small<2><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break;
 #define CASE(l) case l: KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break
-	CASE(1); CASE(2); CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
+	CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
 #undef CASE
 	default: return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "unsupported FFT line length", cudaSuccess, __FILE__, __LINE__);
 	}

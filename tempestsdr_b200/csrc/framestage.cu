@@ -51,6 +51,21 @@ __global__ void __launch_bounds__(256) fs_minmax(const float *__restrict__ in, s
 	const float *src = in + (size_t) f * n;
 	float lo = INFINITY, hi = -INFINITY;
 	double sum = 0.0;
+	if (((n & 3) == 0) && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {      // 16-byte loads
+		const float4 *src4 = reinterpret_cast<const float4 *>(src);
+		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (size_t) gridDim.x * blockDim.x) {
+			const float4 q = __ldg(src4 + i);
+			const float vv[4] = {q.x, q.y, q.z, q.w};
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const float v = vv[u];
+				if (px_is_marker(v)) continue;
+				hi = (v > hi) ? v : hi;
+				lo = (v < lo) ? v : lo;
+				if (SNR) sum += (double) v;
+			}
+		}
+	} else
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
 		const float v = __ldg(src + i);
 		if (px_is_marker(v)) continue;
@@ -176,6 +191,30 @@ __global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__
 	extern __shared__ float2 s_par[];                    // (lastmin, span) per frame
 	for (int f = threadIdx.x; f < nframes; f += blockDim.x) s_par[f] = make_float2(params[f].lastmin, params[f].span);
 	__syncthreads();
+	const bool vec = ((n & 3) == 0) && (((reinterpret_cast<unsigned long long>(in) | reinterpret_cast<unsigned long long>(out) |
+	                                       reinterpret_cast<unsigned long long>(screen)) & 15ull) == 0);
+	if (vec) {                                           // 4 pixels per thread, 16-byte loads and stores
+		const size_t n4 = n >> 2;
+		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) {
+			float4 sc = reinterpret_cast<float4 *>(screen)[i];
+			float s4[4] = {sc.x, sc.y, sc.z, sc.w};
+			#pragma unroll 2
+			for (int f = 0; f < nframes; f++) {
+				const float4 q = __ldg(reinterpret_cast<const float4 *>(in + (size_t) f * n) + i);
+				const float raw[4] = {q.x, q.y, q.z, q.w};
+				const float2 p = s_par[f];
+				#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const float v = px_is_marker(raw[u]) ? raw[u] : __fdiv_rn(__fsub_rn(raw[u], p.x), p.y);
+					const float old = __fmul_rn(s4[u], coeff);
+					s4[u] = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
+				}
+				reinterpret_cast<float4 *>(out + (size_t) f * n)[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+			}
+			reinterpret_cast<float4 *>(screen)[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
+		}
+		return;
+	}
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
 		float s = screen[i];
 		#pragma unroll 4

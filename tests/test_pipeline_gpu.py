@@ -84,6 +84,10 @@ def test_pipeline_drop_resync_and_manual_sync():
     fed = []
     for k, b in enumerate(blocks):
         d = dropped if k == 7 else 0
+        if k == 15:      # an EMPTY block that only reports a loss (TSDRPlugin_UHD.cpp:294 does this)
+            diff = O.dropcomp_shift_with(diff, block, 777)
+            diff, fwd, skip = O.dropcomp_add(diff, 0, block, True)
+            p.process(np.zeros(0, np.float32), 777)
         # oracle bookkeeping for what the decimator receives
         diff = O.dropcomp_shift_with(diff, block, d)
         diff, fwd, skip = O.dropcomp_add(diff, items // 2, block, True)
