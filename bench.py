@@ -284,6 +284,26 @@ def run_ours(args):
             pl.process_ptr(base_ptr + 4 * pos, n, 0)
             pos += n
 
+    # the link under the e2e number: pinned H2D and D2H of one step's bytes, alone and together (context, not a claim)
+    def link_gbs():
+        d_in = torch.empty_like(iq_dev); h_out = torch.empty(FRAMES_PER_STEP * step.n, dtype=torch.float32).pin_memory()
+        d_out = step.frames_out[0]
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        res = {}
+        for name, both in (("h2d", (True, False)), ("d2h", (False, True)), ("duplex", (True, True))):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(3):
+                if both[0]:
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(iq_pinned, non_blocking=True)
+                if both[1]:
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+            nbytes = (iq_pinned.numel() * 4 if both[0] else 0) + (h_out.numel() * 4 if both[1] else 0)
+            res[name + "_gbs"] = nbytes / dt / 1e9
+        return res
+    link = link_gbs()
     e2e_steps = max(2, min(args.steps, 6))
     feed_once(); pl.flush()
     barrier()
@@ -371,7 +391,8 @@ def run_ours(args):
                    "flags": "AUTOSHIFT=1, LOW_PASS_BEFORE_SYNC=1, AUTOGAIN_AFTER=0, motionblur 0 (GUI defaults), PLL write-back off"},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "frames_delivered": int(e2e_frames), "how": "tsdrgpu_pipeline_process() on pinned host IQ in 16 MiB calls, "
+                "steps": e2e_steps, "frames_delivered": int(e2e_frames), "pcie_link_measured": link,
+                "link_bound_MS_per_s": min(link["h2d_gbs"] / 8.0, link["d2h_gbs"] / (4.0 * step.n * FRAMES_PER_STEP / pairs)) * 1e3, "how": "tsdrgpu_pipeline_process() on pinned host IQ in 16 MiB calls, "
                 "frames copied back to pinned host slots; host wall clock between device synchronisations"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }

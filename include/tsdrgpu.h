@@ -85,6 +85,9 @@ typedef struct {
  * the reference asserts there, extbuffer.c:48).  `blocks` may be NULL (count only). */
 TSDRGPU_API uint64_t tsdrgpu_plan_resample(double *offset, const uint32_t *sizes, uint32_t uniform, uint32_t nblocks,
                                            double upsample_by, double downsample_by, tsdrgpu_rs_block_t *blocks);
+/* relative angle errors eps[l] of the reference FFT's stage twiddles (half-angle recurrence, fft.c:132-165): stage l
+ * rotates by (pi/2^l)(1+eps[l]) instead of pi/2^l.  Used by tsdrgpu_fft to track the reference at large N. */
+TSDRGPU_API void tsdrgpu_fft_reference_eps(int stages, int inverse, double *eps);
 /* the normalised 5-tap Gaussian of gaussian.c:16-30 */
 TSDRGPU_API void tsdrgpu_gauss_taps(float taps[5]);
 

@@ -62,6 +62,7 @@ _SIGS = {
     "tsdrgpu_stream_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_geometry": (None, [C.c_uint32, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tsdrgpu_plan_resample": (C.c_uint64, [C.POINTER(C.c_double), C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_void_p]),
+    "tsdrgpu_fft_reference_eps": (None, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "tsdrgpu_gauss_taps": (None, [C.POINTER(C.c_float * 5)]),
     "tsdrgpu_am_demod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tsdrgpu_resampler_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -36,6 +36,8 @@ struct FftPass {
 	long long out_hi, out_lo, out_cs, out_ks;
 	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
 	const float2 *tab_lo, *tab_hi;                      // W_M^e = tab_lo[e & 4095] * tab_hi[e >> 12]  (forward sign)
+	float eps[12];                                      // reference-compatible mode: relative angle error of sub-stage s of this line FFT
+	int pert;                                           // non-zero: use the perturbed-angle butterflies
 	float scale;
 	int in_real, out_abs;
 };
@@ -182,6 +184,58 @@ __global__ void __launch_bounds__(512, 3) fft_pass_small(const float2 *in, float
 // so a 1024-point line makes 3 trips through shared memory instead of 5 + load + store, with one barrier each
 // (ping-pong buffers).  Thread -> (line, butterfly) maps are chosen per pass so that the global accesses of a warp are
 // runs of consecutive complex values: line-fastest on strided passes, butterfly-fastest on contiguous lines.
+// ---- reference-compatible ("perturbed-angle") butterflies ------------------------------------------------------------
+// The reference's stage l rotates by (pi/2^l)(1+eps_l) (see tsdrgpu_fft_reference_eps).  A radix-8 Stockham step with
+// block size p is three radix-2 layers with blocks p, 2p, 4p; written out, layer t multiplies the upper input by
+// e^{-+ i theta_t K}, K = k + p q0 (+ 2p q1): the exact twiddle from the table times a small extra rotation
+// -+ eps_t * pi * K / block_t.  With all eps = 0 this is the ordinary DFT-8 with input twiddles.
+__device__ __forceinline__ float2 pert_tw(const float2 *__restrict__ table, unsigned idx, float phi, bool inverse) {
+	const float2 w = tw_lookup(table, idx, inverse);
+	return cmul(w, make_float2(1.0f - 0.5f * phi * phi, inverse ? phi : -phi));
+}
+#define PI_F 3.14159265358979323846f
+__device__ __forceinline__ void dft8_pert(float2 *v, int k, int p, float e0, float e1, float e2, const float2 *__restrict__ table, bool inverse) {
+	float2 a[4][2], b[2][2][2];
+	const float2 TA = pert_tw(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), e0 * PI_F * (float) k / (float) p, inverse);
+	#pragma unroll
+	for (int r = 0; r < 4; r++) { const float2 hi = cmul(TA, v[r + 4]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
+	#pragma unroll
+	for (int q0 = 0; q0 < 2; q0++) {
+		const int K = k + p * q0;
+		const float2 TB = pert_tw(table, (unsigned) K * (unsigned) (FFT_TABLE / (4 * p)), e1 * PI_F * (float) K / (float) (2 * p), inverse);
+		#pragma unroll
+		for (int m0 = 0; m0 < 2; m0++) { const float2 hi = cmul(TB, a[m0 + 2][q0]); b[m0][q0][0] = cadd(a[m0][q0], hi); b[m0][q0][1] = csub(a[m0][q0], hi); }
+	}
+	#pragma unroll
+	for (int q0 = 0; q0 < 2; q0++) {
+		#pragma unroll
+		for (int q1 = 0; q1 < 2; q1++) {
+			const int K = k + p * q0 + 2 * p * q1;
+			const float2 TC = pert_tw(table, (unsigned) K * (unsigned) (FFT_TABLE / (8 * p)), e2 * PI_F * (float) K / (float) (4 * p), inverse);
+			const float2 hi = cmul(TC, b[1][q0][q1]);
+			v[q0 + 2 * q1] = cadd(b[0][q0][q1], hi); v[q0 + 2 * q1 + 4] = csub(b[0][q0][q1], hi);
+		}
+	}
+}
+__device__ __forceinline__ void dft4_pert(float2 *v, int k, int p, float e0, float e1, const float2 *__restrict__ table, bool inverse) {
+	float2 a[2][2];
+	const float2 TA = pert_tw(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), e0 * PI_F * (float) k / (float) p, inverse);
+	#pragma unroll
+	for (int r = 0; r < 2; r++) { const float2 hi = cmul(TA, v[r + 2]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
+	#pragma unroll
+	for (int q0 = 0; q0 < 2; q0++) {
+		const int K = k + p * q0;
+		const float2 TB = pert_tw(table, (unsigned) K * (unsigned) (FFT_TABLE / (4 * p)), e1 * PI_F * (float) K / (float) (2 * p), inverse);
+		const float2 hi = cmul(TB, a[1][q0]);
+		v[q0] = cadd(a[0][q0], hi); v[q0 + 2] = csub(a[0][q0], hi);
+	}
+}
+__device__ __forceinline__ void dft2_pert(float2 *v, int k, int p, float e0, const float2 *__restrict__ table, bool inverse) {
+	const float2 hi = cmul(pert_tw(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), e0 * PI_F * (float) k / (float) p, inverse), v[1]);
+	const float2 lo = v[0];
+	v[0] = cadd(lo, hi); v[1] = csub(lo, hi);
+}
+
 template <int R>
 __device__ __forceinline__ void apply_stage_twiddles(float2 *v, unsigned tq, const float2 *__restrict__ table, bool inverse) {
 	#pragma unroll
@@ -220,8 +274,8 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 				#pragma unroll
 				for (int m = 0; m < 8; m++) v[m] = __ldg(gin + off + m * step);
 			}
-			float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
-			dft8(u, inverse);
+			if (P.pert) dft8_pert(v, 0, 1, P.eps[0], P.eps[1], P.eps[2], table, inverse);
+			else { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]); dft8(u, inverse); }
 		}
 		if (NSTAGES > 1) {
 			if (active) {
@@ -243,9 +297,12 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 			#pragma unroll
 			for (int m = 0; m < 8; m++) v[m] = line[padq(i + m * L8)];
 			const int k = i & (p - 1);
-			if (k) apply_stage_twiddles<8>(v, (unsigned) k * (unsigned) (FFT_TABLE / (8 * p)), table, inverse);
-			float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
-			dft8(u, inverse);
+			if (P.pert) dft8_pert(v, k, p, P.eps[3 * st + 3], P.eps[3 * st + 4], P.eps[3 * st + 5], table, inverse);
+			else {
+				if (k) apply_stage_twiddles<8>(v, (unsigned) k * (unsigned) (FFT_TABLE / (8 * p)), table, inverse);
+				float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
+				dft8(u, inverse);
+			}
 			float2 *lo = dst + c * LP;
 			const int j = ((i - k) << 3) + k;
 			#pragma unroll
@@ -269,10 +326,17 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 			const float2 *line = src + c * LP;
 			#pragma unroll
 			for (int m = 0; m < RLAST; m++) w[m] = line[padq(i + m * PL)];
-			if (i) apply_stage_twiddles<RLAST>(w, (unsigned) i * (unsigned) (FFT_TABLE / L), table, inverse);
-			if (RLAST == 8) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&w[0]); dft8(u, inverse); }
-			else if (RLAST == 4) dft4(w[0], w[1], w[2], w[3], inverse);
-			else dft2(w[0], w[1]);
+			if (P.pert) {
+				constexpr int S0 = LOG2L - (RLAST == 8 ? 3 : (RLAST == 4 ? 2 : 1));      // first sub-stage of this butterfly
+				if (RLAST == 8) dft8_pert(w, i, PL, P.eps[S0], P.eps[S0 + 1], P.eps[S0 + 2], table, inverse);
+				else if (RLAST == 4) dft4_pert(w, i, PL, P.eps[S0], P.eps[S0 + 1], table, inverse);
+				else dft2_pert(w, i, PL, P.eps[S0], table, inverse);
+			} else {
+				if (i) apply_stage_twiddles<RLAST>(w, (unsigned) i * (unsigned) (FFT_TABLE / L), table, inverse);
+				if (RLAST == 8) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&w[0]); dft8(u, inverse); }
+				else if (RLAST == 4) dft4(w[0], w[1], w[2], w[3], inverse);
+				else dft2(w[0], w[1]);
+			}
 		}
 		const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
 		float2 *o = gout + c * (int) P.out_cs;
@@ -490,9 +554,20 @@ int bundle_for(int log2L, unsigned long long lines) {
 }
 
 int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, FftPass P, unsigned bundles, int inverse,
-                unsigned batch, long long in_bs, long long out_bs) {
+                unsigned batch, long long in_bs, long long out_bs, const double *eps_all = NULL, int l_base = 0) {
 	P.in_bs = in_bs; P.out_bs = out_bs;
 	P.tab_lo = P.tab_hi = NULL;
+	{   // reference-compatible stage angles (default): sub-stage s of this pass is the reference's stage l_base + s
+		static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;      // opt out: the mathematically exact DFT
+		P.pert = 0;
+		for (int s = 0; s < 12; s++) P.eps[s] = 0.0f;
+		if (!exact_dft && eps_all) {
+			for (int s = 0; s < P.log2L && l_base + s < 40; s++) {
+				P.eps[s] = (float) eps_all[l_base + s];
+				if (fabs(eps_all[l_base + s]) > 2e-9) P.pert = 1;
+			}
+		}
+	}
 	static const bool use_tables = getenv("TSDRGPU_FFT_TWIDDLE_TABLES") != NULL;
 	if (P.tw_M && use_tables) { int rc = tw_tables(ctx, stream, P.tw_M, &P.tab_lo, &P.tab_hi); if (rc) return rc; }
 	P.log2C = 0; while ((1 << P.log2C) < P.C) P.log2C++;
@@ -528,11 +603,13 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 	const unsigned long long N = 1ull << log2N;
 	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : data;
 	const long long in0_bs = o.real_in ? o.real_bs : o.data_bs;
+	double eps_all[40];
+	tsdrgpu_fft_reference_eps((int) log2N < 40 ? (int) log2N : 40, inverse, eps_all);
 	FftPass P; memset(&P, 0, sizeof P);
 	if (log2N <= FFT_MAX_LOG2L) {                       // one pass, one CTA
 		P.log2L = (int) log2N; P.C = 1; P.G_lo = 1; P.in_js = 1; P.out_ks = 1; P.scale = o.scale;
 		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs;
-		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs);
+		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs, eps_all, 0);
 	}
 	int rc;
 	if (log2N <= 20) {                                  // N = N1 * N2 (lines <= 1024) ; n = N2*n1 + n2 ; k = k1 + N1*k2
@@ -543,14 +620,14 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N2;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N2;
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
-		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs))) return rc;
+		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 		FftPass Q; memset(&Q, 0, sizeof Q);
 		Q.log2L = (int) l2; Q.C = bundle_for((int) l2, N1); Q.c_fast_in = 0; Q.c_fast_out = 1;
 		Q.G_lo = (unsigned) (N1 / Q.C);
 		Q.in_lo = (long long) Q.C * (long long) N2; Q.in_cs = (long long) N2; Q.in_js = 1;
 		Q.out_lo = Q.C; Q.out_cs = 1; Q.out_ks = (long long) N1;
 		Q.scale = o.scale; Q.out_abs = o.out_abs;
-		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse, o.batch, o.scratch_bs, o.data_bs);
+		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse, o.batch, o.scratch_bs, o.data_bs, eps_all, (int) l1);
 	}
 	// N = N1*N2*N3 ; n = N2N3 n1 + N3 n2 + n3 ; k = k1 + N1 k2 + N1N2 k3
 	const unsigned l1 = (log2N + 2) / 3, l2 = (log2N - l1 + 1) / 2, l3 = log2N - l1 - l2;
@@ -562,7 +639,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N23;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N23;
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
-		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs))) return rc;
+		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 	}
 	{   // pass B: for every k1, length N2 along stride N3, bundle over adjacent n3 (in place in scratch)
 		FftPass B; memset(&B, 0, sizeof B);
@@ -571,7 +648,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		B.in_hi = (long long) N23; B.in_lo = B.C; B.in_cs = 1; B.in_js = (long long) N3;
 		B.out_hi = (long long) N23; B.out_lo = B.C; B.out_cs = 1; B.out_ks = (long long) N3;
 		B.tw_M = N23; B.tw_lo = B.C; B.tw_cs = 1; B.scale = 1.0f;
-		if ((rc = launch_pass(ctx, stream, scratch, scratch, B, (unsigned) (N1 * B.G_lo), inverse, o.batch, o.scratch_bs, o.scratch_bs))) return rc;
+		if ((rc = launch_pass(ctx, stream, scratch, scratch, B, (unsigned) (N1 * B.G_lo), inverse, o.batch, o.scratch_bs, o.scratch_bs, eps_all, (int) l1))) return rc;
 	}
 	{   // pass C: contiguous lines of N3 at (k1,k2); bundle over adjacent k1; output k1 + N1 k2 + N1N2 k3
 		FftPass Cc; memset(&Cc, 0, sizeof Cc);
@@ -580,7 +657,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		Cc.in_hi = (long long) N3; Cc.in_lo = (long long) Cc.C * (long long) N23; Cc.in_cs = (long long) N23; Cc.in_js = 1;
 		Cc.out_hi = (long long) N1; Cc.out_lo = Cc.C; Cc.out_cs = 1; Cc.out_ks = (long long) (N1 * N2);
 		Cc.scale = o.scale; Cc.out_abs = o.out_abs;
-		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse, o.batch, o.scratch_bs, o.data_bs);
+		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse, o.batch, o.scratch_bs, o.data_bs, eps_all, (int) (l1 + l2));
 	}
 }
 

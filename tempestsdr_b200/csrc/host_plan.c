@@ -43,3 +43,24 @@ void tsdrgpu_gauss_taps(float taps[5]) {
 	const float norm = e2 + e1 + e0 + e1 + e2;
 	taps[0] = e2 / norm; taps[1] = e1 / norm; taps[2] = e0 / norm; taps[3] = e1 / norm; taps[4] = e2 / norm;
 }
+
+/* Stage-angle errors of the reference's FFT.  fft_perform (fft.c:132-165) derives the stage twiddle c_l = (c1, c2)
+ * by the half-angle recurrence c2 = sqrt((1-c1)/2), c1 = sqrt((1+c1)/2), which cancels catastrophically for small
+ * angles: the angle of c_l is (pi / 2^l) * (1 + eps[l]) with |eps| growing to ~1e-6 at l = 20 and ~1e-4 at l = 23.
+ * Replaying the recurrence with the same double arithmetic gives eps exactly; the CUDA FFT can then use the same
+ * (wrong) angles so that its results track the reference's instead of the true DFT.  eps[0] = eps[1] = 0. */
+void tsdrgpu_fft_reference_eps(int stages, int inverse, double *eps) {
+	double c1 = -1.0, c2 = 0.0;
+	for (int l = 0; l < stages; l++) {
+		if (l == 0) eps[l] = 0.0;                      /* c = (-1, 0): only k = 0 is ever used */
+		else {
+			const long double ideal = 3.14159265358979323846264338327950288L / (long double) (1ull << l);
+			const long double got = atan2l(fabsl((long double) c2), (long double) c1);
+			eps[l] = (double) (got / ideal - 1.0L);
+		}
+		double n2 = sqrt((1.0 - c1) / 2.0);
+		if (!inverse) n2 = -n2;
+		const double n1 = sqrt((1.0 + c1) / 2.0);
+		c1 = n1; c2 = n2;
+	}
+}
