@@ -262,6 +262,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     # ---- per-kernel timing pass (separate from the timed region above): CUDA events on the launching stream
+    # The side stream is switched off for this pass so that every kernel's event pair measures that kernel alone
+    # (with it on, intervals on the main stream also contain the slowdown from sharing the chip with the sync search).
+    step.join(); torch.cuda.synchronize()
+    step.pp.set_overlap(False)
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
     collect_profile(gpu)
     prof_steps = 3
@@ -269,6 +273,7 @@ def run_ours(args):
         step()
     prof = collect_profile(gpu)
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
+    step.pp.set_overlap(not os.environ.get("BENCH_NO_OVERLAP"))
 
     # ---- e2e through the C-ABI pipeline with host buffers
     chunk = 512 * 1024 * 8                     # floats per process() call (8x the RawFile plugin's block)

@@ -288,12 +288,13 @@ typedef struct {
 typedef struct {
 	uint64_t samples_in, samples_dropped_upstream, samples_resampled;
 	uint64_t frames_processed, frames_delivered, frames_dropped, captures, plots_delivered;
-	uint64_t h2d_bytes, d2h_bytes, gpu_launches;
+	uint64_t h2d_bytes, d2h_bytes, gpu_launches, stitches;
 } tsdrgpu_pipeline_stats_t;
 
 typedef void (*tsdrgpu_frame_cb)(float *buf, int width, int height, void *user);                  /* tsdr_readasync_function */
 typedef void (*tsdrgpu_value_cb)(int value_id, double arg0, double arg1, void *user);             /* tsdr_value_changed_callback */
 typedef void (*tsdrgpu_plot_cb)(int plot_id, int offset, double *values, int size, uint32_t samplerate, void *user);
+typedef void (*tsdrgpu_retune_cb)(int32_t offset_hz, void *user);        /* shiftfreq (TSDRLibrary.c:208): tune to centre + offset */
 
 TSDRGPU_API int  tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t *cfg, tsdrgpu_frame_cb frame_cb,
                                          tsdrgpu_value_cb value_cb, tsdrgpu_plot_cb plot_cb, void *user, tsdrgpu_pipeline_t **p);
@@ -304,6 +305,9 @@ TSDRGPU_API int  tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p);            /* wa
 TSDRGPU_API int  tsdrgpu_pipeline_set_param_int(tsdrgpu_pipeline_t *p, int id, uint32_t value);
 TSDRGPU_API int  tsdrgpu_pipeline_set_resolution(tsdrgpu_pipeline_t *p, int height, double refreshrate);
 TSDRGPU_API int  tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate);
+/* superbandwidth mode (PARAM_AUTOCORR_SUPERRESOLUTION = 1; superb_run, superbandwidth.c:179-254) retunes the front end
+ * between hops through this callback; without it the hops are recorded at one frequency */
+TSDRGPU_API int  tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb);
 TSDRGPU_API int  tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff);
 TSDRGPU_API int  tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels);   /* tsdr_sync: syncoffset += pixels */
 TSDRGPU_API int  tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate);

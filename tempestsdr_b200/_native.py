@@ -32,12 +32,13 @@ class PipelineStats(C.Structure):
     """tsdrgpu_pipeline_stats_t"""
     _fields_ = [(n, C.c_uint64) for n in ("samples_in", "samples_dropped_upstream", "samples_resampled", "frames_processed",
                                           "frames_delivered", "frames_dropped", "captures", "plots_delivered",
-                                          "h2d_bytes", "d2h_bytes", "gpu_launches")]
+                                          "h2d_bytes", "d2h_bytes", "gpu_launches", "stitches")]
 
 
 FRAME_CB = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p)
 VALUE_CB = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_double, C.c_void_p)
 PLOT_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_uint32, C.c_void_p)
+RETUNE_CB = C.CFUNCTYPE(None, C.c_int32, C.c_void_p)
 
 FS_AUTOSHIFT, FS_LOWPASS_BEFORE_SYNC, FS_AUTOGAIN_AFTER_PROC, FS_SUPERRESOLUTION, FS_COMPUTE_SNR = 1, 2, 4, 8, 16
 
@@ -121,6 +122,7 @@ _SIGS = {
     "tsdrgpu_pipeline_set_param_int": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "tsdrgpu_pipeline_set_resolution": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "tsdrgpu_pipeline_set_samplerate": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "tsdrgpu_pipeline_set_retune": (C.c_int, [C.c_void_p, RETUNE_CB]),
     "tsdrgpu_pipeline_set_motionblur": (C.c_int, [C.c_void_p, C.c_float]),
     "tsdrgpu_pipeline_sync": (C.c_int, [C.c_void_p, C.c_int]),
     "tsdrgpu_pipeline_get_geometry": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),

@@ -97,6 +97,10 @@ struct tsdrgpu_pipeline {
 	// autocorrelation side path
 	tsdrgpu_frd *frd; float *d_capture[2]; size_t cap_size[2], cap_fill; int cap_phase; uint32_t cap_rate;
 	double *h_plot_frame[2], *h_plot_line[2]; size_t plot_cap; int plot_slot; int plot_busy[2];
+	// superbandwidth (superb_run's state machine, superbandwidth.c:179-264)
+	struct { int state; int buffid; long long to_gather, gathered, in_frame, to_pause; uint32_t rate; float *d_hops[4]; size_t hop_cap; float *d_out; size_t out_cap; cudaEvent_t ev; } sb;
+	uint32_t samplerate_real;
+	tsdrgpu_retune_cb retune_cb;
 	// delivery
 	pthread_t thread; pthread_mutex_t mu; pthread_cond_t cv_job, cv_done;
 	std::deque<FrameJob> jobs; int stop; uint64_t submitted, delivered;
@@ -404,6 +408,8 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
 	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
 	p->stop = 0; p->submitted = 0; p->delivered = 0; p->last_w = 0; p->last_h = 0;
+	memset(&p->sb, 0, sizeof p->sb); p->samplerate_real = cfg->samplerate; p->retune_cb = NULL;
+	CU_TRY(ctx, cudaEventCreateWithFlags(&p->sb.ev, cudaEventDisableTiming));
 	memset(&p->stats, 0, sizeof p->stats);
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking));
 	CU_TRY(ctx, cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
@@ -449,6 +455,9 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	cudaSetDevice(p->ctx->device);
 	tsdrgpu_resampler_destroy(p->rs); tsdrgpu_framestage_destroy(p->fs); tsdrgpu_frd_destroy(p->frd);
 	for (void *h : p->registered) cudaHostUnregister(h);
+	for (int i = 0; i < 4; i++) if (p->sb.d_hops[i]) cudaFree(p->sb.d_hops[i]);
+	if (p->sb.d_out) cudaFree(p->sb.d_out);
+	cudaEventDestroy(p->sb.ev);
 	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_stage[2], p->d_stage[3], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture[0], p->d_capture[1]};
 	for (float *d : dev) if (d) cudaFree(d);
 	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
@@ -478,11 +487,12 @@ int tsdrgpu_pipeline_set_resolution(tsdrgpu_pipeline_t *p, int height, double re
 int tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate) {
 	if (!p || samplerate == 0) return TSDRGPU_EINVAL;
 	pthread_mutex_lock(&p->geo_mu);
-	p->samplerate = samplerate;
+	p->samplerate = samplerate; p->samplerate_real = samplerate;
 	geometry_locked(p);
 	pthread_mutex_unlock(&p->geo_mu);
 	return TSDRGPU_OK;
 }
+int tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb) { if (!p) return TSDRGPU_EINVAL; p->retune_cb = cb; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff) { if (!p) return TSDRGPU_EINVAL; p->motionblur = coeff; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels) { if (!p) return TSDRGPU_EINVAL; p->syncoffset += pixels; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate) {
@@ -499,7 +509,82 @@ int tsdrgpu_pipeline_stats(tsdrgpu_pipeline_t *p, tsdrgpu_pipeline_stats_t *out)
 	return TSDRGPU_OK;
 }
 
-// the body of the reference's process() (TSDRLibrary.c:264-298), normal (non-superbandwidth) mode
+// ---- superbandwidth mode: superb_run (superbandwidth.c:179-254) + superb_ondataready (:121-152) -------------------
+// Four hops of 10 frames each are recorded at centre frequencies fc + (hop-2)*fs (0.5 s settling pause after every
+// retune), aligned, and stitched into one 4x-rate signal that then flows through the normal decimator / frame stages.
+// The reference does the stitch on a helper thread (~3 s of CPU FFTs); here it runs on the GPU inside the call that
+// completes the last hop (a few ms), so its output appears one process() call earlier.  Everything else is the same.
+enum { SB_STOPPED = 0, SB_STARTING, SB_GATHERING, SB_PAUSE };
+static void superb_stop(tsdrgpu_pipeline *p) {                  // superbandwidth.c:256-264
+	if (p->sb.state == SB_STOPPED) return;
+	p->sb.state = SB_STOPPED;
+	if (p->retune_cb) p->retune_cb(0, p->user);
+	pthread_mutex_lock(&p->geo_mu);
+	p->samplerate = p->samplerate_real;
+	geometry_locked(p);
+	pthread_mutex_unlock(&p->geo_mu);
+}
+static int superb_step(tsdrgpu_pipeline *p, const float *h_iq, uint64_t items_count, int64_t dropped) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	int rc;
+	if (p->sb.state == SB_STOPPED) p->sb.state = SB_STARTING;
+	if (p->sb.state == SB_STARTING) {
+		p->sb.buffid = 0; p->sb.gathered = 0;
+		if (p->samplerate_real != p->sb.rate) {
+			p->sb.rate = p->samplerate_real;
+			pthread_mutex_lock(&p->geo_mu); const double fv = p->refreshrate; pthread_mutex_unlock(&p->geo_mu);
+			p->sb.in_frame = (long long) (p->samplerate_real / fv);
+			p->sb.to_gather = 10 * p->sb.in_frame;                    // SUPER_SAMPLES_TO_RECORD
+			p->sb.to_pause = (long long) (0.5 * p->samplerate_real);   // SUPER_SECS_TO_PAUSE
+			CU_TRY(ctx, cudaStreamSynchronize(p->s_main));
+			for (int i = 0; i < 4; i++) { if (p->sb.d_hops[i]) CU_TRY(ctx, cudaFree(p->sb.d_hops[i])); CU_TRY(ctx, cudaMalloc(&p->sb.d_hops[i], sizeof(float) * 2 * (size_t) p->sb.to_gather)); }
+		}
+		p->sb.state = SB_GATHERING;
+	}
+	if (p->sb.state == SB_PAUSE) {
+		p->sb.gathered += (long long) (items_count / 2);
+		if (p->sb.gathered > p->sb.to_pause) { p->sb.gathered = 0; p->sb.state = SB_GATHERING; }
+	}
+	if (p->sb.state != SB_GATHERING) return TSDRGPU_OK;
+	if (dropped) { p->sb.gathered = 0; return TSDRGPU_OK; }
+	const long long now = (long long) (items_count / 2);
+	const long long take = (p->sb.gathered + now < p->sb.to_gather) ? now : (p->sb.to_gather - p->sb.gathered);
+	if (take > 0) {
+		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->sb.ev, 0));            // the last stitch has finished reading the hop buffers
+		CU_TRY(ctx, cudaMemcpyAsync(p->sb.d_hops[p->sb.buffid] + 2 * p->sb.gathered, h_iq, sizeof(float) * 2 * (size_t) take, cudaMemcpyHostToDevice, p->s_copy));
+		CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));
+		p->stats.h2d_bytes += sizeof(float) * 2 * (size_t) take;
+	}
+	p->sb.gathered += take;
+	if (p->sb.gathered < p->sb.to_gather) return TSDRGPU_OK;
+	const long long count_pairs = p->sb.gathered;
+	p->sb.buffid++; p->sb.gathered = 0;
+	if (p->sb.buffid < 4) {
+		if (p->retune_cb) p->retune_cb((int32_t) ((p->sb.buffid - 2) * (long long) p->sb.rate), p->user);    // shiftfreq, superbandwidth.c:241
+		p->sb.state = SB_PAUSE;
+		return TSDRGPU_OK;
+	}
+	// all hops recorded: align + stitch (superb_ondataready) and hand the 4x-rate signal to the decimator
+	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
+	if (p->sb.out_cap < 8 * N) { CU_TRY(ctx, cudaStreamSynchronize(p->s_main)); if (p->sb.d_out) CU_TRY(ctx, cudaFree(p->sb.d_out)); CU_TRY(ctx, cudaMalloc(&p->sb.d_out, sizeof(float) * 8 * N)); p->sb.out_cap = 8 * N; }
+	int offs[4], total = 0;
+	if ((rc = tsdrgpu_superb_stitch(ctx, p->s_main, p->sb.d_hops, 4, (int) count_pairs, (int) p->sb.in_frame, p->sb.d_out, offs, &total))) return rc;
+	p->stats.stitches++;
+	CU_TRY(ctx, cudaEventRecord(p->sb.ev, p->s_main));
+	pthread_mutex_lock(&p->geo_mu);
+	p->samplerate = 4 * p->sb.rate;                                   // set_internal_samplerate(tsdr, buffscount*samplerate)
+	geometry_locked(p);
+	pthread_mutex_unlock(&p->geo_mu);
+	CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest));
+	if ((rc = grow(ctx, p->s_main, &p->d_decim, &p->decim_cap, 2 * (p->decim_fill + (size_t) total), 2 * p->decim_fill))) return rc;
+	pl_copy_f32<<<2048, 256, 0, p->s_main>>>(p->sb.d_out, p->d_decim + 2 * p->decim_fill, 2ull * (size_t) total);
+	LAUNCH_CHECK(ctx);
+	p->decim_fill += (size_t) total;
+	p->sb.state = SB_STARTING;
+	return drain_blocks(p);
+}
+
+// the body of the reference's process() (TSDRLibrary.c:264-298)
 int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
 	tsdrgpu_ctx_t *ctx = p->ctx;
@@ -511,8 +596,8 @@ int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t 
 	pthread_mutex_unlock(&p->geo_mu);
 	p->stats.samples_in += size2;
 	if (samples_dropped > 0) p->stats.samples_dropped_upstream += (uint64_t) samples_dropped;
-	if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION])
-		return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "superbandwidth mode is driven through tsdrgpu_superb_* (not the streaming pipeline)", cudaSuccess, __FILE__, __LINE__);
+	if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION]) return superb_step(p, h_iq, items_count, samples_dropped);
+	superb_stop(p);
 	const int block = (int) round((double) ((w * h) << 1) * ptos);           // TSDRLibrary.c:284
 	if (block <= 0) return TSDRGPU_OK;
 	p->dev_drop.shift_with((uint32_t) block, samples_dropped);

@@ -242,11 +242,16 @@ static void on_plot(int plot_id, int offset, double *values, int size, uint32_t 
 	if (t->plotready_callback) t->plotready_callback(plot_id, offset, values, size, samplerate, t->callbackctx);
 }
 
+/* shiftfreq (TSDRLibrary.c:208-211): the superbandwidth mode retunes the front end between hops */
+static void on_retune(int32_t offset_hz, void *user) {
+	tsdr_lib_t *t = (tsdr_lib_t *) user;
+	if (t->plugin.initialized) t->plugin.setbasefreq(t->centfreq + offset_hz);
+}
+
 /* the plugin's data callback == the reference's process() (TSDRLibrary.c:264-298), on the plugin's thread */
 static void process(float *buf, uint64_t items_count, void *ctx, int64_t samples_dropped) {
 	tsdr_lib_t *t = (tsdr_lib_t *) ctx;
 	if (t->gpu_failed || !t->pipe) return;
-	if (t->params_int[PARAM_AUTOCORR_SUPERRESOLUTION]) return;     /* handled by tsdrgpu_superb_*  */
 	const int rc = tsdrgpu_pipeline_process(t->pipe, buf, items_count, samples_dropped);
 	if (rc != TSDRGPU_OK) {
 		t->gpu_failed = 1;
@@ -293,6 +298,7 @@ int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 			t->pipe = NULL;
 			goto end;
 		}
+		tsdrgpu_pipeline_set_retune(t->pipe, on_retune);
 	}
 	status = t->plugin.readasync(process, t);                 /* blocks until tsdr_stop or a plugin error */
 	if (status != TSDR_OK) pluginsfault = 1;

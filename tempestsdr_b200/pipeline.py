@@ -22,7 +22,8 @@ class Pipeline:
     def __init__(self, samplerate: int, height: int, refreshrate: float, motionblur: float = 0.0,
                  params: Optional[Dict[str, int]] = None, batch_frames: int = 1, batch_blocks: int = 10,
                  block_when_busy: bool = False, device: int = 0,
-                 on_frame: Optional[Callable] = None, on_value: Optional[Callable] = None, on_plot: Optional[Callable] = None):
+                 on_frame: Optional[Callable] = None, on_value: Optional[Callable] = None, on_plot: Optional[Callable] = None,
+                 on_retune: Optional[Callable] = None):
         self._lib = N.lib()
         ctx = C.c_void_p()
         N.check(self._lib.tsdrgpu_create(C.byref(ctx), device))
@@ -59,6 +60,14 @@ class Pipeline:
         h = C.c_void_p()
         N.check(self._lib.tsdrgpu_pipeline_create(ctx, C.byref(cfg), *self._cbs, None, C.byref(h)), ctx)
         self._h = h
+        if on_retune:
+            def _retune(off, _):
+                try:
+                    on_retune(off)
+                except Exception as e:
+                    self.errors.append(e)
+            self._retune_cb = N.RETUNE_CB(_retune)
+            N.check(self._lib.tsdrgpu_pipeline_set_retune(h, self._retune_cb), ctx)
 
     def process(self, iq: np.ndarray, samples_dropped: int = 0) -> None:
         """iq: interleaved float32 I,Q on the HOST (numpy, or a pinned torch tensor's .numpy())."""

@@ -114,3 +114,60 @@ def run_oracle_stream_flat(O, iq, fs, h, fv):
     pix = np.concatenate(pix)
     frames = [pp.run(pix[k * n:(k + 1) * n], w, h, 0.0, 0.1, 0, 0)[0] for k in range(pix.size // n)]
     return w, frames
+
+
+def test_pipeline_superbandwidth_mode():
+    """PARAM_AUTOCORR_SUPERRESOLUTION: superb_run's state machine (gather 4 hops of 10 frames, 0.5 s pause and a retune
+    after each, stitch) runs inside process(); the stitched signal then flows at 4x the rate through the frame stages."""
+    from tempestsdr_b200 import pipeline
+    O = orc.best()
+    fs, h, fv = 400_000, 80, 50.0
+    sif = int(fs / fv)                         # 8000 samples per frame
+    to_gather, to_pause = 10 * sif, int(0.5 * fs)
+    items = 16384
+    nblk = 2 * (4 * (to_gather + to_pause) // (items // 2) + 8)
+    iq_all = synth.video_like_iq(nblk * items // 2, fs, 200, 80, fv, seed=41, snr_db=25)
+    blocks = [iq_all[k * items:(k + 1) * items].copy() for k in range(nblk)]
+    retunes, frames = [], []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=1, block_when_busy=True,
+                          params={"autoshift": 1, "lowpass_before_sync": 1, "superresolution": 1, "autocorr_plots_off": 1},
+                          on_frame=lambda f, ww, hh: frames.append((f.copy(), ww, hh)), on_retune=lambda off: retunes.append(off))
+    # host-side replay of the reference's state machine (superbandwidth.c:179-254) to know what each hop must contain
+    state, buffid, gathered, hops, cur = "gather", 0, 0, [], []
+    expected_hops = None
+    for b in blocks:
+        p.process(b, 0)
+        now = b.size // 2
+        if expected_hops is not None:
+            continue
+        if state == "pause":
+            gathered += now
+            if gathered > to_pause:
+                gathered, state = 0, "gather"
+        if state == "gather":
+            take = now if gathered + now < to_gather else to_gather - gathered
+            cur.append(b[: 2 * take]); gathered += take
+            if gathered == to_gather:
+                hops.append(np.concatenate(cur)); cur = []; gathered = 0; buffid += 1
+                if buffid == 4:
+                    expected_hops = hops
+                else:
+                    state = "pause"
+    p.flush()
+    st = p.stats()
+    assert st.stitches >= 1 and retunes[:3] == [-fs, 0, fs]           # (hop - 2) * samplerate for hops 1, 2, 3
+    w4, _, _ = O.geometry(4 * fs, h, fv)
+    assert p.geometry()[0] == w4 and len(frames) >= 8 and frames[0][1] == w4
+    # the stitched signal of the first round, through the oracle's stages, gives the same first frames (tolerance: the
+    # stitch is a float FFT, so pixels agree to ~1e-4 of full scale after auto-gain; sync offsets must match exactly)
+    want_iq, offs = O.superb_ondataready(expected_hops, sif)
+    mag = O.am_demod(want_iq)
+    block4 = int(0.1 * 4 * fs / fv)
+    rs = O.resampler(); pp = O.postprocessor(4 * fs, h, fv, 1, 0, superres=1)
+    pix = np.concatenate([rs.run(mag[k * block4:(k + 1) * block4], w4 * h * fv, 4.0 * fs) for k in range(mag.size // block4 // 10 * 10)])
+    n = w4 * h
+    for k in range(min(6, pix.size // n)):
+        ref, _ = pp.run(pix[k * n:(k + 1) * n], w4, h, 0.0, 0.1, 1, 0)
+        got = frames[k][0]
+        assert np.max(np.abs(got - ref)) < 2e-3, f"frame {k}: {np.max(np.abs(got - ref))}"
+    p.close()
