@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
+#include <mutex>
 
 namespace {
 
@@ -35,9 +36,6 @@ struct FftPass {
 	long long in_hi, in_lo, in_cs, in_js;
 	long long out_hi, out_lo, out_cs, out_ks;
 	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
-	const float2 *tab_lo, *tab_hi;                      // W_M^e = tab_lo[e & 4095] * tab_hi[e >> 12]  (forward sign)
-	float eps[12];                                      // reference-compatible mode: relative angle error of sub-stage s of this line FFT
-	int pert;                                           // non-zero: use the perturbed-angle butterflies
 	float scale;
 	int in_real, out_abs;
 };
@@ -164,10 +162,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_small(const float2 *in, float
 			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
 			const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
 			float2 tw;
-			if (P.tab_lo) {                                   // two-level table (opt-in: scattered lookups measured slower)
-				tw = __ldg(P.tab_lo + (unsigned) (e & 4095ull));
-				if (P.tw_M > 4096ull) tw = cmul(tw, __ldg(P.tab_hi + (unsigned) (e >> 12)));
-			} else if (P.tw_M <= (1ull << 24)) { float sn, cs; sincospif(-2.0f * ((float) e / (float) P.tw_M), &sn, &cs); tw = make_float2(cs, sn); }   // exact argument
+			if (P.tw_M <= (1ull << 24)) { float sn, cs; sincospif(-2.0f * ((float) e / (float) P.tw_M), &sn, &cs); tw = make_float2(cs, sn); }   // exact argument
 			else { double dsn, dcs; sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); tw = make_float2((float) dcs, (float) dsn); }
 			if (inverse) tw.y = -tw.y;
 			v = cmul(v, tw);
@@ -184,137 +179,138 @@ __global__ void __launch_bounds__(512, 3) fft_pass_small(const float2 *in, float
 // so a 1024-point line makes 3 trips through shared memory instead of 5 + load + store, with one barrier each
 // (ping-pong buffers).  Thread -> (line, butterfly) maps are chosen per pass so that the global accesses of a warp are
 // runs of consecutive complex values: line-fastest on strided passes, butterfly-fastest on contiguous lines.
-// ---- reference-compatible ("perturbed-angle") butterflies ------------------------------------------------------------
-// The reference's stage l rotates by (pi/2^l)(1+eps_l) (see tsdrgpu_fft_reference_eps).  A radix-8 Stockham step with
-// block size p is three radix-2 layers with blocks p, 2p, 4p; written out, layer t multiplies the upper input by
-// e^{-+ i theta_t K}, K = k + p q0 (+ 2p q1): the exact twiddle from the table times a small extra rotation
-// -+ eps_t * pi * K / block_t.  With all eps = 0 this is the ordinary DFT-8 with input twiddles.
-__device__ __forceinline__ float2 pert_tw(const float2 *__restrict__ table, unsigned idx, float phi, bool inverse) {
-	const float2 w = tw_lookup(table, idx, inverse);
-	return cmul(w, make_float2(1.0f - 0.5f * phi * phi, inverse ? phi : -phi));
+//
+// Butterflies are written as their radix-2 layers (a radix-8 Stockham step with block size p = layers with blocks p, 2p,
+// 4p): layer t multiplies the upper input by T_t[K], K = k + p q0 (+ 2p q1).  The layer twiddles come from a per-pass
+// table built on the host in double precision, T_s[K] = exp(-i pi K / 2^s (1 + eps_s)), stored layer after layer
+// (layer s at offset 2^s - 1), so the seven twiddles of a radix-8 butterfly are table[k + j p - 1], j = 1..7.
+// eps_s is the relative angle error of the reference's stage l_base + s (tsdrgpu_fft_reference_eps; fft.c:161 derives
+// its twiddles by a half-angle recurrence that loses accuracy for small angles) or 0 for the mathematically exact DFT:
+// same kernel, same operation count (12 complex multiplications + 24 additions per 8 points) either way.
+//
+// Shared memory is unpadded; a line's point q lives at slot (q ^ swz(q)) ^ xc(line): swz permutes inside aligned groups
+// of 16 so that the stride-8 stores of stage 0 and the stride-p stores of the p = 8 stage hit 16 distinct bank pairs per
+// half-warp, and xc (a per-line constant < 16) does the same for the line-fastest thread maps of strided passes.
+__device__ __forceinline__ int swz(int q) { return q ^ ((q >> 4) & 7) ^ (((q >> 6) & 1) << 3); }
+
+template <bool INV>
+__device__ __forceinline__ float2 twmul(float2 w, float2 x) {        // x * w (forward) or x * conj(w) (inverse)
+	if (INV) return make_float2(x.x * w.x + x.y * w.y, x.y * w.x - x.x * w.y);
+	return make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
 }
-#define PI_F 3.14159265358979323846f
-__device__ __forceinline__ void dft8_pert(float2 *v, int k, int p, float e0, float e1, float e2, const float2 *__restrict__ table, bool inverse) {
+template <bool INV>
+__device__ __forceinline__ void bf8(float2 *v, const float2 *__restrict__ tw /* = table + k - 1 */, int p) {
 	float2 a[4][2], b[2][2][2];
-	const float2 TA = pert_tw(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), e0 * PI_F * (float) k / (float) p, inverse);
+	const float2 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
+	const float2 TC00 = __ldg(tw + 4 * p), TC10 = __ldg(tw + 5 * p), TC01 = __ldg(tw + 6 * p), TC11 = __ldg(tw + 7 * p);
 	#pragma unroll
-	for (int r = 0; r < 4; r++) { const float2 hi = cmul(TA, v[r + 4]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
+	for (int r = 0; r < 4; r++) { const float2 hi = twmul<INV>(TA, v[r + 4]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
 	#pragma unroll
 	for (int q0 = 0; q0 < 2; q0++) {
-		const int K = k + p * q0;
-		const float2 TB = pert_tw(table, (unsigned) K * (unsigned) (FFT_TABLE / (4 * p)), e1 * PI_F * (float) K / (float) (2 * p), inverse);
+		const float2 TB = q0 ? TB1 : TB0;
 		#pragma unroll
-		for (int m0 = 0; m0 < 2; m0++) { const float2 hi = cmul(TB, a[m0 + 2][q0]); b[m0][q0][0] = cadd(a[m0][q0], hi); b[m0][q0][1] = csub(a[m0][q0], hi); }
+		for (int m0 = 0; m0 < 2; m0++) { const float2 hi = twmul<INV>(TB, a[m0 + 2][q0]); b[m0][q0][0] = cadd(a[m0][q0], hi); b[m0][q0][1] = csub(a[m0][q0], hi); }
 	}
 	#pragma unroll
 	for (int q0 = 0; q0 < 2; q0++) {
 		#pragma unroll
 		for (int q1 = 0; q1 < 2; q1++) {
-			const int K = k + p * q0 + 2 * p * q1;
-			const float2 TC = pert_tw(table, (unsigned) K * (unsigned) (FFT_TABLE / (8 * p)), e2 * PI_F * (float) K / (float) (4 * p), inverse);
-			const float2 hi = cmul(TC, b[1][q0][q1]);
+			const float2 TC = q1 ? (q0 ? TC11 : TC01) : (q0 ? TC10 : TC00);
+			const float2 hi = twmul<INV>(TC, b[1][q0][q1]);
 			v[q0 + 2 * q1] = cadd(b[0][q0][q1], hi); v[q0 + 2 * q1 + 4] = csub(b[0][q0][q1], hi);
 		}
 	}
 }
-__device__ __forceinline__ void dft4_pert(float2 *v, int k, int p, float e0, float e1, const float2 *__restrict__ table, bool inverse) {
+template <bool INV>
+__device__ __forceinline__ void bf4(float2 *v, const float2 *__restrict__ tw, int p) {
 	float2 a[2][2];
-	const float2 TA = pert_tw(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), e0 * PI_F * (float) k / (float) p, inverse);
+	const float2 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
 	#pragma unroll
-	for (int r = 0; r < 2; r++) { const float2 hi = cmul(TA, v[r + 2]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
+	for (int r = 0; r < 2; r++) { const float2 hi = twmul<INV>(TA, v[r + 2]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
 	#pragma unroll
 	for (int q0 = 0; q0 < 2; q0++) {
-		const int K = k + p * q0;
-		const float2 TB = pert_tw(table, (unsigned) K * (unsigned) (FFT_TABLE / (4 * p)), e1 * PI_F * (float) K / (float) (2 * p), inverse);
-		const float2 hi = cmul(TB, a[1][q0]);
+		const float2 hi = twmul<INV>(q0 ? TB1 : TB0, a[1][q0]);
 		v[q0] = cadd(a[0][q0], hi); v[q0 + 2] = csub(a[0][q0], hi);
 	}
 }
-__device__ __forceinline__ void dft2_pert(float2 *v, int k, int p, float e0, const float2 *__restrict__ table, bool inverse) {
-	const float2 hi = cmul(pert_tw(table, (unsigned) k * (unsigned) (FFT_TABLE / (2 * p)), e0 * PI_F * (float) k / (float) p, inverse), v[1]);
+template <bool INV>
+__device__ __forceinline__ void bf2(float2 *v, const float2 *__restrict__ tw, int p) {
+	const float2 hi = twmul<INV>(__ldg(tw + p), v[1]);
 	const float2 lo = v[0];
 	v[0] = cadd(lo, hi); v[1] = csub(lo, hi);
 }
 
-template <int R>
-__device__ __forceinline__ void apply_stage_twiddles(float2 *v, unsigned tq, const float2 *__restrict__ table, bool inverse) {
-	#pragma unroll
-	for (int m = 1; m < R; m++) v[m] = cmul(v[m], tw_lookup(table, m * tq, inverse));
-}
-
-template <int LOG2L>
-__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P,
-                                                          const float2 *__restrict__ table, int inverse_) {
+template <int LOG2L, bool INV>
+__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float2 *__restrict__ stw) {
 	extern __shared__ float2 s[];
 	constexpr int L = 1 << LOG2L, NST8 = LOG2L / 3, RL = LOG2L % 3;
 	constexpr int RLAST = (RL == 0) ? 8 : ((RL == 1) ? 2 : 4);
 	constexpr int NSTAGES = NST8 + (RL ? 1 : 0);
 	constexpr int NMID = NSTAGES - 2;                    // radix-8 stages between the first and the last one
 	constexpr int L8 = L / 8, LOG2L8 = LOG2L - 3;
-	const bool inverse = inverse_ != 0;
-	const int C = P.C, log2C = P.log2C, LP = padq(L) + 1;
+	const int C = P.C, log2C = P.log2C;
 	const int tid = threadIdx.x;
 	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g - g_hi * P.G_lo;
-	const float2 *gin = in + ((long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs);
-	const float *gin_real = reinterpret_cast<const float *>(in) + ((long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs);
+	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs;
 	float2 *gout = out + ((long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo + (long long) blockIdx.y * P.out_bs);
 	const bool active = tid < C * L8;                    // tiny bundles leave part of the last warp idle
+	// per-line slot constants (see above): xa for the buffer stage 0 writes, xb for the buffer the last stage reads
+	const int sha = (log2C >= 4) ? 0 : 3 - log2C, shb = (NSTAGES == 2 || log2C >= 4) ? sha : 4 - log2C;
 	float2 v[8];
 
-	// ---- stage 0: radix 8, p = 1 (all twiddles are 1), inputs x[i + m L/8] from global memory
+	// ---- stage 0: radix 8, p = 1, inputs x[i + m L/8] from global memory
 	{
 		int c, i;
 		if (P.c_fast_in) { c = tid & (C - 1); i = tid >> log2C; } else { i = tid & (L8 - 1); c = tid >> LOG2L8; }
 		if (active) {
 			const int off = c * (int) P.in_cs + i * (int) P.in_js, step = L8 * (int) P.in_js;
 			if (P.in_real) {
+				const float *gr = reinterpret_cast<const float *>(in) + in_base + off;
 				#pragma unroll
-				for (int m = 0; m < 8; m++) v[m] = make_float2(__ldg(gin_real + off + m * step), 0.0f);
+				for (int m = 0; m < 8; m++) v[m] = make_float2(__ldg(gr + m * step), 0.0f);
 			} else {
+				const float2 *gc = in + in_base + off;
 				#pragma unroll
-				for (int m = 0; m < 8; m++) v[m] = __ldg(gin + off + m * step);
+				for (int m = 0; m < 8; m++) v[m] = __ldg(gc + m * step);
 			}
-			if (P.pert) dft8_pert(v, 0, 1, P.eps[0], P.eps[1], P.eps[2], table, inverse);
-			else { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]); dft8(u, inverse); }
+			bf8<INV>(v, stw - 1, 1);
 		}
 		if (NSTAGES > 1) {
 			if (active) {
-				float2 *line = s + c * LP;
+				float2 *line = s + c * L;
+				const int xa = (c << sha) & 15;
 				#pragma unroll
-				for (int m = 0; m < 8; m++) line[padq(8 * i + m)] = v[m];
+				for (int m = 0; m < 8; m++) line[swz(8 * i + m) ^ xa] = v[m];
 			}
 			__syncthreads();
 		}
 	}
-	float2 *src = s, *dst = s + C * LP;
-	int p = 8;
+	float2 *src = s, *dst = s + C * L;
 	// ---- middle radix-8 stages (shared -> shared, ping-pong)
 	#pragma unroll
 	for (int st = 0; st < (NMID > 0 ? NMID : 0); st++) {
+		const int p = 8 << (3 * st);
 		const int i = tid & (L8 - 1), c = tid >> LOG2L8;
 		if (active) {
-			const float2 *line = src + c * LP;
+			const int xa = (c << sha) & 15, xw = (st == NMID - 1) ? ((c << shb) & 15) : xa;
+			const float2 *line = src + c * L;
 			#pragma unroll
-			for (int m = 0; m < 8; m++) v[m] = line[padq(i + m * L8)];
+			for (int m = 0; m < 8; m++) v[m] = line[swz(i + m * L8) ^ xa];
 			const int k = i & (p - 1);
-			if (P.pert) dft8_pert(v, k, p, P.eps[3 * st + 3], P.eps[3 * st + 4], P.eps[3 * st + 5], table, inverse);
-			else {
-				if (k) apply_stage_twiddles<8>(v, (unsigned) k * (unsigned) (FFT_TABLE / (8 * p)), table, inverse);
-				float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
-				dft8(u, inverse);
-			}
-			float2 *lo = dst + c * LP;
+			bf8<INV>(v, stw + k - 1, p);
+			float2 *lo = dst + c * L;
 			const int j = ((i - k) << 3) + k;
 			#pragma unroll
-			for (int m = 0; m < 8; m++) lo[padq(j + m * p)] = v[m];
+			for (int m = 0; m < 8; m++) lo[swz(j + m * p) ^ xw] = v[m];
 		}
 		__syncthreads();
 		float2 *t = src; src = dst; dst = t;
-		p <<= 3;
 	}
 	// ---- last stage: radix RLAST with p = L / RLAST, results X[i + m p] go to global memory
 	constexpr int NB = 8 / RLAST, PL = L / RLAST, LOG2PL = LOG2L - (RLAST == 8 ? 3 : (RLAST == 4 ? 2 : 1));
 	const int T = blockDim.x;
+	const unsigned twmask = (unsigned) (P.tw_M - 1);
+	const float inv_M = P.tw_M ? 1.0f / (float) P.tw_M : 0.0f;       // a power of two: exact
 	#pragma unroll
 	for (int it = 0; it < NB; it++) {
 		const int widx = tid + it * T;
@@ -323,48 +319,50 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 		if (P.c_fast_out) { c = widx & (C - 1); i = widx >> log2C; } else { i = widx & (PL - 1); c = widx >> LOG2PL; }
 		float2 *w = v + it * RLAST;
 		if (NSTAGES > 1) {
-			const float2 *line = src + c * LP;
+			const float2 *line = src + c * L;
+			const int xb = (c << shb) & 15;
 			#pragma unroll
-			for (int m = 0; m < RLAST; m++) w[m] = line[padq(i + m * PL)];
-			if (P.pert) {
-				constexpr int S0 = LOG2L - (RLAST == 8 ? 3 : (RLAST == 4 ? 2 : 1));      // first sub-stage of this butterfly
-				if (RLAST == 8) dft8_pert(w, i, PL, P.eps[S0], P.eps[S0 + 1], P.eps[S0 + 2], table, inverse);
-				else if (RLAST == 4) dft4_pert(w, i, PL, P.eps[S0], P.eps[S0 + 1], table, inverse);
-				else dft2_pert(w, i, PL, P.eps[S0], table, inverse);
+			for (int m = 0; m < RLAST; m++) w[m] = line[swz(i + m * PL) ^ xb];
+			if (RLAST == 8) bf8<INV>(w, stw + i - 1, PL);
+			else if (RLAST == 4) bf4<INV>(w, stw + i - 1, PL);
+			else bf2<INV>(w, stw + i - 1, PL);
+		}
+		float2 *o = gout + c * (int) P.out_cs;
+		const int ks = (int) P.out_ks;
+		if (P.tw_M) {
+			// inter-pass twiddle W_M^(col k): the argument is reduced exactly in integers, sincospif sees an exact float
+			const unsigned col = (unsigned) ((int) g_lo * (int) P.tw_lo + c * (int) P.tw_cs);
+			if (P.tw_M <= (1ull << 24)) {
+				#pragma unroll
+				for (int m = 0; m < RLAST; m++) {
+					const int k = i + m * PL;
+					const unsigned e = (col * (unsigned) k) & twmask;
+					float sn, cs;
+					sincospif(-2.0f * ((float) e * inv_M), &sn, &cs);
+					w[m] = twmul<INV>(make_float2(cs, sn), w[m]);
+				}
 			} else {
-				if (i) apply_stage_twiddles<RLAST>(w, (unsigned) i * (unsigned) (FFT_TABLE / L), table, inverse);
-				if (RLAST == 8) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&w[0]); dft8(u, inverse); }
-				else if (RLAST == 4) dft4(w[0], w[1], w[2], w[3], inverse);
-				else dft2(w[0], w[1]);
+				#pragma unroll
+				for (int m = 0; m < RLAST; m++) {
+					const int k = i + m * PL;
+					const unsigned long long e = ((unsigned long long) col * (unsigned long long) k) & (P.tw_M - 1);
+					double dsn, dcs;
+					sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs);
+					w[m] = twmul<INV>(make_float2((float) dcs, (float) dsn), w[m]);
+				}
 			}
 		}
-		const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
-		float2 *o = gout + c * (int) P.out_cs;
-		#pragma unroll
-		for (int m = 0; m < RLAST; m++) {
-			const int k = i + m * PL;
-			float2 x = w[m];
-			if (P.tw_M) {
-				const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
-				float2 tw;
-				if (P.tw_M <= (1ull << 24)) { float sn, cs; sincospif(-2.0f * ((float) e / (float) P.tw_M), &sn, &cs); tw = make_float2(cs, sn); }   // exact argument
-				else { double dsn, dcs; sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); tw = make_float2((float) dcs, (float) dsn); }
-				if (inverse) tw.y = -tw.y;
-				x = cmul(x, tw);
+		if (P.out_abs) {
+			#pragma unroll
+			for (int m = 0; m < RLAST; m++) {
+				const float x = w[m].x * P.scale, y = w[m].y * P.scale;
+				o[(i + m * PL) * ks] = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), 0.0f);
 			}
-			x.x *= P.scale; x.y *= P.scale;
-			if (P.out_abs) x = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y))), 0.0f);
-			o[(long long) k * P.out_ks] = x;
+		} else {
+			#pragma unroll
+			for (int m = 0; m < RLAST; m++) o[(i + m * PL) * ks] = make_float2(w[m].x * P.scale, w[m].y * P.scale);
 		}
 	}
-}
-
-// inter-pass twiddle tables for modulus M: lo[q] = e^{-2 pi i q / M} (q < 4096), hi[q] = e^{-2 pi i q 4096 / M} (q < M/4096)
-__global__ void fft_tw_table_kernel(float2 *lo, float2 *hi, unsigned long long M) {
-	const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
-	double sn, cs;
-	if (q < 4096) { sincospi(-2.0 * ((double) (q % M)) / (double) M, &sn, &cs); lo[q] = make_float2((float) cs, (float) sn); }
-	if (M > 4096 && q < (unsigned) (M >> 12)) { sincospi(-2.0 * (double) q * 4096.0 / (double) M, &sn, &cs); hi[q] = make_float2((float) cs, (float) sn); }
 }
 
 __global__ void fft_table_kernel(float2 *table) {
@@ -510,23 +508,36 @@ inline unsigned grid1d(unsigned long long n, int sm_count) {
 }
 
 float2 *g_table[64] = {0};          // per device
-struct TwTab { int device; unsigned long long M; float2 *lo, *hi; };
-std::vector<TwTab> g_twtabs;
+// per-pass layer-twiddle tables (see fft_pass_kernel), built on the host in double precision and cached
+struct StageTab { int device, log2L, l_base, pert; float2 *d; };
+std::vector<StageTab> g_stage_tabs;
 std::mutex g_tw_mu;
 
-int tw_tables(tsdrgpu_ctx_t *ctx, cudaStream_t stream, unsigned long long M, const float2 **lo, const float2 **hi) {
+int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all, const float2 **out) {
+	static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;      // opt out: the mathematically exact DFT
+	double eps[FFT_MAX_LOG2L + 1];
+	int pert = 0;
+	for (int sidx = 0; sidx < log2L; sidx++) {
+		eps[sidx] = (!exact_dft && eps_all && l_base + sidx < 40) ? eps_all[l_base + sidx] : 0.0;
+		if (eps[sidx] != 0.0) pert = 1;
+	}
 	std::lock_guard<std::mutex> lock(g_tw_mu);
-	for (auto &t : g_twtabs) if (t.device == ctx->device && t.M == M) { *lo = t.lo; *hi = t.hi; return TSDRGPU_OK; }
-	TwTab t; t.device = ctx->device; t.M = M;
-	const unsigned long long nhi = (M > 4096) ? (M >> 12) : 1;
-	CU_TRY(ctx, cudaMalloc(&t.lo, sizeof(float2) * 4096));
-	CU_TRY(ctx, cudaMalloc(&t.hi, sizeof(float2) * nhi));
-	const unsigned long long threads = nhi > 4096 ? nhi : 4096;
-	fft_tw_table_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, stream>>>(t.lo, t.hi, M);
-	LAUNCH_CHECK(ctx);
-	CU_TRY(ctx, cudaStreamSynchronize(stream));
-	g_twtabs.push_back(t);
-	*lo = t.lo; *hi = t.hi;
+	for (auto &t : g_stage_tabs) if (t.device == ctx->device && t.log2L == log2L && t.l_base == (pert ? l_base : -1) && t.pert == pert) { *out = t.d; return TSDRGPU_OK; }
+	const int L = 1 << log2L;
+	std::vector<float2> h((size_t) L);
+	for (int sidx = 0; sidx < log2L; sidx++) {
+		const int blk = 1 << sidx;
+		for (int K = 0; K < blk; K++) {
+			const double ang = -3.14159265358979323846 * ((double) K / (double) blk) * (1.0 + eps[sidx]);
+			h[(size_t) blk - 1 + K] = make_float2((float) cos(ang), (float) sin(ang));
+		}
+	}
+	h[(size_t) L - 1] = make_float2(1.0f, 0.0f);
+	StageTab t; t.device = ctx->device; t.log2L = log2L; t.l_base = pert ? l_base : -1; t.pert = pert;
+	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float2) * L));
+	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice));
+	g_stage_tabs.push_back(t);
+	*out = t.d;
 	return TSDRGPU_OK;
 }
 
@@ -538,8 +549,9 @@ int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	LAUNCH_CHECK(ctx);
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
 	g_table[ctx->device] = t;
-	const int max_smem = (int) (2 * sizeof(float2) * (FFT_MAX_ELEMS + FFT_MAX_ELEMS / 16 + 64));     // ping-pong
-#define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+	const int max_smem = (int) (2 * sizeof(float2) * FFT_MAX_ELEMS);     // ping-pong
+#define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
 	SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
 #undef SET_ATTR
 	return TSDRGPU_OK;
@@ -556,34 +568,27 @@ int bundle_for(int log2L, unsigned long long lines) {
 int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, FftPass P, unsigned bundles, int inverse,
                 unsigned batch, long long in_bs, long long out_bs, const double *eps_all = NULL, int l_base = 0) {
 	P.in_bs = in_bs; P.out_bs = out_bs;
-	P.tab_lo = P.tab_hi = NULL;
-	{   // reference-compatible stage angles (default): sub-stage s of this pass is the reference's stage l_base + s
-		static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;      // opt out: the mathematically exact DFT
-		P.pert = 0;
-		for (int s = 0; s < 12; s++) P.eps[s] = 0.0f;
-		if (!exact_dft && eps_all) {
-			for (int s = 0; s < P.log2L && l_base + s < 40; s++) {
-				P.eps[s] = (float) eps_all[l_base + s];
-				if (fabs(eps_all[l_base + s]) > 2e-9) P.pert = 1;
-			}
-		}
-	}
-	static const bool use_tables = getenv("TSDRGPU_FFT_TWIDDLE_TABLES") != NULL;
-	if (P.tw_M && use_tables) { int rc = tw_tables(ctx, stream, P.tw_M, &P.tab_lo, &P.tab_hi); if (rc) return rc; }
 	P.log2C = 0; while ((1 << P.log2C) < P.C) P.log2C++;
 	const int L = 1 << P.log2L, total = P.C * L;
 	int threads = (total / 8 + 31) / 32 * 32;            // one radix-8 butterfly (8 elements) per thread and stage
 	if (threads < 32) threads = 32;
 	if (threads > 512) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT bundle too large", cudaSuccess, __FILE__, __LINE__);
-	const int LP = L + (L >> 4) + 1;
 	const int nstages = P.log2L / 3 + ((P.log2L % 3) ? 1 : 0);
-	const size_t smem = sizeof(float2) * (size_t) P.C * LP * (P.log2L >= 3 ? (nstages >= 3 ? 2 : 1) : 1);
 	const dim3 grid(bundles, batch);
 	const float2 *tab = g_table[ctx->device];
+	if (P.log2L <= 2) {
+		const int LP = L + (L >> 4) + 1;
+		const size_t smem = sizeof(float2) * (size_t) P.C * LP;
+		if (P.log2L == 1) KL(ctx, "fft_pass_kernel", stream, fft_pass_small<1><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse));
+		else KL(ctx, "fft_pass_kernel", stream, fft_pass_small<2><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse));
+		return TSDRGPU_OK;
+	}
+	const float2 *stw;
+	{ int rc = stage_table(ctx, P.log2L, l_base, eps_all, &stw); if (rc) return rc; }
+	const size_t smem = sizeof(float2) * (size_t) total * (nstages >= 3 ? 2 : 1);
 	switch (P.log2L) {
-	case 1: KL(ctx, "fft_pass_kernel", stream, fft_pass_small<1><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break;
-	case 2: KL(ctx, "fft_pass_kernel", stream, fft_pass_small<2><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break;
-#define CASE(l) case l: KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse)); break
+#define CASE(l) case l: if (inverse) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
+	                else KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false><<<grid, threads, smem, stream>>>(in, out, P, stw)); break
 	CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
 #undef CASE
 	default: return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "unsupported FFT line length", cudaSuccess, __FILE__, __LINE__);

@@ -21,6 +21,7 @@
 #include "host_plan.h"
 #include <math.h>
 #include <stdlib.h>
+#include <cuda_pipeline.h>
 
 namespace {
 
@@ -433,26 +434,85 @@ __device__ __forceinline__ double window_from_prefix(const double *S, int n, int
 	return (S[n] - S[e]) + S[end - n];
 }
 
-// One CTA walks the frames of the batch in order (the strip size and dx carry from frame to frame).
-// Per frame: blur both strips into double (all threads) + exactness certificate | exact prefix scans (or, when the
-// certificate fails, the serial chains) | every thread scores a slice of the windows of every candidate strip size,
-// first-max reduce | thread 0: pick the strip size, update dx/vx, PLL average.
-__global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
-                                                           int w, int h, int minsize_x, int minsize_y, int nframes,
-                                                           float c0, float c1, float c2, float c3, float c4,
-                                                           SyncState *state, double *__restrict__ chain_scratch, int force_serial,
-                                                           tsdrgpu_frame_result_t *results) {
+// The sync search of a batch is split in two kernels.
+//   fs_sync_prep   (one CTA per frame, frames in parallel): everything that does not depend on the previous frame --
+//                  blur both strips into double, exactness certificate, exact prefix scans, strip totals -- written as
+//                  one record per frame: [x buffer: w+1][y buffer: h+1][ok_x, ok_y, total_x, total_y].  A buffer holds the
+//                  prefix sums S[0..n] when its certificate holds, otherwise the blurred strip in [1..n].
+//   fs_sync        (one CTA walks the frames in order: the strip size and dx carry from frame to frame): records are
+//                  prefetched into shared memory one frame ahead (cp.async), every thread scores a slice of the windows
+//                  of every candidate strip size (serial chains first when a certificate failed), first-max reduce,
+//                  thread 0 picks the strip size and updates dx/vx and the PLL average.
+constexpr int FS_PREP_HDR = 4;
+__host__ __device__ __forceinline__ size_t fs_prep_stride(int w, int h) { return (size_t) w + h + 2 + FS_PREP_HDR; }
+
+__global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync_prep(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
+                                                                int w, int h, float c0, float c1, float c2, float c3, float c4,
+                                                                int force_serial, double *__restrict__ prep) {
 	extern __shared__ double smem_d[];
-	double *buf_x = smem_d, *buf_y = buf_x + (w + 1);    // buf[1..n] = blurred strip, later buf[0..n] = prefix sums
-	__shared__ int cand[2][5];           // strip sizes tried per axis, -1 = skipped
-	__shared__ float totalf[2];
-	__shared__ Best warp_best[10][FS_SYNC_THREADS / 32];
-	__shared__ Best cand_best[2][5];
-	__shared__ SyncState st;
+	double *buf_x = smem_d, *buf_y = buf_x + (w + 1);
 	__shared__ float tiny[16];
 	__shared__ double warp_tot[32];
 	__shared__ int range_lo[2], range_hi[2], range_bad[2], exact_ok[2];
+	__shared__ float totalf[2];
 	const float taps[5] = {c0, c1, c2, c3, c4};
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int f = blockIdx.x;
+	if (threadIdx.x < 2) { range_lo[threadIdx.x] = 255; range_hi[threadIdx.x] = 0; range_bad[threadIdx.x] = 0; }
+	if (threadIdx.x == 0) { buf_x[0] = 0.0; buf_y[0] = 0.0; }
+	blur_to_double(wstrips + (size_t) f * w, buf_x + 1, w, taps, tiny);
+	blur_to_double(hstrips + (size_t) f * h, buf_y + 1, h, taps, tiny);
+	__syncthreads();
+	for (int ax = 0; ax < 2; ax++) {                     // exactness certificate (see above)
+		const int n = ax ? h : w; const double *d = (ax ? buf_y : buf_x) + 1;
+		ExpRange r; r.lo = 255; r.hi = 0; r.bad = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) exp_range_add(r, (float) d[i]);
+		for (int o = 16; o > 0; o >>= 1) {
+			r.lo = min(r.lo, __shfl_xor_sync(0xffffffffu, r.lo, o)); r.hi = max(r.hi, __shfl_xor_sync(0xffffffffu, r.hi, o));
+			r.bad |= __shfl_xor_sync(0xffffffffu, r.bad, o);
+		}
+		if (lane == 0) { atomicMin(&range_lo[ax], r.lo); atomicMax(&range_hi[ax], r.hi); if (r.bad) atomicOr(&range_bad[ax], 1); }
+	}
+	__syncthreads();
+	if (threadIdx.x < 2) {
+		const int ax = threadIdx.x, n = ax ? h : w;
+		int lg = 0; while ((1 << lg) < n) lg++;
+		const int span = (range_hi[ax] >= range_lo[ax]) ? (range_hi[ax] - range_lo[ax]) : 0;
+		exact_ok[ax] = !force_serial && !range_bad[ax] && n <= 16 * (int) blockDim.x && (span < 29 - lg);
+	}
+	__syncthreads();
+	const bool ok_x = exact_ok[0], ok_y = exact_ok[1];
+	if (lane == 0 && warp < 2 && !(warp ? ok_y : ok_x))  // serial total for a strip that failed the certificate (syncdetector.c:81-82)
+		totalf[warp] = __double2float_rn(strip_total((warp ? buf_y : buf_x) + 1, warp ? h : w));
+	if (ok_x) exact_prefix(buf_x, w, warp_tot);
+	if (ok_y) exact_prefix(buf_y, h, warp_tot);
+	__syncthreads();
+	if (threadIdx.x < 2 && exact_ok[threadIdx.x]) totalf[threadIdx.x] = __double2float_rn(threadIdx.x ? buf_y[h] : buf_x[w]);   // findbestfit takes a float
+	__syncthreads();
+	double *rec = prep + (size_t) f * fs_prep_stride(w, h);
+	const int nbody = w + h + 2;
+	for (int i = threadIdx.x; i < nbody; i += blockDim.x) rec[i] = smem_d[i];
+	if (threadIdx.x == 0) {
+		rec[nbody + 0] = ok_x ? 1.0 : 0.0; rec[nbody + 1] = ok_y ? 1.0 : 0.0;
+		rec[nbody + 2] = (double) totalf[0]; rec[nbody + 3] = (double) totalf[1];
+	}
+}
+
+__device__ __forceinline__ void fs_prefetch_record(double *dst, const double *__restrict__ src, int count) {
+	for (int i = threadIdx.x; i < count; i += blockDim.x) __pipeline_memcpy_async(dst + i, src + i, sizeof(double));
+	__pipeline_commit();
+}
+
+__global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const double *__restrict__ prep, int nbuf,
+                                                           int w, int h, int minsize_x, int minsize_y, int nframes,
+                                                           SyncState *state, double *__restrict__ chain_scratch,
+                                                           tsdrgpu_frame_result_t *results) {
+	extern __shared__ double smem_d[];
+	const int rec_len = (int) fs_prep_stride(w, h), nbody = w + h + 2;
+	__shared__ int cand[2][5];           // strip sizes tried per axis, -1 = skipped
+	__shared__ Best warp_best[10][FS_SYNC_THREADS / 32];
+	__shared__ Best cand_best[2][5];
+	__shared__ SyncState st;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
 	auto list_candidates = [&]() {       // clamp the carried strip size, list the sizes to try (syncdetector.c:73-77, 60-69, 88-93)
@@ -469,45 +529,25 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const float *__res
 		}
 	};
 	if (threadIdx.x == 0) { st = *state; list_candidates(); }
+	fs_prefetch_record(smem_d, prep, rec_len);
 
 	for (int f = 0; f < nframes; f++) {
-		if (threadIdx.x < 2) { range_lo[threadIdx.x] = 255; range_hi[threadIdx.x] = 0; range_bad[threadIdx.x] = 0; }
-		blur_to_double(wstrips + (size_t) f * w, buf_x + 1, w, taps, tiny);
-		blur_to_double(hstrips + (size_t) f * h, buf_y + 1, h, taps, tiny);
-		__syncthreads();
-		// exactness certificate (see above)
-		for (int ax = 0; ax < 2; ax++) {
-			const int n = ax ? h : w; const double *d = (ax ? buf_y : buf_x) + 1;
-			ExpRange r; r.lo = 255; r.hi = 0; r.bad = 0;
-			for (int i = threadIdx.x; i < n; i += blockDim.x) exp_range_add(r, (float) d[i]);
-			for (int o = 16; o > 0; o >>= 1) {
-				r.lo = min(r.lo, __shfl_xor_sync(0xffffffffu, r.lo, o)); r.hi = max(r.hi, __shfl_xor_sync(0xffffffffu, r.hi, o));
-				r.bad |= __shfl_xor_sync(0xffffffffu, r.bad, o);
-			}
-			if (lane == 0) { atomicMin(&range_lo[ax], r.lo); atomicMax(&range_hi[ax], r.hi); if (r.bad) atomicOr(&range_bad[ax], 1); }
-		}
-		__syncthreads();
-		if (threadIdx.x < 2) {
-			const int ax = threadIdx.x, n = ax ? h : w;
-			int lg = 0; while ((1 << lg) < n) lg++;
-			const int span = (range_hi[ax] >= range_lo[ax]) ? (range_hi[ax] - range_lo[ax]) : 0;
-			exact_ok[ax] = !force_serial && !range_bad[ax] && n <= 16 * (int) blockDim.x && (span < 29 - lg);
-		}
-		__syncthreads();
-		const bool ok_x = exact_ok[0], ok_y = exact_ok[1];
-		// serial fallback for strips that fail the certificate (window sums go to the global scratch)
-		if ((!ok_x || !ok_y) && lane == 0 && warp < 12) {
-			if (warp < 2) { if (!(warp ? ok_y : ok_x)) totalf[warp] = __double2float_rn(strip_total((warp ? buf_y : buf_x) + 1, warp ? h : w)); }
-			else {
-				const int ax = (warp - 2) / 5, t = (warp - 2) % 5;
+		double *rec = smem_d + (size_t) (nbuf == 2 ? (f & 1) : 0) * rec_len;
+		__pipeline_wait_prior(0);
+		__syncthreads();                                 // record f is in shared memory; the other buffer is no longer read
+		if (nbuf == 2 && f + 1 < nframes) fs_prefetch_record(smem_d + (size_t) ((f + 1) & 1) * rec_len, prep + (size_t) (f + 1) * rec_len, rec_len);
+		double *buf_x = rec, *buf_y = rec + (w + 1);     // prefix sums S[0..n], or the blurred strip in [1..n]
+		const bool ok_x = rec[nbody + 0] != 0.0, ok_y = rec[nbody + 1] != 0.0;
+		const float tot_x = (float) rec[nbody + 2], tot_y = (float) rec[nbody + 3];
+		// serial chains for strips that failed the certificate (window sums go to the global scratch)
+		if ((!ok_x || !ok_y)) {
+			if (lane == 0 && warp < 10) {
+				const int ax = warp / 5, t = warp % 5;
 				const int strip = cand[ax][t];
-				if (strip > 0 && !(ax ? ok_y : ok_x)) window_sums((ax ? buf_y : buf_x) + 1, ax ? h : w, strip, chain_scratch + (size_t) (warp - 2) * FS_MAX_STRIP);
+				if (strip > 0 && !(ax ? ok_y : ok_x)) window_sums((ax ? buf_y : buf_x) + 1, ax ? h : w, strip, chain_scratch + (size_t) warp * FS_MAX_STRIP);
 			}
+			__syncthreads();
 		}
-		if (ok_x) exact_prefix(buf_x, w, warp_tot);
-		if (ok_y) exact_prefix(buf_y, h, warp_tot);
-		if (threadIdx.x < 2 && exact_ok[threadIdx.x]) totalf[threadIdx.x] = __double2float_rn(threadIdx.x ? buf_y[h] : buf_x[w]);   // findbestfit takes a float
-		__syncthreads();
 		// score every window of every candidate; every thread owns a slice of the start positions
 		for (int ci = 0; ci < 10; ci++) {
 			const int ax = ci / 5, t = ci % 5;
@@ -517,7 +557,7 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const float *__res
 			const bool ok = ax ? ok_y : ok_x;
 			const double *S = ax ? buf_y : buf_x;
 			const double *cs = chain_scratch + (size_t) ci * FS_MAX_STRIP;
-			const double total = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
+			const double total = (double) (ax ? tot_y : tot_x), n_out = (double) (size - strip), n_in = (double) strip;
 			Best b; b.score = -INFINITY; b.e = 0x7fffffff;
 			for (int e = threadIdx.x; e < size; e += blockDim.x) {
 				const double c = ok ? window_from_prefix(S, size, e, strip) : cs[e];
@@ -542,7 +582,7 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const float *__res
 				// e = 0 is the starting value of the reference's running maximum even when it is NaN
 				const bool ok = ax ? ok_y : ok_x;
 				const double c0s = ok ? window_from_prefix(ax ? buf_y : buf_x, size, 0, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP];
-				const double s0 = fit_score((double) totalf[ax], c0s, (double) (size - strip), (double) strip);
+				const double s0 = fit_score((double) (ax ? tot_y : tot_x), c0s, (double) (size - strip), (double) strip);
 				if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
 			}
 			cand_best[ax][t] = r;
@@ -585,6 +625,7 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const float *__res
 			list_candidates();                                  // for the next frame
 		}
 		__syncthreads();
+		if (nbuf != 2 && f + 1 < nframes) fs_prefetch_record(smem_d, prep + (size_t) (f + 1) * rec_len, rec_len);
 	}
 	if (threadIdx.x == 0) {
 		// auto-gain fields of the state are owned by the auto-gain epilogue: write back the sync part only
@@ -688,6 +729,7 @@ struct tsdrgpu_framestage {
 	double *d_chain;
 	float taps[5];
 	int overlap, phase, side_pending;
+	double *d_prep; size_t prep_cap;             // fs_sync_prep's per-frame records (consumed by fs_sync on the same stream)
 	cudaStream_t s_side;
 	cudaEvent_t ev_ready[2];                     // main: collapse of this phase done -> side may start
 	cudaEvent_t ev_done[2];                      // side: sync + emit of this phase done -> buffers of the phase are free
@@ -708,6 +750,13 @@ static int fs_reserve(tsdrgpu_framestage *fs, int nframes, size_t n, int w, int 
 		float **bufs[] = {&fs->d_wstrips[0], &fs->d_wstrips[1], &fs->d_hstrips[0], &fs->d_hstrips[1]};
 		for (float **b : bufs) { if (*b) CU_TRY(ctx, cudaFree(*b)); CU_TRY(ctx, cudaMalloc(b, sizeof(float) * sneed)); }
 		fs->strips_cap = sneed;
+	}
+	const size_t pneed = (size_t) nframes * fs_prep_stride(w, h);
+	if (fs->prep_cap < pneed) {
+		CU_TRY(ctx, cudaDeviceSynchronize());
+		if (fs->d_prep) CU_TRY(ctx, cudaFree(fs->d_prep));
+		CU_TRY(ctx, cudaMalloc(&fs->d_prep, sizeof(double) * pneed));
+		fs->prep_cap = pneed;
 	}
 	if (fs->batch_cap < nframes) {
 		CU_TRY(ctx, cudaDeviceSynchronize());
@@ -776,7 +825,7 @@ void tsdrgpu_framestage_destroy(tsdrgpu_framestage_t *fs) {
 	cudaDeviceSynchronize();
 	void *ptrs[] = {fs->d_screen, fs->d_state, fs->d_t1, fs->d_t2[0], fs->d_t2[1], fs->d_wstrips[0], fs->d_wstrips[1], fs->d_hstrips[0],
 	                fs->d_hstrips[1], fs->d_pmin, fs->d_pmax, fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results[0],
-	                fs->d_results[1], fs->d_chain};
+	                fs->d_results[1], fs->d_chain, fs->d_prep};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	cudaStreamDestroy(fs->s_side);
 	for (int i = 0; i < 2; i++) { cudaEventDestroy(fs->ev_ready[i]); cudaEventDestroy(fs->ev_done[i]); }
@@ -860,8 +909,12 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	const double fresh = 1.0 - (double) motionblur;      // dsp.c:29
 	const int minsize_x = (int) (w * 0.05f), minsize_y = (int) (h * 0.01f);   // syncdetector.c:178-179
 	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
-	const size_t sync_smem = sizeof(double) * ((size_t) w + h + 2);
-	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(double) * (2 * FS_MAX_STRIP + 2))));
+	const size_t prep_smem = sizeof(double) * ((size_t) w + h + 2);
+	const size_t rec_bytes = sizeof(double) * fs_prep_stride(w, h);
+	const int sync_nbuf = (2 * rec_bytes <= 96 * 1024) ? 2 : 1;     // prefetch one frame ahead while two records fit beside the main stream's CTAs
+	const size_t sync_smem = rec_bytes * sync_nbuf;
+	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(double) * (2 * FS_MAX_STRIP + 2))));
+	CU_TRY(ctx, cudaFuncSetAttribute(fs_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(double) * (2 * FS_MAX_STRIP + 2 + FS_PREP_HDR))));
 	const int force_serial = getenv("TSDRGPU_SYNC_SERIAL") ? 1 : 0;      // test hook: always take the serial-chain path
 	const unsigned gx = grid_for(n, ctx->sm_count, 4);
 	const size_t total = (size_t) nframes * n;
@@ -873,8 +926,10 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 			CU_TRY(ctx, cudaEventRecord(fs->ev_ready[ph], stream));
 			CU_TRY(ctx, cudaStreamWaitEvent(s2, fs->ev_ready[ph], 0));
 		}
-		KL(ctx, "fs_sync", s2, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, s2>>>(fs->d_wstrips[ph], fs->d_hstrips[ph], w, h, minsize_x, minsize_y, nframes,
-			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], fs->d_state, fs->d_chain, force_serial, d_results));
+		KL(ctx, "fs_sync_prep", s2, fs_sync_prep<<<nframes, FS_SYNC_THREADS, prep_smem, s2>>>(fs->d_wstrips[ph], fs->d_hstrips[ph], w, h,
+			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], force_serial, fs->d_prep));
+		KL(ctx, "fs_sync", s2, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, s2>>>(fs->d_prep, sync_nbuf, w, h, minsize_x, minsize_y, nframes,
+			fs->d_state, fs->d_chain, d_results));
 		return TSDRGPU_OK;
 	};
 	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed
