@@ -22,6 +22,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <cuda_pipeline.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -244,8 +246,16 @@ __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in,
 		const int x = blockIdx.x * CL_COLS + threadIdx.x;
 		if (threadIdx.x < CL_COLS && x < w) {
 			float acc = 0.0f;
-			#pragma unroll 8
-			for (int y = 0; y < h; y++) acc = __fadd_rn(acc, __ldg(src + (size_t) y * w + x));
+			const float *col = src + x;
+			int y = 0;
+			for (; y + 16 <= h; y += 16) {                   // 16 independent loads in flight, then the ordered adds
+				float v[16];
+				#pragma unroll
+				for (int u = 0; u < 16; u++) v[u] = __ldg(col + (size_t) (y + u) * w);
+				#pragma unroll
+				for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
+			}
+			for (; y < h; y++) acc = __fadd_rn(acc, __ldg(col + (size_t) y * w));
 			wbuf[(size_t) f * w + x] = acc;
 		}
 		return;
@@ -503,34 +513,53 @@ __device__ __forceinline__ void fs_prefetch_record(double *dst, const double *__
 	__pipeline_commit();
 }
 
-__global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const double *__restrict__ prep, int nbuf,
-                                                           int w, int h, int minsize_x, int minsize_y, int nframes,
-                                                           SyncState *state, double *__restrict__ chain_scratch,
-                                                           tsdrgpu_frame_result_t *results) {
+// fs_sync runs as ONE thread-block cluster of FS_SEL_CLUSTER CTAs (8 SMs).  Scoring a window costs two correctly rounded
+// double divisions (~56 FP64 instructions) and a frame has ~9300 windows (5 strip sizes x 2 axes): on one SM that is FP64-
+// pipe bound at ~4 us per frame.  The cluster splits the windows in warp-sized units over its 8 SMs; per-CTA maxima travel
+// to CTA 0 through distributed shared memory, CTA 0 picks the strip size / updates dx and broadcasts the next frame's
+// candidate sizes the same way: two cluster barriers per frame.
+constexpr int FS_SEL_THREADS = 256, FS_SEL_CLUSTER = 8, FS_SEL_WARPS = FS_SEL_THREADS / 32;
+
+__global__ void __cluster_dims__(FS_SEL_CLUSTER, 1, 1) __launch_bounds__(FS_SEL_THREADS)
+fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, int minsize_y, int nframes,
+        SyncState *state, double *__restrict__ chain_scratch, tsdrgpu_frame_result_t *results) {
+	cg::cluster_group cluster = cg::this_cluster();
+	const unsigned rank = cluster.block_rank();
 	extern __shared__ double smem_d[];
 	const int rec_len = (int) fs_prep_stride(w, h), nbody = w + h + 2;
-	__shared__ int cand[2][5];           // strip sizes tried per axis, -1 = skipped
-	__shared__ Best warp_best[10][FS_SYNC_THREADS / 32];
+	__shared__ int cand[2][5];                           // strip sizes tried per axis, -1 = skipped (written by CTA 0)
+	__shared__ Best warp_best[FS_SEL_WARPS][10];
+	__shared__ Best rank_best[FS_SEL_CLUSTER][10];       // CTA 0's copy is the one that is used (written remotely)
 	__shared__ Best cand_best[2][5];
-	__shared__ SyncState st;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+	__shared__ SyncState st;                             // CTA 0
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-	auto list_candidates = [&]() {       // clamp the carried strip size, list the sizes to try (syncdetector.c:73-77, 60-69, 88-93)
-		for (int ax = 0; ax < 2; ax++) {
-			const int size = ax ? h : w;
-			int minsize = ax ? minsize_y : minsize_x;
-			if (minsize < 1) minsize = 1;
-			const int half = size >> 1;
-			int &cur = ax ? st.y_strip : st.x_strip;
-			if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
-			const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
-			cand[ax][0] = cur;
-			for (int t = 1; t < 5; t++) cand[ax][t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
+	// clamp the carried strip size, list the sizes to try (syncdetector.c:73-77, 60-69, 88-93), tell every CTA
+	auto list_candidates = [&](int ax) {
+		const int size = ax ? h : w;
+		int minsize = ax ? minsize_y : minsize_x;
+		if (minsize < 1) minsize = 1;
+		const int half = size >> 1;
+		int &cur = ax ? st.y_strip : st.x_strip;
+		if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
+		const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
+		int vals[5];
+		vals[0] = cur;
+		for (int t = 1; t < 5; t++) vals[t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
+		for (unsigned r = 0; r < FS_SEL_CLUSTER; r++) {
+			int *rc = cluster.map_shared_rank(&cand[0][0], r);
+			for (int t = 0; t < 5; t++) rc[ax * 5 + t] = vals[t];
 		}
 	};
-	if (threadIdx.x == 0) { st = *state; list_candidates(); }
+	if (rank == 0) {
+		if (threadIdx.x == 0) st = *state;
+		__syncthreads();
+		if (threadIdx.x == 0 || threadIdx.x == 32) list_candidates(threadIdx.x >> 5);
+	}
 	fs_prefetch_record(smem_d, prep, rec_len);
+	cluster.sync();
 
+	const int units_x = (w + 31) >> 5, units_y = (h + 31) >> 5, units = 5 * (units_x + units_y);
 	for (int f = 0; f < nframes; f++) {
 		double *rec = smem_d + (size_t) (nbuf == 2 ? (f & 1) : 0) * rec_len;
 		__pipeline_wait_prior(0);
@@ -539,57 +568,68 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const double *__re
 		double *buf_x = rec, *buf_y = rec + (w + 1);     // prefix sums S[0..n], or the blurred strip in [1..n]
 		const bool ok_x = rec[nbody + 0] != 0.0, ok_y = rec[nbody + 1] != 0.0;
 		const float tot_x = (float) rec[nbody + 2], tot_y = (float) rec[nbody + 3];
-		// serial chains for strips that failed the certificate (window sums go to the global scratch)
-		if ((!ok_x || !ok_y)) {
-			if (lane == 0 && warp < 10) {
-				const int ax = warp / 5, t = warp % 5;
-				const int strip = cand[ax][t];
-				if (strip > 0 && !(ax ? ok_y : ok_x)) window_sums((ax ? buf_y : buf_x) + 1, ax ? h : w, strip, chain_scratch + (size_t) warp * FS_MAX_STRIP);
+		// serial chains for strips that failed the certificate: chain ci on CTA ci % 8, window sums to the global scratch
+		if (!ok_x || !ok_y) {
+			if (lane == 0) {
+				const int ci = (int) rank + FS_SEL_CLUSTER * warp;
+				if (ci < 10) {
+					const int ax = ci / 5, strip = cand[ax][ci % 5];
+					if (strip > 0 && !(ax ? ok_y : ok_x)) window_sums((ax ? buf_y : buf_x) + 1, ax ? h : w, strip, chain_scratch + (size_t) ci * FS_MAX_STRIP);
+				}
 			}
-			__syncthreads();
+			cluster.sync();
 		}
-		// score every window of every candidate; every thread owns a slice of the start positions
-		for (int ci = 0; ci < 10; ci++) {
-			const int ax = ci / 5, t = ci % 5;
-			const int strip = cand[ax][t];
+		// score every window of every candidate: warp-sized units dealt round-robin over the cluster's warps
+		if (lane < 10) { Best z; z.score = -INFINITY; z.e = 0x7fffffff; warp_best[warp][lane] = z; }
+		__syncwarp();
+		for (int u = (int) rank * FS_SEL_WARPS + warp; u < units; u += FS_SEL_CLUSTER * FS_SEL_WARPS) {
+			int ci, blk;
+			if (u < 5 * units_x) { ci = u / units_x; blk = u - ci * units_x; }
+			else { const int u2 = u - 5 * units_x; ci = u2 / units_y; blk = u2 - ci * units_y; ci += 5; }
+			const int ax = ci / 5, strip = cand[ax][ci % 5];
 			if (strip <= 0) continue;
-			const int size = ax ? h : w;
-			const bool ok = ax ? ok_y : ok_x;
-			const double *S = ax ? buf_y : buf_x;
-			const double *cs = chain_scratch + (size_t) ci * FS_MAX_STRIP;
-			const double total = (double) (ax ? tot_y : tot_x), n_out = (double) (size - strip), n_in = (double) strip;
+			const int size = ax ? h : w, e = (blk << 5) + lane;
 			Best b; b.score = -INFINITY; b.e = 0x7fffffff;
-			for (int e = threadIdx.x; e < size; e += blockDim.x) {
-				const double c = ok ? window_from_prefix(S, size, e, strip) : cs[e];
-				const double sc = fit_score(total, c, n_out, n_in);
+			if (e < size) {
+				const bool ok = ax ? ok_y : ok_x;
+				const double c = ok ? window_from_prefix(ax ? buf_y : buf_x, size, e, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP + e];
+				const double sc = fit_score((double) (ax ? tot_y : tot_x), c, (double) (size - strip), (double) strip);
 				if (sc > b.score) { b.score = sc; b.e = e; }
 			}
 			for (int o = 16; o > 0; o >>= 1) {
 				Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
 				b = best_merge(b, other);
 			}
-			if (lane == 0) warp_best[ci][warp] = b;
+			if (lane == 0) warp_best[warp][ci] = best_merge(warp_best[warp][ci], b);
 		}
 		__syncthreads();
 		if (threadIdx.x < 10) {
-			const int ci = threadIdx.x, ax = ci / 5, t = ci % 5;
-			const int strip = cand[ax][t];
-			Best r; r.score = -1.0; r.e = -1;
-			if (strip > 0) {
-				const int size = ax ? h : w;
-				r = warp_best[ci][0];
-				for (int k = 1; k < nwarps; k++) r = best_merge(r, warp_best[ci][k]);
-				// e = 0 is the starting value of the reference's running maximum even when it is NaN
-				const bool ok = ax ? ok_y : ok_x;
-				const double c0s = ok ? window_from_prefix(ax ? buf_y : buf_x, size, 0, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP];
-				const double s0 = fit_score((double) (ax ? tot_y : tot_x), c0s, (double) (size - strip), (double) strip);
-				if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
-			}
-			cand_best[ax][t] = r;
+			Best r = warp_best[0][threadIdx.x];
+			for (int k = 1; k < FS_SEL_WARPS; k++) r = best_merge(r, warp_best[k][threadIdx.x]);
+			Best *dst = cluster.map_shared_rank(&rank_best[0][0], 0);
+			dst[rank * 10 + threadIdx.x] = r;
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			for (int ax = 0; ax < 2; ax++) {
+		cluster.sync();
+		if (rank == 0) {
+			if (threadIdx.x < 10) {
+				const int ci = threadIdx.x, ax = ci / 5, t = ci % 5;
+				const int strip = cand[ax][t];
+				Best r; r.score = -1.0; r.e = -1;
+				if (strip > 0) {
+					const int size = ax ? h : w;
+					r = rank_best[0][ci];
+					for (int k = 1; k < FS_SEL_CLUSTER; k++) r = best_merge(r, rank_best[k][ci]);
+					// e = 0 is the starting value of the reference's running maximum even when it is NaN
+					const bool ok = ax ? ok_y : ok_x;
+					const double c0s = ok ? window_from_prefix(ax ? buf_y : buf_x, size, 0, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP];
+					const double s0 = fit_score((double) (ax ? tot_y : tot_x), c0s, (double) (size - strip), (double) strip);
+					if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
+				}
+				cand_best[ax][t] = r;
+			}
+			__syncthreads();
+			if (threadIdx.x == 0 || threadIdx.x == 32) {         // one thread per axis
+				const int ax = threadIdx.x >> 5;
 				const int size = ax ? h : w;
 				const double lowpass = ax ? 0.1 : 0.9;          // FRAMERATE_DX_LOWPASS_COEFF_* (syncdetector.c:15-16)
 				int &dx = ax ? st.y_dx : st.x_dx; int &vx = ax ? st.y_vx : st.x_vx;
@@ -613,21 +653,24 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS, 2) fs_sync(const double *__re
 				const int moved = dx - before;
 				vx = (moved > h2) ? (size - moved) : ((moved < -h2) ? (-size - moved) : moved);
 				absvx = (vx >= 0) ? vx : -vx;
+				tsdrgpu_frame_result_t *r = results + f;   // the auto-gain fields of the record belong to fs_results_autogain
+				if (ax == 0) {
+					// frameratepll bookkeeping (syncdetector.c:134-139); the refreshrate write-back is the host's
+					st.avg_speed = __dadd_rn(__dmul_rn(st.avg_speed, 0.99), __dmul_rn(0.01, (double) st.x_vx));
+					st.pll_state = (st.avg_speed < 0.5 && st.avg_speed > -0.5) ? 1 : 0;
+					r->x_dx = st.x_dx; r->x_vx = st.x_vx; r->x_absvx = st.x_absvx; r->x_stripsize = st.x_strip;
+					r->avg_speed = st.avg_speed; r->pll_state = st.pll_state;
+					r->autogain_report = 0; r->reserved = 0;
+				} else {
+					r->y_dx = st.y_dx; r->y_vx = st.y_vx; r->y_absvx = st.y_absvx; r->y_stripsize = st.y_strip;
+				}
+				list_candidates(ax);                              // for the next frame
 			}
-			// frameratepll bookkeeping (syncdetector.c:134-139); the refreshrate write-back is the host's
-			st.avg_speed = __dadd_rn(__dmul_rn(st.avg_speed, 0.99), __dmul_rn(0.01, (double) st.x_vx));
-			st.pll_state = (st.avg_speed < 0.5 && st.avg_speed > -0.5) ? 1 : 0;
-			tsdrgpu_frame_result_t *r = results + f;   // the auto-gain fields of the record belong to fs_results_autogain
-			r->x_dx = st.x_dx; r->x_vx = st.x_vx; r->x_absvx = st.x_absvx; r->x_stripsize = st.x_strip;
-			r->y_dx = st.y_dx; r->y_vx = st.y_vx; r->y_absvx = st.y_absvx; r->y_stripsize = st.y_strip;
-			r->avg_speed = st.avg_speed; r->pll_state = st.pll_state;
-			r->autogain_report = 0; r->reserved = 0;
-			list_candidates();                                  // for the next frame
 		}
-		__syncthreads();
+		cluster.sync();
 		if (nbuf != 2 && f + 1 < nframes) fs_prefetch_record(smem_d, prep + (size_t) (f + 1) * rec_len, rec_len);
 	}
-	if (threadIdx.x == 0) {
+	if (rank == 0 && threadIdx.x == 0) {
 		// auto-gain fields of the state are owned by the auto-gain epilogue: write back the sync part only
 		state->x_dx = st.x_dx; state->x_vx = st.x_vx; state->x_absvx = st.x_absvx; state->x_strip = st.x_strip;
 		state->y_dx = st.y_dx; state->y_vx = st.y_vx; state->y_absvx = st.y_absvx; state->y_strip = st.y_strip;
@@ -928,7 +971,7 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 		}
 		KL(ctx, "fs_sync_prep", s2, fs_sync_prep<<<nframes, FS_SYNC_THREADS, prep_smem, s2>>>(fs->d_wstrips[ph], fs->d_hstrips[ph], w, h,
 			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], force_serial, fs->d_prep));
-		KL(ctx, "fs_sync", s2, fs_sync<<<1, FS_SYNC_THREADS, sync_smem, s2>>>(fs->d_prep, sync_nbuf, w, h, minsize_x, minsize_y, nframes,
+		KL(ctx, "fs_sync", s2, fs_sync<<<FS_SEL_CLUSTER, FS_SEL_THREADS, sync_smem, s2>>>(fs->d_prep, sync_nbuf, w, h, minsize_x, minsize_y, nframes,
 			fs->d_state, fs->d_chain, d_results));
 		return TSDRGPU_OK;
 	};

@@ -217,9 +217,12 @@ __global__ void __launch_bounds__(256) rs_fixup(const float *__restrict__ in, fl
 		} else has_a[b] = 0;
 	}
 	if (threadIdx.x == 0) bank_in[0] = *contrib_state;
-	__syncthreads();
+	int missing = 0;
+	for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x) missing |= !has_a[b];      // own writes
+	missing = __syncthreads_or(missing);
 	// 2. blocks without any A sample pass the incoming bank through (serial, practically never taken)
-	if (threadIdx.x == 0) {
+	if (threadIdx.x == 0 && !missing) *contrib_state = bank_in[nblocks];
+	if (threadIdx.x == 0 && missing) {
 		for (unsigned b = 0; b < nblocks; b++) {
 			if (has_a[b]) continue;
 			const RsBlock B = blocks[b];
