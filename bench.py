@@ -269,6 +269,7 @@ def run_ours(args):
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
     collect_profile(gpu)
     prof_steps = 3
+    caps_before_prof = step.captures
     for _ in range(prof_steps):
         step()
     prof = collect_profile(gpu)
@@ -362,25 +363,34 @@ def run_ours(args):
     ratio = w * HEIGHT * FV / FS
     # algorithmic bytes per launch (DESIGN.md "algorithmic bytes"), per kernel
     n_pix = step.n * FRAMES_PER_STEP
-    alg = {
+    prof_caps = (step.captures - caps_before_prof) / prof_steps          # captures autocorrelated per profiled step
+    alg = {   # ALGORITHMIC bytes per launch
         "rs_main": pairs * (8 + 4 * ratio),                      # 8 B per IQ pair in + 4 B per pixel out
-        "fs_minmax": 4 * n_pix, "fs_normalise": 8 * n_pix, "fs_timelowpass": 8 * n_pix, "fs_collapse": 4 * n_pix, "fs_shift": 8 * n_pix,
-        "demod_kernel": None, "fft_pass_kernel": 16 * (1 << 20),
+        "fs_minmax": 4 * n_pix, "fs_normalise": 8 * n_pix, "fs_timelowpass": 8 * n_pix, "fs_norm_lowpass": 8 * n_pix,
+        "fs_collapse": 4 * n_pix, "fs_shift": 8 * n_pix, "demod_kernel": 12 * pairs,
+        # one FFT pass reads and writes every complex point once; a launch covers all captures of the step (grid.y);
+        # a step's autocorrelations are 4 launches (2 passes forward, 2 inverse)
+        "fft_pass_kernel": 16 * (1 << 20) * prof_caps * 4 / max(1.0, prof.get("fft_pass_kernel", (0, 4 * prof_steps))[1] / prof_steps),
     }
+    label = {"rs_main": "rs_main<IQ> (fused demod+resample)", "fft_pass_kernel": "fft_pass_kernel (one pass over every capture of the step)"}
     total_prof = sum(t for t, _ in prof.values()) or 1.0
     kernels = {k: {"ms_per_step": t / prof_steps, "launches_per_step": c / prof_steps, "share": t / total_prof} for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     dom = next(iter(kernels))
-    roof_k = "rs_main"                                           # the kernel BASELINE configs[1] names
-    t_rs, c_rs = prof.get(roof_k, (0.0, 0))
-    achieved = alg[roof_k] / (t_rs / c_rs * 1e-3) / 1e9 if c_rs else None
-    roofline = {"kernel": "rs_main<IQ> (fused demod+resample)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # the roofline object is for the dominant kernel of the step among the bandwidth kernels; fs_sync (one cluster of 8
+    # CTAs, FP64-latency bound by construction) is listed in per_kernel but has no bandwidth roofline
+    roof_k = next((k for k in kernels if alg.get(k)), "rs_main")
+    t_k, c_k = prof.get(roof_k, (0.0, 0))
+    achieved = alg[roof_k] / (t_k / c_k * 1e-3) / 1e9 if c_k else None
+    roofline = {"kernel": label.get(roof_k, roof_k), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[roof_k], "avg_launch_ms": (t_rs / c_rs) if c_rs else None,
+                "algorithmic_bytes_per_launch": alg[roof_k], "avg_launch_ms": (t_k / c_k) if c_k else None,
                 "dominant_kernel_by_time": dom,
-                "per_kernel": {k: dict(v, **({"achieved_gbs": alg[k] * v["launches_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9} if alg.get(k) else {})) for k, v in kernels.items()}}
+                "per_kernel": {k: dict(v, **({"achieved_gbs": alg[k] * v["launches_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9,
+                                              "frac": alg[k] * v["launches_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9 / peak} if alg.get(k) else {})) for k, v in kernels.items()}}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-        roofline["traffic"] = tr.get("rs_main_dram_bytes_per_launch")
+        roofline["traffic"] = tr.get(roof_k, {}).get("dram_bytes_per_launch")
+        roofline["traffic_source"] = tr.get(roof_k, {}).get("source")
     except Exception:
         pass
     value = world * args.steps * pairs / (ms_total * 1e-3) / 1e6

@@ -301,6 +301,11 @@ TSDRGPU_API int  tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipel
 TSDRGPU_API void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p);
 /* == process(buf, items_count, ctx, samples_dropped): returns once h_iq has been read (it may then be reused) */
 TSDRGPU_API int  tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped);
+/* The same with the samples still in the front end's wire format: the block crosses PCIe as 1 or 2
+ * bytes per component and is converted on the device to exactly the floats TSDRPlugin_RawFile.c:241-261 would have
+ * produced on the host.  fmt uses the RawFile plugin's own numbering (TSDRPlugin_RawFile.c:29-33). */
+enum { TSDRGPU_FMT_FLOAT = 0, TSDRGPU_FMT_INT8 = 1, TSDRGPU_FMT_INT16 = 2, TSDRGPU_FMT_UINT8 = 3, TSDRGPU_FMT_UINT16 = 4 };
+TSDRGPU_API int  tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_samples, int fmt, uint64_t items_count, int64_t samples_dropped);
 TSDRGPU_API int  tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p);            /* waits for the GPU and for every pending callback */
 TSDRGPU_API int  tsdrgpu_pipeline_set_param_int(tsdrgpu_pipeline_t *p, int id, uint32_t value);
 TSDRGPU_API int  tsdrgpu_pipeline_set_resolution(tsdrgpu_pipeline_t *p, int height, double refreshrate);

@@ -13,6 +13,9 @@ ncu --set full --clock-control none --import-source on -k regex:rs_main -s 2 -c 
 # 3. the FFT pass kernel and the sync-search kernel
 ncu --set full --clock-control none --import-source on -k regex:fft_pass_kernel -s 8 -c 4 -o gpurun_out/${TAG}_fft_pass \
     python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_fft_pass.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fs_sync -s 2 -c 1 -o gpurun_out/${TAG}_fs_sync \
+ncu --set full --clock-control none --import-source on -k regex:fs_sync$ -s 2 -c 1 -o gpurun_out/${TAG}_fs_sync \
     python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_fs_sync.log 2>&1
+# 4. the rest of the frame stage, one launch each
+ncu --set full --clock-control none --import-source on -k 'regex:fs_collapse|fs_shift|fs_norm_lowpass|fs_minmax' -s 8 -c 4 -o gpurun_out/${TAG}_frame \
+    python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_frame.log 2>&1
 ls -la gpurun_out/

@@ -38,6 +38,7 @@ struct FftPass {
 	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
 	float scale;
 	int in_real, out_abs;
+	int exact0;                                         // the first three layers of this pass have eps = 0: plain DFT-8
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -191,7 +192,13 @@ __global__ void __launch_bounds__(512, 3) fft_pass_small(const float2 *in, float
 // Shared memory is unpadded; a line's point q lives at slot (q ^ swz(q)) ^ xc(line): swz permutes inside aligned groups
 // of 16 so that the stride-8 stores of stage 0 and the stride-p stores of the p = 8 stage hit 16 distinct bank pairs per
 // half-warp, and xc (a per-line constant < 16) does the same for the line-fastest thread maps of strided passes.
-__device__ __forceinline__ int swz(int q) { return q ^ ((q >> 4) & 7) ^ (((q >> 6) & 1) << 3); }
+// swz is linear over GF(2): swz(a ^ b) = swz(a) ^ swz(b).  Every index the kernel forms is a sum of two terms with
+// disjoint bits (i + m L/8, 8 i + m, j + m p), so slot = swz(thread part) ^ swz(m part) and the m part is a compile-time
+// constant: one XOR and one add per access on 32-bit shared addresses.
+__host__ __device__ constexpr int swz(int q) { return q ^ ((q >> 4) & 7) ^ (((q >> 6) & 1) << 3); }
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts2(unsigned addr, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
+__device__ __forceinline__ float2 lds2(unsigned addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory"); return v; }
 
 template <bool INV>
 __device__ __forceinline__ float2 twmul(float2 w, float2 x) {        // x * w (forward) or x * conj(w) (inverse)
@@ -256,6 +263,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	const bool active = tid < C * L8;                    // tiny bundles leave part of the last warp idle
 	// per-line slot constants (see above): xa for the buffer stage 0 writes, xb for the buffer the last stage reads
 	const int sha = (log2C >= 4) ? 0 : 3 - log2C, shb = (NSTAGES == 2 || log2C >= 4) ? sha : 4 - log2C;
+	const unsigned sbase = smem_addr(s);
 	float2 v[8];
 
 	// ---- stage 0: radix 8, p = 1, inputs x[i + m L/8] from global memory
@@ -273,19 +281,19 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 				#pragma unroll
 				for (int m = 0; m < 8; m++) v[m] = __ldg(gc + m * step);
 			}
-			bf8<INV>(v, stw - 1, 1);
+			if (P.exact0) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]); dft8(u, INV); }     // layers with eps = 0: plain DFT-8
+			else bf8<INV>(v, stw - 1, 1);
 		}
 		if (NSTAGES > 1) {
 			if (active) {
-				float2 *line = s + c * L;
-				const int xa = (c << sha) & 15;
+				const unsigned la = sbase + (unsigned) (c * L) * 8u, rb = (unsigned) (swz(8 * i) ^ ((c << sha) & 15)) * 8u;
 				#pragma unroll
-				for (int m = 0; m < 8; m++) line[swz(8 * i + m) ^ xa] = v[m];
+				for (int m = 0; m < 8; m++) sts2(la + (rb ^ (unsigned) (m * 8)), v[m]);
 			}
 			__syncthreads();
 		}
 	}
-	float2 *src = s, *dst = s + C * L;
+	unsigned src = sbase, dst = sbase + (unsigned) (C * L) * 8u;
 	// ---- middle radix-8 stages (shared -> shared, ping-pong)
 	#pragma unroll
 	for (int st = 0; st < (NMID > 0 ? NMID : 0); st++) {
@@ -293,18 +301,18 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 		const int i = tid & (L8 - 1), c = tid >> LOG2L8;
 		if (active) {
 			const int xa = (c << sha) & 15, xw = (st == NMID - 1) ? ((c << shb) & 15) : xa;
-			const float2 *line = src + c * L;
+			const unsigned lr = src + (unsigned) (c * L) * 8u, rb = (unsigned) (swz(i) ^ xa) * 8u;
 			#pragma unroll
-			for (int m = 0; m < 8; m++) v[m] = line[swz(i + m * L8) ^ xa];
+			for (int m = 0; m < 8; m++) v[m] = lds2(lr + (rb ^ (unsigned) (swz(m * L8) * 8)));
 			const int k = i & (p - 1);
 			bf8<INV>(v, stw + k - 1, p);
-			float2 *lo = dst + c * L;
 			const int j = ((i - k) << 3) + k;
+			const unsigned lw = dst + (unsigned) (c * L) * 8u, wb = (unsigned) (swz(j) ^ xw) * 8u;
 			#pragma unroll
-			for (int m = 0; m < 8; m++) lo[swz(j + m * p) ^ xw] = v[m];
+			for (int m = 0; m < 8; m++) sts2(lw + (wb ^ (unsigned) (swz(m * p) * 8)), v[m]);
 		}
 		__syncthreads();
-		float2 *t = src; src = dst; dst = t;
+		const unsigned t = src; src = dst; dst = t;
 	}
 	// ---- last stage: radix RLAST with p = L / RLAST, results X[i + m p] go to global memory
 	constexpr int NB = 8 / RLAST, PL = L / RLAST, LOG2PL = LOG2L - (RLAST == 8 ? 3 : (RLAST == 4 ? 2 : 1));
@@ -319,10 +327,9 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 		if (P.c_fast_out) { c = widx & (C - 1); i = widx >> log2C; } else { i = widx & (PL - 1); c = widx >> LOG2PL; }
 		float2 *w = v + it * RLAST;
 		if (NSTAGES > 1) {
-			const float2 *line = src + c * L;
-			const int xb = (c << shb) & 15;
+			const unsigned lr = src + (unsigned) (c * L) * 8u, rb = (unsigned) (swz(i) ^ ((c << shb) & 15)) * 8u;
 			#pragma unroll
-			for (int m = 0; m < RLAST; m++) w[m] = line[swz(i + m * PL) ^ xb];
+			for (int m = 0; m < RLAST; m++) w[m] = lds2(lr + (rb ^ (unsigned) (swz(m * PL) * 8)));
 			if (RLAST == 8) bf8<INV>(w, stw + i - 1, PL);
 			else if (RLAST == 4) bf4<INV>(w, stw + i - 1, PL);
 			else bf2<INV>(w, stw + i - 1, PL);
@@ -585,6 +592,8 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	}
 	const float2 *stw;
 	{ int rc = stage_table(ctx, P.log2L, l_base, eps_all, &stw); if (rc) return rc; }
+	P.exact0 = 1;
+	for (int sidx = 0; sidx < 3 && sidx < P.log2L; sidx++) if (eps_all && l_base + sidx < 40 && fabs(eps_all[l_base + sidx]) > 1e-10) P.exact0 = 0;
 	const size_t smem = sizeof(float2) * (size_t) total * (nstages >= 3 ? 2 : 1);
 	switch (P.log2L) {
 #define CASE(l) case l: if (inverse) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \

@@ -201,18 +201,24 @@ __global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__
 		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) {
 			float4 sc = reinterpret_cast<float4 *>(screen)[i];
 			float s4[4] = {sc.x, sc.y, sc.z, sc.w};
-			#pragma unroll 2
-			for (int f = 0; f < nframes; f++) {
-				const float4 q = __ldg(reinterpret_cast<const float4 *>(in + (size_t) f * n) + i);
-				const float raw[4] = {q.x, q.y, q.z, q.w};
-				const float2 p = s_par[f];
+			for (int f0 = 0; f0 < nframes; f0 += 4) {         // 4 frames of loads in flight, then the ordered updates
+				float4 q4[4];
 				#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const float v = px_is_marker(raw[u]) ? raw[u] : __fdiv_rn(__fsub_rn(raw[u], p.x), p.y);
-					const float old = __fmul_rn(s4[u], coeff);
-					s4[u] = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
+				for (int g = 0; g < 4; g++) if (f0 + g < nframes) q4[g] = __ldg(reinterpret_cast<const float4 *>(in + (size_t) (f0 + g) * n) + i);
+				#pragma unroll
+				for (int g = 0; g < 4; g++) {
+					const int f = f0 + g;
+					if (f >= nframes) break;
+					const float raw[4] = {q4[g].x, q4[g].y, q4[g].z, q4[g].w};
+					const float2 p = s_par[f];
+					#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const float v = px_is_marker(raw[u]) ? raw[u] : __fdiv_rn(__fsub_rn(raw[u], p.x), p.y);
+						const float old = __fmul_rn(s4[u], coeff);
+						s4[u] = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
+					}
+					reinterpret_cast<float4 *>(out + (size_t) f * n)[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
 				}
-				reinterpret_cast<float4 *>(out + (size_t) f * n)[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
 			}
 			reinterpret_cast<float4 *>(screen)[i] = make_float4(s4[0], s4[1], s4[2], s4[3]);
 		}
@@ -236,46 +242,81 @@ __global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__
 // ---------------------------------------------------------------- row / column collapse (dsp.c:96-110)
 // Sequential single-precision accumulation in raster order == per column: top to bottom; per row: left to right.
 // grid.x = column CTAs (128 columns each) followed by row CTAs (64 rows each); grid.y = frame.
-constexpr int CL_COLS = 128, CL_ROWS = 64, CL_TILE = 128;
+// Both sums are chains of dependent additions (1125 per column, 740 per row at cfg2) that may not be re-associated, so
+// the only parallelism is across chains; what has to be hidden is the memory latency inside a chain.  A CTA streams its
+// slab of the frame through a 4-stage ring in shared memory with cp.async (the next three stages are in flight while one
+// is summed), the owner threads read their operands from shared memory:
+//   column CTA: 128 columns x all rows, stages of 16 rows, thread c owns column c;
+//   row CTA:    32 rows x all columns, stages of 64 columns (pitch 65: conflict-free), lane r of warp 0 owns row r.
+// The frame is read twice, the second time mostly from L2 (the two kinds of CTA of a frame are neighbours in the grid).
+constexpr int CL_COLS = 128, CL_CROWS = 16, CL_ROWS = 32, CL_RCOLS = 64, CL_RPITCH = CL_RCOLS + 1, CL_STAGES = 4;
+constexpr int CL_SMEM_FLOATS = CL_STAGES * (CL_CROWS * CL_COLS > CL_ROWS * CL_RPITCH ? CL_CROWS * CL_COLS : CL_ROWS * CL_RPITCH);
 __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in, int w, int h, float *__restrict__ wbuf,
                                                    float *__restrict__ hbuf, int col_ctas) {
-	__shared__ float tile[CL_ROWS][CL_TILE + 1];
-	const int f = blockIdx.y;
+	__shared__ float ring[CL_SMEM_FLOATS];
+	const int f = blockIdx.y, tid = threadIdx.x;
 	const float *src = in + (size_t) f * w * h;
 	if ((int) blockIdx.x < col_ctas) {
-		const int x = blockIdx.x * CL_COLS + threadIdx.x;
-		if (threadIdx.x < CL_COLS && x < w) {
-			float acc = 0.0f;
-			const float *col = src + x;
-			int y = 0;
-			for (; y + 16 <= h; y += 16) {                   // 16 independent loads in flight, then the ordered adds
-				float v[16];
-				#pragma unroll
-				for (int u = 0; u < 16; u++) v[u] = __ldg(col + (size_t) (y + u) * w);
-				#pragma unroll
-				for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
+		const int x0 = blockIdx.x * CL_COLS, cols = min(CL_COLS, w - x0);
+		const int nit = (h + CL_CROWS - 1) / CL_CROWS;
+		auto issue = [&](int it) {
+			if (it < nit) {
+				float *dst = ring + (it % CL_STAGES) * (CL_CROWS * CL_COLS);
+				const int y0 = it * CL_CROWS, rows = min(CL_CROWS, h - y0);
+				for (int idx = tid; idx < rows * CL_COLS; idx += 256) {
+					const int r = idx / CL_COLS, c = idx % CL_COLS;
+					if (c < cols) __pipeline_memcpy_async(dst + idx, src + (size_t) (y0 + r) * w + x0 + c, sizeof(float));
+				}
 			}
-			for (; y < h; y++) acc = __fadd_rn(acc, __ldg(col + (size_t) y * w));
-			wbuf[(size_t) f * w + x] = acc;
+			__pipeline_commit();
+		};
+		for (int st = 0; st < CL_STAGES - 1; st++) issue(st);
+		float acc = 0.0f;
+		for (int it = 0; it < nit; it++) {
+			__pipeline_wait_prior(CL_STAGES - 2);
+			__syncthreads();                             // stage `it` has landed; the buffer of stage it-1 is free again
+			issue(it + CL_STAGES - 1);
+			if (tid < cols) {
+				const float *buf = ring + (it % CL_STAGES) * (CL_CROWS * CL_COLS) + tid;
+				const int rows = min(CL_CROWS, h - it * CL_CROWS);
+				if (rows == CL_CROWS) {
+					#pragma unroll
+					for (int r = 0; r < CL_CROWS; r++) acc = __fadd_rn(acc, buf[r * CL_COLS]);
+				} else for (int r = 0; r < rows; r++) acc = __fadd_rn(acc, buf[r * CL_COLS]);
+			}
 		}
+		if (tid < cols) wbuf[(size_t) f * w + x0 + tid] = acc;
 		return;
 	}
-	const int y0 = ((int) blockIdx.x - col_ctas) * CL_ROWS;
-	const int rows = min(CL_ROWS, h - y0);
+	const int y0 = ((int) blockIdx.x - col_ctas) * CL_ROWS, rows = min(CL_ROWS, h - y0);
+	const int nit = (w + CL_RCOLS - 1) / CL_RCOLS;
+	auto issue = [&](int it) {
+		if (it < nit) {
+			float *dst = ring + (it % CL_STAGES) * (CL_ROWS * CL_RPITCH);
+			const int c0 = it * CL_RCOLS, cols = min(CL_RCOLS, w - c0);
+			for (int idx = tid; idx < rows * CL_RCOLS; idx += 256) {
+				const int r = idx / CL_RCOLS, c = idx % CL_RCOLS;
+				if (c < cols) __pipeline_memcpy_async(dst + r * CL_RPITCH + c, src + (size_t) (y0 + r) * w + c0 + c, sizeof(float));
+			}
+		}
+		__pipeline_commit();
+	};
+	for (int st = 0; st < CL_STAGES - 1; st++) issue(st);
 	float acc = 0.0f;
-	for (int x0 = 0; x0 < w; x0 += CL_TILE) {
-		const int cols = min(CL_TILE, w - x0);
-		for (int idx = threadIdx.x; idx < rows * CL_TILE; idx += blockDim.x) {
-			const int ry = idx / CL_TILE, cx = idx % CL_TILE;
-			if (cx < cols) tile[ry][cx] = __ldg(src + (size_t) (y0 + ry) * w + x0 + cx);
-		}
+	for (int it = 0; it < nit; it++) {
+		__pipeline_wait_prior(CL_STAGES - 2);
 		__syncthreads();
-		if ((int) threadIdx.x < rows) {
-			for (int cx = 0; cx < cols; cx++) acc = __fadd_rn(acc, tile[threadIdx.x][cx]);
+		issue(it + CL_STAGES - 1);
+		if (tid < rows) {
+			const float *buf = ring + (it % CL_STAGES) * (CL_ROWS * CL_RPITCH) + tid * CL_RPITCH;
+			const int cols = min(CL_RCOLS, w - it * CL_RCOLS);
+			if (cols == CL_RCOLS) {
+				#pragma unroll 16
+				for (int c = 0; c < CL_RCOLS; c++) acc = __fadd_rn(acc, buf[c]);
+			} else for (int c = 0; c < cols; c++) acc = __fadd_rn(acc, buf[c]);
 		}
-		__syncthreads();
 	}
-	if ((int) threadIdx.x < rows) hbuf[(size_t) f * h + y0 + threadIdx.x] = acc;
+	if (tid < rows) hbuf[(size_t) f * h + y0 + tid] = acc;
 }
 
 // ---------------------------------------------------------------- sync search (syncdetector.c:26-153, gaussian.c)
@@ -690,16 +731,27 @@ __global__ void fs_results_autogain(int nframes, const FrameParams *__restrict__
 // ---------------------------------------------------------------- circular 2-D re-centre (syncdetector.c:187-207)
 __global__ void __launch_bounds__(256) fs_shift(const float *__restrict__ in, float *__restrict__ out, int w, int h,
                                                 const tsdrgpu_frame_result_t *__restrict__ results) {
+	// one destination row per CTA iteration: no division per pixel, the wrap is a compare; up to 4 loads in flight per thread
 	const int f = blockIdx.y;
 	const int dx = results[f].x_dx, dy = results[f].y_dx;
 	const size_t n = (size_t) w * h;
 	const float *src = in + (size_t) f * n;
 	float *dst = out + (size_t) f * n;
-	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-		const int y = (int) (i / w), x = (int) (i - (size_t) y * w);
+	for (int y = blockIdx.x; y < h; y += gridDim.x) {
 		int sy = y + dy; if (sy >= h) sy -= h;
-		int sx = x + dx; if (sx >= w) sx -= w;
-		dst[i] = __ldg(src + (size_t) sy * w + sx);
+		const float *srow = src + (size_t) sy * w;
+		float *drow = dst + (size_t) y * w;
+		for (int x0 = threadIdx.x; x0 < w; x0 += 4 * 256) {
+			float v[4];
+			#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int x = x0 + u * 256;
+				int sx = x + dx; if (sx >= w) sx -= w;
+				if (x < w) v[u] = __ldg(srow + sx);
+			}
+			#pragma unroll
+			for (int u = 0; u < 4; u++) { const int x = x0 + u * 256; if (x < w) drow[x] = v[u]; }
+		}
 	}
 }
 
@@ -978,7 +1030,7 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed
 	auto emit = [&](float *src, float *dst, bool greenlines, bool may_modify, float **result, cudaStream_t s2) -> int {
 		if (autoshift) {
-			KL(ctx, "fs_shift", s2, fs_shift<<<dim3(gx, nframes), 256, 0, s2>>>(src, dst, w, h, d_results));
+			KL(ctx, "fs_shift", s2, fs_shift<<<dim3((unsigned) h, nframes), 256, 0, s2>>>(src, dst, w, h, d_results));
 			*result = dst;
 		} else if (greenlines && may_modify) {
 			KL(ctx, "fs_greenlines", s2, fs_greenlines<<<dim3(8, nframes), 256, 0, s2>>>(src, w, h, d_results));
@@ -1006,7 +1058,7 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 			lp_in = fs->d_t1;
 			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
 		}
-		if (fuse) KL(ctx, "fs_norm_lowpass", stream, fs_norm_lowpass<<<gx, 256, sizeof(float2) * nframes, stream>>>(d_in, T2, fs->d_screen, n, nframes, fs->d_params, motionblur, fresh));
+		if (fuse) KL(ctx, "fs_norm_lowpass", stream, fs_norm_lowpass<<<(unsigned) ((n / 4 + 255) / 256 ? (n / 4 + 255) / 256 : 1), 256, sizeof(float2) * nframes, stream>>>(d_in, T2, fs->d_screen, n, nframes, fs->d_params, motionblur, fresh));
 		else KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, T2, fs->d_screen, n, nframes, motionblur, fresh));
 		if (overlapped) tail = fs->s_side;
 		if ((rc = collapse_sync(T2, tail))) return rc;

@@ -62,6 +62,41 @@ __global__ void pl_copy_f32(const float *__restrict__ src, float *__restrict__ d
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// Raw sample formats of the RawFile front end converted on the device: the same values as the plugin's
+// host loop (TSDRPlugin_RawFile.c:241-261) -- int8 v/128.0, uint8 (v-128)/128.0 (exact in float), int16 v/32767.0 and
+// uint16 (v-32767)/32767.0 (double quotient rounded to float, exactly as the C expression).
+__device__ __forceinline__ float raw_to_float(int v, int fmt) {
+	switch (fmt) {
+	case TSDRGPU_FMT_INT8:   return (float) v * 0.0078125f;
+	case TSDRGPU_FMT_UINT8:  return (float) (v - 128) * 0.0078125f;
+	case TSDRGPU_FMT_INT16:  return __double2float_rn(__ddiv_rn((double) v, 32767.0));
+	default:                 return __double2float_rn(__ddiv_rn((double) (v - 32767), 32767.0));
+	}
+}
+__global__ void __launch_bounds__(256) pl_convert(const void *__restrict__ raw, float *__restrict__ dst, size_t items, int fmt) {
+	const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (fmt == TSDRGPU_FMT_INT8 || fmt == TSDRGPU_FMT_UINT8) {
+		const size_t n4 = items >> 2;
+		for (size_t i = t0; i < n4; i += stride) {           // 4 samples per thread
+			const uchar4 q = __ldg(reinterpret_cast<const uchar4 *>(raw) + i);
+			float4 o;
+			if (fmt == TSDRGPU_FMT_INT8) { o.x = raw_to_float((signed char) q.x, fmt); o.y = raw_to_float((signed char) q.y, fmt); o.z = raw_to_float((signed char) q.z, fmt); o.w = raw_to_float((signed char) q.w, fmt); }
+			else { o.x = raw_to_float(q.x, fmt); o.y = raw_to_float(q.y, fmt); o.z = raw_to_float(q.z, fmt); o.w = raw_to_float(q.w, fmt); }
+			reinterpret_cast<float4 *>(dst)[i] = o;
+		}
+		for (size_t i = (n4 << 2) + t0; i < items; i += stride) {
+			const unsigned char b = reinterpret_cast<const unsigned char *>(raw)[i];
+			dst[i] = raw_to_float(fmt == TSDRGPU_FMT_INT8 ? (int) (signed char) b : (int) b, fmt);
+		}
+		return;
+	}
+	for (size_t i = t0; i < items; i += stride) {
+		const unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(raw) + i);
+		dst[i] = raw_to_float(fmt == TSDRGPU_FMT_INT16 ? (int) (short) u : (int) u, fmt);
+	}
+}
+static inline size_t fmt_bytes(int fmt) { return fmt == TSDRGPU_FMT_FLOAT ? 4 : ((fmt == TSDRGPU_FMT_INT8 || fmt == TSDRGPU_FMT_UINT8) ? 1 : 2); }
+
 }  // namespace
 
 struct tsdrgpu_pipeline {
@@ -81,6 +116,7 @@ struct tsdrgpu_pipeline {
 
 	// stage 0: H2D staging of the plugin's buffer
 	float *d_stage[4]; size_t stage_cap[4];           // floats; 4 slots so H2D runs ahead of the kernels
+	void *d_raw[4]; size_t raw_cap[4];                // bytes; raw-format blocks land here and are converted into d_stage
 	std::vector<void *> registered;
 	// stage 1: decimator input (IQ pairs waiting for whole blocks)
 	float *d_decim; size_t decim_cap, decim_fill;     // pairs
@@ -402,7 +438,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	pthread_mutex_init(&p->geo_mu, NULL); pthread_mutex_init(&p->mu, NULL);
 	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
 	geometry_locked(p);
-	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; } p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
+	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
 	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
 	p->slot_cap = 0; p->d_capture[0] = p->d_capture[1] = NULL; p->cap_size[0] = p->cap_size[1] = 0; p->cap_fill = 0; p->cap_phase = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
@@ -460,6 +496,7 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	cudaEventDestroy(p->sb.ev);
 	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_stage[2], p->d_stage[3], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture[0], p->d_capture[1]};
 	for (float *d : dev) if (d) cudaFree(d);
+	for (int i = 0; i < 4; i++) if (p->d_raw[i]) cudaFree(p->d_raw[i]);
 	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
 	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
 	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
@@ -524,7 +561,19 @@ static void superb_stop(tsdrgpu_pipeline *p) {                  // superbandwidt
 	geometry_locked(p);
 	pthread_mutex_unlock(&p->geo_mu);
 }
-static int superb_step(tsdrgpu_pipeline *p, const float *h_iq, uint64_t items_count, int64_t dropped) {
+// make room for `bytes` of raw samples in slot ss (contents are not preserved)
+static int raw_reserve(tsdrgpu_pipeline *p, int ss, size_t bytes) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	if (p->raw_cap[ss] >= bytes) return TSDRGPU_OK;
+	CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest)); CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));
+	if (p->d_raw[ss]) CU_TRY(ctx, cudaFree(p->d_raw[ss]));
+	const size_t cap = bytes + bytes / 2;
+	CU_TRY(ctx, cudaMalloc(&p->d_raw[ss], cap));
+	p->raw_cap[ss] = cap;
+	return TSDRGPU_OK;
+}
+
+static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t items_count, int64_t dropped) {
 	tsdrgpu_ctx_t *ctx = p->ctx;
 	int rc;
 	if (p->sb.state == SB_STOPPED) p->sb.state = SB_STARTING;
@@ -551,9 +600,17 @@ static int superb_step(tsdrgpu_pipeline *p, const float *h_iq, uint64_t items_co
 	const long long take = (p->sb.gathered + now < p->sb.to_gather) ? now : (p->sb.to_gather - p->sb.gathered);
 	if (take > 0) {
 		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->sb.ev, 0));            // the last stitch has finished reading the hop buffers
-		CU_TRY(ctx, cudaMemcpyAsync(p->sb.d_hops[p->sb.buffid] + 2 * p->sb.gathered, h_iq, sizeof(float) * 2 * (size_t) take, cudaMemcpyHostToDevice, p->s_copy));
+		float *hop = p->sb.d_hops[p->sb.buffid] + 2 * p->sb.gathered;
+		const size_t bytes = fmt_bytes(fmt) * 2 * (size_t) take;
+		if (fmt == TSDRGPU_FMT_FLOAT) CU_TRY(ctx, cudaMemcpyAsync(hop, h_iq, bytes, cudaMemcpyHostToDevice, p->s_copy));
+		else {
+			if ((rc = raw_reserve(p, 0, bytes))) return rc;
+			CU_TRY(ctx, cudaMemcpyAsync(p->d_raw[0], h_iq, bytes, cudaMemcpyHostToDevice, p->s_copy));
+			pl_convert<<<1024, 256, 0, p->s_copy>>>(p->d_raw[0], hop, 2 * (size_t) take, fmt);
+			LAUNCH_CHECK(ctx);
+		}
 		CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));
-		p->stats.h2d_bytes += sizeof(float) * 2 * (size_t) take;
+		p->stats.h2d_bytes += bytes;
 	}
 	p->sb.gathered += take;
 	if (p->sb.gathered < p->sb.to_gather) return TSDRGPU_OK;
@@ -586,9 +643,14 @@ static int superb_step(tsdrgpu_pipeline *p, const float *h_iq, uint64_t items_co
 
 // the body of the reference's process() (TSDRLibrary.c:264-298)
 int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped) {
+	return tsdrgpu_pipeline_process_raw(p, h_iq, TSDRGPU_FMT_FLOAT, items_count, samples_dropped);
+}
+
+int tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_iq, int fmt, uint64_t items_count, int64_t samples_dropped) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
 	tsdrgpu_ctx_t *ctx = p->ctx;
 	BIND(ctx);
+	ARG_TRY(ctx, fmt >= TSDRGPU_FMT_FLOAT && fmt <= TSDRGPU_FMT_UINT16);
 	ARG_TRY(ctx, (items_count & 1) == 0);                     // assert at TSDRLibrary.c:265
 	const uint64_t size2 = items_count >> 1;
 	pthread_mutex_lock(&p->geo_mu);
@@ -596,7 +658,7 @@ int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t 
 	pthread_mutex_unlock(&p->geo_mu);
 	p->stats.samples_in += size2;
 	if (samples_dropped > 0) p->stats.samples_dropped_upstream += (uint64_t) samples_dropped;
-	if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION]) return superb_step(p, h_iq, items_count, samples_dropped);
+	if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION]) return superb_step(p, h_iq, fmt, items_count, samples_dropped);
 	superb_stop(p);
 	const int block = (int) round((double) ((w * h) << 1) * ptos);           // TSDRLibrary.c:284
 	if (block <= 0) return TSDRGPU_OK;
@@ -617,11 +679,18 @@ int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t 
 		// (after the ingest kernels that read the slot four calls ago) and return once the host buffer has been read.
 		// The light per-block kernels (capture demod, append to the decimator input) run on their own stream, so the
 		// copy of block k+1..k+3 never waits behind the heavy resample / frame / FFT kernels of earlier blocks.
+		const size_t bytes = fmt_bytes(fmt) * items_count;
+		if (fmt != TSDRGPU_FMT_FLOAT && (rc = raw_reserve(p, ss, bytes))) return rc;
 		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->ev_used[ss], 0));
-		CU_TRY(ctx, cudaMemcpyAsync(stage, h_iq, sizeof(float) * items_count, cudaMemcpyHostToDevice, p->s_copy));
+		CU_TRY(ctx, cudaMemcpyAsync(fmt == TSDRGPU_FMT_FLOAT ? (void *) stage : p->d_raw[ss], h_iq, bytes, cudaMemcpyHostToDevice, p->s_copy));
 		CU_TRY(ctx, cudaEventRecord(p->ev_h2d[ss], p->s_copy));
 		CU_TRY(ctx, cudaStreamWaitEvent(p->s_ingest, p->ev_h2d[ss], 0));
-		p->stats.h2d_bytes += sizeof(float) * items_count;
+		if (fmt != TSDRGPU_FMT_FLOAT) {                                    // raw samples -> float IQ, on the device
+			const size_t want = (items_count / 4 + 255) / 256;
+			pl_convert<<<(unsigned) (want < 2048 ? (want ? want : 1) : 2048), 256, 0, p->s_ingest>>>(p->d_raw[ss], stage, items_count, fmt);
+			LAUNCH_CHECK(ctx);
+		}
+		p->stats.h2d_bytes += bytes;
 		if ((rc = feed_capture(p, stage, size2, samples_dropped != 0))) return rc;
 	} else if (plots_on && samples_dropped != 0) p->cap_fill = 0;
 	uint32_t skip = 0;
