@@ -329,6 +329,34 @@ def run_ours(args):
     e2e_frames = s1.frames_delivered - s0.frames_delivered
     pl.close()
 
+    # ---- the same e2e with the samples crossing PCIe as int8 (raw sink / tsdrgpu_pipeline_process_raw):
+    # reported beside the headline, never instead of it (the reference arm reads float32)
+    e2e_int8 = None
+    if world == 1 and not os.environ.get("BENCH_NO_INT8"):
+        q8 = torch.clamp(torch.round(iq_pinned * (100.0 / float(iq_pinned.abs().max()))), -127, 127).to(torch.int8).pin_memory()
+        pl8 = pipeline.Pipeline(samplerate=FS, height=HEIGHT, refreshrate=FV, batch_frames=16, batch_blocks=160, block_when_busy=True,
+                                device=local, params={"autoshift": 1, "lowpass_before_sync": 1})
+        ptr8, n8 = q8.data_ptr(), q8.numel()
+
+        def feed8():
+            pos = 0
+            while pos < n8:
+                n = min(chunk, n8 - pos)
+                pl8.process_raw_ptr(ptr8 + pos, 1, n, 0)
+                pos += n
+        feed8(); pl8.flush()
+        a0 = pl8.stats(); t8 = time.perf_counter()
+        for _ in range(e2e_steps):
+            feed8()
+        pl8.flush(); torch.cuda.synchronize()
+        t8 = time.perf_counter() - t8
+        a1 = pl8.stats()
+        e2e_int8 = {"value": e2e_steps * pairs / t8 / 1e6, "unit": "MS/s", "h2d_bytes_per_step": int((a1.h2d_bytes - a0.h2d_bytes) // e2e_steps),
+                    "d2h_bytes_per_step": int((a1.d2h_bytes - a0.d2h_bytes) // e2e_steps), "frames_delivered": int(a1.frames_delivered - a0.frames_delivered),
+                    "how": "tsdrgpu_pipeline_process_raw(int8) on pinned host samples, converted on the device (TSDRPlugin_RawFile.c:247 values); "
+                           "float32 frames copied back as in e2e"}
+        pl8.close()
+
     # ---- N > 1 only: the path's one real exchange, the superbandwidth stitch with one hop per GPU (configs[3])
     superb = None
     if world > 1:
@@ -413,6 +441,8 @@ def run_ours(args):
     }
     if superb:
         line["superbandwidth"] = superb
+    if e2e_int8:
+        line["e2e_int8_transport"] = e2e_int8
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -35,9 +35,10 @@ typedef struct tsdrx_raw_sink {
 	 * given to tsdrplugin_readasync, samples_dropped = IQ pairs lost before this block.  The buffer may be reused as
 	 * soon as the call returns.  Returns 0, or non-zero when the library has stopped accepting data. */
 	int   (*ingest)(const void *samples, int fmt, uint64_t items_count, void *ctx, int64_t samples_dropped);
-	/* page-locked host memory for the plugin's read buffer (faster DMA); either may fail/be NULL: use malloc then */
-	void *(*alloc_host)(size_t bytes);
-	void  (*free_host)(void *p);
+	/* page-locked host memory for the plugin's read buffer (faster DMA), valid inside tsdrplugin_readasync with its
+	 * ctx; either may be NULL or fail: use malloc then */
+	void *(*alloc_host)(size_t bytes, void *ctx);
+	void  (*free_host)(void *p, void *ctx);
 } tsdrx_raw_sink_t;
 
 typedef void (*tsdrpluginx_set_raw_sink_fn)(const tsdrx_raw_sink_t *sink);   /* sink == NULL: forget it */

@@ -305,6 +305,8 @@ TSDRGPU_API int  tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_
  * bytes per component and is converted on the device to exactly the floats TSDRPlugin_RawFile.c:241-261 would have
  * produced on the host.  fmt uses the RawFile plugin's own numbering (TSDRPlugin_RawFile.c:29-33). */
 enum { TSDRGPU_FMT_FLOAT = 0, TSDRGPU_FMT_INT8 = 1, TSDRGPU_FMT_INT16 = 2, TSDRGPU_FMT_UINT8 = 3, TSDRGPU_FMT_UINT16 = 4 };
+/* the conversion alone, device to device (d_raw: items_count samples of `fmt`; d_out: items_count floats) */
+TSDRGPU_API int  tsdrgpu_convert_samples(tsdrgpu_ctx_t *ctx, void *stream, const void *d_raw, int fmt, uint64_t items_count, float *d_out);
 TSDRGPU_API int  tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_samples, int fmt, uint64_t items_count, int64_t samples_dropped);
 TSDRGPU_API int  tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p);            /* waits for the GPU and for every pending callback */
 TSDRGPU_API int  tsdrgpu_pipeline_set_param_int(tsdrgpu_pipeline_t *p, int id, uint32_t value);

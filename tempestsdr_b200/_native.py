@@ -118,6 +118,7 @@ _SIGS = {
     "tsdrgpu_pipeline_create": (C.c_int, [C.c_void_p, C.POINTER(PipelineConfig), FRAME_CB, VALUE_CB, PLOT_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_pipeline_destroy": (None, [C.c_void_p]),
     "tsdrgpu_pipeline_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]),
+    "tsdrgpu_convert_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
     "tsdrgpu_pipeline_process_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64]),
     "tsdrgpu_pipeline_flush": (C.c_int, [C.c_void_p]),
     "tsdrgpu_pipeline_set_param_int": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),

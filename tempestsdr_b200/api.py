@@ -76,6 +76,13 @@ class Context:
         self.chk(self._lib.tsdrgpu_am_demod(self._h, self.stream, iq.data_ptr(), iq.numel() // 2, out.data_ptr()))
         return out
 
+    def convert_samples(self, raw: torch.Tensor) -> torch.Tensor:
+        """TSDRPlugin_RawFile.c:241-261 on the device: int8 / uint8 / int16 / uint16 (or float32) samples -> float32."""
+        fmt = {torch.float32: 0, torch.int8: 1, torch.int16: 2, torch.uint8: 3, torch.uint16: 4}[raw.dtype]
+        out = torch.empty(raw.numel(), dtype=torch.float32, device=raw.device)
+        self.chk(self._lib.tsdrgpu_convert_samples(self._h, self.stream, raw.data_ptr(), fmt, raw.numel(), out.data_ptr()))
+        return out
+
     # ------------------------------------------------------------------ a8-a10, a14 (stage level)
     def dsp_autogain_run(self, state: List[float], frame: torch.Tensor, norm: float, snr: bool = True) -> torch.Tensor:
         """dsp.c:41-94.  state = [lastmax, lastmin, snr] is updated in place."""

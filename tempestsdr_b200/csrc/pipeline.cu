@@ -642,6 +642,17 @@ static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t 
 }
 
 // the body of the reference's process() (TSDRLibrary.c:264-298)
+int tsdrgpu_convert_samples(tsdrgpu_ctx_t *ctx, void *stream, const void *d_raw, int fmt, uint64_t items_count, float *d_out) {
+	BIND(ctx);
+	ARG_TRY(ctx, fmt >= TSDRGPU_FMT_FLOAT && fmt <= TSDRGPU_FMT_UINT16);
+	if (items_count == 0) return TSDRGPU_OK;
+	ARG_TRY(ctx, d_raw != NULL && d_out != NULL);
+	if (fmt == TSDRGPU_FMT_FLOAT) { CU_TRY(ctx, cudaMemcpyAsync(d_out, d_raw, sizeof(float) * items_count, cudaMemcpyDeviceToDevice, (cudaStream_t) stream)); return TSDRGPU_OK; }
+	const size_t want = (items_count / 4 + 255) / 256;
+	KL(ctx, "pl_convert", (cudaStream_t) stream, pl_convert<<<(unsigned) (want < 2048 ? (want ? want : 1) : 2048), 256, 0, (cudaStream_t) stream>>>(d_raw, d_out, items_count, fmt));
+	return TSDRGPU_OK;
+}
+
 int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped) {
 	return tsdrgpu_pipeline_process_raw(p, h_iq, TSDRGPU_FMT_FLOAT, items_count, samples_dropped);
 }

@@ -13,6 +13,7 @@
 #include "../../include/TSDRLibrary.h"
 #include "../../include/TSDRCodes.h"
 #include "../../include/TSDRPlugin.h"
+#include "../../include/TSDRPluginX.h"
 #include "../../include/tsdrgpu.h"
 
 #include <dlfcn.h>
@@ -36,6 +37,7 @@ typedef struct {
 	int      (*readasync)(tsdrplugin_readasync_function, void *);
 	char *   (*getlasterrortext)(void);
 	void     (*cleanup)(void);
+	tsdrpluginx_set_raw_sink_fn set_raw_sink;       /* optional 11th symbol (include/TSDRPluginX.h), NULL for ordinary plugins */
 	volatile int initialized;
 } plugin_t;
 
@@ -87,6 +89,7 @@ static void set_internal_samplerate(tsdr_lib_t *t, uint32_t samplerate) {
 
 /* ---- plugin loader: dlopen(RTLD_NOW) + exactly these ten symbols (TSDRPluginLoader.c:33-72) --------------- */
 static void plugin_close(plugin_t *p) {
+	if (p->initialized && p->set_raw_sink) p->set_raw_sink(NULL);
 	if (p->initialized && p->cleanup) p->cleanup();
 	p->initialized = 0;
 	if (p->handle) { dlclose(p->handle); p->handle = NULL; }
@@ -101,6 +104,7 @@ static int plugin_load(plugin_t *p, const char *path) {
 	SYM(setgain, "tsdrplugin_setgain"); SYM(readasync, "tsdrplugin_readasync"); SYM(getlasterrortext, "tsdrplugin_getlasterrortext");
 	SYM(cleanup, "tsdrplugin_cleanup");
 #undef SYM
+	*(void **) (&p->set_raw_sink) = dlsym(p->handle, "tsdrpluginx_set_raw_sink");      /* optional */
 	p->initialized = 1;
 	return TSDR_OK;
 }
@@ -158,6 +162,8 @@ int tsdr_unloadplugin(tsdr_lib_t *t) {
 	return ok(t);
 }
 
+static const tsdrx_raw_sink_t g_raw_sink;          /* defined beside tsdr_readasync */
+
 int tsdr_loadplugin(tsdr_lib_t *t, const char *path, const char *params) {
 	if (t->nativerunning || t->running) return fail(t, "The library is already running in async mode. Stop it first!", TSDR_ALREADY_RUNNING);
 	plugin_close(&t->plugin);
@@ -167,6 +173,7 @@ int tsdr_loadplugin(tsdr_lib_t *t, const char *path, const char *params) {
 	if (status != TSDR_OK) { plugin_close(&t->plugin); return fail(t, "The selected library is not a valid TSDR plugin!", status); }
 	char name[256];
 	t->plugin.getName(name);
+	if (t->plugin.set_raw_sink && !getenv("TSDR_NO_RAW_SINK")) t->plugin.set_raw_sink(&g_raw_sink);
 	char *mutable_params = strdup(params ? params : "");    /* RawFile's tokenizer writes into the string it is given */
 	status = t->plugin.init(mutable_params);
 	free(mutable_params);
@@ -259,6 +266,27 @@ static void process(float *buf, uint64_t items_count, void *ctx, int64_t samples
 		t->plugin.stop();
 	}
 }
+
+/* ---- optional raw sink (include/TSDRPluginX.h): the plugin keeps its samples in wire format, the GPU converts ---- */
+static int raw_ingest(const void *samples, int fmt, uint64_t items_count, void *ctx, int64_t samples_dropped) {
+	tsdr_lib_t *t = (tsdr_lib_t *) ctx;
+	if (t->gpu_failed || !t->pipe) return 1;
+	const int rc = tsdrgpu_pipeline_process_raw(t->pipe, samples, fmt, items_count, samples_dropped);
+	if (rc != TSDRGPU_OK) {
+		t->gpu_failed = 1;
+		fail(t, tsdrgpu_last_error(t->gpu), TSDR_CANNOT_OPEN_DEVICE);
+		t->plugin.stop();
+		return 1;
+	}
+	return 0;
+}
+static void *raw_alloc_host(size_t bytes, void *ctx) {
+	tsdr_lib_t *t = (tsdr_lib_t *) ctx;
+	void *p = NULL;
+	return (t && t->gpu && tsdrgpu_malloc_host(t->gpu, bytes, &p) == TSDRGPU_OK) ? p : NULL;
+}
+static void raw_free_host(void *p, void *ctx) { tsdr_lib_t *t = (tsdr_lib_t *) ctx; if (t && t->gpu) tsdrgpu_free_host(t->gpu, p); }
+static const tsdrx_raw_sink_t g_raw_sink = { 1, raw_ingest, raw_alloc_host, raw_free_host };
 
 int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 	if (t->nativerunning || t->running) return fail(t, "The library is already running in async mode. Stop it first!", TSDR_ALREADY_RUNNING);

@@ -13,6 +13,7 @@ import numpy as np
 
 from . import _native as N
 
+RAW_FORMATS = {"float32": 0, "int8": 1, "int16": 2, "uint8": 3, "uint16": 4}     # TSDRPlugin_RawFile.c:29-33
 PARAM_IDS = {"autoshift": 0, "framerate_pll": 1, "autocorr_plots_reset": 2, "autocorr_plots_off": 3,
              "superresolution": 4, "nearest_neighbour_resampling": 5, "lowpass_before_sync": 6,
              "autogain_after_processing": 7, "autocorr_dump": 8}
@@ -76,6 +77,16 @@ class Pipeline:
 
     def process_ptr(self, ptr: int, items: int, samples_dropped: int = 0) -> None:
         N.check(self._lib.tsdrgpu_pipeline_process(self._h, C.c_void_p(ptr), items, samples_dropped), self._ctx)
+
+    def process_raw(self, samples: np.ndarray, samples_dropped: int = 0) -> None:
+        """samples: interleaved I,Q on the HOST still in the front end's wire format (int8 / uint8 / int16 / uint16 /
+        float32); converted on the device to the floats TSDRPlugin_RawFile.c:241-261 produces on the host."""
+        fmt = RAW_FORMATS[samples.dtype.name]
+        assert samples.flags.c_contiguous
+        N.check(self._lib.tsdrgpu_pipeline_process_raw(self._h, samples.ctypes.data_as(C.c_void_p), fmt, samples.size, samples_dropped), self._ctx)
+
+    def process_raw_ptr(self, ptr: int, fmt: int, items: int, samples_dropped: int = 0) -> None:
+        N.check(self._lib.tsdrgpu_pipeline_process_raw(self._h, C.c_void_p(ptr), fmt, items, samples_dropped), self._ctx)
 
     def flush(self) -> None:
         N.check(self._lib.tsdrgpu_pipeline_flush(self._h), self._ctx)

@@ -131,11 +131,11 @@ TSDRPLUGIN_API int __stdcall tsdrplugin_readasync(tsdrplugin_readasync_function 
 	const size_t block_bytes = (size_t) S.block_items * (size_t) S.bytes_per_item;
 	int pinned = 0;
 	unsigned char *raw = NULL;
-	if (sink && sink->alloc_host && sink->free_host && (raw = sink->alloc_host(block_bytes)) != NULL) pinned = 1;
+	if (sink && sink->alloc_host && sink->free_host && (raw = sink->alloc_host(block_bytes, ctx)) != NULL) pinned = 1;
 	if (!raw) raw = malloc(block_bytes);
 	float *conv = (!sink && S.fmt != TSDRX_FMT_FLOAT) ? malloc(sizeof(float) * S.block_items) : NULL;
 	if (!raw || (!sink && S.fmt != TSDRX_FMT_FLOAT && !conv)) {
-		if (raw) { if (pinned) sink->free_host(raw); else free(raw); }
+		if (raw) { if (pinned) sink->free_host(raw, ctx); else free(raw); }
 		free(conv); fclose(f);
 		return set_error(TSDR_ERR_PLUGIN, "Out of memory.");
 	}
@@ -163,7 +163,7 @@ TSDRPLUGIN_API int __stdcall tsdrplugin_readasync(tsdrplugin_readasync_function 
 			else due = now_s();
 		}
 	}
-	if (pinned) sink->free_host(raw); else free(raw);
+	if (pinned) sink->free_host(raw, ctx); else free(raw);
 	free(conv);
 	fclose(f);
 	S.running = 0;
