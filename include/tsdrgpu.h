@@ -188,6 +188,9 @@ TSDRGPU_API int tsdrgpu_gaussianblur(tsdrgpu_ctx_t *ctx, void *stream, float *d_
  * the JNI glue's float->ARGB mapping (JavaGUI/jni/TSDRLibraryNDK.c:222-283), bit-exact; transparent (2048.0f)
  * pixels keep the previous content of d_argb. */
 TSDRGPU_API int tsdrgpu_pixels_argb(tsdrgpu_ctx_t *ctx, void *stream, const float *d_frame, int n, int inverted, int32_t *d_argb);
+/* a batch of frames converted IN PLACE (float frame f becomes its n int32 pixels); d_last (n int32, caller-zeroed at start)
+ * is the host's persistent pixel buffer carried across frames and calls, so transparent samples behave as in the GUI */
+TSDRGPU_API int tsdrgpu_pixels_argb_batch(tsdrgpu_ctx_t *ctx, void *stream, float *d_frames_inout, uint64_t n, int nframes, int inverted, int32_t *d_last);
 
 /* ---------------------------------------------------------------------------- a19/a20  FFT and correlations
  * replace fft_perform, fft_autocorrelation, fft_crosscorrelation (fft.c:49-176).  Same definitions as the
@@ -316,6 +319,10 @@ TSDRGPU_API int  tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t
  * between hops through this callback; without it the hops are recorded at one frequency */
 TSDRGPU_API int  tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb);
 TSDRGPU_API int  tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff);
+/* deliver final pixels.  mode 1: the frame callback's buffer holds w*h int32 pixels of the JNI glue's
+ * float->ARGB rule (TSDRLibraryNDK.c:222-283) instead of floats (same size, so the callback type is unchanged: cast it);
+ * inverted as the GUI's "inverted colours".  mode 0 (default): floats, as the reference. */
+TSDRGPU_API int  tsdrgpu_pipeline_set_output_argb(tsdrgpu_pipeline_t *p, int mode, int inverted);
 TSDRGPU_API int  tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels);   /* tsdr_sync: syncoffset += pixels */
 TSDRGPU_API int  tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate);
 TSDRGPU_API int  tsdrgpu_pipeline_stats(tsdrgpu_pipeline_t *p, tsdrgpu_pipeline_stats_t *out);

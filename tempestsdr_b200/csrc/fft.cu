@@ -265,6 +265,19 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	const int sha = (log2C >= 4) ? 0 : 3 - log2C, shb = (NSTAGES == 2 || log2C >= 4) ? sha : 4 - log2C;
 	const unsigned sbase = smem_addr(s);
 	float2 v[8];
+	// Inter-pass twiddles W_M^(col k): a thread's eight outputs are k = i0 + (L/8) j, j = 0..7, of ONE column, so
+	// W^(col k) = W^(col i0) * W^(col (L/8) j): one sincospif per thread for the first factor (exactly reduced argument),
+	// the second from a per-CTA table of 8 values per column (double-precision sincospi, once per CTA).
+	__shared__ float2 tw_step[8 * 32];
+	const bool tw_fast = P.tw_M != 0 && P.tw_M <= (1ull << 24) && P.c_fast_out && C <= 32 && (int) blockDim.x == C * L8 && NSTAGES > 1;
+	if (tw_fast && tid < 8 * C) {
+		const int cc = tid >> 3, j = tid & 7;
+		const unsigned col = (unsigned) ((int) g_lo * (int) P.tw_lo + cc * (int) P.tw_cs);
+		const unsigned e = (col * (unsigned) (L8 * j)) & (unsigned) (P.tw_M - 1);
+		double dsn, dcs;
+		sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs);
+		tw_step[tid] = make_float2((float) dcs, (float) dsn);
+	}
 
 	// ---- stage 0: radix 8, p = 1, inputs x[i + m L/8] from global memory
 	{
@@ -319,6 +332,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	const int T = blockDim.x;
 	const unsigned twmask = (unsigned) (P.tw_M - 1);
 	const float inv_M = P.tw_M ? 1.0f / (float) P.tw_M : 0.0f;       // a power of two: exact
+	float2 tw_base = make_float2(1.0f, 0.0f);
 	#pragma unroll
 	for (int it = 0; it < NB; it++) {
 		const int widx = tid + it * T;
@@ -339,7 +353,20 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 		if (P.tw_M) {
 			// inter-pass twiddle W_M^(col k): the argument is reduced exactly in integers, sincospif sees an exact float
 			const unsigned col = (unsigned) ((int) g_lo * (int) P.tw_lo + c * (int) P.tw_cs);
-			if (P.tw_M <= (1ull << 24)) {
+			if (tw_fast) {
+				if (it == 0) {
+					const unsigned e = (col * (unsigned) i) & twmask;            // i == i0 in the first round
+					float sn, cs;
+					sincospif(-2.0f * ((float) e * inv_M), &sn, &cs);
+					tw_base = make_float2(cs, sn);
+				}
+				#pragma unroll
+				for (int m = 0; m < RLAST; m++) {
+					const float2 st = tw_step[c * 8 + it + NB * m];
+					const float2 tw = make_float2(tw_base.x * st.x - tw_base.y * st.y, tw_base.x * st.y + tw_base.y * st.x);
+					w[m] = twmul<INV>(tw, w[m]);
+				}
+			} else if (P.tw_M <= (1ull << 24)) {
 				#pragma unroll
 				for (int m = 0; m < RLAST; m++) {
 					const int k = i + m * PL;

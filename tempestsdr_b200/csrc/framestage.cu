@@ -788,6 +788,33 @@ __global__ void __launch_bounds__(256) fs_argb(const float *__restrict__ frame, 
 	}
 }
 
+// The same rule over a batch of frames, in place (a float frame becomes its int32 pixels), with the host's persistent pixel
+// buffer (`last`) carried from frame to frame: a transparent sample (2048.0f) shows what that pixel showed before.
+__global__ void __launch_bounds__(256) fs_argb_batch(float *frames, size_t n, int nframes, int inverted, int *__restrict__ last) {
+	const int white = 255 | (255 << 8) | (255 << 16);
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		int prev = last[i];
+		for (int f = 0; f < nframes; f++) {
+			float *slot = frames + (size_t) f * n + i;
+			const float v = *slot;
+			int px;
+			if (v > 0.0f && v <= 1.0f) {
+				int g = (int) __fmul_rn(v, 255.0f);
+				if (inverted) g = 255 - g;
+				px = g | (g << 8) | (g << 16);
+			} else if (v <= 0.0f) px = inverted ? white : 0;
+			else if (v == 256.0f) px = 255 << 16;
+			else if (v == 512.0f) px = 255 << 8;
+			else if (v == 1024.0f) px = 255;
+			else if (v == 2048.0f) px = prev;
+			else px = inverted ? 0 : white;
+			*reinterpret_cast<int *>(slot) = px;
+			prev = px;
+		}
+		last[i] = prev;
+	}
+}
+
 __global__ void fs_blur_kernel(float *data, int n, float c0, float c1, float c2, float c3, float c4) {
 	extern __shared__ float smem[];
 	float *src = smem, *dst = smem + n;
@@ -1164,6 +1191,14 @@ int tsdrgpu_pixels_argb(tsdrgpu_ctx_t *ctx, void *stream, const float *d_frame, 
 	ARG_TRY(ctx, n > 0 && d_frame && d_argb);
 	fs_argb<<<grid_for((size_t) n, ctx->sm_count), 256, 0, (cudaStream_t) stream>>>(d_frame, n, inverted, d_argb);
 	LAUNCH_CHECK(ctx);
+	return TSDRGPU_OK;
+}
+
+int tsdrgpu_pixels_argb_batch(tsdrgpu_ctx_t *ctx, void *stream, float *d_frames_inout, uint64_t n, int nframes, int inverted, int32_t *d_last) {
+	BIND(ctx);
+	if (nframes == 0) return TSDRGPU_OK;
+	ARG_TRY(ctx, n > 0 && nframes > 0 && d_frames_inout && d_last);
+	KL(ctx, "fs_argb_batch", (cudaStream_t) stream, fs_argb_batch<<<grid_for((size_t) n, ctx->sm_count), 256, 0, (cudaStream_t) stream>>>(d_frames_inout, (size_t) n, nframes, inverted, d_last));
 	return TSDRGPU_OK;
 }
 

@@ -112,6 +112,7 @@ struct tsdrgpu_pipeline {
 	pthread_mutex_t geo_mu;
 	uint32_t samplerate; int height, width; double refreshrate, pixelrate, ptos;
 	float motionblur; volatile int syncoffset;
+	volatile int argb_mode, argb_inverted; int32_t *d_argb_last; size_t argb_cap;      // 8f-2: final pixels instead of floats
 	uint32_t params[9];
 
 	// stage 0: H2D staging of the plugin's buffer
@@ -350,6 +351,15 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 		CU_TRY(ctx, cudaEventRecord(p->ev_main, p->s_main));
 		CU_TRY(ctx, cudaStreamWaitEvent(p->s_out, p->ev_main, 0));             // serial stage orders finish on the main stream
 		if ((rc = tsdrgpu_framestage_join(p->fs, p->s_out))) return rc;        // the overlapped order finishes on the side stream
+		if (p->argb_mode) {                                                    // float frames -> the host's int32 pixels, in place
+			if (p->argb_cap != n) {
+				if (p->d_argb_last) CU_TRY(ctx, cudaFree(p->d_argb_last));
+				CU_TRY(ctx, cudaMalloc(&p->d_argb_last, sizeof(int32_t) * n));
+				CU_TRY(ctx, cudaMemsetAsync(p->d_argb_last, 0, sizeof(int32_t) * n, p->s_out));
+				p->argb_cap = n;
+			}
+			if ((rc = tsdrgpu_pixels_argb_batch(ctx, p->s_out, p->d_frames[op], n, nf, p->argb_inverted, p->d_argb_last))) return rc;
+		}
 		CU_TRY(ctx, cudaMemcpyAsync(p->h_frames[slot], p->d_frames[op], sizeof(float) * n * nf, cudaMemcpyDeviceToHost, p->s_out));
 		CU_TRY(ctx, cudaEventRecord(p->ev_out[op], p->s_out));
 		p->stats.d2h_bytes += sizeof(float) * n * nf;
@@ -438,7 +448,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	pthread_mutex_init(&p->geo_mu, NULL); pthread_mutex_init(&p->mu, NULL);
 	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
 	geometry_locked(p);
-	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
+	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->argb_mode = 0; p->argb_inverted = 0; p->d_argb_last = NULL; p->argb_cap = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
 	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
 	p->slot_cap = 0; p->d_capture[0] = p->d_capture[1] = NULL; p->cap_size[0] = p->cap_size[1] = 0; p->cap_fill = 0; p->cap_phase = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
@@ -497,6 +507,7 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_stage[2], p->d_stage[3], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture[0], p->d_capture[1]};
 	for (float *d : dev) if (d) cudaFree(d);
 	for (int i = 0; i < 4; i++) if (p->d_raw[i]) cudaFree(p->d_raw[i]);
+	if (p->d_argb_last) cudaFree(p->d_argb_last);
 	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
 	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
 	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
@@ -531,6 +542,7 @@ int tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate) 
 }
 int tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb) { if (!p) return TSDRGPU_EINVAL; p->retune_cb = cb; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff) { if (!p) return TSDRGPU_EINVAL; p->motionblur = coeff; return TSDRGPU_OK; }
+int tsdrgpu_pipeline_set_output_argb(tsdrgpu_pipeline_t *p, int mode, int inverted) { if (!p) return TSDRGPU_EINVAL; p->argb_mode = mode != 0; p->argb_inverted = inverted != 0; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels) { if (!p) return TSDRGPU_EINVAL; p->syncoffset += pixels; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate) {
 	if (!p) return TSDRGPU_EINVAL;

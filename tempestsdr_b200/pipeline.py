@@ -93,6 +93,11 @@ class Pipeline:
         if self.errors:
             raise self.errors[0]
 
+    def set_output_argb(self, on: bool, inverted: bool = False) -> None:
+        """Deliver the JNI glue's int32 pixels (TSDRLibraryNDK.c:222-283) instead of floats; on_frame then receives the
+        same float32 array object whose bytes are int32 pixels: use frame.view(np.int32)."""
+        N.check(self._lib.tsdrgpu_pipeline_set_output_argb(self._h, int(on), int(inverted)), self._ctx)
+
     def set_param(self, name: str, value: int) -> None:
         N.check(self._lib.tsdrgpu_pipeline_set_param_int(self._h, PARAM_IDS[name], value), self._ctx)
 

@@ -171,3 +171,54 @@ def test_pipeline_superbandwidth_mode():
         got = frames[k][0]
         assert np.max(np.abs(got - ref)) < 2e-3, f"frame {k}: {np.max(np.abs(got - ref))}"
     p.close()
+
+
+@pytest.mark.parametrize("inverted", [False, True])
+def test_pipeline_argb_output_and_raw_int8_ingest(inverted):
+    """SURVEY 8f-1 + 8f-2 through the streaming pipeline: int8 samples in (converted on the device), final int32 pixels out
+    (the JNI glue's rule, TSDRLibraryNDK.c:222-283).  Expected: the oracle's stage-wise replay of the host-converted floats,
+    pushed through the oracle's pixel rule with a persistent host pixel buffer."""
+    from tempestsdr_b200 import pipeline
+    O = orc.best()
+    fs, h, fv = 2_000_000, 125, 60.0
+    w, _, _ = O.geometry(fs, h, fv)
+    nblk, items = 16, 65536
+    iq = synth.video_like_iq(nblk * items // 2, fs, w, h, fv, seed=91)
+    q = np.clip(np.round(iq / np.abs(iq).max() * 110.0), -128, 127).astype(np.int8)
+    as_float = (q.astype(np.float64) / 128.0).astype(np.float32)           # TSDRPlugin_RawFile.c:247
+    blocks_f = [as_float[k * items:(k + 1) * items] for k in range(nblk)]
+    _, frames = run_oracle_stream(O, blocks_f, fs, h, fv)
+    got = []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=4, batch_blocks=40, block_when_busy=True,
+                          params={"autoshift": 1, "lowpass_before_sync": 1, "autocorr_plots_off": 1},
+                          on_frame=lambda f, ww, hh: got.append(f.view(np.int32).copy()))
+    p.set_output_argb(True, inverted)
+    for k in range(nblk):
+        p.process_raw(q[k * items:(k + 1) * items].copy(), 0)
+    p.flush()
+    assert 4 <= len(got) <= len(frames)
+    for k, g in enumerate(got):
+        assert np.array_equal(g, O.pixels_argb(frames[k], inverted)), f"frame {k}"
+    p.close()
+
+
+def test_pixels_argb_batch_keeps_transparent_pixels():
+    from tempestsdr_b200 import _native
+    from tempestsdr_b200.api import Context
+    O = orc.best()
+    gpu = Context(0)
+    rng = np.random.default_rng(3)
+    n, nf = 1000, 5
+    f = rng.uniform(-0.2, 1.3, (nf, n)).astype(np.float32)
+    f[:, ::7] = 2048.0; f[2, ::7] = 0.5; f[:, 3::11] = 512.0; f[1, 5::13] = 256.0; f[3, 1::17] = 1024.0
+    d = torch.from_numpy(f.copy()).cuda()
+    last = torch.zeros(n, dtype=torch.int32, device="cuda")
+    gpu.chk(_native.lib().tsdrgpu_pixels_argb_batch(gpu._h, gpu.stream, d.data_ptr(), n, nf, 0, last.data_ptr()))
+    got = d.view(torch.int32).cpu().numpy()
+    prev = np.zeros(n, np.int32)
+    for k in range(nf):
+        want = O.pixels_argb(f[k], False).astype(np.int32)
+        want[f[k] == 2048.0] = prev[f[k] == 2048.0]
+        assert np.array_equal(got[k], want), f"frame {k}"
+        prev = want
+    assert np.array_equal(last.cpu().numpy(), prev)
