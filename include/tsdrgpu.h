@@ -88,6 +88,10 @@ TSDRGPU_API uint64_t tsdrgpu_plan_resample(double *offset, const uint32_t *sizes
 /* relative angle errors eps[l] of the reference FFT's stage twiddles (half-angle recurrence, fft.c:132-165): stage l
  * rotates by (pi/2^l)(1+eps[l]) instead of pi/2^l.  Used by tsdrgpu_fft to track the reference at large N. */
 TSDRGPU_API void tsdrgpu_fft_reference_eps(int stages, int inverse, double *eps);
+/* host-only: the GUI's auto-resolution arithmetic on the two autocorrelation plots (JavaGUI .../PlotVisualizer.java:203-236,
+ * Main.java:1233-1253,1301-1303,1346-1350): first strict maximum of each plot -> fps, height.  Optional outputs may be NULL. */
+TSDRGPU_API int tsdrgpu_detect_videomode(const double *frame_plot, int frame_offset, int frame_len, const double *line_plot, int line_offset,
+                                         int line_len, uint32_t samplerate, double *fps, int *height, int *frame_index, int *line_index);
 /* the normalised 5-tap Gaussian of gaussian.c:16-30 */
 TSDRGPU_API void tsdrgpu_gauss_taps(float taps[5]);
 
@@ -323,6 +327,13 @@ TSDRGPU_API int  tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float co
  * float->ARGB rule (TSDRLibraryNDK.c:222-283) instead of floats (same size, so the callback type is unchanged: cast it);
  * inverted as the GUI's "inverted colours".  mode 0 (default): floats, as the reference. */
 TSDRGPU_API int  tsdrgpu_pipeline_set_output_argb(tsdrgpu_pipeline_t *p, int mode, int inverted);
+/* SURVEY section 8f-4 / 8f-3, both off by default because the reference announces neither:
+ *  report_snr:  value callback id 4 (VALUE_ID_SNR, TSDRLibrary.h:52) with dsp_autogain_t.snr next to every auto-gain report
+ *               (the announce dsp.c:234 leaves commented out);
+ *  detect_mode: after every pair of plots, value callback id TSDRGPU_VALUE_ID_DETECTED_MODE with (fps, height) computed
+ *               like the GUI's auto-resolution (tsdrgpu_detect_videomode). */
+#define TSDRGPU_VALUE_ID_DETECTED_MODE 100
+TSDRGPU_API int  tsdrgpu_pipeline_set_reports(tsdrgpu_pipeline_t *p, int report_snr, int detect_mode);
 TSDRGPU_API int  tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels);   /* tsdr_sync: syncoffset += pixels */
 TSDRGPU_API int  tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate);
 TSDRGPU_API int  tsdrgpu_pipeline_stats(tsdrgpu_pipeline_t *p, tsdrgpu_pipeline_stats_t *out);

@@ -64,3 +64,26 @@ void tsdrgpu_fft_reference_eps(int stages, int inverse, double *eps) {
 		c1 = n1; c2 = n2;
 	}
 }
+
+/* Auto video-mode detection, the arithmetic the GUI does on the two autocorrelation plots:
+ * PlotVisualizer.java:203-236 takes the index of the first strict maximum of a plot (starting from element 0),
+ * Main.java:1301-1303 turns the frame plot's into fps = samplerate / (offset + index), Main.java:1346-1350 + 1041-1043 the
+ * line plot's into height = round((frame offset + index) / (line offset + index)), Java's Math.round = floor(x + 0.5). */
+static int first_max(const double *v, int n) {
+	int best = 0;
+	double top = v[0];
+	for (int i = 1; i < n; i++) if (v[i] > top) { top = v[i]; best = i; }
+	return best;
+}
+int tsdrgpu_detect_videomode(const double *frame_plot, int frame_offset, int frame_len, const double *line_plot, int line_offset, int line_len,
+                             uint32_t samplerate, double *fps, int *height, int *frame_index, int *line_index) {
+	if (!frame_plot || !line_plot || frame_len <= 0 || line_len <= 0) return TSDRGPU_EINVAL;
+	const int fi = first_max(frame_plot, frame_len), li = first_max(line_plot, line_len);
+	const double frame_length = (double) (frame_offset + fi), line_length = (double) (line_offset + li);
+	if (frame_length <= 0 || line_length <= 0) return TSDRGPU_EINVAL;
+	if (fps) *fps = (double) (long long) samplerate / frame_length;
+	if (height) *height = (int) floor(frame_length / line_length + 0.5);
+	if (frame_index) *frame_index = fi;
+	if (line_index) *line_index = li;
+	return TSDRGPU_OK;
+}

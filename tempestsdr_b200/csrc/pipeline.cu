@@ -36,6 +36,7 @@ struct FrameJob {
 	cudaEvent_t ev;
 	uint32_t samplerate;      // plots
 	int foff, flen, loff, llen; uint64_t calls; int reset_announce;
+	int snr_valid;            // frames: results carry an SNR to announce
 };
 
 // block-aligned dropping, dsp.c:313-368 (integer bookkeeping, host side)
@@ -112,6 +113,7 @@ struct tsdrgpu_pipeline {
 	pthread_mutex_t geo_mu;
 	uint32_t samplerate; int height, width; double refreshrate, pixelrate, ptos;
 	float motionblur; volatile int syncoffset;
+	volatile int report_snr, detect_mode;              // 8f-4 / 8f-3, both off by default (the reference announces neither)
 	volatile int argb_mode, argb_inverted; int32_t *d_argb_last; size_t argb_cap;      // 8f-2: final pixels instead of floats
 	uint32_t params[9];
 
@@ -181,6 +183,7 @@ static void *delivery_main(void *arg) {
 					if (p->value_cb) p->value_cb(0 /* VALUE_ID_PLL_FRAMERATE */, rr, 0, p->user);
 				}
 				if (p->h_report[j.slot][f] && p->value_cb) p->value_cb(3 /* VALUE_ID_AUTOGAIN_VALUES */, r.lastmin, r.lastmax, p->user);
+				if (p->h_report[j.slot][f] && p->value_cb && j.snr_valid) p->value_cb(4 /* VALUE_ID_SNR: the announce dsp.c:234 leaves commented out */, r.snr, 0, p->user);
 				if (p->frame_cb) p->frame_cb(p->h_frames[j.slot] + f * n, j.w, j.h, p->user);
 			}
 			pthread_mutex_lock(&p->mu);
@@ -193,6 +196,11 @@ static void *delivery_main(void *arg) {
 				p->plot_cb(1 /* PLOT_ID_LINE */, j.loff, p->h_plot_line[j.slot], j.llen, j.samplerate, p->user);
 			}
 			if (p->value_cb) p->value_cb(2 /* VALUE_ID_AUTOCORRECT_FRAMES_COUNT */, 0, (double) j.calls, p->user);
+			if (p->detect_mode && p->value_cb && j.flen > 0 && j.llen > 0) {
+				double fps = 0; int height = 0;
+				tsdrgpu_detect_videomode(p->h_plot_frame[j.slot], j.foff, j.flen, p->h_plot_line[j.slot], j.loff, j.llen, j.samplerate, &fps, &height, NULL, NULL);
+				p->value_cb(TSDRGPU_VALUE_ID_DETECTED_MODE, fps, (double) height, p->user);
+			}
 			pthread_mutex_lock(&p->mu);
 			p->plot_busy[j.slot] = 0; p->stats.plots_delivered++;
 			pthread_mutex_unlock(&p->mu);
@@ -344,6 +352,8 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 		if (p->params[TSDRGPU_PARAM_LOW_PASS_BEFORE_SYNC]) flags |= TSDRGPU_FS_LOWPASS_BEFORE_SYNC;
 		if (p->params[TSDRGPU_PARAM_AUTOGAIN_AFTER_PROCESSING]) flags |= TSDRGPU_FS_AUTOGAIN_AFTER_PROC;
 		if (p->params[TSDRGPU_PARAM_AUTOCORR_SUPERRESOLUTION]) flags |= TSDRGPU_FS_SUPERRESOLUTION;
+		const int want_snr = p->report_snr;
+		if (want_snr) flags |= TSDRGPU_FS_COMPUTE_SNR;
 		if ((rc = tsdrgpu_framestage_run_async(p->fs, p->s_main, p->d_pix + p->pix_read, nf, w, h, p->motionblur,
 		                                       0.1f /* NORMALISATION_LOWPASS_COEFF, TSDRLibrary.c:37 */, flags, p->d_frames[op],
 		                                       p->h_results[slot], p->h_report[slot]))) return rc;
@@ -366,7 +376,7 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 		p->pix_read += n * nf;
 		p->stats.frames_processed += nf;
 		FrameJob j; memset(&j, 0, sizeof j);
-		j.kind = 0; j.slot = slot; j.nframes = nf; j.w = w; j.h = h;
+		j.kind = 0; j.slot = slot; j.nframes = nf; j.w = w; j.h = h; j.snr_valid = want_snr;
 		if ((rc = submit(p, j, p->s_out))) return rc;
 	}
 	// compact the pixel buffer when the consumed prefix is large
@@ -448,7 +458,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	pthread_mutex_init(&p->geo_mu, NULL); pthread_mutex_init(&p->mu, NULL);
 	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
 	geometry_locked(p);
-	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->argb_mode = 0; p->argb_inverted = 0; p->d_argb_last = NULL; p->argb_cap = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
+	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->argb_mode = 0; p->argb_inverted = 0; p->report_snr = 0; p->detect_mode = 0; p->d_argb_last = NULL; p->argb_cap = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
 	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
 	p->slot_cap = 0; p->d_capture[0] = p->d_capture[1] = NULL; p->cap_size[0] = p->cap_size[1] = 0; p->cap_fill = 0; p->cap_phase = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
@@ -543,6 +553,7 @@ int tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate) 
 int tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb) { if (!p) return TSDRGPU_EINVAL; p->retune_cb = cb; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff) { if (!p) return TSDRGPU_EINVAL; p->motionblur = coeff; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_output_argb(tsdrgpu_pipeline_t *p, int mode, int inverted) { if (!p) return TSDRGPU_EINVAL; p->argb_mode = mode != 0; p->argb_inverted = inverted != 0; return TSDRGPU_OK; }
+int tsdrgpu_pipeline_set_reports(tsdrgpu_pipeline_t *p, int report_snr, int detect_mode) { if (!p) return TSDRGPU_EINVAL; p->report_snr = report_snr != 0; p->detect_mode = detect_mode != 0; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_sync(tsdrgpu_pipeline_t *p, int pixels) { if (!p) return TSDRGPU_EINVAL; p->syncoffset += pixels; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_get_geometry(tsdrgpu_pipeline_t *p, int *width, int *height, double *refreshrate) {
 	if (!p) return TSDRGPU_EINVAL;

@@ -98,6 +98,10 @@ class Pipeline:
         same float32 array object whose bytes are int32 pixels: use frame.view(np.int32)."""
         N.check(self._lib.tsdrgpu_pipeline_set_output_argb(self._h, int(on), int(inverted)), self._ctx)
 
+    def set_reports(self, snr: bool = False, detect_mode: bool = False) -> None:
+        """on_value then also receives (4, snr, 0) beside every auto-gain report and (100, fps, height) after every pair of plots."""
+        N.check(self._lib.tsdrgpu_pipeline_set_reports(self._h, int(snr), int(detect_mode)), self._ctx)
+
     def set_param(self, name: str, value: int) -> None:
         N.check(self._lib.tsdrgpu_pipeline_set_param_int(self._h, PARAM_IDS[name], value), self._ctx)
 

@@ -76,3 +76,27 @@ def test_gauss_taps_match_oracle():
     imp = np.zeros(11, np.float32); imp[5] = 1.0
     blurred = orc.port().gaussianblur(imp)
     assert np.array_equal(np.array(taps[:], np.float32)[::-1].view(np.uint32), blurred[3:8].view(np.uint32))
+
+
+def test_detect_videomode_matches_the_gui_arithmetic():
+    """tsdrgpu_detect_videomode (host-only) against a restatement of PlotVisualizer.java:203-236 + Main.java:1301-1303,1346-1350."""
+    import ctypes as C
+    import numpy as np
+    from tempestsdr_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(8)
+    for trial in range(50):
+        fs = int(rng.integers(2_000_000, 60_000_000))
+        foff, flen = fs // 87, fs // 55 - fs // 87                     # frameratedetector.c:20-25 windows
+        loff, llen = int(fs / (1500 * 87.0)), int(fs / (590 * 55.0)) - int(fs / (1500 * 87.0))
+        fp = rng.random(flen); lp = rng.random(max(llen, 1))
+        if trial % 3 == 0:                                             # ties: the FIRST maximum wins
+            fp[[5, 9]] = 2.0; lp[[1, min(3, lp.size - 1)]] = 2.0
+        fi, li = int(np.argmax(fp)), int(np.argmax(lp))
+        want_fps = float(fs) / float(foff + fi)
+        want_h = int(np.floor((foff + fi) / float(loff + li) + 0.5))
+        fps, h, a, b = C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        rc = lib.tsdrgpu_detect_videomode(fp.ctypes.data_as(C.POINTER(C.c_double)), foff, fp.size, lp.ctypes.data_as(C.POINTER(C.c_double)), loff, lp.size,
+                                          fs, C.byref(fps), C.byref(h), C.byref(a), C.byref(b))
+        assert rc == 0 and (a.value, b.value) == (fi, li) and fps.value == want_fps and h.value == want_h
+    assert lib.tsdrgpu_detect_videomode(None, 0, 0, None, 0, 0, 1, None, None, None, None) != 0

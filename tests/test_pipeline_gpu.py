@@ -222,3 +222,50 @@ def test_pixels_argb_batch_keeps_transparent_pixels():
         assert np.array_equal(got[k], want), f"frame {k}"
         prev = want
     assert np.array_equal(last.cpu().numpy(), prev)
+
+
+def test_pipeline_optional_reports_snr_and_detected_mode():
+    """8f-4 / 8f-3: with the reports on, the value callback also carries (4, snr) beside each auto-gain report -- the SNR of
+    dsp_autogain_run (dsp.c:84-93) -- and (100, fps, height) after each pair of plots, the GUI's auto-resolution arithmetic."""
+    import ctypes as C
+    from tempestsdr_b200 import pipeline, _native
+    O = orc.best()
+    fs, h, fv = 2_000_000, 125, 60.0
+    w, _, _ = O.geometry(fs, h, fv)
+    nblk, items = 40, 65536
+    iq_all = synth.video_like_iq(nblk * items // 2, fs, w, h, fv, seed=55)
+    values, plots = [], []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=1, block_when_busy=True,
+                          params={"autoshift": 1, "lowpass_before_sync": 1},
+                          on_value=lambda vid, a, b: values.append((vid, a, b)),
+                          on_plot=lambda pid, off, v, sr: plots.append((pid, off, v.copy(), sr)))
+    p.set_reports(snr=True, detect_mode=True)
+    for k in range(nblk):
+        p.process(iq_all[k * items:(k + 1) * items].copy(), 0)
+    p.flush()
+    snrs = [a for vid, a, b in values if vid == 4]
+    gains = [(a, b) for vid, a, b in values if vid == 3]
+    assert len(snrs) == len(gains) >= 1 and all(np.isfinite(s) and s > 0 for s in snrs)
+    # the oracle's SNR for the same frames: the report comes every AUTOGAIN_REPORT_EVERY_FRAMES+2 frames (dsp.c:231)
+    pp = O.postprocessor(fs, h, fv, 1, 0)
+    rs = O.resampler()
+    mag = O.am_demod(iq_all)
+    block = int(0.1 * fs / fv)
+    pix = np.concatenate([rs.run(mag[k * block:(k + 1) * block], w * h * fv, fs) for k in range(mag.size // block)])
+    want = []
+    for k in range(pix.size // (w * h)):
+        out, res = pp.run(pix[k * w * h:(k + 1) * w * h], w, h, 0.0, 0.1, 1, 0)
+        if res.autogain_callback_fired:
+            want.append(float(res.snr))
+    assert len(want) >= len(snrs)
+    for g, wv in zip(snrs, want):
+        assert abs(g - wv) <= 1e-5 * abs(wv)               # float intermediates: 1e-5 relative (north_star)
+    det = [(a, b) for vid, a, b in values if vid == 100]
+    fplots = [(off, v, sr) for pid, off, v, sr in plots if pid == 0]
+    lplots = [(off, v, sr) for pid, off, v, sr in plots if pid == 1]
+    assert len(det) == len(fplots) == len(lplots) >= 1
+    lib = _native.lib()
+    for (fps, hh), (fo, fpv, sr), (lo, lpv, _) in zip(det, fplots, lplots):
+        fi, li = int(np.argmax(fpv)), int(np.argmax(lpv))
+        assert fps == float(sr) / float(fo + fi) and hh == float(int(np.floor((fo + fi) / float(lo + li) + 0.5)))
+    p.close()
