@@ -135,7 +135,11 @@ class DeviceStep:
     def __call__(self):
         gpu = self.gpu
         # samples -> pixels (fused demod + resample), appended behind the pixels left over from the last step
-        out = self.rs.process(self.iq, (self.block, self.nblocks), self.up, float(FS), in_is_iq=True, out=self.pix[self.pix_fill:])
+        # (the same pass also leaves the magnitudes for the frame-rate detector: one demodulation feeds both consumers,
+        # as am_demod does in the reference's process(), TSDRLibrary.c:286-292)
+        fused_mag = not os.environ.get("BENCH_SEPARATE_DEMOD")
+        out = self.rs.process(self.iq, (self.block, self.nblocks), self.up, float(FS), in_is_iq=True, out=self.pix[self.pix_fill:],
+                              mag_out=self.mag[self.mag_fill:] if fused_mag else None)
         self.pix_fill += out.numel()
         nf = min(self.pix_fill // self.n, FRAMES_PER_STEP)
         self.pp.process(self.pix[: nf * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=self.frames_out[self.k & 1][: nf * self.n], want_results=False)
@@ -147,7 +151,8 @@ class DeviceStep:
         self.frames += nf
         # frame-rate detector: the whole stream is demodulated once; every complete capture of 3.1*fs/55 samples is
         # autocorrelated (batched FFTs) and accumulated in order
-        gpu.chk(gpu._lib.tsdrgpu_am_demod(gpu._h, gpu.stream, self.iq.data_ptr(), self.pairs, self.mag.data_ptr() + 4 * self.mag_fill))
+        if not fused_mag:
+            gpu.chk(gpu._lib.tsdrgpu_am_demod(gpu._h, gpu.stream, self.iq.data_ptr(), self.pairs, self.mag.data_ptr() + 4 * self.mag_fill))
         self.mag_fill += self.pairs
         ncap = self.mag_fill // self.cap
         if ncap:
@@ -393,7 +398,7 @@ def run_ours(args):
     n_pix = step.n * FRAMES_PER_STEP
     prof_caps = (step.captures - caps_before_prof) / prof_steps          # captures autocorrelated per profiled step
     alg = {   # ALGORITHMIC bytes per launch
-        "rs_main": pairs * (8 + 4 * ratio),                      # 8 B per IQ pair in + 4 B per pixel out
+        "rs_main": pairs * (8 + 4 * ratio + (0 if os.environ.get("BENCH_SEPARATE_DEMOD") else 4)),   # 8 B per IQ pair in + 4 B per pixel out (+ 4 B magnitude out)
         "fs_minmax": 4 * n_pix, "fs_normalise": 8 * n_pix, "fs_timelowpass": 8 * n_pix, "fs_norm_lowpass": 8 * n_pix,
         "fs_collapse": 4 * n_pix, "fs_shift": 8 * n_pix, "demod_kernel": 12 * pairs,
         # one FFT pass reads and writes every complex point once; a launch covers all captures of the step (grid.y);

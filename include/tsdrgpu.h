@@ -127,6 +127,11 @@ TSDRGPU_API int  tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream, con
                                        double upsample_by, double downsample_by, int nearest_neighbour,
                                        float *d_out, uint64_t out_capacity, uint64_t *h_n_out);
 
+/* One-shot: the NEXT tsdrgpu_resampler_run with IQ input also writes |x| of every input sample to d_mag (one float per
+ * sample, blocks back to back like d_in) -- am_demod's output for the frame-rate detector (TSDRLibrary.c:286-292 feeds both
+ * consumers from one demodulated buffer) without a second pass over the IQ. */
+TSDRGPU_API int  tsdrgpu_resampler_set_mag_out(tsdrgpu_resampler_t *r, float *d_mag);
+
 /* ---------------------------------------------------------------------------- a7-a15  frame stage
  * replaces dsp_post_process + dsp_postprocess_t (dsp.c:112-239), dsp_autogain_run (:41-94),
  * dsp_timelowpass_run (:22-33), dsp_average_v_h (:96-110), syncdetector_run / findthesweetspot / findbestfit /

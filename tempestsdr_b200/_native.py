@@ -74,6 +74,7 @@ _SIGS = {
     "tsdrgpu_resampler_plan": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_double]),
     "tsdrgpu_resampler_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32,
                                         C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_resampler_set_mag_out": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_framestage_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_framestage_destroy": (None, [C.c_void_p]),
     "tsdrgpu_framestage_reset": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -226,9 +226,12 @@ class Resampler:
         return self.ctx._lib.tsdrgpu_resampler_plan(self._h, p, u, n, upsample_by, downsample_by)
 
     def process(self, x: torch.Tensor, block_sizes, upsample_by: float, downsample_by: float, nearest: bool = False,
-                in_is_iq: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Run consecutive decimator blocks.  block_sizes: sequence of sizes, or (uniform_block, nblocks)."""
+                in_is_iq: bool = False, out: Optional[torch.Tensor] = None, mag_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Run consecutive decimator blocks.  block_sizes: sequence of sizes, or (uniform_block, nblocks).
+        mag_out (IQ input only): also receives |x| of every input sample (am_demod's output for the frame-rate detector)."""
         p, u, n, keep = self._blocks(block_sizes)
+        if mag_out is not None:
+            self.ctx.chk(self.ctx._lib.tsdrgpu_resampler_set_mag_out(self._h, _f32(mag_out).data_ptr()))
         need = self.ctx._lib.tsdrgpu_resampler_plan(self._h, p, u, n, upsample_by, downsample_by)
         if out is None:
             out = torch.empty(max(int(need), 1), dtype=torch.float32, device=x.device)

@@ -38,6 +38,7 @@ struct FftPass {
 	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
 	float scale;
 	int in_real, out_abs;
+	const float2 *tw_step;                              // host-built W_M^(col (L/8) j), [col][8]; NULL: compute every twiddle
 	int exact0;                                         // the first three layers of this pass have eps = 0: plain DFT-8
 };
 
@@ -267,17 +268,8 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	float2 v[8];
 	// Inter-pass twiddles W_M^(col k): a thread's eight outputs are k = i0 + (L/8) j, j = 0..7, of ONE column, so
 	// W^(col k) = W^(col i0) * W^(col (L/8) j): one sincospif per thread for the first factor (exactly reduced argument),
-	// the second from a per-CTA table of 8 values per column (double-precision sincospi, once per CTA).
-	__shared__ float2 tw_step[8 * 32];
-	const bool tw_fast = P.tw_M != 0 && P.tw_M <= (1ull << 24) && P.c_fast_out && C <= 32 && (int) blockDim.x == C * L8 && NSTAGES > 1;
-	if (tw_fast && tid < 8 * C) {
-		const int cc = tid >> 3, j = tid & 7;
-		const unsigned col = (unsigned) ((int) g_lo * (int) P.tw_lo + cc * (int) P.tw_cs);
-		const unsigned e = (col * (unsigned) (L8 * j)) & (unsigned) (P.tw_M - 1);
-		double dsn, dcs;
-		sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs);
-		tw_step[tid] = make_float2((float) dcs, (float) dsn);
-	}
+	// the second from a host-built table of 8 values per column (double precision; P.tw_step[col * 8 + j]).
+	const bool tw_fast = P.tw_step != NULL && P.c_fast_out && (int) blockDim.x == C * L8;
 
 	// ---- stage 0: radix 8, p = 1, inputs x[i + m L/8] from global memory
 	{
@@ -362,7 +354,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 				}
 				#pragma unroll
 				for (int m = 0; m < RLAST; m++) {
-					const float2 st = tw_step[c * 8 + it + NB * m];
+					const float2 st = __ldg(P.tw_step + col * 8u + (unsigned) (it + NB * m));
 					const float2 tw = make_float2(tw_base.x * st.x - tw_base.y * st.y, tw_base.x * st.y + tw_base.y * st.x);
 					w[m] = twmul<INV>(tw, w[m]);
 				}
@@ -575,6 +567,27 @@ int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all
 	return TSDRGPU_OK;
 }
 
+// W_M^(col * L8 * j) for every column of a pass and j = 0..7 (see fft_pass_kernel), built on the host, cached
+struct StepTab { int device; unsigned long long M; unsigned ncols, L8; float2 *d; };
+std::vector<StepTab> g_step_tabs;
+int step_table(tsdrgpu_ctx_t *ctx, unsigned long long M, unsigned ncols, unsigned L8, const float2 **out) {
+	std::lock_guard<std::mutex> lock(g_tw_mu);
+	for (auto &t : g_step_tabs) if (t.device == ctx->device && t.M == M && t.ncols == ncols && t.L8 == L8) { *out = t.d; return TSDRGPU_OK; }
+	std::vector<float2> h((size_t) ncols * 8);
+	for (unsigned col = 0; col < ncols; col++)
+		for (unsigned j = 0; j < 8; j++) {
+			const unsigned long long e = ((unsigned long long) col * (unsigned long long) (L8 * j)) & (M - 1);
+			const double ang = -2.0 * 3.14159265358979323846 * ((double) e / (double) M);
+			h[(size_t) col * 8 + j] = make_float2((float) cos(ang), (float) sin(ang));
+		}
+	StepTab t; t.device = ctx->device; t.M = M; t.ncols = ncols; t.L8 = L8;
+	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float2) * h.size()));
+	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+	g_step_tabs.push_back(t);
+	*out = t.d;
+	return TSDRGPU_OK;
+}
+
 int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	if (g_table[ctx->device]) return TSDRGPU_OK;
 	float2 *t;
@@ -619,6 +632,12 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	}
 	const float2 *stw;
 	{ int rc = stage_table(ctx, P.log2L, l_base, eps_all, &stw); if (rc) return rc; }
+	P.tw_step = NULL;
+	if (P.tw_M && P.tw_M <= (1ull << 24) && P.c_fast_out && P.log2L >= 3 && P.tw_lo == P.C && P.tw_cs == 1) {
+		// columns of this pass: col = g_lo * C + c, g_lo < G_lo
+		const unsigned ncols = P.G_lo * (unsigned) P.C;
+		if (ncols <= (1u << 20)) { int rc = step_table(ctx, P.tw_M, ncols, (unsigned) (L >> 3), &P.tw_step); if (rc) return rc; }
+	}
 	P.exact0 = 1;
 	for (int sidx = 0; sidx < 3 && sidx < P.log2L; sidx++) if (eps_all && l_base + sidx < 40 && fabs(eps_all[l_base + sidx]) > 1e-10) P.exact0 = 0;
 	const size_t smem = sizeof(float2) * (size_t) total * (nstages >= 3 ? 2 : 1);

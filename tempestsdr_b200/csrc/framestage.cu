@@ -249,11 +249,15 @@ __global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__
 //   column CTA: 128 columns x all rows, stages of 16 rows, thread c owns column c;
 //   row CTA:    32 rows x all columns, stages of 64 columns (pitch 65: conflict-free), lane r of warp 0 owns row r.
 // The frame is read twice, the second time mostly from L2 (the two kinds of CTA of a frame are neighbours in the grid).
-constexpr int CL_COLS = 128, CL_CROWS = 16, CL_ROWS = 32, CL_RCOLS = 64, CL_RPITCH = CL_RCOLS + 1, CL_STAGES = 4;
-constexpr int CL_SMEM_FLOATS = CL_STAGES * (CL_CROWS * CL_COLS > CL_ROWS * CL_RPITCH ? CL_CROWS * CL_COLS : CL_ROWS * CL_RPITCH);
+constexpr int CL_COLS = 128, CL_CROWS = 16, CL_ROWS = 32, CL_RCOLS = 64, CL_STAGES = 4;
+constexpr int CL_RPITCH_V = CL_RCOLS + 4, CL_RPITCH_S = CL_RCOLS + 1;       // 16-byte rows read with LDS.128 / scalar rows, both conflict-free
+constexpr int CL_SMEM_FLOATS = CL_STAGES * (CL_CROWS * CL_COLS > CL_ROWS * CL_RPITCH_V ? CL_CROWS * CL_COLS : CL_ROWS * CL_RPITCH_V);
+// VEC: the frame's rows start on 16-byte boundaries (w % 4 == 0, aligned base): 16-byte cp.async and float4 reads of the
+// ring -- a quarter of the copy instructions, which is what bounds this kernel (ncu: issue slots, not DRAM).
+template <bool VEC>
 __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in, int w, int h, float *__restrict__ wbuf,
                                                    float *__restrict__ hbuf, int col_ctas) {
-	__shared__ float ring[CL_SMEM_FLOATS];
+	__shared__ __align__(16) float ring[CL_SMEM_FLOATS];
 	const int f = blockIdx.y, tid = threadIdx.x;
 	const float *src = in + (size_t) f * w * h;
 	if ((int) blockIdx.x < col_ctas) {
@@ -263,9 +267,17 @@ __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in,
 			if (it < nit) {
 				float *dst = ring + (it % CL_STAGES) * (CL_CROWS * CL_COLS);
 				const int y0 = it * CL_CROWS, rows = min(CL_CROWS, h - y0);
-				for (int idx = tid; idx < rows * CL_COLS; idx += 256) {
-					const int r = idx / CL_COLS, c = idx % CL_COLS;
-					if (c < cols) __pipeline_memcpy_async(dst + idx, src + (size_t) (y0 + r) * w + x0 + c, sizeof(float));
+				const float *s0 = src + (size_t) y0 * w + x0;
+				if (VEC) {
+					for (int idx = tid; idx < rows * (CL_COLS / 4); idx += 256) {
+						const int r = idx / (CL_COLS / 4), c = (idx % (CL_COLS / 4)) * 4;
+						if (c < cols) __pipeline_memcpy_async(dst + r * CL_COLS + c, s0 + r * w + c, 16);
+					}
+				} else {
+					for (int idx = tid; idx < rows * CL_COLS; idx += 256) {
+						const int r = idx / CL_COLS, c = idx % CL_COLS;
+						if (c < cols) __pipeline_memcpy_async(dst + idx, s0 + r * w + c, sizeof(float));
+					}
 				}
 			}
 			__pipeline_commit();
@@ -288,15 +300,24 @@ __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in,
 		if (tid < cols) wbuf[(size_t) f * w + x0 + tid] = acc;
 		return;
 	}
+	constexpr int RP = VEC ? CL_RPITCH_V : CL_RPITCH_S;
 	const int y0 = ((int) blockIdx.x - col_ctas) * CL_ROWS, rows = min(CL_ROWS, h - y0);
 	const int nit = (w + CL_RCOLS - 1) / CL_RCOLS;
 	auto issue = [&](int it) {
 		if (it < nit) {
-			float *dst = ring + (it % CL_STAGES) * (CL_ROWS * CL_RPITCH);
+			float *dst = ring + (it % CL_STAGES) * (CL_ROWS * RP);
 			const int c0 = it * CL_RCOLS, cols = min(CL_RCOLS, w - c0);
-			for (int idx = tid; idx < rows * CL_RCOLS; idx += 256) {
-				const int r = idx / CL_RCOLS, c = idx % CL_RCOLS;
-				if (c < cols) __pipeline_memcpy_async(dst + r * CL_RPITCH + c, src + (size_t) (y0 + r) * w + c0 + c, sizeof(float));
+			const float *s0 = src + (size_t) y0 * w + c0;
+			if (VEC) {
+				for (int idx = tid; idx < rows * (CL_RCOLS / 4); idx += 256) {
+					const int r = idx / (CL_RCOLS / 4), c = (idx % (CL_RCOLS / 4)) * 4;
+					if (c < cols) __pipeline_memcpy_async(dst + r * RP + c, s0 + r * w + c, 16);
+				}
+			} else {
+				for (int idx = tid; idx < rows * CL_RCOLS; idx += 256) {
+					const int r = idx / CL_RCOLS, c = idx % CL_RCOLS;
+					if (c < cols) __pipeline_memcpy_async(dst + r * RP + c, s0 + r * w + c, sizeof(float));
+				}
 			}
 		}
 		__pipeline_commit();
@@ -308,9 +329,15 @@ __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in,
 		__syncthreads();
 		issue(it + CL_STAGES - 1);
 		if (tid < rows) {
-			const float *buf = ring + (it % CL_STAGES) * (CL_ROWS * CL_RPITCH) + tid * CL_RPITCH;
+			const float *buf = ring + (it % CL_STAGES) * (CL_ROWS * RP) + tid * RP;
 			const int cols = min(CL_RCOLS, w - it * CL_RCOLS);
-			if (cols == CL_RCOLS) {
+			if (VEC) {
+				#pragma unroll 4
+				for (int c = 0; c < cols; c += 4) {
+					const float4 q = *reinterpret_cast<const float4 *>(buf + c);
+					acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y); acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
+				}
+			} else if (cols == CL_RCOLS) {
 				#pragma unroll 16
 				for (int c = 0; c < CL_RCOLS; c++) acc = __fadd_rn(acc, buf[c]);
 			} else for (int c = 0; c < cols; c++) acc = __fadd_rn(acc, buf[c]);
@@ -559,7 +586,7 @@ __device__ __forceinline__ void fs_prefetch_record(double *dst, const double *__
 // pipe bound at ~4 us per frame.  The cluster splits the windows in warp-sized units over its 8 SMs; per-CTA maxima travel
 // to CTA 0 through distributed shared memory, CTA 0 picks the strip size / updates dx and broadcasts the next frame's
 // candidate sizes the same way: two cluster barriers per frame.
-constexpr int FS_SEL_THREADS = 256, FS_SEL_CLUSTER = 8, FS_SEL_WARPS = FS_SEL_THREADS / 32;
+constexpr int FS_SEL_THREADS = 512, FS_SEL_CLUSTER = 8, FS_SEL_WARPS = FS_SEL_THREADS / 32;
 
 __global__ void __cluster_dims__(FS_SEL_CLUSTER, 1, 1) __launch_bounds__(FS_SEL_THREADS)
 fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, int minsize_y, int nframes,
@@ -661,10 +688,13 @@ fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, 
 					r = rank_best[0][ci];
 					for (int k = 1; k < FS_SEL_CLUSTER; k++) r = best_merge(r, rank_best[k][ci]);
 					// e = 0 is the starting value of the reference's running maximum even when it is NaN
+					// (with the certificate every score is a finite square, so this only matters on the serial-chain path)
 					const bool ok = ax ? ok_y : ok_x;
-					const double c0s = ok ? window_from_prefix(ax ? buf_y : buf_x, size, 0, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP];
-					const double s0 = fit_score((double) (ax ? tot_y : tot_x), c0s, (double) (size - strip), (double) strip);
-					if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
+					if (!ok || r.e == 0x7fffffff) {
+						const double c0s = ok ? window_from_prefix(ax ? buf_y : buf_x, size, 0, strip) : chain_scratch[(size_t) ci * FS_MAX_STRIP];
+						const double s0 = fit_score((double) (ax ? tot_y : tot_x), c0s, (double) (size - strip), (double) strip);
+						if (!(s0 == s0) || r.e == 0x7fffffff) { r.score = s0; r.e = 0; }
+					}
 				}
 				cand_best[ax][t] = r;
 			}
@@ -1043,7 +1073,9 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 
 	// collapse on `stream`, then sync search on `s2` (== stream unless overlapped)
 	auto collapse_sync = [&](const float *src, cudaStream_t s2) -> int {
-		KL(ctx, "fs_collapse", stream, fs_collapse<<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
+		const bool cvec = (w % 4 == 0) && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0);
+		if (cvec) KL(ctx, "fs_collapse", stream, fs_collapse<true><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
+		else KL(ctx, "fs_collapse", stream, fs_collapse<false><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
 		if (s2 != stream) {
 			CU_TRY(ctx, cudaEventRecord(fs->ev_ready[ph], stream));
 			CU_TRY(ctx, cudaStreamWaitEvent(s2, fs->ev_ready[ph], 0));
@@ -1171,7 +1203,9 @@ int tsdrgpu_average_v_h(tsdrgpu_ctx_t *ctx, void *stream, int w, int h, const fl
 	BIND(ctx);
 	ARG_TRY(ctx, w > 0 && h > 0 && d_in && d_wbuf && d_hbuf);
 	const int col_ctas = (w + CL_COLS - 1) / CL_COLS, row_ctas = (h + CL_ROWS - 1) / CL_ROWS;
-	KL(ctx, "fs_collapse", (cudaStream_t) stream, fs_collapse<<<dim3(col_ctas + row_ctas, 1), 256, 0, (cudaStream_t) stream>>>(d_in, w, h, d_wbuf, d_hbuf, col_ctas));
+	if ((w % 4 == 0) && ((reinterpret_cast<unsigned long long>(d_in) & 15ull) == 0))
+		KL(ctx, "fs_collapse", (cudaStream_t) stream, fs_collapse<true><<<dim3(col_ctas + row_ctas, 1), 256, 0, (cudaStream_t) stream>>>(d_in, w, h, d_wbuf, d_hbuf, col_ctas));
+	else KL(ctx, "fs_collapse", (cudaStream_t) stream, fs_collapse<false><<<dim3(col_ctas + row_ctas, 1), 256, 0, (cudaStream_t) stream>>>(d_in, w, h, d_wbuf, d_hbuf, col_ctas));
 	return TSDRGPU_OK;
 }
 

@@ -66,7 +66,8 @@ __device__ __forceinline__ bool rs_isA(const Geo &g, double Pkm1) { return Pkm1 
 template <bool IQ>
 __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ in, float *__restrict__ out,
                                                       const RsBlock *__restrict__ blocks,
-                                                      const uint2 *__restrict__ tile_info /* {block, first sample} per tile */) {
+                                                      const uint2 *__restrict__ tile_info /* {block, first sample} per tile */,
+                                                      float *__restrict__ mag_out /* optional: |x| of every input sample, same indexing as `in` */) {
 	__shared__ float s_mag[RS_HALO + RS_TILE];
 	__shared__ __align__(16) float s_out[RS_OUT_CAP + 8];
 
@@ -83,7 +84,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 		const unsigned long long first = B.in_start + s0 - halo;
 		float *dst = s_mag + (RS_HALO - halo);
 		#pragma unroll 8
-		for (unsigned i = threadIdx.x; i < n_load; i += RS_THREADS) dst[i] = rs_load<IQ>(in, first + i);
+		for (unsigned i = threadIdx.x; i < n_load; i += RS_THREADS) {
+			const float m = rs_load<IQ>(in, first + i);
+			dst[i] = m;
+			if (IQ && mag_out != NULL && i >= halo) mag_out[first + i] = m;      // the demodulated stream, for the frame-rate detector
+		}
 	}
 	const double pbase_d = (s0 == 0) ? 0.0 : rs_P(rs_geo(s0 - 1, r, phase).c);
 	const double pend_d = rs_P(rs_geo(s1 - 1, r, phase).c);
@@ -287,6 +292,7 @@ struct tsdrgpu_resampler {
 	static constexpr int SLOTS = 4;
 	void *h_desc[SLOTS]; void *d_desc[SLOTS]; size_t desc_bytes[SLOTS]; cudaEvent_t ev[SLOTS]; int next;
 	double *d_bank; int *d_has_a; size_t bank_cap;
+	float *d_mag_next;         // one-shot: the next IQ run also writes the magnitudes here (tsdrgpu_resampler_set_mag_out)
 };
 
 extern "C" {
@@ -326,6 +332,12 @@ void tsdrgpu_resampler_destroy(tsdrgpu_resampler_t *r) {
 	if (r->d_bank) cudaFree(r->d_bank);
 	if (r->d_has_a) cudaFree(r->d_has_a);
 	delete r;
+}
+
+int tsdrgpu_resampler_set_mag_out(tsdrgpu_resampler_t *r, float *d_mag) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, r != NULL);
+	r->d_mag_next = d_mag;
+	return TSDRGPU_OK;
 }
 
 int tsdrgpu_resampler_reset(tsdrgpu_resampler_t *r, void *stream) {
@@ -411,6 +423,8 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 	const RsBlock *db = (const RsBlock *) r->d_desc[slot];
 	const uint2 *dp = (const uint2 *) (db + nblocks);
 
+	float *mag = r->d_mag_next; r->d_mag_next = NULL;
+	if (mag && (!in_is_iq || nearest)) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "magnitude output needs IQ input and the box resampler", cudaSuccess, __FILE__, __LINE__);
 	if (nearest) {
 		dim3 grid((max_out + 1023) / 1024, nblocks);
 		if (in_is_iq) KL(ctx, "rs_nearest", stream, rs_nearest<true><<<grid, 256, 0, stream>>>(d_in, d_out, db));
@@ -422,8 +436,8 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			CU_TRY(ctx, cudaMalloc(&r->d_bank, sizeof(double) * r->bank_cap));
 			CU_TRY(ctx, cudaMalloc(&r->d_has_a, sizeof(int) * r->bank_cap));
 		}
-		if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp));
-		else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp));
+		if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+		else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
 		if (in_is_iq) KL(ctx, "rs_fixup", stream, rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 		else KL(ctx, "rs_fixup", stream, rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 	}

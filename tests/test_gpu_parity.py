@@ -92,9 +92,15 @@ def test_resample_stream(gpu, O, name, nearest, fused):
     r = gpu.resampler()
     x = dev(iq) if fused else dev(mag)
     # two calls: state (contrib on device, offset on host) must carry across calls exactly
-    a = r.process(x[: (2 if fused else 1) * sum(sizes[:5])], sizes[:5], up, fs, nearest, in_is_iq=fused).clone()
+    want_mag = fused and not nearest                        # the fused pass can also leave am_demod's output (one demodulation, two consumers)
+    mag_a = torch.full((sum(sizes[:5]) + 3,), -1.0, device="cuda") if want_mag else None
+    a = r.process(x[: (2 if fused else 1) * sum(sizes[:5])], sizes[:5], up, fs, nearest, in_is_iq=fused, mag_out=mag_a).clone()
     b = r.process(x[(2 if fused else 1) * sum(sizes[:5]):], sizes[5:], up, fs, nearest, in_is_iq=fused)
     got = torch.cat([a, b]).cpu().numpy()
+    if want_mag:
+        m = mag_a.cpu().numpy()
+        assert_same_bits(m[:-3], mag[: sum(sizes[:5])], "magnitudes from the fused pass")
+        assert np.all(m[-3:] == -1.0)                      # nothing written past the input
     if stale:
         assert np.all(got[stale] == 0.0)
         want = want.copy(); want[stale] = 0.0

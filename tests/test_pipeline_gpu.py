@@ -180,6 +180,7 @@ def test_pipeline_argb_output_and_raw_int8_ingest(inverted):
     pushed through the oracle's pixel rule with a persistent host pixel buffer."""
     from tempestsdr_b200 import pipeline
     O = orc.best()
+    P = orc.port()                                         # the host pixel rule lives in the JNI glue: restated in the port only
     fs, h, fv = 2_000_000, 125, 60.0
     w, _, _ = O.geometry(fs, h, fv)
     nblk, items = 16, 65536
@@ -198,14 +199,14 @@ def test_pipeline_argb_output_and_raw_int8_ingest(inverted):
     p.flush()
     assert 4 <= len(got) <= len(frames)
     for k, g in enumerate(got):
-        assert np.array_equal(g, O.pixels_argb(frames[k], inverted)), f"frame {k}"
+        assert np.array_equal(g, P.pixels_argb(frames[k], inverted)), f"frame {k}"
     p.close()
 
 
 def test_pixels_argb_batch_keeps_transparent_pixels():
     from tempestsdr_b200 import _native
     from tempestsdr_b200.api import Context
-    O = orc.best()
+    O = orc.port()
     gpu = Context(0)
     rng = np.random.default_rng(3)
     n, nf = 1000, 5
