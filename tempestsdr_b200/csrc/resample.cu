@@ -59,6 +59,7 @@ __device__ __forceinline__ double rs_t(const Geo &g, double Pk, double r, double
 	if (Pk < g.hi && Pk > g.lo) return __dmul_rn(__dsub_rn(g.hi, Pk), v);
 	return __dmul_rn(r, v);
 }
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
 // does sample k emit an A pixel?  (dsp.c:288)
 __device__ __forceinline__ bool rs_isA(const Geo &g, double Pkm1) { return Pkm1 < g.lo && Pkm1 < g.c; }
 
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 	// staging index = (p - pbase) + aoff, chosen so that shared and global addresses are congruent modulo 16 bytes
 	const unsigned aoff = (unsigned) ((reinterpret_cast<unsigned long long>(gout + pbase) >> 2) & 3ull);
 	float *sq = s_out + aoff;
+	const unsigned sq_addr = (unsigned) __cvta_generic_to_shared(sq);
 	__syncthreads();
 
 	// One warp owns 256 CONSECUTIVE samples, 32 per round: what sample k needs from sample k-1 (its pid, whether it emitted
@@ -106,33 +108,41 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const unsigned wbase = s0 + warp * (RS_TILE / (RS_THREADS / 32));
 	if (wbase < s1) {
-		double carryP = 0.0, carryT = 0.0; int carryA = 0;
+		// "the sample before" lives in lane 31's old* registers: in round 0 it is sample wbase-1, later the previous round's
+		// lane 31.  One rotate-by-one shuffle per quantity then serves every lane (lane 31 contributes its OLD value, which
+		// nobody else needs this round; lane 0 receives it).
+		double oldP = 0.0, oldT = 0.0; int oldA = 0;
 		if (wbase > 0) {                                         // the sample just before this warp's range (once per warp)
 			const unsigned kp = wbase - 1;
 			const Geo gp = rs_geo(kp, r, phase);
-			carryP = rs_P(gp.c);
+			oldP = rs_P(gp.c);
 			const double Ppm1 = (kp == 0) ? 0.0 : rs_P(rs_geo(kp - 1, r, phase).c);
-			carryA = rs_isA(gp, Ppm1);
+			oldA = rs_isA(gp, Ppm1);
 			const float vp = (kp + RS_HALO >= s0) ? s_mag[RS_HALO + kp - s0] : rs_load<IQ>(in, B.in_start + kp);
-			carryT = rs_t(gp, carryP, r, (double) vp);
+			oldT = rs_t(gp, oldP, r, (double) vp);
 		}
-		for (unsigned base = wbase; base < min(wbase + (unsigned) (RS_TILE / (RS_THREADS / 32)), s1); base += 32) {
+		const unsigned wend = min(wbase + (unsigned) (RS_TILE / (RS_THREADS / 32)), s1);
+		const unsigned from = (lane + 31u) & 31u;
+		const bool is_last = lane == 31u;
+		double kd = (double) (wbase + lane);                     // exact; advanced by 32.0 per round instead of converted
+		const float *sm = s_mag + RS_HALO + (wbase - s0) + lane;
+		for (unsigned base = wbase; base < wend; base += 32, kd = __dadd_rn(kd, 32.0), sm += 32) {
 			const unsigned k = base + lane;
-			const bool live = k < s1;
-			const unsigned kk = live ? k : (s1 - 1);             // idle lanes shadow the last sample (results unused)
-			const Geo g = rs_geo(kk, r, phase);
-			const double Pk = rs_P(g.c);
-			const float vf = s_mag[RS_HALO + (kk - s0)];
+			Geo g;
+			g.lo = __dadd_rn(__dmul_rn(kd, r), phase);
+			g.hi = __dadd_rn(g.lo, r);
+			g.c = __dadd_rn(g.hi, -1.0);
+			double Pk = ceil(g.c);                               // == rs_P: fmax(0, ceil(c))
+			if (!(g.c > 0.0)) Pk = 0.0;
+			const float vf = *sm;                                // lanes past the tile's end read a valid slot; their results are unused
 			const double v = (double) vf;
-			const double tk = rs_t(g, Pk, r, v);
-			double Pkm1 = __shfl_up_sync(0xffffffffu, Pk, 1);
-			if (lane == 0) Pkm1 = carryP;
+			const double tk = __dmul_rn((Pk < g.hi && Pk > g.lo) ? __dsub_rn(g.hi, Pk) : r, v);     // == rs_t
+			const double Pkm1 = __shfl_sync(0xffffffffu, is_last ? oldP : Pk, from);
 			const bool isA = rs_isA(g, Pkm1);
-			int prevA = __shfl_up_sync(0xffffffffu, (int) isA, 1);
-			double prevT = __shfl_up_sync(0xffffffffu, tk, 1);
-			if (lane == 0) { prevA = carryA; prevT = carryT; }
-			carryP = __shfl_sync(0xffffffffu, Pk, 31); carryA = __shfl_sync(0xffffffffu, (int) isA, 31); carryT = __shfl_sync(0xffffffffu, tk, 31);
-			if (!live) continue;
+			const int prevA = __shfl_sync(0xffffffffu, is_last ? oldA : (int) isA, from);
+			const double prevT = __shfl_sync(0xffffffffu, is_last ? oldT : tk, from);
+			oldP = Pk; oldA = (int) isA; oldT = tk;
+			if (k >= s1) continue;
 			const unsigned p0 = (unsigned) Pkm1, cnt = (unsigned) Pk - p0;
 			float first = vf;
 			bool write_first = true;
@@ -164,11 +174,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 				} else write_first = false;      // the bank reaches past the block start -> rs_fixup writes this pixel
 			}
 			if (staged) {
-				float *d = sq + (p0 - pbase);
-				if (cnt > 0 && write_first) d[0] = first;
-				if (cnt > 1) d[1] = vf;
-				if (cnt > 2) d[2] = vf;
-				for (unsigned c = 3; c < cnt; c++) d[c] = vf;
+				const unsigned d = sq_addr + ((p0 - pbase) << 2);   // 32-bit shared address: one add per store
+				if (cnt > 0 && write_first) sts_f32(d, first);
+				if (cnt > 1) sts_f32(d + 4, vf);
+				if (cnt > 2) sts_f32(d + 8, vf);
+				for (unsigned c = 3; c < cnt; c++) sts_f32(d + 4 * c, vf);
 			} else {
 				for (unsigned c = 0; c < cnt; c++) {
 					const unsigned p = p0 + c;
