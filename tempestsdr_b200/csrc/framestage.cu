@@ -346,6 +346,83 @@ __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in,
 	if (tid < rows) hbuf[(size_t) f * h + y0 + tid] = acc;
 }
 
+// ---- the same kernel with the copies handed to the TMA engine -----------------------------------------------------------
+// ncu on the cp.async version: bound by issue slots, i.e. by the copy instructions themselves.  Here the rows of a stage are
+// 1-D bulk copies (cp.async.bulk, SASS UBLKCP): one lane of warp 0 issues one row (512 B for a column CTA, 256 B for a row
+// CTA), completion is counted in bytes on the stage's mbarrier, the owner threads wait on it and add.  128 threads per CTA:
+// nobody is needed for copying.  Requires 16-byte aligned rows (w % 4 == 0), as the VEC variant.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+	             :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_row(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+constexpr int CL_TMA_THREADS = 128;
+__global__ void __launch_bounds__(CL_TMA_THREADS) fs_collapse_tma(const float *__restrict__ in, int w, int h, float *__restrict__ wbuf,
+                                                                  float *__restrict__ hbuf, int col_ctas) {
+	__shared__ __align__(128) float ring[CL_SMEM_FLOATS];
+	__shared__ __align__(8) unsigned long long bars[CL_STAGES];
+	const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const float *src = in + (size_t) f * w * h;
+	const unsigned ring_a = (unsigned) __cvta_generic_to_shared(ring), bar_a = (unsigned) __cvta_generic_to_shared(bars);
+	if (tid == 0) {
+		for (int st = 0; st < CL_STAGES; st++) mbar_init(bar_a + 8 * st, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const bool colcta = (int) blockIdx.x < col_ctas;
+	// geometry of this CTA's slab: `nrows` rows per stage of `rowbytes` bytes, `nit` stages
+	const int x0 = colcta ? blockIdx.x * CL_COLS : 0, y0 = colcta ? 0 : ((int) blockIdx.x - col_ctas) * CL_ROWS;
+	const int cols = colcta ? min(CL_COLS, w - x0) : 0, rows = colcta ? 0 : min(CL_ROWS, h - y0);
+	const int nit = colcta ? (h + CL_CROWS - 1) / CL_CROWS : (w + CL_RCOLS - 1) / CL_RCOLS;
+	auto issue = [&](int it) {                           // warp 0 only
+		if (it >= nit) return;
+		const unsigned bar = bar_a + 8 * (it % CL_STAGES);
+		if (colcta) {
+			const int r0 = it * CL_CROWS, nr = min(CL_CROWS, h - r0);
+			if (lane == 0) mbar_expect_tx(bar, (unsigned) (nr * cols * 4));
+			__syncwarp();
+			if (lane < nr) tma_row(ring_a + 4u * (unsigned) ((it % CL_STAGES) * (CL_CROWS * CL_COLS) + lane * CL_COLS), src + (size_t) (r0 + lane) * w + x0, (unsigned) (cols * 4), bar);
+		} else {
+			const int c0 = it * CL_RCOLS, nc = min(CL_RCOLS, w - c0);
+			if (lane == 0) mbar_expect_tx(bar, (unsigned) (rows * nc * 4));
+			__syncwarp();
+			if (lane < rows) tma_row(ring_a + 4u * (unsigned) ((it % CL_STAGES) * (CL_ROWS * CL_RPITCH_V) + lane * CL_RPITCH_V), src + (size_t) (y0 + lane) * w + c0, (unsigned) (nc * 4), bar);
+		}
+	};
+	if (warp == 0) for (int st = 0; st < CL_STAGES - 1; st++) issue(st);
+	float acc = 0.0f;
+	const bool owner = colcta ? (tid < cols) : (tid < rows);
+	for (int it = 0; it < nit; it++) {
+		__syncthreads();                                 // everybody is done with the buffer of stage it-1: it may be refilled
+		if (warp == 0) issue(it + CL_STAGES - 1);
+		if (owner) {
+			mbar_wait(bar_a + 8 * (it % CL_STAGES), (unsigned) ((it / CL_STAGES) & 1));
+			if (colcta) {
+				const float *buf = ring + (it % CL_STAGES) * (CL_CROWS * CL_COLS) + tid;
+				const int nr = min(CL_CROWS, h - it * CL_CROWS);
+				if (nr == CL_CROWS) {
+					#pragma unroll
+					for (int r = 0; r < CL_CROWS; r++) acc = __fadd_rn(acc, buf[r * CL_COLS]);
+				} else for (int r = 0; r < nr; r++) acc = __fadd_rn(acc, buf[r * CL_COLS]);
+			} else {
+				const float *buf = ring + (it % CL_STAGES) * (CL_ROWS * CL_RPITCH_V) + tid * CL_RPITCH_V;
+				const int nc = min(CL_RCOLS, w - it * CL_RCOLS);
+				#pragma unroll 4
+				for (int c = 0; c < nc; c += 4) {
+					const float4 q = *reinterpret_cast<const float4 *>(buf + c);
+					acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y); acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
+				}
+			}
+		}
+	}
+	if (owner) { if (colcta) wbuf[(size_t) f * w + x0 + tid] = acc; else hbuf[(size_t) f * h + y0 + tid] = acc; }
+}
+
 // ---------------------------------------------------------------- sync search (syncdetector.c:26-153, gaussian.c)
 struct SweetIn { int size, minsize; double lowpass; };
 
@@ -1074,7 +1151,9 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	// collapse on `stream`, then sync search on `s2` (== stream unless overlapped)
 	auto collapse_sync = [&](const float *src, cudaStream_t s2) -> int {
 		const bool cvec = (w % 4 == 0) && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0);
-		if (cvec) KL(ctx, "fs_collapse", stream, fs_collapse<true><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
+		static const bool no_tma = getenv("TSDRGPU_NO_TMA") != NULL;
+		if (cvec && !no_tma) KL(ctx, "fs_collapse", stream, fs_collapse_tma<<<dim3(col_ctas + row_ctas, nframes), CL_TMA_THREADS, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
+		else if (cvec) KL(ctx, "fs_collapse", stream, fs_collapse<true><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
 		else KL(ctx, "fs_collapse", stream, fs_collapse<false><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
 		if (s2 != stream) {
 			CU_TRY(ctx, cudaEventRecord(fs->ev_ready[ph], stream));

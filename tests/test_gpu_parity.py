@@ -201,6 +201,33 @@ def test_post_process_sequence(gpu, O, lpbs, aap, autoshift, mb, batches):
         k += nb
 
 
+@pytest.mark.parametrize("name", ["cfg2", "cfg5", "odd"])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_post_process_full_size_frames(gpu, O, name, overlap):
+    """The frame stage at BASELINE's real frame sizes (740x1125, 1481x1125) and at an odd width (no 16-byte rows: the
+    scalar collapse path), default GUI stage order, two batches, with and without the side-stream overlap."""
+    from tempestsdr_b200.api import PostProcessFlags
+    fs, hgt, fv = CFGS[name]
+    w, _, _ = O.geometry(fs, hgt, fv)
+    po = O.postprocessor(fs, hgt, fv, 1, 0)
+    frames = [synth.video_like_frame(w, hgt, seed=40 + k, shift_x=(70 + 31 * k) % w, shift_y=(25 + 11 * k) % hgt) for k in range(5)]
+    want = [po.run(f, w, hgt, 0.0, 0.1, 1, 0) for f in frames]
+    pg = gpu.post_processor()
+    pg.set_overlap(overlap)
+    flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True)
+    k = 0
+    outs = []
+    for nb in (2, 3):
+        x = dev(np.concatenate(frames[k:k + nb]))
+        out = torch.empty(nb * w * hgt, dtype=torch.float32, device="cuda")
+        pg.process(x, w, hgt, 0.0, 0.1, flags, out=out, want_results=False)
+        outs.append(out); k += nb
+    pg.join(); torch.cuda.synchronize()
+    got = torch.cat(outs).cpu().numpy().reshape(5, -1)
+    for i in range(5):
+        assert_same_bits(got[i], want[i][0], f"{name} frame {i}")
+
+
 @pytest.mark.parametrize("mode", ["forced_serial", "wide_dynamic_range", "denormals"])
 def test_sync_search_serial_fallback(gpu, O, mode, monkeypatch):
     """The sync search replaces the reference's serial sliding sums by exact prefix sums when a per-strip exactness
