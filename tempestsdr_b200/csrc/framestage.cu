@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(256) fs_collapse(const float *__restrict__ in,
 // ncu on the cp.async version: bound by issue slots, i.e. by the copy instructions themselves.  Here the rows of a stage are
 // 1-D bulk copies (cp.async.bulk, SASS UBLKCP): one lane of warp 0 issues one row (512 B for a column CTA, 256 B for a row
 // CTA), completion is counted in bytes on the stage's mbarrier, the owner threads wait on it and add.  128 threads per CTA:
-// nobody is needed for copying.  Requires 16-byte aligned rows (w % 4 == 0), as the VEC variant.
+// nobody is needed for copying.  Requires 16-byte aligned rows (w % 4 == 0), as the VEC variant.  Measured slower than the
+// cp.async ring at this slab shape (many small rows: the TMA unit's request rate binds), hence opt-in (TSDRGPU_COLLAPSE_TMA=1).
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
@@ -1151,8 +1152,10 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 	// collapse on `stream`, then sync search on `s2` (== stream unless overlapped)
 	auto collapse_sync = [&](const float *src, cudaStream_t s2) -> int {
 		const bool cvec = (w % 4 == 0) && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0);
-		static const bool no_tma = getenv("TSDRGPU_NO_TMA") != NULL;
-		if (cvec && !no_tma) KL(ctx, "fs_collapse", stream, fs_collapse_tma<<<dim3(col_ctas + row_ctas, nframes), CL_TMA_THREADS, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
+		// measured (64 frames of 740x1125): cp.async ring 90 us, TMA ring 115 us -- 1.3 M bulk copies of 256-512 B per launch
+		// are bound by the TMA unit's request rate, so the cp.async variant is the default and TMA is opt-in
+		const bool use_tma = getenv("TSDRGPU_COLLAPSE_TMA") != NULL;
+		if (cvec && use_tma) KL(ctx, "fs_collapse", stream, fs_collapse_tma<<<dim3(col_ctas + row_ctas, nframes), CL_TMA_THREADS, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
 		else if (cvec) KL(ctx, "fs_collapse", stream, fs_collapse<true><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
 		else KL(ctx, "fs_collapse", stream, fs_collapse<false><<<dim3(col_ctas + row_ctas, nframes), 256, 0, stream>>>(src, w, h, fs->d_wstrips[ph], fs->d_hstrips[ph], col_ctas));
 		if (s2 != stream) {

@@ -202,8 +202,8 @@ def test_post_process_sequence(gpu, O, lpbs, aap, autoshift, mb, batches):
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg5", "odd"])
-@pytest.mark.parametrize("overlap", [False, True])
-def test_post_process_full_size_frames(gpu, O, name, overlap):
+@pytest.mark.parametrize("overlap", [False, True, "tma"])
+def test_post_process_full_size_frames(gpu, O, name, overlap, monkeypatch):
     """The frame stage at BASELINE's real frame sizes (740x1125, 1481x1125) and at an odd width (no 16-byte rows: the
     scalar collapse path), default GUI stage order, two batches, with and without the side-stream overlap."""
     from tempestsdr_b200.api import PostProcessFlags
@@ -212,8 +212,10 @@ def test_post_process_full_size_frames(gpu, O, name, overlap):
     po = O.postprocessor(fs, hgt, fv, 1, 0)
     frames = [synth.video_like_frame(w, hgt, seed=40 + k, shift_x=(70 + 31 * k) % w, shift_y=(25 + 11 * k) % hgt) for k in range(5)]
     want = [po.run(f, w, hgt, 0.0, 0.1, 1, 0) for f in frames]
+    if overlap == "tma":                                   # the opt-in TMA (cp.async.bulk + mbarrier) variant of the collapse kernel
+        monkeypatch.setenv("TSDRGPU_COLLAPSE_TMA", "1")
     pg = gpu.post_processor()
-    pg.set_overlap(overlap)
+    pg.set_overlap(bool(overlap))
     flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True)
     k = 0
     outs = []
