@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 	// staging index = (p - pbase) + aoff, chosen so that shared and global addresses are congruent modulo 16 bytes
 	const unsigned aoff = (unsigned) ((reinterpret_cast<unsigned long long>(gout + pbase) >> 2) & 3ull);
 	float *sq = s_out + aoff;
-	const unsigned sq_addr = (unsigned) __cvta_generic_to_shared(sq);
+	const unsigned sq_addr = (unsigned) __cvta_generic_to_shared(s_out) + (aoff << 2);      // array base folds to a constant
 	__syncthreads();
 
 	// One warp owns 256 CONSECUTIVE samples, 32 per round: what sample k needs from sample k-1 (its pid, whether it emitted
