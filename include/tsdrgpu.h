@@ -58,6 +58,11 @@ TSDRGPU_API int tsdrgpu_profile_collect(tsdrgpu_ctx_t *ctx, char *names, double 
 /* plumbing for C hosts that do not bring their own allocator (Python callers use torch tensors instead) */
 TSDRGPU_API int tsdrgpu_malloc(tsdrgpu_ctx_t *ctx, size_t bytes, void **d_ptr);
 TSDRGPU_API int tsdrgpu_free(tsdrgpu_ctx_t *ctx, void *d_ptr);
+/* one process per GPU on one node: map another rank's tsdrgpu_malloc'd buffer into this process (CUDA IPC, NVLink peer
+ * access); the 64-byte handle travels by whatever means the ranks already have (torch.distributed all_gather_object) */
+TSDRGPU_API int tsdrgpu_ipc_export(tsdrgpu_ctx_t *ctx, void *d_ptr, uint8_t handle[64]);
+TSDRGPU_API int tsdrgpu_ipc_import(tsdrgpu_ctx_t *ctx, const uint8_t handle[64], void **d_ptr);
+TSDRGPU_API int tsdrgpu_ipc_release(tsdrgpu_ctx_t *ctx, void *d_ptr);
 TSDRGPU_API int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr);   /* pinned */
 TSDRGPU_API int tsdrgpu_free_host(tsdrgpu_ctx_t *ctx, void *h_ptr);
 TSDRGPU_API int tsdrgpu_memcpy_h2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *h_src, size_t bytes);
@@ -258,6 +263,13 @@ TSDRGPU_API int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream, float *c
  *   the strided residue s of the output (y[H*p + s], p < N) -- see DESIGN.md "superbandwidth decomposition". */
 TSDRGPU_API int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream, const float *d_hop, int count_pairs,
                                             int best_offset_floats, float *d_spectrum);
+/* tsdrgpu_superb_local_spectra with the all-gather fused into the transforms: the last pass of each FFT stores its result
+ * into the gather buffer of every rank (d_peer_bufs[p], host array of nhops device pointers; the peers' buffers mapped with
+ * tsdrgpu_ipc_import) at slot `rank` ([X | D] at complex offset rank*block_stride_complex).  The caller then only needs a
+ * barrier across the ranks before reading its own buffer. */
+TSDRGPU_API int tsdrgpu_superb_local_spectra_scatter(tsdrgpu_ctx_t *ctx, void *stream, const float *d_hop, int count_pairs, int samples_in_frame,
+                                                     float *const *d_peer_bufs, int nhops, int rank, uint64_t block_stride_complex,
+                                                     uint32_t *h_n, uint32_t *h_nd);
 /* the same with ONE exchange in total: every rank sends [FFT_N(raw hop) | FFT_nd(first
  * difference of |hop|)] (n + nd complex, returned in *h_n / *h_nd), one all-gather, then every rank derives the
  * integer alignment lags itself (tsdrgpu_superb_lags, exact) and applies them as spectral phase ramps while mixing. */

@@ -127,6 +127,11 @@ _SIGS = {
     "tsdrgpu_pipeline_set_samplerate": (C.c_int, [C.c_void_p, C.c_uint32]),
     "tsdrgpu_pipeline_set_retune": (C.c_int, [C.c_void_p, RETUNE_CB]),
     "tsdrgpu_pipeline_set_motionblur": (C.c_int, [C.c_void_p, C.c_float]),
+    "tsdrgpu_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tsdrgpu_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tsdrgpu_ipc_release": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tsdrgpu_superb_local_spectra_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                                       C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "tsdrgpu_pipeline_set_reports": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "tsdrgpu_detect_videomode": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_uint32,
                                            C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -1,5 +1,6 @@
 // ctx.cu -- context, memory and stream plumbing of libtsdrgpu (include/tsdrgpu.h, "context" section).
 #include "common.cuh"
+#include <string.h>
 
 thread_local char g_tsdrgpu_err[512] = "";
 
@@ -69,6 +70,28 @@ int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr) {
 	return TSDRGPU_OK;
 }
 int tsdrgpu_free_host(tsdrgpu_ctx_t *ctx, void *h_ptr) { BIND(ctx); CU_TRY(ctx, cudaFreeHost(h_ptr)); return TSDRGPU_OK; }
+// ---- peer access between the processes of one node (one process per GPU): CUDA IPC handles of tsdrgpu_malloc'd buffers
+int tsdrgpu_ipc_export(tsdrgpu_ctx_t *ctx, void *d_ptr, uint8_t handle[64]) {
+	BIND(ctx); ARG_TRY(ctx, d_ptr != NULL && handle != NULL);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	CU_TRY(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+	memcpy(handle, &h, 64);
+	return TSDRGPU_OK;
+}
+int tsdrgpu_ipc_import(tsdrgpu_ctx_t *ctx, const uint8_t handle[64], void **d_ptr) {
+	BIND(ctx); ARG_TRY(ctx, d_ptr != NULL && handle != NULL);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	CU_TRY(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_ipc_release(tsdrgpu_ctx_t *ctx, void *d_ptr) {
+	BIND(ctx);
+	if (d_ptr) CU_TRY(ctx, cudaIpcCloseMemHandle(d_ptr));
+	return TSDRGPU_OK;
+}
+
 int tsdrgpu_memcpy_h2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *h_src, size_t bytes) {
 	BIND(ctx);
 	CU_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream));

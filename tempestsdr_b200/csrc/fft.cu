@@ -39,6 +39,7 @@ struct FftPass {
 	float scale;
 	int in_real, out_abs;
 	const float2 *tw_step;                              // host-built W_M^(col (L/8) j), [col][8]; NULL: compute every twiddle
+	float2 *fan[16]; int nfan;                          // FAN kernels: the last stage stores to every fan[p] + offset instead of `out`
 	int exact0;                                         // the first three layers of this pass have eps = 0: plain DFT-8
 };
 
@@ -248,7 +249,7 @@ __device__ __forceinline__ void bf2(float2 *v, const float2 *__restrict__ tw, in
 	v[0] = cadd(lo, hi); v[1] = csub(lo, hi);
 }
 
-template <int LOG2L, bool INV>
+template <int LOG2L, bool INV, bool FAN = false>
 __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float2 *__restrict__ stw) {
 	extern __shared__ float2 s[];
 	constexpr int L = 1 << LOG2L, NST8 = LOG2L / 3, RL = LOG2L % 3;
@@ -378,7 +379,17 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 				}
 			}
 		}
-		if (P.out_abs) {
+		if (FAN) {
+			// fused "transform + all-gather": the result goes straight into every peer's gather buffer (NVLink peer stores;
+			// fan[own rank] is local memory), so the exchange overlaps the transform instead of following it
+			const long long ob = (gout - out) + (long long) c * (int) P.out_cs;
+			#pragma unroll
+			for (int m = 0; m < RLAST; m++) {
+				const float2 val = make_float2(w[m].x * P.scale, w[m].y * P.scale);
+				const long long idx = ob + (long long) (i + m * PL) * ks;
+				for (int pr = 0; pr < P.nfan; pr++) P.fan[pr][idx] = val;
+			}
+		} else if (P.out_abs) {
 			#pragma unroll
 			for (int m = 0; m < RLAST; m++) {
 				const float x = w[m].x * P.scale, y = w[m].y * P.scale;
@@ -598,16 +609,20 @@ int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	g_table[ctx->device] = t;
 	const int max_smem = (int) (2 * sizeof(float2) * FFT_MAX_ELEMS);     // ping-pong
 #define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
 	SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
 #undef SET_ATTR
 	return TSDRGPU_OK;
 }
 
-int bundle_for(int log2L, unsigned long long lines) {
+int bundle_for(int log2L, unsigned long long lines, bool contiguous_lines = false) {
 	const int L = 1 << log2L;
 	int C = 4096 / L; if (C < 8) C = 8;
 	while ((long long) C * L > FFT_MAX_ELEMS) C >>= 1;
+	// experiment knob: smaller bundles (more, smaller CTAs per SM) on passes whose lines are contiguous in memory
+	static const int small = getenv("TSDRGPU_FFT_SMALL_BUNDLE") ? atoi(getenv("TSDRGPU_FFT_SMALL_BUNDLE")) : 0;
+	if (contiguous_lines && small >= 512) while ((long long) C * L > small && C > 1) C >>= 1;
 	while ((unsigned long long) C > lines) C >>= 1;
 	return C < 1 ? 1 : C;
 }
@@ -643,6 +658,7 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	const size_t smem = sizeof(float2) * (size_t) total * (nstages >= 3 ? 2 : 1);
 	switch (P.log2L) {
 #define CASE(l) case l: if (inverse) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
+	                else if (P.nfan > 0) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
 	                else KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false><<<grid, threads, smem, stream>>>(in, out, P, stw)); break
 	CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
 #undef CASE
@@ -655,6 +671,7 @@ struct FftOpts {
 	const float *real_in; bool out_abs; float scale;
 	unsigned batch;                 // independent transforms (grid.y)
 	long long data_bs, scratch_bs, real_bs;   // distance between consecutive transforms in data (complex), scratch (complex), real_in (floats)
+	float2 *const *fan; int nfan;             // forward only: the final pass stores the result to every fan[p] (same layout as `data`) instead of `data`
 };
 
 // N-point transform of `data` (complex, natural order) through `scratch`; result lands in `data`.
@@ -666,9 +683,14 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 	double eps_all[40];
 	tsdrgpu_fft_reference_eps((int) log2N < 40 ? (int) log2N : 40, inverse, eps_all);
 	FftPass P; memset(&P, 0, sizeof P);
+	auto with_fan = [&](FftPass &F) {                   // the pass that produces the final result
+		F.nfan = 0;
+		if (o.fan && o.nfan > 0 && !inverse) { F.nfan = o.nfan < 16 ? o.nfan : 16; for (int q = 0; q < F.nfan; q++) F.fan[q] = o.fan[q]; }
+	};
 	if (log2N <= FFT_MAX_LOG2L) {                       // one pass, one CTA
 		P.log2L = (int) log2N; P.C = 1; P.G_lo = 1; P.in_js = 1; P.out_ks = 1; P.scale = o.scale;
 		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs;
+		with_fan(P);
 		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs, eps_all, 0);
 	}
 	int rc;
@@ -682,11 +704,12 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
 		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 		FftPass Q; memset(&Q, 0, sizeof Q);
-		Q.log2L = (int) l2; Q.C = bundle_for((int) l2, N1); Q.c_fast_in = 0; Q.c_fast_out = 1;
+		Q.log2L = (int) l2; Q.C = bundle_for((int) l2, N1, true); Q.c_fast_in = 0; Q.c_fast_out = 1;
 		Q.G_lo = (unsigned) (N1 / Q.C);
 		Q.in_lo = (long long) Q.C * (long long) N2; Q.in_cs = (long long) N2; Q.in_js = 1;
 		Q.out_lo = Q.C; Q.out_cs = 1; Q.out_ks = (long long) N1;
 		Q.scale = o.scale; Q.out_abs = o.out_abs;
+		with_fan(Q);
 		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse, o.batch, o.scratch_bs, o.data_bs, eps_all, (int) l1);
 	}
 	// N = N1*N2*N3 ; n = N2N3 n1 + N3 n2 + n3 ; k = k1 + N1 k2 + N1N2 k3
@@ -712,11 +735,12 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 	}
 	{   // pass C: contiguous lines of N3 at (k1,k2); bundle over adjacent k1; output k1 + N1 k2 + N1N2 k3
 		FftPass Cc; memset(&Cc, 0, sizeof Cc);
-		Cc.log2L = (int) l3; Cc.C = bundle_for((int) l3, N1); Cc.c_fast_in = 0; Cc.c_fast_out = 1;
+		Cc.log2L = (int) l3; Cc.C = bundle_for((int) l3, N1, true); Cc.c_fast_in = 0; Cc.c_fast_out = 1;
 		Cc.G_lo = (unsigned) (N1 / Cc.C);                // g = k2 * G_lo + (k1 / C)
 		Cc.in_hi = (long long) N3; Cc.in_lo = (long long) Cc.C * (long long) N23; Cc.in_cs = (long long) N23; Cc.in_js = 1;
 		Cc.out_hi = (long long) N1; Cc.out_lo = Cc.C; Cc.out_cs = 1; Cc.out_ks = (long long) (N1 * N2);
 		Cc.scale = o.scale; Cc.out_abs = o.out_abs;
+		with_fan(Cc);
 		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse, o.batch, o.scratch_bs, o.data_bs, eps_all, (int) (l1 + l2));
 	}
 }
@@ -999,6 +1023,46 @@ int tsdrgpu_superb_local_spectra(tsdrgpu_ctx_t *ctx, void *stream_, const float 
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, X, N, 0))) return rc;
 	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), D, nd));
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, D, nd, 0))) return rc;
+	*h_n = (uint32_t) N; *h_nd = (uint32_t) nd;
+	return TSDRGPU_OK;
+}
+
+// The same contribution, but delivered: the final pass of each of the two transforms stores its result straight into the
+// gather buffer of EVERY rank (d_peer_bufs[p] = rank p's buffer, mapped here through CUDA IPC; the own entry is local memory)
+// at this rank's slot, so the all-gather happens inside the transform's epilogue, over NVLink, while the transform runs.
+// What remains for the caller is a barrier (all ranks have finished storing) before anybody reads its buffer.
+int tsdrgpu_superb_local_spectra_scatter(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop, int count_pairs, int samples_in_frame,
+                                         float *const *d_peer_bufs, int nhops, int rank, uint64_t block_stride_complex,
+                                         uint32_t *h_n, uint32_t *h_nd) {
+	BIND(ctx); ARG_TRY(ctx, d_hop && d_peer_bufs && count_pairs > 0 && samples_in_frame > 0 && h_n && h_nd);
+	ARG_TRY(ctx, nhops > 0 && nhops <= 16 && rank >= 0 && rank < nhops);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
+	int size = (int) ((2 * N / samples_in_frame) * samples_in_frame);          // superbandwidth.c:84-86 with bufsize = 2N floats
+	ARG_TRY(ctx, size >= 2);
+	size = (int) tsdrgpu_fft_getrealsize((uint32_t) size);
+	const unsigned long long nd = (unsigned long long) size / 2;
+	ARG_TRY(ctx, N + nd <= block_stride_complex && N > 4 && nd > 4);
+	int rc = ensure_table(ctx, stream);
+	if (rc) return rc;
+	void *work, *scratch;
+	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * N, &work))) return rc;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N, &scratch))) return rc;
+	float2 *fanX[16], *fanD[16];
+	for (int q = 0; q < nhops; q++) {
+		ARG_TRY(ctx, d_peer_bufs[q] != NULL);
+		fanX[q] = reinterpret_cast<float2 *>(d_peer_bufs[q]) + (size_t) rank * block_stride_complex;
+		fanD[q] = fanX[q] + N;
+	}
+	FftOpts o; memset(&o, 0, sizeof o); o.batch = 1;
+	// X = FFT_N(raw hop)
+	CU_TRY(ctx, cudaMemcpyAsync(work, d_hop, sizeof(float2) * N, cudaMemcpyDeviceToDevice, stream));
+	o.scale = 1.0f / (float) N; o.fan = fanX; o.nfan = nhops;
+	if ((rc = fft_run(ctx, stream, (float2 *) work, (float2 *) scratch, ilog2(N), 0, o))) return rc;
+	// D = FFT_nd(first difference of |hop|)
+	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), (float2 *) work, nd));
+	o.scale = 1.0f / (float) nd; o.fan = fanD;
+	if ((rc = fft_run(ctx, stream, (float2 *) work, (float2 *) scratch, ilog2(nd), 0, o))) return rc;
 	*h_n = (uint32_t) N; *h_nd = (uint32_t) nd;
 	return TSDRGPU_OK;
 }

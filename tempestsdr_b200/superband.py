@@ -76,3 +76,86 @@ def stitch_simulated(ctx: api.Context, hops: Sequence[torch.Tensor], samples_in_
     for s in range(H):
         full[s::H] = residue(ctx, gathered, H, n, nd, s, lags).view(n, 2)
     return full.reshape(-1), [2 * l for l in lags]
+
+
+class PeerExchange:
+    """Gather buffers of all ranks mapped into every rank (CUDA IPC over NVLink), for the fused transform + all-gather.
+
+    Every rank allocates one buffer of ``world * block_stride`` complex values with ``tsdrgpu_malloc`` and publishes its
+    IPC handle (one ``all_gather_object`` at set-up, never on the data path).  ``stitch_distributed_fused`` then makes each
+    rank's forward transforms store their result into all buffers directly (``tsdrgpu_superb_local_spectra_scatter``); what
+    is left of the exchange is a barrier."""
+
+    def __init__(self, ctx: api.Context, n_max_complex: int, group=None):
+        import torch.distributed as dist
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.block_stride = int(n_max_complex)
+        self.nbytes = 8 * self.block_stride * self.world
+        lib = ctx._lib
+        own = C.c_void_p()
+        ctx.chk(lib.tsdrgpu_malloc(ctx._h, self.nbytes, C.byref(own)))
+        self.own = own.value
+        handle = (C.c_uint8 * 64)()
+        ctx.chk(lib.tsdrgpu_ipc_export(ctx._h, C.c_void_p(self.own), handle))
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peers: List[int] = []
+        self._opened: List[int] = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peers.append(self.own)
+                continue
+            p = C.c_void_p()
+            ctx.chk(lib.tsdrgpu_ipc_import(ctx._h, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(p)))
+            self.peers.append(p.value); self._opened.append(p.value)
+        self._arr = (C.c_void_p * self.world)(*self.peers)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{torch.cuda.current_device()}")
+
+    def gathered(self) -> torch.Tensor:
+        """This rank's gather buffer as a float32 tensor view (valid after ``barrier``)."""
+        return _device_view(self.own, self.nbytes // 4)
+
+    def barrier(self) -> None:
+        """All ranks have finished storing into all buffers: a 4-byte all-reduce ordered behind the transforms on the stream."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self) -> None:
+        import torch.distributed as dist
+        lib = self.ctx._lib
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)             # nobody still stores into a buffer that is about to be unmapped / freed
+        for p in self._opened:
+            lib.tsdrgpu_ipc_release(self.ctx._h, C.c_void_p(p))
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self.own:
+            lib.tsdrgpu_free(self.ctx._h, C.c_void_p(self.own)); self.own = 0
+
+
+def _device_view(ptr: int, nfloats: int) -> torch.Tensor:
+    """A float32 torch tensor over device memory this package allocated itself (``__cuda_array_interface__``)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=f"cuda:{torch.cuda.current_device()}")
+
+
+def stitch_distributed_fused(ctx: api.Context, hop: torch.Tensor, samples_in_frame: int, ex: PeerExchange):
+    """``stitch_distributed`` with the all-gather fused into the forward transforms (peer stores over NVLink)."""
+    pairs = hop.numel() // 2
+    hn, hnd = C.c_uint32(0), C.c_uint32(0)
+    ex.barrier()                                   # every rank is done reading its buffer from the previous stitch
+    ctx.chk(ctx._lib.tsdrgpu_superb_local_spectra_scatter(ctx._h, ctx.stream, hop.data_ptr(), pairs, samples_in_frame, ex._arr,
+                                                          ex.world, ex.rank, ex.block_stride, C.byref(hn), C.byref(hnd)))
+    ex.barrier()
+    n, nd = hn.value, hnd.value
+    gathered = ex.gathered()
+    lags = (C.c_int * ex.world)()
+    ctx.chk(ctx._lib.tsdrgpu_superb_lags(ctx._h, ctx.stream, gathered.data_ptr(), ex.world, ex.block_stride, n, nd, lags))
+    out = torch.empty(2 * n, dtype=torch.float32, device=hop.device)
+    ctx.chk(ctx._lib.tsdrgpu_superb_residue_ifft_lag(ctx._h, ctx.stream, gathered.data_ptr(), ex.world, ex.block_stride, n,
+                                                     residue_of_rank(ex.rank, ex.world), lags, out.data_ptr()))
+    return out, list(lags), n

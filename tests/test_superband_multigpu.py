@@ -36,6 +36,17 @@ def _worker(rank, world, port, q):
         err = float(np.max(np.abs(got - ref)) / np.max(np.abs(want)))
         ok = ok and err <= 8e-6          # tolerance 8e-6 of the peak (float FFT, see test_gpu_parity)
         msg = f"err={err:.3g} lags={lags} offs={list(offs)}"
+    # the same stitch with the all-gather fused into the forward transforms (peer stores over NVLink, CUDA IPC): the same
+    # kernels see the same gathered data, so the result must be bit-identical to the NCCL path
+    ex = superband.PeerExchange(ctx, 2 * ctx.fft_getrealsize(pairs))
+    for _ in range(2):                                     # twice: the buffers are reused
+        res2, lags2, n2 = superband.stitch_distributed_fused(ctx, torch.from_numpy(hops[rank]).cuda(), sif, ex)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(res, res2)) and lags2 == lags and n2 == n
+        ok = ok and same
+        msg += f" fused_same={same}"
+        dist.barrier()                                     # nobody starts overwriting buffers that a slower rank still reads
+    ex.close()
     q.put((rank, ok, msg))
     dist.destroy_process_group()
 
