@@ -382,6 +382,29 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         superb = {"hops": world, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": world * n_fft / (tms.item() * 1e-3) / 1e6,
                   "allgather_bytes_per_rank": 8 * (n_fft + n_fft // 2), "collective": "one NCCL all_gather_into_tensor per stitch"}
+        # the same stitch with the all-gather fused into the forward transforms' last pass (NVLink peer stores through CUDA IPC,
+        # a 4-byte all-reduce as the barrier): DESIGN.md section 6
+        try:
+            ex = superband.PeerExchange(gpu, 2 * n_fft)
+            for _ in range(2):
+                superband.stitch_distributed_fused(gpu, hop, int(FS / FV), ex)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                res_f, lags_f, _ = superband.stitch_distributed_fused(gpu, hop, int(FS / FV), ex)
+            f1.record()
+            barrier()
+            tf = torch.tensor([f0.elapsed_time(f1) / reps], device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            same = torch.tensor([int(bool(torch.equal(res, res_f)) and list(lags_f) == list(lags))], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            superb["fused_peer_store"] = {"ms_per_stitch": tf.item(), "stitched_MS_per_s": world * n_fft / (tf.item() * 1e-3) / 1e6,
+                                          "bit_identical_to_nccl_path": bool(same.item()),
+                                          "how": "FFT last pass stores into every rank's gather buffer (peer memory), then a 4-byte all-reduce as barrier"}
+            ex.close()
+        except Exception as e:                                   # peer access unavailable on this box: the NCCL figure stands alone
+            superb["fused_peer_store"] = {"unavailable": repr(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
