@@ -247,8 +247,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps     # host time to ENQUEUE a step (nothing is waited for)
     step.join()                                   # the side stream's tail (last sync search + re-centring) is inside the timed region
     e1.record()
     barrier()
@@ -266,6 +268,14 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # host cost of enqueueing a step when nothing throttles it (3 steps right after a full synchronisation: the resampler's
+    # 4-slot descriptor ring cannot be full yet).  Informational: it tells how far the host is from being the bottleneck.
+    step.join(); torch.cuda.synchronize()
+    t_h = time.perf_counter()
+    for _ in range(3):
+        step()
+    host_enqueue_free_ms = (time.perf_counter() - t_h) * 1e3 / 3
+    step.join(); torch.cuda.synchronize()
     # ---- per-kernel timing pass (separate from the timed region above): CUDA events on the launching stream
     # The side stream is switched off for this pass so that every kernel's event pair measures that kernel alone
     # (with it on, intervals on the main stream also contain the slowdown from sharing the chip with the sync search).
@@ -459,6 +469,7 @@ def run_ours(args):
                                f"{FRAMES_PER_STEP} frames per step ({pairs} IQ pairs, {8 * pairs / 1e6:.0f} MB > L2, so no L2 flush is needed)",
                    "frames_per_step": frames_done / args.steps, "autocorr_captures_per_step": caps_done / args.steps,
                    "frames_per_s": world * frames_done / (ms_total * 1e-3), "parallelism": f"replicas x{world}" if world > 1 else "single stream",
+                   "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_per_step_unthrottled": host_enqueue_free_ms,
                    "flags": "AUTOSHIFT=1, LOW_PASS_BEFORE_SYNC=1, AUTOGAIN_AFTER=0, motionblur 0 (GUI defaults), PLL write-back off"},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
