@@ -131,6 +131,7 @@ class DeviceStep:
         self.frames = 0
         self.captures = 0
         self.k = 0
+        self.chunk = int(os.environ.get("BENCH_FRAME_CHUNK", "0"))
 
     def __call__(self):
         gpu = self.gpu
@@ -142,7 +143,13 @@ class DeviceStep:
                               mag_out=self.mag[self.mag_fill:] if fused_mag else None)
         self.pix_fill += out.numel()
         nf = min(self.pix_fill // self.n, FRAMES_PER_STEP)
-        self.pp.process(self.pix[: nf * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=self.frames_out[self.k & 1][: nf * self.n], want_results=False)
+        # the frame stage in sub-batches of `chunk` frames (default: the whole step at once).  Smaller sub-batches keep a batch's
+        # intermediate frames in L2 between the kernels of the stage at the price of more launches.
+        chunk = self.chunk if self.chunk > 0 else nf
+        fo = self.frames_out[self.k & 1]
+        for c0 in range(0, nf, chunk):
+            c1 = min(nf, c0 + chunk)
+            self.pp.process(self.pix[c0 * self.n: c1 * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=fo[c0 * self.n: c1 * self.n], want_results=False)
         self.k += 1
         left = self.pix_fill - nf * self.n
         if left:
