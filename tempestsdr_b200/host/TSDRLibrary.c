@@ -327,6 +327,12 @@ int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 			goto end;
 		}
 		tsdrgpu_pipeline_set_retune(t->pipe, on_retune);
+		/* opt-in extras, all off by default so that an unchanged host sees exactly the reference's callbacks */
+		{
+			const char *snr = getenv("TSDR_REPORT_SNR"), *mode = getenv("TSDR_DETECT_MODE"), *argb = getenv("TSDR_OUTPUT_ARGB");
+			if ((snr && atoi(snr)) || (mode && atoi(mode))) tsdrgpu_pipeline_set_reports(t->pipe, snr && atoi(snr), mode && atoi(mode));
+			if (argb && argb[0] && argb[0] != '0') tsdrgpu_pipeline_set_output_argb(t->pipe, 1, strcmp(argb, "inverted") == 0);
+		}
 	}
 	status = t->plugin.readasync(process, t);                 /* blocks until tsdr_stop or a plugin error */
 	if (status != TSDR_OK) pluginsfault = 1;
