@@ -737,13 +737,17 @@ int tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_iq, int fm
 		LAUNCH_CHECK(ctx);
 		p->decim_fill += fwd;
 	}
-	if (need_data) {
-		CU_TRY(ctx, cudaEventRecord(p->ev_used[ss], p->s_ingest));         // the slot may be overwritten after this point
-		CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));                     // the host buffer has been read
-	}
+	if (need_data) CU_TRY(ctx, cudaEventRecord(p->ev_used[ss], p->s_ingest));   // the slot may be overwritten after this point
 	CU_TRY(ctx, cudaEventRecord(p->ev_ingest, p->s_ingest));
 	CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_ingest, 0));          // the resampler may read what was appended
-	return drain_blocks(p);
+	// Everything above and the launches below are only ENQUEUED (ordered on the device by events), so the host's launch
+	// work for the heavy kernels runs while this block's H2D copy is still in flight; the copy is waited for last.
+	rc = drain_blocks(p);
+	if (need_data) {
+		const cudaError_t e = cudaStreamSynchronize(p->s_copy);             // the host buffer has been read
+		if (e != cudaSuccess && rc == TSDRGPU_OK) return tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "cudaStreamSynchronize(s_copy)", e, __FILE__, __LINE__);
+	}
+	return rc;
 }
 
 }  // extern "C"
