@@ -429,6 +429,41 @@ __global__ void k_abs(float2 *answer, unsigned long long from, unsigned long lon
 		answer[i] = make_float2(mag_exact(v.x, v.y), 0.0f);
 	}
 }
+// ---- real-input transforms at half size (opt-in, see autocorrelation_batch) ------------------------------------------------
+// z[j] = x[2j] + i x[2j+1] has been transformed (N/2 points, unscaled) into Z.  With E, O the transforms of the even and odd
+// samples, E = (Z[k] + conj Z[-k]) / 2, O = (Z[k] - conj Z[-k]) / 2i, and the reference's LAST radix-2 stage (its perturbed
+// angle: last[k] = exp(-i pi k / (N/2) (1 + eps_{m-1})), host-built) gives X[k] = E + last[k] O, X[k + N/2] = E - last[k] O.
+__device__ __forceinline__ void real_split(float2 zk, float2 zm, float2 w, float2 &x0, float2 &x1) {
+	const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+	const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+	const float2 t = make_float2(w.x * o.x - w.y * o.y, w.x * o.y + w.y * o.x);
+	x0 = make_float2(e.x + t.x, e.y + t.y); x1 = make_float2(e.x - t.x, e.y - t.y);
+}
+// forward: R[k] = |X[k]| / N for all N outputs, as REAL numbers (they are the next transform's real input); grid.y = batch
+__global__ void __launch_bounds__(256) k_real_fwd_finish(const float2 *__restrict__ Z, long long z_bs, const float2 *__restrict__ last,
+                                                         unsigned half, float inv_n, float *__restrict__ R, long long r_bs) {
+	const float2 *z = Z + (long long) blockIdx.y * z_bs;
+	float *r = R + (long long) blockIdx.y * r_bs;
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < half; k += gridDim.x * blockDim.x) {
+		float2 x0, x1;
+		real_split(z[k], z[(half - k) & (half - 1)], __ldg(last + k), x0, x1);
+		r[k] = mag_exact(x0.x * inv_n, x0.y * inv_n);
+		r[k + half] = mag_exact(x1.x * inv_n, x1.y * inv_n);
+	}
+}
+// inverse (no scaling, conjugate twiddle): the N complex outputs
+__global__ void __launch_bounds__(256) k_real_inv_finish(const float2 *__restrict__ Z, long long z_bs, const float2 *__restrict__ last,
+                                                         unsigned half, float2 *__restrict__ Y, long long y_bs) {
+	const float2 *z = Z + (long long) blockIdx.y * z_bs;
+	float2 *y = Y + (long long) blockIdx.y * y_bs;
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < half; k += gridDim.x * blockDim.x) {
+		const float2 w = __ldg(last + k);
+		float2 x0, x1;
+		real_split(z[k], z[(half - k) & (half - 1)], make_float2(w.x, -w.y), x0, x1);
+		y[k] = x0; y[k + half] = x1;
+	}
+}
+
 // a = (aI*bI + aQ*bQ, aI*bQ - aQ*bI)                                   (fft.c:80-89)
 __global__ void k_conj_mul(float2 *a, const float2 *b, unsigned long long n) {
 	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
@@ -672,14 +707,15 @@ struct FftOpts {
 	unsigned batch;                 // independent transforms (grid.y)
 	long long data_bs, scratch_bs, real_bs;   // distance between consecutive transforms in data (complex), scratch (complex), real_in (floats)
 	float2 *const *fan; int nfan;             // forward only: the final pass stores the result to every fan[p] (same layout as `data`) instead of `data`
+	const float2 *cplx_in; long long cplx_bs; // the first pass reads its (complex) input from here instead of `data` (which is then output only)
 };
 
 // N-point transform of `data` (complex, natural order) through `scratch`; result lands in `data`.
 // With opts.real_in the input is read from a real array instead (data is output only).
 int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scratch, unsigned log2N, int inverse, FftOpts o) {
 	const unsigned long long N = 1ull << log2N;
-	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : data;
-	const long long in0_bs = o.real_in ? o.real_bs : o.data_bs;
+	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : (o.cplx_in ? o.cplx_in : data);
+	const long long in0_bs = o.real_in ? o.real_bs : (o.cplx_in ? o.cplx_bs : o.data_bs);
 	double eps_all[40];
 	tsdrgpu_fft_reference_eps((int) log2N < 40 ? (int) log2N : 40, inverse, eps_all);
 	FftPass P; memset(&P, 0, sizeof P);
@@ -784,6 +820,56 @@ int tsdrgpu_fft(tsdrgpu_ctx_t *ctx, void *stream, float *d_iq, uint32_t size, in
 // batch of independent autocorrelations: transform b reads d_real + b*real_stride (floats) and writes
 // d_answer + b*answer_stride (floats, 2*size each).  skip_tail leaves answer[2N .. 2*size) untouched (the
 // frame-rate detector never reads lags >= N).
+// last[k] = exp(-i pi k / half (1 + eps)), k < half: the reference's final radix-2 stage of an (2 half)-point transform
+struct LastTab { int device; unsigned half; double eps; float2 *d; };
+static std::vector<LastTab> g_last_tabs;
+static int last_stage_table(tsdrgpu_ctx_t *ctx, unsigned half, double eps, const float2 **out) {
+	std::lock_guard<std::mutex> lock(g_tw_mu);
+	for (auto &t : g_last_tabs) if (t.device == ctx->device && t.half == half && t.eps == eps) { *out = t.d; return TSDRGPU_OK; }
+	std::vector<float2> h(half);
+	for (unsigned k = 0; k < half; k++) {
+		const double ang = -3.14159265358979323846 * ((double) k / (double) half) * (1.0 + eps);
+		h[k] = make_float2((float) cos(ang), (float) sin(ang));
+	}
+	LastTab t; t.device = ctx->device; t.half = half; t.eps = eps;
+	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float2) * half));
+	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float2) * half, cudaMemcpyHostToDevice));
+	g_last_tabs.push_back(t);
+	*out = t.d;
+	return TSDRGPU_OK;
+}
+
+// EXPERIMENTAL (opt-in: TSDRGPU_AUTOCORR_HALF=1; written without access to a GPU at the end of round 1, to be validated and
+// made the default in the next round): both transforms of the autocorrelation at half size.  The capture and |X|/N are
+// real; a real sequence of length N is a complex one of length N/2, one N/2-point transform + the reference's last radix-2
+// stage (k_real_*_finish) gives the N-point result.  profiles/studies/real_input_autocorr_study.py measures the only
+// approximation (the mirror identity under perturbed stage angles): 6.6e-10 of the zero-lag peak at 2^20, 7.9e-9 at 2^22.
+static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *ans, long long ans_bs, const float *d_real,
+                                      long long real_stride, unsigned long long N, unsigned batch, float2 *scratch) {
+	const unsigned log2N = ilog2(N), half = (unsigned) (N >> 1);
+	double eps_all[40];
+	tsdrgpu_fft_reference_eps((int) log2N, 0, eps_all);
+	static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;
+	const float2 *last;
+	int rc = last_stage_table(ctx, half, exact_dft ? 0.0 : eps_all[log2N - 1], &last);
+	if (rc) return rc;
+	const dim3 grid(grid1d(half, ctx->sm_count), batch);
+	// forward: Z = FFT_{N/2}(capture viewed as complex pairs), unscaled, into the first half of each answer slot
+	FftOpts f; memset(&f, 0, sizeof f);
+	f.scale = 1.0f; f.batch = batch; f.data_bs = ans_bs; f.scratch_bs = (long long) N;
+	f.cplx_in = reinterpret_cast<const float2 *>(d_real); f.cplx_bs = real_stride / 2;
+	if ((rc = fft_run(ctx, stream, ans, scratch, log2N - 1, 0, f))) return rc;
+	// R = |X| / N as N reals = N/2 complex, into the first half of each scratch slot
+	KL(ctx, "k_real_fwd_finish", stream, k_real_fwd_finish<<<grid, 256, 0, stream>>>(ans, ans_bs, last, half, 1.0f / (float) N,
+	                                                                                  reinterpret_cast<float *>(scratch), 2ll * (long long) N));
+	// inverse: Z' = IFFT_{N/2}(R viewed as complex pairs) in place in the first half of the scratch slot, work space = its second half
+	FftOpts g; memset(&g, 0, sizeof g);
+	g.scale = 1.0f; g.batch = batch; g.data_bs = (long long) N; g.scratch_bs = (long long) N;
+	if ((rc = fft_run(ctx, stream, scratch, scratch + half, log2N - 1, 1, g))) return rc;
+	KL(ctx, "k_real_inv_finish", stream, k_real_inv_finish<<<grid, 256, 0, stream>>>(scratch, (long long) N, last, half, ans, ans_bs));
+	return TSDRGPU_OK;
+}
+
 static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float *d_answer, long long answer_stride,
                                  const float *d_real, long long real_stride, uint32_t size, unsigned batch, bool skip_tail) {
 	int rc = ensure_table(ctx, stream);
@@ -802,6 +888,9 @@ static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float 
 		}
 		if (N == 1) return TSDRGPU_OK;
 	}
+	if (getenv("TSDRGPU_AUTOCORR_HALF") && N >= 16 && (real_stride & 1) == 0 && (answer_stride & 1) == 0
+	    && (reinterpret_cast<unsigned long long>(d_real) & 7ull) == 0)
+		return autocorrelation_batch_half(ctx, stream, ans, answer_stride / 2, d_real, real_stride, N, batch, (float2 *) scratch);
 	// forward transform of the first N samples, real input widened on load, |X|/N on store
 	FftOpts f; memset(&f, 0, sizeof f);
 	f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N; f.batch = batch;

@@ -5,6 +5,8 @@ restatement.  Integer/index results and every float produced by the sample->pixe
 the FFT family is tolerance-based (float32 Stockham vs the reference's float-storage radix-2): the tolerance is
 written next to each check, relative to the peak magnitude of the reference result.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -330,6 +332,19 @@ def test_autocorrelation_and_xcorr(gpu, O, size):
         da, db = dev(a), dev(b)
         gpu.fft_crosscorrelation(da, db, size)
         _close(da[: 2 * n], O.crosscorrelation(a, b)[: 2 * n], 4e-6, f"xcorr {size}")
+
+
+@pytest.mark.skipif(not os.environ.get("TSDRGPU_TEST_EXPERIMENTAL"), reason="opt-in path written after the round's GPU budget was spent; "
+                    "enable with TSDRGPU_TEST_EXPERIMENTAL=1 (DESIGN.md section 9)")
+@pytest.mark.parametrize("size", [4096, 70_001 + 1, 450_910, 1_409_090])
+def test_autocorrelation_half_size_path(gpu, O, size, monkeypatch):
+    """TSDRGPU_AUTOCORR_HALF=1: both transforms at half size (real input packed as complex pairs + the reference's last radix-2
+    stage).  Same tolerance as the default path; profiles/studies/real_input_autocorr_study.py bounds the approximation."""
+    monkeypatch.setenv("TSDRGPU_AUTOCORR_HALF", "1")
+    x = np.abs(synth.noise_iq(size, seed=size)[:size]).astype(np.float32)
+    want = O.autocorrelation(x)
+    got = gpu.fft_autocorrelation(dev(x))
+    _close(got, want, 2e-6, f"half-size autocorrelation {size}")
 
 
 def test_accumulate_exact_and_framerate_plots(gpu, O):
