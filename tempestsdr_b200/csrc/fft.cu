@@ -839,8 +839,8 @@ static int last_stage_table(tsdrgpu_ctx_t *ctx, unsigned half, double eps, const
 	return TSDRGPU_OK;
 }
 
-// EXPERIMENTAL (opt-in: TSDRGPU_AUTOCORR_HALF=1; written without access to a GPU at the end of round 1, to be validated and
-// made the default in the next round): both transforms of the autocorrelation at half size.  The capture and |X|/N are
+// Opt-in (TSDRGPU_AUTOCORR_HALF=1; parity-tested on the B200, speed not yet measured -- to become the default once it is):
+// both transforms of the autocorrelation at half size.  The capture and |X|/N are
 // real; a real sequence of length N is a complex one of length N/2, one N/2-point transform + the reference's last radix-2
 // stage (k_real_*_finish) gives the N-point result.  profiles/studies/real_input_autocorr_study.py measures the only
 // approximation (the mirror identity under perturbed stage angles): 6.6e-10 of the zero-lag peak at 2^20, 7.9e-9 at 2^22.

@@ -334,12 +334,11 @@ def test_autocorrelation_and_xcorr(gpu, O, size):
         _close(da[: 2 * n], O.crosscorrelation(a, b)[: 2 * n], 4e-6, f"xcorr {size}")
 
 
-@pytest.mark.skipif(not os.environ.get("TSDRGPU_TEST_EXPERIMENTAL"), reason="opt-in path written after the round's GPU budget was spent; "
-                    "enable with TSDRGPU_TEST_EXPERIMENTAL=1 (DESIGN.md section 9)")
 @pytest.mark.parametrize("size", [4096, 70_001 + 1, 450_910, 1_409_090])
 def test_autocorrelation_half_size_path(gpu, O, size, monkeypatch):
-    """TSDRGPU_AUTOCORR_HALF=1: both transforms at half size (real input packed as complex pairs + the reference's last radix-2
-    stage).  Same tolerance as the default path; profiles/studies/real_input_autocorr_study.py bounds the approximation."""
+    """TSDRGPU_AUTOCORR_HALF=1 (opt-in until its speed has been measured): both transforms at half size (real input packed as
+    complex pairs + the reference's last radix-2 stage).  Same tolerance as the default path;
+    profiles/studies/real_input_autocorr_study.py bounds the approximation."""
     monkeypatch.setenv("TSDRGPU_AUTOCORR_HALF", "1")
     x = np.abs(synth.noise_iq(size, seed=size)[:size]).astype(np.float32)
     want = O.autocorrelation(x)
