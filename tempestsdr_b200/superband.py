@@ -55,13 +55,32 @@ def residue_of_rank(rank: int, world: int) -> int:
     return rank % world
 
 
-def stitch_distributed(ctx: api.Context, hop: torch.Tensor, samples_in_frame: int, group=None):
-    """Rank-local view of the stitch: returns (this rank's residue as interleaved IQ, lags in pairs, N)."""
+def own_lag_from_gathered(ctx: api.Context, gathered: torch.Tensor, rank: int, n: int, nd: int) -> int:
+    """The alignment lag of hop `rank` against hop 0 only: tsdrgpu_superb_lags on the two-block view {block 0, block rank}."""
+    if rank == 0:
+        return 0
+    lags = (C.c_int * 2)()
+    ctx.chk(ctx._lib.tsdrgpu_superb_lags(ctx._h, ctx.stream, gathered.data_ptr(), 2, rank * (n + nd), n, nd, lags))
+    return int(lags[1])
+
+
+def stitch_distributed(ctx: api.Context, hop: torch.Tensor, samples_in_frame: int, group=None, distributed_lags: bool = False):
+    """Rank-local view of the stitch: returns (this rank's residue as interleaved IQ, lags in pairs, N).
+
+    distributed_lags=False: every rank derives all H-1 lags itself from the gathered difference spectra (one collective in
+    total, redundant cross-correlations).  True: rank q computes only ITS lag and the H integers are exchanged with a second,
+    4-byte-per-rank all-gather -- the lag work per rank no longer grows with H (not yet measured: DESIGN.md section 9)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     block, n, nd = local_block(ctx, hop, samples_in_frame)
     gathered = gather_blocks(block, group)
-    lags = lags_from_gathered(ctx, gathered, world, n, nd)
+    if distributed_lags:
+        mine = torch.tensor([own_lag_from_gathered(ctx, gathered, rank, n, nd)], dtype=torch.int32, device=gathered.device)
+        every = torch.empty(world, dtype=torch.int32, device=gathered.device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        lags = [int(v) for v in every.cpu()]
+    else:
+        lags = lags_from_gathered(ctx, gathered, world, n, nd)
     return residue(ctx, gathered, world, n, nd, residue_of_rank(rank, world), lags), lags, n
 
 

@@ -36,6 +36,11 @@ def _worker(rank, world, port, q):
         err = float(np.max(np.abs(got - ref)) / np.max(np.abs(want)))
         ok = ok and err <= 8e-6          # tolerance 8e-6 of the peak (float FFT, see test_gpu_parity)
         msg = f"err={err:.3g} lags={lags} offs={list(offs)}"
+    # lags computed one per rank and exchanged (instead of all of them on every rank): the same integers, hence the same result
+    res3, lags3, n3 = superband.stitch_distributed(ctx, torch.from_numpy(hops[rank]).cuda(), sif, distributed_lags=True)
+    same3 = bool(torch.equal(res, res3)) and lags3 == lags and n3 == n
+    ok = ok and same3
+    msg += f" distributed_lags_same={same3}"
     # the same stitch with the all-gather fused into the forward transforms (peer stores over NVLink, CUDA IPC): the same
     # kernels see the same gathered data, so the result must be bit-identical to the NCCL path
     ex = superband.PeerExchange(ctx, 2 * ctx.fft_getrealsize(pairs))
