@@ -5,18 +5,20 @@
 // frameratedetector_runontodata (frameratedetector.c:34-126), complex_to_abs_diff / superb_bestfit /
 // superb_ondataready (superbandwidth.c:67-152).
 //
-// FFT design (no tensor cores: nothing here is a dense contraction; the bound is HBM / L2 bandwidth):
-//   N = 2^m is factored into 1, 2 or 3 line lengths L_i <= 2048 (Cooley-Tukey index maps).  One CTA transforms a
-//   BUNDLE of C adjacent lines entirely in shared memory (in-place radix-4/2 Stockham stages, natural order in and
-//   out), multiplies by the inter-pass twiddle and writes the bundle back.  Bundling makes every global access a
-//   run of >= C consecutive complex values (>= 64..128 B) even on the strided passes, so each pass is one
-//   coalesced read + one coalesced write of the array: 16 N bytes per pass, 2 passes up to N = 2^22, 3 above.
-//   The transposing last pass writes to the other buffer (scratch <-> data), so no extra copy pass exists.
-//   Real->complex widening and |X|/N are fused into the first / last pass of the forward transform of the
-//   autocorrelation.
-// Numerics: float32 data, twiddles from a double-computed table (intra-line) and sincospif of an exactly reduced
-// argument (inter-pass).  The reference keeps float32 storage between its radix-2 stages too (fft.c:150-155), so
-// both carry ~1e-7*sqrt(log2 N) relative noise; results agree to ~1e-6 of the spectrum's peak (not bit-exact).
+// FFT design (no tensor cores: nothing here is a dense contraction; the bound is HBM bandwidth and issue slots):
+//   N = 2^m is factored into 1, 2 or 3 line lengths (Cooley-Tukey index maps; 2 passes up to 2^20, 3 above).  One CTA
+//   transforms a BUNDLE of C adjacent lines (4096 points, 512 threads): radix-8 Stockham stages written as their radix-2
+//   layers, the first fed from global memory, the last storing to global memory through the epilogue (inter-pass twiddle,
+//   scale, |.|), the ones between through XOR-swizzled shared memory.  Bundling makes every global access a run of >= C
+//   consecutive complex values even on the strided passes, so each pass is one coalesced read + one coalesced write of
+//   the array: 16 N bytes per pass.  The transposing last pass writes to the other buffer, so no copy pass exists.
+//   Real->complex widening and |X|/N are fused into the first / last pass of the autocorrelation's forward transform;
+//   a FAN variant of the last pass stores into the gather buffers of all ranks (superbandwidth, one hop per GPU).
+// Numerics: float32 data.  Layer twiddles come from host-built double-precision tables that carry the REFERENCE'S stage
+// angles (its half-angle recurrence, fft.c:161, is off by up to 5e-5 relative at the largest stages: see
+// tsdrgpu_fft_reference_eps), inter-pass twiddles from sincospif of an exactly reduced argument times a host-built step
+// table.  The reference keeps float32 storage between its radix-2 stages too (fft.c:150-155); results agree to <= 1e-6 of
+// the spectrum's peak up to 2^22 (not bit-exact).
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>

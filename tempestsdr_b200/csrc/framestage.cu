@@ -9,14 +9,16 @@
 //   (2) the per-pixel temporal IIR (screenbuffer),
 //   (3) the sync detector's small integer state.
 // So a batch of F frames is processed stage by stage with F as an extra (parallel) grid dimension, the scalar
-// recurrences run in one-thread epilogues, and only the sync search (inherently sequential double-precision
-// sliding sums over <= a few thousand strip elements) walks the frames one after another inside a single CTA.
+// recurrences run in one-thread epilogues, and of the sync search only the CHOICE of the strip size walks the frames one
+// after another (one 8-CTA cluster): its sliding double-precision sums are replaced, under a per-strip exactness
+// certificate, by prefix sums prepared for all frames in parallel (fs_sync_prep / fs_sync below).
 // All pixel values and all integer results are bit-identical to the reference: every float/double operation is
 // issued as an individual IEEE round-to-nearest instruction in the reference's order; the order-sensitive
 // single-precision row/column sums are accumulated in exactly the reference's order (one owner thread per
 // row / per column).  Only `snr` (dead in the reference, dsp.c:234) uses tree-ordered double sums.
 //
-// Every kernel here is HBM-bound elementwise/reduction work: coalesced loads, grid sized by pixels x frames.
+// Every other kernel here is HBM-bound elementwise/reduction work: coalesced (vectorised where aligned) loads, cp.async rings
+// for the order-bound row/column sums, grid sized by pixels x frames.
 #include "common.cuh"
 #include "host_plan.h"
 #include <math.h>

@@ -6,7 +6,8 @@
 // and plot buffers out: this is the object the C host library (tempestsdr_b200/host/TSDRLibrary.c) drives from
 // the reference's own process() callback, and the one bench.py times end to end.
 //
-// Data movement per IQ block: one H2D copy of the plugin's buffer (pinned if the pointer could be registered),
+// Data movement per IQ block: one H2D copy of the plugin's buffer (float32, or the front end's 8/16-bit wire format
+// converted on the device: tsdrgpu_pipeline_process_raw),
 // everything else stays in HBM: IQ -> (fused demod+resample) -> pixel stream -> (frame stage, batches of frames)
 // -> one D2H copy of the finished frames into page-locked slots -> frame callback on the delivery thread.
 // The reference's rings, which copy every sample 2x per stage under a mutex, do not exist here; what is kept
