@@ -100,3 +100,33 @@ def test_detect_videomode_matches_the_gui_arithmetic():
                                           fs, C.byref(fps), C.byref(h), C.byref(a), C.byref(b))
         assert rc == 0 and (a.value, b.value) == (fi, li) and fps.value == want_fps and h.value == want_h
     assert lib.tsdrgpu_detect_videomode(None, 0, 0, None, 0, 0, 1, None, None, None, None) != 0
+
+
+def test_resample_plan_random_sweep_against_the_oracle():
+    """Host planning (output count per block, carried phase) for random geometries, ratios below and above 1 and ragged
+    block sizes equals the oracle's resampler block by block: the data-independent half of dsp_resample_process
+    (dsp.c:256-307) that the CUDA path trusts the host for."""
+    import ctypes as C
+    import numpy as np
+    from tempestsdr_b200 import _native
+    lib = _native.lib()
+    P = orc.port()
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        down = float(rng.integers(1_000_000, 60_000_000))
+        ratio = float(rng.choice([0.37, 0.5, 0.999, 1.0, 1.25, 1.998, 2.0, 3.3, 7.5])) * (1.0 + (rng.random() - 0.5) * 1e-3)
+        up = down * ratio
+        sizes = rng.integers(max(8, int(4 / ratio) + 4), 5000, size=12).astype(np.uint32)
+        rs = P.resampler()
+        off = C.c_double(0.0)
+        total = 0
+        for s in sizes:
+            one = np.array([s], dtype=np.uint32)
+            n = lib.tsdrgpu_plan_resample(C.byref(off), one.ctypes.data_as(C.c_void_p), 0, 1, up, down, None)
+            out = rs.run(np.zeros(int(s), np.float32), up, down)
+            assert n == out.size, (trial, int(s), ratio)
+            assert off.value == rs.state[1], (trial, int(s), ratio)
+            total += n
+        off2 = C.c_double(0.0)
+        assert lib.tsdrgpu_plan_resample(C.byref(off2), sizes.ctypes.data_as(C.c_void_p), 0, len(sizes), up, down, None) == total
+        assert off2.value == off.value
