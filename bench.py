@@ -469,6 +469,20 @@ def run_ours(args):
     except Exception:
         pass
     value = world * args.steps * pairs / (ms_total * 1e-3) / 1e6
+    # opt-in code paths measured on the same workload in a child process (own CUDA context: whatever happens there cannot touch
+    # the numbers above).  Informational; the headline is always the default path.
+    variants = None
+    if world == 1 and not os.environ.get("BENCH_NO_VARIANTS"):
+        variants = {}
+        for name, env in (("autocorr_half_size", {"TSDRGPU_AUTOCORR_HALF": "1"}),):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))],
+                                   capture_output=True, text=True, timeout=180, env=dict(os.environ, BENCH_QUICK="1", **env))
+                q = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                variants[name] = {"value": q["value"], "unit": "MS/s", "ms_per_step": q["ms_per_step"], "env": env,
+                                  "note": "device-resident value of the same workload with this opt-in path (DESIGN.md section 9)"}
+            except Exception as e:
+                variants[name] = {"unavailable": repr(e)[:160], "env": env}
     cpu = cpu_baseline(w)
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -494,6 +508,8 @@ def run_ours(args):
         line["superbandwidth"] = superb
     if e2e_int8:
         line["e2e_int8_transport"] = e2e_int8
+    if variants:
+        line["variants"] = variants
     emit(line)
     if world > 1:
         dist.destroy_process_group()
