@@ -269,9 +269,28 @@ def run_ours(args):
     launches = gpu.launches - launches0
     frames_done, caps_done = step.frames - frames0, step.captures - caps0
 
-    if os.environ.get("BENCH_QUICK"):                 # used under ncu: the timed steps only
+    if os.environ.get("BENCH_QUICK"):                 # used under ncu and for the opt-in variants: the timed steps only
+        quick = {"quick": True, "value": world * args.steps * pairs / (ms_total * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": ms_total / args.steps}
+        if os.environ.get("BENCH_VARIANT_CHECK") and os.environ.get("TSDRGPU_AUTOCORR_HALF") and world == 1:
+            # the batched frame-rate detector with and without the half-size transforms on the same four captures: how far the two
+            # running-mean plots are apart, relative to the plot's peak (the parity bound of the default path is 1e-5)
+            try:
+                step.join(); torch.cuda.synchronize()
+                caps = torch.abs(torch.randn(4 * step.cap, device=iq_dev.device)) + 0.25
+                got = {}
+                for mode in ("1", None):
+                    if mode is None:
+                        os.environ.pop("TSDRGPU_AUTOCORR_HALF", None)
+                    det = gpu.framerate_detector()
+                    det.run_batch(FS, caps, step.cap, 4, step.cap)
+                    (_, fp), (_, lp) = det.plots(FS)
+                    got[mode] = (fp.copy(), lp.copy())
+                os.environ["TSDRGPU_AUTOCORR_HALF"] = "1"
+                quick["frd_plot_max_rel_diff_vs_default"] = max(float(np.max(np.abs(got["1"][i] - got[None][i])) / np.max(np.abs(got[None][i]))) for i in (0, 1))
+            except Exception as e:
+                quick["frd_plot_check_failed"] = repr(e)[:160]
         if rank == 0:
-            emit({"quick": True, "value": world * args.steps * pairs / (ms_total * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": ms_total / args.steps})
+            emit(quick)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -477,9 +496,10 @@ def run_ours(args):
         for name, env in (("autocorr_half_size", {"TSDRGPU_AUTOCORR_HALF": "1"}),):
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))],
-                                   capture_output=True, text=True, timeout=180, env=dict(os.environ, BENCH_QUICK="1", **env))
+                                   capture_output=True, text=True, timeout=180, env=dict(os.environ, BENCH_QUICK="1", BENCH_VARIANT_CHECK="1", **env))
                 q = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
                 variants[name] = {"value": q["value"], "unit": "MS/s", "ms_per_step": q["ms_per_step"], "env": env,
+                                  **{k: q[k] for k in ("frd_plot_max_rel_diff_vs_default", "frd_plot_check_failed") if k in q},
                                   "note": "device-resident value of the same workload with this opt-in path (DESIGN.md section 9)"}
             except Exception as e:
                 variants[name] = {"unavailable": repr(e)[:160], "env": env}
