@@ -151,3 +151,29 @@ def test_host_library_end_to_end(tmp_path):
     for k, wv in enumerate(want):
         assert np.array_equal(got[k].view(np.uint32), wv.view(np.uint32)), f"frame {k}"
     lib.tsdr_free(C.byref(t))
+
+
+def test_a_plain_c_host_links_and_runs(tmp_path):
+    """INTEGRATION.md section A, literally: a C program compiled against include/TSDRLibrary.h and linked with libTSDRLibrary.a +
+    libtsdrgpu.so drives init -> setresolution -> loadplugin -> readasync -> free.  On this machine's hardware it must either
+    deliver frames (GPU) or fail with TSDR_CANNOT_OPEN_DEVICE and the 'no CPU fallback' text (no GPU)."""
+    import subprocess
+    libdir = os.path.join(ROOT, "tempestsdr_b200", "lib")
+    exe = tmp_path / "host_smoke"
+    subprocess.run(["gcc", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_host", "host_smoke.c"),
+                    os.path.join(libdir, "libTSDRLibrary.a"), "-L", libdir, "-ltsdrgpu", f"-Wl,-rpath,{libdir}", "-ldl", "-lpthread", "-lm",
+                    "-o", str(exe)], check=True)
+    raw = tmp_path / "iq.int8"
+    (np.random.default_rng(3).integers(-100, 100, 4 << 20, dtype=np.int64).astype(np.int8)).tofile(raw)
+    plugin = os.path.join(libdir, "TSDRPlugin_RawFileGPU.so")
+    r = subprocess.run([str(exe), plugin, f'"{raw}" 2000000 int8 nopace'], capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, TSDR_NO_DROP="1"))
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr[-500:])
+    import torch
+    if torch.cuda.is_available():
+        assert "rc=0" in r.stdout
+    else:
+        assert "rc=6" in r.stdout and "no CPU fallback" in r.stdout
+    # and a plugin that does not exist is reported like the reference does (TSDR_INCOMPATIBLE_PLUGIN = 7)
+    r = subprocess.run([str(exe), "/nonexistent/plugin.so", "x"], capture_output=True, text=True, timeout=60)
+    assert "loadplugin rc=7" in r.stdout
