@@ -61,7 +61,8 @@ def make_iq(pairs: int, seed: int) -> np.ndarray:
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index):
+        """index: one GPU index, or a comma-separated list (then `per_gpu` in the result tells the GPUs apart)."""
         self.index, self.proc, self.path = index, None, None
 
     def start(self):
@@ -85,13 +86,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per = [], [], set(), {}
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 9:
                     continue
                 sm.append(float(p[1])); mx.append(float(p[2]))
+                per.setdefault(p[0], []).append(float(p[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
@@ -100,6 +102,8 @@ class ClockSampler:
             pass
         if sm:
             out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            if len(per) > 1:
+                out["per_gpu"] = {k: statistics.median(v) for k, v in sorted(per.items())}
         return out
 
 
@@ -249,8 +253,11 @@ def run_ours(args):
     launches0 = gpu.launches
     frames0, caps0 = step.frames, step.captures
     sampler = ClockSampler(local)
+    sampler_all = ClockSampler(",".join(str(i) for i in range(world))) if world > 1 else None     # every GPU of the job, informational
     if rank == 0:
         sampler.start()
+        if sampler_all:
+            sampler_all.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -262,6 +269,10 @@ def run_ours(args):
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and sampler_all:
+        allg = sampler_all.stop()
+        if allg.get("sm_mhz") is not None:
+            clocks["all_gpus"] = allg                 # the headline keys above stay rank 0's GPU, as at N = 1
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
