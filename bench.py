@@ -38,15 +38,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FS, HEIGHT, FV = 25_000_000, 1125, 60.0
-FRAMES_PER_STEP = 64
+FRAMES_PER_BATCH = 64                                     # frames per launch group (one pass over the resident 213 MB of IQ)
+BATCHES_PER_STEP = int(os.environ.get("BENCH_BATCHES_PER_STEP", "48"))   # one step = 48 such passes = 3072 frames = 1.28 G IQ pairs (~40 ms)
+FRAMES_PER_STEP = FRAMES_PER_BATCH * BATCHES_PER_STEP
 METRIC = "IQ MS/s ingested -> 1080p60 frames (demod+resample+frame stage+autocorrelation), whole job"
 
 
 def geometry():
-    from tempestsdr_b200 import _native as N
-    w, pr, pt = C.c_int(0), C.c_double(0), C.c_double(0)
-    N.lib().tsdrgpu_geometry(FS, HEIGHT, FV, C.byref(w), C.byref(pr), C.byref(pt))
-    return w.value
+    """set_internal_samplerate's width (TSDRLibrary.c:540-550), restated in Python so that the reference arm loads none of
+    this repo's native code."""
+    return int(2 * (FS / (FV * HEIGHT)))
 
 
 def make_iq(pairs: int, seed: int) -> np.ndarray:
@@ -116,7 +117,7 @@ class DeviceStep:
         from tempestsdr_b200.api import FrameRateDetector, PostProcessFlags
         self.torch, self.gpu, self.iq, self.w = torch, gpu, iq_dev, w
         self.block = int(0.1 * FS / FV)
-        self.nblocks = FRAMES_PER_STEP * 10
+        self.nblocks = FRAMES_PER_BATCH * 10
         self.n = w * HEIGHT
         self.up = w * HEIGHT * FV
         self.rs = gpu.resampler()
@@ -128,7 +129,7 @@ class DeviceStep:
         max_pix = int(self.rs.plan((self.block, self.nblocks), self.up, float(FS))) + 1024
         self.pix = torch.empty(max_pix + self.n + 1024, dtype=torch.float32, device=iq_dev.device)
         self.pix_fill = 0
-        self.frames_out = [torch.empty(FRAMES_PER_STEP * self.n, dtype=torch.float32, device=iq_dev.device) for _ in range(2)]
+        self.frames_out = [torch.empty(FRAMES_PER_BATCH * self.n, dtype=torch.float32, device=iq_dev.device) for _ in range(2)]
         self.pairs = self.block * self.nblocks
         self.mag = torch.empty(self.cap + self.pairs, dtype=torch.float32, device=iq_dev.device)   # demodulated stream, capture-aligned
         self.mag_fill = 0
@@ -146,7 +147,7 @@ class DeviceStep:
         out = self.rs.process(self.iq, (self.block, self.nblocks), self.up, float(FS), in_is_iq=True, out=self.pix[self.pix_fill:],
                               mag_out=self.mag[self.mag_fill:] if fused_mag else None)
         self.pix_fill += out.numel()
-        nf = min(self.pix_fill // self.n, FRAMES_PER_STEP)
+        nf = min(self.pix_fill // self.n, FRAMES_PER_BATCH)
         # the frame stage in sub-batches of `chunk` frames (default: the whole step at once).  Smaller sub-batches keep a batch's
         # intermediate frames in L2 between the kernels of the stage at the price of more launches.
         chunk = self.chunk if self.chunk > 0 else nf
@@ -156,8 +157,8 @@ class DeviceStep:
             self.pp.process(self.pix[c0 * self.n: c1 * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=fo[c0 * self.n: c1 * self.n], want_results=False)
         self.k += 1
         left = self.pix_fill - nf * self.n
-        if left:
-            self.pix[:left].copy_(self.pix[nf * self.n: self.pix_fill])      # left << nf*n: the ranges do not overlap
+        if left:                                                             # left << nf*n: the ranges do not overlap
+            gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, self.pix.data_ptr(), self.pix.data_ptr() + 4 * nf * self.n, 4 * left))
         self.pix_fill = left
         self.frames += nf
         # frame-rate detector: the whole stream is demodulated once; every complete capture of 3.1*fs/55 samples is
@@ -170,7 +171,7 @@ class DeviceStep:
             self.frd.run_batch(FS, self.mag, self.cap, ncap, self.cap)
             rest = self.mag_fill - ncap * self.cap
             if rest:
-                self.mag[:rest].copy_(self.mag[ncap * self.cap: self.mag_fill])
+                gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, self.mag.data_ptr(), self.mag.data_ptr() + 4 * ncap * self.cap, 4 * rest))
             self.mag_fill = rest
             self.captures += ncap
 
@@ -222,6 +223,90 @@ def cpu_baseline(w, seconds_budget=25.0):
                       f"{ncap} captures of {cap} samples autocorrelated: {t_cap:.2f} s each; stages driven serially on one thread"}
 
 
+def _load_tsdr(path):
+    lib = C.CDLL(path)
+    lib.tsdr_init.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tsdr_setresolution.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.tsdr_motionblur.argtypes = [C.c_void_p, C.c_float]
+    lib.tsdr_setgain.argtypes = [C.c_void_p, C.c_float]
+    lib.tsdr_setparameter_int.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    lib.tsdr_loadplugin.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    lib.tsdr_readasync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tsdr_stop.argtypes = [C.c_void_p]
+    lib.tsdr_free.argtypes = [C.POINTER(C.c_void_p)]
+    lib.tsdr_getlasterrortext.argtypes = [C.c_void_p]
+    lib.tsdr_getlasterrortext.restype = C.c_char_p
+    return lib
+
+
+def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier):
+    """The drop-in boundary end to end, measured the way the reference arm is measured: this repo's libTSDRLibrary.so driven
+    through tsdr_init / tsdr_loadplugin / tsdr_readasync with an UNMODIFIED front-end plugin -- the reference's own
+    TSDRPlugin_RawFile (pacing off: its PERFORMANCE_BENCHMARK switch) reading float32 IQ from a file and calling process() with
+    its pageable 2 MiB malloc'd buffer -- and counting the frames the frame callback receives.  The plugin binary is a data
+    source, not an oracle; when it did not travel with the snapshot this repo's own file plugin plays the same role (host
+    conversion, float callback, no raw sink)."""
+    FRAME_CB = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p)
+    VALUE_CB = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_double, C.c_void_p)
+    PLOT_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_uint32, C.c_void_p)
+    ref_plugin = os.path.join(ROOT, "oracle", "_ref", "libTSDRPlugin_RawFile_nopace.so")
+    own_plugin = os.path.join(ROOT, "tempestsdr_b200", "lib", "TSDRPlugin_RawFileGPU.so")
+    per_frame = int(FS / FV)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.NamedTemporaryFile(prefix=f"tsdr_iq_r{rank}_", suffix=".raw", delete=False, dir=shm)
+    make_iq(16 * per_frame, seed=1000 + rank).tofile(tmp); tmp.close()
+    os.environ["TSDR_CUDA_DEVICE"] = str(local); os.environ["TSDR_BATCH_FRAMES"] = "16"; os.environ["TSDR_NO_DROP"] = "1"
+    if os.path.exists(ref_plugin):
+        plugin, params, which = ref_plugin, f'"{tmp.name}" {FS} float', "reference TSDRPlugin_RawFile (unmodified source, pacing switch off)"
+    else:
+        os.environ["TSDR_NO_RAW_SINK"] = "1"
+        plugin, params, which = own_plugin, f'"{tmp.name}" {FS} float nopace', "this repo's TSDRPlugin_RawFileGPU in plain ten-symbol mode (reference plugin binary absent)"
+    lib = _load_tsdr(os.path.join(ROOT, "tempestsdr_b200", "lib", "libTSDRLibrary.so"))
+    count = {"frames": 0, "w": 0, "h": 0}
+
+    def on_frame(buf, ww, hh, ctx):
+        count["frames"] += 1; count["w"] = ww; count["h"] = hh
+    fcb, vcb, pcb = FRAME_CB(on_frame), VALUE_CB(lambda *a: None), PLOT_CB(lambda *a: None)
+    t = C.c_void_p()
+    lib.tsdr_init(C.byref(t), C.cast(vcb, C.c_void_p), C.cast(pcb, C.c_void_p), None)
+    lib.tsdr_setresolution(t, HEIGHT, FV); lib.tsdr_motionblur(t, 0.0); lib.tsdr_setgain(t, 0.5)
+    for pid, v in ((0, 1), (1, 0), (6, 1)):          # AUTOSHIFT=1, PLL=0, LOW_PASS_BEFORE_SYNC=1: the reference arm's settings
+        lib.tsdr_setparameter_int(t, pid, v)
+    out = {"unavailable": None}
+    try:
+        rc = lib.tsdr_loadplugin(t, plugin.encode(), params.encode())
+        if rc != 0:
+            raise RuntimeError(f"tsdr_loadplugin rc={rc}: {lib.tsdr_getlasterrortext(t)}")
+        rcs = []
+        th = threading.Thread(target=lambda: rcs.append(lib.tsdr_readasync(t, C.cast(fcb, C.c_void_p), None)), daemon=True)
+        th.start()
+        deadline = time.perf_counter() + 30.0
+        while count["frames"] < 64 and th.is_alive() and time.perf_counter() < deadline:     # warm-up: buffers grow, plugin buffer gets registered
+            time.sleep(0.02)
+        if not th.is_alive() or count["frames"] < 64:
+            raise RuntimeError(f"no frames from tsdr_readasync (rc={rcs}): {lib.tsdr_getlasterrortext(t)}")
+        barrier()
+        f0, t0 = count["frames"], time.perf_counter()
+        time.sleep(seconds)
+        f1, t1 = count["frames"], time.perf_counter()
+        barrier()
+        lib.tsdr_stop(t)
+        th.join(timeout=30)
+        fps = (f1 - f0) / (t1 - t0)
+        out = {"value_per_rank": fps * per_frame / 1e6, "frames_per_s": fps, "seconds": t1 - t0, "frames_delivered": f1 - f0,
+               "frame": [count["w"], count["h"]], "plugin": which, "readasync_rc": rcs[0] if rcs else None,
+               "h2d_bytes_per_frame": 8 * per_frame, "d2h_bytes_per_frame": 4 * count["w"] * count["h"]}
+    except Exception as e:
+        out = {"unavailable": repr(e)[:300]}
+    finally:
+        try:
+            lib.tsdr_free(C.byref(t))
+        except Exception:
+            pass
+        os.unlink(tmp.name)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -231,16 +316,24 @@ def run_ours(args):
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     torch.cuda.set_device(local)
+    gpu = api.Context(local)
+    # this rank's threads and page-locked buffers on the socket its GPU hangs off (8 ranks on a two-socket box)
+    numa_node = gpu._lib.tsdrgpu_device_numa_node(gpu._h)
+    numa_bound = gpu._lib.tsdrgpu_bind_thread_near_device(gpu._h) == 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    gpu = api.Context(local)
     w = geometry()
     block = int(0.1 * FS / FV)
-    pairs = block * 10 * FRAMES_PER_STEP
+    pairs = block * 10 * FRAMES_PER_BATCH                 # IQ pairs per batch (one pass over the resident buffer)
+    pairs_step = pairs * BATCHES_PER_STEP
     iq_host = make_iq(pairs, seed=1000 + rank)
     iq_pinned = torch.from_numpy(iq_host).pin_memory()
     iq_dev = iq_pinned.cuda(non_blocking=True)
-    step = DeviceStep(gpu, iq_dev, w)
+    batch = DeviceStep(gpu, iq_dev, w)
+
+    def step():
+        for _ in range(BATCHES_PER_STEP):
+            batch()
 
     def barrier():
         if world > 1:
@@ -251,7 +344,7 @@ def run_ours(args):
         step()
     barrier()
     launches0 = gpu.launches
-    frames0, caps0 = step.frames, step.captures
+    frames0, caps0 = batch.frames, batch.captures
     sampler = ClockSampler(local)
     sampler_all = ClockSampler(",".join(str(i) for i in range(world))) if world > 1 else None     # every GPU of the job, informational
     if rank == 0:
@@ -264,8 +357,8 @@ def run_ours(args):
     t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps     # host time to ENQUEUE a step (nothing is waited for)
-    step.join()                                   # the side stream's tail (last sync search + re-centring) is inside the timed region
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / (args.steps * BATCHES_PER_STEP)   # host time to ENQUEUE one batch (throttled by the 4-slot descriptor ring)
+    batch.join()                                  # the side stream's tail (last sync search + re-centring) is inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -278,57 +371,44 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
     launches = gpu.launches - launches0
-    frames_done, caps_done = step.frames - frames0, step.captures - caps0
+    frames_done, caps_done = batch.frames - frames0, batch.captures - caps0
+    value = world * args.steps * pairs_step / (ms_total * 1e-3) / 1e6
 
     if os.environ.get("BENCH_QUICK"):                 # used under ncu and for the opt-in variants: the timed steps only
-        quick = {"quick": True, "value": world * args.steps * pairs / (ms_total * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": ms_total / args.steps}
-        if os.environ.get("BENCH_VARIANT_CHECK") and os.environ.get("TSDRGPU_AUTOCORR_HALF") and world == 1:
-            # the batched frame-rate detector with and without the half-size transforms on the same four captures: how far the two
-            # running-mean plots are apart, relative to the plot's peak (the parity bound of the default path is 1e-5)
-            try:
-                step.join(); torch.cuda.synchronize()
-                caps = torch.abs(torch.randn(4 * step.cap, device=iq_dev.device)) + 0.25
-                got = {}
-                for mode in ("1", None):
-                    if mode is None:
-                        os.environ.pop("TSDRGPU_AUTOCORR_HALF", None)
-                    det = gpu.framerate_detector()
-                    det.run_batch(FS, caps, step.cap, 4, step.cap)
-                    (_, fp), (_, lp) = det.plots(FS)
-                    got[mode] = (fp.copy(), lp.copy())
-                os.environ["TSDRGPU_AUTOCORR_HALF"] = "1"
-                quick["frd_plot_max_rel_diff_vs_default"] = max(float(np.max(np.abs(got["1"][i] - got[None][i])) / np.max(np.abs(got[None][i]))) for i in (0, 1))
-            except Exception as e:
-                quick["frd_plot_check_failed"] = repr(e)[:160]
         if rank == 0:
-            emit(quick)
+            emit({"quick": True, "value": value, "unit": "MS/s", "ms_per_step": ms_total / args.steps, "ms_per_batch": ms_total / (args.steps * BATCHES_PER_STEP)})
         if world > 1:
             dist.destroy_process_group()
         return
-    # host cost of enqueueing a step when nothing throttles it (3 steps right after a full synchronisation: the resampler's
-    # 4-slot descriptor ring cannot be full yet).  Informational: it tells how far the host is from being the bottleneck.
-    step.join(); torch.cuda.synchronize()
-    t_h = time.perf_counter()
-    for _ in range(3):
-        step()
-    host_enqueue_free_ms = (time.perf_counter() - t_h) * 1e3 / 3
-    step.join(); torch.cuda.synchronize()
-    # ---- per-kernel timing pass (separate from the timed region above): CUDA events on the launching stream
+    # ---- per-kernel timing pass (separate from the timed region above): CUDA events on the launching stream.
     # The side stream is switched off for this pass so that every kernel's event pair measures that kernel alone
     # (with it on, intervals on the main stream also contain the slowdown from sharing the chip with the sync search).
-    step.join(); torch.cuda.synchronize()
-    step.pp.set_overlap(False)
+    batch.join(); torch.cuda.synchronize()
+    batch.pp.set_overlap(False)
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
     collect_profile(gpu)
-    prof_steps = 3
-    caps_before_prof = step.captures
-    for _ in range(prof_steps):
-        step()
+    prof_batches = 3
+    caps_before_prof = batch.captures
+    for _ in range(prof_batches):
+        batch()
     prof = collect_profile(gpu)
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
-    step.pp.set_overlap(not os.environ.get("BENCH_NO_OVERLAP"))
+    batch.pp.set_overlap(not os.environ.get("BENCH_NO_OVERLAP"))
+    prof_caps = (batch.captures - caps_before_prof) / prof_batches          # captures autocorrelated per profiled batch
+    acs = autocorr_sweep(gpu, torch) if (rank == 0 and not os.environ.get("BENCH_NO_SWEEP")) else None
+    barrier()
 
-    # ---- e2e through the C-ABI pipeline with host buffers
+    # ---- e2e (headline): the reference-facing API end to end with an unmodified plugin, as the reference arm is measured
+    e2e_seconds = float(os.environ.get("BENCH_E2E_SECONDS", "3.0"))
+    api_run = e2e_through_tsdr_api(local, rank, w, e2e_seconds, barrier)
+    if world > 1:
+        tot = torch.tensor([api_run.get("value_per_rank", 0.0), 1.0 if "value_per_rank" in api_run else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot)
+        api_total, api_ok = tot[0].item(), int(tot[1].item())
+    else:
+        api_total, api_ok = api_run.get("value_per_rank", 0.0), int("value_per_rank" in api_run)
+
+    # ---- beside it: tsdrgpu_pipeline_process() fed from PINNED host memory in 16 MiB calls (what a GPU-aware front end can do)
     chunk = 512 * 1024 * 8                     # floats per process() call (8x the RawFile plugin's block)
     pl = pipeline.Pipeline(samplerate=FS, height=HEIGHT, refreshrate=FV, batch_frames=16, batch_blocks=160, block_when_busy=True,
                            device=local, params={"autoshift": 1, "lowpass_before_sync": 1})
@@ -342,10 +422,10 @@ def run_ours(args):
             pl.process_ptr(base_ptr + 4 * pos, n, 0)
             pos += n
 
-    # the link under the e2e number: pinned H2D and D2H of one step's bytes, alone and together (context, not a claim)
+    # the link under the e2e number: pinned H2D and D2H of one batch's bytes, alone and together (context, not a claim)
     def link_gbs():
-        d_in = torch.empty_like(iq_dev); h_out = torch.empty(FRAMES_PER_STEP * step.n, dtype=torch.float32).pin_memory()
-        d_out = step.frames_out[0]
+        d_in = torch.empty_like(iq_dev); h_out = torch.empty(FRAMES_PER_BATCH * batch.n, dtype=torch.float32).pin_memory()
+        d_out = batch.frames_out[0]
         s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
         res = {}
         reps = 4
@@ -364,26 +444,37 @@ def run_ours(args):
             res[name + "_gbs"] = nbytes / dt / 1e9
         return res
     link = link_gbs()
-    e2e_steps = max(2, min(args.steps, 6))
     feed_once(); pl.flush()
     barrier()
     s0 = pl.stats()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        feed_once()
+    e2e_passes = 0
+    while True:                                   # at least 2 s of wall clock, the same number of passes on every rank
+        feed_once(); e2e_passes += 1
+        go = torch.tensor([1.0 if time.perf_counter() - t0 < 2.0 else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(go, op=dist.ReduceOp.MAX)
+        if go.item() == 0.0 or e2e_passes >= 400:
+            break
     pl.flush()
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     s1 = pl.stats()
-    e2e_val = world * e2e_steps * pairs / t_e2e.item() / 1e6
-    h2d = (s1.h2d_bytes - s0.h2d_bytes) // e2e_steps
-    d2h = (s1.d2h_bytes - s0.d2h_bytes) // e2e_steps
-    e2e_frames = s1.frames_delivered - s0.frames_delivered
+    pinned_val = world * e2e_passes * pairs / t_e2e.item() / 1e6
+    pinned = {"value": pinned_val, "unit": "MS/s", "seconds": t_e2e.item(), "passes": e2e_passes,
+              "h2d_bytes_per_pass": int((s1.h2d_bytes - s0.h2d_bytes) // e2e_passes), "d2h_bytes_per_pass": int((s1.d2h_bytes - s0.d2h_bytes) // e2e_passes),
+              "frames_delivered": int(s1.frames_delivered - s0.frames_delivered), "pcie_link_measured": link,
+              # bytes per sample over the link: 8 in + 4*pixels-per-sample out; bound by each direction alone and by both together
+              "link_bound_MS_per_s": min(link["h2d_gbs"] / 8.0, link["d2h_gbs"] / (4.0 * batch.n * FRAMES_PER_BATCH / pairs),
+                                         link["duplex_gbs"] / (8.0 + 4.0 * batch.n * FRAMES_PER_BATCH / pairs)) * 1e3,
+              "how": "tsdrgpu_pipeline_process() on PINNED host IQ in 16 MiB calls, frames copied back to pinned host slots; "
+                     "host wall clock between device synchronisations"}
+    pinned["of_link_bound"] = pinned_val / world / pinned["link_bound_MS_per_s"]
     pl.close()
 
-    # ---- the same e2e with the samples crossing PCIe as int8 (raw sink / tsdrgpu_pipeline_process_raw):
+    # ---- the same with the samples crossing PCIe as int8 (raw sink / tsdrgpu_pipeline_process_raw):
     # reported beside the headline, never instead of it (the reference arm reads float32)
     e2e_int8 = None
     if world == 1 and not os.environ.get("BENCH_NO_INT8"):
@@ -399,66 +490,25 @@ def run_ours(args):
                 pl8.process_raw_ptr(ptr8 + pos, 1, n, 0)
                 pos += n
         feed8(); pl8.flush()
-        a0 = pl8.stats(); t8 = time.perf_counter()
-        for _ in range(e2e_steps):
-            feed8()
+        a0 = pl8.stats(); t8 = time.perf_counter(); n8p = 0
+        while time.perf_counter() - t8 < 1.0:
+            feed8(); n8p += 1
         pl8.flush(); torch.cuda.synchronize()
         t8 = time.perf_counter() - t8
         a1 = pl8.stats()
-        e2e_int8 = {"value": e2e_steps * pairs / t8 / 1e6, "unit": "MS/s", "h2d_bytes_per_step": int((a1.h2d_bytes - a0.h2d_bytes) // e2e_steps),
-                    "d2h_bytes_per_step": int((a1.d2h_bytes - a0.d2h_bytes) // e2e_steps), "frames_delivered": int(a1.frames_delivered - a0.frames_delivered),
+        e2e_int8 = {"value": n8p * pairs / t8 / 1e6, "unit": "MS/s", "h2d_bytes_per_pass": int((a1.h2d_bytes - a0.h2d_bytes) // n8p),
+                    "d2h_bytes_per_pass": int((a1.d2h_bytes - a0.d2h_bytes) // n8p), "frames_delivered": int(a1.frames_delivered - a0.frames_delivered),
                     "how": "tsdrgpu_pipeline_process_raw(int8) on pinned host samples, converted on the device (TSDRPlugin_RawFile.c:247 values); "
                            "float32 frames copied back as in e2e"}
         pl8.close()
 
     # ---- N > 1 only: the path's one real exchange, the superbandwidth stitch with one hop per GPU (configs[3])
-    superb = None
-    if world > 1:
-        from tempestsdr_b200 import superband
-        hop_pairs = 10 * int(FS / FV)                        # SUPER_SAMPLES_TO_RECORD frames per hop -> N = 2^22
-        hop = iq_dev[: 2 * hop_pairs].contiguous()
-        for _ in range(2):
-            superband.stitch_distributed(gpu, hop, int(FS / FV))
-        barrier()
-        s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        s0e.record()
-        for _ in range(reps):
-            res, lags, n_fft = superband.stitch_distributed(gpu, hop, int(FS / FV))
-        s1e.record()
-        barrier()
-        tms = torch.tensor([s0e.elapsed_time(s1e) / reps], device="cuda")
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        superb = {"hops": world, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": world * n_fft / (tms.item() * 1e-3) / 1e6,
-                  "allgather_bytes_per_rank": 8 * (n_fft + n_fft // 2), "collective": "one NCCL all_gather_into_tensor per stitch"}
-        # the same stitch with the all-gather fused into the forward transforms' last pass (NVLink peer stores through CUDA IPC,
-        # a 4-byte all-reduce as the barrier): DESIGN.md section 6
-        try:
-            ex = superband.PeerExchange(gpu, 2 * n_fft)
-            for _ in range(2):
-                superband.stitch_distributed_fused(gpu, hop, int(FS / FV), ex)
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(reps):
-                res_f, lags_f, _ = superband.stitch_distributed_fused(gpu, hop, int(FS / FV), ex)
-            f1.record()
-            barrier()
-            tf = torch.tensor([f0.elapsed_time(f1) / reps], device="cuda")
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            same = torch.tensor([int(bool(torch.equal(res, res_f)) and list(lags_f) == list(lags))], device="cuda")
-            dist.all_reduce(same, op=dist.ReduceOp.MIN)
-            superb["fused_peer_store"] = {"ms_per_stitch": tf.item(), "stitched_MS_per_s": world * n_fft / (tf.item() * 1e-3) / 1e6,
-                                          "bit_identical_to_nccl_path": bool(same.item()),
-                                          "how": "FFT last pass stores into every rank's gather buffer (peer memory), then a 4-byte all-reduce as barrier"}
-            ex.close()
-        except Exception as e:                                   # peer access unavailable on this box: the NCCL figure stands alone
-            superb["fused_peer_store"] = {"unavailable": repr(e)[:200]}
+    superb = superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier) if world > 1 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (by total device time in the profiled steps)
+    # ---- roofline of the dominant kernel (by total device time in the profiled batches)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -466,23 +516,25 @@ def run_ours(args):
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
     ratio = w * HEIGHT * FV / FS
-    # algorithmic bytes per launch (DESIGN.md "algorithmic bytes"), per kernel
-    n_pix = step.n * FRAMES_PER_STEP
-    prof_caps = (step.captures - caps_before_prof) / prof_steps          # captures autocorrelated per profiled step
-    alg = {   # ALGORITHMIC bytes per launch
+    n_pix = batch.n * FRAMES_PER_BATCH
+    NFFT = 1 << 20                                        # cfg2 capture 1 409 090 -> N = 2^20
+    # ALGORITHMIC bytes per launch.  The autocorrelation of one capture runs at half size (N/2 complex
+    # points per transform): per capture the fused passes move  fwd A: read 8*(N/2) write 8*(N/2);  fwd B (+ finish, |X|/N):
+    # read 8*(N/2) write 4*N;  inv A: read 4*N write 8*(N/2);  inv B (+ finish): read 8*(N/2) write 8*N  = 40*N bytes in all
+    # (SURVEY 8d's single-pass ideal is 28*N); a launch covers every capture of the batch (grid.y).
+    alg = {
         "rs_main": pairs * (8 + 4 * ratio + (0 if os.environ.get("BENCH_SEPARATE_DEMOD") else 4)),   # 8 B per IQ pair in + 4 B per pixel out (+ 4 B magnitude out)
         "fs_minmax": 4 * n_pix, "fs_normalise": 8 * n_pix, "fs_timelowpass": 8 * n_pix, "fs_norm_lowpass": 8 * n_pix,
         "fs_collapse": 4 * n_pix, "fs_shift": 8 * n_pix, "demod_kernel": 12 * pairs,
-        # one FFT pass reads and writes every complex point once; a launch covers all captures of the step (grid.y);
-        # a step's autocorrelations are 4 launches (2 passes forward, 2 inverse)
-        "fft_pass_kernel": 16 * (1 << 20) * prof_caps * 4 / max(1.0, prof.get("fft_pass_kernel", (0, 4 * prof_steps))[1] / prof_steps),
+        "fft_pass_kernel": FFT_BYTES_PER_CAPTURE(NFFT) * prof_caps / max(1.0, prof.get("fft_pass_kernel", (0, 4 * prof_batches))[1] / prof_batches),
     }
-    label = {"rs_main": "rs_main<IQ> (fused demod+resample)", "fft_pass_kernel": "fft_pass_kernel (one pass over every capture of the step)"}
+    alg.update({k: v * prof_caps for k, v in FINISH_BYTES(NFFT).items()})
+    label = {"rs_main": "rs_main<IQ> (fused demod+resample)", "fft_pass_kernel": "fft_pass_kernel (one pass over every capture of the batch)"}
     total_prof = sum(t for t, _ in prof.values()) or 1.0
-    kernels = {k: {"ms_per_step": t / prof_steps, "launches_per_step": c / prof_steps, "share": t / total_prof} for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    kernels = {k: {"ms_per_batch": t / prof_batches, "launches_per_batch": c / prof_batches, "share": t / total_prof} for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     dom = next(iter(kernels))
-    # the roofline object is for the dominant kernel of the step among the bandwidth kernels; fs_sync (one cluster of 8
-    # CTAs, FP64-latency bound by construction) is listed in per_kernel but has no bandwidth roofline
+    # the roofline object is for the dominant kernel of the step among the bandwidth kernels; fs_sync (clusters of CTAs walking
+    # the frames in order, FP64-latency bound by construction) is listed in per_kernel but has no bandwidth roofline
     roof_k = next((k for k in kernels if alg.get(k)), "rs_main")
     t_k, c_k = prof.get(roof_k, (0.0, 0))
     achieved = alg[roof_k] / (t_k / c_k * 1e-3) / 1e9 if c_k else None
@@ -490,60 +542,128 @@ def run_ours(args):
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[roof_k], "avg_launch_ms": (t_k / c_k) if c_k else None,
                 "dominant_kernel_by_time": dom,
-                "per_kernel": {k: dict(v, **({"achieved_gbs": alg[k] * v["launches_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9,
-                                              "frac": alg[k] * v["launches_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9 / peak} if alg.get(k) else {})) for k, v in kernels.items()}}
+                # the whole batch against SURVEY 8d's algorithmic bytes: 16 B per sample + 16 B per pixel + 28 N per capture
+                "whole_step": {"algorithmic_bytes_per_batch": 16 * pairs + 16 * n_pix + 28 * NFFT * (caps_done / (args.steps * BATCHES_PER_STEP)),
+                               "ms_per_batch": ms_total / (args.steps * BATCHES_PER_STEP)},
+                "per_kernel": {k: dict(v, **({"achieved_gbs": alg[k] * v["launches_per_batch"] / (v["ms_per_batch"] * 1e-3) / 1e9,
+                                              "frac": alg[k] * v["launches_per_batch"] / (v["ms_per_batch"] * 1e-3) / 1e9 / peak} if alg.get(k) else {})) for k, v in kernels.items()}}
+    ws = roofline["whole_step"]
+    ws["achieved_gbs"] = ws["algorithmic_bytes_per_batch"] / (ws["ms_per_batch"] * 1e-3) / 1e9
+    ws["frac"] = ws["achieved_gbs"] / peak
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
         roofline["traffic"] = tr.get(roof_k, {}).get("dram_bytes_per_launch")
         roofline["traffic_source"] = tr.get(roof_k, {}).get("source")
     except Exception:
         pass
-    value = world * args.steps * pairs / (ms_total * 1e-3) / 1e6
-    # opt-in code paths measured on the same workload in a child process (own CUDA context: whatever happens there cannot touch
-    # the numbers above).  Informational; the headline is always the default path.
-    variants = None
-    if world == 1 and not os.environ.get("BENCH_NO_VARIANTS"):
-        variants = {}
-        for name, env in (("autocorr_half_size", {"TSDRGPU_AUTOCORR_HALF": "1"}),):
-            try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))],
-                                   capture_output=True, text=True, timeout=180, env=dict(os.environ, BENCH_QUICK="1", BENCH_VARIANT_CHECK="1", **env))
-                q = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-                variants[name] = {"value": q["value"], "unit": "MS/s", "ms_per_step": q["ms_per_step"], "env": env,
-                                  **{k: q[k] for k in ("frd_plot_max_rel_diff_vs_default", "frd_plot_check_failed") if k in q},
-                                  "note": "device-resident value of the same workload with this opt-in path (DESIGN.md section 9)"}
-            except Exception as e:
-                variants[name] = {"unavailable": repr(e)[:160], "env": env}
     cpu = cpu_baseline(w)
+    if api_ok == world:
+        e2e = {"value": api_total, "unit": "MS/s",
+               "h2d_bytes_per_step": int(api_run["h2d_bytes_per_frame"] * FRAMES_PER_STEP), "d2h_bytes_per_step": int(api_run["d2h_bytes_per_frame"] * FRAMES_PER_STEP),
+               "seconds": api_run["seconds"], "frames_per_s_rank0": api_run["frames_per_s"], "plugin": api_run["plugin"],
+               "how": "this repo's libTSDRLibrary.so through tsdr_init/tsdr_loadplugin/tsdr_readasync with an unmodified file plugin handing over "
+                      "its pageable 2 MiB malloc'd float32 buffer (page-locked in place after it came back 3 times), 16 frames per launch group, "
+                      "frames delivered to the tsdr_readasync_function counted x samples per frame -- the reference arm's own method; the plugin's "
+                      "single thread (fread + memcpy per block) is inside the timed region",
+               "pinned_process": pinned}
+    else:                                          # the API run failed on some rank: the pinned figure stands, and says so
+        e2e = {"value": pinned_val, "unit": "MS/s", "h2d_bytes_per_step": pinned["h2d_bytes_per_pass"] * BATCHES_PER_STEP,
+               "d2h_bytes_per_step": pinned["d2h_bytes_per_pass"] * BATCHES_PER_STEP, "how": pinned["how"], "tsdr_api_run": api_run, "pinned_process": pinned}
     line = {
         "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 accumulators where the reference uses them)", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 1080p60 geometry (1125 total lines -> 740x1125 px frames), 25 MS/s float32 IQ, "
-                               f"{FRAMES_PER_STEP} frames per step ({pairs} IQ pairs, {8 * pairs / 1e6:.0f} MB > L2, so no L2 flush is needed)",
+        "config": {"workload": "BASELINE configs[1]: 1080p60 geometry (1125 total lines -> 740x1125 px frames), 25 MS/s float32 IQ; one step = "
+                               f"{BATCHES_PER_STEP} passes over {pairs} resident IQ pairs ({8 * pairs / 1e6:.0f} MB > L2, so no L2 flush is needed) = "
+                               f"{FRAMES_PER_STEP} frames, {pairs_step} IQ pairs",
                    "frames_per_step": frames_done / args.steps, "autocorr_captures_per_step": caps_done / args.steps,
                    "frames_per_s": world * frames_done / (ms_total * 1e-3), "parallelism": f"replicas x{world}" if world > 1 else "single stream",
-                   "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_per_step_unthrottled": host_enqueue_free_ms,
+                   "host_enqueue_ms_per_batch": host_enqueue_ms, "numa": {"device_node": numa_node, "rank_bound_to_node": numa_bound},
                    "flags": "AUTOSHIFT=1, LOW_PASS_BEFORE_SYNC=1, AUTOGAIN_AFTER=0, motionblur 0 (GUI defaults), PLL write-back off"},
         "gpu_launches": int(launches),
-        "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "frames_delivered": int(e2e_frames), "pcie_link_measured": link,
-                # bytes per sample over the link: 8 in + 4*pixels-per-sample out; bound by each direction alone and by both together
-                "link_bound_MS_per_s": min(link["h2d_gbs"] / 8.0, link["d2h_gbs"] / (4.0 * step.n * FRAMES_PER_STEP / pairs),
-                                           link["duplex_gbs"] / (8.0 + 4.0 * step.n * FRAMES_PER_STEP / pairs)) * 1e3,
-                "how": "tsdrgpu_pipeline_process() on pinned host IQ in 16 MiB calls, "
-                "frames copied back to pinned host slots; host wall clock between device synchronisations"},
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
     }
+    if acs:
+        line["autocorr_sweep"] = acs
     if superb:
         line["superbandwidth"] = superb
     if e2e_int8:
         line["e2e_int8_transport"] = e2e_int8
-    if variants:
-        line["variants"] = variants
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+FFT_FUSED_FINISH = False          # flips when k_real_*_finish move into the pass epilogues (then 40 N per capture instead of 52 N)
+
+
+def FFT_BYTES_PER_CAPTURE(n, passes=2):
+    """bytes the FFT PASS kernels of one half-size autocorrelation move: `passes` global passes per N/2-point transform, each
+    reading and writing N/2 complex points (8 N bytes per pass); with the finish steps fused into the passes the forward's last
+    pass writes N reals (4 N), the inverse's first reads them and its last writes N complex (8 N): 40 N at 2 passes."""
+    if FFT_FUSED_FINISH:
+        return (2 * passes - 2) * 8 * n + (4 + 4) * n + (4 + 4) * n + (4 + 8) * n - 8 * n if passes == 2 else (2 * passes) * 8 * n + 8 * n
+    return 2 * passes * 8 * n
+
+
+def FINISH_BYTES(n):
+    return {"k_real_fwd_finish": 8 * n, "k_real_inv_finish": 12 * n}
+
+
+def autocorr_sweep(gpu, torch):
+    """BASELINE configs[2]: autocorrelation (fft.c:49-64) of windows of 2^16 .. 2^24 real samples on one B200.  Per size: the device
+    time of one autocorrelation (CUDA events around `reps` back-to-back calls on inputs that together exceed L2 at the small
+    sizes), GB/s against the bytes the passes actually move and against SURVEY 8d's 28*N single-pass ideal."""
+    peak = None
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+    peak = peak or 6650.0
+    out = {}
+    lib = gpu._lib
+    for logn in range(16, 25):
+        n = 1 << logn
+        batch = max(1, min(64, (1 << 26) // n))           # >= 256 MB of answers per launch at every size: larger than L2
+        x = torch.rand(batch * n, device="cuda") + 0.25
+        ans = torch.empty(batch * 2 * n, device="cuda")
+        run = lambda: gpu.chk(lib.tsdrgpu_autocorrelation_batch(gpu._h, gpu.stream, ans.data_ptr(), x.data_ptr(), n, batch, n))
+        for _ in range(3):
+            run()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(reps):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps / batch
+        passes = 1 if logn - 1 <= 11 else (2 if logn - 1 <= 20 else 3)     # global passes per half-size transform (fft_run's factorisation)
+        moved = FFT_BYTES_PER_CAPTURE(n, passes) + (0 if FFT_FUSED_FINISH else sum(FINISH_BYTES(n).values()))
+        out[f"2^{logn}"] = {"us_per_autocorrelation": ms * 1e3, "batch": batch, "passes_per_transform": passes,
+                            "gbs_vs_bytes_moved": moved / (ms * 1e-3) / 1e9, "frac_vs_bytes_moved": moved / (ms * 1e-3) / 1e9 / peak,
+                            "gbs_vs_28N": 28 * n / (ms * 1e-3) / 1e9, "frac_vs_28N": 28 * n / (ms * 1e-3) / 1e9 / peak}
+        del x, ans
+    return out
+
+
+def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
+    from tempestsdr_b200 import superband
+    hop_pairs = 10 * int(FS / FV)                        # SUPER_SAMPLES_TO_RECORD frames per hop -> N = 2^21
+    hop = iq_dev[: 2 * hop_pairs].contiguous()
+    for _ in range(2):
+        superband.stitch_distributed(gpu, hop, int(FS / FV))
+    barrier()
+    s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    s0e.record()
+    for _ in range(reps):
+        res, lags, n_fft = superband.stitch_distributed(gpu, hop, int(FS / FV))
+    s1e.record()
+    barrier()
+    tms = torch.tensor([s0e.elapsed_time(s1e) / reps], device="cuda")
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    return {"hops": world, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": world * n_fft / (tms.item() * 1e-3) / 1e6,
+            "allgather_bytes_per_rank": 8 * (n_fft + n_fft // 2), "collective": "one NCCL all_gather_into_tensor per stitch"}
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
@@ -576,7 +696,7 @@ def run_reference(args):
                                 "--steps", str(args.steps), "--warmup", str(args.warmup)], capture_output=True, text=True,
                                env=dict(os.environ, BENCH_REF_IQ_FILE=tmp.name))
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            if r.returncode == 0 and lines:
+            if lines:                                   # the measurement was printed; how the reference's shutdown went afterwards does not matter
                 child = json.loads(lines[-1]); child["attempts"] = attempt + 1
                 break
             sys.stderr.write(f"[bench] reference pipeline attempt {attempt + 1} ended with rc={r.returncode} (the unmodified library crashed); retrying\n")
@@ -592,6 +712,7 @@ def run_reference(args):
                "e2e": {"value": cpu["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     fps, caps, seconds, per_frame = child["fps"], child["caps"], child["seconds"], child["per_frame"]
+    native_maps = child.get("native_libraries_mapped")
     value = fps * per_frame / 1e6
     cpu = {"value": value, "unit": "MS/s", "cores": min(ncores, 6), "kind": "reference",
            "sample": f"the reference's own threaded pipeline (plugin + decimate + post-process + video + autocorr threads) for "
@@ -602,7 +723,8 @@ def run_reference(args):
                       "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "f32", "data": "synthetic", "cpu_baseline": cpu,
                       "config": {"workload": "BASELINE configs[1]: 1080p60 geometry (1125 lines), 25 MS/s float32 IQ from a file through "
-                                             "TSDRPlugin_RawFile (pacing off) and the unmodified reference library", "frames_per_s": fps},
+                                             "TSDRPlugin_RawFile (pacing off) and the unmodified reference library", "frames_per_s": fps,
+                                 "native_libraries_mapped_by_the_measuring_process": native_maps},
                       "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -646,9 +768,21 @@ def run_reference_child(args):
             results.append(((count["frames"] - f0) / dt, (count["plots"] - p0) / 2 / dt))
     fps = statistics.mean(r[0] for r in results)
     caps = statistics.mean(r[1] for r in results)
-    emit({"fps": fps, "caps": caps, "seconds": seconds, "per_frame": per_frame})
+    try:                                             # which native libraries this child had mapped (the reference's, none of this repo's)
+        maps = sorted({l.split()[-1] for l in open("/proc/self/maps") if l.rstrip().endswith(".so") and ("/oracle/" in l or "tempestsdr_b200" in l)})
+    except Exception:
+        maps = []
+    emit({"fps": fps, "caps": caps, "seconds": seconds, "per_frame": per_frame, "native_libraries_mapped": maps})
     sys.stdout.flush(); sys.stderr.flush()
-    os._exit(0)      # the measurement is over: leave without tsdr_stop / interpreter teardown (the reference's shutdown path races too)
+    # End the run the way a host would: tsdr_stop from this thread, then a normal interpreter exit so that exit hooks (the
+    # driver's library recorder among them) run.  The reference's shutdown path races now and then: a watchdog
+    # ends the process if it hangs -- the measurement is already on stdout by then.
+    wd = threading.Timer(10.0, lambda: os._exit(0)); wd.daemon = True; wd.start()
+    try:
+        lib.tsdr_stop(t)
+        th.join(timeout=8)
+    except Exception:
+        pass
 
 
 _RESULT_OUT = None

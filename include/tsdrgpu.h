@@ -63,10 +63,15 @@ TSDRGPU_API int tsdrgpu_free(tsdrgpu_ctx_t *ctx, void *d_ptr);
 TSDRGPU_API int tsdrgpu_ipc_export(tsdrgpu_ctx_t *ctx, void *d_ptr, uint8_t handle[64]);
 TSDRGPU_API int tsdrgpu_ipc_import(tsdrgpu_ctx_t *ctx, const uint8_t handle[64], void **d_ptr);
 TSDRGPU_API int tsdrgpu_ipc_release(tsdrgpu_ctx_t *ctx, void *d_ptr);
-TSDRGPU_API int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr);   /* pinned */
+TSDRGPU_API int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr);   /* pinned, on the device's NUMA node when known */
+/* NUMA node the device hangs off (sysfs), -1 when unknown; pin the calling thread to that node's cores (0 = done).
+ * TSDRGPU_NO_NUMA=1 switches both off. */
+TSDRGPU_API int tsdrgpu_device_numa_node(tsdrgpu_ctx_t *ctx);
+TSDRGPU_API int tsdrgpu_bind_thread_near_device(tsdrgpu_ctx_t *ctx);
 TSDRGPU_API int tsdrgpu_free_host(tsdrgpu_ctx_t *ctx, void *h_ptr);
 TSDRGPU_API int tsdrgpu_memcpy_h2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *h_src, size_t bytes);
 TSDRGPU_API int tsdrgpu_memcpy_d2h(tsdrgpu_ctx_t *ctx, void *stream, void *h_dst, const void *d_src, size_t bytes);
+TSDRGPU_API int tsdrgpu_memcpy_d2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *d_src, size_t bytes);
 TSDRGPU_API int tsdrgpu_memset(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, int value, size_t bytes);
 TSDRGPU_API int tsdrgpu_stream_create(tsdrgpu_ctx_t *ctx, void **stream);
 TSDRGPU_API int tsdrgpu_stream_destroy(tsdrgpu_ctx_t *ctx, void *stream);
@@ -97,6 +102,9 @@ TSDRGPU_API void tsdrgpu_fft_reference_eps(int stages, int inverse, double *eps)
  * Main.java:1233-1253,1301-1303,1346-1350): first strict maximum of each plot -> fps, height.  Optional outputs may be NULL. */
 TSDRGPU_API int tsdrgpu_detect_videomode(const double *frame_plot, int frame_offset, int frame_len, const double *line_plot, int line_offset,
                                          int line_len, uint32_t samplerate, double *fps, int *height, int *frame_index, int *line_index);
+/* frameratepll's write-back (syncdetector.c:141-152) for one frame, from the frame stage's per-frame result: returns 1 and
+ * moves *refreshrate when the reference would (PLL on is the caller's condition; x_vx != 0 is checked here), else 0. */
+TSDRGPU_API int tsdrgpu_pll_step(double *refreshrate, int32_t x_vx, int32_t pll_state, double avg_speed);
 /* the normalised 5-tap Gaussian of gaussian.c:16-30 */
 TSDRGPU_API void tsdrgpu_gauss_taps(float taps[5]);
 
@@ -313,6 +321,7 @@ typedef struct {
 	uint64_t samples_in, samples_dropped_upstream, samples_resampled;
 	uint64_t frames_processed, frames_delivered, frames_dropped, captures, plots_delivered;
 	uint64_t h2d_bytes, d2h_bytes, gpu_launches, stitches;
+	uint64_t host_buffers_registered;   /* plugin buffers page-locked in place (cudaHostRegister) after they kept coming back */
 } tsdrgpu_pipeline_stats_t;
 
 typedef void (*tsdrgpu_frame_cb)(float *buf, int width, int height, void *user);                  /* tsdr_readasync_function */

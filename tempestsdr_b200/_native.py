@@ -32,7 +32,7 @@ class PipelineStats(C.Structure):
     """tsdrgpu_pipeline_stats_t"""
     _fields_ = [(n, C.c_uint64) for n in ("samples_in", "samples_dropped_upstream", "samples_resampled", "frames_processed",
                                           "frames_delivered", "frames_dropped", "captures", "plots_delivered",
-                                          "h2d_bytes", "d2h_bytes", "gpu_launches", "stitches")]
+                                          "h2d_bytes", "d2h_bytes", "gpu_launches", "stitches", "host_buffers_registered")]
 
 
 FRAME_CB = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_void_p)
@@ -57,6 +57,9 @@ _SIGS = {
     "tsdrgpu_free_host": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tsdrgpu_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tsdrgpu_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tsdrgpu_device_numa_node": (C.c_int, [C.c_void_p]),
+    "tsdrgpu_bind_thread_near_device": (C.c_int, [C.c_void_p]),
     "tsdrgpu_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "tsdrgpu_stream_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_stream_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -65,6 +68,7 @@ _SIGS = {
     "tsdrgpu_plan_resample": (C.c_uint64, [C.POINTER(C.c_double), C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_void_p]),
     "tsdrgpu_fft_reference_eps": (None, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "tsdrgpu_gauss_taps": (None, [C.POINTER(C.c_float * 5)]),
+    "tsdrgpu_pll_step": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_double]),
     "tsdrgpu_am_demod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tsdrgpu_resampler_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_resampler_destroy": (None, [C.c_void_p]),

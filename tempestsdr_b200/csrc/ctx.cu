@@ -1,6 +1,11 @@
 // ctx.cu -- context, memory and stream plumbing of libtsdrgpu (include/tsdrgpu.h, "context" section).
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <ctype.h>
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 thread_local char g_tsdrgpu_err[512] = "";
 
@@ -64,10 +69,72 @@ int tsdrgpu_malloc(tsdrgpu_ctx_t *ctx, size_t bytes, void **d_ptr) {
 	return TSDRGPU_OK;
 }
 int tsdrgpu_free(tsdrgpu_ctx_t *ctx, void *d_ptr) { BIND(ctx); CU_TRY(ctx, cudaFree(d_ptr)); return TSDRGPU_OK; }
+// ---- host memory near the GPU -------------------------------------------------------------------------------------------
+// On a two-socket box half of the GPUs hang off each socket; page-locked buffers on the far socket cross the inter-socket link
+// on every DMA (round 1: 8 streams reached 64 % of 8x one stream).  The NUMA node of the device comes from sysfs; allocations
+// are steered with set_mempolicy(MPOL_PREFERRED) around cudaMallocHost (the driver faults the pages in inside that call),
+// raw syscalls because libnuma is not a dependency.  Everything degrades to a no-op when sysfs or the syscall says no.
+int tsdrgpu_device_numa_node(tsdrgpu_ctx_t *ctx) {
+	if (!ctx) return -1;
+	char bus[32] = {0}, path[128];
+	if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) != cudaSuccess) { cudaGetLastError(); return -1; }
+	for (char *c = bus; *c; c++) *c = (char) tolower(*c);
+	snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+	FILE *f = fopen(path, "r");
+	if (!f) return -1;
+	int node = -1;
+	if (fscanf(f, "%d", &node) != 1) node = -1;
+	fclose(f);
+	return node;
+}
+static long mempolicy_prefer(int node, int *old_mode, unsigned long *old_mask) {
+#if defined(SYS_set_mempolicy) && defined(SYS_get_mempolicy)
+	if (node < 0 || node >= 64) return -1;
+	if (syscall(SYS_get_mempolicy, old_mode, old_mask, 64ul, NULL, 0ul) != 0) return -1;
+	unsigned long mask = 1ul << node;
+	return syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 64ul);
+#else
+	(void) node; (void) old_mode; (void) old_mask; return -1;
+#endif
+}
+static void mempolicy_restore(int old_mode, unsigned long old_mask) {
+#if defined(SYS_set_mempolicy)
+	syscall(SYS_set_mempolicy, old_mode, old_mode == 0 ? NULL : &old_mask, old_mode == 0 ? 0ul : 64ul);
+#endif
+}
 int tsdrgpu_malloc_host(tsdrgpu_ctx_t *ctx, size_t bytes, void **h_ptr) {
 	BIND(ctx); ARG_TRY(ctx, h_ptr != NULL);
-	CU_TRY(ctx, cudaMallocHost(h_ptr, bytes ? bytes : 1));
+	int old_mode = 0; unsigned long old_mask = 0;
+	const bool steer = !getenv("TSDRGPU_NO_NUMA") && mempolicy_prefer(tsdrgpu_device_numa_node(ctx), &old_mode, &old_mask) == 0;
+	const cudaError_t e = cudaMallocHost(h_ptr, bytes ? bytes : 1);
+	if (steer) mempolicy_restore(old_mode, old_mask);
+	CU_TRY(ctx, e);
 	return TSDRGPU_OK;
+}
+// pin the CALLING thread to the cores of the device's NUMA node (what a per-GPU worker process or thread wants); 0 = done
+int tsdrgpu_bind_thread_near_device(tsdrgpu_ctx_t *ctx) {
+	if (getenv("TSDRGPU_NO_NUMA")) return TSDRGPU_EINVAL;
+	const int node = tsdrgpu_device_numa_node(ctx);
+	if (node < 0) return TSDRGPU_EINVAL;
+	char path[128], list[4096] = {0};
+	snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+	FILE *f = fopen(path, "r");
+	if (!f) return TSDRGPU_EINVAL;
+	if (!fgets(list, sizeof list, f)) { fclose(f); return TSDRGPU_EINVAL; }
+	fclose(f);
+	cpu_set_t allowed, want;
+	CPU_ZERO(&want);
+	if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return TSDRGPU_EINVAL;
+	int any = 0;
+	for (char *tok = strtok(list, ",\n"); tok; tok = strtok(NULL, ",\n")) {
+		int a = 0, b = 0;
+		const int k = sscanf(tok, "%d-%d", &a, &b);
+		if (k < 1) continue;
+		if (k == 1) b = a;
+		for (int c = a; c <= b && c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); any = 1; }
+	}
+	if (!any) return TSDRGPU_EINVAL;                   // a cgroup / taskset already excludes that node: leave things alone
+	return sched_setaffinity(0, sizeof want, &want) == 0 ? TSDRGPU_OK : TSDRGPU_EINVAL;
 }
 int tsdrgpu_free_host(tsdrgpu_ctx_t *ctx, void *h_ptr) { BIND(ctx); CU_TRY(ctx, cudaFreeHost(h_ptr)); return TSDRGPU_OK; }
 // ---- peer access between the processes of one node (one process per GPU): CUDA IPC handles of tsdrgpu_malloc'd buffers
@@ -100,6 +167,11 @@ int tsdrgpu_memcpy_h2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void
 int tsdrgpu_memcpy_d2h(tsdrgpu_ctx_t *ctx, void *stream, void *h_dst, const void *d_src, size_t bytes) {
 	BIND(ctx);
 	CU_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_memcpy_d2d(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, const void *d_src, size_t bytes) {
+	BIND(ctx);
+	if (bytes) CU_TRY(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
 	return TSDRGPU_OK;
 }
 int tsdrgpu_memset(tsdrgpu_ctx_t *ctx, void *stream, void *d_dst, int value, size_t bytes) {
@@ -174,7 +246,7 @@ int tsdrgpu_pinned(tsdrgpu_ctx_t *ctx, size_t bytes, void **out) {
 	if (ctx->pinned_bytes < bytes) {
 		if (ctx->pinned) { CU_TRY(ctx, cudaDeviceSynchronize()); CU_TRY(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = NULL; ctx->pinned_bytes = 0; }
 		size_t want = bytes * 2 + 4096;
-		CU_TRY(ctx, cudaMallocHost(&ctx->pinned, want));
+		{ int rc_ = tsdrgpu_malloc_host(ctx, want, &ctx->pinned); if (rc_) return rc_; }
 		ctx->pinned_bytes = want;
 	}
 	*out = ctx->pinned;

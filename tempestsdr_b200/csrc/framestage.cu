@@ -1087,10 +1087,12 @@ int tsdrgpu_framestage_set_overlap(tsdrgpu_framestage_t *fs, int on) {
 int tsdrgpu_framestage_join(tsdrgpu_framestage_t *fs, void *stream) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, fs != NULL);
 	BIND(fs->ctx);
+	// side_pending stays set once the side stream has been used: every consumer stream that joins (the pipeline's output
+	// stream after each batch, the caller's main stream when it leaves the overlapped order) must get its own wait, and a
+	// wait on an event that completed long ago costs nothing on the device
 	if (fs->side_pending) {
 		CU_TRY(fs->ctx, cudaStreamWaitEvent((cudaStream_t) stream, fs->ev_done[0], 0));
 		CU_TRY(fs->ctx, cudaStreamWaitEvent((cudaStream_t) stream, fs->ev_done[1], 0));
-		fs->side_pending = 0;
 	}
 	return TSDRGPU_OK;
 }

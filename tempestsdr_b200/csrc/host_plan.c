@@ -35,6 +35,15 @@ void tsdrgpu_geometry(uint32_t samplerate, int height, double refreshrate, int *
 	*pixeltimeoversampletime = (samplerate != 0 && pr != 0) ? ((double) samplerate) / pr : 0.0;
 }
 
+/* frameratepll's write-back (syncdetector.c:141-152): `refreshrate -= vx * 1e-5` while unlocked, `avg_speed * 1e-6` once
+ * locked, only when the frame moved (vx != 0).  The averages themselves come from the frame stage (fs_sync). */
+int tsdrgpu_pll_step(double *refreshrate, int32_t x_vx, int32_t pll_state, double avg_speed) {
+	if (x_vx == 0) return 0;
+	const double diff = (pll_state == 0) ? x_vx * 0.00001 : avg_speed * 0.000001;
+	*refreshrate -= diff;
+	return 1;
+}
+
 void tsdrgpu_gauss_taps(float taps[5]) {
 	/* CALC_GAUSSCOEFF(N,i) = expf(-2.0f*ALPHA*ALPHA*i*i/(N*N)) with textual i in {-2,-1,0,1,2}, N = 5 */
 	const float e2 = expf(-2.0f * 1.0f * 1.0f * -2 * -2 / (5 * 5));

@@ -38,6 +38,7 @@ struct FrameJob {
 	uint32_t samplerate;      // plots
 	int foff, flen, loff, llen; uint64_t calls; int reset_announce;
 	int snr_valid;            // frames: results carry an SNR to announce
+	int pll_valid;            // frames: h_pll_rr holds the refresh rates the PLL set
 };
 
 // block-aligned dropping, dsp.c:313-368 (integer bookkeeping, host side)
@@ -78,7 +79,10 @@ __device__ __forceinline__ float raw_to_float(int v, int fmt) {
 __global__ void __launch_bounds__(256) pl_convert(const void *__restrict__ raw, float *__restrict__ dst, size_t items, int fmt) {
 	const size_t stride = (size_t) gridDim.x * blockDim.x, t0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (fmt == TSDRGPU_FMT_INT8 || fmt == TSDRGPU_FMT_UINT8) {
-		const size_t n4 = items >> 2;
+		// 4 samples per thread only where both sides allow it (the superbandwidth gather appends at odd pair counts: dst is then
+		// only 8-byte aligned); otherwise everything goes through the scalar tail loop
+		const bool vec = ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) && ((reinterpret_cast<unsigned long long>(raw) & 3ull) == 0);
+		const size_t n4 = vec ? (items >> 2) : 0;
 		for (size_t i = t0; i < n4; i += stride) {           // 4 samples per thread
 			const uchar4 q = __ldg(reinterpret_cast<const uchar4 *>(raw) + i);
 			float4 o;
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) pl_convert(const void *__restrict__ raw, 
 		}
 		return;
 	}
-	for (size_t i = t0; i < items; i += stride) {
+	for (size_t i = t0; i < items; i += stride) {                 // 16-bit formats: scalar (2-byte alignment is the format's own)
 		const unsigned short u = __ldg(reinterpret_cast<const unsigned short *>(raw) + i);
 		dst[i] = raw_to_float(fmt == TSDRGPU_FMT_INT16 ? (int) (short) u : (int) u, fmt);
 	}
@@ -121,9 +125,16 @@ struct tsdrgpu_pipeline {
 	// stage 0: H2D staging of the plugin's buffer
 	float *d_stage[4]; size_t stage_cap[4];           // floats; 4 slots so H2D runs ahead of the kernels
 	void *d_raw[4]; size_t raw_cap[4];                // bytes; raw-format blocks land here and are converted into d_stage
-	std::vector<void *> registered;
+	// plugin buffers seen on process(): page-locked in place (cudaHostRegister) once the same buffer keeps coming back, so that
+	// an unmodified plugin's malloc'd block crosses PCIe by direct DMA instead of through the driver's staging copy
+	struct HostBuf { const void *base; size_t bytes; int seen; int state; };      // state: 0 candidate, 1 registered here, 2 pinned by its owner, 3 refused
+	std::vector<HostBuf> hostbufs; int host_register;
 	// stage 1: decimator input (IQ pairs waiting for whole blocks)
-	float *d_decim; size_t decim_cap, decim_fill;     // pairs
+	// samples waiting for whole decimator blocks: [decim_read, decim_read + decim_fill) samples of decim_elem floats each
+	// (2 = interleaved I,Q, demodulated inside rs_main; 1 = magnitudes, what the multi-GPU superbandwidth stitch delivers).
+	// Consumed from the front by moving decim_read; compacted only when the hole in front is at least as large as what is
+	// left, so source and destination of the move never overlap.
+	float *d_decim; size_t decim_cap /* floats */, decim_fill, decim_read; int decim_elem;
 	DropComp dev_drop;
 	// stage 2: pixels waiting for whole frames
 	tsdrgpu_resampler *rs;
@@ -133,6 +144,8 @@ struct tsdrgpu_pipeline {
 	tsdrgpu_framestage *fs;
 	float *d_frames[2]; size_t frames_cap[2];          // double-buffered: D2H of batch k overlaps the kernels of batch k+1
 	float *h_frames[PL_SLOTS]; tsdrgpu_frame_result_t *h_results[PL_SLOTS]; int32_t *h_report[PL_SLOTS]; size_t slot_cap;
+	double *h_pll_rr[PL_SLOTS];                        // refresh rate after frame f when the PLL moved it there (NaN: it did not)
+	cudaEvent_t ev_res;                                // the batch's sync results have reached the host (PLL write-back needs them)
 	int slot_busy[PL_SLOTS];
 	// autocorrelation side path
 	tsdrgpu_frd *frd; float *d_capture[2]; size_t cap_size[2], cap_fill; int cap_phase; uint32_t cap_rate;
@@ -162,6 +175,7 @@ static void geometry_locked(tsdrgpu_pipeline *p) {      // set_internal_samplera
 static void *delivery_main(void *arg) {
 	tsdrgpu_pipeline *p = (tsdrgpu_pipeline *) arg;
 	cudaSetDevice(p->ctx->device);
+	tsdrgpu_bind_thread_near_device(p->ctx);          // the frames it hands out live in page-locked memory on the device's node
 	for (;;) {
 		pthread_mutex_lock(&p->mu);
 		while (p->jobs.empty() && !p->stop) pthread_cond_wait(&p->cv_job, &p->mu);
@@ -173,16 +187,9 @@ static void *delivery_main(void *arg) {
 			const size_t n = (size_t) j.w * j.h;
 			for (int f = 0; f < j.nframes; f++) {
 				const tsdrgpu_frame_result_t &r = p->h_results[j.slot][f];
-				// frameratepll's write-back (syncdetector.c:141-152): refreshrate moves, geometry follows
-				if (p->params[TSDRGPU_PARAM_INT_FRAMERATE_PLL] && r.x_vx != 0) {
-					const double diff = (r.pll_state == 0) ? r.x_vx * 0.00001 : r.avg_speed * 0.000001;
-					pthread_mutex_lock(&p->geo_mu);
-					p->refreshrate -= diff;
-					geometry_locked(p);
-					const double rr = p->refreshrate;
-					pthread_mutex_unlock(&p->geo_mu);
-					if (p->value_cb) p->value_cb(0 /* VALUE_ID_PLL_FRAMERATE */, rr, 0, p->user);
-				}
+				// frameratepll's announce (syncdetector.c:151): the write-back itself happened in drain_frames, in stream order
+				if (j.pll_valid && p->h_pll_rr[j.slot][f] == p->h_pll_rr[j.slot][f] && p->value_cb)
+					p->value_cb(0 /* VALUE_ID_PLL_FRAMERATE */, p->h_pll_rr[j.slot][f], 0, p->user);
 				if (p->h_report[j.slot][f] && p->value_cb) p->value_cb(3 /* VALUE_ID_AUTOGAIN_VALUES */, r.lastmin, r.lastmax, p->user);
 				if (p->h_report[j.slot][f] && p->value_cb && j.snr_valid) p->value_cb(4 /* VALUE_ID_SNR: the announce dsp.c:234 leaves commented out */, r.snr, 0, p->user);
 				if (p->frame_cb) p->frame_cb(p->h_frames[j.slot] + f * n, j.w, j.h, p->user);
@@ -238,6 +245,69 @@ static int grow(tsdrgpu_ctx_t *ctx, cudaStream_t s, float **buf, size_t *cap, si
 	return TSDRGPU_OK;
 }
 
+// room for `more` samples behind the ones waiting in the decimator input (contents kept); returns where they go
+static int decim_reserve(tsdrgpu_pipeline *p, size_t more, float **where) {
+	const size_t E = (size_t) p->decim_elem, used = E * (p->decim_read + p->decim_fill);
+	int rc = grow(p->ctx, p->s_main, &p->d_decim, &p->decim_cap, used + E * more, used);
+	if (rc) return rc;
+	*where = p->d_decim + used;
+	return TSDRGPU_OK;
+}
+// the decimator input switches between I,Q pairs and magnitudes: what is still waiting is converted (rare: at most a few
+// blocks, when superbandwidth mode with one hop per GPU starts or ends)
+static int decim_set_elem(tsdrgpu_pipeline *p, int elem) {
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	if (p->decim_elem == elem) return TSDRGPU_OK;
+	CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest));
+	const size_t n = p->decim_fill;
+	int rc;
+	if (n) {
+		void *tmp;
+		float *src = p->d_decim + (size_t) p->decim_elem * p->decim_read;
+		if ((rc = tsdrgpu_scratch(ctx, 3, sizeof(float) * 2 * n, &tmp))) return rc;
+		if (elem == 1) {                                  // pairs -> magnitudes (am_demod, TSDRLibrary.c:244-262)
+			if ((rc = tsdrgpu_am_demod(ctx, p->s_main, src, n, (float *) tmp))) return rc;
+			CU_TRY(ctx, cudaMemcpyAsync(p->d_decim, tmp, sizeof(float) * n, cudaMemcpyDeviceToDevice, p->s_main));
+		} else {                                          // magnitudes -> pairs (m, 0): |(m, 0)| == m
+			CU_TRY(ctx, cudaMemsetAsync(tmp, 0, sizeof(float) * 2 * n, p->s_main));
+			CU_TRY(ctx, cudaMemcpy2DAsync(tmp, 2 * sizeof(float), src, sizeof(float), sizeof(float), n, cudaMemcpyDeviceToDevice, p->s_main));
+			if ((rc = grow(ctx, p->s_main, &p->d_decim, &p->decim_cap, 2 * n, 0))) return rc;
+			CU_TRY(ctx, cudaMemcpyAsync(p->d_decim, tmp, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, p->s_main));
+		}
+		CU_TRY(ctx, cudaEventRecord(p->ev_decim, p->s_main));
+	}
+	p->decim_read = 0; p->decim_elem = elem;
+	return TSDRGPU_OK;
+}
+
+// A plugin hands over the same malloc'd buffer call after call (TSDRPlugin_RawFile.c:212, Mirics, SDRplay).  From pageable memory
+// cudaMemcpyAsync goes through the driver's staging buffer at a fraction of the link rate; once a buffer has come back
+// REG_AFTER times it is page-locked in place.  Buffers are released again when the run ends (tsdrgpu_pipeline_destroy).
+// TSDR_NO_HOST_REGISTER=1 switches this off (a plugin that unmaps and remaps its buffer at the same address in mid-run would
+// otherwise be read through the stale mapping).
+static const void *host_source(tsdrgpu_pipeline *p, const void *h, size_t bytes) {
+	constexpr int REG_AFTER = 3;
+	if (!p->host_register || bytes < 65536 || h == NULL) return h;
+	for (auto &b : p->hostbufs) {
+		if (b.base != h) continue;
+		if (b.state == 1 && bytes > b.bytes) { cudaHostUnregister(const_cast<void *>(b.base)); cudaGetLastError(); b.state = 0; b.seen = REG_AFTER - 1; }
+		if (b.state != 0) return h;
+		if (++b.seen < REG_AFTER) return h;
+		cudaPointerAttributes a;
+		if (cudaPointerGetAttributes(&a, h) == cudaSuccess && a.type != cudaMemoryTypeUnregistered) { b.state = 2; return h; }
+		cudaGetLastError();
+		if (cudaHostRegister(const_cast<void *>(h), bytes, cudaHostRegisterDefault) == cudaSuccess) { b.state = 1; b.bytes = bytes; p->stats.host_buffers_registered++; }
+		else { cudaGetLastError(); b.state = 3; }
+		return h;
+	}
+	if (p->hostbufs.size() >= 8) {
+		if (p->hostbufs.front().state == 1) { cudaHostUnregister(const_cast<void *>(p->hostbufs.front().base)); cudaGetLastError(); }
+		p->hostbufs.erase(p->hostbufs.begin());
+	}
+	p->hostbufs.push_back({h, bytes, 1, 0});
+	return h;
+}
+
 // ---- autocorrelation side path: append demodulated samples, fire a capture when full (frameratedetector.c:128-230)
 static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, bool dropped) {
 	tsdrgpu_ctx_t *ctx = p->ctx;
@@ -286,8 +356,8 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 				pthread_mutex_unlock(&p->mu);
 				for (int s = 0; s < 2; s++) {
 					if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
-					CU_TRY(ctx, cudaMallocHost(&p->h_plot_frame[s], sizeof(double) * need));
-					CU_TRY(ctx, cudaMallocHost(&p->h_plot_line[s], sizeof(double) * need));
+					if ((rc = tsdrgpu_malloc_host(ctx, sizeof(double) * need, (void **) &p->h_plot_frame[s]))) return rc;
+					if ((rc = tsdrgpu_malloc_host(ctx, sizeof(double) * need, (void **) &p->h_plot_line[s]))) return rc;
 				}
 				p->plot_cap = need;
 			}
@@ -338,10 +408,11 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 			while (p->delivered < p->submitted) pthread_cond_wait(&p->cv_done, &p->mu);
 			pthread_mutex_unlock(&p->mu);
 			for (int s = 0; s < PL_SLOTS; s++) {
-				if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
-				CU_TRY(ctx, cudaMallocHost(&p->h_frames[s], sizeof(float) * n * nf));
-				CU_TRY(ctx, cudaMallocHost(&p->h_results[s], sizeof(tsdrgpu_frame_result_t) * nf));
-				CU_TRY(ctx, cudaMallocHost(&p->h_report[s], sizeof(int32_t) * nf));
+				if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); free(p->h_pll_rr[s]); }
+				p->h_pll_rr[s] = (double *) malloc(sizeof(double) * nf);
+				if ((rc = tsdrgpu_malloc_host(ctx, sizeof(float) * n * nf, (void **) &p->h_frames[s]))) return rc;
+				if ((rc = tsdrgpu_malloc_host(ctx, sizeof(tsdrgpu_frame_result_t) * nf, (void **) &p->h_results[s]))) return rc;
+				if ((rc = tsdrgpu_malloc_host(ctx, sizeof(int32_t) * nf, (void **) &p->h_report[s]))) return rc;
 			}
 			p->slot_cap = n * nf;
 		}
@@ -362,6 +433,8 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 		CU_TRY(ctx, cudaEventRecord(p->ev_main, p->s_main));
 		CU_TRY(ctx, cudaStreamWaitEvent(p->s_out, p->ev_main, 0));             // serial stage orders finish on the main stream
 		if ((rc = tsdrgpu_framestage_join(p->fs, p->s_out))) return rc;        // the overlapped order finishes on the side stream
+		const bool pll_on = p->params[TSDRGPU_PARAM_INT_FRAMERATE_PLL] != 0;
+		if (pll_on) CU_TRY(ctx, cudaEventRecord(p->ev_res, p->s_out));          // the batch's results are on the host behind this
 		if (p->argb_mode) {                                                    // float frames -> the host's int32 pixels, in place
 			if (p->argb_cap != n) {
 				if (p->d_argb_last) CU_TRY(ctx, cudaFree(p->d_argb_last));
@@ -377,7 +450,23 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 		p->pix_read += n * nf;
 		p->stats.frames_processed += nf;
 		FrameJob j; memset(&j, 0, sizeof j);
-		j.kind = 0; j.slot = slot; j.nframes = nf; j.w = w; j.h = h; j.snr_valid = want_snr;
+		j.kind = 0; j.slot = slot; j.nframes = nf; j.w = w; j.h = h; j.snr_valid = want_snr; j.pll_valid = pll_on;
+		if (pll_on) {
+			// frameratepll's write-back (syncdetector.c:141-152).  The reference does it from its post-processing thread while the
+			// decimating thread reads refreshrate unlocked; here it is applied in stream order: the results of this
+			// batch move the refresh rate before the decimator plans its next group of blocks, frame by frame in order.  The
+			// price is one host wait per batch, paid only while the PLL is switched on (the frames' D2H is already queued).
+			CU_TRY(ctx, cudaEventSynchronize(p->ev_res));
+			for (int f = 0; f < nf; f++) {
+				const tsdrgpu_frame_result_t &r = p->h_results[slot][f];
+				pthread_mutex_lock(&p->geo_mu);
+				double rr = p->refreshrate;
+				const int moved = tsdrgpu_pll_step(&rr, r.x_vx, r.pll_state, r.avg_speed);
+				if (moved) { p->refreshrate = rr; geometry_locked(p); }
+				pthread_mutex_unlock(&p->geo_mu);
+				p->h_pll_rr[slot][f] = moved ? rr : nan("");
+			}
+		}
 		if ((rc = submit(p, j, p->s_out))) return rc;
 	}
 	// compact the pixel buffer when the consumed prefix is large
@@ -396,28 +485,29 @@ static int drain_frames(tsdrgpu_pipeline *p, int w, int h) {
 static int drain_blocks(tsdrgpu_pipeline *p) {
 	tsdrgpu_ctx_t *ctx = p->ctx;
 	int rc;
-	pthread_mutex_lock(&p->geo_mu);
-	const int w = p->width, h = p->height; const double fv = p->refreshrate; const uint32_t fs_ = p->samplerate;
-	pthread_mutex_unlock(&p->geo_mu);
-	if (w <= 0 || h <= 0) return TSDRGPU_OK;
-	if (w != p->last_w || h != p->last_h) {            // postprocessingthread purges downstream on a size change
+	for (;;) {
+		// the live geometry, read again for every group of blocks: the PLL (drain_frames) or the host may have moved it
+		pthread_mutex_lock(&p->geo_mu);
+		const int w = p->width, h = p->height; const double fv = p->refreshrate; const uint32_t fs_ = p->samplerate;
+		pthread_mutex_unlock(&p->geo_mu);
+		if (w <= 0 || h <= 0) return TSDRGPU_OK;
 		p->last_w = w; p->last_h = h;
-	}
-	const uint32_t block = (uint32_t) (0.1 * fs_ / fv);                 // FRAMES_TO_POLL, TSDRLibrary.c:41,335
-	if (block == 0) return TSDRGPU_OK;
-	const uint32_t min_blocks = p->cfg.batch_blocks > 0 ? (uint32_t) p->cfg.batch_blocks : 10;
-	while (p->decim_fill / block >= min_blocks) {
+		const uint32_t block = (uint32_t) (0.1 * fs_ / fv);                 // FRAMES_TO_POLL, TSDRLibrary.c:41,335
+		if (block == 0) return TSDRGPU_OK;
+		const uint32_t min_blocks = p->cfg.batch_blocks > 0 ? (uint32_t) p->cfg.batch_blocks : 10;
+		if (p->decim_fill / block < min_blocks) return TSDRGPU_OK;
 		// whole multiples of the batch size, so the grouping (and with it every result) does not depend on how the
-		// plugin happened to cut the stream into process() calls
+		// plugin happened to cut the stream into process() calls; with the PLL on exactly one group at a time, because the
+		// frames it completes may move the refresh rate the next group is resampled with
 		uint32_t nb = (uint32_t) ((p->decim_fill / block / min_blocks) * min_blocks);
 		if (nb > 4000) nb = (4000 / min_blocks) * min_blocks;
-		if (nb == 0) nb = min_blocks;
+		if (nb == 0 || p->params[TSDRGPU_PARAM_INT_FRAMERATE_PLL]) nb = min_blocks;
 		const double up = (double) (w * h) * fv;        // width*height*refreshrate, TSDRLibrary.c:340
 		const uint64_t npix = tsdrgpu_resampler_plan(p->rs, NULL, block, nb, up, (double) fs_);
 		if (npix == 0) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "resampler plan produced no pixels", cudaSuccess, __FILE__, __LINE__);
 		if ((rc = grow(ctx, p->s_main, &p->d_pix, &p->pix_cap, p->pix_fill + npix + 64, p->pix_fill))) return rc;
 		uint64_t n_out = 0;
-		if ((rc = tsdrgpu_resampler_run(p->rs, p->s_main, p->d_decim, 1, NULL, block, nb, up, (double) fs_,
+		if ((rc = tsdrgpu_resampler_run(p->rs, p->s_main, p->d_decim + (size_t) p->decim_elem * p->decim_read, p->decim_elem == 2, NULL, block, nb, up, (double) fs_,
 		                                (int) p->params[TSDRGPU_PARAM_NEAREST_NEIGHBOUR_RESAMPLING], p->d_pix + p->pix_fill,
 		                                p->pix_cap - p->pix_fill, &n_out))) return rc;
 		// pixel-level alignment (dsp.c:326-346 on the pixel ring) and manual sync (TSDRLibrary.c:344-346)
@@ -434,15 +524,18 @@ static int drain_blocks(tsdrgpu_pipeline *p) {
 		p->pix_fill += fwd;
 		const int so = p->syncoffset; p->syncoffset = 0;
 		p->pix_drop.shift_with(totalpixels, -(int64_t) so);
-		// consume the blocks: move the tail to the front
-		const size_t used = (size_t) nb * block, left = p->decim_fill - used;
-		if (left) { pl_copy_f32<<<(unsigned) ((2 * left + 255) / 256 < 1024 ? (2 * left + 255) / 256 : 1024), 256, 0, p->s_main>>>(p->d_decim + 2 * used, p->d_decim, 2 * left); LAUNCH_CHECK(ctx); }
+		// consume the blocks; move what is left to the front once the hole there is big enough for a non-overlapping move
+		const size_t used = (size_t) nb * block, left = p->decim_fill - used, E = (size_t) p->decim_elem;
+		p->decim_read += used; p->decim_fill = left;
+		if (left == 0) p->decim_read = 0;
+		else if (p->decim_read >= left) {
+			pl_copy_f32<<<(unsigned) ((E * left + 255) / 256 < 1024 ? (E * left + 255) / 256 : 1024), 256, 0, p->s_main>>>(p->d_decim + E * p->decim_read, p->d_decim, E * left); LAUNCH_CHECK(ctx);
+			p->decim_read = 0;
+		}
 		CU_TRY(ctx, cudaEventRecord(p->ev_decim, p->s_main));                // later appends (ingest stream) must come after this
-		p->decim_fill = left;
 		p->stats.samples_resampled += used;
 		if ((rc = drain_frames(p, w, h))) return rc;
 	}
-	return TSDRGPU_OK;
 }
 
 extern "C" {
@@ -459,10 +552,12 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	pthread_mutex_init(&p->geo_mu, NULL); pthread_mutex_init(&p->mu, NULL);
 	pthread_cond_init(&p->cv_job, NULL); pthread_cond_init(&p->cv_done, NULL);
 	geometry_locked(p);
-	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->argb_mode = 0; p->argb_inverted = 0; p->report_snr = 0; p->detect_mode = 0; p->d_argb_last = NULL; p->argb_cap = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0;
+	for (int i = 0; i < 4; i++) { p->d_stage[i] = NULL; p->stage_cap[i] = 0; p->d_raw[i] = NULL; p->raw_cap[i] = 0; } p->argb_mode = 0; p->argb_inverted = 0; p->report_snr = 0; p->detect_mode = 0; p->d_argb_last = NULL; p->argb_cap = 0; p->stage_slot = 0; p->d_decim = NULL; p->decim_cap = 0; p->decim_fill = 0; p->decim_read = 0; p->decim_elem = 2;
 	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
 	p->slot_cap = 0; p->d_capture[0] = p->d_capture[1] = NULL; p->cap_size[0] = p->cap_size[1] = 0; p->cap_fill = 0; p->cap_phase = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
-	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->slot_busy[s] = 0; }
+	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->h_pll_rr[s] = NULL; p->slot_busy[s] = 0; }
+	p->host_register = getenv("TSDR_NO_HOST_REGISTER") ? 0 : 1;
+	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
 	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
 	p->stop = 0; p->submitted = 0; p->delivered = 0; p->last_w = 0; p->last_h = 0;
 	memset(&p->sb, 0, sizeof p->sb); p->samplerate_real = cfg->samplerate; p->retune_cb = NULL;
@@ -511,7 +606,7 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	pthread_join(p->thread, NULL);
 	cudaSetDevice(p->ctx->device);
 	tsdrgpu_resampler_destroy(p->rs); tsdrgpu_framestage_destroy(p->fs); tsdrgpu_frd_destroy(p->frd);
-	for (void *h : p->registered) cudaHostUnregister(h);
+	for (auto &b : p->hostbufs) if (b.state == 1) { cudaHostUnregister(const_cast<void *>(b.base)); cudaGetLastError(); }
 	for (int i = 0; i < 4; i++) if (p->sb.d_hops[i]) cudaFree(p->sb.d_hops[i]);
 	if (p->sb.d_out) cudaFree(p->sb.d_out);
 	cudaEventDestroy(p->sb.ev);
@@ -519,7 +614,8 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	for (float *d : dev) if (d) cudaFree(d);
 	for (int i = 0; i < 4; i++) if (p->d_raw[i]) cudaFree(p->d_raw[i]);
 	if (p->d_argb_last) cudaFree(p->d_argb_last);
-	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); }
+	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); free(p->h_pll_rr[s]); }
+	cudaEventDestroy(p->ev_res);
 	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
 	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
 	for (int i = 0; i < 2; i++) cudaEventDestroy(p->ev_out[i]);
@@ -657,8 +753,10 @@ static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t 
 	geometry_locked(p);
 	pthread_mutex_unlock(&p->geo_mu);
 	CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest));
-	if ((rc = grow(ctx, p->s_main, &p->d_decim, &p->decim_cap, 2 * (p->decim_fill + (size_t) total), 2 * p->decim_fill))) return rc;
-	pl_copy_f32<<<2048, 256, 0, p->s_main>>>(p->sb.d_out, p->d_decim + 2 * p->decim_fill, 2ull * (size_t) total);
+	float *where;
+	if ((rc = decim_set_elem(p, 2))) return rc;
+	if ((rc = decim_reserve(p, (size_t) total, &where))) return rc;
+	pl_copy_f32<<<2048, 256, 0, p->s_main>>>(p->sb.d_out, where, 2ull * (size_t) total);
 	LAUNCH_CHECK(ctx);
 	p->decim_fill += (size_t) total;
 	p->sb.state = SB_STARTING;
@@ -700,51 +798,69 @@ int tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_iq, int fm
 	p->dev_drop.shift_with((uint32_t) block, samples_dropped);
 	const bool drop_all = p->dev_drop.will_drop_all((uint32_t) size2);
 	const bool plots_on = !p->params[TSDRGPU_PARAM_AUTOCORR_PLOTS_OFF];
-	int rc;
+	int rc = TSDRGPU_OK;
 	const bool need_data = size2 > 0 && (!drop_all || (plots_on && samples_dropped != 0));
 	const int ss = p->stage_slot;
 	float *stage = NULL;
-	if (need_data) {
-		ARG_TRY(ctx, h_iq != NULL);
-		p->stage_slot = (p->stage_slot + 1) & 3;
-		if (p->stage_cap[ss] < items_count) { CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest)); CU_TRY(ctx, cudaStreamSynchronize(p->s_copy)); }
-		if ((rc = grow(ctx, p->s_main, &p->d_stage[ss], &p->stage_cap[ss], items_count, 0))) return rc;
-		stage = p->d_stage[ss];
-		// The plugin's buffer is only valid during this call: copy it on the copy stream into one of four staging slots
-		// (after the ingest kernels that read the slot four calls ago) and return once the host buffer has been read.
-		// The light per-block kernels (capture demod, append to the decimator input) run on their own stream, so the
-		// copy of block k+1..k+3 never waits behind the heavy resample / frame / FFT kernels of earlier blocks.
-		const size_t bytes = fmt_bytes(fmt) * items_count;
-		if (fmt != TSDRGPU_FMT_FLOAT && (rc = raw_reserve(p, ss, bytes))) return rc;
-		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->ev_used[ss], 0));
-		CU_TRY(ctx, cudaMemcpyAsync(fmt == TSDRGPU_FMT_FLOAT ? (void *) stage : p->d_raw[ss], h_iq, bytes, cudaMemcpyHostToDevice, p->s_copy));
-		CU_TRY(ctx, cudaEventRecord(p->ev_h2d[ss], p->s_copy));
-		CU_TRY(ctx, cudaStreamWaitEvent(p->s_ingest, p->ev_h2d[ss], 0));
-		if (fmt != TSDRGPU_FMT_FLOAT) {                                    // raw samples -> float IQ, on the device
-			const size_t want = (items_count / 4 + 255) / 256;
-			pl_convert<<<(unsigned) (want < 2048 ? (want ? want : 1) : 2048), 256, 0, p->s_ingest>>>(p->d_raw[ss], stage, items_count, fmt);
-			LAUNCH_CHECK(ctx);
+	bool copy_issued = false;
+	// Every path out of this block -- success or failure -- passes the synchronisation of the copy stream below: the header's
+	// contract is that the caller's buffer is read during the call only.
+	do {
+		if (need_data) {
+			if (h_iq == NULL) { rc = tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "invalid argument: h_iq != NULL", cudaSuccess, __FILE__, __LINE__); break; }
+			p->stage_slot = (p->stage_slot + 1) & 3;
+			if (p->stage_cap[ss] < items_count) { cudaStreamSynchronize(p->s_ingest); cudaStreamSynchronize(p->s_copy); }
+			if ((rc = grow(ctx, p->s_main, &p->d_stage[ss], &p->stage_cap[ss], items_count, 0))) break;
+			stage = p->d_stage[ss];
+			// The plugin's buffer is only valid during this call: copy it on the copy stream into one of four staging slots
+			// (after the ingest kernels that read the slot four calls ago) and return once the host buffer has been read.
+			// The light per-block kernels (capture demod, append to the decimator input) run on their own stream, so the
+			// copy of block k+1..k+3 never waits behind the heavy resample / frame / FFT kernels of earlier blocks.
+			const size_t bytes = fmt_bytes(fmt) * items_count;
+			if (fmt != TSDRGPU_FMT_FLOAT && (rc = raw_reserve(p, ss, bytes))) break;
+			const void *src = host_source(p, h_iq, bytes);
+			cudaError_t e = cudaStreamWaitEvent(p->s_copy, p->ev_used[ss], 0);
+			if (e == cudaSuccess) { e = cudaMemcpyAsync(fmt == TSDRGPU_FMT_FLOAT ? (void *) stage : p->d_raw[ss], src, bytes, cudaMemcpyHostToDevice, p->s_copy); copy_issued = true; }
+			if (e == cudaSuccess) e = cudaEventRecord(p->ev_h2d[ss], p->s_copy);
+			if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_ingest, p->ev_h2d[ss], 0);
+			if (e != cudaSuccess) { rc = tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "H2D of the plugin's block", e, __FILE__, __LINE__); break; }
+			if (fmt != TSDRGPU_FMT_FLOAT) {                                    // raw samples -> float IQ, on the device
+				const size_t want = (items_count / 4 + 255) / 256;
+				pl_convert<<<(unsigned) (want < 2048 ? (want ? want : 1) : 2048), 256, 0, p->s_ingest>>>(p->d_raw[ss], stage, items_count, fmt);
+				ctx->launches++;
+				if ((e = cudaGetLastError()) != cudaSuccess) { rc = tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "kernel launch", e, __FILE__, __LINE__); break; }
+			}
+			p->stats.h2d_bytes += bytes;
+			if ((rc = feed_capture(p, stage, size2, samples_dropped != 0))) break;
+		} else if (plots_on && samples_dropped != 0) p->cap_fill = 0;
+		uint32_t skip = 0;
+		const uint32_t fwd = p->dev_drop.add((uint32_t) size2, (uint32_t) block, true, &skip);
+		if (fwd) {
+			float *where;
+			if ((rc = decim_set_elem(p, 2))) break;
+			if (p->decim_cap < 2 * (p->decim_read + p->decim_fill + fwd)) cudaStreamSynchronize(p->s_ingest);
+			if ((rc = decim_reserve(p, fwd, &where))) break;
+			cudaError_t e = cudaStreamWaitEvent(p->s_ingest, p->ev_decim, 0);  // the last compaction of the decimator input is done
+			if (e == cudaSuccess) {
+				pl_copy_f32<<<(unsigned) ((2ull * fwd + 255) / 256 < 2048 ? (2ull * fwd + 255) / 256 : 2048), 256, 0, p->s_ingest>>>(stage + 2ull * skip, where, 2ull * fwd);
+				ctx->launches++;
+				e = cudaGetLastError();
+			}
+			if (e != cudaSuccess) { rc = tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "append to the decimator input", e, __FILE__, __LINE__); break; }
+			p->decim_fill += fwd;
 		}
-		p->stats.h2d_bytes += bytes;
-		if ((rc = feed_capture(p, stage, size2, samples_dropped != 0))) return rc;
-	} else if (plots_on && samples_dropped != 0) p->cap_fill = 0;
-	uint32_t skip = 0;
-	const uint32_t fwd = p->dev_drop.add((uint32_t) size2, (uint32_t) block, true, &skip);
-	if (fwd) {
-		if (p->decim_cap < 2 * (p->decim_fill + fwd)) { CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest)); }
-		if ((rc = grow(ctx, p->s_main, &p->d_decim, &p->decim_cap, 2 * (p->decim_fill + fwd), 2 * p->decim_fill))) return rc;
-		CU_TRY(ctx, cudaStreamWaitEvent(p->s_ingest, p->ev_decim, 0));       // the last compaction of the decimator input is done
-		pl_copy_f32<<<(unsigned) ((2ull * fwd + 255) / 256 < 2048 ? (2ull * fwd + 255) / 256 : 2048), 256, 0, p->s_ingest>>>(stage + 2ull * skip, p->d_decim + 2 * p->decim_fill, 2ull * fwd);
-		LAUNCH_CHECK(ctx);
-		p->decim_fill += fwd;
-	}
-	if (need_data) CU_TRY(ctx, cudaEventRecord(p->ev_used[ss], p->s_ingest));   // the slot may be overwritten after this point
-	CU_TRY(ctx, cudaEventRecord(p->ev_ingest, p->s_ingest));
-	CU_TRY(ctx, cudaStreamWaitEvent(p->s_main, p->ev_ingest, 0));          // the resampler may read what was appended
-	// Everything above and the launches below are only ENQUEUED (ordered on the device by events), so the host's launch
-	// work for the heavy kernels runs while this block's H2D copy is still in flight; the copy is waited for last.
-	rc = drain_blocks(p);
-	if (need_data) {
+		{
+			cudaError_t e = cudaSuccess;
+			if (need_data) e = cudaEventRecord(p->ev_used[ss], p->s_ingest);  // the slot may be overwritten after this point
+			if (e == cudaSuccess) e = cudaEventRecord(p->ev_ingest, p->s_ingest);
+			if (e == cudaSuccess) e = cudaStreamWaitEvent(p->s_main, p->ev_ingest, 0);      // the resampler may read what was appended
+			if (e != cudaSuccess) { rc = tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "stream ordering", e, __FILE__, __LINE__); break; }
+		}
+		// Everything above and the launches below are only ENQUEUED (ordered on the device by events), so the host's launch
+		// work for the heavy kernels runs while this block's H2D copy is still in flight; the copy is waited for last.
+		rc = drain_blocks(p);
+	} while (0);
+	if (copy_issued) {
 		const cudaError_t e = cudaStreamSynchronize(p->s_copy);             // the host buffer has been read
 		if (e != cudaSuccess && rc == TSDRGPU_OK) return tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "cudaStreamSynchronize(s_copy)", e, __FILE__, __LINE__);
 	}

@@ -49,7 +49,7 @@ struct tsdr_lib {
 	double pixelrate, refreshrate, pixeltimeoversampletime;
 	uint32_t centfreq;
 	float gain, motionblur;
-	char *errormsg; int errormsg_code;
+	char *errormsg, *errormsg_old; int errormsg_code;
 	uint32_t params_int[COUNT_PARAM_INT];
 	double params_double[COUNT_PARAM_DOUBLE];
 	tsdr_value_changed_callback callback;
@@ -60,15 +60,24 @@ struct tsdr_lib {
 	tsdrgpu_ctx_t *gpu; tsdrgpu_pipeline_t *pipe;
 	int gpu_failed;
 	pthread_mutex_t mu; pthread_cond_t finished;
+	/* t->pipe lives from tsdr_readasync's set-up to its tear-down while setters arrive from other threads: readers (the
+	 * setters, the plugin's data callback) hold pipe_lock shared, the tear-down takes it exclusively before the object dies */
+	pthread_rwlock_t pipe_lock;
+	pthread_mutex_t err_mu;              /* errormsg is replaced from the plugin's thread too (GPU failures) */
 };
 
 /* ---- error text: library-owned, NULL after a successful call (TSDRLibrary.c:136-159) ---------------------- */
 static int fail(tsdr_lib_t *t, const char *msg, int status) {
-	t->errormsg_code = status;
-	if (status == TSDR_OK) return status;
+	if (status == TSDR_OK) { t->errormsg_code = status; return status; }
 	if (!msg) msg = "An exception with no detailed explanation cause has occurred. This could as well be a bug in the TSDRlibrary or in one of its plugins.";
-	free(t->errormsg);
+	/* the previous text is kept alive until the NEXT failure replaces it (a reader that fetched the pointer just before an
+	 * update still sees valid memory, as with the reference's realloc'd buffer nobody frees in between) */
+	pthread_mutex_lock(&t->err_mu);
+	free(t->errormsg_old);
+	t->errormsg_old = t->errormsg;
 	t->errormsg = strdup(msg);
+	t->errormsg_code = status;
+	pthread_mutex_unlock(&t->err_mu);
 	return status;
 }
 static int ok(tsdr_lib_t *t) { t->errormsg_code = TSDR_OK; return TSDR_OK; }
@@ -76,7 +85,15 @@ static int plugin_result(tsdr_lib_t *t, int status) {
 	return status == TSDR_OK ? ok(t) : fail(t, t->plugin.getlasterrortext ? t->plugin.getlasterrortext() : NULL, status);
 }
 
-char *tsdr_getlasterrortext(tsdr_lib_t *t) { return t->errormsg_code == TSDR_OK ? NULL : t->errormsg; }
+char *tsdr_getlasterrortext(tsdr_lib_t *t) {
+	pthread_mutex_lock(&t->err_mu);
+	char *text = t->errormsg_code == TSDR_OK ? NULL : t->errormsg;
+	pthread_mutex_unlock(&t->err_mu);
+	return text;
+}
+
+/* run `call` on the live pipeline, if there is one, with the object pinned against the run's tear-down */
+#define WITH_PIPE(t, call) do { pthread_rwlock_rdlock(&(t)->pipe_lock); if ((t)->pipe) { call; } pthread_rwlock_unlock(&(t)->pipe_lock); } while (0)
 
 /* ---- geometry (set_internal_samplerate, TSDRLibrary.c:540-550) ------------------------------------------- */
 static void set_internal_samplerate(tsdr_lib_t *t, uint32_t samplerate) {
@@ -114,6 +131,7 @@ void tsdr_init(tsdr_lib_t **out, tsdr_value_changed_callback callback, tsdr_on_p
 	tsdr_lib_t *t = (tsdr_lib_t *) calloc(1, sizeof(tsdr_lib_t));   /* every field defined, unlike TSDRLibrary.c:62-94 */
 	t->callback = callback; t->plotready_callback = plotready_callback; t->callbackctx = ctx;
 	pthread_mutex_init(&t->mu, NULL); pthread_cond_init(&t->finished, NULL);
+	pthread_rwlock_init(&t->pipe_lock, NULL); pthread_mutex_init(&t->err_mu, NULL);
 	*out = t;
 }
 
@@ -123,8 +141,9 @@ void tsdr_free(tsdr_lib_t **pt) {
 	t->callback = NULL; t->plotready_callback = NULL;
 	plugin_close(&t->plugin);
 	if (t->gpu) tsdrgpu_destroy(t->gpu);
-	free(t->errormsg);
+	free(t->errormsg); free(t->errormsg_old);
 	pthread_mutex_destroy(&t->mu); pthread_cond_destroy(&t->finished);
+	pthread_rwlock_destroy(&t->pipe_lock); pthread_mutex_destroy(&t->err_mu);
 	free(t);
 	*pt = NULL;
 }
@@ -145,7 +164,7 @@ int tsdr_setbasefreq(tsdr_lib_t *t, uint32_t freq) {
 	t->centfreq = freq;
 	if (!t->plugin.initialized) return ok(t);
 	t->params_int[PARAM_AUTOCORR_PLOTS_RESET] = 2;            /* frameratedetector_flushcachedestimation */
-	if (t->pipe) tsdrgpu_pipeline_set_param_int(t->pipe, PARAM_AUTOCORR_PLOTS_RESET, 2);
+	WITH_PIPE(t, tsdrgpu_pipeline_set_param_int(t->pipe, PARAM_AUTOCORR_PLOTS_RESET, 2));
 	return plugin_result(t, t->plugin.setbasefreq(t->centfreq));
 }
 
@@ -185,43 +204,47 @@ int tsdr_setresolution(tsdr_lib_t *t, int height, double refreshrate) {
 	if (height <= 0 || refreshrate <= 0) return fail(t, "The supplied height is invalid or refreshrate is negative!", TSDR_WRONG_VIDEOPARAMS);
 	t->height = height; t->refreshrate = refreshrate;
 	if (t->plugin.initialized) set_internal_samplerate(t, t->samplerate);
-	if (t->pipe) tsdrgpu_pipeline_set_resolution(t->pipe, height, refreshrate);
+	WITH_PIPE(t, tsdrgpu_pipeline_set_resolution(t->pipe, height, refreshrate));
 	return ok(t);
 }
 
 int tsdr_motionblur(tsdr_lib_t *t, float coeff) {
 	if (coeff < 0.0f || coeff > 1.0f) return TSDR_WRONG_VIDEOPARAMS;
 	t->motionblur = coeff;
-	if (t->pipe) tsdrgpu_pipeline_set_motionblur(t->pipe, coeff);
+	WITH_PIPE(t, tsdrgpu_pipeline_set_motionblur(t->pipe, coeff));
 	return ok(t);
 }
 
 int tsdr_sync(tsdr_lib_t *t, int pixels, int direction) {      /* TSDRLibrary.c:576-602 */
 	if (pixels == 0) return TSDR_OK;
 	int delta = 0;
+	/* the geometry the frames are produced with right now: in superbandwidth mode the pipeline runs at 4x the plugin's rate
+	 * (superb_ondataready calls set_internal_samplerate(4 fs), superbandwidth.c:151, so tsdr->width follows there too) */
+	int width = t->width, height = t->height;
+	WITH_PIPE(t, tsdrgpu_pipeline_get_geometry(t->pipe, &width, &height, NULL));
 	switch (direction) {
 	case DIRECTION_CUSTOM: delta = pixels; break;
 	case DIRECTION_UP:
-		if (pixels > t->height || pixels < 0) return fail(t, "Cannot shift up with more pixels than the height of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
-		delta = pixels * t->width; break;
+		if (pixels > height || pixels < 0) return fail(t, "Cannot shift up with more pixels than the height of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
+		delta = pixels * width; break;
 	case DIRECTION_DOWN:
-		if (pixels > t->height || pixels < 0) return fail(t, "Cannot shift down with more pixels than the height of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
-		delta = -pixels * t->width; break;
+		if (pixels > height || pixels < 0) return fail(t, "Cannot shift down with more pixels than the height of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
+		delta = -pixels * width; break;
 	case DIRECTION_LEFT:
-		if (pixels > t->width || pixels < 0) return fail(t, "Cannot shift to the left with more pixels than the width of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
+		if (pixels > width || pixels < 0) return fail(t, "Cannot shift to the left with more pixels than the width of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
 		delta = pixels; break;
 	case DIRECTION_RIGHT:
-		if (pixels > t->width || pixels < 0) return fail(t, "Cannot shift to the right with more pixels than the width of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
+		if (pixels > width || pixels < 0) return fail(t, "Cannot shift to the right with more pixels than the width of the image or shift is negative!", TSDR_WRONG_VIDEOPARAMS);
 		delta = -pixels; break;
 	}
-	if (t->pipe && delta) tsdrgpu_pipeline_sync(t->pipe, delta);
+	if (delta) WITH_PIPE(t, tsdrgpu_pipeline_sync(t->pipe, delta));
 	return ok(t);
 }
 
 int tsdr_setparameter_int(tsdr_lib_t *t, int parameter, uint32_t value) {
 	if (parameter < 0 || parameter >= COUNT_PARAM_INT) return fail(t, "Invalid integer parameter id", TSDR_INVALID_PARAMETER);
 	t->params_int[parameter] = value;
-	if (t->pipe) tsdrgpu_pipeline_set_param_int(t->pipe, parameter, value);
+	WITH_PIPE(t, tsdrgpu_pipeline_set_param_int(t->pipe, parameter, value));
 	return ok(t);
 }
 
@@ -258,8 +281,9 @@ static void on_retune(int32_t offset_hz, void *user) {
 /* the plugin's data callback == the reference's process() (TSDRLibrary.c:264-298), on the plugin's thread */
 static void process(float *buf, uint64_t items_count, void *ctx, int64_t samples_dropped) {
 	tsdr_lib_t *t = (tsdr_lib_t *) ctx;
-	if (t->gpu_failed || !t->pipe) return;
-	const int rc = tsdrgpu_pipeline_process(t->pipe, buf, items_count, samples_dropped);
+	if (t->gpu_failed) return;
+	int rc = TSDRGPU_OK;
+	WITH_PIPE(t, rc = tsdrgpu_pipeline_process(t->pipe, buf, items_count, samples_dropped));
 	if (rc != TSDRGPU_OK) {
 		t->gpu_failed = 1;
 		fail(t, tsdrgpu_last_error(t->gpu), TSDR_CANNOT_OPEN_DEVICE);
@@ -270,8 +294,10 @@ static void process(float *buf, uint64_t items_count, void *ctx, int64_t samples
 /* ---- optional raw sink (include/TSDRPluginX.h): the plugin keeps its samples in wire format, the GPU converts ---- */
 static int raw_ingest(const void *samples, int fmt, uint64_t items_count, void *ctx, int64_t samples_dropped) {
 	tsdr_lib_t *t = (tsdr_lib_t *) ctx;
-	if (t->gpu_failed || !t->pipe) return 1;
-	const int rc = tsdrgpu_pipeline_process_raw(t->pipe, samples, fmt, items_count, samples_dropped);
+	if (t->gpu_failed) return 1;
+	int rc = TSDRGPU_OK, live = 0;
+	WITH_PIPE(t, (live = 1, rc = tsdrgpu_pipeline_process_raw(t->pipe, samples, fmt, items_count, samples_dropped)));
+	if (!live) return 1;
 	if (rc != TSDRGPU_OK) {
 		t->gpu_failed = 1;
 		fail(t, tsdrgpu_last_error(t->gpu), TSDR_CANNOT_OPEN_DEVICE);
@@ -321,25 +347,30 @@ int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 		cfg.batch_blocks = 10 * (cfg.batch_frames > 0 ? cfg.batch_frames : 1);
 		cfg.block_when_busy = getenv("TSDR_NO_DROP") ? 1 : 0;
 		t->frame_cb = cb; t->frame_ctx = ctx;
-		if (tsdrgpu_pipeline_create(t->gpu, &cfg, on_frame, on_value, on_plot, t, &t->pipe) != TSDRGPU_OK) {
+		tsdrgpu_pipeline_t *np = NULL;
+		if (tsdrgpu_pipeline_create(t->gpu, &cfg, on_frame, on_value, on_plot, t, &np) != TSDRGPU_OK) {
 			status = fail(t, tsdrgpu_last_error(t->gpu), TSDR_CANNOT_OPEN_DEVICE);
-			t->pipe = NULL;
 			goto end;
 		}
-		tsdrgpu_pipeline_set_retune(t->pipe, on_retune);
+		tsdrgpu_pipeline_set_retune(np, on_retune);
 		/* opt-in extras, all off by default so that an unchanged host sees exactly the reference's callbacks */
 		{
 			const char *snr = getenv("TSDR_REPORT_SNR"), *mode = getenv("TSDR_DETECT_MODE"), *argb = getenv("TSDR_OUTPUT_ARGB");
-			if ((snr && atoi(snr)) || (mode && atoi(mode))) tsdrgpu_pipeline_set_reports(t->pipe, snr && atoi(snr), mode && atoi(mode));
-			if (argb && argb[0] && argb[0] != '0') tsdrgpu_pipeline_set_output_argb(t->pipe, 1, strcmp(argb, "inverted") == 0);
+			if ((snr && atoi(snr)) || (mode && atoi(mode))) tsdrgpu_pipeline_set_reports(np, snr && atoi(snr), mode && atoi(mode));
+			if (argb && argb[0] && argb[0] != '0') tsdrgpu_pipeline_set_output_argb(np, 1, strcmp(argb, "inverted") == 0);
 		}
+		pthread_rwlock_wrlock(&t->pipe_lock);
+		t->pipe = np;                                 /* published: setters on other threads reach the run from here on */
+		pthread_rwlock_unlock(&t->pipe_lock);
 	}
 	status = t->plugin.readasync(process, t);                 /* blocks until tsdr_stop or a plugin error */
 	if (status != TSDR_OK) pluginsfault = 1;
 	tsdrgpu_pipeline_flush(t->pipe);
 	{
+		pthread_rwlock_wrlock(&t->pipe_lock);        /* no setter is inside the object any more, none can enter */
 		tsdrgpu_pipeline_t *p = t->pipe;
 		t->pipe = NULL;
+		pthread_rwlock_unlock(&t->pipe_lock);
 		tsdrgpu_pipeline_destroy(p);
 	}
 	if (t->gpu_failed) status = TSDR_CANNOT_OPEN_DEVICE;

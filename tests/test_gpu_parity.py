@@ -203,6 +203,37 @@ def test_post_process_sequence(gpu, O, lpbs, aap, autoshift, mb, batches):
         k += nb
 
 
+@pytest.mark.parametrize("batches", [(12,), (1, 4, 7)])
+def test_post_process_pll_writeback_arithmetic(gpu, O, batches):
+    """PLL on (syncdetector.c:133-153): the frame stage leaves vx / avg_speed / pll_state per frame, tsdrgpu_pll_step applies
+    the reference's write-back to the refresh rate.  Against the oracle built with PLL = 1: same frames, same sync state, and
+    the refresh rate after every frame EXACTLY equal (drifting frames, so the rate moves on most of them and the lock toggles)."""
+    import ctypes as C
+    from tempestsdr_b200 import _native
+    from tempestsdr_b200.api import PostProcessFlags
+    fs, hgt, fv = CFGS["cfg1"]
+    w, _, _ = O.geometry(fs, hgt, fv)
+    po = O.postprocessor(fs, hgt, fv, 1, 1)
+    shifts = [60, 63, 66, 69, 72, 72, 72, 73, 73, 74, 90, 110]
+    frames = [synth.video_like_frame(w, hgt, seed=k, shift_x=sx, shift_y=20) for k, sx in enumerate(shifts)]
+    want = [po.run(f, w, hgt, 0.0, 0.1, 1, 0) for f in frames]
+    assert sum(r.pll_callback_fired for _, r in want) >= 4
+    pg = gpu.post_processor()
+    rr = C.c_double(fv)
+    k = 0
+    for nb in batches:
+        out, res = pg.process(dev(np.concatenate(frames[k:k + nb])), w, hgt, 0.0, 0.1, PostProcessFlags())
+        out = out.cpu().numpy().reshape(nb, -1)
+        for i in range(nb):
+            wf, wr = want[k + i]
+            assert_same_bits(out[i], wf, f"frame {k + i}")
+            assert _results_tuple(res[i]) == wr.x.astuple() + wr.y.astuple()
+            assert res[i].avg_speed == wr.avg_speed and res[i].pll_state == wr.pll_state
+            moved = _native.lib().tsdrgpu_pll_step(C.byref(rr), res[i].x_vx, res[i].pll_state, res[i].avg_speed)
+            assert moved == wr.pll_callback_fired and rr.value == wr.refreshrate_after, f"refresh rate after frame {k + i}"
+        k += nb
+
+
 @pytest.mark.parametrize("name", ["cfg2", "cfg5", "odd"])
 @pytest.mark.parametrize("overlap", [False, True, "tma"])
 def test_post_process_full_size_frames(gpu, O, name, overlap, monkeypatch):
@@ -290,7 +321,7 @@ def _close(got, want, tol, what):
     return err, rel_l2
 
 
-@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 7, 10, 11, 12, 13, 16, 20, 23])
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 7, 10, 11, 12, 13, 16, 20, 23, 24])
 def test_fft(gpu, O, logn):
     n = 1 << logn
     x = synth.noise_iq(n, seed=logn)
@@ -303,7 +334,10 @@ def test_fft(gpu, O, logn):
         # float32 between stages (~1e-7*sqrt(log2 N) noise each).  Above 2^19 the reference itself drifts from the true DFT by up to 5e-5 (its stage twiddles come
         # from the half-angle recurrence c2 = sqrt((1-c1)/2), fft.c:161, which cancels for small angles); the CUDA FFT
         # uses the same perturbed stage angles (tsdrgpu_fft_reference_eps), so it tracks the reference, not the true DFT.
-        _close(d, want, 1e-6 if logn <= 22 else 2e-6, f"fft 2^{logn} inv={inv}")
+        # 2^24 (the top of BASELINE configs[2]'s sweep): the last stage's angle error is 1e-4 relative there and the float32
+        # rounding of 24 stages adds up; measured 2.1e-6 worst case, bound 4e-6
+        err, _ = _close(d, want, 1e-6 if logn <= 22 else (2e-6 if logn == 23 else 4e-6), f"fft 2^{logn} inv={inv}")
+        print(f"fft 2^{logn} inv={inv}: max|err|/peak = {err:.3g}")
 
 
 def test_reference_stage_angle_model():
@@ -317,8 +351,10 @@ def test_reference_stage_angle_model():
     assert 1e-7 < abs(eps[20]) < 1e-5 and abs(eps[23]) > abs(eps[18])
 
 
-@pytest.mark.parametrize("size", [1, 5, 1000, 4096, 70_001, 450_909])
+@pytest.mark.parametrize("size", [1, 5, 1000, 4096, 70_001, 450_909, 450_910, 1_409_090, 2_818_181])
 def test_autocorrelation_and_xcorr(gpu, O, size):
+    """The default path: even sizes take the half-size transforms, odd sizes the N-point ones (cfg1 / cfg2 / cfg5 capture sizes
+    450 909, 1 409 090 and 2 818 181 included)."""
     x = np.abs(synth.noise_iq(size, seed=size)[:size]).astype(np.float32)
     want = O.autocorrelation(x)
     got = gpu.fft_autocorrelation(dev(x))
@@ -335,15 +371,18 @@ def test_autocorrelation_and_xcorr(gpu, O, size):
 
 
 @pytest.mark.parametrize("size", [4096, 70_001 + 1, 450_910, 1_409_090])
-def test_autocorrelation_half_size_path(gpu, O, size, monkeypatch):
-    """TSDRGPU_AUTOCORR_HALF=1 (opt-in until its speed has been measured): both transforms at half size (real input packed as
-    complex pairs + the reference's last radix-2 stage).  Same tolerance as the default path;
-    profiles/studies/real_input_autocorr_study.py bounds the approximation."""
-    monkeypatch.setenv("TSDRGPU_AUTOCORR_HALF", "1")
+def test_autocorrelation_full_size_path(gpu, O, size, monkeypatch):
+    """TSDRGPU_AUTOCORR_FULL=1: the N-point transforms (fft.c:49-64 literally) instead of the default half-size ones (real input
+    packed as complex pairs + the reference's last radix-2 stage; profiles/studies/real_input_autocorr_study.py bounds that
+    approximation).  Same tolerance either way, and the two paths agree with each other far inside it."""
     x = np.abs(synth.noise_iq(size, seed=size)[:size]).astype(np.float32)
     want = O.autocorrelation(x)
+    half = gpu.fft_autocorrelation(dev(x)).cpu().numpy()
+    monkeypatch.setenv("TSDRGPU_AUTOCORR_FULL", "1")
     got = gpu.fft_autocorrelation(dev(x))
-    _close(got, want, 2e-6, f"half-size autocorrelation {size}")
+    _close(got, want, 2e-6, f"full-size autocorrelation {size}")
+    n = gpu.fft_getrealsize(size)
+    _close(half[: 2 * n], got.cpu().numpy()[: 2 * n], 1e-6, f"half-size vs full-size path {size}")
 
 
 def test_accumulate_exact_and_framerate_plots(gpu, O):
@@ -460,7 +499,11 @@ def test_full_size_properties(gpu):
     A, ra = pa.process(frames, w, h, 0.0, 0.1, fl)
     B = torch.cat([pb.process(frames[k * n:(k + 1) * n], w, h, 0.0, 0.1, fl)[0] for k in range(nframes)])
     assert torch.equal(A, B)
-    assert torch.equal(torch.sort(A[:n])[0] >= 0, torch.ones(n, dtype=torch.bool, device="cuda")) or True
+    # AUTOSHIFT on: frame f of the output is the temporally filtered frame circularly shifted by (x_dx, y_dx) -- with motionblur 0
+    # the filtered frame is the auto-gained input, so the output is a PERMUTATION of it: same multiset of values
+    lo, hi = ra[0].lastmin, ra[0].lastmax
+    norm = ((frames[:n] - lo) / (hi - lo if hi != lo else 1.0)).float()
+    assert torch.equal(torch.sort(A[:n])[0], torch.sort(norm)[0])
     # (4) FFT round trip and Parseval at 2^22
     x = torch.randn(2 << 22, device="cuda")
     y = x.clone()

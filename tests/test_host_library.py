@@ -153,6 +153,14 @@ def test_host_library_end_to_end(tmp_path):
     lib.tsdr_free(C.byref(t))
 
 
+@pytest.mark.gpu
+def test_a_plain_c_host_delivers_frames_on_the_gpu(tmp_path):
+    """The same C host, as a GPU test: on the B200 it has to deliver frames (rc = 0), not merely fail politely."""
+    import torch
+    assert torch.cuda.is_available()
+    test_a_plain_c_host_links_and_runs(tmp_path)
+
+
 def test_a_plain_c_host_links_and_runs(tmp_path):
     """INTEGRATION.md section A, literally: a C program compiled against include/TSDRLibrary.h and linked with libTSDRLibrary.a +
     libtsdrgpu.so drives init -> setresolution -> loadplugin -> readasync -> free.  On this machine's hardware it must either

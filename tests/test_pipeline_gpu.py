@@ -66,6 +66,94 @@ def test_pipeline_matches_stagewise_oracle():
     p.close()
 
 
+def run_oracle_stream_pll(O, iq_blocks, fs, h, fv):
+    """The same single-threaded replay with the PLL switched on (syncdetector.c:133-153): after every frame the refresh rate
+    the oracle's post-processor holds moves, and the NEXT group of ten decimator blocks is cut and resampled with it -- the
+    deterministic order the pipeline documents (the threaded reference races here)."""
+    w, _, _ = O.geometry(fs, h, fv)
+    rs = O.resampler(); pp = O.postprocessor(fs, h, fv, 1, 1)
+    decim = np.zeros(0, np.float32); pix = np.zeros(0, np.float32)
+    fv_live, w_live = fv, w
+    frames, rates = [], []
+    for iq in iq_blocks:
+        decim = np.concatenate([decim, O.am_demod(iq)])
+        while True:
+            block = int(0.1 * fs / fv_live)
+            if decim.size < 10 * block:
+                break
+            w_grp, fv_grp = w_live, fv_live
+            for k in range(10):
+                pix = np.concatenate([pix, rs.run(decim[k * block:(k + 1) * block], float(w_grp * h) * fv_grp, fs)])
+            decim = decim[10 * block:]
+            n = w_grp * h
+            while pix.size >= n:
+                out, res = pp.run(pix[:n], w_grp, h, 0.0, 0.1, 1, 0)
+                frames.append((out, w_grp)); pix = pix[n:]
+                if res.pll_callback_fired:
+                    rates.append(res.refreshrate_after)
+                fv_live, w_live = res.refreshrate_after, res.width_after
+    return frames, rates
+
+
+@pytest.mark.parametrize("items", [65536, 200_000])
+def test_pipeline_pll_writeback(items):
+    """PARAM_INT_FRAMERATE_PLL = 1, the GUI's default (Main.java): every frame whose picture moved (vx != 0) moves the refresh
+    rate (syncdetector.c:141-152), the decimator's next blocks are cut and resampled with the new rate (TSDRLibrary.c:335-340)
+    and the host hears about it (value id 0).  Frames bit-exact, announced rates exactly equal, for two ways of cutting the
+    stream into process() calls (the write-back is applied in stream order, not on a racing thread)."""
+    from tempestsdr_b200 import pipeline
+    O = orc.best()
+    fs, h, fv = 2_000_000, 125, 60.0
+    w, _, _ = O.geometry(fs, h, fv)
+    total = 24 * 65536
+    # the source's frame rate is 2500 ppm off the configured one: the picture drifts, vx != 0 on most frames
+    iq_all = synth.video_like_iq(total // 2, fs, w, h, fv, seed=61, fv_ppm=2500.0)
+    blocks = [iq_all[k:k + items].copy() for k in range(0, total, items)]
+    want, want_rates = run_oracle_stream_pll(O, blocks, fs, h, fv)
+    assert len(want_rates) >= 5 and len(set(want_rates)) == len(want_rates)
+    got, values = [], []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=1, batch_blocks=10, block_when_busy=True,
+                          params={"autoshift": 1, "framerate_pll": 1, "lowpass_before_sync": 1, "autocorr_plots_off": 1},
+                          on_frame=lambda f, ww, hh: got.append((f.copy(), ww)), on_value=lambda vid, a, b: values.append((vid, a, b)))
+    for b in blocks:
+        p.process(b, 0)
+    p.flush()
+    assert len(got) == len(want) > 5
+    for k, ((g, gw), (wv, ww)) in enumerate(zip(got, want)):
+        assert gw == ww and np.array_equal(g.view(np.uint32), wv.view(np.uint32)), f"frame {k}"
+    assert [a for vid, a, b in values if vid == 0] == want_rates
+    assert p.geometry()[2] == want_rates[-1]
+    p.close()
+
+
+@pytest.mark.parametrize("name,nframes,batch", [("cfg2", 5, 2), ("cfg5", 3, 1)])
+def test_pipeline_at_baseline_shapes(name, nframes, batch):
+    """The streaming pipeline at BASELINE's own shapes -- cfg2: 25 MS/s -> 740x1125 frames, cfg5: 50 MS/s -> 1481x1125 -- fed in
+    the RawFile plugin's block size (524 288 floats): frames bit-exact against the stage-wise replay of the reference."""
+    from tempestsdr_b200 import pipeline
+    from tests.test_gpu_parity import CFGS
+    O = orc.best()
+    fs, h, fv = CFGS[name]
+    w, _, _ = O.geometry(fs, h, fv)
+    items = 512 * 1024
+    pairs = (nframes * int(fs / fv) + 3 * int(0.1 * fs / fv))
+    nblk = (2 * pairs + items - 1) // items
+    iq_all = synth.video_like_iq(nblk * items // 2, fs, 2576, 1125, fv, seed=73, snr_db=25.0)
+    blocks = [iq_all[k * items:(k + 1) * items] for k in range(nblk)]
+    _, want = run_oracle_stream(O, blocks, fs, h, fv)
+    got = []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=batch, batch_blocks=10 * batch, block_when_busy=True,
+                          params={"autoshift": 1, "lowpass_before_sync": 1, "autocorr_plots_off": 1},
+                          on_frame=lambda f, ww, hh: got.append((f.copy(), ww, hh)))
+    for b in blocks:
+        p.process(b.copy(), 0)
+    p.flush()
+    assert len(got) >= nframes - 1 and len(got) == (len(want) // batch) * batch
+    for k, (g, ww, hh) in enumerate(got):
+        assert (ww, hh) == (w, h) and np.array_equal(g.view(np.uint32), want[k].view(np.uint32)), f"{name} frame {k}"
+    p.close()
+
+
 def test_pipeline_drop_resync_and_manual_sync():
     """Upstream sample drops discard up to the next multiple of `block` (dsp.c:313-368) so frames stay aligned."""
     from tempestsdr_b200 import pipeline
