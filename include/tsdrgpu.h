@@ -290,6 +290,27 @@ TSDRGPU_API int tsdrgpu_superb_residue_ifft_lag(tsdrgpu_ctx_t *ctx, void *stream
 TSDRGPU_API int tsdrgpu_superb_residue_ifft(tsdrgpu_ctx_t *ctx, void *stream, const float *d_gathered, int nhops, uint32_t n,
                                             int residue, float *d_out_residue);
 
+/* ---- one hop per GPU, behind the C-ABI (csrc/superb_mgpu.cu) ----------------------
+ * superb_ondataready sharded over the GPUs of one node: rank q owns hop q.  Local spectra -> this rank's alignment lag (hop 0's
+ * difference spectrum read from rank 0 over NVLink) -> an all-to-all mix (bins pulled from the peers, residues pushed to
+ * them) -> one N-point inverse per rank -> |.| pushed into the root's window -> the root interleaves the time-contiguous
+ * MAGNITUDE stream (what am_demod makes of superb_run's output, TSDRLibrary.c:271-274).  No host synchronisation, no
+ * collective library: flags in peer memory order the phases.  A group object exists once per rank; the windows are tied
+ * together either through CUDA IPC handles (one process per GPU: export -> exchange by any means -> connect_ipc) or directly
+ * (all ranks in one process: connect_local).  nranks in {2, 4, 8, 16}. */
+typedef struct tsdrgpu_superb_mgpu tsdrgpu_superb_mgpu_t;
+TSDRGPU_API int  tsdrgpu_superb_mgpu_create(tsdrgpu_ctx_t *ctx, int nranks, int rank, int root, uint32_t max_pairs_per_hop, tsdrgpu_superb_mgpu_t **g);
+TSDRGPU_API void tsdrgpu_superb_mgpu_destroy(tsdrgpu_superb_mgpu_t *g);
+TSDRGPU_API int  tsdrgpu_superb_mgpu_export(tsdrgpu_superb_mgpu_t *g, uint8_t handle[64]);
+TSDRGPU_API int  tsdrgpu_superb_mgpu_connect_ipc(tsdrgpu_superb_mgpu_t *g, const uint8_t *handles /* nranks x 64 bytes, rank-major */);
+TSDRGPU_API int  tsdrgpu_superb_mgpu_connect_local(tsdrgpu_superb_mgpu_t *const *all_ranks, int nranks);
+/* every rank calls this once per stitch (same count_pairs / samples_in_frame), each on a stream of its own device; asynchronous.
+ * The root's d_stream_out receives nranks * N magnitudes, N = fft_getrealsize(count_pairs) returned in *h_n. */
+TSDRGPU_API int  tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream, const float *d_hop, int count_pairs, int samples_in_frame,
+                                            float *d_stream_out, uint32_t *h_n);
+/* lags (complex samples) of the last stitch as every rank published them, and the status word (0 = fine); synchronises `stream` */
+TSDRGPU_API int  tsdrgpu_superb_mgpu_lags(tsdrgpu_superb_mgpu_t *g, void *stream, int *h_lags, uint32_t *h_status);
+
 /* ---------------------------------------------------------------------------- a1, a3, a5, a16, a17  streaming pipeline
  * replaces the body of process() (TSDRLibrary.c:264-298), decimatingthread / postprocessingthread /
  * videodecodingthread (TSDRLibrary.c:300-418) with their three rings (circbuff.c), dsp_dropped_compensation_*

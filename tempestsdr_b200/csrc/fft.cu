@@ -517,24 +517,43 @@ __global__ void k_rotate(const float2 *src, float2 *dst, unsigned long long n, u
 	}
 }
 // argmax of |x| over [0, n): first maximum wins                         (superbandwidth.c:100-116)
-__global__ void __launch_bounds__(1024) k_argmax_mag(const float2 *x, unsigned n, int *result) {
-	__shared__ float s_v[32]; __shared__ unsigned s_i[32];
-	float best = -1.0f; unsigned bi = 0xffffffffu;
-	for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-		const float2 v = x[i];
-		const float m = mag_exact(v.x, v.y);
-		if (m > best) { best = m; bi = i; }
-	}
-	for (int o = 16; o > 0; o >>= 1) {
-		const float ov = __shfl_xor_sync(0xffffffffu, best, o); const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
-		if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-	}
+// Two steps over the whole chip instead of one CTA: every CTA reduces a contiguous chunk to (value, index), the last step
+// (one CTA) reduces the partials.  "First maximum" = smallest index among equal values, so the result does not depend on
+// how the range is cut; the reference starts from element 0 and only moves on a strict '>' (NaN never wins).
+__device__ __forceinline__ void argmax_merge(float &best, unsigned &bi, float ov, unsigned oi) {
+	if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+__device__ __forceinline__ void argmax_block_reduce(float &best, unsigned &bi, float *s_v, unsigned *s_i) {
+	for (int o = 16; o > 0; o >>= 1) argmax_merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
 	if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		for (int w = 1; w < (int) (blockDim.x >> 5); w++) if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) { best = s_v[w]; bi = s_i[w]; }
-		// the reference starts from element 0 and only moves on a strict '>' (NaN never wins)
-		*result = (bi == 0xffffffffu) ? 0 : (int) bi;
+	if (threadIdx.x == 0) for (int w = 1; w < (int) (blockDim.x >> 5); w++) argmax_merge(best, bi, s_v[w], s_i[w]);
+}
+__global__ void __launch_bounds__(256) k_argmax_partial(const float2 *__restrict__ x, unsigned n, float *__restrict__ pv, unsigned *__restrict__ pi) {
+	__shared__ float s_v[8]; __shared__ unsigned s_i[8];
+	const unsigned per = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = min(n, lo + per);
+	float best = -1.0f; unsigned bi = 0xffffffffu;
+	for (unsigned i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const float2 v = __ldg(x + i);
+		const float m = mag_exact(v.x, v.y);
+		if (m > best) { best = m; bi = i; }              // a thread walks upwards: the first of equal values stays
+	}
+	argmax_block_reduce(best, bi, s_v, s_i);
+	if (threadIdx.x == 0) { pv[blockIdx.x] = best; pi[blockIdx.x] = bi; }
+}
+__global__ void __launch_bounds__(256) k_argmax_final(const float *__restrict__ pv, const unsigned *__restrict__ pi, unsigned parts, int *result) {
+	__shared__ float s_v[8]; __shared__ unsigned s_i[8];
+	float best = -1.0f; unsigned bi = 0xffffffffu;
+	for (unsigned i = threadIdx.x; i < parts; i += blockDim.x) argmax_merge(best, bi, pv[i], pi[i]);
+	argmax_block_reduce(best, bi, s_v, s_i);
+	if (threadIdx.x == 0) *result = (bi == 0xffffffffu) ? 0 : (int) bi;
+}
+// rotate left by *shift complex elements, the shift read from device memory (the lag the kernels before produced)
+__global__ void k_rotate_dev(const float2 *src, float2 *dst, unsigned long long n, const int *shift_) {
+	const unsigned long long shift = (unsigned long long) *shift_;
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+		unsigned long long s = i + shift; if (s >= n) s -= n;
+		dst[i] = src[s];
 	}
 }
 // U_s[m] = e^{+2 pi i m s/(H N)} * sum_q e^{+2 pi i q s / H} X_q[m]     (superbandwidth decomposition)
@@ -798,6 +817,26 @@ int tsdrgpu_fft_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, 
 	return fft_run(ctx, stream, data, (float2 *) scratch, ilog2(n_pow2), inverse, o);
 }
 
+// out of place: out = FFT(in), both n_pow2 complex, `in` untouched
+int tsdrgpu_fft_oop_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float2 *out, unsigned long long n_pow2, int inverse) {
+	int rc = ensure_table(ctx, stream);
+	if (rc) return rc;
+	if (n_pow2 <= 1) { if (n_pow2 == 1) CU_TRY(ctx, cudaMemcpyAsync(out, in, sizeof(float2), cudaMemcpyDeviceToDevice, stream)); return TSDRGPU_OK; }
+	void *scratch;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * n_pow2, &scratch))) return rc;
+	FftOpts o; memset(&o, 0, sizeof o); o.batch = 1; o.scale = inverse ? 1.0f : 1.0f / (float) n_pow2;
+	o.cplx_in = in; o.cplx_bs = 0;
+	return fft_run(ctx, stream, out, (float2 *) scratch, ilog2(n_pow2), inverse, o);
+}
+// *d_result = index of the first maximum of |x[0..n)|; d_part: room for 2 * TSDRGPU_ARGMAX_PARTS 32-bit words
+int tsdrgpu_argmax_mag_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *x, unsigned n, void *d_part, int *d_result) {
+	unsigned parts = (n + 4095) / 4096; if (parts > TSDRGPU_ARGMAX_PARTS) parts = TSDRGPU_ARGMAX_PARTS; if (parts < 1) parts = 1;
+	float *pv = (float *) d_part; unsigned *pi = (unsigned *) d_part + TSDRGPU_ARGMAX_PARTS;
+	KL(ctx, "k_argmax", stream, k_argmax_partial<<<parts, 256, 0, stream>>>(x, n, pv, pi));
+	KL(ctx, "k_argmax", stream, k_argmax_final<<<1, 256, 0, stream>>>(pv, pi, parts, d_result));
+	return TSDRGPU_OK;
+}
+
 struct tsdrgpu_frd {
 	tsdrgpu_ctx_t *ctx;
 	float *d_big; size_t big_cap;                 // extbuff (2*size floats)
@@ -1049,24 +1088,32 @@ int tsdrgpu_complex_to_abs_diff(tsdrgpu_ctx_t *ctx, void *stream_, float *d_data
 	return TSDRGPU_OK;
 }
 
-int tsdrgpu_superb_bestfit(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop0, const float *d_hopi, int size_floats,
-                           int samples_in_frame, int *h_best_offset) {
-	BIND(ctx); ARG_TRY(ctx, d_hop0 && d_hopi && h_best_offset && size_floats > 0 && samples_in_frame > 0);
-	cudaStream_t stream = (cudaStream_t) stream_;
+// the lag (in complex samples) of hop i against hop 0, left in device memory at d_lag -- no host round trip
+static int superb_bestfit_dev(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float *d_hop0, const float *d_hopi, int size_floats,
+                              int samples_in_frame, int *d_lag) {
 	int size = (size_floats / samples_in_frame) * samples_in_frame;      // superbandwidth.c:84-86
 	ARG_TRY(ctx, size >= 2);
 	size = (int) tsdrgpu_fft_getrealsize((uint32_t) size);
 	const unsigned long long pairs = (unsigned long long) size / 2;
-	void *wa, *wb; int rc;
+	void *wa, *wb, *part; int rc;
 	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * pairs + 256, &wa))) return rc;
-	if ((rc = tsdrgpu_scratch(ctx, 2, sizeof(float2) * pairs + 256, &wb))) return rc;
+	if ((rc = tsdrgpu_scratch(ctx, 2, sizeof(float2) * pairs + 8 * TSDRGPU_ARGMAX_PARTS + 256, &wb))) return rc;
 	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), (float2 *) wa, pairs));
 	KL(ctx, "k_abs_diff", stream, k_abs_diff<<<grid1d(pairs, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hopi), (float2 *) wb, pairs));
 	if ((rc = tsdrgpu_crosscorrelation(ctx, stream, (float *) wa, (float *) wb, (uint32_t) pairs))) return rc;
-	int *d_res = reinterpret_cast<int *>((char *) wb);    // wb is free again after the cross-correlation
-	KL(ctx, "k_argmax_mag", stream, k_argmax_mag<<<1, 1024, 0, stream>>>((const float2 *) wa, (unsigned) pairs, d_res));
+	part = wb;                                            // wb is free again after the cross-correlation
+	return tsdrgpu_argmax_mag_internal(ctx, stream, (const float2 *) wa, (unsigned) pairs, part, d_lag);
+}
+
+int tsdrgpu_superb_bestfit(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_hop0, const float *d_hopi, int size_floats,
+                           int samples_in_frame, int *h_best_offset) {
+	BIND(ctx); ARG_TRY(ctx, d_hop0 && d_hopi && h_best_offset && size_floats > 0 && samples_in_frame > 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	void *res; int rc;
+	if ((rc = tsdrgpu_scratch(ctx, 3, 256, &res))) return rc;
+	if ((rc = superb_bestfit_dev(ctx, stream, d_hop0, d_hopi, size_floats, samples_in_frame, (int *) res))) return rc;
 	int lag = 0;
-	CU_TRY(ctx, cudaMemcpyAsync(&lag, d_res, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	CU_TRY(ctx, cudaMemcpyAsync(&lag, res, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
 	*h_best_offset = 2 * lag;
 	return TSDRGPU_OK;
@@ -1081,20 +1128,33 @@ int tsdrgpu_superb_hop_spectrum(tsdrgpu_ctx_t *ctx, void *stream_, const float *
 	return tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_spectrum), N, 0);
 }
 
+// superb_ondataready (superbandwidth.c:121-152) on one GPU.  Everything stays on the device: the H-1 alignment lags are left
+// in device memory by the grid argmax, the rotations read them from there, and the host sees them once, at the end (one
+// synchronisation per stitch instead of one per hop).
 int tsdrgpu_superb_stitch(tsdrgpu_ctx_t *ctx, void *stream_, float *const *d_hops, int nhops, int count_pairs, int samples_in_frame,
                           float *d_out, int *h_best_offsets, int *h_total_samples) {
-	BIND(ctx); ARG_TRY(ctx, d_hops && nhops > 0 && count_pairs > 0 && d_out && h_best_offsets);
+	BIND(ctx); ARG_TRY(ctx, d_hops && nhops > 0 && nhops <= 16 && count_pairs > 0 && d_out && h_best_offsets);
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
 	int rc;
-	h_best_offsets[0] = 0;
+	void *lags_;
+	if ((rc = tsdrgpu_scratch(ctx, 3, 256, &lags_))) return rc;
+	int *d_lags = (int *) lags_;
+	CU_TRY(ctx, cudaMemsetAsync(d_lags, 0, sizeof(int) * 16, stream));
 	for (int i = 1; i < nhops; i++)
-		if ((rc = tsdrgpu_superb_bestfit(ctx, stream, d_hops[0], d_hops[i], (int) (2 * N), samples_in_frame, &h_best_offsets[i]))) return rc;
-	for (int i = 0; i < nhops; i++)
-		if ((rc = tsdrgpu_superb_hop_spectrum(ctx, stream, d_hops[i], count_pairs, h_best_offsets[i], d_out + (size_t) i * 2 * N))) return rc;
+		if ((rc = superb_bestfit_dev(ctx, stream, d_hops[0], d_hops[i], (int) (2 * N), samples_in_frame, d_lags + i))) return rc;
+	for (int i = 0; i < nhops; i++) {
+		float2 *spec = reinterpret_cast<float2 *>(d_out) + (size_t) i * N;
+		KL(ctx, "k_rotate", stream, k_rotate_dev<<<grid1d(N, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hops[i]), spec, N, d_lags + i));
+		if ((rc = tsdrgpu_fft_internal(ctx, stream, spec, N, 0))) return rc;
+	}
 	const unsigned long long total = N * (unsigned long long) nhops;
 	const unsigned long long tp = 1ull << ilog2(total);            // fft_perform transforms the largest power of two (fft.c:101-105)
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, reinterpret_cast<float2 *>(d_out), tp, 1))) return rc;
+	int lags[16];
+	CU_TRY(ctx, cudaMemcpyAsync(lags, d_lags, sizeof(int) * 16, cudaMemcpyDeviceToHost, stream));
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	for (int i = 0; i < nhops; i++) h_best_offsets[i] = 2 * lags[i];
 	if (h_total_samples) *h_total_samples = (int) total;
 	return TSDRGPU_OK;
 }
@@ -1168,13 +1228,13 @@ int tsdrgpu_superb_lags(tsdrgpu_ctx_t *ctx, void *stream_, const float *d_gather
 	const float2 *G = reinterpret_cast<const float2 *>(d_gathered);
 	void *wa, *res; int rc;
 	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * nd + 256, &wa))) return rc;
-	if ((rc = tsdrgpu_scratch(ctx, 2, sizeof(int) * 16 + 256, &res))) return rc;
+	if ((rc = tsdrgpu_scratch(ctx, 2, 256 + 8 * TSDRGPU_ARGMAX_PARTS + 256, &res))) return rc;
 	h_lags[0] = 0;
 	for (int q = 1; q < nhops; q++) {
 		CU_TRY(ctx, cudaMemcpyAsync(wa, G + n, sizeof(float2) * nd, cudaMemcpyDeviceToDevice, stream));            // D_0
 		KL(ctx, "k_conj_mul", stream, k_conj_mul<<<grid1d(nd, ctx->sm_count), 256, 0, stream>>>((float2 *) wa, G + (size_t) q * block_stride_complex + n, nd));
 		if ((rc = tsdrgpu_fft_internal(ctx, stream, (float2 *) wa, nd, 1))) return rc;
-		KL(ctx, "k_argmax_mag", stream, k_argmax_mag<<<1, 1024, 0, stream>>>((const float2 *) wa, nd, (int *) res + q));
+		if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, (const float2 *) wa, nd, (char *) res + 256, (int *) res + q))) return rc;
 	}
 	CU_TRY(ctx, cudaMemcpyAsync(h_lags + 1, (int *) res + 1, sizeof(int) * (nhops - 1), cudaMemcpyDeviceToHost, stream));
 	CU_TRY(ctx, cudaStreamSynchronize(stream));

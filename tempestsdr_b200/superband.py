@@ -178,3 +178,74 @@ def stitch_distributed_fused(ctx: api.Context, hop: torch.Tensor, samples_in_fra
     ctx.chk(ctx._lib.tsdrgpu_superb_residue_ifft_lag(ctx._h, ctx.stream, gathered.data_ptr(), ex.world, ex.block_stride, n,
                                                      residue_of_rank(ex.rank, ex.world), lags, out.data_ptr()))
     return out, list(lags), n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The product path (csrc/superb_mgpu.cu, tsdrgpu_superb_mgpu_*): everything above the C-ABI is bookkeeping.
+class SuperbGroup:
+    """One rank's handle on a superbandwidth group (tsdrgpu_superb_mgpu_t): rank q owns hop q, the root ends up with the
+    time-contiguous magnitude stream.  No collective library is involved in a stitch: the kernels exchange data and flags
+    through windows mapped into every rank.
+
+    * one process per GPU (torchrun): ``SuperbGroup.for_process_group(ctx, max_pairs)`` -- the 64-byte CUDA IPC handles of the
+      windows travel once, at set-up, through ``torch.distributed.all_gather_object``;
+    * all ranks in one process: ``SuperbGroup.local(ctxs, max_pairs)`` (one context per device; several contexts on ONE
+      device also work and let a single GPU replay the whole dataflow).
+    """
+
+    def __init__(self, ctx: api.Context, nranks: int, rank: int, root: int, max_pairs: int):
+        self.ctx, self.nranks, self.rank, self.root = ctx, nranks, rank, root
+        h = C.c_void_p()
+        ctx.chk(ctx._lib.tsdrgpu_superb_mgpu_create(ctx._h, nranks, rank, root, max_pairs, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def for_process_group(cls, ctx: api.Context, max_pairs: int, root: int = 0, group=None) -> "SuperbGroup":
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        g = cls(ctx, world, rank, root, max_pairs)
+        handle = (C.c_uint8 * 64)()
+        ctx.chk(ctx._lib.tsdrgpu_superb_mgpu_export(g._h, handle))
+        handles: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        ctx.chk(ctx._lib.tsdrgpu_superb_mgpu_connect_ipc(g._h, blob))
+        dist.barrier(group=group)
+        return g
+
+    @classmethod
+    def local(cls, ctxs: Sequence[api.Context], max_pairs: int, root: int = 0) -> List["SuperbGroup"]:
+        gs = [cls(c, len(ctxs), r, root, max_pairs) for r, c in enumerate(ctxs)]
+        arr = (C.c_void_p * len(gs))(*[g._h for g in gs])
+        gs[0].ctx.chk(gs[0].ctx._lib.tsdrgpu_superb_mgpu_connect_local(arr, len(gs)))
+        return gs
+
+    def stitch(self, hop: torch.Tensor, samples_in_frame: int, out: Optional[torch.Tensor] = None):
+        """This rank's share of one stitch, asynchronous on the current stream of the context's device.  On the root returns
+        the magnitude stream (nranks * N floats, time-contiguous); elsewhere None."""
+        pairs = hop.numel() // 2
+        n = self.ctx.fft_getrealsize(pairs)
+        if self.rank == self.root and out is None:
+            out = torch.empty(self.nranks * n, dtype=torch.float32, device=hop.device)
+        hn = C.c_uint32(0)
+        self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_stitch(self._h, self.ctx.stream, hop.data_ptr(), pairs, samples_in_frame,
+                                                              out.data_ptr() if out is not None else None, C.byref(hn)))
+        return (out[: self.nranks * hn.value] if self.rank == self.root else None)
+
+    def lags(self) -> List[int]:
+        """Alignment lags (complex samples) of the last stitch; synchronises and raises if a rank went missing."""
+        lags = (C.c_int * self.nranks)()
+        status = C.c_uint32(0)
+        self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_lags(self._h, self.ctx.stream, lags, C.byref(status)))
+        return list(lags)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.tsdrgpu_superb_mgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

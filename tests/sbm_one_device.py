@@ -1,0 +1,51 @@
+"""All H ranks of a superbandwidth group on ONE device (see test_superbandwidth_one_hop_per_rank_on_one_device).
+
+    python -m tests.sbm_one_device H
+
+Against superb_ondataready + am_demod of the reference (superbandwidth.c:121-152, TSDRLibrary.c:244-262): lags exact, magnitudes
+to 1e-5 of the peak (float32 transforms in a different summation order; north_star's bound for float intermediates), two
+stitches in a row (epoch-valued flags)."""
+import sys
+
+import numpy as np
+import torch
+
+from oracle import oracle as orc
+from tempestsdr_b200 import api, superband, synth
+
+
+def run(H: int) -> None:
+    O = orc.best()
+    fs, fv = 400_000, 50.0
+    sif = int(fs / fv)
+    pairs = 10 * sif
+    base = synth.video_like_iq(pairs + 9000, fs, 200, 160, fv, seed=19, snr_db=25)
+    offsets = [0, 1234, 77, 3999, 512, 6001, 2500, 4242][:H]
+    ctxs = [api.Context(0) for _ in range(H)]
+    streams = [torch.cuda.Stream() for _ in range(H)]
+    groups = superband.SuperbGroup.local(ctxs, pairs)
+    for rnd in range(2):
+        hops = [base[2 * l: 2 * (l + pairs)].copy() + synth.noise_iq(pairs, seed=100 * rnd + i, scale=0.01) for i, l in enumerate(offsets)]
+        want_iq, offs = O.superb_ondataready(hops, sif)
+        want = O.am_demod(want_iq)
+        d_hops = [torch.from_numpy(h).cuda() for h in hops]
+        torch.cuda.synchronize()
+        out = None
+        for r in range(H):
+            with torch.cuda.stream(streams[r]):
+                res = groups[r].stitch(d_hops[r], sif)
+                out = res if res is not None else out
+        torch.cuda.synchronize()
+        lags = groups[0].lags()
+        assert [2 * l for l in lags] == [int(o) for o in offs], (rnd, lags, list(offs))
+        assert groups[H - 1].lags() == lags
+        got = out.cpu().numpy()
+        assert got.shape == want.shape, (got.shape, want.shape)
+        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        print(f"H={H} round {rnd}: lags {lags}, max|err|/peak = {err:.3g}")
+        assert err <= 1e-5, err
+    print("sbm ok")
+
+
+if __name__ == "__main__":
+    run(int(sys.argv[1]))

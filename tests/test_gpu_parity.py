@@ -436,6 +436,18 @@ def test_superbandwidth(gpu, O):
     _close(sim, want, 8e-6, "one-exchange stitch")
 
 
+@pytest.mark.parametrize("H", [2, 4, 8])
+def test_superbandwidth_one_hop_per_rank_on_one_device(H):
+    """csrc/superb_mgpu.cu (tsdrgpu_superb_mgpu_*) with all H ranks living on THIS GPU (one context and one stream per rank,
+    windows cross-linked by connect_local): the complete product dataflow -- local spectra, lag from rank 0's difference
+    spectrum, all-to-all mix, residue inverse, |.| into the root's slots, interleave -- with its flag synchronisation, on a
+    single device (tests/sbm_one_device.py; a process of its own so that every rank's stream gets a hardware queue of its own)."""
+    import subprocess, sys
+    r = subprocess.run([sys.executable, "-m", "tests.sbm_one_device", str(H)], capture_output=True, text=True, timeout=240,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32"))
+    assert r.returncode == 0 and "sbm ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_golden_vectors_gpu(gpu):
     from tempestsdr_b200.api import PostProcessFlags
@@ -502,7 +514,9 @@ def test_full_size_properties(gpu):
     # AUTOSHIFT on: frame f of the output is the temporally filtered frame circularly shifted by (x_dx, y_dx) -- with motionblur 0
     # the filtered frame is the auto-gained input, so the output is a PERMUTATION of it: same multiset of values
     lo, hi = ra[0].lastmin, ra[0].lastmax
-    norm = ((frames[:n] - lo) / (hi - lo if hi != lo else 1.0)).float()
+    span = np.float32(hi) - np.float32(lo) if hi != lo else np.float32(1.0)
+    # tensor / tensor: a true IEEE division per element (a Python scalar divisor would be turned into a multiplication by 1/span)
+    norm = torch.div(frames[:n] - float(np.float32(lo)), torch.full((n,), float(span), device="cuda"))
     assert torch.equal(torch.sort(A[:n])[0], torch.sort(norm)[0])
     # (4) FFT round trip and Parseval at 2^22
     x = torch.randn(2 << 22, device="cuda")
