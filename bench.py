@@ -647,23 +647,124 @@ def autocorr_sweep(gpu, torch):
 
 
 def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
+    """BASELINE configs[3] / the path's one sharded row: superbandwidth with one hop per GPU, H = world hops of
+    10 frames of 25 MS/s IQ each (N = 2^21 per hop).  Reports, all with an L2 flush between repetitions (a stitch runs once per
+    H x 0.67 s of signal in production: cold caches are the honest state):
+      ms_per_stitch       hops resident on their GPUs -> time-contiguous magnitude stream resident on the root (max over ranks)
+      one_gpu_ms          the same H hops through the one-GPU stitch (tsdrgpu_superb_stitch) on rank 0's GPU, its IQ output
+      speedup             one_gpu_ms / ms_per_stitch
+      frames_per_s        root: stitch + resample + frame stage of the stitched stream, frames of the H x rate geometry per second
+      parity              sharded magnitudes vs |one-GPU stitch| (max error / peak), lags equal
+      nccl_allgather_baseline_ms   round 1's formulation (one NCCL all-gather of raw spectra, every rank derives every lag)"""
     from tempestsdr_b200 import superband
-    hop_pairs = 10 * int(FS / FV)                        # SUPER_SAMPLES_TO_RECORD frames per hop -> N = 2^21
-    hop = iq_dev[: 2 * hop_pairs].contiguous()
-    for _ in range(2):
-        superband.stitch_distributed(gpu, hop, int(FS / FV))
+    from tempestsdr_b200.api import PostProcessFlags
+    H = world
+    sif = int(FS / FV)
+    hop_pairs = 10 * sif                                  # SUPER_SAMPLES_TO_RECORD frames per hop -> N = 2^21
+    src = torch.from_numpy(make_iq(hop_pairs + 16 * 1000, seed=4242)).cuda()       # the same on every rank: rank 0 can rebuild every hop
+    offs = [0] + [131 + 977 * q for q in range(1, H)]
+    hop_of = lambda q: src[2 * offs[q]: 2 * (offs[q] + hop_pairs)].contiguous()
+    hop = hop_of(rank)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")            # 256 MB > L2
+    grp = superband.SuperbGroup.for_process_group(gpu, hop_pairs)
+    n_fft = gpu.fft_getrealsize(hop_pairs)
+    out = torch.empty(H * n_fft, dtype=torch.float32, device="cuda") if rank == 0 else None
+    for _ in range(3):
+        grp.stitch(hop, sif, out=out)
+    lags = grp.lags()
     barrier()
-    s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    s0e.record()
-    for _ in range(reps):
-        res, lags, n_fft = superband.stitch_distributed(gpu, hop, int(FS / FV))
-    s1e.record()
+    reps = 10
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record(); grp.stitch(hop, sif, out=out); b.record()
     barrier()
-    tms = torch.tensor([s0e.elapsed_time(s1e) / reps], device="cuda")
+    tms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / reps], device="cuda")
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    return {"hops": world, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": world * n_fft / (tms.item() * 1e-3) / 1e6,
-            "allgather_bytes_per_rank": 8 * (n_fft + n_fft // 2), "collective": "one NCCL all_gather_into_tensor per stitch"}
+    res = {"hops": H, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": H * n_fft / (tms.item() * 1e-3) / 1e6,
+           "lags": lags, "l2_flushed_between_repetitions": True,
+           "exchange": "peer-memory windows (CUDA IPC over NVLink), flags in peer memory; no collective library on the data path",
+           "nvlink_bytes_received_per_rank": int(8 * (n_fft // 2) * (1 if rank else 0) + 2 * 8 * n_fft * (H - 1) // H),
+           "nvlink_bytes_received_by_root_for_stream": int(4 * n_fft * (H - 1))}
+    # ---- rank 0: the same hops on one GPU, parity, frames
+    one = torch.zeros(3, device="cuda", dtype=torch.float64)
+    if rank == 0:
+        hops = [hop_of(q) for q in range(H)]
+        for _ in range(2):
+            one_iq, one_offs = gpu.superb_stitch(hops, sif)
+        t1 = []
+        for _ in range(5):
+            flush.zero_(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); one_iq, one_offs = gpu.superb_stitch(hops, sif); b.record(); torch.cuda.synchronize()
+            t1.append(a.elapsed_time(b))
+        one_ms = sum(t1) / len(t1)
+        ref_mag = gpu.am_demod(one_iq)
+        err = float((out - ref_mag).abs().max() / ref_mag.abs().max())
+        lags_equal = [2 * l for l in lags] == list(one_offs)
+        # frames from the stitched stream: H x the rate, same lines
+        wH = int(2 * (H * FS / (FV * HEIGHT)))
+        blockH = int(0.1 * H * FS / FV)
+        nblk = (H * n_fft) // blockH
+        rs, pp = gpu.resampler(), gpu.post_processor()
+        upH = float(wH * HEIGHT) * FV
+        pix = torch.empty(int(rs.plan((blockH, nblk), upH, float(H * FS))) + 1024, dtype=torch.float32, device="cuda")
+        nH = wH * HEIGHT
+        frames_out = torch.empty(((pix.numel() // nH) + 1) * nH, dtype=torch.float32, device="cuda")
+
+        def round_trip():
+            grp_out = grp.stitch(hop, sif, out=out)
+            px = rs.process(grp_out, (blockH, nblk), upH, float(H * FS), in_is_iq=False, out=pix)
+            nf = px.numel() // nH
+            pp.process(px[: nf * nH], wH, HEIGHT, 0.0, 0.1, PostProcessFlags(autoshift=True, lowpass_before_sync=True, superresolution=True),
+                       out=frames_out[: nf * nH], want_results=False)
+            return nf
+        res["_round_trip"] = round_trip
+        one[0], one[1], one[2] = one_ms, err, 1.0 if lags_equal else 0.0
+    # the frame rounds need every rank to take part in the stitch
+    nf = 0
+    for _ in range(2):
+        if rank == 0:
+            nf = res["_round_trip"]()
+        else:
+            grp.stitch(hop, sif)
+    barrier()
+    fe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in fe:
+        flush.zero_()
+        a.record()
+        if rank == 0:
+            nf = res["_round_trip"]()
+        else:
+            grp.stitch(hop, sif)
+        b.record()
+    barrier()
+    res.pop("_round_trip", None)
+    ft = torch.tensor([sum(a.elapsed_time(b) for a, b in fe) / len(fe)], device="cuda")
+    dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+    dist.all_reduce(one)
+    res.update({"one_gpu_ms": one[0].item(), "speedup_vs_one_gpu": one[0].item() / tms.item(),
+                "parity_vs_one_gpu_path": {"max_err_over_peak": one[1].item(), "lags_equal": bool(one[2].item() == 1.0), "bound": 1e-5},
+                "frames": {"frames_per_round": int(nf) if rank == 0 else None, "ms_per_round_stitch_plus_frames": ft.item(),
+                           "frames_per_s": (nf / (ft.item() * 1e-3)) if rank == 0 else None, "geometry": [int(2 * (H * FS / (FV * HEIGHT))), HEIGHT]}})
+    grp.lags()                                            # raises if any wait timed out
+    # ---- round 1's formulation as the baseline: one NCCL all-gather of the raw spectra, every rank derives every lag
+    try:
+        for _ in range(2):
+            superband.stitch_distributed(gpu, hop, sif)
+        barrier()
+        ne = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in ne:
+            flush.zero_()
+            a.record(); superband.stitch_distributed(gpu, hop, sif); b.record()
+        barrier()
+        nt = torch.tensor([sum(a.elapsed_time(b) for a, b in ne) / len(ne)], device="cuda")
+        dist.all_reduce(nt, op=dist.ReduceOp.MAX)
+        res["nccl_allgather_baseline_ms"] = nt.item()
+    except Exception as e:
+        res["nccl_allgather_baseline_ms"] = None; res["nccl_allgather_baseline_error"] = repr(e)[:160]
+    grp.close()
+    return res
 
 
 # --------------------------------------------------------------------------------------------------- reference arm

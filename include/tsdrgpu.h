@@ -304,6 +304,8 @@ TSDRGPU_API void tsdrgpu_superb_mgpu_destroy(tsdrgpu_superb_mgpu_t *g);
 TSDRGPU_API int  tsdrgpu_superb_mgpu_export(tsdrgpu_superb_mgpu_t *g, uint8_t handle[64]);
 TSDRGPU_API int  tsdrgpu_superb_mgpu_connect_ipc(tsdrgpu_superb_mgpu_t *g, const uint8_t *handles /* nranks x 64 bytes, rank-major */);
 TSDRGPU_API int  tsdrgpu_superb_mgpu_connect_local(tsdrgpu_superb_mgpu_t *const *all_ranks, int nranks);
+/* unmap the peers' windows; with one process per GPU: all ranks disconnect, synchronise among themselves, then destroy */
+TSDRGPU_API int  tsdrgpu_superb_mgpu_disconnect(tsdrgpu_superb_mgpu_t *g);
 /* every rank calls this once per stitch (same count_pairs / samples_in_frame), each on a stream of its own device; asynchronous.
  * The root's d_stream_out receives nranks * N magnitudes, N = fft_getrealsize(count_pairs) returned in *h_n. */
 TSDRGPU_API int  tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream, const float *d_hop, int count_pairs, int samples_in_frame,
@@ -369,6 +371,14 @@ TSDRGPU_API int  tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t
 /* superbandwidth mode (PARAM_AUTOCORR_SUPERRESOLUTION = 1; superb_run, superbandwidth.c:179-254) retunes the front end
  * between hops through this callback; without it the hops are recorded at one frequency */
 TSDRGPU_API int  tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb);
+/* superbandwidth with ONE HOP PER GPU (tsdrgpu_superb_mgpu_*): devices[0] = the pipeline's own device, n in {2, 4, 8} hops =
+ * devices of this node with peer access; hop i is recorded into device i's memory and transformed there, device 0 receives the
+ * stitched magnitude stream and makes the frames.  n <= 1: back to 4 hops on one GPU (the reference's SUPER_HOPS_TO_MAKE). */
+TSDRGPU_API int  tsdrgpu_pipeline_set_superb_devices(tsdrgpu_pipeline_t *p, const int *devices, int n);
+/* Page-lock the caller's sample buffers in place (cudaHostRegister) once the same buffer has been handed to process() three
+ * times, so that pageable plugin memory crosses PCIe by direct DMA.  Off by default: only for callers that keep their buffer
+ * mapped for the whole run (the reference's plugins malloc once per tsdrplugin_readasync); released at destroy. */
+TSDRGPU_API int  tsdrgpu_pipeline_set_host_registration(tsdrgpu_pipeline_t *p, int on);
 TSDRGPU_API int  tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff);
 /* deliver final pixels.  mode 1: the frame callback's buffer holds w*h int32 pixels of the JNI glue's
  * float->ARGB rule (TSDRLibraryNDK.c:222-283) instead of floats (same size, so the callback type is unchanged: cast it);

@@ -125,6 +125,7 @@ _SIGS = {
     "tsdrgpu_superb_mgpu_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_superb_mgpu_connect_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_superb_mgpu_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "tsdrgpu_superb_mgpu_disconnect": (C.c_int, [C.c_void_p]),
     "tsdrgpu_superb_mgpu_stitch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32)]),
     "tsdrgpu_superb_mgpu_lags": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "tsdrgpu_pipeline_create": (C.c_int, [C.c_void_p, C.POINTER(PipelineConfig), FRAME_CB, VALUE_CB, PLOT_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -138,6 +139,8 @@ _SIGS = {
     "tsdrgpu_pipeline_set_samplerate": (C.c_int, [C.c_void_p, C.c_uint32]),
     "tsdrgpu_pipeline_set_retune": (C.c_int, [C.c_void_p, RETUNE_CB]),
     "tsdrgpu_pipeline_set_motionblur": (C.c_int, [C.c_void_p, C.c_float]),
+    "tsdrgpu_pipeline_set_host_registration": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsdrgpu_pipeline_set_superb_devices": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]),
     "tsdrgpu_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tsdrgpu_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_ipc_release": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -39,7 +39,7 @@ extern thread_local char g_tsdrgpu_err[512];
 
 static inline int tsdrgpu_fail(tsdrgpu_ctx_t *ctx, int code, const char *what, cudaError_t e, const char *file, int line) {
 	char *dst = ctx ? ctx->err : g_tsdrgpu_err;
-	if (e != cudaSuccess) snprintf(dst, 512, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+	if (e != cudaSuccess) { snprintf(dst, 512, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line); cudaGetLastError(); /* reported here: do not let it resurface at the next launch check */ }
 	else snprintf(dst, 512, "%s (%s:%d)", what, file, line);
 	return code;
 }

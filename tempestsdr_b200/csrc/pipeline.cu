@@ -151,7 +151,14 @@ struct tsdrgpu_pipeline {
 	tsdrgpu_frd *frd; float *d_capture[2]; size_t cap_size[2], cap_fill; int cap_phase; uint32_t cap_rate;
 	double *h_plot_frame[2], *h_plot_line[2]; size_t plot_cap; int plot_slot; int plot_busy[2];
 	// superbandwidth (superb_run's state machine, superbandwidth.c:179-264)
-	struct { int state; int buffid; long long to_gather, gathered, in_frame, to_pause; uint32_t rate; float *d_hops[4]; size_t hop_cap; float *d_out; size_t out_cap; cudaEvent_t ev; } sb;
+	struct {
+		int state; int buffid; long long to_gather, gathered, in_frame, to_pause; uint32_t rate;
+		int nhops;                                    // SUPER_HOPS_TO_MAKE (superbandwidth.c:22): 4, or the number of devices when the hops are sharded
+		float *d_hops[16]; size_t hop_cap; float *d_out; size_t out_cap; cudaEvent_t ev;
+		// one hop per GPU (tsdrgpu_pipeline_set_superb_devices): rank i records hop i on device dev[i]; rank 0 is this pipeline's device
+		int ndev; int dev[16]; tsdrgpu_ctx_t *rctx[16]; tsdrgpu_superb_mgpu_t *grp[16]; cudaStream_t rstream[16], rcopy[16]; cudaEvent_t rev[16];
+		void *rraw[16]; size_t rraw_cap[16]; uint32_t grp_pairs;
+	} sb;
 	uint32_t samplerate_real;
 	tsdrgpu_retune_cb retune_cb;
 	// delivery
@@ -164,6 +171,7 @@ struct tsdrgpu_pipeline {
 extern "C" {
 int tsdrgpu_resampler_create(tsdrgpu_ctx_t *, tsdrgpu_resampler **);
 }
+enum { SB_STOPPED = 0, SB_STARTING, SB_GATHERING, SB_PAUSE };
 
 static void geometry_locked(tsdrgpu_pipeline *p) {      // set_internal_samplerate, TSDRLibrary.c:540-550
 	double pr, pt; int w;
@@ -283,8 +291,11 @@ static int decim_set_elem(tsdrgpu_pipeline *p, int elem) {
 // A plugin hands over the same malloc'd buffer call after call (TSDRPlugin_RawFile.c:212, Mirics, SDRplay).  From pageable memory
 // cudaMemcpyAsync goes through the driver's staging buffer at a fraction of the link rate; once a buffer has come back
 // REG_AFTER times it is page-locked in place.  Buffers are released again when the run ends (tsdrgpu_pipeline_destroy).
-// TSDR_NO_HOST_REGISTER=1 switches this off (a plugin that unmaps and remaps its buffer at the same address in mid-run would
-// otherwise be read through the stale mapping).
+// OPT-IN (tsdrgpu_pipeline_set_host_registration): a registration pins the PHYSICAL pages behind an address range, so it is
+// only safe for a caller that keeps its buffer mapped for the whole run, as the reference's plugins do (one malloc per
+// tsdrplugin_readasync).  A caller that frees and re-allocates a buffer per call (numpy temporaries land on the same address
+// again and again) would be read through the stale mapping -- measured: wrong frames, then cudaErrorInvalidValue.  The C host
+// library switches it on for the plugins it loads (TSDR_NO_HOST_REGISTER=1 keeps it off).
 static const void *host_source(tsdrgpu_pipeline *p, const void *h, size_t bytes) {
 	constexpr int REG_AFTER = 3;
 	if (!p->host_register || bytes < 65536 || h == NULL) return h;
@@ -540,6 +551,8 @@ static int drain_blocks(tsdrgpu_pipeline *p) {
 
 extern "C" {
 
+static void superb_release_devices(tsdrgpu_pipeline *p);
+
 int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t *cfg, tsdrgpu_frame_cb frame_cb,
                             tsdrgpu_value_cb value_cb, tsdrgpu_plot_cb plot_cb, void *user, tsdrgpu_pipeline_t **out) {
 	BIND(ctx); ARG_TRY(ctx, cfg != NULL && out != NULL);
@@ -556,7 +569,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	p->d_pix = NULL; p->pix_cap = 0; p->pix_read = 0; p->pix_fill = 0; p->d_frames[0] = p->d_frames[1] = NULL; p->frames_cap[0] = p->frames_cap[1] = 0; p->out_phase = 0;
 	p->slot_cap = 0; p->d_capture[0] = p->d_capture[1] = NULL; p->cap_size[0] = p->cap_size[1] = 0; p->cap_fill = 0; p->cap_phase = 0; p->cap_rate = 0; p->plot_cap = 0; p->plot_slot = 0;
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->h_pll_rr[s] = NULL; p->slot_busy[s] = 0; }
-	p->host_register = getenv("TSDR_NO_HOST_REGISTER") ? 0 : 1;
+	p->host_register = 0;                               // opt-in: tsdrgpu_pipeline_set_host_registration
 	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
 	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
 	p->stop = 0; p->submitted = 0; p->delivered = 0; p->last_w = 0; p->last_h = 0;
@@ -607,7 +620,7 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	cudaSetDevice(p->ctx->device);
 	tsdrgpu_resampler_destroy(p->rs); tsdrgpu_framestage_destroy(p->fs); tsdrgpu_frd_destroy(p->frd);
 	for (auto &b : p->hostbufs) if (b.state == 1) { cudaHostUnregister(const_cast<void *>(b.base)); cudaGetLastError(); }
-	for (int i = 0; i < 4; i++) if (p->sb.d_hops[i]) cudaFree(p->sb.d_hops[i]);
+	superb_release_devices(p);
 	if (p->sb.d_out) cudaFree(p->sb.d_out);
 	cudaEventDestroy(p->sb.ev);
 	float *dev[] = {p->d_stage[0], p->d_stage[1], p->d_stage[2], p->d_stage[3], p->d_decim, p->d_pix, p->d_frames[0], p->d_frames[1], p->d_capture[0], p->d_capture[1]};
@@ -647,6 +660,33 @@ int tsdrgpu_pipeline_set_samplerate(tsdrgpu_pipeline_t *p, uint32_t samplerate) 
 	pthread_mutex_unlock(&p->geo_mu);
 	return TSDRGPU_OK;
 }
+// superbandwidth with one hop per GPU: devices[0] must be the pipeline's own device; n in {2, 4, 8} = number of hops.  n <= 1
+// returns to the one-GPU mode (4 hops).  Call while no superbandwidth round is in flight (before PARAM_AUTOCORR_SUPERRESOLUTION
+// is switched on).  The same device may be listed more than once (test set-ups on a single GPU).
+int tsdrgpu_pipeline_set_superb_devices(tsdrgpu_pipeline_t *p, const int *devices, int n) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
+	tsdrgpu_ctx_t *ctx = p->ctx;
+	BIND(ctx);
+	CU_TRY(ctx, cudaStreamSynchronize(p->s_main));
+	superb_release_devices(p);
+	p->sb.state = SB_STOPPED;
+	if (n <= 1) return TSDRGPU_OK;
+	ARG_TRY(ctx, devices != NULL && (n == 2 || n == 4 || n == 8) && devices[0] == ctx->device);
+	p->sb.rctx[0] = ctx; p->sb.dev[0] = ctx->device; p->sb.rstream[0] = p->s_main; p->sb.rcopy[0] = p->s_copy;
+	for (int i = 1; i < n; i++) {
+		int rc = tsdrgpu_create(&p->sb.rctx[i], devices[i]);
+		if (rc) { snprintf(ctx->err, sizeof ctx->err, "%s", tsdrgpu_last_error(NULL)); p->sb.ndev = i; superb_release_devices(p); return rc; }
+		p->sb.dev[i] = devices[i];
+		cudaSetDevice(devices[i]);
+		cudaStreamCreateWithFlags(&p->sb.rstream[i], cudaStreamNonBlocking);
+		cudaStreamCreateWithFlags(&p->sb.rcopy[i], cudaStreamNonBlocking);
+		cudaEventCreateWithFlags(&p->sb.rev[i], cudaEventDisableTiming);
+	}
+	p->sb.ndev = n;
+	CU_TRY(ctx, cudaSetDevice(ctx->device));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_pipeline_set_host_registration(tsdrgpu_pipeline_t *p, int on) { if (!p) return TSDRGPU_EINVAL; p->host_register = on != 0; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_retune(tsdrgpu_pipeline_t *p, tsdrgpu_retune_cb cb) { if (!p) return TSDRGPU_EINVAL; p->retune_cb = cb; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_motionblur(tsdrgpu_pipeline_t *p, float coeff) { if (!p) return TSDRGPU_EINVAL; p->motionblur = coeff; return TSDRGPU_OK; }
 int tsdrgpu_pipeline_set_output_argb(tsdrgpu_pipeline_t *p, int mode, int inverted) { if (!p) return TSDRGPU_EINVAL; p->argb_mode = mode != 0; p->argb_inverted = inverted != 0; return TSDRGPU_OK; }
@@ -671,7 +711,6 @@ int tsdrgpu_pipeline_stats(tsdrgpu_pipeline_t *p, tsdrgpu_pipeline_stats_t *out)
 // retune), aligned, and stitched into one 4x-rate signal that then flows through the normal decimator / frame stages.
 // The reference does the stitch on a helper thread (~3 s of CPU FFTs); here it runs on the GPU inside the call that
 // completes the last hop (a few ms), so its output appears one process() call earlier.  Everything else is the same.
-enum { SB_STOPPED = 0, SB_STARTING, SB_GATHERING, SB_PAUSE };
 static void superb_stop(tsdrgpu_pipeline *p) {                  // superbandwidth.c:256-264
 	if (p->sb.state == SB_STOPPED) return;
 	p->sb.state = SB_STOPPED;
@@ -693,20 +732,55 @@ static int raw_reserve(tsdrgpu_pipeline *p, int ss, size_t bytes) {
 	return TSDRGPU_OK;
 }
 
+// the devices of the sharded mode own contexts, streams and (once the hop size is known) the superbandwidth group
+static void superb_release_devices(tsdrgpu_pipeline *p) {
+	for (int i = 0; i < p->sb.ndev; i++) {
+		if (p->sb.grp[i]) { tsdrgpu_superb_mgpu_destroy(p->sb.grp[i]); p->sb.grp[i] = NULL; }
+	}
+	for (int i = 0; i < 16; i++) {
+		if (p->sb.d_hops[i]) { cudaSetDevice(i < p->sb.ndev ? p->sb.dev[i] : p->ctx->device); cudaFree(p->sb.d_hops[i]); p->sb.d_hops[i] = NULL; }
+		if (p->sb.rraw[i]) { cudaSetDevice(p->sb.dev[i]); cudaFree(p->sb.rraw[i]); p->sb.rraw[i] = NULL; p->sb.rraw_cap[i] = 0; }
+	}
+	for (int i = 1; i < p->sb.ndev; i++) {
+		cudaSetDevice(p->sb.dev[i]);
+		if (p->sb.rstream[i]) cudaStreamDestroy(p->sb.rstream[i]);
+		if (p->sb.rcopy[i]) cudaStreamDestroy(p->sb.rcopy[i]);
+		if (p->sb.rev[i]) cudaEventDestroy(p->sb.rev[i]);
+		if (p->sb.rctx[i]) tsdrgpu_destroy(p->sb.rctx[i]);
+		p->sb.rstream[i] = NULL; p->sb.rcopy[i] = NULL; p->sb.rev[i] = NULL; p->sb.rctx[i] = NULL;
+	}
+	p->sb.ndev = 0; p->sb.rate = 0;
+	cudaSetDevice(p->ctx->device);
+}
+
 static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t items_count, int64_t dropped) {
 	tsdrgpu_ctx_t *ctx = p->ctx;
 	int rc;
+	const int H = p->sb.ndev > 1 ? p->sb.ndev : 4;                    // SUPER_HOPS_TO_MAKE
+	const bool sharded = p->sb.ndev > 1;
 	if (p->sb.state == SB_STOPPED) p->sb.state = SB_STARTING;
 	if (p->sb.state == SB_STARTING) {
 		p->sb.buffid = 0; p->sb.gathered = 0;
-		if (p->samplerate_real != p->sb.rate) {
-			p->sb.rate = p->samplerate_real;
+		if (p->samplerate_real != p->sb.rate || p->sb.nhops != H) {
+			p->sb.rate = p->samplerate_real; p->sb.nhops = H;
 			pthread_mutex_lock(&p->geo_mu); const double fv = p->refreshrate; pthread_mutex_unlock(&p->geo_mu);
 			p->sb.in_frame = (long long) (p->samplerate_real / fv);
 			p->sb.to_gather = 10 * p->sb.in_frame;                    // SUPER_SAMPLES_TO_RECORD
 			p->sb.to_pause = (long long) (0.5 * p->samplerate_real);   // SUPER_SECS_TO_PAUSE
 			CU_TRY(ctx, cudaStreamSynchronize(p->s_main));
-			for (int i = 0; i < 4; i++) { if (p->sb.d_hops[i]) CU_TRY(ctx, cudaFree(p->sb.d_hops[i])); CU_TRY(ctx, cudaMalloc(&p->sb.d_hops[i], sizeof(float) * 2 * (size_t) p->sb.to_gather)); }
+			for (int i = 0; i < 16; i++) if (p->sb.d_hops[i]) { CU_TRY(ctx, cudaSetDevice(sharded && i < H ? p->sb.dev[i] : ctx->device)); CU_TRY(ctx, cudaFree(p->sb.d_hops[i])); p->sb.d_hops[i] = NULL; }
+			for (int i = 0; i < H; i++) {
+				CU_TRY(ctx, cudaSetDevice(sharded ? p->sb.dev[i] : ctx->device));
+				CU_TRY(ctx, cudaMalloc(&p->sb.d_hops[i], sizeof(float) * 2 * (size_t) p->sb.to_gather));
+			}
+			CU_TRY(ctx, cudaSetDevice(ctx->device));
+			if (sharded) {                                            // (re)build the group for this hop size
+				for (int i = 0; i < H; i++) if (p->sb.grp[i]) { tsdrgpu_superb_mgpu_destroy(p->sb.grp[i]); p->sb.grp[i] = NULL; }
+				for (int i = 0; i < H; i++)
+					if ((rc = tsdrgpu_superb_mgpu_create(p->sb.rctx[i], H, i, 0, (uint32_t) p->sb.to_gather, &p->sb.grp[i]))) { snprintf(ctx->err, sizeof ctx->err, "%s", tsdrgpu_last_error(p->sb.rctx[i])); return rc; }
+				if ((rc = tsdrgpu_superb_mgpu_connect_local(p->sb.grp, H))) { snprintf(ctx->err, sizeof ctx->err, "%s", tsdrgpu_last_error(p->sb.rctx[0])); return rc; }
+				CU_TRY(ctx, cudaSetDevice(ctx->device));
+			}
 		}
 		p->sb.state = SB_GATHERING;
 	}
@@ -719,46 +793,75 @@ static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t 
 	const long long now = (long long) (items_count / 2);
 	const long long take = (p->sb.gathered + now < p->sb.to_gather) ? now : (p->sb.to_gather - p->sb.gathered);
 	if (take > 0) {
-		CU_TRY(ctx, cudaStreamWaitEvent(p->s_copy, p->sb.ev, 0));            // the last stitch has finished reading the hop buffers
-		float *hop = p->sb.d_hops[p->sb.buffid] + 2 * p->sb.gathered;
+		const int b = p->sb.buffid;
+		float *hop = p->sb.d_hops[b] + 2 * p->sb.gathered;
 		const size_t bytes = fmt_bytes(fmt) * 2 * (size_t) take;
-		if (fmt == TSDRGPU_FMT_FLOAT) CU_TRY(ctx, cudaMemcpyAsync(hop, h_iq, bytes, cudaMemcpyHostToDevice, p->s_copy));
-		else {
-			if ((rc = raw_reserve(p, 0, bytes))) return rc;
-			CU_TRY(ctx, cudaMemcpyAsync(p->d_raw[0], h_iq, bytes, cudaMemcpyHostToDevice, p->s_copy));
-			pl_convert<<<1024, 256, 0, p->s_copy>>>(p->d_raw[0], hop, 2 * (size_t) take, fmt);
-			LAUNCH_CHECK(ctx);
+		// hop b lives on the device that will transform it: the block goes there straight from the host
+		cudaStream_t cs = (sharded && b > 0) ? p->sb.rcopy[b] : p->s_copy;
+		if (sharded && b > 0) CU_TRY(ctx, cudaSetDevice(p->sb.dev[b]));
+		cudaError_t e = cudaStreamWaitEvent(cs, (sharded && b > 0) ? p->sb.rev[b] : p->sb.ev, 0);     // the last stitch has finished reading the hop buffer
+		if (e == cudaSuccess) {
+			if (fmt == TSDRGPU_FMT_FLOAT) e = cudaMemcpyAsync(hop, h_iq, bytes, cudaMemcpyHostToDevice, cs);
+			else {
+				void **raw = (sharded && b > 0) ? &p->sb.rraw[b] : &p->d_raw[0];
+				size_t *cap = (sharded && b > 0) ? &p->sb.rraw_cap[b] : &p->raw_cap[0];
+				if (*cap < bytes) { cudaStreamSynchronize(cs); if (*raw) cudaFree(*raw); *raw = NULL; e = cudaMalloc(raw, bytes + bytes / 2); *cap = (e == cudaSuccess) ? bytes + bytes / 2 : 0; }
+				if (e == cudaSuccess) e = cudaMemcpyAsync(*raw, h_iq, bytes, cudaMemcpyHostToDevice, cs);
+				if (e == cudaSuccess) { pl_convert<<<1024, 256, 0, cs>>>(*raw, hop, 2 * (size_t) take, fmt); ctx->launches++; e = cudaGetLastError(); }
+			}
 		}
-		CU_TRY(ctx, cudaStreamSynchronize(p->s_copy));
+		const cudaError_t e2 = cudaStreamSynchronize(cs);            // the plugin's buffer has been read, whatever happened
+		cudaSetDevice(ctx->device);
+		if (e != cudaSuccess || e2 != cudaSuccess) return tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "H2D of a superbandwidth hop block", e != cudaSuccess ? e : e2, __FILE__, __LINE__);
 		p->stats.h2d_bytes += bytes;
 	}
 	p->sb.gathered += take;
 	if (p->sb.gathered < p->sb.to_gather) return TSDRGPU_OK;
 	const long long count_pairs = p->sb.gathered;
 	p->sb.buffid++; p->sb.gathered = 0;
-	if (p->sb.buffid < 4) {
-		if (p->retune_cb) p->retune_cb((int32_t) ((p->sb.buffid - 2) * (long long) p->sb.rate), p->user);    // shiftfreq, superbandwidth.c:241
+	if (p->sb.buffid < H) {
+		if (p->retune_cb) p->retune_cb((int32_t) ((p->sb.buffid - H / 2) * (long long) p->sb.rate), p->user);    // shiftfreq, superbandwidth.c:241
 		p->sb.state = SB_PAUSE;
 		return TSDRGPU_OK;
 	}
-	// all hops recorded: align + stitch (superb_ondataready) and hand the 4x-rate signal to the decimator
+	// all hops recorded: align + stitch (superb_ondataready) and hand the H-times-rate signal to the decimator
 	const unsigned long long N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
-	if (p->sb.out_cap < 8 * N) { CU_TRY(ctx, cudaStreamSynchronize(p->s_main)); if (p->sb.d_out) CU_TRY(ctx, cudaFree(p->sb.d_out)); CU_TRY(ctx, cudaMalloc(&p->sb.d_out, sizeof(float) * 8 * N)); p->sb.out_cap = 8 * N; }
-	int offs[4], total = 0;
-	if ((rc = tsdrgpu_superb_stitch(ctx, p->s_main, p->sb.d_hops, 4, (int) count_pairs, (int) p->sb.in_frame, p->sb.d_out, offs, &total))) return rc;
+	size_t total_samples = 0;
+	CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest));
+	if (!sharded) {
+		if (p->sb.out_cap < 2 * (size_t) H * N) { CU_TRY(ctx, cudaStreamSynchronize(p->s_main)); if (p->sb.d_out) CU_TRY(ctx, cudaFree(p->sb.d_out)); CU_TRY(ctx, cudaMalloc(&p->sb.d_out, sizeof(float) * 2 * (size_t) H * N)); p->sb.out_cap = 2 * (size_t) H * N; }
+		int offs[16], total = 0;
+		if ((rc = tsdrgpu_superb_stitch(ctx, p->s_main, p->sb.d_hops, H, (int) count_pairs, (int) p->sb.in_frame, p->sb.d_out, offs, &total))) return rc;
+		CU_TRY(ctx, cudaEventRecord(p->sb.ev, p->s_main));
+		float *where;
+		if ((rc = decim_set_elem(p, 2))) return rc;
+		if ((rc = decim_reserve(p, (size_t) total, &where))) return rc;
+		pl_copy_f32<<<2048, 256, 0, p->s_main>>>(p->sb.d_out, where, 2ull * (size_t) total);
+		LAUNCH_CHECK(ctx);
+		total_samples = (size_t) total;
+	} else {
+		// one hop per GPU: every rank runs its share on its own device; rank 0 (this pipeline's device, the main stream) receives
+		// the time-contiguous MAGNITUDE stream straight into the decimator input (superb_mgpu.cu)
+		float *where;
+		if ((rc = decim_set_elem(p, 1))) return rc;
+		if ((rc = decim_reserve(p, (size_t) H * N, &where))) return rc;
+		for (int r = 0; r < H; r++) {
+			uint32_t n = 0;
+			rc = tsdrgpu_superb_mgpu_stitch(p->sb.grp[r], r == 0 ? p->s_main : p->sb.rstream[r], p->sb.d_hops[r], (int) count_pairs, (int) p->sb.in_frame, r == 0 ? where : NULL, &n);
+			if (rc) { snprintf(ctx->err, sizeof ctx->err, "%s", tsdrgpu_last_error(p->sb.rctx[r])); cudaSetDevice(ctx->device); return rc; }
+			if (r > 0) { cudaSetDevice(p->sb.dev[r]); cudaEventRecord(p->sb.rev[r], p->sb.rstream[r]); }
+		}
+		CU_TRY(ctx, cudaSetDevice(ctx->device));
+		CU_TRY(ctx, cudaEventRecord(p->sb.ev, p->s_main));
+		ctx->launches += 0;
+		total_samples = (size_t) H * N;
+	}
 	p->stats.stitches++;
-	CU_TRY(ctx, cudaEventRecord(p->sb.ev, p->s_main));
 	pthread_mutex_lock(&p->geo_mu);
-	p->samplerate = 4 * p->sb.rate;                                   // set_internal_samplerate(tsdr, buffscount*samplerate)
+	p->samplerate = (uint32_t) H * p->sb.rate;                        // set_internal_samplerate(tsdr, buffscount*samplerate)
 	geometry_locked(p);
 	pthread_mutex_unlock(&p->geo_mu);
-	CU_TRY(ctx, cudaStreamSynchronize(p->s_ingest));
-	float *where;
-	if ((rc = decim_set_elem(p, 2))) return rc;
-	if ((rc = decim_reserve(p, (size_t) total, &where))) return rc;
-	pl_copy_f32<<<2048, 256, 0, p->s_main>>>(p->sb.d_out, where, 2ull * (size_t) total);
-	LAUNCH_CHECK(ctx);
-	p->decim_fill += (size_t) total;
+	p->decim_fill += total_samples;
 	p->sb.state = SB_STARTING;
 	return drain_blocks(p);
 }

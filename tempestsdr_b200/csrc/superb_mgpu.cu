@@ -186,6 +186,7 @@ struct tsdrgpu_superb_mgpu {
 	Peers peers; int connected; int ipc_opened[SBM_MAX_RANKS];
 	float2 *d_work, *d_p; void *d_part; int *d_lag;   // local temporaries
 	unsigned epoch; unsigned last_n;
+	unsigned prep_n, prep_nd;                         // transform sizes whose kernels and twiddle tables are known to be resident
 	long long timeout_cycles;
 };
 
@@ -218,6 +219,20 @@ int tsdrgpu_superb_mgpu_create(tsdrgpu_ctx_t *ctx, int nranks, int rank, int roo
 	const char *to = getenv("TSDRGPU_SBM_TIMEOUT_MS");
 	g->timeout_cycles = (long long) ((to ? atof(to) : 4000.0) * 1.9e6);      // ~1.9 GHz SM clock
 	*out = g;
+	return TSDRGPU_OK;
+}
+
+// unmap the peers' windows (one process per GPU: every rank disconnects, THEN every rank destroys -- a barrier of the caller's
+// choosing in between -- so that no window is freed while another process still has it mapped)
+int tsdrgpu_superb_mgpu_disconnect(tsdrgpu_superb_mgpu_t *g) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, g != NULL);
+	BIND(g->ctx);
+	CU_TRY(g->ctx, cudaDeviceSynchronize());
+	for (int q = 0; q < g->H; q++) {
+		if (g->ipc_opened[q] && g->peers.win[q]) { cudaIpcCloseMemHandle(g->peers.win[q]); g->ipc_opened[q] = 0; }
+		if (q != g->rank) g->peers.win[q] = NULL;
+	}
+	g->connected = 0;
 	return TSDRGPU_OK;
 }
 
@@ -280,6 +295,38 @@ int tsdrgpu_superb_mgpu_connect_local(tsdrgpu_superb_mgpu_t *const *all, int nra
 	return TSDRGPU_OK;
 }
 
+// Everything a stitch launches must already be loaded when the first flag-waiting kernel goes into the stream: with CUDA's lazy
+// module loading the FIRST launch of a kernel may synchronise the whole context, and a context that holds a kernel spinning
+// on a flag which only work not yet enqueued can raise would never drain (all ranks of one process on one device, or the
+// host thread that drives every device in turn).  So the transforms of this size run once on dummy data -- which also builds
+// their twiddle tables (cudaMalloc + cudaMemcpy) and sizes the scratch -- and the small kernels are touched by name.
+}  // extern "C"
+template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); cudaGetLastError(); }
+extern "C" {
+static int sbm_prepare(tsdrgpu_superb_mgpu *g, cudaStream_t stream, unsigned N, unsigned nd) {
+	if (g->prep_n == N && g->prep_nd == nd) return TSDRGPU_OK;
+	tsdrgpu_ctx_t *ctx = g->ctx;
+	float2 *V = reinterpret_cast<float2 *>(g->win + g->off_v);
+	int rc;
+	CU_TRY(ctx, cudaMemsetAsync(g->d_work, 0, sizeof(float2) * N, stream));
+	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, V, N, 0))) return rc;
+	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_p, nd, 0))) return rc;
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, g->d_p, nd, 1))) return rc;
+	if ((rc = tsdrgpu_fft_internal(ctx, stream, V, N, 1))) return rc;
+	int *tmp_lag = g->d_lag + 8;
+	if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, g->d_p, nd, g->d_part, tmp_lag))) return rc;
+	preload(sbm_sync); preload(sbm_abs_diff); preload(sbm_xcorr_pull); preload(sbm_abs_push);
+	switch (g->H) {
+	case 2: preload(sbm_mix<2>); preload(sbm_interleave<2>); break;
+	case 4: preload(sbm_mix<4>); preload(sbm_interleave<4>); break;
+	case 8: preload(sbm_mix<8>); preload(sbm_interleave<8>); break;
+	default: preload(sbm_mix<16>); preload(sbm_interleave<16>); break;
+	}
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	g->prep_n = N; g->prep_nd = nd;
+	return TSDRGPU_OK;
+}
+
 // Rank-local part of one stitch; every rank of the group calls it once per stitch with the same count_pairs / samples_in_frame,
 // each on a stream of its own device.  Asynchronous.  The root's d_stream_out receives nranks * N magnitudes (N returned in
 // *h_n), time-contiguous: sample H p + s is residue s, element p.  d_stream_out is ignored on the other ranks.
@@ -299,10 +346,11 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 	ARG_TRY(ctx, N <= g->n_max && N >= 64 && nd >= 8 && (N % (unsigned) g->H) == 0);
 	const int H = g->H, rank = g->rank;
 	const unsigned all = (H >= 32) ? 0xffffffffu : ((1u << H) - 1u);
+	int rc;
+	if ((rc = sbm_prepare(g, stream, N, nd))) return rc;
 	const unsigned epoch = ++g->epoch;
 	g->last_n = N;
 	float2 *D = reinterpret_cast<float2 *>(g->win + g->off_d), *X = reinterpret_cast<float2 *>(g->win + g->off_x), *V = reinterpret_cast<float2 *>(g->win + g->off_v);
-	int rc;
 	// ---- phase 1: local spectra into the own window
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, reinterpret_cast<const float2 *>(d_hop), X, N, 0))) return rc;
 	KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));

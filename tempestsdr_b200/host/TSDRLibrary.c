@@ -329,9 +329,20 @@ int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 	if ((status = tsdr_setgain(t, t->gain)) != TSDR_OK) goto end;
 	if (t->pixeltimeoversampletime <= 0) goto end;
 
+	/* TSDR_CUDA_DEVICES="0,1,2,3": superbandwidth mode records one hop per listed GPU and shards the stitch over them
+	 * (tsdrgpu_pipeline_set_superb_devices); the first entry is the device everything else runs on.  TSDR_CUDA_DEVICE=n: one GPU. */
+	int devlist[16], ndev = 0;
+	{
+		const char *list = getenv("TSDR_CUDA_DEVICES");
+		if (list) {
+			char *copy = strdup(list), *save = NULL;
+			for (char *tok = strtok_r(copy, ", ", &save); tok && ndev < 16; tok = strtok_r(NULL, ", ", &save)) devlist[ndev++] = atoi(tok);
+			free(copy);
+		}
+	}
 	if (!t->gpu) {
 		const char *dev = getenv("TSDR_CUDA_DEVICE");
-		if (tsdrgpu_create(&t->gpu, dev ? atoi(dev) : 0) != TSDRGPU_OK) {
+		if (tsdrgpu_create(&t->gpu, ndev > 0 ? devlist[0] : (dev ? atoi(dev) : 0)) != TSDRGPU_OK) {
 			status = fail(t, tsdrgpu_last_error(NULL), TSDR_CANNOT_OPEN_DEVICE);
 			t->gpu = NULL;
 			goto end;
@@ -353,6 +364,13 @@ int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 			goto end;
 		}
 		tsdrgpu_pipeline_set_retune(np, on_retune);
+		/* a plugin keeps its buffer for the whole tsdrplugin_readasync (TSDRPlugin_RawFile.c:212, 263): page-lock it in place */
+		tsdrgpu_pipeline_set_host_registration(np, getenv("TSDR_NO_HOST_REGISTER") ? 0 : 1);
+		if (ndev > 1 && tsdrgpu_pipeline_set_superb_devices(np, devlist, ndev) != TSDRGPU_OK) {
+			status = fail(t, tsdrgpu_last_error(t->gpu), TSDR_CANNOT_OPEN_DEVICE);
+			tsdrgpu_pipeline_destroy(np);
+			goto end;
+		}
 		/* opt-in extras, all off by default so that an unchanged host sees exactly the reference's callbacks */
 		{
 			const char *snr = getenv("TSDR_REPORT_SNR"), *mode = getenv("TSDR_DETECT_MODE"), *argb = getenv("TSDR_OUTPUT_ARGB");

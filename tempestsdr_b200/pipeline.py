@@ -108,6 +108,11 @@ class Pipeline:
     def set_resolution(self, height: int, refreshrate: float) -> None:
         N.check(self._lib.tsdrgpu_pipeline_set_resolution(self._h, height, refreshrate), self._ctx)
 
+    def set_superb_devices(self, devices) -> None:
+        """Superbandwidth mode with one hop per GPU: devices[0] is this pipeline's device, len(devices) in {2, 4, 8} = hops."""
+        arr = (C.c_int * len(devices))(*devices)
+        N.check(self._lib.tsdrgpu_pipeline_set_superb_devices(self._h, arr, len(devices)), self._ctx)
+
     def set_motionblur(self, coeff: float) -> None:
         N.check(self._lib.tsdrgpu_pipeline_set_motionblur(self._h, coeff), self._ctx)
 

@@ -210,6 +210,7 @@ class SuperbGroup:
         dist.all_gather_object(handles, bytes(handle), group=group)
         blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
         ctx.chk(ctx._lib.tsdrgpu_superb_mgpu_connect_ipc(g._h, blob))
+        g._spans_processes = True
         dist.barrier(group=group)
         return g
 
@@ -239,13 +240,20 @@ class SuperbGroup:
         self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_lags(self._h, self.ctx.stream, lags, C.byref(status)))
         return list(lags)
 
-    def close(self):
+    def close(self, group=None):
+        """Collective when the group spans processes: everybody unmaps, a barrier, everybody frees."""
         if getattr(self, "_h", None):
+            self.ctx._lib.tsdrgpu_superb_mgpu_disconnect(self._h)
+            if getattr(self, "_spans_processes", False):
+                import torch.distributed as dist
+                dist.barrier(group=group)
             self.ctx._lib.tsdrgpu_superb_mgpu_destroy(self._h)
             self._h = None
 
     def __del__(self):
         try:
-            self.close()
+            if getattr(self, "_h", None):
+                self.ctx._lib.tsdrgpu_superb_mgpu_destroy(self._h)
+                self._h = None
         except Exception:
             pass

@@ -443,8 +443,8 @@ def test_superbandwidth_one_hop_per_rank_on_one_device(H):
     spectrum, all-to-all mix, residue inverse, |.| into the root's slots, interleave -- with its flag synchronisation, on a
     single device (tests/sbm_one_device.py; a process of its own so that every rank's stream gets a hardware queue of its own)."""
     import subprocess, sys
-    r = subprocess.run([sys.executable, "-m", "tests.sbm_one_device", str(H)], capture_output=True, text=True, timeout=240,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32"))
+    r = subprocess.run([sys.executable, "-m", "tests.sbm_one_device", str(H)], capture_output=True, text=True, timeout=120,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", TSDRGPU_SBM_TIMEOUT_MS="1500"))
     assert r.returncode == 0 and "sbm ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
 
 

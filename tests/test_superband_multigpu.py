@@ -28,7 +28,7 @@ def _worker(rank, world, port, q):
     ctx = api.Context(rank)
     res, lags, n = superband.stitch_distributed(ctx, torch.from_numpy(hops[rank]).cuda(), sif)
     ok, msg = True, ""
-    if world in (2, 4):      # the reference stitches `world` hops into a world*N-point inverse (needs a power of two)
+    if world in (2, 4, 8):   # the reference stitches `world` hops into a world*N-point inverse (needs a power of two)
         want, offs = orc.best().superb_ondataready(hops, sif)
         ok = [2 * l for l in lags] == list(offs)
         got = res.cpu().numpy().reshape(-1, 2)
@@ -52,11 +52,28 @@ def _worker(rank, world, port, q):
         msg += f" fused_same={same}"
         dist.barrier()                                     # nobody starts overwriting buffers that a slower rank still reads
     ex.close()
+    # ---- the product path: tsdrgpu_superb_mgpu_* (csrc/superb_mgpu.cu) with the windows mapped across the processes through CUDA
+    # IPC.  Against superb_ondataready + am_demod of the reference: lags exact, magnitudes to 1e-5 of the peak; two stitches.
+    grp = superband.SuperbGroup.for_process_group(ctx, pairs)
+    want, offs = orc.best().superb_ondataready(hops, sif)
+    want_mag = orc.best().am_demod(want)
+    for rnd in range(2):
+        out = grp.stitch(torch.from_numpy(hops[rank]).cuda(), sif)
+        new_lags = grp.lags()
+        good = [2 * l for l in new_lags] == [int(o) for o in offs]
+        if rank == 0:
+            err = float(np.max(np.abs(out.cpu().numpy() - want_mag)) / np.max(np.abs(want_mag)))
+            good = good and err <= 1e-5
+            msg += f" mgpu[{rnd}] err={err:.3g}"
+        ok = ok and good
+        msg += f" mgpu[{rnd}] lags_ok={good}"
+        dist.barrier()
+    grp.close()
     q.put((rank, ok, msg))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_one_hop_per_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
