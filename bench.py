@@ -528,7 +528,7 @@ def run_ours(args):
         "fs_collapse": 4 * n_pix, "fs_shift": 8 * n_pix, "demod_kernel": 12 * pairs,
         "fft_pass_kernel": FFT_BYTES_PER_CAPTURE(NFFT) * prof_caps / max(1.0, prof.get("fft_pass_kernel", (0, 4 * prof_batches))[1] / prof_batches),
     }
-    alg.update({k: v * prof_caps for k, v in FINISH_BYTES(NFFT).items()})
+    alg.update({k: v * prof_caps for k, v in FINISH_BYTES(NFFT, int(FS / 55.0) - int(FS / 87.0) + int(FS / (590 * 55.0)) - int(FS / (1500 * 87.0))).items()})
     label = {"rs_main": "rs_main<IQ> (fused demod+resample)", "fft_pass_kernel": "fft_pass_kernel (one pass over every capture of the batch)"}
     total_prof = sum(t for t, _ in prof.values()) or 1.0
     kernels = {k: {"ms_per_batch": t / prof_batches, "launches_per_batch": c / prof_batches, "share": t / total_prof} for k, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
@@ -606,8 +606,10 @@ def FFT_BYTES_PER_CAPTURE(n, passes=2):
     return 2 * passes * 8 * n
 
 
-def FINISH_BYTES(n):
-    return {"k_real_fwd_finish": 8 * n, "k_real_inv_finish": 12 * n}
+def FINISH_BYTES(n, window_lags=None):
+    """forward finish: N/2 complex in, N reals out; inverse finish: z[k], z[N/2-k] and one table entry in, y[k] out -- for every
+    lag (12 N), or only for the lags of the frame-rate detector's two windows"""
+    return {"k_real_fwd_finish": 8 * n, "k_real_inv_finish": 12 * n if window_lags is None else 32 * window_lags}
 
 
 def autocorr_sweep(gpu, torch):
@@ -665,24 +667,26 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
     offs = [0] + [131 + 977 * q for q in range(1, H)]
     hop_of = lambda q: src[2 * offs[q]: 2 * (offs[q] + hop_pairs)].contiguous()
     hop = hop_of(rank)
+    hop0 = hop_of(0)                                      # the alignment reference, kept on every device (the pipeline copies hop 0 to all GPUs at ingest)
     flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")            # 256 MB > L2
     grp = superband.SuperbGroup.for_process_group(gpu, hop_pairs)
     n_fft = gpu.fft_getrealsize(hop_pairs)
     out = torch.empty(H * n_fft, dtype=torch.float32, device="cuda") if rank == 0 else None
     for _ in range(3):
-        grp.stitch(hop, sif, out=out)
+        grp.stitch(hop, sif, out=out, hop0=hop0)
     lags = grp.lags()
     barrier()
     reps = 10
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for a, b in evs:
         flush.zero_()
-        a.record(); grp.stitch(hop, sif, out=out); b.record()
+        a.record(); grp.stitch(hop, sif, out=out, hop0=hop0); b.record()
     barrier()
     tms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / reps], device="cuda")
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     res = {"hops": H, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": H * n_fft / (tms.item() * 1e-3) / 1e6,
            "lags": lags, "l2_flushed_between_repetitions": True,
+           "resident_before_the_timed_region": "hop q on GPU q, plus a copy of hop 0 (the alignment reference) on every GPU, as the pipeline leaves them",
            "exchange": "peer-memory windows (CUDA IPC over NVLink), flags in peer memory; no collective library on the data path",
            "nvlink_bytes_received_per_rank": int(8 * (n_fft // 2) * (1 if rank else 0) + 2 * 8 * n_fft * (H - 1) // H),
            "nvlink_bytes_received_by_root_for_stream": int(4 * n_fft * (H - 1))}
@@ -713,7 +717,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
         frames_out = torch.empty(((pix.numel() // nH) + 1) * nH, dtype=torch.float32, device="cuda")
 
         def round_trip():
-            grp_out = grp.stitch(hop, sif, out=out)
+            grp_out = grp.stitch(hop, sif, out=out, hop0=hop0)
             px = rs.process(grp_out, (blockH, nblk), upH, float(H * FS), in_is_iq=False, out=pix)
             nf = px.numel() // nH
             pp.process(px[: nf * nH], wH, HEIGHT, 0.0, 0.1, PostProcessFlags(autoshift=True, lowpass_before_sync=True, superresolution=True),
@@ -727,7 +731,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
         if rank == 0:
             nf = res["_round_trip"]()
         else:
-            grp.stitch(hop, sif)
+            grp.stitch(hop, sif, hop0=hop0)
     barrier()
     fe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
     for a, b in fe:
@@ -736,7 +740,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
         if rank == 0:
             nf = res["_round_trip"]()
         else:
-            grp.stitch(hop, sif)
+            grp.stitch(hop, sif, hop0=hop0)
         b.record()
     barrier()
     res.pop("_round_trip", None)

@@ -307,9 +307,11 @@ TSDRGPU_API int  tsdrgpu_superb_mgpu_connect_local(tsdrgpu_superb_mgpu_t *const 
 /* unmap the peers' windows; with one process per GPU: all ranks disconnect, synchronise among themselves, then destroy */
 TSDRGPU_API int  tsdrgpu_superb_mgpu_disconnect(tsdrgpu_superb_mgpu_t *g);
 /* every rank calls this once per stitch (same count_pairs / samples_in_frame), each on a stream of its own device; asynchronous.
+ * d_hop: this rank's hop.  d_hop0: a copy of hop 0 (the alignment reference, superbandwidth.c:133) on THIS device, or NULL --
+ * then its difference spectrum is read from rank 0 over NVLink after one more barrier; either all ranks pass it or none.
  * The root's d_stream_out receives nranks * N magnitudes, N = fft_getrealsize(count_pairs) returned in *h_n. */
-TSDRGPU_API int  tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream, const float *d_hop, int count_pairs, int samples_in_frame,
-                                            float *d_stream_out, uint32_t *h_n);
+TSDRGPU_API int  tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream, const float *d_hop, const float *d_hop0, int count_pairs,
+                                            int samples_in_frame, float *d_stream_out, uint32_t *h_n);
 /* lags (complex samples) of the last stitch as every rank published them, and the status word (0 = fine); synchronises `stream` */
 TSDRGPU_API int  tsdrgpu_superb_mgpu_lags(tsdrgpu_superb_mgpu_t *g, void *stream, int *h_lags, uint32_t *h_status);
 

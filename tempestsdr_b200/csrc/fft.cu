@@ -43,6 +43,8 @@ struct FftPass {
 	const float2 *tw_step;                              // host-built W_M^(col (L/8) j), [col][8]; NULL: compute every twiddle
 	float2 *fan[16]; int nfan;                          // FAN kernels: the last stage stores to every fan[p] + offset instead of `out`
 	int exact0;                                         // the first three layers of this pass have eps = 0: plain DFT-8
+	int conj_in, conj_out;                              // inverse transforms: conjugate on load (first pass) / on store (last pass)
+	float *abs_real;                                    // with out_abs: |.| goes here as float32 (same element index) instead of (|.|, 0) to `out` -- may be peer memory
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -55,8 +57,25 @@ __device__ __forceinline__ float2 tw_lookup(const float2 *__restrict__ table, un
 }
 
 // ---- in-register small DFTs (natural order in, natural order out) -------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed single precision (sm_100: add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2): one instruction works on both halves of
+// a complex value held in an aligned register pair.  The pass kernel is bound by issue slots, not by the FP pipes, so halving
+// the arithmetic instruction count is what counts: a complex add is 1 instruction instead of 2, a complex multiply by a
+// twiddle kept in both forms (c, s) and (-s, c) is 2 instead of 4 (the scalar broadcast of x.x / x.y is an operand modifier).
+__device__ __forceinline__ unsigned long long pk2(float2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 up2(unsigned long long r) { float2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a; }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return up2(r); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {      // a - b = b * (-1, -1) + a
+	unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(b)), "l"(pk2(make_float2(-1.0f, -1.0f))), "l"(pk2(a))); return up2(r);
+}
+// x * w with w given as (c, s) and its quarter turn (-s, c):  (x.x c - x.y s, x.x s + x.y c)
+__device__ __forceinline__ float2 cmulp(float2 x, float4 w) {
+	unsigned long long t, r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk2(make_float2(x.y, x.y))), "l"(pk2(make_float2(w.z, w.w))));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(make_float2(x.x, x.x))), "l"(pk2(make_float2(w.x, w.y))), "l"(t));
+	return up2(r);
+}
+__device__ __forceinline__ float4 twform(float2 w) { return make_float4(w.x, w.y, -w.y, w.x); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(make_float2(s, s)))); return up2(r); }
 // multiply by -i (forward) or +i (inverse)
 __device__ __forceinline__ float2 rot90(float2 a, bool inverse) { return inverse ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
 
@@ -204,55 +223,51 @@ __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)
 __device__ __forceinline__ void sts2(unsigned addr, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
 __device__ __forceinline__ float2 lds2(unsigned addr) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory"); return v; }
 
-template <bool INV>
-__device__ __forceinline__ float2 twmul(float2 w, float2 x) {        // x * w (forward) or x * conj(w) (inverse)
-	if (INV) return make_float2(x.x * w.x + x.y * w.y, x.y * w.x - x.x * w.y);
-	return make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
-}
-template <bool INV>
-__device__ __forceinline__ void bf8(float2 *v, const float2 *__restrict__ tw /* = table + k - 1 */, int p) {
+// Butterflies exist in the FORWARD direction only.  An inverse transform is the conjugate of the forward transform of the
+// conjugated input -- conj(x conj(w)) = conj(x) w, and IEEE arithmetic is sign-symmetric -- so an inverse pass conjugates what it
+// loads from global memory in its first pass and what it stores in its last one (FftPass.conj_in / conj_out) and is otherwise
+// the same code.  Layer twiddles arrive as float4 (c, s, -s, c): one 16-byte load feeds the two packed instructions of cmulp.
+__device__ __forceinline__ void bf8(float2 *v, const float4 *__restrict__ tw /* = table + k - 1 */, int p) {
 	float2 a[4][2], b[2][2][2];
-	const float2 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
-	const float2 TC00 = __ldg(tw + 4 * p), TC10 = __ldg(tw + 5 * p), TC01 = __ldg(tw + 6 * p), TC11 = __ldg(tw + 7 * p);
+	const float4 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
+	const float4 TC00 = __ldg(tw + 4 * p), TC10 = __ldg(tw + 5 * p), TC01 = __ldg(tw + 6 * p), TC11 = __ldg(tw + 7 * p);
 	#pragma unroll
-	for (int r = 0; r < 4; r++) { const float2 hi = twmul<INV>(TA, v[r + 4]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
+	for (int r = 0; r < 4; r++) { const float2 hi = cmulp(v[r + 4], TA); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
 	#pragma unroll
 	for (int q0 = 0; q0 < 2; q0++) {
-		const float2 TB = q0 ? TB1 : TB0;
+		const float4 TB = q0 ? TB1 : TB0;
 		#pragma unroll
-		for (int m0 = 0; m0 < 2; m0++) { const float2 hi = twmul<INV>(TB, a[m0 + 2][q0]); b[m0][q0][0] = cadd(a[m0][q0], hi); b[m0][q0][1] = csub(a[m0][q0], hi); }
+		for (int m0 = 0; m0 < 2; m0++) { const float2 hi = cmulp(a[m0 + 2][q0], TB); b[m0][q0][0] = cadd(a[m0][q0], hi); b[m0][q0][1] = csub(a[m0][q0], hi); }
 	}
 	#pragma unroll
 	for (int q0 = 0; q0 < 2; q0++) {
 		#pragma unroll
 		for (int q1 = 0; q1 < 2; q1++) {
-			const float2 TC = q1 ? (q0 ? TC11 : TC01) : (q0 ? TC10 : TC00);
-			const float2 hi = twmul<INV>(TC, b[1][q0][q1]);
+			const float4 TC = q1 ? (q0 ? TC11 : TC01) : (q0 ? TC10 : TC00);
+			const float2 hi = cmulp(b[1][q0][q1], TC);
 			v[q0 + 2 * q1] = cadd(b[0][q0][q1], hi); v[q0 + 2 * q1 + 4] = csub(b[0][q0][q1], hi);
 		}
 	}
 }
-template <bool INV>
-__device__ __forceinline__ void bf4(float2 *v, const float2 *__restrict__ tw, int p) {
+__device__ __forceinline__ void bf4(float2 *v, const float4 *__restrict__ tw, int p) {
 	float2 a[2][2];
-	const float2 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
+	const float4 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
 	#pragma unroll
-	for (int r = 0; r < 2; r++) { const float2 hi = twmul<INV>(TA, v[r + 2]); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
+	for (int r = 0; r < 2; r++) { const float2 hi = cmulp(v[r + 2], TA); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
 	#pragma unroll
 	for (int q0 = 0; q0 < 2; q0++) {
-		const float2 hi = twmul<INV>(q0 ? TB1 : TB0, a[1][q0]);
+		const float2 hi = cmulp(a[1][q0], q0 ? TB1 : TB0);
 		v[q0] = cadd(a[0][q0], hi); v[q0 + 2] = csub(a[0][q0], hi);
 	}
 }
-template <bool INV>
-__device__ __forceinline__ void bf2(float2 *v, const float2 *__restrict__ tw, int p) {
-	const float2 hi = twmul<INV>(__ldg(tw + p), v[1]);
+__device__ __forceinline__ void bf2(float2 *v, const float4 *__restrict__ tw, int p) {
+	const float2 hi = cmulp(v[1], __ldg(tw + p));
 	const float2 lo = v[0];
 	v[0] = cadd(lo, hi); v[1] = csub(lo, hi);
 }
 
-template <int LOG2L, bool INV, bool FAN = false>
-__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float2 *__restrict__ stw) {
+template <int LOG2L, bool FAN = false>
+__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float4 *__restrict__ stw) {
 	extern __shared__ float2 s[];
 	constexpr int L = 1 << LOG2L, NST8 = LOG2L / 3, RL = LOG2L % 3;
 	constexpr int RLAST = (RL == 0) ? 8 : ((RL == 1) ? 2 : 4);
@@ -288,9 +303,13 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 				const float2 *gc = in + in_base + off;
 				#pragma unroll
 				for (int m = 0; m < 8; m++) v[m] = __ldg(gc + m * step);
+				if (P.conj_in) {
+					#pragma unroll
+					for (int m = 0; m < 8; m++) v[m].y = -v[m].y;
+				}
 			}
-			if (P.exact0) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]); dft8(u, INV); }     // layers with eps = 0: plain DFT-8
-			else bf8<INV>(v, stw - 1, 1);
+			if (P.exact0) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]); dft8(u, false); }     // layers with eps = 0: plain DFT-8
+			else bf8(v, stw - 1, 1);
 		}
 		if (NSTAGES > 1) {
 			if (active) {
@@ -313,7 +332,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 			#pragma unroll
 			for (int m = 0; m < 8; m++) v[m] = lds2(lr + (rb ^ (unsigned) (swz(m * L8) * 8)));
 			const int k = i & (p - 1);
-			bf8<INV>(v, stw + k - 1, p);
+			bf8(v, stw + k - 1, p);
 			const int j = ((i - k) << 3) + k;
 			const unsigned lw = dst + (unsigned) (c * L) * 8u, wb = (unsigned) (swz(j) ^ xw) * 8u;
 			#pragma unroll
@@ -327,7 +346,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	const int T = blockDim.x;
 	const unsigned twmask = (unsigned) (P.tw_M - 1);
 	const float inv_M = P.tw_M ? 1.0f / (float) P.tw_M : 0.0f;       // a power of two: exact
-	float2 tw_base = make_float2(1.0f, 0.0f);
+	float4 tw_base4 = make_float4(1.0f, 0.0f, -0.0f, 1.0f);
 	#pragma unroll
 	for (int it = 0; it < NB; it++) {
 		const int widx = tid + it * T;
@@ -339,9 +358,9 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 			const unsigned lr = src + (unsigned) (c * L) * 8u, rb = (unsigned) (swz(i) ^ ((c << shb) & 15)) * 8u;
 			#pragma unroll
 			for (int m = 0; m < RLAST; m++) w[m] = lds2(lr + (rb ^ (unsigned) (swz(m * PL) * 8)));
-			if (RLAST == 8) bf8<INV>(w, stw + i - 1, PL);
-			else if (RLAST == 4) bf4<INV>(w, stw + i - 1, PL);
-			else bf2<INV>(w, stw + i - 1, PL);
+			if (RLAST == 8) bf8(w, stw + i - 1, PL);
+			else if (RLAST == 4) bf4(w, stw + i - 1, PL);
+			else bf2(w, stw + i - 1, PL);
 		}
 		float2 *o = gout + c * (int) P.out_cs;
 		const int ks = (int) P.out_ks;
@@ -353,13 +372,12 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 					const unsigned e = (col * (unsigned) i) & twmask;            // i == i0 in the first round
 					float sn, cs;
 					sincospif(-2.0f * ((float) e * inv_M), &sn, &cs);
-					tw_base = make_float2(cs, sn);
+					tw_base4 = make_float4(cs, sn, -sn, cs);
 				}
 				#pragma unroll
 				for (int m = 0; m < RLAST; m++) {
 					const float2 st = __ldg(P.tw_step + col * 8u + (unsigned) (it + NB * m));
-					const float2 tw = make_float2(tw_base.x * st.x - tw_base.y * st.y, tw_base.x * st.y + tw_base.y * st.x);
-					w[m] = twmul<INV>(tw, w[m]);
+					w[m] = cmulp(w[m], twform(cmulp(st, tw_base4)));
 				}
 			} else if (P.tw_M <= (1ull << 24)) {
 				#pragma unroll
@@ -368,7 +386,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 					const unsigned e = (col * (unsigned) k) & twmask;
 					float sn, cs;
 					sincospif(-2.0f * ((float) e * inv_M), &sn, &cs);
-					w[m] = twmul<INV>(make_float2(cs, sn), w[m]);
+					w[m] = cmulp(w[m], make_float4(cs, sn, -sn, cs));
 				}
 			} else {
 				#pragma unroll
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 					const unsigned long long e = ((unsigned long long) col * (unsigned long long) k) & (P.tw_M - 1);
 					double dsn, dcs;
 					sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs);
-					w[m] = twmul<INV>(make_float2((float) dcs, (float) dsn), w[m]);
+					w[m] = cmulp(w[m], make_float4((float) dcs, (float) dsn, -(float) dsn, (float) dcs));
 				}
 			}
 		}
@@ -463,6 +481,22 @@ __global__ void __launch_bounds__(256) k_real_inv_finish(const float2 *__restric
 		float2 x0, x1;
 		real_split(z[k], z[(half - k) & (half - 1)], make_float2(w.x, -w.y), x0, x1);
 		y[k] = x0; y[k + half] = x1;
+	}
+}
+
+// the same, but only the lags a caller will read: lags [lo0, hi0) and [lo1, hi1), all below `half` (the frame-rate detector's
+// two windows, frameratedetector.c:91-95): the kernel touches (hi0-lo0)+(hi1-lo1) lags instead of N
+__global__ void __launch_bounds__(256) k_real_inv_finish_win(const float2 *__restrict__ Z, long long z_bs, const float2 *__restrict__ last,
+                                                             unsigned half, float2 *__restrict__ Y, long long y_bs, unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1) {
+	const float2 *z = Z + (long long) blockIdx.y * z_bs;
+	float2 *y = Y + (long long) blockIdx.y * y_bs;
+	const unsigned n0 = hi0 - lo0, total = n0 + (hi1 - lo1);
+	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		const unsigned k = (t < n0) ? (lo0 + t) : (lo1 + (t - n0));
+		const float2 w = __ldg(last + k);
+		float2 x0, x1;
+		real_split(z[k], z[(half - k) & (half - 1)], make_float2(w.x, -w.y), x0, x1);
+		y[k] = x0;
 	}
 }
 
@@ -602,11 +636,11 @@ inline unsigned grid1d(unsigned long long n, int sm_count) {
 
 float2 *g_table[64] = {0};          // per device
 // per-pass layer-twiddle tables (see fft_pass_kernel), built on the host in double precision and cached
-struct StageTab { int device, log2L, l_base, pert; float2 *d; };
+struct StageTab { int device, log2L, l_base, pert; float4 *d; };
 std::vector<StageTab> g_stage_tabs;
 std::mutex g_tw_mu;
 
-int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all, const float2 **out) {
+int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all, const float4 **out) {
 	static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;      // opt out: the mathematically exact DFT
 	double eps[FFT_MAX_LOG2L + 1];
 	int pert = 0;
@@ -617,18 +651,19 @@ int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all
 	std::lock_guard<std::mutex> lock(g_tw_mu);
 	for (auto &t : g_stage_tabs) if (t.device == ctx->device && t.log2L == log2L && t.l_base == (pert ? l_base : -1) && t.pert == pert) { *out = t.d; return TSDRGPU_OK; }
 	const int L = 1 << log2L;
-	std::vector<float2> h((size_t) L);
+	std::vector<float4> h((size_t) L);                  // (c, s, -s, c): the twiddle and its quarter turn, one 16-byte load (cmulp)
 	for (int sidx = 0; sidx < log2L; sidx++) {
 		const int blk = 1 << sidx;
 		for (int K = 0; K < blk; K++) {
 			const double ang = -3.14159265358979323846 * ((double) K / (double) blk) * (1.0 + eps[sidx]);
-			h[(size_t) blk - 1 + K] = make_float2((float) cos(ang), (float) sin(ang));
+			const float c = (float) cos(ang), sn = (float) sin(ang);
+			h[(size_t) blk - 1 + K] = make_float4(c, sn, -sn, c);
 		}
 	}
-	h[(size_t) L - 1] = make_float2(1.0f, 0.0f);
+	h[(size_t) L - 1] = make_float4(1.0f, 0.0f, -0.0f, 1.0f);
 	StageTab t; t.device = ctx->device; t.log2L = log2L; t.l_base = pert ? l_base : -1; t.pert = pert;
-	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float2) * L));
-	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice));
+	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float4) * L));
+	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float4) * L, cudaMemcpyHostToDevice));
 	g_stage_tabs.push_back(t);
 	*out = t.d;
 	return TSDRGPU_OK;
@@ -665,8 +700,7 @@ int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
 	g_table[ctx->device] = t;
 	const int max_smem = (int) (2 * sizeof(float2) * FFT_MAX_ELEMS);     // ping-pong
 #define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
 	SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
 #undef SET_ATTR
 	return TSDRGPU_OK;
@@ -701,7 +735,7 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 		else KL(ctx, "fft_pass_kernel", stream, fft_pass_small<2><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse));
 		return TSDRGPU_OK;
 	}
-	const float2 *stw;
+	const float4 *stw;
 	{ int rc = stage_table(ctx, P.log2L, l_base, eps_all, &stw); if (rc) return rc; }
 	P.tw_step = NULL;
 	if (P.tw_M && P.tw_M <= (1ull << 24) && P.c_fast_out && P.log2L >= 3 && P.tw_lo == P.C && P.tw_cs == 1) {
@@ -713,8 +747,7 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	for (int sidx = 0; sidx < 3 && sidx < P.log2L; sidx++) if (eps_all && l_base + sidx < 40 && fabs(eps_all[l_base + sidx]) > 1e-10) P.exact0 = 0;
 	const size_t smem = sizeof(float2) * (size_t) total * (nstages >= 3 ? 2 : 1);
 	switch (P.log2L) {
-#define CASE(l) case l: if (inverse) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
-	                else if (P.nfan > 0) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
+#define CASE(l) case l: if (P.nfan > 0) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
 	                else KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false><<<grid, threads, smem, stream>>>(in, out, P, stw)); break
 	CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
 #undef CASE
@@ -729,6 +762,7 @@ struct FftOpts {
 	long long data_bs, scratch_bs, real_bs;   // distance between consecutive transforms in data (complex), scratch (complex), real_in (floats)
 	float2 *const *fan; int nfan;             // forward only: the final pass stores the result to every fan[p] (same layout as `data`) instead of `data`
 	const float2 *cplx_in; long long cplx_bs; // the first pass reads its (complex) input from here instead of `data` (which is then output only)
+	float *abs_real;                          // with out_abs (batch 1): the final pass stores |.| as float32 here (peer memory allowed) and leaves `data` alone
 };
 
 // N-point transform of `data` (complex, natural order) through `scratch`; result lands in `data`.
@@ -746,8 +780,9 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 	};
 	if (log2N <= FFT_MAX_LOG2L) {                       // one pass, one CTA
 		P.log2L = (int) log2N; P.C = 1; P.G_lo = 1; P.in_js = 1; P.out_ks = 1; P.scale = o.scale;
-		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs;
+		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs; P.abs_real = o.out_abs ? o.abs_real : NULL;
 		with_fan(P);
+		P.conj_in = P.conj_out = inverse ? 1 : 0;
 		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs, eps_all, 0);
 	}
 	int rc;
@@ -759,14 +794,16 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N2;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N2;
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
+		P.conj_in = inverse ? 1 : 0;
 		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 		FftPass Q; memset(&Q, 0, sizeof Q);
 		Q.log2L = (int) l2; Q.C = bundle_for((int) l2, N1, true); Q.c_fast_in = 0; Q.c_fast_out = 1;
 		Q.G_lo = (unsigned) (N1 / Q.C);
 		Q.in_lo = (long long) Q.C * (long long) N2; Q.in_cs = (long long) N2; Q.in_js = 1;
 		Q.out_lo = Q.C; Q.out_cs = 1; Q.out_ks = (long long) N1;
-		Q.scale = o.scale; Q.out_abs = o.out_abs;
+		Q.scale = o.scale; Q.out_abs = o.out_abs; Q.abs_real = o.out_abs ? o.abs_real : NULL;
 		with_fan(Q);
+		Q.conj_out = inverse ? 1 : 0;
 		return launch_pass(ctx, stream, scratch, data, Q, Q.G_lo, inverse, o.batch, o.scratch_bs, o.data_bs, eps_all, (int) l1);
 	}
 	// N = N1*N2*N3 ; n = N2N3 n1 + N3 n2 + n3 ; k = k1 + N1 k2 + N1N2 k3
@@ -779,6 +816,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N23;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N23;
 		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
+		P.conj_in = inverse ? 1 : 0;
 		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 	}
 	{   // pass B: for every k1, length N2 along stride N3, bundle over adjacent n3 (in place in scratch)
@@ -796,8 +834,9 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		Cc.G_lo = (unsigned) (N1 / Cc.C);                // g = k2 * G_lo + (k1 / C)
 		Cc.in_hi = (long long) N3; Cc.in_lo = (long long) Cc.C * (long long) N23; Cc.in_cs = (long long) N23; Cc.in_js = 1;
 		Cc.out_hi = (long long) N1; Cc.out_lo = Cc.C; Cc.out_cs = 1; Cc.out_ks = (long long) (N1 * N2);
-		Cc.scale = o.scale; Cc.out_abs = o.out_abs;
+		Cc.scale = o.scale; Cc.out_abs = o.out_abs; Cc.abs_real = o.out_abs ? o.abs_real : NULL;
 		with_fan(Cc);
+		Cc.conj_out = inverse ? 1 : 0;
 		return launch_pass(ctx, stream, scratch, data, Cc, (unsigned) (N2 * Cc.G_lo), inverse, o.batch, o.scratch_bs, o.data_bs, eps_all, (int) (l1 + l2));
 	}
 }
@@ -827,6 +866,17 @@ int tsdrgpu_fft_oop_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const floa
 	FftOpts o; memset(&o, 0, sizeof o); o.batch = 1; o.scale = inverse ? 1.0f : 1.0f / (float) n_pow2;
 	o.cplx_in = in; o.cplx_bs = 0;
 	return fft_run(ctx, stream, out, (float2 *) scratch, ilog2(n_pow2), inverse, o);
+}
+// inverse transform of `data` (n_pow2 complex, clobbered) whose final pass stores |y| as float32 straight into real_out (n_pow2
+// floats; peer memory allowed: the stores of the last butterflies ARE the transfer)
+int tsdrgpu_ifft_abs_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float *real_out, unsigned long long n_pow2) {
+	int rc = ensure_table(ctx, stream);
+	if (rc) return rc;
+	ARG_TRY(ctx, n_pow2 >= 8);
+	void *scratch;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * n_pow2, &scratch))) return rc;
+	FftOpts o; memset(&o, 0, sizeof o); o.batch = 1; o.scale = 1.0f; o.out_abs = true; o.abs_real = real_out;
+	return fft_run(ctx, stream, data, (float2 *) scratch, ilog2(n_pow2), 1, o);
 }
 // *d_result = index of the first maximum of |x[0..n)|; d_part: room for 2 * TSDRGPU_ARGMAX_PARTS 32-bit words
 int tsdrgpu_argmax_mag_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *x, unsigned n, void *d_part, int *d_result) {
@@ -885,8 +935,24 @@ static int last_stage_table(tsdrgpu_ctx_t *ctx, unsigned half, double eps, const
 // real; a real sequence of length N is a complex one of length N/2, one N/2-point transform + the reference's last radix-2
 // stage (k_real_*_finish) gives the N-point result.  profiles/studies/real_input_autocorr_study.py measures the only
 // approximation (the mirror identity under perturbed stage angles): 6.6e-10 of the zero-lag peak at 2^20, 7.9e-9 at 2^22.
+struct LagWindows { unsigned lo0, hi0, lo1, hi1; };      // only these lags of every answer are needed (all zero: every lag)
+
+// How many captures share one pair of work buffers.  The four passes and two finish steps of a capture hand N/2 complex
+// values from one to the next; with every capture of a big batch in flight at once those intermediates (8 N bytes per capture
+// and step) stream through HBM.  Processing the batch in groups whose two work buffers (2 x G x 4 N bytes) stay inside the
+// 126 MB L2 turns them into L2 traffic: HBM then sees the capture once on the way in and the requested lags on the way out.
+static unsigned autocorr_group(unsigned long long N, unsigned batch) {
+	const int forced = getenv("TSDRGPU_AUTOCORR_GROUP") ? atoi(getenv("TSDRGPU_AUTOCORR_GROUP")) : -1;       // experiment knob, read per call
+	if (forced == 0) return batch;
+	if (forced > 0) return (unsigned) forced < batch ? (unsigned) forced : batch;
+	const unsigned long long budget = 48ull << 20;       // bytes of L2 the two work buffers may take
+	unsigned long long g = budget / (8ull * N);
+	if (g < 1) g = 1;
+	return g < batch ? (unsigned) g : batch;
+}
+
 static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *ans, long long ans_bs, const float *d_real,
-                                      long long real_stride, unsigned long long N, unsigned batch, float2 *scratch) {
+                                      long long real_stride, unsigned long long N, unsigned batch, LagWindows win) {
 	const unsigned log2N = ilog2(N), half = (unsigned) (N >> 1);
 	double eps_all[40];
 	tsdrgpu_fft_reference_eps((int) log2N, 0, eps_all);
@@ -894,31 +960,43 @@ static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, f
 	const float2 *last;
 	int rc = last_stage_table(ctx, half, exact_dft ? 0.0 : eps_all[log2N - 1], &last);
 	if (rc) return rc;
-	const dim3 grid(grid1d(half, ctx->sm_count), batch);
-	// forward: Z = FFT_{N/2}(capture viewed as complex pairs), unscaled, into the first half of each answer slot
-	FftOpts f; memset(&f, 0, sizeof f);
-	f.scale = 1.0f; f.batch = batch; f.data_bs = ans_bs; f.scratch_bs = (long long) N;
-	f.cplx_in = reinterpret_cast<const float2 *>(d_real); f.cplx_bs = real_stride / 2;
-	if ((rc = fft_run(ctx, stream, ans, scratch, log2N - 1, 0, f))) return rc;
-	// R = |X| / N as N reals = N/2 complex, into the first half of each scratch slot
-	KL(ctx, "k_real_fwd_finish", stream, k_real_fwd_finish<<<grid, 256, 0, stream>>>(ans, ans_bs, last, half, 1.0f / (float) N,
-	                                                                                  reinterpret_cast<float *>(scratch), 2ll * (long long) N));
-	// inverse: Z' = IFFT_{N/2}(R viewed as complex pairs) in place in the first half of the scratch slot, work space = its second half
-	FftOpts g; memset(&g, 0, sizeof g);
-	g.scale = 1.0f; g.batch = batch; g.data_bs = (long long) N; g.scratch_bs = (long long) N;
-	if ((rc = fft_run(ctx, stream, scratch, scratch + half, log2N - 1, 1, g))) return rc;
-	KL(ctx, "k_real_inv_finish", stream, k_real_inv_finish<<<grid, 256, 0, stream>>>(scratch, (long long) N, last, half, ans, ans_bs));
+	const unsigned G = autocorr_group(N, batch);
+	void *w0_, *w1_;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * half * G, &w0_))) return rc;
+	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * half * G, &w1_))) return rc;
+	float2 *W0 = (float2 *) w0_, *W1 = (float2 *) w1_;
+	const bool windowed = win.hi0 > win.lo0 || win.hi1 > win.lo1;
+	for (unsigned g0 = 0; g0 < batch; g0 += G) {
+		const unsigned gb = (batch - g0 < G) ? (batch - g0) : G;
+		const dim3 grid(grid1d(half, ctx->sm_count), gb);
+		// forward: Z = FFT_{N/2}(capture viewed as complex pairs), unscaled: capture -> W0 -> W1
+		FftOpts f; memset(&f, 0, sizeof f);
+		f.scale = 1.0f; f.batch = gb; f.data_bs = (long long) half; f.scratch_bs = (long long) half;
+		f.cplx_in = reinterpret_cast<const float2 *>(d_real + (long long) g0 * real_stride); f.cplx_bs = real_stride / 2;
+		if ((rc = fft_run(ctx, stream, W1, W0, log2N - 1, 0, f))) return rc;
+		// R = |X| / N as N reals = N/2 complex: W1 -> W0
+		KL(ctx, "k_real_fwd_finish", stream, k_real_fwd_finish<<<grid, 256, 0, stream>>>(W1, (long long) half, last, half, 1.0f / (float) N,
+		                                                                                  reinterpret_cast<float *>(W0), (long long) N));
+		// inverse: Z' = IFFT_{N/2}(R viewed as complex pairs): W0 -> W1 -> W0
+		FftOpts gopt; memset(&gopt, 0, sizeof gopt);
+		gopt.scale = 1.0f; gopt.batch = gb; gopt.data_bs = (long long) half; gopt.scratch_bs = (long long) half;
+		if ((rc = fft_run(ctx, stream, W0, W1, log2N - 1, 1, gopt))) return rc;
+		float2 *out = ans + (long long) g0 * ans_bs;
+		if (windowed) {
+			const unsigned total = (win.hi0 - win.lo0) + (win.hi1 - win.lo1);
+			KL(ctx, "k_real_inv_finish", stream, k_real_inv_finish_win<<<dim3(grid1d(total, ctx->sm_count), gb), 256, 0, stream>>>(W0, (long long) half, last, half, out, ans_bs,
+				win.lo0, win.hi0, win.lo1, win.hi1));
+		} else KL(ctx, "k_real_inv_finish", stream, k_real_inv_finish<<<grid, 256, 0, stream>>>(W0, (long long) half, last, half, out, ans_bs));
+	}
 	return TSDRGPU_OK;
 }
 
 static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float *d_answer, long long answer_stride,
-                                 const float *d_real, long long real_stride, uint32_t size, unsigned batch, bool skip_tail) {
+                                 const float *d_real, long long real_stride, uint32_t size, unsigned batch, bool skip_tail, LagWindows win = LagWindows{0, 0, 0, 0}) {
 	int rc = ensure_table(ctx, stream);
 	if (rc) return rc;
 	const unsigned long long N = tsdrgpu_fft_getrealsize(size);
 	float2 *ans = reinterpret_cast<float2 *>(d_answer);
-	void *scratch;
-	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N * batch, &scratch))) return rc;
 	if (N == 1 || !skip_tail) {
 		for (unsigned b = 0; b < batch; b++) {       // the part that never enters a transform (fft.c:52-60): (|x|, 0)
 			const unsigned long long from = (N == 1) ? 0 : N;
@@ -932,8 +1010,12 @@ static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float 
 	// default: both transforms at half size (autocorrelation_batch_half); TSDRGPU_AUTOCORR_FULL=1 keeps the N-point transforms
 	const bool full_size = getenv("TSDRGPU_AUTOCORR_FULL") != NULL;     // read per call: the tests flip it inside one process
 	if (!full_size && N >= 16 && (real_stride & 1) == 0 && (answer_stride & 1) == 0
-	    && (reinterpret_cast<unsigned long long>(d_real) & 7ull) == 0)
-		return autocorrelation_batch_half(ctx, stream, ans, answer_stride / 2, d_real, real_stride, N, batch, (float2 *) scratch);
+	    && (reinterpret_cast<unsigned long long>(d_real) & 7ull) == 0) {
+		if (win.hi0 > (unsigned) (N >> 1) || win.hi1 > (unsigned) (N >> 1)) win = LagWindows{0, 0, 0, 0};      // a window beyond N/2: produce every lag
+		return autocorrelation_batch_half(ctx, stream, ans, answer_stride / 2, d_real, real_stride, N, batch, win);
+	}
+	void *scratch;
+	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N * batch, &scratch))) return rc;
 	// forward transform of the first N samples, real input widened on load, |X|/N on store
 	FftOpts f; memset(&f, 0, sizeof f);
 	f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N; f.batch = batch;
@@ -1034,7 +1116,10 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 	const uint64_t first_calls = f->calls + 1;                  // extbuffer.c:81, one prepare per capture
 	f->calls += batch;
 	int rc;
-	if ((rc = autocorrelation_batch(ctx, stream, f->d_big, 2ll * size, d_capture, (long long) capture_stride, size, batch, skip_tail))) return rc;
+	// only the two lag windows are ever read (frameratedetector.c:106-109): the last step writes nothing else
+	LagWindows win = LagWindows{0, 0, 0, 0};
+	if (skip_tail && !getenv("TSDRGPU_AUTOCORR_ALL_LAGS")) win = LagWindows{(unsigned) fmin, (unsigned) fmax, (unsigned) lmin, (unsigned) lmax};
+	if ((rc = autocorrelation_batch(ctx, stream, f->d_big, 2ll * size, d_capture, (long long) capture_stride, size, batch, skip_tail, win))) return rc;
 	if (flen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) flen, ctx->sm_count), 256, 0, stream>>>(f->d_p1, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, fmin, flen));
 	if (llen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) llen, ctx->sm_count), 256, 0, stream>>>(f->d_p2, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, lmin, llen));
 	if (calls) *calls = f->calls;

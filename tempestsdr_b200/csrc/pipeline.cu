@@ -158,6 +158,7 @@ struct tsdrgpu_pipeline {
 		// one hop per GPU (tsdrgpu_pipeline_set_superb_devices): rank i records hop i on device dev[i]; rank 0 is this pipeline's device
 		int ndev; int dev[16]; tsdrgpu_ctx_t *rctx[16]; tsdrgpu_superb_mgpu_t *grp[16]; cudaStream_t rstream[16], rcopy[16]; cudaEvent_t rev[16];
 		void *rraw[16]; size_t rraw_cap[16]; uint32_t grp_pairs;
+		float *d_hop0[16];                            // every device's copy of hop 0, the alignment reference (filled when hop 0 is complete)
 	} sb;
 	uint32_t samplerate_real;
 	tsdrgpu_retune_cb retune_cb;
@@ -740,6 +741,7 @@ static void superb_release_devices(tsdrgpu_pipeline *p) {
 	for (int i = 0; i < 16; i++) {
 		if (p->sb.d_hops[i]) { cudaSetDevice(i < p->sb.ndev ? p->sb.dev[i] : p->ctx->device); cudaFree(p->sb.d_hops[i]); p->sb.d_hops[i] = NULL; }
 		if (p->sb.rraw[i]) { cudaSetDevice(p->sb.dev[i]); cudaFree(p->sb.rraw[i]); p->sb.rraw[i] = NULL; p->sb.rraw_cap[i] = 0; }
+		if (p->sb.d_hop0[i]) { cudaSetDevice(p->sb.dev[i]); cudaFree(p->sb.d_hop0[i]); p->sb.d_hop0[i] = NULL; }
 	}
 	for (int i = 1; i < p->sb.ndev; i++) {
 		cudaSetDevice(p->sb.dev[i]);
@@ -772,6 +774,8 @@ static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t 
 			for (int i = 0; i < H; i++) {
 				CU_TRY(ctx, cudaSetDevice(sharded ? p->sb.dev[i] : ctx->device));
 				CU_TRY(ctx, cudaMalloc(&p->sb.d_hops[i], sizeof(float) * 2 * (size_t) p->sb.to_gather));
+				if (p->sb.d_hop0[i]) { CU_TRY(ctx, cudaFree(p->sb.d_hop0[i])); p->sb.d_hop0[i] = NULL; }
+				if (sharded && i > 0) CU_TRY(ctx, cudaMalloc(&p->sb.d_hop0[i], sizeof(float) * 2 * (size_t) p->sb.to_gather));
 			}
 			CU_TRY(ctx, cudaSetDevice(ctx->device));
 			if (sharded) {                                            // (re)build the group for this hop size
@@ -819,6 +823,18 @@ static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t 
 	if (p->sb.gathered < p->sb.to_gather) return TSDRGPU_OK;
 	const long long count_pairs = p->sb.gathered;
 	p->sb.buffid++; p->sb.gathered = 0;
+	if (sharded && p->sb.buffid == 1) {
+		// hop 0 is complete: every other device gets its copy now (NVLink peer copy, seconds before the stitch needs it), so that
+		// each rank derives its alignment lag from local data (superb_mgpu.cu phase 2)
+		for (int i = 1; i < H; i++) {
+			cudaSetDevice(p->sb.dev[i]);
+			cudaError_t e = cudaStreamWaitEvent(p->sb.rcopy[i], p->sb.rev[i], 0);
+			if (e == cudaSuccess) e = cudaMemcpyPeerAsync(p->sb.d_hop0[i], p->sb.dev[i], p->sb.d_hops[0], p->sb.dev[0], sizeof(float) * 2 * (size_t) count_pairs, p->sb.rcopy[i]);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(p->sb.rcopy[i]);
+			if (e != cudaSuccess) { cudaSetDevice(ctx->device); return tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "peer copy of the alignment reference (hop 0)", e, __FILE__, __LINE__); }
+		}
+		cudaSetDevice(ctx->device);
+	}
 	if (p->sb.buffid < H) {
 		if (p->retune_cb) p->retune_cb((int32_t) ((p->sb.buffid - H / 2) * (long long) p->sb.rate), p->user);    // shiftfreq, superbandwidth.c:241
 		p->sb.state = SB_PAUSE;
@@ -847,7 +863,7 @@ static int superb_step(tsdrgpu_pipeline *p, const void *h_iq, int fmt, uint64_t 
 		if ((rc = decim_reserve(p, (size_t) H * N, &where))) return rc;
 		for (int r = 0; r < H; r++) {
 			uint32_t n = 0;
-			rc = tsdrgpu_superb_mgpu_stitch(p->sb.grp[r], r == 0 ? p->s_main : p->sb.rstream[r], p->sb.d_hops[r], (int) count_pairs, (int) p->sb.in_frame, r == 0 ? where : NULL, &n);
+			rc = tsdrgpu_superb_mgpu_stitch(p->sb.grp[r], r == 0 ? p->s_main : p->sb.rstream[r], p->sb.d_hops[r], r == 0 ? p->sb.d_hops[0] : p->sb.d_hop0[r], (int) count_pairs, (int) p->sb.in_frame, r == 0 ? where : NULL, &n);
 			if (rc) { snprintf(ctx->err, sizeof ctx->err, "%s", tsdrgpu_last_error(p->sb.rctx[r])); cudaSetDevice(ctx->device); return rc; }
 			if (r > 0) { cudaSetDevice(p->sb.dev[r]); cudaEventRecord(p->sb.rev[r], p->sb.rstream[r]); }
 		}

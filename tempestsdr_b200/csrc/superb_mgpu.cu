@@ -4,10 +4,13 @@
 // one H*N-point inverse transform.  Sharded, rank q owns hop q and nothing is done twice:
 //
 //   phase 1  local    X_q = FFT_N(hop_q)/N,  D_q = FFT_nd(first difference of |hop_q|)/nd          -> own window
-//   barrier  SPEC     (flags in peer memory)
-//   phase 2  lag      P = conj(D_0) D_q with D_0 READ FROM RANK 0 over NVLink inside the multiply, IFFT_nd, grid argmax
-//                     -> lag_q, written into every rank's window together with its flag (no host round trip)
-//   barrier  LAG
+//   phase 2  lag      P = conj(D_0) D_q, IFFT_nd, grid argmax -> lag_q, written into every rank's window together with its flag
+//                     (no host round trip).  D_0 comes from the rank's OWN copy of hop 0 when the caller keeps the alignment
+//                     reference on every device (d_hop0: the pipeline copies the first hop to all devices while the later
+//                     hops are still being recorded; 23 us of redundant transform instead of a broadcast whose source link
+//                     carries (H-1) x 8 nd bytes); without it D_0 is READ FROM RANK 0 over NVLink inside the multiply, after
+//                     an extra barrier (SPEC)
+//   barrier  LAG      (flags in peer memory; also: every X is in its window)
 //   phase 3  mix      all-to-all instead of an all-gather: rank r owns the bins m in [r N/H, (r+1) N/H).  It PULLS X_q[m] from
 //                     every rank q, forms for all residues s
 //                         V_s[m] = e^{2 pi i m s/(H N)} sum_q e^{2 pi i (q s/H + m lag_q/N)} X_q[m]
@@ -15,8 +18,9 @@
 //                     every rank receives 2 (H-1)/H N complex values instead of (H-1) N -- at H = 8, 3.5x less NVLink traffic
 //   barrier  MIX
 //   phase 4  residue  y[H p + s] = IDFT_N{V_s}[p] on rank s (the H N-point inverse decomposes exactly: DESIGN.md section 6),
-//                     |y| (am_demod, TSDRLibrary.c:244-262: what process() does to superb_run's output) written as float32
-//                     into slot s of the ROOT rank's window (peer stores, 4 B per sample: SURVEY 8e option B)
+//                     |y| (am_demod, TSDRLibrary.c:244-262: what process() does to superb_run's output) stored as float32 BY
+//                     THE LAST BUTTERFLIES OF THE TRANSFORM into slot s of the ROOT rank's window (peer stores over NVLink,
+//                     4 B per sample: SURVEY 8e option B) -- the transfer overlaps the transform
 //   barrier  RES      (root only waits)
 //   phase 5  root     interleave the H residue slots into the time-contiguous magnitude stream -> decimator -> frames
 //
@@ -144,14 +148,6 @@ __global__ void __launch_bounds__(256) sbm_mix(MixArgs A) {
 			const double nr = pr * bc - pi_ * bs, ni = pr * bs + pi_ * bc;
 			pr = nr; pi_ = ni;
 		}
-	}
-}
-
-// |y| of this rank's residue into slot `rank` of the root's window (coalesced peer stores, 4 B per sample)
-__global__ void __launch_bounds__(256) sbm_abs_push(const float4 *__restrict__ y, float2 *__restrict__ slot, unsigned n2) {
-	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
-		const float4 v = y[i];
-		slot[i] = make_float2(mag_exact(v.x, v.y), mag_exact(v.z, v.w));
 	}
 }
 
@@ -312,10 +308,10 @@ static int sbm_prepare(tsdrgpu_superb_mgpu *g, cudaStream_t stream, unsigned N, 
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, V, N, 0))) return rc;
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_p, nd, 0))) return rc;
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, g->d_p, nd, 1))) return rc;
-	if ((rc = tsdrgpu_fft_internal(ctx, stream, V, N, 1))) return rc;
+	if ((rc = tsdrgpu_ifft_abs_internal(ctx, stream, V, reinterpret_cast<float *>(g->d_work), N))) return rc;
 	int *tmp_lag = g->d_lag + 8;
 	if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, g->d_p, nd, g->d_part, tmp_lag))) return rc;
-	preload(sbm_sync); preload(sbm_abs_diff); preload(sbm_xcorr_pull); preload(sbm_abs_push);
+	preload(sbm_sync); preload(sbm_abs_diff); preload(sbm_xcorr_pull);
 	switch (g->H) {
 	case 2: preload(sbm_mix<2>); preload(sbm_interleave<2>); break;
 	case 4: preload(sbm_mix<4>); preload(sbm_interleave<4>); break;
@@ -330,7 +326,7 @@ static int sbm_prepare(tsdrgpu_superb_mgpu *g, cudaStream_t stream, unsigned N, 
 // Rank-local part of one stitch; every rank of the group calls it once per stitch with the same count_pairs / samples_in_frame,
 // each on a stream of its own device.  Asynchronous.  The root's d_stream_out receives nranks * N magnitudes (N returned in
 // *h_n), time-contiguous: sample H p + s is residue s, element p.  d_stream_out is ignored on the other ranks.
-int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const float *d_hop, int count_pairs, int samples_in_frame,
+int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const float *d_hop, const float *d_hop0, int count_pairs, int samples_in_frame,
                                float *d_stream_out, uint32_t *h_n) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, g != NULL);
 	tsdrgpu_ctx_t *ctx = g->ctx;
@@ -355,14 +351,23 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, reinterpret_cast<const float2 *>(d_hop), X, N, 0))) return rc;
 	KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
-	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
-	// ---- phase 2: this rank's alignment lag against hop 0, D_0 pulled from rank 0 inside the multiply
+	// ---- phase 2: this rank's alignment lag against hop 0
 	if (rank != 0) {
-		KL(ctx, "sbm_xcorr_pull", stream, sbm_xcorr_pull<<<grid_for(nd / 2, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float4 *>(g->peers.win[0] + g->off_d),
-			reinterpret_cast<const float4 *>(D), reinterpret_cast<float4 *>(g->d_p), nd / 2));
+		const float4 *d0;
+		if (d_hop0) {                                         // the alignment reference is resident here: its difference spectrum locally
+			KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), g->d_work, nd));
+			if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_p, nd, 0))) return rc;
+			d0 = reinterpret_cast<const float4 *>(g->d_p);
+		} else {                                              // pull it from rank 0 once every rank's spectra are in place
+			KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
+			d0 = reinterpret_cast<const float4 *>(g->peers.win[0] + g->off_d);
+		}
+		KL(ctx, "sbm_xcorr_pull", stream, sbm_xcorr_pull<<<grid_for(nd / 2, ctx->sm_count), 256, 0, stream>>>(d0, reinterpret_cast<const float4 *>(D), reinterpret_cast<float4 *>(g->d_p), nd / 2));
 		if ((rc = tsdrgpu_fft_internal(ctx, stream, g->d_p, nd, 1))) return rc;
 		if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, g->d_p, nd, g->d_part, g->d_lag))) return rc;
-	}   // rank 0: d_lag stays 0
+	} else if (!d_hop0) {                                     // rank 0 takes part in the SPEC barrier the others wait in; its lag stays 0
+		KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
+	}
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_LAG, epoch, all, all, g->d_lag, g->timeout_cycles));
 	// ---- phase 3: all-to-all mix
 	{
@@ -376,10 +381,9 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 		}
 	}
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_MIX, epoch, all, all, (const int *) NULL, g->timeout_cycles));
-	// ---- phase 4: this rank's residue of the H N-point inverse, demodulated, into the root's slot
-	if ((rc = tsdrgpu_fft_internal(ctx, stream, V, N, 1))) return rc;
-	float2 *slot = reinterpret_cast<float2 *>(g->peers.win[g->root] + g->off_r + sizeof(float) * g->slot_stride * (size_t) rank);
-	KL(ctx, "sbm_abs_push", stream, sbm_abs_push<<<grid_for(N / 2, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float4 *>(V), slot, N / 2));
+	// ---- phase 4: this rank's residue of the H N-point inverse; the last pass stores |y| straight into the root's slot
+	float *slot = reinterpret_cast<float *>(g->peers.win[g->root] + g->off_r) + g->slot_stride * (size_t) rank;
+	if ((rc = tsdrgpu_ifft_abs_internal(ctx, stream, V, slot, N))) return rc;
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_RES, epoch, 1u << g->root, rank == g->root ? all : 0u, (const int *) NULL, g->timeout_cycles));
 	// ---- phase 5 (root): the time-contiguous magnitude stream
 	if (rank == g->root) {

@@ -221,15 +221,16 @@ class SuperbGroup:
         gs[0].ctx.chk(gs[0].ctx._lib.tsdrgpu_superb_mgpu_connect_local(arr, len(gs)))
         return gs
 
-    def stitch(self, hop: torch.Tensor, samples_in_frame: int, out: Optional[torch.Tensor] = None):
+    def stitch(self, hop: torch.Tensor, samples_in_frame: int, out: Optional[torch.Tensor] = None, hop0: Optional[torch.Tensor] = None):
         """This rank's share of one stitch, asynchronous on the current stream of the context's device.  On the root returns
-        the magnitude stream (nranks * N floats, time-contiguous); elsewhere None."""
+        the magnitude stream (nranks * N floats, time-contiguous); elsewhere None.  hop0: this device's copy of hop 0 (the
+        alignment reference), passed by every rank or by none."""
         pairs = hop.numel() // 2
         n = self.ctx.fft_getrealsize(pairs)
         if self.rank == self.root and out is None:
             out = torch.empty(self.nranks * n, dtype=torch.float32, device=hop.device)
         hn = C.c_uint32(0)
-        self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_stitch(self._h, self.ctx.stream, hop.data_ptr(), pairs, samples_in_frame,
+        self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_stitch(self._h, self.ctx.stream, hop.data_ptr(), hop0.data_ptr() if hop0 is not None else None, pairs, samples_in_frame,
                                                               out.data_ptr() if out is not None else None, C.byref(hn)))
         return (out[: self.nranks * hn.value] if self.rank == self.root else None)
 

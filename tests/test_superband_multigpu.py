@@ -58,7 +58,8 @@ def _worker(rank, world, port, q):
     want, offs = orc.best().superb_ondataready(hops, sif)
     want_mag = orc.best().am_demod(want)
     for rnd in range(2):
-        out = grp.stitch(torch.from_numpy(hops[rank]).cuda(), sif)
+        # first with this device's own copy of hop 0 (the alignment reference), then pulling rank 0's difference spectrum
+        out = grp.stitch(torch.from_numpy(hops[rank]).cuda(), sif, hop0=torch.from_numpy(hops[0]).cuda() if rnd == 0 else None)
         new_lags = grp.lags()
         good = [2 * l for l in new_lags] == [int(o) for o in offs]
         if rank == 0:
