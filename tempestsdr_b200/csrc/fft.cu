@@ -413,11 +413,14 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 			#pragma unroll
 			for (int m = 0; m < RLAST; m++) {
 				const float x = w[m].x * P.scale, y = w[m].y * P.scale;
-				o[(i + m * PL) * ks] = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), 0.0f);
+				const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+				if (P.abs_real) P.abs_real[(gout - out) + (long long) c * (int) P.out_cs + (long long) (i + m * PL) * ks] = mag;
+				else o[(i + m * PL) * ks] = make_float2(mag, 0.0f);
 			}
 		} else {
+			const float sy = P.conj_out ? -P.scale : P.scale;      // inverse transforms: the conjugate on the way out (see bf8)
 			#pragma unroll
-			for (int m = 0; m < RLAST; m++) o[(i + m * PL) * ks] = make_float2(w[m].x * P.scale, w[m].y * P.scale);
+			for (int m = 0; m < RLAST; m++) o[(i + m * PL) * ks] = make_float2(w[m].x * P.scale, w[m].y * sy);
 		}
 	}
 }
@@ -937,18 +940,16 @@ static int last_stage_table(tsdrgpu_ctx_t *ctx, unsigned half, double eps, const
 // approximation (the mirror identity under perturbed stage angles): 6.6e-10 of the zero-lag peak at 2^20, 7.9e-9 at 2^22.
 struct LagWindows { unsigned lo0, hi0, lo1, hi1; };      // only these lags of every answer are needed (all zero: every lag)
 
-// How many captures share one pair of work buffers.  The four passes and two finish steps of a capture hand N/2 complex
-// values from one to the next; with every capture of a big batch in flight at once those intermediates (8 N bytes per capture
-// and step) stream through HBM.  Processing the batch in groups whose two work buffers (2 x G x 4 N bytes) stay inside the
-// 126 MB L2 turns them into L2 traffic: HBM then sees the capture once on the way in and the requested lags on the way out.
+// How many captures share one pair of work buffers (TSDRGPU_AUTOCORR_GROUP; default: the whole batch).  Small groups would keep
+// the intermediates of the four passes inside the 126 MB L2 instead of streaming them through HBM; measured on the B200
+// (profiles/studies/autocorr_group_sweep.py, 19 captures of 2^20): 41.6 / 22.4 / 20.4 / 17.4 / 17.1 us per capture at groups of
+// 1 / 4 / 6 / 10 / 19 -- the pass kernel is bound by issue slots and shared-memory traffic, not by HBM, so what small groups buy
+// in L2 hits they lose twice over in partial waves (128 CTAs per capture on 444 resident slots).  The knob stays for studies.
 static unsigned autocorr_group(unsigned long long N, unsigned batch) {
-	const int forced = getenv("TSDRGPU_AUTOCORR_GROUP") ? atoi(getenv("TSDRGPU_AUTOCORR_GROUP")) : -1;       // experiment knob, read per call
-	if (forced == 0) return batch;
-	if (forced > 0) return (unsigned) forced < batch ? (unsigned) forced : batch;
-	const unsigned long long budget = 48ull << 20;       // bytes of L2 the two work buffers may take
-	unsigned long long g = budget / (8ull * N);
-	if (g < 1) g = 1;
-	return g < batch ? (unsigned) g : batch;
+	(void) N;
+	const int forced = getenv("TSDRGPU_AUTOCORR_GROUP") ? atoi(getenv("TSDRGPU_AUTOCORR_GROUP")) : 0;       // read per call
+	if (forced > 0 && (unsigned) forced < batch) return (unsigned) forced;
+	return batch;
 }
 
 static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *ans, long long ans_bs, const float *d_real,

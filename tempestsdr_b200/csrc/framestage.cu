@@ -601,12 +601,33 @@ __device__ __forceinline__ double window_from_prefix(const double *S, int n, int
 //                  prefetched into shared memory one frame ahead (cp.async), every thread scores a slice of the windows
 //                  of every candidate strip size (serial chains first when a certificate failed), first-max reduce,
 //                  thread 0 picks the strip size and updates dx/vx and the PLL average.
-constexpr int FS_PREP_HDR = 4;
+// Speculation tables.  Which strip sizes frame f tries depends on frame f-1's winner -- but the winner almost always stays where
+// it was or moves by one step of 4.  fs_sync_prep therefore scores, for every frame of the batch IN PARALLEL, every strip size
+// that can come up while the carried size stays within +-4*FS_SPEC_J of its value at the start of the batch (the sizes
+// themselves, their +-4 neighbours, halves and doubles), leaving one (score, first index) pair per size.  fs_sync_walk then
+// walks the frames with table look-ups only; the moment a frame asks for a size that is not in its table (a jump by a factor
+// of two, a strip that failed the exactness certificate) it stops, and the cluster kernel fs_sync takes over from that frame
+// with the literal search.  Same arithmetic, same first-maximum rule: identical integers either way.
+constexpr int FS_SPEC_J = 3, FS_SPEC_MAX = 24;            // sizes cur0 + 4j, |j| <= J, and what their candidate lists contain (<= 23)
+constexpr int FS_SPEC_AX = 1 + 3 * FS_SPEC_MAX;           // per axis: count, sizes[], scores[], first indices[]
+constexpr int FS_PREP_HDR = 4 + 2 * FS_SPEC_AX;
 __host__ __device__ __forceinline__ size_t fs_prep_stride(int w, int h) { return (size_t) w + h + 2 + FS_PREP_HDR; }
+
+// the strip sizes a frame's search tries, in the reference's order (syncdetector.c:60-69, 73-77, 88-93); vals[t] = -1: skipped.
+// `cur` is clamped in place like the reference clamps sweetspot_data_t.curr_stripsize.
+__device__ __forceinline__ void sweet_candidates(int &cur, int size, int minsize, int vals[5]) {
+	if (minsize < 1) minsize = 1;
+	const int half = size >> 1;
+	if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
+	const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
+	vals[0] = cur;
+	for (int t = 1; t < 5; t++) vals[t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
+}
 
 __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync_prep(const float *__restrict__ wstrips, const float *__restrict__ hstrips,
                                                                 int w, int h, float c0, float c1, float c2, float c3, float c4,
-                                                                int force_serial, double *__restrict__ prep) {
+                                                                int force_serial, double *__restrict__ prep,
+                                                                const SyncState *__restrict__ state, int minsize_x, int minsize_y, int spec_on) {
 	extern __shared__ double smem_d[];
 	double *buf_x = smem_d, *buf_y = buf_x + (w + 1);
 	__shared__ float tiny[16];
@@ -654,11 +675,136 @@ __global__ void __launch_bounds__(FS_SYNC_THREADS) fs_sync_prep(const float *__r
 		rec[nbody + 0] = ok_x ? 1.0 : 0.0; rec[nbody + 1] = ok_y ? 1.0 : 0.0;
 		rec[nbody + 2] = (double) totalf[0]; rec[nbody + 3] = (double) totalf[1];
 	}
+	// ---- speculation tables (see FS_SPEC_*): one warp per (axis, strip size), lanes over the window positions
+	__shared__ int spec_n[2], spec_size[2][FS_SPEC_MAX];
+	if (threadIdx.x < 2) {
+		const int ax = threadIdx.x, size = ax ? h : w, half = size >> 1;
+		int minsize = ax ? minsize_y : minsize_x; if (minsize < 1) minsize = 1;
+		int n = 0;
+		if (spec_on && exact_ok[ax]) {
+			int cur0 = ax ? state->y_strip : state->x_strip;
+			if (cur0 < minsize) cur0 = minsize; else if (cur0 > half) cur0 = half;
+			auto add = [&](int v) { for (int i = 0; i < n; i++) if (spec_size[ax][i] == v) return; if (n < FS_SPEC_MAX) spec_size[ax][n++] = v; };
+			for (int j = -FS_SPEC_J; j <= FS_SPEC_J; j++) {
+				int c = cur0 + 4 * j;
+				if (c < minsize || c > half) continue;           // the carried size always lies in [minsize, half]
+				int vals[5];
+				sweet_candidates(c, size, minsize, vals);
+				for (int t = 0; t < 5; t++) if (vals[t] > 0) add(vals[t]);
+			}
+		}
+		spec_n[ax] = n;
+	}
+	__syncthreads();
+	double *spec = rec + nbody + 4;
+	const int items = spec_n[0] + spec_n[1];
+	for (int it = warp; it < items; it += (int) (blockDim.x >> 5)) {
+		const int ax = it < spec_n[0] ? 0 : 1, idx = ax ? it - spec_n[0] : it;
+		const int size = ax ? h : w, strip = spec_size[ax][idx];
+		const double *S = ax ? buf_y : buf_x;
+		const double tot = (double) totalf[ax], n_out = (double) (size - strip), n_in = (double) strip;
+		Best b; b.score = -INFINITY; b.e = 0x7fffffff;
+		for (int e = lane; e < size; e += 32) {
+			const double sc = fit_score(tot, window_from_prefix(S, size, e, strip), n_out, n_in);
+			if (sc > b.score) { b.score = sc; b.e = e; }          // a lane walks upwards: the first of equal scores stays
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			Best other; other.score = __shfl_xor_sync(0xffffffffu, b.score, o); other.e = __shfl_xor_sync(0xffffffffu, b.e, o);
+			b = best_merge(b, other);
+		}
+		if (lane == 0) {
+			if (b.e == 0x7fffffff) { b.score = fit_score(tot, window_from_prefix(S, size, 0, strip), n_out, n_in); b.e = 0; }   // as fs_sync does
+			double *a = spec + ax * FS_SPEC_AX;
+			a[1 + idx] = (double) strip; a[1 + FS_SPEC_MAX + idx] = b.score; a[1 + 2 * FS_SPEC_MAX + idx] = (double) b.e;
+		}
+	}
+	if (threadIdx.x < 2) spec[threadIdx.x * FS_SPEC_AX] = (double) spec_n[threadIdx.x];
 }
 
 __device__ __forceinline__ void fs_prefetch_record(double *dst, const double *__restrict__ src, int count) {
 	for (int i = threadIdx.x; i < count; i += blockDim.x) __pipeline_memcpy_async(dst + i, src + i, sizeof(double));
 	__pipeline_commit();
+}
+
+// What findthesweetspot does once the best window of the winning strip size is known (syncdetector.c:95-118) plus, on the x
+// axis, frameratepll's averages (syncdetector.c:134-139): one thread per axis.  Shared by the table walker and the cluster search.
+__device__ __forceinline__ void sweet_update(int ax, SyncState &st, Best best, int best_size, int size, tsdrgpu_frame_result_t *r) {
+	const double lowpass = ax ? 0.1 : 0.9;          // FRAMERATE_DX_LOWPASS_COEFF_* (syncdetector.c:15-16)
+	int &dx = ax ? st.y_dx : st.x_dx; int &vx = ax ? st.y_vx : st.x_vx;
+	int &absvx = ax ? st.y_absvx : st.x_absvx; int &cur = ax ? st.y_strip : st.x_strip;
+	const int best_start = (best.e == 0) ? 0 : best.e - 1;   // index recorded before the slide
+	cur = best_size;
+	const int h2 = size / 2;
+	int centre = (best_start + best_size / 2) % size;
+	const int jump = centre - dx;
+	if (jump > h2) dx += size; else if (jump < -h2) centre += size;
+	const int before = dx;
+	const double mixed = __dadd_rn(__dmul_rn((double) centre, lowpass), __dmul_rn(__dsub_rn(1.0, lowpass), (double) dx));
+	dx = (int) (((long long) round(mixed)) % ((long long) size));
+	const int moved = dx - before;
+	vx = (moved > h2) ? (size - moved) : ((moved < -h2) ? (-size - moved) : moved);
+	absvx = (vx >= 0) ? vx : -vx;
+	if (ax == 0) {
+		// frameratepll bookkeeping (syncdetector.c:134-139); the refreshrate write-back is the host's
+		st.avg_speed = __dadd_rn(__dmul_rn(st.avg_speed, 0.99), __dmul_rn(0.01, (double) st.x_vx));
+		st.pll_state = (st.avg_speed < 0.5 && st.avg_speed > -0.5) ? 1 : 0;
+		r->x_dx = st.x_dx; r->x_vx = st.x_vx; r->x_absvx = st.x_absvx; r->x_stripsize = st.x_strip;
+		r->avg_speed = st.avg_speed; r->pll_state = st.pll_state;
+		r->autogain_report = 0; r->reserved = 0;
+	} else {
+		r->y_dx = st.y_dx; r->y_vx = st.y_vx; r->y_absvx = st.y_absvx; r->y_stripsize = st.y_strip;
+	}
+}
+
+// The table walker (see FS_SPEC_*): two threads, one per axis, walk the frames in order using only fs_sync_prep's per-frame
+// tables; *resume receives the first frame that could not be served (nframes when all were): fs_sync continues there.
+__global__ void __launch_bounds__(64) fs_sync_walk(const double *__restrict__ prep, int w, int h, int minsize_x, int minsize_y, int nframes,
+                                                   SyncState *state, tsdrgpu_frame_result_t *results, int *resume) {
+	__shared__ double tab[2][2 * FS_SPEC_AX];             // double-buffered copy of a frame's two tables
+	__shared__ int fail[2];
+	__shared__ SyncState st;
+	const int rec_len = (int) fs_prep_stride(w, h), nbody = w + h + 2;
+	const int ax = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	auto fetch = [&](int f) {                             // all 64 threads: frame f's tables -> tab[f & 1]
+		const double *src = prep + (size_t) f * rec_len + nbody + 4;
+		for (int i = threadIdx.x; i < 2 * FS_SPEC_AX; i += 64) tab[f & 1][i] = src[i];
+	};
+	if (threadIdx.x == 0) { st = *state; fail[0] = fail[1] = 0; }
+	if (nframes > 0) fetch(0);
+	__syncthreads();
+	int f = 0;
+	for (; f < nframes; f++) {
+		if (f + 1 < nframes) fetch(f + 1);                // in flight while this frame is decided
+		Best best; best.score = -1.0; best.e = -1; int best_size = 0;
+		if (lane == 0) {
+			const double *a = tab[f & 1] + ax * FS_SPEC_AX;
+			const int n = (int) a[0], size = ax ? h : w;
+			int cur = ax ? st.y_strip : st.x_strip, vals[5];
+			sweet_candidates(cur, size, ax ? minsize_y : minsize_x, vals);
+			bool ok = n > 0, first = true;
+			for (int t = 0; t < 5 && ok; t++) {
+				if (vals[t] <= 0) continue;
+				int idx = -1;
+				for (int i = 0; i < n; i++) if ((int) a[1 + i] == vals[t]) { idx = i; break; }
+				if (idx < 0) { ok = false; break; }
+				Best c; c.score = a[1 + FS_SPEC_MAX + idx]; c.e = (int) a[1 + 2 * FS_SPEC_MAX + idx];
+				// pick among candidates in the reference's order, strict '>' (syncdetector.c:60-69)
+				if (first || c.score > best.score) { best = c; best_size = vals[t]; }
+				first = false;
+			}
+			if (!ok) fail[ax] = 1;
+		}
+		__syncthreads();
+		if (fail[0] | fail[1]) break;
+		if (lane == 0) sweet_update(ax, st, best, best_size, ax ? h : w, results + f);
+		__syncthreads();                                  // both axes done with tab[f & 1] and st before the next frame's fetch overwrites / reads
+	}
+	if (threadIdx.x == 0) {
+		state->x_dx = st.x_dx; state->x_vx = st.x_vx; state->x_absvx = st.x_absvx; state->x_strip = st.x_strip;
+		state->y_dx = st.y_dx; state->y_vx = st.y_vx; state->y_absvx = st.y_absvx; state->y_strip = st.y_strip;
+		state->avg_speed = st.avg_speed; state->pll_state = st.pll_state;
+		*resume = f;
+	}
 }
 
 // fs_sync runs as ONE thread-block cluster of FS_SEL_CLUSTER CTAs (8 SMs).  Scoring a window costs two correctly rounded
@@ -670,7 +816,9 @@ constexpr int FS_SEL_THREADS = 512, FS_SEL_CLUSTER = 8, FS_SEL_WARPS = FS_SEL_TH
 
 __global__ void __cluster_dims__(FS_SEL_CLUSTER, 1, 1) __launch_bounds__(FS_SEL_THREADS)
 fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, int minsize_y, int nframes,
-        SyncState *state, double *__restrict__ chain_scratch, tsdrgpu_frame_result_t *results) {
+        SyncState *state, double *__restrict__ chain_scratch, tsdrgpu_frame_result_t *results, const int *__restrict__ resume) {
+	const int f_start = resume ? *resume : 0;             // frames before it were served by fs_sync_walk
+	if (f_start >= nframes) return;                       // every CTA of the cluster sees the same value: nobody is left at a barrier
 	cg::cluster_group cluster = cg::this_cluster();
 	const unsigned rank = cluster.block_rank();
 	extern __shared__ double smem_d[];
@@ -684,16 +832,9 @@ fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, 
 
 	// clamp the carried strip size, list the sizes to try (syncdetector.c:73-77, 60-69, 88-93), tell every CTA
 	auto list_candidates = [&](int ax) {
-		const int size = ax ? h : w;
-		int minsize = ax ? minsize_y : minsize_x;
-		if (minsize < 1) minsize = 1;
-		const int half = size >> 1;
 		int &cur = ax ? st.y_strip : st.x_strip;
-		if (cur < minsize) cur = minsize; else if (cur > half) cur = half;
-		const int tries[5] = {cur, cur - 4, cur + 4, cur >> 1, cur << 1};
 		int vals[5];
-		vals[0] = cur;
-		for (int t = 1; t < 5; t++) vals[t] = (tries[t] >= minsize && tries[t] < half && tries[t] != cur) ? tries[t] : -1;
+		sweet_candidates(cur, ax ? h : w, ax ? minsize_y : minsize_x, vals);
 		for (unsigned r = 0; r < FS_SEL_CLUSTER; r++) {
 			int *rc = cluster.map_shared_rank(&cand[0][0], r);
 			for (int t = 0; t < 5; t++) rc[ax * 5 + t] = vals[t];
@@ -704,11 +845,11 @@ fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, 
 		__syncthreads();
 		if (threadIdx.x == 0 || threadIdx.x == 32) list_candidates(threadIdx.x >> 5);
 	}
-	fs_prefetch_record(smem_d, prep, rec_len);
+	fs_prefetch_record(smem_d + (size_t) (nbuf == 2 ? (f_start & 1) : 0) * rec_len, prep + (size_t) f_start * rec_len, rec_len);
 	cluster.sync();
 
 	const int units_x = (w + 31) >> 5, units_y = (h + 31) >> 5, units = 5 * (units_x + units_y);
-	for (int f = 0; f < nframes; f++) {
+	for (int f = f_start; f < nframes; f++) {
 		double *rec = smem_d + (size_t) (nbuf == 2 ? (f & 1) : 0) * rec_len;
 		__pipeline_wait_prior(0);
 		__syncthreads();                                 // record f is in shared memory; the other buffer is no longer read
@@ -781,10 +922,6 @@ fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, 
 			__syncthreads();
 			if (threadIdx.x == 0 || threadIdx.x == 32) {         // one thread per axis
 				const int ax = threadIdx.x >> 5;
-				const int size = ax ? h : w;
-				const double lowpass = ax ? 0.1 : 0.9;          // FRAMERATE_DX_LOWPASS_COEFF_* (syncdetector.c:15-16)
-				int &dx = ax ? st.y_dx : st.x_dx; int &vx = ax ? st.y_vx : st.x_vx;
-				int &absvx = ax ? st.y_absvx : st.x_absvx; int &cur = ax ? st.y_strip : st.x_strip;
 				// pick among candidates in the reference's order, strict '>' (syncdetector.c:60-69)
 				Best best = cand_best[ax][0];
 				int best_size = cand[ax][0];
@@ -792,29 +929,7 @@ fs_sync(const double *__restrict__ prep, int nbuf, int w, int h, int minsize_x, 
 					if (cand[ax][t] <= 0) continue;
 					if (cand_best[ax][t].score > best.score) { best = cand_best[ax][t]; best_size = cand[ax][t]; }
 				}
-				const int best_start = (best.e == 0) ? 0 : best.e - 1;   // index recorded before the slide
-				cur = best_size;
-				const int h2 = size / 2;
-				int centre = (best_start + best_size / 2) % size;
-				const int jump = centre - dx;
-				if (jump > h2) dx += size; else if (jump < -h2) centre += size;
-				const int before = dx;
-				const double mixed = __dadd_rn(__dmul_rn((double) centre, lowpass), __dmul_rn(__dsub_rn(1.0, lowpass), (double) dx));
-				dx = (int) (((long long) round(mixed)) % ((long long) size));
-				const int moved = dx - before;
-				vx = (moved > h2) ? (size - moved) : ((moved < -h2) ? (-size - moved) : moved);
-				absvx = (vx >= 0) ? vx : -vx;
-				tsdrgpu_frame_result_t *r = results + f;   // the auto-gain fields of the record belong to fs_results_autogain
-				if (ax == 0) {
-					// frameratepll bookkeeping (syncdetector.c:134-139); the refreshrate write-back is the host's
-					st.avg_speed = __dadd_rn(__dmul_rn(st.avg_speed, 0.99), __dmul_rn(0.01, (double) st.x_vx));
-					st.pll_state = (st.avg_speed < 0.5 && st.avg_speed > -0.5) ? 1 : 0;
-					r->x_dx = st.x_dx; r->x_vx = st.x_vx; r->x_absvx = st.x_absvx; r->x_stripsize = st.x_strip;
-					r->avg_speed = st.avg_speed; r->pll_state = st.pll_state;
-					r->autogain_report = 0; r->reserved = 0;
-				} else {
-					r->y_dx = st.y_dx; r->y_vx = st.y_vx; r->y_absvx = st.y_absvx; r->y_stripsize = st.y_strip;
-				}
+				sweet_update(ax, st, best, best_size, ax ? h : w, results + f);   // the auto-gain fields of the record belong to fs_results_autogain
 				list_candidates(ax);                              // for the next frame
 			}
 		}
@@ -959,6 +1074,7 @@ struct tsdrgpu_framestage {
 	float *d_pmin, *d_pmax; double *d_psum, *d_psq, *d_plin; FrameParams *d_params; int batch_cap;
 	tsdrgpu_frame_result_t *d_results[2];
 	double *d_chain;
+	int *d_resume;                               // first frame of the batch fs_sync_walk could not serve from the tables
 	float taps[5];
 	int overlap, phase, side_pending;
 	double *d_prep; size_t prep_cap;             // fs_sync_prep's per-frame records (consumed by fs_sync on the same stream)
@@ -1038,6 +1154,8 @@ int tsdrgpu_framestage_create(tsdrgpu_ctx_t *ctx, tsdrgpu_framestage_t **out) {
 	tsdrgpu_gauss_taps(fs->taps);
 	CU_TRY(ctx, cudaMalloc(&fs->d_state, sizeof(SyncState)));
 	CU_TRY(ctx, cudaMalloc(&fs->d_chain, sizeof(double) * 10 * FS_MAX_STRIP));
+	CU_TRY(ctx, cudaMalloc(&fs->d_resume, 256));
+	CU_TRY(ctx, cudaMemset(fs->d_resume, 0, 256));
 	{   // highest priority: its single CTA should be placed as soon as an SM has room, ahead of the main stream's queued CTAs
 		int lo = 0, hi = 0;
 		CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1057,7 +1175,7 @@ void tsdrgpu_framestage_destroy(tsdrgpu_framestage_t *fs) {
 	cudaDeviceSynchronize();
 	void *ptrs[] = {fs->d_screen, fs->d_state, fs->d_t1, fs->d_t2[0], fs->d_t2[1], fs->d_wstrips[0], fs->d_wstrips[1], fs->d_hstrips[0],
 	                fs->d_hstrips[1], fs->d_pmin, fs->d_pmax, fs->d_psum, fs->d_psq, fs->d_plin, fs->d_params, fs->d_results[0],
-	                fs->d_results[1], fs->d_chain, fs->d_prep};
+	                fs->d_results[1], fs->d_chain, fs->d_prep, fs->d_resume};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	cudaStreamDestroy(fs->s_side);
 	for (int i = 0; i < 2; i++) { cudaEventDestroy(fs->ev_ready[i]); cudaEventDestroy(fs->ev_done[i]); }
@@ -1166,10 +1284,12 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 			CU_TRY(ctx, cudaEventRecord(fs->ev_ready[ph], stream));
 			CU_TRY(ctx, cudaStreamWaitEvent(s2, fs->ev_ready[ph], 0));
 		}
+		static const bool no_spec = getenv("TSDRGPU_SYNC_NO_SPEC") != NULL;      // test hook: always the literal cluster search
 		KL(ctx, "fs_sync_prep", s2, fs_sync_prep<<<nframes, FS_SYNC_THREADS, prep_smem, s2>>>(fs->d_wstrips[ph], fs->d_hstrips[ph], w, h,
-			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], force_serial, fs->d_prep));
+			fs->taps[0], fs->taps[1], fs->taps[2], fs->taps[3], fs->taps[4], force_serial, fs->d_prep, fs->d_state, minsize_x, minsize_y, no_spec ? 0 : 1));
+		KL(ctx, "fs_sync_walk", s2, fs_sync_walk<<<1, 64, 0, s2>>>(fs->d_prep, w, h, minsize_x, minsize_y, nframes, fs->d_state, d_results, fs->d_resume));
 		KL(ctx, "fs_sync", s2, fs_sync<<<FS_SEL_CLUSTER, FS_SEL_THREADS, sync_smem, s2>>>(fs->d_prep, sync_nbuf, w, h, minsize_x, minsize_y, nframes,
-			fs->d_state, fs->d_chain, d_results));
+			fs->d_state, fs->d_chain, d_results, fs->d_resume));
 		return TSDRGPU_OK;
 	};
 	// syncdetector_run's output stage: src -> dst (dst != src), or in place on src when allowed
