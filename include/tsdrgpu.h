@@ -105,6 +105,8 @@ TSDRGPU_API int tsdrgpu_detect_videomode(const double *frame_plot, int frame_off
 /* frameratepll's write-back (syncdetector.c:141-152) for one frame, from the frame stage's per-frame result: returns 1 and
  * moves *refreshrate when the reference would (PLL on is the caller's condition; x_vx != 0 is checked here), else 0. */
 TSDRGPU_API int tsdrgpu_pll_step(double *refreshrate, int32_t x_vx, int32_t pll_state, double avg_speed);
+/* the same arithmetic from peak indices picked elsewhere (tsdrgpu_frd_peaks: on the device) */
+TSDRGPU_API int tsdrgpu_videomode_from_peaks(int frame_offset, int frame_index, int line_offset, int line_index, uint32_t samplerate, double *fps, int *height);
 /* the normalised 5-tap Gaussian of gaussian.c:16-30 */
 TSDRGPU_API void tsdrgpu_gauss_taps(float taps[5]);
 
@@ -252,6 +254,12 @@ TSDRGPU_API int  tsdrgpu_frd_run_batch(tsdrgpu_frd_t *frd, void *stream, uint32_
 /* copies the current running means (device-resident) to host buffers; synchronises */
 TSDRGPU_API int  tsdrgpu_frd_get_plots(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, double *h_frame_plot, int frame_cap,
                                        double *h_line_plot, int line_cap);
+/* SURVEY 8f-3 on the device: index of the first strict maximum of each plot (PlotVisualizer.java:203-236), reduced on the GPU
+ * right behind the running means of every run.  h_peaks[0] = frame plot, [1] = line plot.  _async: page-locked destination. */
+TSDRGPU_API int  tsdrgpu_frd_peaks(tsdrgpu_frd_t *frd, void *stream, int32_t *h_peaks);                  /* synchronises */
+TSDRGPU_API int  tsdrgpu_plot_peaks(tsdrgpu_ctx_t *ctx, void *stream, const double *d_frame_plot, int frame_len, const double *d_line_plot, int line_len,
+                                    int32_t *h_peaks);                                                     /* synchronises */
+TSDRGPU_API int  tsdrgpu_frd_peaks_async(tsdrgpu_frd_t *frd, void *stream, int32_t *h_peaks_pinned);
 TSDRGPU_API int  tsdrgpu_accumulate(tsdrgpu_ctx_t *ctx, void *stream, double *d_out, uint64_t calls,
                                     const float *d_in_complex, int startid, int length);
 

@@ -110,6 +110,10 @@ _SIGS = {
                                         C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "tsdrgpu_frd_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
     "tsdrgpu_frd_get_plots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "tsdrgpu_frd_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "tsdrgpu_plot_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    "tsdrgpu_frd_peaks_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tsdrgpu_videomode_from_peaks": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "tsdrgpu_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]),
     "tsdrgpu_complex_to_abs_diff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "tsdrgpu_superb_bestfit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),

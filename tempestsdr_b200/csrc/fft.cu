@@ -226,11 +226,12 @@ __device__ __forceinline__ float2 lds2(unsigned addr) { float2 v; asm volatile("
 // Butterflies exist in the FORWARD direction only.  An inverse transform is the conjugate of the forward transform of the
 // conjugated input -- conj(x conj(w)) = conj(x) w, and IEEE arithmetic is sign-symmetric -- so an inverse pass conjugates what it
 // loads from global memory in its first pass and what it stores in its last one (FftPass.conj_in / conj_out) and is otherwise
-// the same code.  Layer twiddles arrive as float4 (c, s, -s, c): one 16-byte load feeds the two packed instructions of cmulp.
-__device__ __forceinline__ void bf8(float2 *v, const float4 *__restrict__ tw /* = table + k - 1 */, int p) {
+// the same code.  Layer twiddles are loaded as (c, s) and turned into cmulp's (c, s, -s, c) in registers: 16-byte table entries
+// were measured slower (twice the L1 wavefronts on a kernel whose first stall reason is the memory-instruction queue).
+__device__ __forceinline__ void bf8(float2 *v, const float2 *__restrict__ tw /* = table + k - 1 */, int p) {
 	float2 a[4][2], b[2][2][2];
-	const float4 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
-	const float4 TC00 = __ldg(tw + 4 * p), TC10 = __ldg(tw + 5 * p), TC01 = __ldg(tw + 6 * p), TC11 = __ldg(tw + 7 * p);
+	const float4 TA = twform(__ldg(tw + p)), TB0 = twform(__ldg(tw + 2 * p)), TB1 = twform(__ldg(tw + 3 * p));
+	const float4 TC00 = twform(__ldg(tw + 4 * p)), TC10 = twform(__ldg(tw + 5 * p)), TC01 = twform(__ldg(tw + 6 * p)), TC11 = twform(__ldg(tw + 7 * p));
 	#pragma unroll
 	for (int r = 0; r < 4; r++) { const float2 hi = cmulp(v[r + 4], TA); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
 	#pragma unroll
@@ -249,9 +250,9 @@ __device__ __forceinline__ void bf8(float2 *v, const float4 *__restrict__ tw /* 
 		}
 	}
 }
-__device__ __forceinline__ void bf4(float2 *v, const float4 *__restrict__ tw, int p) {
+__device__ __forceinline__ void bf4(float2 *v, const float2 *__restrict__ tw, int p) {
 	float2 a[2][2];
-	const float4 TA = __ldg(tw + p), TB0 = __ldg(tw + 2 * p), TB1 = __ldg(tw + 3 * p);
+	const float4 TA = twform(__ldg(tw + p)), TB0 = twform(__ldg(tw + 2 * p)), TB1 = twform(__ldg(tw + 3 * p));
 	#pragma unroll
 	for (int r = 0; r < 2; r++) { const float2 hi = cmulp(v[r + 2], TA); a[r][0] = cadd(v[r], hi); a[r][1] = csub(v[r], hi); }
 	#pragma unroll
@@ -260,14 +261,14 @@ __device__ __forceinline__ void bf4(float2 *v, const float4 *__restrict__ tw, in
 		v[q0] = cadd(a[0][q0], hi); v[q0 + 2] = csub(a[0][q0], hi);
 	}
 }
-__device__ __forceinline__ void bf2(float2 *v, const float4 *__restrict__ tw, int p) {
-	const float2 hi = cmulp(v[1], __ldg(tw + p));
+__device__ __forceinline__ void bf2(float2 *v, const float2 *__restrict__ tw, int p) {
+	const float2 hi = cmulp(v[1], twform(__ldg(tw + p)));
 	const float2 lo = v[0];
 	v[0] = cadd(lo, hi); v[1] = csub(lo, hi);
 }
 
 template <int LOG2L, bool FAN = false>
-__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float4 *__restrict__ stw) {
+__global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float2 *__restrict__ stw) {
 	extern __shared__ float2 s[];
 	constexpr int L = 1 << LOG2L, NST8 = LOG2L / 3, RL = LOG2L % 3;
 	constexpr int RLAST = (RL == 0) ? 8 : ((RL == 1) ? 2 : 4);
@@ -535,6 +536,30 @@ __global__ void k_accumulate_batch(double *out, unsigned long long first_calls, 
 		out[i] = acc;
 	}
 }
+// SURVEY 8f-3 on the device: the index of the first strict maximum of each running-mean plot, the pick the GUI makes on the
+// host (PlotVisualizer.java:203-236: start from element 0, move on a strict '>').  One CTA per plot; NaN never wins, a NaN in
+// element 0 keeps index 0 (nothing compares greater than it), equal values keep the smallest index.
+__global__ void __launch_bounds__(1024) k_plot_peaks(const double *p0, int n0, const double *p1, int n1, int *peaks) {
+	__shared__ double s_v[32]; __shared__ int s_i[32];
+	const double *v = blockIdx.x ? p1 : p0;
+	const int n = blockIdx.x ? n1 : n0;
+	double best = -INFINITY; int bi = 0x7fffffff;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		const double x = v[i];
+		if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+		if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+	}
+	if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < (int) (blockDim.x >> 5); w++) if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) { best = s_v[w]; bi = s_i[w]; }
+		const double first = n > 0 ? v[0] : 0.0;
+		peaks[blockIdx.x] = (n <= 0 || first != first || bi == 0x7fffffff) ? 0 : bi;
+	}
+}
 // first difference of magnitudes, out of place                          (superbandwidth.c:67-81)
 __global__ void k_abs_diff(const float2 *src, float2 *dst, unsigned long long pairs) {
 	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (unsigned long long) gridDim.x * blockDim.x) {
@@ -639,11 +664,11 @@ inline unsigned grid1d(unsigned long long n, int sm_count) {
 
 float2 *g_table[64] = {0};          // per device
 // per-pass layer-twiddle tables (see fft_pass_kernel), built on the host in double precision and cached
-struct StageTab { int device, log2L, l_base, pert; float4 *d; };
+struct StageTab { int device, log2L, l_base, pert; float2 *d; };
 std::vector<StageTab> g_stage_tabs;
 std::mutex g_tw_mu;
 
-int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all, const float4 **out) {
+int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all, const float2 **out) {
 	static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;      // opt out: the mathematically exact DFT
 	double eps[FFT_MAX_LOG2L + 1];
 	int pert = 0;
@@ -654,19 +679,18 @@ int stage_table(tsdrgpu_ctx_t *ctx, int log2L, int l_base, const double *eps_all
 	std::lock_guard<std::mutex> lock(g_tw_mu);
 	for (auto &t : g_stage_tabs) if (t.device == ctx->device && t.log2L == log2L && t.l_base == (pert ? l_base : -1) && t.pert == pert) { *out = t.d; return TSDRGPU_OK; }
 	const int L = 1 << log2L;
-	std::vector<float4> h((size_t) L);                  // (c, s, -s, c): the twiddle and its quarter turn, one 16-byte load (cmulp)
+	std::vector<float2> h((size_t) L);
 	for (int sidx = 0; sidx < log2L; sidx++) {
 		const int blk = 1 << sidx;
 		for (int K = 0; K < blk; K++) {
 			const double ang = -3.14159265358979323846 * ((double) K / (double) blk) * (1.0 + eps[sidx]);
-			const float c = (float) cos(ang), sn = (float) sin(ang);
-			h[(size_t) blk - 1 + K] = make_float4(c, sn, -sn, c);
+			h[(size_t) blk - 1 + K] = make_float2((float) cos(ang), (float) sin(ang));
 		}
 	}
-	h[(size_t) L - 1] = make_float4(1.0f, 0.0f, -0.0f, 1.0f);
+	h[(size_t) L - 1] = make_float2(1.0f, 0.0f);
 	StageTab t; t.device = ctx->device; t.log2L = log2L; t.l_base = pert ? l_base : -1; t.pert = pert;
-	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float4) * L));
-	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float4) * L, cudaMemcpyHostToDevice));
+	CU_TRY(ctx, cudaMalloc(&t.d, sizeof(float2) * L));
+	CU_TRY(ctx, cudaMemcpy(t.d, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice));
 	g_stage_tabs.push_back(t);
 	*out = t.d;
 	return TSDRGPU_OK;
@@ -738,7 +762,7 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 		else KL(ctx, "fft_pass_kernel", stream, fft_pass_small<2><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse));
 		return TSDRGPU_OK;
 	}
-	const float4 *stw;
+	const float2 *stw;
 	{ int rc = stage_table(ctx, P.log2L, l_base, eps_all, &stw); if (rc) return rc; }
 	P.tw_step = NULL;
 	if (P.tw_M && P.tw_M <= (1ull << 24) && P.c_fast_out && P.log2L >= 3 && P.tw_lo == P.C && P.tw_cs == 1) {
@@ -895,6 +919,7 @@ struct tsdrgpu_frd {
 	float *d_big; size_t big_cap;                 // extbuff (2*size floats)
 	double *d_p1, *d_p2; size_t p1_cap, p2_cap;   // the two running means
 	uint64_t calls; int fresh;
+	int *d_peaks;                                 // first strict maximum of each plot (k_plot_peaks), refreshed with every run
 };
 
 extern "C" {
@@ -1065,6 +1090,8 @@ int tsdrgpu_frd_create(tsdrgpu_ctx_t *ctx, tsdrgpu_frd_t **out) {
 	tsdrgpu_frd *f = new tsdrgpu_frd();
 	memset(f, 0, sizeof *f);
 	f->ctx = ctx; f->fresh = 1;
+	CU_TRY(ctx, cudaMalloc(&f->d_peaks, 256));
+	CU_TRY(ctx, cudaMemset(f->d_peaks, 0, 256));
 	*out = f;
 	return TSDRGPU_OK;
 }
@@ -1074,6 +1101,7 @@ void tsdrgpu_frd_destroy(tsdrgpu_frd_t *f) {
 	if (f->d_big) cudaFree(f->d_big);
 	if (f->d_p1) cudaFree(f->d_p1);
 	if (f->d_p2) cudaFree(f->d_p2);
+	if (f->d_peaks) cudaFree(f->d_peaks);
 	delete f;
 }
 int tsdrgpu_frd_reset(tsdrgpu_frd_t *f) { if (!f) return TSDRGPU_EINVAL; f->fresh = 1; return TSDRGPU_OK; }
@@ -1123,6 +1151,7 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 	if ((rc = autocorrelation_batch(ctx, stream, f->d_big, 2ll * size, d_capture, (long long) capture_stride, size, batch, skip_tail, win))) return rc;
 	if (flen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) flen, ctx->sm_count), 256, 0, stream>>>(f->d_p1, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, fmin, flen));
 	if (llen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) llen, ctx->sm_count), 256, 0, stream>>>(f->d_p2, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, lmin, llen));
+	KL(ctx, "k_plot_peaks", stream, k_plot_peaks<<<2, 1024, 0, stream>>>(f->d_p1, flen, f->d_p2, llen, f->d_peaks));
 	if (calls) *calls = f->calls;
 	if (h_frame_plot || h_line_plot) {
 		if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
@@ -1158,6 +1187,35 @@ int tsdrgpu_frd_get_plots(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, 
 	if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
 	if (h_line_plot) CU_TRY(ctx, cudaMemcpyAsync(h_line_plot, f->d_p2, sizeof(double) * (size_t) (llen < line_cap ? llen : line_cap), cudaMemcpyDeviceToHost, stream));
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	return TSDRGPU_OK;
+}
+
+// where the two plots peak, picked on the device right after the running means were updated.
+// h_peaks[0] = frame plot, [1] = line plot (indices into the plots; add the window offsets for lags).  tsdrgpu_frd_peaks
+// synchronises; the _async form needs page-locked memory and is valid once the stream has passed it.
+// stage-level entry: the same reduction on any two device-resident plots (synchronises)
+int tsdrgpu_plot_peaks(tsdrgpu_ctx_t *ctx, void *stream_, const double *d_frame_plot, int frame_len, const double *d_line_plot, int line_len, int32_t *h_peaks) {
+	BIND(ctx); ARG_TRY(ctx, d_frame_plot && d_line_plot && frame_len >= 0 && line_len >= 0 && h_peaks);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	void *d;
+	int rc = tsdrgpu_scratch(ctx, 3, 256, &d);
+	if (rc) return rc;
+	KL(ctx, "k_plot_peaks", stream, k_plot_peaks<<<2, 1024, 0, stream>>>(d_frame_plot, frame_len, d_line_plot, line_len, (int *) d));
+	CU_TRY(ctx, cudaMemcpyAsync(h_peaks, d, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+	CU_TRY(ctx, cudaStreamSynchronize(stream));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_frd_peaks_async(tsdrgpu_frd_t *f, void *stream, int32_t *h_peaks_pinned) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL && h_peaks_pinned != NULL);
+	BIND(f->ctx);
+	CU_TRY(f->ctx, cudaMemcpyAsync(h_peaks_pinned, f->d_peaks, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	return TSDRGPU_OK;
+}
+int tsdrgpu_frd_peaks(tsdrgpu_frd_t *f, void *stream, int32_t *h_peaks) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL && h_peaks != NULL);
+	BIND(f->ctx);
+	CU_TRY(f->ctx, cudaMemcpyAsync(h_peaks, f->d_peaks, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	CU_TRY(f->ctx, cudaStreamSynchronize((cudaStream_t) stream));
 	return TSDRGPU_OK;
 }
 

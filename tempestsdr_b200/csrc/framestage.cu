@@ -756,48 +756,57 @@ __device__ __forceinline__ void sweet_update(int ax, SyncState &st, Best best, i
 	}
 }
 
-// The table walker (see FS_SPEC_*): two threads, one per axis, walk the frames in order using only fs_sync_prep's per-frame
-// tables; *resume receives the first frame that could not be served (nframes when all were): fs_sync continues there.
+// The table walker (see FS_SPEC_*): one warp per axis walks the frames in order using only fs_sync_prep's per-frame tables.
+// Lane i of a warp keeps entry i of its axis' table (size, score, first index) in registers -- the next frame's entries are
+// loaded while the current frame is decided -- so a look-up is a ballot and two shuffles; lane 0 then does findthesweetspot's
+// scalar update.  *resume receives the first frame that could not be served (nframes when all were): fs_sync continues there.
 __global__ void __launch_bounds__(64) fs_sync_walk(const double *__restrict__ prep, int w, int h, int minsize_x, int minsize_y, int nframes,
                                                    SyncState *state, tsdrgpu_frame_result_t *results, int *resume) {
-	__shared__ double tab[2][2 * FS_SPEC_AX];             // double-buffered copy of a frame's two tables
 	__shared__ int fail[2];
 	__shared__ SyncState st;
 	const int rec_len = (int) fs_prep_stride(w, h), nbody = w + h + 2;
 	const int ax = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	auto fetch = [&](int f) {                             // all 64 threads: frame f's tables -> tab[f & 1]
-		const double *src = prep + (size_t) f * rec_len + nbody + 4;
-		for (int i = threadIdx.x; i < 2 * FS_SPEC_AX; i += 64) tab[f & 1][i] = src[i];
+	const int size = ax ? h : w, minsize = ax ? minsize_y : minsize_x;
+	struct Entry { int n, sz, e; double score; };
+	auto fetch = [&](int f) {
+		const double *a = prep + (size_t) f * rec_len + nbody + 4 + ax * FS_SPEC_AX;
+		Entry t;
+		t.n = (int) a[0];
+		const bool live = lane < FS_SPEC_MAX;                // FS_SPEC_MAX <= 32: one entry per lane
+		t.sz = live ? (int) a[1 + lane] : -2;
+		t.score = live ? a[1 + FS_SPEC_MAX + lane] : 0.0;
+		t.e = live ? (int) a[1 + 2 * FS_SPEC_MAX + lane] : 0;
+		if (lane >= t.n) t.sz = -2;                          // entries beyond the count are stale memory
+		return t;
 	};
 	if (threadIdx.x == 0) { st = *state; fail[0] = fail[1] = 0; }
-	if (nframes > 0) fetch(0);
+	Entry cur_t = fetch(0);
 	__syncthreads();
 	int f = 0;
 	for (; f < nframes; f++) {
-		if (f + 1 < nframes) fetch(f + 1);                // in flight while this frame is decided
+		Entry next_t = cur_t;
+		if (f + 1 < nframes) next_t = fetch(f + 1);          // in flight while this frame is decided
+		int cur = ax ? st.y_strip : st.x_strip, vals[5];
+		sweet_candidates(cur, size, minsize, vals);          // every lane: a handful of integer operations
 		Best best; best.score = -1.0; best.e = -1; int best_size = 0;
-		if (lane == 0) {
-			const double *a = tab[f & 1] + ax * FS_SPEC_AX;
-			const int n = (int) a[0], size = ax ? h : w;
-			int cur = ax ? st.y_strip : st.x_strip, vals[5];
-			sweet_candidates(cur, size, ax ? minsize_y : minsize_x, vals);
-			bool ok = n > 0, first = true;
-			for (int t = 0; t < 5 && ok; t++) {
-				if (vals[t] <= 0) continue;
-				int idx = -1;
-				for (int i = 0; i < n; i++) if ((int) a[1 + i] == vals[t]) { idx = i; break; }
-				if (idx < 0) { ok = false; break; }
-				Best c; c.score = a[1 + FS_SPEC_MAX + idx]; c.e = (int) a[1 + 2 * FS_SPEC_MAX + idx];
-				// pick among candidates in the reference's order, strict '>' (syncdetector.c:60-69)
-				if (first || c.score > best.score) { best = c; best_size = vals[t]; }
-				first = false;
-			}
-			if (!ok) fail[ax] = 1;
+		bool ok = cur_t.n > 0, first = true;
+		#pragma unroll
+		for (int t = 0; t < 5; t++) {
+			if (vals[t] <= 0) continue;
+			const unsigned hit = __ballot_sync(0xffffffffu, cur_t.sz == vals[t]);
+			if (!hit) { ok = false; continue; }
+			const int src = __ffs(hit) - 1;
+			Best c; c.score = __shfl_sync(0xffffffffu, cur_t.score, src); c.e = __shfl_sync(0xffffffffu, cur_t.e, src);
+			// pick among candidates in the reference's order, strict '>' (syncdetector.c:60-69)
+			if (first || c.score > best.score) { best = c; best_size = vals[t]; }
+			first = false;
 		}
+		if (lane == 0 && !ok) fail[ax] = 1;
 		__syncthreads();
 		if (fail[0] | fail[1]) break;
-		if (lane == 0) sweet_update(ax, st, best, best_size, ax ? h : w, results + f);
-		__syncthreads();                                  // both axes done with tab[f & 1] and st before the next frame's fetch overwrites / reads
+		if (lane == 0) sweet_update(ax, st, best, best_size, size, results + f);
+		__syncthreads();                                     // st is up to date for both warps before the next frame reads it
+		cur_t = next_t;
 	}
 	if (threadIdx.x == 0) {
 		state->x_dx = st.x_dx; state->x_vx = st.x_vx; state->x_absvx = st.x_absvx; state->x_strip = st.x_strip;

@@ -84,6 +84,14 @@ static int first_max(const double *v, int n) {
 	for (int i = 1; i < n; i++) if (v[i] > top) { top = v[i]; best = i; }
 	return best;
 }
+/* the same arithmetic from peak indices that were picked elsewhere (on the device: k_plot_peaks) */
+int tsdrgpu_videomode_from_peaks(int frame_offset, int frame_index, int line_offset, int line_index, uint32_t samplerate, double *fps, int *height) {
+	const double frame_length = (double) (frame_offset + frame_index), line_length = (double) (line_offset + line_index);
+	if (frame_length <= 0 || line_length <= 0) return TSDRGPU_EINVAL;
+	if (fps) *fps = (double) (long long) samplerate / frame_length;
+	if (height) *height = (int) floor(frame_length / line_length + 0.5);
+	return TSDRGPU_OK;
+}
 int tsdrgpu_detect_videomode(const double *frame_plot, int frame_offset, int frame_len, const double *line_plot, int line_offset, int line_len,
                              uint32_t samplerate, double *fps, int *height, int *frame_index, int *line_index) {
 	if (!frame_plot || !line_plot || frame_len <= 0 || line_len <= 0) return TSDRGPU_EINVAL;

@@ -150,6 +150,7 @@ struct tsdrgpu_pipeline {
 	// autocorrelation side path
 	tsdrgpu_frd *frd; float *d_capture[2]; size_t cap_size[2], cap_fill; int cap_phase; uint32_t cap_rate;
 	double *h_plot_frame[2], *h_plot_line[2]; size_t plot_cap; int plot_slot; int plot_busy[2];
+	int32_t *h_peaks[2];                               // where the two plots peak, picked on the device (8f-3)
 	// superbandwidth (superb_run's state machine, superbandwidth.c:179-264)
 	struct {
 		int state; int buffid; long long to_gather, gathered, in_frame, to_pause; uint32_t rate;
@@ -367,7 +368,8 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 				while (p->delivered < p->submitted) pthread_cond_wait(&p->cv_done, &p->mu);
 				pthread_mutex_unlock(&p->mu);
 				for (int s = 0; s < 2; s++) {
-					if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
+					if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); cudaFreeHost(p->h_peaks[s]); }
+					if ((rc = tsdrgpu_malloc_host(ctx, 64, (void **) &p->h_peaks[s]))) return rc;
 					if ((rc = tsdrgpu_malloc_host(ctx, sizeof(double) * need, (void **) &p->h_plot_frame[s]))) return rc;
 					if ((rc = tsdrgpu_malloc_host(ctx, sizeof(double) * need, (void **) &p->h_plot_line[s]))) return rc;
 				}
@@ -377,6 +379,7 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 			if ((rc = tsdrgpu_frd_run_async(p->frd, p->s_main, p->samplerate, cap, (uint32_t) want,
 			                                slot >= 0 ? p->h_plot_frame[slot] : NULL, fmax - fmin,
 			                                slot >= 0 ? p->h_plot_line[slot] : NULL, lmax - lmin, &calls))) return rc;
+			if (slot >= 0 && (rc = tsdrgpu_frd_peaks_async(p->frd, p->s_main, p->h_peaks[slot]))) return rc;
 			CU_TRY(ctx, cudaEventRecord(p->ev_cap_used[cph], p->s_main));
 			p->stats.captures++;
 			if (slot >= 0) {
@@ -572,7 +575,7 @@ int tsdrgpu_pipeline_create(tsdrgpu_ctx_t *ctx, const tsdrgpu_pipeline_config_t 
 	for (int s = 0; s < PL_SLOTS; s++) { p->h_frames[s] = NULL; p->h_results[s] = NULL; p->h_report[s] = NULL; p->h_pll_rr[s] = NULL; p->slot_busy[s] = 0; }
 	p->host_register = 0;                               // opt-in: tsdrgpu_pipeline_set_host_registration
 	CU_TRY(ctx, cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
-	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; }
+	for (int s = 0; s < 2; s++) { p->h_plot_frame[s] = NULL; p->h_plot_line[s] = NULL; p->plot_busy[s] = 0; p->h_peaks[s] = NULL; }
 	p->stop = 0; p->submitted = 0; p->delivered = 0; p->last_w = 0; p->last_h = 0;
 	memset(&p->sb, 0, sizeof p->sb); p->samplerate_real = cfg->samplerate; p->retune_cb = NULL;
 	CU_TRY(ctx, cudaEventCreateWithFlags(&p->sb.ev, cudaEventDisableTiming));
@@ -630,7 +633,7 @@ void tsdrgpu_pipeline_destroy(tsdrgpu_pipeline_t *p) {
 	if (p->d_argb_last) cudaFree(p->d_argb_last);
 	for (int s = 0; s < PL_SLOTS; s++) if (p->h_frames[s]) { cudaFreeHost(p->h_frames[s]); cudaFreeHost(p->h_results[s]); cudaFreeHost(p->h_report[s]); free(p->h_pll_rr[s]); }
 	cudaEventDestroy(p->ev_res);
-	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); }
+	for (int s = 0; s < 2; s++) if (p->h_plot_frame[s]) { cudaFreeHost(p->h_plot_frame[s]); cudaFreeHost(p->h_plot_line[s]); cudaFreeHost(p->h_peaks[s]); }
 	cudaStreamDestroy(p->s_main); cudaStreamDestroy(p->s_copy); cudaStreamDestroy(p->s_out);
 	for (int i = 0; i < 2; i++) cudaEventDestroy(p->ev_out[i]);
 	cudaEventDestroy(p->ev_main);

@@ -205,6 +205,161 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// rs_main4: the same function as rs_main, laid out for fewer instructions per sample (rs_main: 156 per sample, 66 % of the issue
+// slots busy at 0.42 of the HBM roofline -- ncu r02a).  A thread owns FOUR consecutive samples:
+//   * it loads them itself with two 16-byte loads (IQ) / one (magnitudes) straight from global memory -- groups are aligned on
+//     the ADDRESS, so a tile may start up to three samples early; those samples only serve as "the sample before" -- and writes
+//     their magnitudes back with one 16-byte store where the address allows: no staging of the input in shared memory at all;
+//   * what sample k needs from sample k-1 (its pid, whether it emitted an A pixel, what it banked) is in the thread's own
+//     registers for three samples out of four; the fourth comes from the lane below with one shuffle per quantity, lane 0 works
+//     it out for itself (once per 128 samples);
+//   * everything else -- closed-form pid, exact double operations, pixel assembly in shared memory, 16-byte stores of the
+//     finished run -- is rs_main's.  Bit-identical output (same tests, and TSDRGPU_RS_V1=1 switches back to rs_main).
+// The rare sample whose bank is not simply what the previous sample left (r <= 1, or a landing within one ulp of a pixel edge)
+// goes through rs_bank_walk, out of line.
+template <bool IQ>
+__device__ __noinline__ bool rs_bank_walk(const float *__restrict__ in, const RsBlock &B, unsigned k, double *bank_out) {
+	const double r = B.r, phase = B.phase;
+	long long L = (long long) k - 2;
+	while (L >= 0) {
+		const Geo gl = rs_geo((unsigned) L, r, phase);
+		const double Plm1 = (L == 0) ? 0.0 : rs_P(rs_geo((unsigned) L - 1, r, phase).c);
+		if (rs_isA(gl, Plm1)) break;
+		L--;
+	}
+	if (L < 0) return false;                             // the bank reaches past the block start -> rs_fixup writes this pixel
+	double bank = 0.0;
+	for (unsigned j = (unsigned) L; j < k; j++) {
+		const Geo gj = rs_geo(j, r, phase);
+		bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) rs_load<IQ>(in, B.in_start + j)));
+	}
+	*bank_out = bank;
+	return true;
+}
+
+template <bool IQ>
+__global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__ in, float *__restrict__ out,
+                                                       const RsBlock *__restrict__ blocks, const uint2 *__restrict__ tile_info,
+                                                       float *__restrict__ mag_out) {
+	__shared__ __align__(16) float s_out[RS_OUT_CAP + 8];
+	const uint2 ti = tile_info[blockIdx.x];
+	const RsBlock B = blocks[ti.x];
+	const unsigned s0 = ti.y, s1 = min(s0 + (unsigned) RS_TILE, B.size);
+	const double r = B.r, phase = B.phase;
+	const double pbase_d = (s0 == 0) ? 0.0 : rs_P(rs_geo(s0 - 1, r, phase).c);
+	const unsigned pbase = (unsigned) pbase_d, pend = (unsigned) rs_P(rs_geo(s1 - 1, r, phase).c);
+	float *gout = out + B.out_start;
+	const unsigned aoff = (unsigned) ((reinterpret_cast<unsigned long long>(gout + pbase) >> 2) & 3ull);
+	float *sq = s_out + aoff;
+	const unsigned sq_addr = (unsigned) __cvta_generic_to_shared(s_out) + (aoff << 2);
+	// groups of four samples aligned on the input ADDRESS (16 bytes): the tile starts `shift` samples early
+	const float *tile_in = in + (IQ ? 2ull : 1ull) * (B.in_start + s0);
+	const int shift = IQ ? (int) ((reinterpret_cast<unsigned long long>(tile_in) >> 3) & 1ull) : (int) ((reinterpret_cast<unsigned long long>(tile_in) >> 2) & 3ull);
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const int size = (int) B.size;
+	for (int base = (int) s0 - shift + (int) warp * 128; base < (int) s1; base += (RS_THREADS / 32) * 128) {
+		const int k0 = base + 4 * (int) lane;
+		// ---- the four samples of this thread (zero outside the block)
+		float vf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+		if (k0 >= 0 && k0 + 3 < size) {
+			if (IQ) {
+				const float4 *p4 = reinterpret_cast<const float4 *>(in + 2ull * (B.in_start + (unsigned) k0));
+				const float4 a = ldg_stream_f4(p4), b = ldg_stream_f4(p4 + 1);
+				vf[0] = mag_exact(a.x, a.y); vf[1] = mag_exact(a.z, a.w); vf[2] = mag_exact(b.x, b.y); vf[3] = mag_exact(b.z, b.w);
+			} else {
+				const float4 a = ldg_stream_f4(reinterpret_cast<const float4 *>(in + B.in_start + (unsigned) k0));
+				vf[0] = a.x; vf[1] = a.y; vf[2] = a.z; vf[3] = a.w;
+			}
+		} else {
+			#pragma unroll
+			for (int j = 0; j < 4; j++) if (k0 + j >= 0 && k0 + j < size) vf[j] = rs_load<IQ>(in, B.in_start + (unsigned) (k0 + j));
+		}
+		if (IQ && mag_out != NULL) {                          // the demodulated stream, for the frame-rate detector: owned samples only
+			float *m = mag_out + ((long long) B.in_start + k0);   // (k0 may be negative: the pointer is only dereferenced under the masks below)
+			const bool all_owned = k0 >= (int) s0 && k0 + 3 < (int) s1;
+			const unsigned ma = (unsigned) ((reinterpret_cast<unsigned long long>(m) >> 2) & 3ull);
+			if (all_owned && ma == 0) *reinterpret_cast<float4 *>(m) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+			else if (all_owned && ma == 2) { *reinterpret_cast<float2 *>(m) = make_float2(vf[0], vf[1]); *reinterpret_cast<float2 *>(m + 2) = make_float2(vf[2], vf[3]); }
+			else {
+				#pragma unroll
+				for (int j = 0; j < 4; j++) if (k0 + j >= (int) s0 && k0 + j < (int) s1) m[j] = vf[j];
+			}
+		}
+		// ---- geometry of the four samples (dsp.c:282-284), all exact single IEEE operations
+		const double kd0 = (double) k0;
+		double lo[4], hi[4], cc[4], P[4], T[4];
+		#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const double kd = (j == 0) ? kd0 : __dadd_rn(kd0, (double) j);      // exact
+			lo[j] = __dadd_rn(__dmul_rn(kd, r), phase);
+			hi[j] = __dadd_rn(lo[j], r);
+			cc[j] = __dadd_rn(hi[j], -1.0);
+			double pk = ceil(cc[j]);
+			if (!(cc[j] > 0.0)) pk = 0.0;                     // == rs_P
+			P[j] = pk;
+			T[j] = __dmul_rn((pk < hi[j] && pk > lo[j]) ? __dsub_rn(hi[j], pk) : r, (double) vf[j]);      // == rs_t
+		}
+		// ---- the sample before this thread's first one: from the lane below, lane 0 works it out itself
+		const int a3 = (P[2] < lo[3] && P[2] < cc[3]) ? 1 : 0;            // does this thread's last sample emit an A pixel?  (dsp.c:288)
+		double Pm = __shfl_up_sync(0xffffffffu, P[3], 1), Tm = __shfl_up_sync(0xffffffffu, T[3], 1);
+		int Am = __shfl_up_sync(0xffffffffu, a3, 1);
+		if (lane == 0) {
+			Pm = 0.0; Tm = 0.0; Am = 0;
+			if (k0 > 0) {
+				const unsigned kp = (unsigned) k0 - 1;
+				const Geo gp = rs_geo(kp, r, phase);
+				Pm = rs_P(gp.c);
+				Am = rs_isA(gp, kp == 0 ? 0.0 : rs_P(rs_geo(kp - 1, r, phase).c)) ? 1 : 0;
+				Tm = rs_t(gp, Pm, r, (double) rs_load<IQ>(in, B.in_start + kp));
+			}
+		}
+		const double Pprev[4] = {Pm, P[0], P[1], P[2]}, Tprev[4] = {Tm, T[0], T[1], T[2]};
+		bool A[4];
+		#pragma unroll
+		for (int j = 0; j < 4; j++) A[j] = Pprev[j] < lo[j] && Pprev[j] < cc[j];
+		const bool Aprev[4] = {Am != 0, A[0], A[1], A[2]};
+		// ---- emit: sample k owns pixels P(k-1) .. P(k)-1 (see the header of this file)
+		#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int k = k0 + j;
+			const double Pkm1 = Pprev[j], prevT = Tprev[j];
+			const bool isA = A[j], prevA = Aprev[j];
+			if (k < (int) s0 || k >= (int) s1) continue;      // not this tile's sample (alignment lead-in, or past the end)
+			const unsigned p0 = (unsigned) Pkm1, cnt = (unsigned) P[j] - p0;
+			float first = vf[j];
+			bool write_first = true;
+			if (isA) {
+				double bank = 0.0;
+				bool have = false;
+				if (k > 0 && prevA) { bank = __dadd_rn(0.0, prevT); have = true; }      // the common case for r > 1
+				else if (k > 0) have = rs_bank_walk<IQ>(in, B, (unsigned) k, &bank);
+				if (have) first = __double2float_rn(__dadd_rn(bank, __dmul_rn((double) vf[j], __dadd_rn(__dsub_rn(1.0, lo[j]), Pkm1))));
+				else write_first = false;                     // the bank reaches past the block start -> rs_fixup writes this pixel
+			}
+			const unsigned d = sq_addr + ((p0 - pbase) << 2);
+			if (cnt > 0 && write_first) sts_f32(d, first);
+			if (cnt > 1) sts_f32(d + 4, vf[j]);
+			if (cnt > 2) sts_f32(d + 8, vf[j]);
+			for (unsigned c = 3; c < cnt; c++) sts_f32(d + 4 * c, vf[j]);
+		}
+	}
+	__syncthreads();
+	// write the assembled run of pixels: scalar head to a 16-byte boundary, float4 body, scalar tail
+	const unsigned pe = min(pend, B.n_out);
+	if (pe <= pbase) return;
+	const unsigned count = pe - pbase;
+	float *gdst = gout + pbase;
+	const unsigned head = min((4u - aoff) & 3u, count);
+	if (threadIdx.x < head) gdst[threadIdx.x] = sq[threadIdx.x];
+	const unsigned body4 = (count - head) >> 2;
+	const float4 *s4 = reinterpret_cast<const float4 *>(sq + head);
+	float4 *g4 = reinterpret_cast<float4 *>(gdst + head);
+	for (unsigned q = threadIdx.x; q < body4; q += RS_THREADS) g4[q] = s4[q];
+	const unsigned done = head + (body4 << 2);
+	if (threadIdx.x < count - done) gdst[done + threadIdx.x] = sq[done + threadIdx.x];
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // One CTA.  Resolves the per-block quantities that cross block boundaries (see header comment).
 template <bool IQ>
 __global__ void __launch_bounds__(256) rs_fixup(const float *__restrict__ in, float *__restrict__ out,
@@ -446,8 +601,17 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			CU_TRY(ctx, cudaMalloc(&r->d_bank, sizeof(double) * r->bank_cap));
 			CU_TRY(ctx, cudaMalloc(&r->d_has_a, sizeof(int) * r->bank_cap));
 		}
-		if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
-		else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
+		// rs_main4 (four samples per thread) stages every tile's pixels in shared memory: ratios up to 3; beyond that, and on
+		// request (TSDRGPU_RS_V1=1, the cross-check of the tests), the one-sample-per-thread kernel
+		const double ratio = upsample_by / downsample_by;
+		const bool v1 = getenv("TSDRGPU_RS_V1") != NULL || !(ratio <= 2.99);
+		if (v1) {
+			if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+			else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
+		} else {
+			if (in_is_iq) KL(ctx, "rs_main", stream, rs_main4<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+			else KL(ctx, "rs_main", stream, rs_main4<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
+		}
 		if (in_is_iq) KL(ctx, "rs_fixup", stream, rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 		else KL(ctx, "rs_fixup", stream, rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 	}

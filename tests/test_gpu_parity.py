@@ -407,6 +407,48 @@ def test_accumulate_exact_and_framerate_plots(gpu, O):
         assert int(np.argmax(gp)) == int(np.argmax(fp))       # the lag the GUI would pick is the same
 
 
+def test_plot_peaks_on_the_device_match_the_gui_pick(gpu):
+    """the first strict maximum of the two autocorrelation plots, reduced on the GPU (k_plot_peaks), against the
+    GUI's pick restated on the host (tsdrgpu_detect_videomode <- PlotVisualizer.java:203-236): 120 seeded plots with ties,
+    plateaus, infinities, NaNs (in element 0 and elsewhere) and degenerate lengths; and the detector's own plots after a run."""
+    import ctypes as C
+    from tempestsdr_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(2024)
+
+    def host_pick(fp, lp):
+        fi, li = C.c_int(-1), C.c_int(-1)
+        rc = lib.tsdrgpu_detect_videomode(fp.ctypes.data_as(C.POINTER(C.c_double)), 1, fp.size, lp.ctypes.data_as(C.POINTER(C.c_double)), 1, lp.size,
+                                          1000, None, None, C.byref(fi), C.byref(li))
+        assert rc == 0
+        return fi.value, li.value
+    for case in range(120):
+        n0 = int(rng.integers(1, 200_000)) if case % 5 else int(rng.integers(1, 40))
+        n1 = int(rng.integers(1, 900))
+        fp, lp = rng.standard_normal(n0), rng.uniform(0, 1, n1)
+        if case % 4 == 1:                                  # plateaus and exact ties: the first one must win
+            fp = np.round(fp * 3) / 3; lp = np.round(lp * 5) / 5
+        if case % 7 == 2:
+            fp[rng.integers(0, n0)] = np.inf; lp[rng.integers(0, n1)] = -np.inf
+        if case % 9 == 3:
+            fp[rng.integers(0, n0)] = np.nan                # a NaN elsewhere never wins
+        if case % 11 == 4:
+            lp[0] = np.nan                                  # a NaN in element 0 is never beaten
+        if case % 13 == 5:
+            fp[:] = fp[0]
+        got = (C.c_int32 * 2)()
+        gpu.chk(lib.tsdrgpu_plot_peaks(gpu._h, gpu.stream, dev(fp).data_ptr(), n0, dev(lp).data_ptr(), n1, got))
+        assert (got[0], got[1]) == host_pick(fp, lp), f"case {case}"
+    det = gpu.framerate_detector()
+    fs = 2_000_000
+    size = det.capture_size(fs)
+    x = orc.port().am_demod(synth.video_like_iq(size, fs, 400, 200, 50.0, seed=8))
+    (fo, fp), (lo, lp), _ = det.run(fs, dev(x))
+    got = (C.c_int32 * 2)()
+    gpu.chk(lib.tsdrgpu_frd_peaks(det._h, gpu.stream, got))
+    assert (got[0], got[1]) == host_pick(fp, lp)
+
+
 # ------------------------------------------------------------------------------------------------ a22
 def test_superbandwidth(gpu, O):
     fs, fv = 400_000, 50.0
