@@ -374,6 +374,10 @@ enum { TSDRGPU_FMT_FLOAT = 0, TSDRGPU_FMT_INT8 = 1, TSDRGPU_FMT_INT16 = 2, TSDRG
 /* the conversion alone, device to device (d_raw: items_count samples of `fmt`; d_out: items_count floats) */
 TSDRGPU_API int  tsdrgpu_convert_samples(tsdrgpu_ctx_t *ctx, void *stream, const void *d_raw, int fmt, uint64_t items_count, float *d_out);
 TSDRGPU_API int  tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_samples, int fmt, uint64_t items_count, int64_t samples_dropped);
+/* For a front end with a ring of page-locked buffers: returns once everything is enqueued; the buffer must stay untouched until
+ * tsdrgpu_pipeline_sync_input() returns.  Consecutive blocks then cross the link back to back. */
+TSDRGPU_API int  tsdrgpu_pipeline_process_raw_async(tsdrgpu_pipeline_t *p, const void *h_pinned_samples, int fmt, uint64_t items_count, int64_t samples_dropped);
+TSDRGPU_API int  tsdrgpu_pipeline_sync_input(tsdrgpu_pipeline_t *p);
 TSDRGPU_API int  tsdrgpu_pipeline_flush(tsdrgpu_pipeline_t *p);            /* waits for the GPU and for every pending callback */
 TSDRGPU_API int  tsdrgpu_pipeline_set_param_int(tsdrgpu_pipeline_t *p, int id, uint32_t value);
 TSDRGPU_API int  tsdrgpu_pipeline_set_resolution(tsdrgpu_pipeline_t *p, int height, double refreshrate);

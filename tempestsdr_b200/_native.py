@@ -137,6 +137,8 @@ _SIGS = {
     "tsdrgpu_pipeline_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]),
     "tsdrgpu_convert_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
     "tsdrgpu_pipeline_process_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64]),
+    "tsdrgpu_pipeline_process_raw_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64]),
+    "tsdrgpu_pipeline_sync_input": (C.c_int, [C.c_void_p]),
     "tsdrgpu_pipeline_flush": (C.c_int, [C.c_void_p]),
     "tsdrgpu_pipeline_set_param_int": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "tsdrgpu_pipeline_set_resolution": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),

@@ -814,7 +814,10 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 	}
 	int rc;
 	if (log2N <= 20) {                                  // N = N1 * N2 (lines <= 1024) ; n = N2*n1 + n2 ; k = k1 + N1*k2
-		const unsigned l1 = (log2N + 1) / 2, l2 = log2N - l1;
+		// odd log2 N: the SHORTER line goes to the strided pass (bundle of 8 columns = 64-byte runs instead of 4 = 32-byte runs on
+		// both its loads and its stores); TSDRGPU_FFT_SPLIT=ceil restores the other split for comparison
+		static const bool split_ceil = getenv("TSDRGPU_FFT_SPLIT") && !strcmp(getenv("TSDRGPU_FFT_SPLIT"), "ceil");
+		const unsigned l1 = split_ceil ? (log2N + 1) / 2 : log2N / 2, l2 = log2N - l1;
 		const unsigned long long N1 = 1ull << l1, N2 = 1ull << l2;
 		P.log2L = (int) l1; P.C = bundle_for((int) l1, N2); P.c_fast_in = P.c_fast_out = 1;
 		P.G_lo = (unsigned) (N2 / P.C);

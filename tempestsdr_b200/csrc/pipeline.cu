@@ -897,11 +897,29 @@ int tsdrgpu_convert_samples(tsdrgpu_ctx_t *ctx, void *stream, const void *d_raw,
 	return TSDRGPU_OK;
 }
 
+static int process_impl(tsdrgpu_pipeline_t *p, const void *h_iq, int fmt, uint64_t items_count, int64_t samples_dropped, bool wait_for_copy);
+
 int tsdrgpu_pipeline_process(tsdrgpu_pipeline_t *p, const float *h_iq, uint64_t items_count, int64_t samples_dropped) {
-	return tsdrgpu_pipeline_process_raw(p, h_iq, TSDRGPU_FMT_FLOAT, items_count, samples_dropped);
+	return process_impl(p, h_iq, TSDRGPU_FMT_FLOAT, items_count, samples_dropped, true);
+}
+int tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_iq, int fmt, uint64_t items_count, int64_t samples_dropped) {
+	return process_impl(p, h_iq, fmt, items_count, samples_dropped, true);
+}
+// For a front end that owns a ring of PAGE-LOCKED buffers: the call returns as soon as everything is enqueued, the buffer must
+// stay untouched until tsdrgpu_pipeline_sync_input() has returned (or the buffer three calls later has been accepted: there are
+// four staging slots).  Copies of consecutive blocks then run back to back on the link instead of waiting for the host's
+// enqueue work in between.  Not for pageable memory (a pageable cudaMemcpyAsync is synchronous anyway).
+int tsdrgpu_pipeline_process_raw_async(tsdrgpu_pipeline_t *p, const void *h_pinned, int fmt, uint64_t items_count, int64_t samples_dropped) {
+	return process_impl(p, h_pinned, fmt, items_count, samples_dropped, false);
+}
+int tsdrgpu_pipeline_sync_input(tsdrgpu_pipeline_t *p) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
+	BIND(p->ctx);
+	CU_TRY(p->ctx, cudaStreamSynchronize(p->s_copy));
+	return TSDRGPU_OK;
 }
 
-int tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_iq, int fmt, uint64_t items_count, int64_t samples_dropped) {
+static int process_impl(tsdrgpu_pipeline_t *p, const void *h_iq, int fmt, uint64_t items_count, int64_t samples_dropped, bool wait_for_copy) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, p != NULL);
 	tsdrgpu_ctx_t *ctx = p->ctx;
 	BIND(ctx);
@@ -982,7 +1000,7 @@ int tsdrgpu_pipeline_process_raw(tsdrgpu_pipeline_t *p, const void *h_iq, int fm
 		// work for the heavy kernels runs while this block's H2D copy is still in flight; the copy is waited for last.
 		rc = drain_blocks(p);
 	} while (0);
-	if (copy_issued) {
+	if (copy_issued && (wait_for_copy || rc != TSDRGPU_OK)) {
 		const cudaError_t e = cudaStreamSynchronize(p->s_copy);             // the host buffer has been read
 		if (e != cudaSuccess && rc == TSDRGPU_OK) return tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "cudaStreamSynchronize(s_copy)", e, __FILE__, __LINE__);
 	}

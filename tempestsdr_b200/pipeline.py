@@ -88,6 +88,13 @@ class Pipeline:
     def process_raw_ptr(self, ptr: int, fmt: int, items: int, samples_dropped: int = 0) -> None:
         N.check(self._lib.tsdrgpu_pipeline_process_raw(self._h, C.c_void_p(ptr), fmt, items, samples_dropped), self._ctx)
 
+    def process_raw_ptr_async(self, ptr: int, fmt: int, items: int, samples_dropped: int = 0) -> None:
+        """Page-locked buffers only: returns once enqueued; the buffer must stay untouched until sync_input()."""
+        N.check(self._lib.tsdrgpu_pipeline_process_raw_async(self._h, C.c_void_p(ptr), fmt, items, samples_dropped), self._ctx)
+
+    def sync_input(self) -> None:
+        N.check(self._lib.tsdrgpu_pipeline_sync_input(self._h), self._ctx)
+
     def flush(self) -> None:
         N.check(self._lib.tsdrgpu_pipeline_flush(self._h), self._ctx)
         if self.errors:
