@@ -49,13 +49,6 @@ struct FftPass {
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// W^{q}_{2048} (forward sign); inverse conjugates
-__device__ __forceinline__ float2 tw_lookup(const float2 *__restrict__ table, unsigned q, bool inverse) {
-	float2 w = __ldg(table + (q & (FFT_TABLE - 1)));
-	if (inverse) w.y = -w.y;
-	return w;
-}
-
 // ---- in-register small DFTs (natural order in, natural order out) -------------------------------------------------
 // Packed single precision (sm_100: add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2): one instruction works on both halves of
 // a complex value held in an aligned register pair.  The pass kernel is bound by issue slots, not by the FP pipes, so halving
@@ -100,100 +93,25 @@ __device__ __forceinline__ void dft8(float2 (&v)[8], bool inverse) {
 	v[4] = csub(e0, o0); v[5] = csub(e1, o1); v[6] = csub(e2, o2); v[7] = csub(e3, o3);
 }
 
-// shared-memory index with one pad element per 16 (keeps the stride-R Stockham writes spread over the banks)
-__device__ __forceinline__ int padq(int q) { return q + (q >> 4); }
-
-// One Stockham stage of radix R on every line of the bundle.  Each thread owns `8/R` butterflies (8 elements):
-// read -> barrier -> write -> barrier (in place).
-template <int R, int LOG2L>
-__device__ __forceinline__ void stockham_stage(float2 *s, int LP, int C, int p, const float2 *__restrict__ table, bool inverse) {
-	constexpr int L = 1 << LOG2L, PER_LINE = L / R, LOGPL = LOG2L - (R == 8 ? 3 : (R == 4 ? 2 : 1)), NB = 8 / R;
-	const int work = C * PER_LINE;
-	float2 v[8];
-	#pragma unroll
-	for (int it = 0; it < NB; it++) {
-		const int widx = threadIdx.x + it * blockDim.x;
-		if (widx < work) {
-			const int c = widx >> LOGPL, i = widx & (PER_LINE - 1);
-			const int k = i & (p - 1);
-			const float2 *line = s + c * LP;
-			#pragma unroll
-			for (int m = 0; m < R; m++) v[it * R + m] = line[padq(i + m * PER_LINE)];
-			if (k) {
-				const unsigned tq = (unsigned) k * (unsigned) (FFT_TABLE / (R * p));
-				#pragma unroll
-				for (int m = 1; m < R; m++) v[it * R + m] = cmul(v[it * R + m], tw_lookup(table, m * tq, inverse));
-			}
-			if (R == 8) {
-				float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]);
-				dft8(u, inverse);
-			} else if (R == 4) dft4(v[it * 4 + 0], v[it * 4 + 1], v[it * 4 + 2], v[it * 4 + 3], inverse);
-			else dft2(v[it * 2 + 0], v[it * 2 + 1]);
-		}
-	}
-	__syncthreads();
-	#pragma unroll
-	for (int it = 0; it < NB; it++) {
-		const int widx = threadIdx.x + it * blockDim.x;
-		if (widx < work) {
-			const int c = widx >> LOGPL, i = widx & (PER_LINE - 1);
-			const int k = i & (p - 1);
-			const int j = (i - k) * R + k;
-			float2 *line = s + c * LP;
-			#pragma unroll
-			for (int m = 0; m < R; m++) line[padq(j + m * p)] = v[it * R + m];
-		}
-	}
-	__syncthreads();
-}
-
+// transforms of 2 or 4 points (whole transforms only: passes of longer ones have lines of >= 64): one thread each, exact
+// twiddles (the reference's first two stages have no angle error), the same load / store conventions as the pass kernel
 template <int LOG2L>
-__global__ void __launch_bounds__(512, 3) fft_pass_small(const float2 *in, float2 *out, FftPass P,
-                                                        const float2 *__restrict__ table, int inverse_) {
-	extern __shared__ float2 s[];
+__global__ void __launch_bounds__(32) fft_tiny_kernel(const float2 *in, float2 *out, FftPass P) {
+	if (threadIdx.x != 0) return;
 	constexpr int L = 1 << LOG2L;
-	const bool inverse = inverse_ != 0;
-	const int C = P.C, LP = padq(L) + 1, total = C * L, log2C = P.log2C;
-	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g - g_hi * P.G_lo;
-	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs;
-	const long long out_base = (long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo + (long long) blockIdx.y * P.out_bs;
-
-	// ---- load the bundle (runs of C consecutive values on strided passes, whole lines on contiguous ones)
-	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-		int c, j;
-		if (P.c_fast_in) { c = idx & (C - 1); j = idx >> log2C; } else { j = idx & (L - 1); c = idx >> LOG2L; }
-		const long long src = in_base + (long long) c * P.in_cs + (long long) j * P.in_js;
-		float2 v;
-		if (P.in_real) v = make_float2(__ldg(reinterpret_cast<const float *>(in) + src), 0.0f); else v = __ldg(in + src);
-		s[c * LP + padq(j)] = v;
-	}
-	__syncthreads();
-
-	// ---- Stockham stages: the odd radix (2 or 4) first, where all twiddles are 1, then radix 8
-	int p = 1;
-	constexpr int FIRST = (LOG2L % 3 == 0) ? 8 : ((LOG2L % 3 == 1) ? 2 : 4);
-	if (FIRST == 2) { stockham_stage<2, LOG2L>(s, LP, C, p, table, inverse); p = 2; }
-	else if (FIRST == 4) { stockham_stage<4, LOG2L>(s, LP, C, p, table, inverse); p = 4; }
+	const long long ib = (long long) blockIdx.y * P.in_bs, ob = (long long) blockIdx.y * P.out_bs;
+	float2 v[L];
 	#pragma unroll
-	for (int st = 0; st < LOG2L / 3; st++) { stockham_stage<8, (LOG2L >= 3 ? LOG2L : 3)>(s, LP, C, p, table, inverse); p <<= 3; }
-
-	// ---- inter-pass twiddle, scaling, optional |.|, store
-	for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-		int c, k;
-		if (P.c_fast_out) { c = idx & (C - 1); k = idx >> log2C; } else { k = idx & (L - 1); c = idx >> LOG2L; }
-		float2 v = s[c * LP + padq(k)];
-		if (P.tw_M) {
-			const unsigned long long col = (unsigned long long) ((long long) g_lo * P.tw_lo + (long long) c * P.tw_cs);
-			const unsigned long long e = (col * (unsigned long long) k) & (P.tw_M - 1);
-			float2 tw;
-			if (P.tw_M <= (1ull << 24)) { float sn, cs; sincospif(-2.0f * ((float) e / (float) P.tw_M), &sn, &cs); tw = make_float2(cs, sn); }   // exact argument
-			else { double dsn, dcs; sincospi(-2.0 * ((double) e / (double) P.tw_M), &dsn, &dcs); tw = make_float2((float) dcs, (float) dsn); }
-			if (inverse) tw.y = -tw.y;
-			v = cmul(v, tw);
-		}
-		v.x *= P.scale; v.y *= P.scale;
-		if (P.out_abs) v = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))), 0.0f);
-		out[out_base + (long long) c * P.out_cs + (long long) k * P.out_ks] = v;
+	for (int j = 0; j < L; j++) {
+		v[j] = P.in_real ? make_float2(reinterpret_cast<const float *>(in)[ib + j], 0.0f) : in[ib + j];
+		if (P.conj_in) v[j].y = -v[j].y;
+	}
+	if (L == 2) dft2(v[0], v[1]); else dft4(v[0], v[1], v[2], v[3], false);
+	#pragma unroll
+	for (int k = 0; k < L; k++) {
+		float2 r = make_float2(v[k].x * P.scale, v[k].y * (P.conj_out ? -P.scale : P.scale));
+		if (P.out_abs) r = make_float2(__fsqrt_rn(__fadd_rn(__fmul_rn(r.x, r.x), __fmul_rn(r.y, r.y))), 0.0f);
+		out[ob + k] = r;
 	}
 }
 
@@ -267,9 +185,27 @@ __device__ __forceinline__ void bf2(float2 *v, const float2 *__restrict__ tw, in
 	v[0] = cadd(lo, hi); v[1] = csub(lo, hi);
 }
 
-template <int LOG2L, bool FAN = false>
+// ---- TMA: a pass whose lines are contiguous in memory (the second pass of a two-pass plan, the third of a three-pass plan,
+// a single-pass transform) gets its whole bundle with bulk copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) issued
+// by one thread and counted in bytes on an mbarrier: C copies of one line each -- or ONE copy of C L complex values when the
+// lines of the bundle are adjacent, as in two-pass plans -- land linearly in the half of the ping-pong buffer the first
+// butterfly does not write; the threads wait on the barrier and read their eight inputs from shared memory (consecutive
+// lanes read consecutive values: conflict-free without a swizzle).  The eight dependent global loads per thread, their address
+// arithmetic and their scoreboard stalls are gone from the instruction stream.
+__device__ __forceinline__ void fft_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void fft_mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void fft_mbar_wait(unsigned bar, unsigned parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+	             :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fft_bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int LOG2L, bool FAN = false, bool TMA = false>
 __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, float2 *out, FftPass P, const float2 *__restrict__ stw) {
-	extern __shared__ float2 s[];
+	extern __shared__ __align__(128) float2 s[];
 	constexpr int L = 1 << LOG2L, NST8 = LOG2L / 3, RL = LOG2L % 3;
 	constexpr int RLAST = (RL == 0) ? 8 : ((RL == 1) ? 2 : 4);
 	constexpr int NSTAGES = NST8 + (RL ? 1 : 0);
@@ -290,11 +226,34 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	// the second from a host-built table of 8 values per column (double precision; P.tw_step[col * 8 + j]).
 	const bool tw_fast = P.tw_step != NULL && P.c_fast_out && (int) blockDim.x == C * L8;
 
-	// ---- stage 0: radix 8, p = 1, inputs x[i + m L/8] from global memory
+	// ---- stage 0: radix 8, p = 1, inputs x[i + m L/8] from global memory (or, TMA, from the bundle the bulk copies landed)
 	{
 		int c, i;
 		if (P.c_fast_in) { c = tid & (C - 1); i = tid >> log2C; } else { i = tid & (L8 - 1); c = tid >> LOG2L8; }
-		if (active) {
+		if (TMA) {
+			__shared__ __align__(8) unsigned long long bar_mem;
+			const unsigned bar = smem_addr(&bar_mem);
+			const unsigned landing = sbase + ((NSTAGES > 1) ? (unsigned) (C * L) * 8u : 0u);      // the half stage 0 does not write
+			if (tid == 0) { fft_mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+			__syncthreads();
+			if (tid == 0) {
+				const unsigned line_bytes = (unsigned) L * 8u;
+				fft_mbar_expect_tx(bar, (unsigned) C * line_bytes);
+				const float2 *g0 = in + in_base;
+				if ((int) P.in_cs == L) fft_bulk_g2s(landing, g0, (unsigned) C * line_bytes, bar);          // adjacent lines: one copy
+				else for (int cc = 0; cc < C; cc++) fft_bulk_g2s(landing + (unsigned) cc * line_bytes, g0 + (long long) cc * P.in_cs, line_bytes, bar);
+			}
+			fft_mbar_wait(bar, 0);
+			if (active) {
+				const unsigned lr = landing + (unsigned) (c * L + i) * 8u;
+				#pragma unroll
+				for (int m = 0; m < 8; m++) v[m] = lds2(lr + (unsigned) (m * L8) * 8u);
+				if (P.conj_in) {
+					#pragma unroll
+					for (int m = 0; m < 8; m++) v[m].y = -v[m].y;
+				}
+			}
+		} else if (active) {
 			const int off = c * (int) P.in_cs + i * (int) P.in_js, step = L8 * (int) P.in_js;
 			if (P.in_real) {
 				const float *gr = reinterpret_cast<const float *>(in) + in_base + off;
@@ -309,6 +268,8 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 					for (int m = 0; m < 8; m++) v[m].y = -v[m].y;
 				}
 			}
+		}
+		if (active) {
 			if (P.exact0) { float2 (&u)[8] = *reinterpret_cast<float2 (*)[8]>(&v[0]); dft8(u, false); }     // layers with eps = 0: plain DFT-8
 			else bf8(v, stw - 1, 1);
 		}
@@ -426,15 +387,6 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	}
 }
 
-__global__ void fft_table_kernel(float2 *table) {
-	const int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q < FFT_TABLE) {
-		double sn, cs;
-		sincospi(-2.0 * (double) q / (double) FFT_TABLE, &sn, &cs);
-		table[q] = make_float2((float) cs, (float) sn);
-	}
-}
-
 // ---- small elementwise helpers -----------------------------------------------------------------------------
 __global__ void k_scale(float2 *d, unsigned long long n, float scale) {
 	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
@@ -544,9 +496,12 @@ __global__ void __launch_bounds__(1024) k_plot_peaks(const double *p0, int n0, c
 	const double *v = blockIdx.x ? p1 : p0;
 	const int n = blockIdx.x ? n1 : n0;
 	double best = -INFINITY; int bi = 0x7fffffff;
-	for (int i = threadIdx.x; i < n; i += blockDim.x) {
-		const double x = v[i];
-		if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+	for (int i0 = threadIdx.x; i0 < n; i0 += 8 * (int) blockDim.x) {      // eight loads in flight per thread, folded in index order
+		double x[8];
+		#pragma unroll
+		for (int u = 0; u < 8; u++) { const int i = i0 + u * (int) blockDim.x; x[u] = (i < n) ? v[i] : -INFINITY; }
+		#pragma unroll
+		for (int u = 0; u < 8; u++) { const int i = i0 + u * (int) blockDim.x; if (i < n && (x[u] > best || (x[u] == best && i < bi))) { best = x[u]; bi = i; } }
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -662,7 +617,7 @@ inline unsigned grid1d(unsigned long long n, int sm_count) {
 	return (unsigned) (want < cap ? (want ? want : 1) : cap);
 }
 
-float2 *g_table[64] = {0};          // per device
+bool g_attr_set[64] = {false};      // per device: the pass kernels' dynamic shared-memory limit has been raised
 // per-pass layer-twiddle tables (see fft_pass_kernel), built on the host in double precision and cached
 struct StageTab { int device, log2L, l_base, pert; float2 *d; };
 std::vector<StageTab> g_stage_tabs;
@@ -718,18 +673,15 @@ int step_table(tsdrgpu_ctx_t *ctx, unsigned long long M, unsigned ncols, unsigne
 }
 
 int ensure_table(tsdrgpu_ctx_t *ctx, cudaStream_t stream) {
-	if (g_table[ctx->device]) return TSDRGPU_OK;
-	float2 *t;
-	CU_TRY(ctx, cudaMalloc(&t, sizeof(float2) * FFT_TABLE));
-	fft_table_kernel<<<FFT_TABLE / 256, 256, 0, stream>>>(t);
-	LAUNCH_CHECK(ctx);
-	CU_TRY(ctx, cudaStreamSynchronize(stream));
-	g_table[ctx->device] = t;
+	(void) stream;
+	if (g_attr_set[ctx->device]) return TSDRGPU_OK;
 	const int max_smem = (int) (2 * sizeof(float2) * FFT_MAX_ELEMS);     // ping-pong
-#define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+#define SET_ATTR(l) CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+	CU_TRY(ctx, cudaFuncSetAttribute(fft_pass_kernel<l, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
 	SET_ATTR(3); SET_ATTR(4); SET_ATTR(5); SET_ATTR(6); SET_ATTR(7); SET_ATTR(8); SET_ATTR(9); SET_ATTR(10); SET_ATTR(11);
 #undef SET_ATTR
+	g_attr_set[ctx->device] = true;
 	return TSDRGPU_OK;
 }
 
@@ -754,12 +706,9 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	if (threads > 512) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "FFT bundle too large", cudaSuccess, __FILE__, __LINE__);
 	const int nstages = P.log2L / 3 + ((P.log2L % 3) ? 1 : 0);
 	const dim3 grid(bundles, batch);
-	const float2 *tab = g_table[ctx->device];
 	if (P.log2L <= 2) {
-		const int LP = L + (L >> 4) + 1;
-		const size_t smem = sizeof(float2) * (size_t) P.C * LP;
-		if (P.log2L == 1) KL(ctx, "fft_pass_kernel", stream, fft_pass_small<1><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse));
-		else KL(ctx, "fft_pass_kernel", stream, fft_pass_small<2><<<grid, threads, smem, stream>>>(in, out, P, tab, inverse));
+		if (P.log2L == 1) KL(ctx, "fft_pass_kernel", stream, fft_tiny_kernel<1><<<dim3(1, batch), 32, 0, stream>>>(in, out, P));
+		else KL(ctx, "fft_pass_kernel", stream, fft_tiny_kernel<2><<<dim3(1, batch), 32, 0, stream>>>(in, out, P));
 		return TSDRGPU_OK;
 	}
 	const float2 *stw;
@@ -772,10 +721,15 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 	}
 	P.exact0 = 1;
 	for (int sidx = 0; sidx < 3 && sidx < P.log2L; sidx++) if (eps_all && l_base + sidx < 40 && fabs(eps_all[l_base + sidx]) > 1e-10) P.exact0 = 0;
-	const size_t smem = sizeof(float2) * (size_t) total * (nstages >= 3 ? 2 : 1);
+	// bulk copies (TMA) feed the passes whose lines are contiguous and 16-byte aligned; TSDRGPU_FFT_NO_TMA=1 keeps the plain loads
+	static const bool no_tma = getenv("TSDRGPU_FFT_NO_TMA") != NULL;
+	const bool tma = !no_tma && !P.c_fast_in && !P.in_real && P.in_js == 1 && P.nfan == 0 && total * 8 == threads * 64
+	                 && ((reinterpret_cast<unsigned long long>(in) | ((unsigned long long) in_bs * 8ull)) & 15ull) == 0;
+	const size_t smem = sizeof(float2) * (size_t) total * ((nstages >= 3 || (tma && nstages == 2)) ? 2 : 1);
 	switch (P.log2L) {
-#define CASE(l) case l: if (P.nfan > 0) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
-	                else KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false><<<grid, threads, smem, stream>>>(in, out, P, stw)); break
+#define CASE(l) case l: if (P.nfan > 0) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, true, false><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
+	                else if (tma) KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false, true><<<grid, threads, smem, stream>>>(in, out, P, stw)); \
+	                else KL(ctx, "fft_pass_kernel", stream, fft_pass_kernel<l, false, false><<<grid, threads, smem, stream>>>(in, out, P, stw)); break
 	CASE(3); CASE(4); CASE(5); CASE(6); CASE(7); CASE(8); CASE(9); CASE(10); CASE(11);
 #undef CASE
 	default: return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "unsupported FFT line length", cudaSuccess, __FILE__, __LINE__);

@@ -437,7 +437,8 @@ def test_plot_peaks_on_the_device_match_the_gui_pick(gpu):
         if case % 13 == 5:
             fp[:] = fp[0]
         got = (C.c_int32 * 2)()
-        gpu.chk(lib.tsdrgpu_plot_peaks(gpu._h, gpu.stream, dev(fp).data_ptr(), n0, dev(lp).data_ptr(), n1, got))
+        d_fp, d_lp = dev(fp), dev(lp)                        # kept alive across the call (a temporary's memory would be reused)
+        gpu.chk(lib.tsdrgpu_plot_peaks(gpu._h, gpu.stream, d_fp.data_ptr(), n0, d_lp.data_ptr(), n1, got))
         assert (got[0], got[1]) == host_pick(fp, lp), f"case {case}"
     det = gpu.framerate_detector()
     fs = 2_000_000
