@@ -218,8 +218,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main(const float *__restrict__ 
 // The rare sample whose bank is not simply what the previous sample left (r <= 1, or a landing within one ulp of a pixel edge)
 // goes through rs_bank_walk, out of line.
 template <bool IQ>
-__device__ __noinline__ bool rs_bank_walk(const float *__restrict__ in, const RsBlock &B, unsigned k, double *bank_out) {
-	const double r = B.r, phase = B.phase;
+__device__ __noinline__ bool rs_bank_walk(const float *__restrict__ in, unsigned long long in_start, double r, double phase, unsigned k, double *bank_out) {
 	long long L = (long long) k - 2;
 	while (L >= 0) {
 		const Geo gl = rs_geo((unsigned) L, r, phase);
@@ -231,7 +230,7 @@ __device__ __noinline__ bool rs_bank_walk(const float *__restrict__ in, const Rs
 	double bank = 0.0;
 	for (unsigned j = (unsigned) L; j < k; j++) {
 		const Geo gj = rs_geo(j, r, phase);
-		bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) rs_load<IQ>(in, B.in_start + j)));
+		bank = __dadd_rn(bank, rs_t(gj, rs_P(gj.c), r, (double) rs_load<IQ>(in, in_start + j)));
 	}
 	*bank_out = bank;
 	return true;
@@ -244,45 +243,68 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__
 	__shared__ __align__(16) float s_out[RS_OUT_CAP + 8];
 	const uint2 ti = tile_info[blockIdx.x];
 	const RsBlock B = blocks[ti.x];
-	const unsigned s0 = ti.y, s1 = min(s0 + (unsigned) RS_TILE, B.size);
+	// Tiles are windows of RS_TILE samples aligned on the input ADDRESS (16 bytes; the host cuts a block's first tile short by
+	// `shift` samples so that every later tile starts aligned): the window starts `shift` samples before s0, and the samples
+	// in front of s0 only serve as "the sample before".  Two rounds of 128 samples per warp cover the window exactly.
+	const unsigned s0 = ti.y;
+	const float *tile_in = in + (IQ ? 2ull : 1ull) * (B.in_start + s0);
+	const int shift = IQ ? (int) ((reinterpret_cast<unsigned long long>(tile_in) >> 3) & 1ull) : (int) ((reinterpret_cast<unsigned long long>(tile_in) >> 2) & 3ull);
+	const unsigned s1 = min(s0 - (unsigned) shift + (unsigned) RS_TILE, B.size);
 	const double r = B.r, phase = B.phase;
+	const unsigned long long in_start = B.in_start;
 	const double pbase_d = (s0 == 0) ? 0.0 : rs_P(rs_geo(s0 - 1, r, phase).c);
 	const unsigned pbase = (unsigned) pbase_d, pend = (unsigned) rs_P(rs_geo(s1 - 1, r, phase).c);
 	float *gout = out + B.out_start;
 	const unsigned aoff = (unsigned) ((reinterpret_cast<unsigned long long>(gout + pbase) >> 2) & 3ull);
 	float *sq = s_out + aoff;
 	const unsigned sq_addr = (unsigned) __cvta_generic_to_shared(s_out) + (aoff << 2);
-	// groups of four samples aligned on the input ADDRESS (16 bytes): the tile starts `shift` samples early
-	const float *tile_in = in + (IQ ? 2ull : 1ull) * (B.in_start + s0);
-	const int shift = IQ ? (int) ((reinterpret_cast<unsigned long long>(tile_in) >> 3) & 1ull) : (int) ((reinterpret_cast<unsigned long long>(tile_in) >> 2) & 3ull);
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const int size = (int) B.size;
-	for (int base = (int) s0 - shift + (int) warp * 128; base < (int) s1; base += (RS_THREADS / 32) * 128) {
-		const int k0 = base + 4 * (int) lane;
-		// ---- the four samples of this thread (zero outside the block)
-		float vf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-		if (k0 >= 0 && k0 + 3 < size) {
-			if (IQ) {
-				const float4 *p4 = reinterpret_cast<const float4 *>(in + 2ull * (B.in_start + (unsigned) k0));
-				const float4 a = ldg_stream_f4(p4), b = ldg_stream_f4(p4 + 1);
-				vf[0] = mag_exact(a.x, a.y); vf[1] = mag_exact(a.z, a.w); vf[2] = mag_exact(b.x, b.y); vf[3] = mag_exact(b.z, b.w);
-			} else {
-				const float4 a = ldg_stream_f4(reinterpret_cast<const float4 *>(in + B.in_start + (unsigned) k0));
-				vf[0] = a.x; vf[1] = a.y; vf[2] = a.z; vf[3] = a.w;
+	constexpr int ROUNDS = RS_TILE / (RS_THREADS * 4);       // 2
+	// ---- all loads of the tile first (four 16-byte loads in flight per thread), then the magnitudes
+	float vf[ROUNDS][4];
+	{
+		float4 raw[ROUNDS][IQ ? 2 : 1];
+		bool fast[ROUNDS];
+		#pragma unroll
+		for (int rd = 0; rd < ROUNDS; rd++) {
+			const int k0 = (int) s0 - shift + rd * (RS_THREADS * 4) + (int) warp * 128 + 4 * (int) lane;
+			fast[rd] = k0 >= 0 && k0 + 3 < size;
+			if (fast[rd]) {
+				if (IQ) {
+					const float4 *p4 = reinterpret_cast<const float4 *>(in + 2ull * (in_start + (unsigned) k0));
+					raw[rd][0] = ldg_stream_f4(p4); raw[rd][IQ ? 1 : 0] = ldg_stream_f4(p4 + 1);
+				} else raw[rd][0] = ldg_stream_f4(reinterpret_cast<const float4 *>(in + in_start + (unsigned) k0));
 			}
-		} else {
-			#pragma unroll
-			for (int j = 0; j < 4; j++) if (k0 + j >= 0 && k0 + j < size) vf[j] = rs_load<IQ>(in, B.in_start + (unsigned) (k0 + j));
 		}
+		#pragma unroll
+		for (int rd = 0; rd < ROUNDS; rd++) {
+			const int k0 = (int) s0 - shift + rd * (RS_THREADS * 4) + (int) warp * 128 + 4 * (int) lane;
+			if (fast[rd]) {
+				if (IQ) {
+					const float4 a = raw[rd][0], b = raw[rd][IQ ? 1 : 0];
+					vf[rd][0] = mag_exact(a.x, a.y); vf[rd][1] = mag_exact(a.z, a.w); vf[rd][2] = mag_exact(b.x, b.y); vf[rd][3] = mag_exact(b.z, b.w);
+				} else { const float4 a = raw[rd][0]; vf[rd][0] = a.x; vf[rd][1] = a.y; vf[rd][2] = a.z; vf[rd][3] = a.w; }
+			} else {
+				#pragma unroll
+				for (int j = 0; j < 4; j++) vf[rd][j] = (k0 + j >= 0 && k0 + j < size) ? rs_load<IQ>(in, in_start + (unsigned) (k0 + j)) : 0.0f;
+			}
+		}
+	}
+	#pragma unroll
+	for (int rd = 0; rd < ROUNDS; rd++) {
+		const int k0 = (int) s0 - shift + rd * (RS_THREADS * 4) + (int) warp * 128 + 4 * (int) lane;
+		if (k0 - 4 * (int) lane >= (int) s1) break;           // the whole warp is past the tile's end (uniform per warp)
+		const float *v4 = vf[rd];
 		if (IQ && mag_out != NULL) {                          // the demodulated stream, for the frame-rate detector: owned samples only
-			float *m = mag_out + ((long long) B.in_start + k0);   // (k0 may be negative: the pointer is only dereferenced under the masks below)
+			float *m = mag_out + ((long long) in_start + k0);   // (k0 may be negative: the pointer is only dereferenced under the masks below)
 			const bool all_owned = k0 >= (int) s0 && k0 + 3 < (int) s1;
 			const unsigned ma = (unsigned) ((reinterpret_cast<unsigned long long>(m) >> 2) & 3ull);
-			if (all_owned && ma == 0) *reinterpret_cast<float4 *>(m) = make_float4(vf[0], vf[1], vf[2], vf[3]);
-			else if (all_owned && ma == 2) { *reinterpret_cast<float2 *>(m) = make_float2(vf[0], vf[1]); *reinterpret_cast<float2 *>(m + 2) = make_float2(vf[2], vf[3]); }
+			if (all_owned && ma == 0) *reinterpret_cast<float4 *>(m) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+			else if (all_owned && ma == 2) { *reinterpret_cast<float2 *>(m) = make_float2(v4[0], v4[1]); *reinterpret_cast<float2 *>(m + 2) = make_float2(v4[2], v4[3]); }
 			else {
 				#pragma unroll
-				for (int j = 0; j < 4; j++) if (k0 + j >= (int) s0 && k0 + j < (int) s1) m[j] = vf[j];
+				for (int j = 0; j < 4; j++) if (k0 + j >= (int) s0 && k0 + j < (int) s1) m[j] = v4[j];
 			}
 		}
 		// ---- geometry of the four samples (dsp.c:282-284), all exact single IEEE operations
@@ -297,7 +319,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__
 			double pk = ceil(cc[j]);
 			if (!(cc[j] > 0.0)) pk = 0.0;                     // == rs_P
 			P[j] = pk;
-			T[j] = __dmul_rn((pk < hi[j] && pk > lo[j]) ? __dsub_rn(hi[j], pk) : r, (double) vf[j]);      // == rs_t
+			T[j] = __dmul_rn((pk < hi[j] && pk > lo[j]) ? __dsub_rn(hi[j], pk) : r, (double) v4[j]);      // == rs_t
 		}
 		// ---- the sample before this thread's first one: from the lane below, lane 0 works it out itself
 		const int a3 = (P[2] < lo[3] && P[2] < cc[3]) ? 1 : 0;            // does this thread's last sample emit an A pixel?  (dsp.c:288)
@@ -310,7 +332,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__
 				const Geo gp = rs_geo(kp, r, phase);
 				Pm = rs_P(gp.c);
 				Am = rs_isA(gp, kp == 0 ? 0.0 : rs_P(rs_geo(kp - 1, r, phase).c)) ? 1 : 0;
-				Tm = rs_t(gp, Pm, r, (double) rs_load<IQ>(in, B.in_start + kp));
+				Tm = rs_t(gp, Pm, r, (double) rs_load<IQ>(in, in_start + kp));
 			}
 		}
 		const double Pprev[4] = {Pm, P[0], P[1], P[2]}, Tprev[4] = {Tm, T[0], T[1], T[2]};
@@ -326,21 +348,21 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__
 			const bool isA = A[j], prevA = Aprev[j];
 			if (k < (int) s0 || k >= (int) s1) continue;      // not this tile's sample (alignment lead-in, or past the end)
 			const unsigned p0 = (unsigned) Pkm1, cnt = (unsigned) P[j] - p0;
-			float first = vf[j];
+			float first = v4[j];
 			bool write_first = true;
 			if (isA) {
 				double bank = 0.0;
 				bool have = false;
 				if (k > 0 && prevA) { bank = __dadd_rn(0.0, prevT); have = true; }      // the common case for r > 1
-				else if (k > 0) have = rs_bank_walk<IQ>(in, B, (unsigned) k, &bank);
-				if (have) first = __double2float_rn(__dadd_rn(bank, __dmul_rn((double) vf[j], __dadd_rn(__dsub_rn(1.0, lo[j]), Pkm1))));
+				else if (k > 0) have = rs_bank_walk<IQ>(in, in_start, r, phase, (unsigned) k, &bank);
+				if (have) first = __double2float_rn(__dadd_rn(bank, __dmul_rn((double) v4[j], __dadd_rn(__dsub_rn(1.0, lo[j]), Pkm1))));
 				else write_first = false;                     // the bank reaches past the block start -> rs_fixup writes this pixel
 			}
 			const unsigned d = sq_addr + ((p0 - pbase) << 2);
 			if (cnt > 0 && write_first) sts_f32(d, first);
-			if (cnt > 1) sts_f32(d + 4, vf[j]);
-			if (cnt > 2) sts_f32(d + 8, vf[j]);
-			for (unsigned c = 3; c < cnt; c++) sts_f32(d + 4 * c, vf[j]);
+			if (cnt > 1) sts_f32(d + 4, v4[j]);
+			if (cnt > 2) sts_f32(d + 8, v4[j]);
+			for (unsigned c = 3; c < cnt; c++) sts_f32(d + 4 * c, v4[j]);
 		}
 	}
 	__syncthreads();
@@ -557,7 +579,7 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 
 	// descriptor slot: [RsBlock x nblocks][{block, first sample} x tiles]
 	size_t max_tiles = 0;
-	for (uint32_t b = 0; b < nblocks; b++) max_tiles += ((size_t) (block_sizes ? block_sizes[b] : uniform_block) + RS_TILE - 1) / RS_TILE;
+	for (uint32_t b = 0; b < nblocks; b++) max_tiles += ((size_t) (block_sizes ? block_sizes[b] : uniform_block) + RS_TILE - 1) / RS_TILE + 1;
 	const size_t need = sizeof(tsdrgpu_rs_block_t) * nblocks + sizeof(uint2) * (max_tiles + 1);
 	const int slot = r->next; r->next = (r->next + 1) % tsdrgpu_resampler::SLOTS;
 	CU_TRY(ctx, cudaEventSynchronize(r->ev[slot]));
@@ -579,8 +601,18 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 	if (total > out_capacity)
 		return tsdrgpu_fail(ctx, TSDRGPU_ECAPACITY, "resampler output buffer too small", cudaSuccess, __FILE__, __LINE__);
 	unsigned tiles = 0, max_out = 0;
+	// rs_main4 (four samples per thread) stages every tile's pixels in shared memory: ratios up to 3; beyond that, and on
+	// request (TSDRGPU_RS_V1=1, the cross-check of the tests), the one-sample-per-thread kernel.  rs_main4's tiles are windows
+	// aligned on the input address: a block's first tile is cut short by the samples its start lies past a 16-byte boundary.
+	const double ratio = upsample_by / downsample_by;
+	const bool v1 = getenv("TSDRGPU_RS_V1") != NULL || !(ratio <= 2.99) || nearest;
 	for (uint32_t b = 0; b < nblocks; b++) {
-		for (unsigned s0 = 0; s0 < hb[b].size; s0 += RS_TILE) hp[tiles++] = make_uint2(b, s0);
+		unsigned lead = 0;
+		if (!v1) {
+			const unsigned long long addr = reinterpret_cast<unsigned long long>(d_in) + (in_is_iq ? 8ull : 4ull) * hb[b].in_start;
+			lead = in_is_iq ? (unsigned) ((addr >> 3) & 1ull) : (unsigned) ((addr >> 2) & 3ull);
+		}
+		for (unsigned s0 = 0; s0 < hb[b].size; s0 = (s0 == 0) ? RS_TILE - lead : s0 + RS_TILE) hp[tiles++] = make_uint2(b, s0);
 		if (hb[b].n_out > max_out) max_out = hb[b].n_out;
 	}
 	CU_TRY(ctx, cudaMemcpyAsync(r->d_desc[slot], r->h_desc[slot], need, cudaMemcpyHostToDevice, stream));
@@ -601,10 +633,6 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			CU_TRY(ctx, cudaMalloc(&r->d_bank, sizeof(double) * r->bank_cap));
 			CU_TRY(ctx, cudaMalloc(&r->d_has_a, sizeof(int) * r->bank_cap));
 		}
-		// rs_main4 (four samples per thread) stages every tile's pixels in shared memory: ratios up to 3; beyond that, and on
-		// request (TSDRGPU_RS_V1=1, the cross-check of the tests), the one-sample-per-thread kernel
-		const double ratio = upsample_by / downsample_by;
-		const bool v1 = getenv("TSDRGPU_RS_V1") != NULL || !(ratio <= 2.99);
 		if (v1) {
 			if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
 			else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
