@@ -26,11 +26,23 @@ def main():
             continue
         print(f"  roofline: {r['kernel']}: {r['achieved']:.0f} of {r['peak']:.0f} {r['unit']} = {100 * r['frac']:.1f} %"
               f"  (traffic {r.get('traffic')} B/launch, algorithmic {r.get('algorithmic_bytes_per_launch', 0):.0f} B/launch)")
-        print(f"  {'kernel':22s} {'ms/step':>8s} {'launches':>8s} {'alg GB/s':>9s} {'of peak':>8s}")
-        for k, v in sorted(r.get("per_kernel", {}).items(), key=lambda kv: -kv[1]["ms_per_step"]):
+        ws = r.get("whole_step")
+        if ws:
+            print(f"  whole batch vs SURVEY 8d bytes: {ws['achieved_gbs']:.0f} GB/s = {100 * ws['frac']:.1f} % ({ws['ms_per_batch']:.4f} ms per batch)")
+        # round 1 files say ms_per_step / launches_per_step (a step was one batch of 64 frames), round 2 files ms_per_batch
+        ms = lambda v: v.get("ms_per_batch", v.get("ms_per_step"))
+        ln = lambda v: v.get("launches_per_batch", v.get("launches_per_step"))
+        print(f"  {'kernel':22s} {'ms/batch':>8s} {'launches':>8s} {'alg GB/s':>9s} {'of peak':>8s}")
+        for k, v in sorted(r.get("per_kernel", {}).items(), key=lambda kv: -ms(kv[1])):
             gbs = f"{v['achieved_gbs']:.0f}" if "achieved_gbs" in v else "-"
             frac = f"{100 * v['frac']:.0f} %" if "frac" in v else "-"
-            print(f"  {k:22s} {v['ms_per_step']:8.4f} {v['launches_per_step']:8.1f} {gbs:>9s} {frac:>8s}")
+            print(f"  {k:22s} {ms(v):8.4f} {ln(v):8.1f} {gbs:>9s} {frac:>8s}")
+        if "pinned_process" in e2e:
+            pp = e2e["pinned_process"]
+            print(f"  e2e beside the headline: pinned process() {pp['value'] / 1e3:.2f} GS/s = {100 * pp.get('of_link_bound', 0):.0f} % of the measured link bound")
+        if "autocorr_sweep" in d:
+            for size, v in d["autocorr_sweep"].items():
+                print(f"  autocorr {size}: {v['us_per_autocorrelation']:.2f} us  {v['gbs_vs_bytes_moved']:.0f} GB/s moved ({100 * v['frac_vs_bytes_moved']:.0f} %)  {v['gbs_vs_28N']:.0f} GB/s vs 28N ({100 * v['frac_vs_28N']:.0f} %)")
         for key in ("e2e_int8_transport", "superbandwidth", "variants"):
             if key in d:
                 print(f"  {key}: {json.dumps(d[key])[:400]}")

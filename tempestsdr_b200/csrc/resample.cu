@@ -59,6 +59,9 @@ __device__ __forceinline__ double rs_t(const Geo &g, double Pk, double r, double
 	if (Pk < g.hi && Pk > g.lo) return __dmul_rn(__dsub_rn(g.hi, Pk), v);
 	return __dmul_rn(r, v);
 }
+__device__ __forceinline__ void sts_f32_if(unsigned addr, float v, bool p) {
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" :: "r"(addr), "f"(v), "r"((int) p) : "memory");
+}
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
 // does sample k emit an A pixel?  (dsp.c:288)
 __device__ __forceinline__ bool rs_isA(const Geo &g, double Pkm1) { return Pkm1 < g.lo && Pkm1 < g.c; }
@@ -340,29 +343,25 @@ __global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__
 		#pragma unroll
 		for (int j = 0; j < 4; j++) A[j] = Pprev[j] < lo[j] && Pprev[j] < cc[j];
 		const bool Aprev[4] = {Am != 0, A[0], A[1], A[2]};
-		// ---- emit: sample k owns pixels P(k-1) .. P(k)-1 (see the header of this file)
+		// ---- emit: sample k owns pixels P(k-1) .. P(k)-1 (see the header of this file).  Straight-line code: the A value is
+		// computed for every sample and selected, the stores are predicated instructions (r <= 2: at most three pixels per
+		// sample); the only branch left is the rare bank walk.
 		#pragma unroll
 		for (int j = 0; j < 4; j++) {
 			const int k = k0 + j;
-			const double Pkm1 = Pprev[j], prevT = Tprev[j];
-			const bool isA = A[j], prevA = Aprev[j];
-			if (k < (int) s0 || k >= (int) s1) continue;      // not this tile's sample (alignment lead-in, or past the end)
+			const double Pkm1 = Pprev[j];
+			const bool own = k >= (int) s0 && k < (int) s1;   // not owned: alignment lead-in, or past the tile's end
 			const unsigned p0 = (unsigned) Pkm1, cnt = (unsigned) P[j] - p0;
-			float first = v4[j];
-			bool write_first = true;
-			if (isA) {
-				double bank = 0.0;
-				bool have = false;
-				if (k > 0 && prevA) { bank = __dadd_rn(0.0, prevT); have = true; }      // the common case for r > 1
-				else if (k > 0) have = rs_bank_walk<IQ>(in, in_start, r, phase, (unsigned) k, &bank);
-				if (have) first = __double2float_rn(__dadd_rn(bank, __dmul_rn((double) v4[j], __dadd_rn(__dsub_rn(1.0, lo[j]), Pkm1))));
-				else write_first = false;                     // the bank reaches past the block start -> rs_fixup writes this pixel
-			}
+			double bank = __dadd_rn(0.0, Tprev[j]);           // the common case for r > 1: what the previous sample left
+			bool have = k > 0 && Aprev[j];
+			if (A[j] && !Aprev[j] && k > 0 && own) have = rs_bank_walk<IQ>(in, in_start, r, phase, (unsigned) k, &bank);   // rare
+			const float aval = __double2float_rn(__dadd_rn(bank, __dmul_rn((double) v4[j], __dadd_rn(__dsub_rn(1.0, lo[j]), Pkm1))));
+			const float first = A[j] ? aval : v4[j];
+			// an A pixel whose bank reaches past the block start is left to rs_fixup (have == false)
 			const unsigned d = sq_addr + ((p0 - pbase) << 2);
-			if (cnt > 0 && write_first) sts_f32(d, first);
-			if (cnt > 1) sts_f32(d + 4, v4[j]);
-			if (cnt > 2) sts_f32(d + 8, v4[j]);
-			for (unsigned c = 3; c < cnt; c++) sts_f32(d + 4 * c, v4[j]);
+			sts_f32_if(d, first, own && cnt > 0 && (!A[j] || have));
+			sts_f32_if(d + 4, v4[j], own && cnt > 1);
+			sts_f32_if(d + 8, v4[j], own && cnt > 2);
 		}
 	}
 	__syncthreads();
@@ -602,10 +601,11 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 		return tsdrgpu_fail(ctx, TSDRGPU_ECAPACITY, "resampler output buffer too small", cudaSuccess, __FILE__, __LINE__);
 	unsigned tiles = 0, max_out = 0;
 	// rs_main4 (four samples per thread) stages every tile's pixels in shared memory: ratios up to 3; beyond that, and on
-	// request (TSDRGPU_RS_V1=1, the cross-check of the tests), the one-sample-per-thread kernel.  rs_main4's tiles are windows
+	// request (TSDRGPU_RS_V1=1, the cross-check of the tests), the one-sample-per-thread kernel (every geometry the reference
+	// can produce has r = (int)(2x)/x <= 2, TSDRLibrary.c:540-550).  rs_main4's tiles are windows
 	// aligned on the input address: a block's first tile is cut short by the samples its start lies past a 16-byte boundary.
 	const double ratio = upsample_by / downsample_by;
-	const bool v1 = getenv("TSDRGPU_RS_V1") != NULL || !(ratio <= 2.99) || nearest;
+	const bool v1 = getenv("TSDRGPU_RS_V1") != NULL || !(ratio <= 2.0) || nearest;      // r <= 2: a sample emits at most 3 pixels
 	for (uint32_t b = 0; b < nblocks; b++) {
 		unsigned lead = 0;
 		if (!v1) {
