@@ -129,7 +129,7 @@ class DeviceStep:
         max_pix = int(self.rs.plan((self.block, self.nblocks), self.up, float(FS))) + 1024
         self.pix = torch.empty(max_pix + self.n + 1024, dtype=torch.float32, device=iq_dev.device)
         self.pix_fill = 0
-        self.frames_out = [torch.empty(FRAMES_PER_BATCH * self.n, dtype=torch.float32, device=iq_dev.device) for _ in range(2)]
+        self.frames_out = [torch.empty((FRAMES_PER_BATCH + 2) * self.n, dtype=torch.float32, device=iq_dev.device) for _ in range(2)]
         self.pairs = self.block * self.nblocks
         self.mag = torch.empty(self.cap + self.pairs, dtype=torch.float32, device=iq_dev.device)   # demodulated stream, capture-aligned
         self.mag_fill = 0
@@ -137,6 +137,7 @@ class DeviceStep:
         self.captures = 0
         self.k = 0
         self.chunk = int(os.environ.get("BENCH_FRAME_CHUNK", "0"))
+        self.l2_frames = int(os.environ.get("BENCH_L2_FRAMES", "0"))
 
     def __call__(self):
         gpu = self.gpu
@@ -144,23 +145,31 @@ class DeviceStep:
         # (the same pass also leaves the magnitudes for the frame-rate detector: one demodulation feeds both consumers,
         # as am_demod does in the reference's process(), TSDRLibrary.c:286-292)
         fused_mag = not os.environ.get("BENCH_SEPARATE_DEMOD")
-        out = self.rs.process(self.iq, (self.block, self.nblocks), self.up, float(FS), in_is_iq=True, out=self.pix[self.pix_fill:],
-                              mag_out=self.mag[self.mag_fill:] if fused_mag else None)
-        self.pix_fill += out.numel()
-        nf = min(self.pix_fill // self.n, FRAMES_PER_BATCH)
-        # the frame stage in sub-batches of `chunk` frames (default: the whole step at once).  Smaller sub-batches keep a batch's
-        # intermediate frames in L2 between the kernels of the stage at the price of more launches.
-        chunk = self.chunk if self.chunk > 0 else nf
+        # The batch goes through resampler + frame stage in sub-batches of `self.l2_frames` frames (BENCH_L2_FRAMES; default: the
+        # whole batch at once): with sub-batches of 16 frames the pixels a resampler launch writes (53 MB), the frames the frame
+        # stage hands from kernel to kernel and its output stay inside the 126 MB L2 from one kernel to the next, and the same
+        # pixel buffer is written again before most of it was ever evicted.  This is what tsdrgpu_pipeline_* does with
+        # batch_frames = 16 (the e2e path); here it is a knob of the device-resident step.
+        cf = self.l2_frames if self.l2_frames > 0 else FRAMES_PER_BATCH
         fo = self.frames_out[self.k & 1]
-        for c0 in range(0, nf, chunk):
-            c1 = min(nf, c0 + chunk)
-            self.pp.process(self.pix[c0 * self.n: c1 * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=fo[c0 * self.n: c1 * self.n], want_results=False)
+        done = 0
+        for b0 in range(0, self.nblocks, 10 * cf):
+            nb = min(10 * cf, self.nblocks - b0)
+            out = self.rs.process(self.iq[2 * self.block * b0: 2 * self.block * (b0 + nb)], (self.block, nb), self.up, float(FS), in_is_iq=True,
+                                  out=self.pix[self.pix_fill:], mag_out=self.mag[self.mag_fill + self.block * b0:] if fused_mag else None)
+            self.pix_fill += out.numel()
+            nf = min(self.pix_fill // self.n, FRAMES_PER_BATCH + 1 - done)
+            chunk = self.chunk if self.chunk > 0 else nf
+            for c0 in range(0, nf, chunk):
+                c1 = min(nf, c0 + chunk)
+                self.pp.process(self.pix[c0 * self.n: c1 * self.n], self.w, HEIGHT, 0.0, 0.1, self.flags, out=fo[(done + c0) * self.n: (done + c1) * self.n], want_results=False)
+            left = self.pix_fill - nf * self.n
+            if left and nf:                                                      # left << nf*n: the ranges do not overlap
+                gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, self.pix.data_ptr(), self.pix.data_ptr() + 4 * nf * self.n, 4 * left))
+            self.pix_fill = left
+            done += nf
         self.k += 1
-        left = self.pix_fill - nf * self.n
-        if left:                                                             # left << nf*n: the ranges do not overlap
-            gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, self.pix.data_ptr(), self.pix.data_ptr() + 4 * nf * self.n, 4 * left))
-        self.pix_fill = left
-        self.frames += nf
+        self.frames += done
         # frame-rate detector: the whole stream is demodulated once; every complete capture of 3.1*fs/55 samples is
         # autocorrelated (batched FFTs) and accumulated in order
         if not fused_mag:
@@ -427,7 +436,7 @@ def run_ours(args):
     # the link under the e2e number: pinned H2D and D2H of one batch's bytes, alone and together (context, not a claim)
     def link_gbs():
         d_in = torch.empty_like(iq_dev); h_out = torch.empty(FRAMES_PER_BATCH * batch.n, dtype=torch.float32).pin_memory()
-        d_out = batch.frames_out[0]
+        d_out = batch.frames_out[0][: FRAMES_PER_BATCH * batch.n]
         s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
         res = {}
         reps = 4

@@ -767,7 +767,10 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs, eps_all, 0);
 	}
 	int rc;
-	if (log2N <= 20) {                                  // N = N1 * N2 (lines <= 1024) ; n = N2*n1 + n2 ; k = k1 + N1*k2
+	// two passes up to 2^21 (1024 x 2048: the 2048-point lines go to the contiguous pass, one TMA bulk copy per 2-line bundle);
+	// TSDRGPU_FFT_2PASS_MAX=20 restores three passes at 2^21 for comparison
+	static const unsigned two_pass_max = getenv("TSDRGPU_FFT_2PASS_MAX") ? (unsigned) atoi(getenv("TSDRGPU_FFT_2PASS_MAX")) : 21u;
+	if (log2N <= two_pass_max && log2N <= 22) {         // N = N1 * N2 ; n = N2*n1 + n2 ; k = k1 + N1*k2
 		// odd log2 N: the SHORTER line goes to the strided pass (bundle of 8 columns = 64-byte runs instead of 4 = 32-byte runs on
 		// both its loads and its stores); TSDRGPU_FFT_SPLIT=ceil restores the other split for comparison
 		static const bool split_ceil = getenv("TSDRGPU_FFT_SPLIT") && !strcmp(getenv("TSDRGPU_FFT_SPLIT"), "ceil");

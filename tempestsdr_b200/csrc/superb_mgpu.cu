@@ -1,28 +1,33 @@
 // superb_mgpu.cu -- a22 with one hop per GPU: superb_ondataready (superbandwidth.c:121-152) sharded over H GPUs of one node.
 //
 // The reference aligns H hops against hop 0 (H-1 cross-correlations), transforms each hop, concatenates the spectra and runs
-// one H*N-point inverse transform.  Sharded, rank q owns hop q and nothing is done twice:
+// one H*N-point inverse fft_perform: bit reversal, then radix-2 decimation-in-time stages 0 .. log2(HN)-1, each with ITS OWN
+// slightly wrong angle (fft.c:161; tsdrgpu_fft_reference_eps: 2.6e-5 relative at stage 22).  The sharding follows exactly that
+// structure, so the result tracks the reference as closely as the one-GPU path does (1e-6 of the peak), not merely the true DFT:
+// after bit reversal, block rev(t) of the big array holds the inputs k = H u + t, and the first log2 N stages turn it into the
+// N-point transform of that decimated sub-sequence; the last log2 H stages combine the H blocks position by position.
 //
-//   phase 1  local    X_q = FFT_N(hop_q)/N,  D_q = FFT_nd(first difference of |hop_q|)/nd          -> own window
-//   phase 2  lag      P = conj(D_0) D_q, IFFT_nd, grid argmax -> lag_q, written into every rank's window together with its flag
-//                     (no host round trip).  D_0 comes from the rank's OWN copy of hop 0 when the caller keeps the alignment
-//                     reference on every device (d_hop0: the pipeline copies the first hop to all devices while the later
-//                     hops are still being recorded; 23 us of redundant transform instead of a broadcast whose source link
-//                     carries (H-1) x 8 nd bytes); without it D_0 is READ FROM RANK 0 over NVLink inside the multiply, after
-//                     an extra barrier (SPEC)
-//   barrier  LAG      (flags in peer memory; also: every X is in its window)
-//   phase 3  mix      all-to-all instead of an all-gather: rank r owns the bins m in [r N/H, (r+1) N/H).  It PULLS X_q[m] from
-//                     every rank q, forms for all residues s
-//                         V_s[m] = e^{2 pi i m s/(H N)} sum_q e^{2 pi i (q s/H + m lag_q/N)} X_q[m]
-//                     (rotating hop q by lag_q samples == a phase ramp on its spectrum) and PUSHES V_s[m] into rank s's window:
-//                     every rank receives 2 (H-1)/H N complex values instead of (H-1) N -- at H = 8, 3.5x less NVLink traffic
+//   phase 1  local    X_q = FFT_N(hop_q)/N  (fft_perform on the hop, as superbandwidth.c:138-140);
+//                     lag_q: P = conj(D_0) D_q, IFFT_nd, grid argmax, D = FFT_nd(first difference of |hop|)/nd.  D_0 comes from the
+//                     rank's OWN copy of hop 0 when the caller keeps the alignment reference on every device (d_hop0: the
+//                     pipeline copies the first hop to all devices while the later hops are still being recorded; 23 us of
+//                     redundant transform instead of a broadcast whose source link carries (H-1) x 8 nd bytes); without it D_0
+//                     is READ FROM RANK 0 over NVLink inside the multiply, after an extra barrier (SPEC).
+//                     Rotating the hop by lag_q samples (superbandwidth.c:135-137) is a phase ramp on its spectrum: applied
+//                     here, locally, while the spectrum is re-ordered for the exchange:
+//                         Xp_q[t][u'] = X_q[t + H u'] e^{2 pi i (t + H u') lag_q / N}         -> own window, one run per destination t
+//   barrier  LAG      (flags in peer memory; the lag rides along for the record)
+//   phase 2  blocks   all-to-all #1: rank t PULLS its run from every rank (contiguous N/H values each) -> B_t[u] = X~[H u + t],
+//                     then A_t = IDFT_N(B_t) with the reference's stage angles (the one-GPU transform, unchanged) -> own window
 //   barrier  MIX
-//   phase 4  residue  y[H p + s] = IDFT_N{V_s}[p] on rank s (the H N-point inverse decomposes exactly: DESIGN.md section 6),
-//                     |y| (am_demod, TSDRLibrary.c:244-262: what process() does to superb_run's output) stored as float32 BY
-//                     THE LAST BUTTERFLIES OF THE TRANSFORM into slot s of the ROOT rank's window (peer stores over NVLink,
-//                     4 B per sample: SURVEY 8e option B) -- the transfer overlaps the transform
+//   phase 3  combine  all-to-all #2: rank r owns the positions v in [r N/H, (r+1) N/H).  It PULLS A_t[v] from every rank, runs
+//                     the reference's last log2 H radix-2 stages across the H blocks (their perturbed angles, twiddles in double),
+//                     takes |y| (am_demod, TSDRLibrary.c:244-262: what process() does to superb_run's output) and PUSHES
+//                     y[v + N c], c = 0..H-1, as float32 into the ROOT's window -- already time-contiguous, in runs of N/H
+//                     samples (SURVEY 8e option B: 4 B per sample)
 //   barrier  RES      (root only waits)
-//   phase 5  root     interleave the H residue slots into the time-contiguous magnitude stream -> decimator -> frames
+//   phase 4  root     one device-to-device copy of the stream to where the caller wants it -> decimator -> frames
+//   NVLink traffic per rank: 2 (H-1)/H N complex in (an all-gather would be (H-1) N), the root takes (H-1) N floats.
 //
 // Synchronisation between ranks never touches the host and never calls a collective library: every window starts with a
 // small header of epoch-valued flags; a one-CTA kernel between phases stores this rank's flag into every peer (release,
@@ -32,7 +37,7 @@
 // other devices of this process (cudaDeviceEnablePeerAccess: the C host library with TSDR_CUDA_DEVICES).
 //
 // Parity: lags exact (same float operations as the one-GPU path up to the transform, first-maximum argmax); samples are
-// tolerance-based like every FFT result here (the summation order differs from the reference's radix-2 code).
+// tolerance-based like every FFT result here: <= 1e-5 of the peak against superb_ondataready + am_demod (measured ~1e-6).
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -103,66 +108,76 @@ __global__ void __launch_bounds__(256) sbm_xcorr_pull(const float4 *__restrict__
 	}
 }
 
-// the all-to-all mix (phase 3, see the header).  One thread per bin m of this rank's range.
-struct MixArgs { Peers peers; size_t off_x, off_v; int H, log2H, rank; unsigned n; };
-template <int H>
-__global__ void __launch_bounds__(256) sbm_mix(MixArgs A) {
-	__shared__ float2 root[H];                        // e^{2 pi i j / H}
-	__shared__ int lag[H];
-	if (threadIdx.x < H) {
-		double sn, cs;
-		sincospi(2.0 * (double) threadIdx.x / (double) H, &sn, &cs);
-		root[threadIdx.x] = make_float2((float) cs, (float) sn);
-		lag[threadIdx.x] = reinterpret_cast<const WinHeader *>(A.peers.win[A.rank])->lag[threadIdx.x];
-	}
-	__syncthreads();
-	const unsigned n = A.n, per = n / H, m0 = (unsigned) A.rank * per;
+// phase 1 epilogue: Xp[t][u'] = X[t + H u'] e^{2 pi i (t + H u') lag / N} -- the spectrum re-ordered so that what rank t will
+// pull is one contiguous run, with this hop's alignment ramp applied (the argument is reduced exactly in integers)
+__global__ void __launch_bounds__(256) sbm_permute_ramp(const float2 *__restrict__ X, float2 *__restrict__ Xp, unsigned n, int log2H, const int *__restrict__ lag_) {
+	const unsigned lag = (unsigned) *lag_, per = n >> log2H;
 	const float inv_n = 1.0f / (float) n;             // n is a power of two: exact
-	for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < per; j += gridDim.x * blockDim.x) {
-		const unsigned m = m0 + j;
-		float2 x[H];
-		#pragma unroll
-		for (int q = 0; q < H; q++) x[q] = ld_peer_f2(reinterpret_cast<const float2 *>(A.peers.win[q] + A.off_x) + m);     // H loads in flight
-		// z_q = e^{2 pi i m lag_q / N} X_q[m]: the argument is reduced exactly in integers before it becomes a float
-		#pragma unroll
-		for (int q = 0; q < H; q++) {
-			const unsigned e = (unsigned) (((unsigned long long) m * (unsigned long long) (unsigned) lag[q]) & (unsigned long long) (n - 1));
-			float sn, cs;
-			sincospif(2.0f * ((float) e * inv_n), &sn, &cs);
-			x[q] = make_float2(x[q].x * cs - x[q].y * sn, x[q].x * sn + x[q].y * cs);
-		}
-		// ramp e^{2 pi i m s/(H N)} = b^s, b = e^{2 pi i m/(H N)}: one double sincospi, the powers by double multiplication
-		double bs, bc;
-		sincospi(2.0 * ((double) m / ((double) H * (double) n)), &bs, &bc);
-		double pr = 1.0, pi_ = 0.0;
-		#pragma unroll
-		for (int s = 0; s < H; s++) {
-			float ar = 0.0f, ai = 0.0f;                // H-point DFT across the hops, sign +
-			#pragma unroll
-			for (int q = 0; q < H; q++) {
-				const float2 w = root[(q * s) & (H - 1)];
-				ar += w.x * x[q].x - w.y * x[q].y; ai += w.x * x[q].y + w.y * x[q].x;
-			}
-			const float rr = (float) pr, ri = (float) pi_;
-			reinterpret_cast<float2 *>(A.peers.win[s] + A.off_v)[m] = make_float2(ar * rr - ai * ri, ar * ri + ai * rr);    // peer store
-			const double nr = pr * bc - pi_ * bs, ni = pr * bs + pi_ * bc;
-			pr = nr; pi_ = ni;
-		}
+	for (unsigned o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+		const unsigned t = o / per, up = o - t * per, m = t + (up << log2H);
+		const float2 x = __ldg(X + m);
+		const unsigned e = (unsigned) (((unsigned long long) m * (unsigned long long) lag) & (unsigned long long) (n - 1));
+		float sn, cs;
+		sincospif(2.0f * ((float) e * inv_n), &sn, &cs);
+		Xp[o] = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
 	}
 }
 
-// root: stream[H p + s] = slot_s[p]
+// phase 2: B_t = [ run t of rank 0 | run t of rank 1 | ... ]  (N/H complex from each peer, 16-byte loads over NVLink)
+struct PullArgs { Peers peers; size_t off_xp; int H, rank; unsigned per; };
+__global__ void __launch_bounds__(256) sbm_pull_blocks(PullArgs A, float4 *__restrict__ dst) {
+	const unsigned per2 = A.per >> 1, total = per2 * (unsigned) A.H;       // float4 = two complex values
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const unsigned q = i / per2, j = i - q * per2;
+		const float4 *src = reinterpret_cast<const float4 *>(A.peers.win[q] + A.off_xp) + (size_t) A.rank * per2 + j;
+		dst[i] = ld_peer_f4(src);
+	}
+}
+
+// phase 3: the reference's last log2 H radix-2 decimation-in-time stages across the H blocks, for this rank's positions v.
+// Block b of the big array is A_{rev(b)}; at stage s (fft_perform's stage l = log2 N + s) blocks b and b + 2^s (bit s of b clear)
+// meet with the twiddle exp(+i pi (v + N beta) / (N 2^s) (1 + eps_l)), beta = b mod 2^s.  Output block c is y[v + N c].
+struct FinalArgs { Peers peers; size_t off_a, off_r; int H, log2H, rank, root; unsigned n; double eps[4]; };
 template <int H>
-__global__ void __launch_bounds__(256) sbm_interleave(const float *__restrict__ slots, size_t slot_stride, unsigned n, float *__restrict__ stream) {
-	for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-		float v[H];
+__global__ void __launch_bounds__(256) sbm_final(FinalArgs A) {
+	constexpr int LOG2H = (H == 2) ? 1 : (H == 4) ? 2 : (H == 8) ? 3 : 4;
+	__shared__ double2 cfac[LOG2H][H / 2];            // exp(+i pi beta / 2^s (1 + eps_s)), beta < 2^s
+	if (threadIdx.x < LOG2H * (H / 2)) {
+		const int sidx = threadIdx.x / (H / 2), beta = threadIdx.x % (H / 2);
+		double sn = 0.0, cs = 1.0;
+		if (beta < (1 << sidx)) sincospi(((double) beta / (double) (1 << sidx)) * (1.0 + A.eps[sidx]), &sn, &cs);
+		cfac[sidx][beta] = make_double2(cs, sn);
+	}
+	__syncthreads();
+	const unsigned n = A.n, per = n / H, v0 = (unsigned) A.rank * per;
+	float *stream = reinterpret_cast<float *>(A.peers.win[A.root] + A.off_r);
+	for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < per; j += gridDim.x * blockDim.x) {
+		const unsigned v = v0 + j;
+		float2 a[H];
 		#pragma unroll
-		for (int s = 0; s < H; s++) v[s] = __ldg(slots + (size_t) s * slot_stride + p);
-		float *o = stream + (size_t) p * H;
-		if (H >= 4) {
+		for (int b = 0; b < H; b++) {                    // block b <- rank rev(b); H loads in flight
+			const int t = (int) (__brev((unsigned) b) >> (32 - LOG2H));
+			a[b] = ld_peer_f2(reinterpret_cast<const float2 *>(A.peers.win[t] + A.off_a) + v);
+		}
+		#pragma unroll
+		for (int sidx = 0; sidx < LOG2H; sidx++) {
+			double bs, bc;                                // exp(+i pi (v / N) / 2^s (1 + eps))
+			sincospi((((double) v / (double) n) / (double) (1 << sidx)) * (1.0 + A.eps[sidx]), &bs, &bc);
 			#pragma unroll
-			for (int s = 0; s < H; s += 4) *reinterpret_cast<float4 *>(o + s) = make_float4(v[s], v[s + 1], v[s + 2], v[s + 3]);
-		} else *reinterpret_cast<float2 *>(o) = make_float2(v[0], v[1]);
+			for (int b = 0; b < H; b++) {
+				if (b & (1 << sidx)) continue;
+				const int beta = b & ((1 << sidx) - 1);
+				const double2 cf = cfac[sidx][beta];
+				const float wr = (float) (bc * cf.x - bs * cf.y), wi = (float) (bc * cf.y + bs * cf.x);
+				const float2 hi = a[b | (1 << sidx)];
+				const float2 th = make_float2(hi.x * wr - hi.y * wi, hi.x * wi + hi.y * wr);
+				const float2 lo = a[b];
+				a[b] = make_float2(lo.x + th.x, lo.y + th.y);
+				a[b | (1 << sidx)] = make_float2(lo.x - th.x, lo.y - th.y);
+			}
+		}
+		#pragma unroll
+		for (int c = 0; c < H; c++) stream[(size_t) c * n + v] = mag_exact(a[c].x, a[c].y);      // peer stores, coalesced over v
 	}
 }
 
@@ -178,9 +193,9 @@ struct tsdrgpu_superb_mgpu {
 	int H, log2H, rank, root;
 	unsigned n_max;                                   // largest transform length the window was sized for
 	unsigned char *win; size_t win_bytes;
-	size_t off_d, off_x, off_v, off_r, slot_stride;   // byte offsets of D, X, V, residue slots; floats between two slots
+	size_t off_d, off_x, off_v, off_r;                // byte offsets in the window: D (difference spectrum), Xp (re-ordered spectrum), A (block transform), the root's stream
 	Peers peers; int connected; int ipc_opened[SBM_MAX_RANKS];
-	float2 *d_work, *d_p; void *d_part; int *d_lag;   // local temporaries
+	float2 *d_work, *d_p, *d_x; void *d_part; int *d_lag;   // local temporaries
 	unsigned epoch; unsigned last_n;
 	unsigned prep_n, prep_nd;                         // transform sizes whose kernels and twiddle tables are known to be resident
 	long long timeout_cycles;
@@ -201,12 +216,12 @@ int tsdrgpu_superb_mgpu_create(tsdrgpu_ctx_t *ctx, int nranks, int rank, int roo
 	g->off_x = g->off_d + sizeof(float2) * n;         // nd <= n
 	g->off_v = g->off_x + sizeof(float2) * n;
 	g->off_r = g->off_v + sizeof(float2) * n;
-	g->slot_stride = n;
 	g->win_bytes = g->off_r + sizeof(float) * n * (size_t) nranks;
 	CU_TRY(ctx, cudaMalloc(&g->win, g->win_bytes));
 	CU_TRY(ctx, cudaMemset(g->win, 0, sizeof(WinHeader)));
 	CU_TRY(ctx, cudaMalloc(&g->d_work, sizeof(float2) * n));
 	CU_TRY(ctx, cudaMalloc(&g->d_p, sizeof(float2) * n));
+	CU_TRY(ctx, cudaMalloc(&g->d_x, sizeof(float2) * n));
 	CU_TRY(ctx, cudaMalloc(&g->d_part, 8 * TSDRGPU_ARGMAX_PARTS));
 	CU_TRY(ctx, cudaMalloc(&g->d_lag, 256));
 	CU_TRY(ctx, cudaMemset(g->d_lag, 0, 256));
@@ -237,7 +252,7 @@ void tsdrgpu_superb_mgpu_destroy(tsdrgpu_superb_mgpu_t *g) {
 	cudaSetDevice(g->ctx->device);
 	cudaDeviceSynchronize();
 	for (int q = 0; q < g->H; q++) if (g->ipc_opened[q] && g->peers.win[q]) cudaIpcCloseMemHandle(g->peers.win[q]);
-	cudaFree(g->win); cudaFree(g->d_work); cudaFree(g->d_p); cudaFree(g->d_part); cudaFree(g->d_lag);
+	cudaFree(g->win); cudaFree(g->d_work); cudaFree(g->d_p); cudaFree(g->d_x); cudaFree(g->d_part); cudaFree(g->d_lag);
 	delete g;
 }
 
@@ -302,21 +317,20 @@ extern "C" {
 static int sbm_prepare(tsdrgpu_superb_mgpu *g, cudaStream_t stream, unsigned N, unsigned nd) {
 	if (g->prep_n == N && g->prep_nd == nd) return TSDRGPU_OK;
 	tsdrgpu_ctx_t *ctx = g->ctx;
-	float2 *V = reinterpret_cast<float2 *>(g->win + g->off_v);
 	int rc;
 	CU_TRY(ctx, cudaMemsetAsync(g->d_work, 0, sizeof(float2) * N, stream));
-	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, V, N, 0))) return rc;
+	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_x, N, 0))) return rc;
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_p, nd, 0))) return rc;
 	if ((rc = tsdrgpu_fft_internal(ctx, stream, g->d_p, nd, 1))) return rc;
-	if ((rc = tsdrgpu_ifft_abs_internal(ctx, stream, V, reinterpret_cast<float *>(g->d_work), N))) return rc;
+	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_x, N, 1))) return rc;
 	int *tmp_lag = g->d_lag + 8;
 	if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, g->d_p, nd, g->d_part, tmp_lag))) return rc;
-	preload(sbm_sync); preload(sbm_abs_diff); preload(sbm_xcorr_pull);
+	preload(sbm_sync); preload(sbm_abs_diff); preload(sbm_xcorr_pull); preload(sbm_permute_ramp); preload(sbm_pull_blocks);
 	switch (g->H) {
-	case 2: preload(sbm_mix<2>); preload(sbm_interleave<2>); break;
-	case 4: preload(sbm_mix<4>); preload(sbm_interleave<4>); break;
-	case 8: preload(sbm_mix<8>); preload(sbm_interleave<8>); break;
-	default: preload(sbm_mix<16>); preload(sbm_interleave<16>); break;
+	case 2: preload(sbm_final<2>); break;
+	case 4: preload(sbm_final<4>); break;
+	case 8: preload(sbm_final<8>); break;
+	default: preload(sbm_final<16>); break;
 	}
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
 	g->prep_n = N; g->prep_nd = nd;
@@ -346,56 +360,57 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 	if ((rc = sbm_prepare(g, stream, N, nd))) return rc;
 	const unsigned epoch = ++g->epoch;
 	g->last_n = N;
-	float2 *D = reinterpret_cast<float2 *>(g->win + g->off_d), *X = reinterpret_cast<float2 *>(g->win + g->off_x), *V = reinterpret_cast<float2 *>(g->win + g->off_v);
-	// ---- phase 1: local spectra into the own window
-	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, reinterpret_cast<const float2 *>(d_hop), X, N, 0))) return rc;
-	KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));
-	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
-	// ---- phase 2: this rank's alignment lag against hop 0
+	float2 *D = reinterpret_cast<float2 *>(g->win + g->off_d), *Xp = reinterpret_cast<float2 *>(g->win + g->off_x), *Ablk = reinterpret_cast<float2 *>(g->win + g->off_v);
+	// ---- phase 1: this hop's spectrum, this hop's alignment lag, the spectrum re-ordered + ramped into the own window
+	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, reinterpret_cast<const float2 *>(d_hop), g->d_x, N, 0))) return rc;
 	if (rank != 0) {
+		KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));
+		if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
 		const float4 *d0;
 		if (d_hop0) {                                         // the alignment reference is resident here: its difference spectrum locally
 			KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), g->d_work, nd));
 			if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_p, nd, 0))) return rc;
 			d0 = reinterpret_cast<const float4 *>(g->d_p);
-		} else {                                              // pull it from rank 0 once every rank's spectra are in place
+		} else {                                              // pull it from rank 0 once its spectra are in place
 			KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
 			d0 = reinterpret_cast<const float4 *>(g->peers.win[0] + g->off_d);
 		}
 		KL(ctx, "sbm_xcorr_pull", stream, sbm_xcorr_pull<<<grid_for(nd / 2, ctx->sm_count), 256, 0, stream>>>(d0, reinterpret_cast<const float4 *>(D), reinterpret_cast<float4 *>(g->d_p), nd / 2));
 		if ((rc = tsdrgpu_fft_internal(ctx, stream, g->d_p, nd, 1))) return rc;
 		if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, g->d_p, nd, g->d_part, g->d_lag))) return rc;
-	} else if (!d_hop0) {                                     // rank 0 takes part in the SPEC barrier the others wait in; its lag stays 0
+	} else if (!d_hop0) {                                     // rank 0 serves its difference spectrum; its own lag stays 0
+		KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));
+		if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
 		KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
 	}
+	KL(ctx, "sbm_permute_ramp", stream, sbm_permute_ramp<<<grid_for(N, ctx->sm_count, 16), 256, 0, stream>>>(g->d_x, Xp, N, g->log2H, g->d_lag));
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_LAG, epoch, all, all, g->d_lag, g->timeout_cycles));
-	// ---- phase 3: all-to-all mix
+	// ---- phase 2: all-to-all #1 (pull this rank's run from everybody), the block transform with the reference's stage angles
 	{
-		MixArgs A; A.peers = g->peers; A.off_x = g->off_x; A.off_v = g->off_v; A.H = H; A.log2H = g->log2H; A.rank = rank; A.n = N;
+		PullArgs A; A.peers = g->peers; A.off_xp = g->off_x; A.H = H; A.rank = rank; A.per = N / (unsigned) H;
+		KL(ctx, "sbm_pull_blocks", stream, sbm_pull_blocks<<<grid_for(N / 2, ctx->sm_count, 16), 256, 0, stream>>>(A, reinterpret_cast<float4 *>(g->d_work)));
+	}
+	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, Ablk, N, 1))) return rc;
+	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_MIX, epoch, all, all, (const int *) NULL, g->timeout_cycles));
+	// ---- phase 3: all-to-all #2 + the reference's last log2 H stages + |.| pushed into the root's (time-contiguous) stream
+	{
+		FinalArgs A; A.peers = g->peers; A.off_a = g->off_v; A.off_r = g->off_r; A.H = H; A.log2H = g->log2H; A.rank = rank; A.root = g->root; A.n = N;
+		double eps_all[40];
+		unsigned log2N = 0; while ((1u << log2N) < N) log2N++;
+		tsdrgpu_fft_reference_eps((int) (log2N + (unsigned) g->log2H), 1, eps_all);
+		static const bool exact_dft = getenv("TSDRGPU_FFT_TRUE_DFT") != NULL;
+		for (int sidx = 0; sidx < 4; sidx++) A.eps[sidx] = (!exact_dft && sidx < g->log2H) ? eps_all[log2N + sidx] : 0.0;
 		const unsigned grid = grid_for(N / H, ctx->sm_count, 16);
 		switch (H) {
-		case 2: KL(ctx, "sbm_mix", stream, sbm_mix<2><<<grid, 256, 0, stream>>>(A)); break;
-		case 4: KL(ctx, "sbm_mix", stream, sbm_mix<4><<<grid, 256, 0, stream>>>(A)); break;
-		case 8: KL(ctx, "sbm_mix", stream, sbm_mix<8><<<grid, 256, 0, stream>>>(A)); break;
-		default: KL(ctx, "sbm_mix", stream, sbm_mix<16><<<grid, 256, 0, stream>>>(A)); break;
+		case 2: KL(ctx, "sbm_final", stream, sbm_final<2><<<grid, 256, 0, stream>>>(A)); break;
+		case 4: KL(ctx, "sbm_final", stream, sbm_final<4><<<grid, 256, 0, stream>>>(A)); break;
+		case 8: KL(ctx, "sbm_final", stream, sbm_final<8><<<grid, 256, 0, stream>>>(A)); break;
+		default: KL(ctx, "sbm_final", stream, sbm_final<16><<<grid, 256, 0, stream>>>(A)); break;
 		}
 	}
-	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_MIX, epoch, all, all, (const int *) NULL, g->timeout_cycles));
-	// ---- phase 4: this rank's residue of the H N-point inverse; the last pass stores |y| straight into the root's slot
-	float *slot = reinterpret_cast<float *>(g->peers.win[g->root] + g->off_r) + g->slot_stride * (size_t) rank;
-	if ((rc = tsdrgpu_ifft_abs_internal(ctx, stream, V, slot, N))) return rc;
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_RES, epoch, 1u << g->root, rank == g->root ? all : 0u, (const int *) NULL, g->timeout_cycles));
-	// ---- phase 5 (root): the time-contiguous magnitude stream
-	if (rank == g->root) {
-		const float *slots = reinterpret_cast<const float *>(g->win + g->off_r);
-		const unsigned grid = grid_for(N, ctx->sm_count, 16);
-		switch (H) {
-		case 2: KL(ctx, "sbm_interleave", stream, sbm_interleave<2><<<grid, 256, 0, stream>>>(slots, g->slot_stride, N, d_stream_out)); break;
-		case 4: KL(ctx, "sbm_interleave", stream, sbm_interleave<4><<<grid, 256, 0, stream>>>(slots, g->slot_stride, N, d_stream_out)); break;
-		case 8: KL(ctx, "sbm_interleave", stream, sbm_interleave<8><<<grid, 256, 0, stream>>>(slots, g->slot_stride, N, d_stream_out)); break;
-		default: KL(ctx, "sbm_interleave", stream, sbm_interleave<16><<<grid, 256, 0, stream>>>(slots, g->slot_stride, N, d_stream_out)); break;
-		}
-	}
+	// ---- phase 4 (root): the stream is complete and time-contiguous in the window; hand it to the caller
+	if (rank == g->root) CU_TRY(ctx, cudaMemcpyAsync(d_stream_out, g->win + g->off_r, sizeof(float) * (size_t) H * N, cudaMemcpyDeviceToDevice, stream));
 	if (h_n) *h_n = N;
 	return TSDRGPU_OK;
 }

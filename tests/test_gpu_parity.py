@@ -321,7 +321,7 @@ def _close(got, want, tol, what):
     return err, rel_l2
 
 
-@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 7, 10, 11, 12, 13, 16, 20, 23, 24])
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 7, 10, 11, 12, 13, 16, 20, 21, 23, 24])
 def test_fft(gpu, O, logn):
     n = 1 << logn
     x = synth.noise_iq(n, seed=logn)
