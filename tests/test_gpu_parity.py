@@ -491,6 +491,17 @@ def test_superbandwidth_one_hop_per_rank_on_one_device(H):
     assert r.returncode == 0 and "sbm ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
 
 
+def test_superbandwidth_one_hop_per_rank_at_the_baseline_hop_size():
+    """The same at BASELINE configs[3]'s own size: 4 hops of 10 frames of 25 MS/s IQ (N = 2^21 per hop, a 2^23-point inverse) against
+    superb_ondataready + am_demod of the compiled reference -- lags exact, magnitudes to 1e-5 of the peak.  At this size the
+    reference's last stages are off the true DFT by 5e-5, so only a decomposition that follows its stage structure passes."""
+    import subprocess, sys
+    r = subprocess.run([sys.executable, "-m", "tests.sbm_one_device", "4", "full"], capture_output=True, text=True, timeout=280,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", TSDRGPU_SBM_TIMEOUT_MS="3000"))
+    assert r.returncode == 0 and "sbm ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+    print(r.stdout[-300:])
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_golden_vectors_gpu(gpu):
     from tempestsdr_b200.api import PostProcessFlags
