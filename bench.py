@@ -37,8 +37,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FS, HEIGHT, FV = 25_000_000, 1125, 60.0
-FRAMES_PER_BATCH = 64                                     # frames per launch group (one pass over the resident 213 MB of IQ)
+# The headline workload is BASELINE configs[1] ("cfg2" in SURVEY section 8).  BENCH_SHAPE=cfg5 / cfg1 re-runs the device-resident
+# step on configs[4]'s per-GPU shape (50 MS/s, 1481x1125) or configs[0]'s (8 MS/s, 507x525): child processes of the default N=1 run,
+# reported under "other_shapes", never as the headline.
+SHAPES = {"cfg2": (25_000_000, 1125, 2576), "cfg5": (50_000_000, 1125, 2576), "cfg1": (8_000_000, 525, 800)}
+SHAPE = os.environ.get("BENCH_SHAPE", "cfg2")
+FS, HEIGHT, RASTER_W = SHAPES[SHAPE]
+FV = 60.0
+FRAMES_PER_BATCH = 256 if SHAPE == "cfg1" else 64         # frames per launch group (one pass over the resident 213 MB of IQ; cfg1's small frames: 256 -> 273 MB, still > L2)
 BATCHES_PER_STEP = int(os.environ.get("BENCH_BATCHES_PER_STEP", "48"))   # one step = 48 such passes = 3072 frames = 1.28 G IQ pairs (~40 ms)
 FRAMES_PER_STEP = FRAMES_PER_BATCH * BATCHES_PER_STEP
 METRIC = "IQ MS/s ingested -> 1080p60 frames (demod+resample+frame stage+autocorrelation), whole job"
@@ -54,7 +60,7 @@ def make_iq(pairs: int, seed: int) -> np.ndarray:
     """Video-like synthetic IQ, generated for one frame period and tiled (cheap, deterministic)."""
     from tempestsdr_b200 import synth
     per_frame = int(FS / FV)
-    base = synth.video_like_iq(4 * per_frame, FS, 2576, 1125, FV, seed=seed, snr_db=25.0)
+    base = synth.video_like_iq(4 * per_frame, FS, RASTER_W, HEIGHT, FV, seed=seed, snr_db=25.0)
     reps = (2 * pairs + base.size - 1) // base.size
     return np.ascontiguousarray(np.tile(base, reps)[: 2 * pairs])
 
@@ -385,7 +391,12 @@ def run_ours(args):
 
     if os.environ.get("BENCH_QUICK"):                 # used under ncu and for the opt-in variants: the timed steps only
         if rank == 0:
-            emit({"quick": True, "value": value, "unit": "MS/s", "ms_per_step": ms_total / args.steps, "ms_per_batch": ms_total / (args.steps * BATCHES_PER_STEP)})
+            q = {"quick": True, "value": value, "unit": "MS/s", "ms_per_step": ms_total / args.steps, "ms_per_batch": ms_total / (args.steps * BATCHES_PER_STEP),
+                 "shape": SHAPE, "samplerate": FS, "frame": [w, HEIGHT], "frames_per_s": frames_done / (ms_total * 1e-3),
+                 "captures_per_batch": caps_done / (args.steps * BATCHES_PER_STEP)}
+            if os.environ.get("BENCH_SHAPE_CPU"):
+                q["cpu_baseline"] = cpu_baseline(w)
+            emit(q)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -513,6 +524,19 @@ def run_ours(args):
                            "float32 frames copied back as in e2e"}
         pl8.close()
 
+    # ---- the other BASELINE shapes (device-resident step only; child processes so that this process's state is untouched)
+    other_shapes = None
+    if world == 1 and rank == 0 and SHAPE == "cfg2" and not os.environ.get("BENCH_NO_SHAPES"):
+        other_shapes = {}
+        for name, cpu in (("cfg5", False), ("cfg1", True)):
+            env = dict(os.environ, BENCH_SHAPE=name, BENCH_QUICK="1", BENCH_BATCHES_PER_STEP="8")
+            if cpu:
+                env["BENCH_SHAPE_CPU"] = "1"
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "10", "--warmup", "3"], env=env, capture_output=True, text=True, timeout=240)
+                other_shapes[name] = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            except Exception as e:
+                other_shapes[name] = {"error": repr(e)[:200]}
     # ---- N > 1 only: the path's one real exchange, the superbandwidth stitch with one hop per GPU (configs[3])
     superb = superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier) if world > 1 else None
     if rank != 0:
@@ -600,6 +624,8 @@ def run_ours(args):
         line["superbandwidth"] = superb
     if e2e_int8:
         line["e2e_int8_transport"] = e2e_int8
+    if other_shapes:
+        line["other_shapes"] = other_shapes
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -763,6 +789,23 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
                 "frames": {"frames_per_round": int(nf) if rank == 0 else None, "ms_per_round_stitch_plus_frames": ft.item(),
                            "frames_per_s": (nf / (ft.item() * 1e-3)) if rank == 0 else None, "geometry": [int(2 * (H * FS / (FV * HEIGHT))), HEIGHT]}})
     grp.lags()                                            # raises if any wait timed out
+    # ---- where one stitch spends its time: CUDA events around every launch of 3 stitches on every rank (a flag-waiting kernel's
+    # time is the wait for the slowest peer); informational, outside every timed region above
+    try:
+        collect_profile(gpu)
+        gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
+        for _ in range(3):
+            flush.zero_()
+            grp.stitch(hop, sif, out=out, hop0=hop0)
+        torch.cuda.synchronize()
+        gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
+        mine = {k: round(1e3 * t / 3, 2) for k, (t, c) in collect_profile(gpu).items()}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        res["per_kernel_us_per_stitch"] = {"rank0_root": everyone[0], "rank1": everyone[1], "last_rank": everyone[-1]}
+    except Exception as e:
+        res["per_kernel_us_per_stitch"] = {"error": repr(e)[:160]}
+    barrier()
     # ---- round 1's formulation as the baseline: one NCCL all-gather of the raw spectra, every rank derives every lag
     try:
         for _ in range(2):
