@@ -271,6 +271,8 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
     tmp = tempfile.NamedTemporaryFile(prefix=f"tsdr_iq_r{rank}_", suffix=".raw", delete=False, dir=shm)
     make_iq(16 * per_frame, seed=1000 + rank).tofile(tmp); tmp.close()
     os.environ["TSDR_CUDA_DEVICE"] = str(local); os.environ["TSDR_BATCH_FRAMES"] = "16"; os.environ["TSDR_NO_DROP"] = "1"
+    stats_file = tmp.name + ".stats"
+    os.environ["TSDR_STATS_FILE"] = stats_file      # the library's own clock around its data callback: plugin time vs. library time per block
     if os.path.exists(ref_plugin):
         plugin, params, which = ref_plugin, f'"{tmp.name}" {FS} float', "reference TSDRPlugin_RawFile (unmodified source, pacing switch off)"
     else:
@@ -301,9 +303,9 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
         if not th.is_alive() or count["frames"] < 64:
             raise RuntimeError(f"no frames from tsdr_readasync (rc={rcs}): {lib.tsdr_getlasterrortext(t)}")
         barrier()
-        f0, t0 = count["frames"], time.perf_counter()
+        f0, t0, m0 = count["frames"], time.perf_counter(), time.monotonic()
         time.sleep(seconds)
-        f1, t1 = count["frames"], time.perf_counter()
+        f1, t1, m1 = count["frames"], time.perf_counter(), time.monotonic()
         barrier()
         lib.tsdr_stop(t)
         th.join(timeout=30)
@@ -311,6 +313,18 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
         out = {"value_per_rank": fps * per_frame / 1e6, "frames_per_s": fps, "seconds": t1 - t0, "frames_delivered": f1 - f0,
                "frame": [count["w"], count["h"]], "plugin": which, "readasync_rc": rcs[0] if rcs else None,
                "h2d_bytes_per_frame": 8 * per_frame, "d2h_bytes_per_frame": 4 * count["w"] * count["h"]}
+        try:
+            st = json.load(open(stats_file))
+            log = [e for e in st.get("log", []) if m0 <= e[0] <= m1]           # cumulative samples inside the timed window (CLOCK_MONOTONIC)
+            if len(log) >= 2:
+                n = max(1, log[-1][3] - log[0][3]); ins = log[-1][1] - log[0][1]; outs = log[-1][2] - log[0][2]; scope = "timed window"
+            else:
+                n = max(1, st["callbacks"]); ins = st["inside_callback_s"]; outs = st["between_callbacks_s"]; scope = "whole run, warm-up included"
+            out["plugin_thread_per_block_us"] = {"inside_the_library_callback": 1e6 * ins / n, "in_the_plugin_between_callbacks": 1e6 * outs / n, "blocks": int(n),
+                                                 "note": "the plugin's one thread alternates fread + memcpy of a 2 MiB block (its own code) with the callback "
+                                                         "(this library: H2D of the block, waited for, + enqueueing the kernels); " + scope}
+        except Exception:
+            pass
     except Exception as e:
         out = {"unavailable": repr(e)[:300]}
     finally:
@@ -319,6 +333,8 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
         except Exception:
             pass
         os.unlink(tmp.name)
+        if os.path.exists(stats_file):
+            os.unlink(stats_file)
     return out
 
 
@@ -354,6 +370,21 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    cpu_group = None
+    if world > 1:
+        try:
+            cpu_group = dist.new_group(backend="gloo")    # a barrier that parks the ranks on the HOST (no kernel on any GPU)
+        except Exception:
+            cpu_group = None
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            if cpu_group is not None:
+                dist.barrier(group=cpu_group)
+            else:
+                dist.barrier()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -538,7 +569,12 @@ def run_ours(args):
             except Exception as e:
                 other_shapes[name] = {"error": repr(e)[:200]}
     # ---- N > 1 only: the path's one real exchange, the superbandwidth stitch with one hop per GPU (configs[3])
-    superb = superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier) if world > 1 else None
+    superb = None
+    if world > 1:
+        try:
+            superb = superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier)
+        except Exception as e:                            # never lose the headline line to the informational section
+            superb = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -596,6 +632,7 @@ def run_ours(args):
         e2e = {"value": api_total, "unit": "MS/s",
                "h2d_bytes_per_step": int(api_run["h2d_bytes_per_frame"] * FRAMES_PER_STEP), "d2h_bytes_per_step": int(api_run["d2h_bytes_per_frame"] * FRAMES_PER_STEP),
                "seconds": api_run["seconds"], "frames_per_s_rank0": api_run["frames_per_s"], "plugin": api_run["plugin"],
+               "plugin_thread_per_block_us": api_run.get("plugin_thread_per_block_us"),
                "how": "this repo's libTSDRLibrary.so through tsdr_init/tsdr_loadplugin/tsdr_readasync with an unmodified file plugin handing over "
                       "its pageable 2 MiB malloc'd float32 buffer (page-locked in place after it came back 3 times), 16 frames per launch group, "
                       "frames delivered to the tsdr_readasync_function counted x samples per frame -- the reference arm's own method; the plugin's "
@@ -685,7 +722,7 @@ def autocorr_sweep(gpu, torch):
     return out
 
 
-def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
+def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier):
     """BASELINE configs[3] / the path's one sharded row: superbandwidth with one hop per GPU, H = world hops of
     10 frames of 25 MS/s IQ each (N = 2^21 per hop).  Reports, all with an L2 flush between repetitions (a stitch runs once per
     H x 0.67 s of signal in production: cold caches are the honest state):
@@ -694,7 +731,10 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
       speedup             one_gpu_ms / ms_per_stitch
       frames_per_s        root: stitch + resample + frame stage of the stitched stream, frames of the H x rate geometry per second
       parity              sharded magnitudes vs |one-GPU stitch| (max error / peak), lags equal
-      nccl_allgather_baseline_ms   round 1's formulation (one NCCL all-gather of raw spectra, every rank derives every lag)"""
+      nccl_allgather_baseline_ms   round 1's formulation (one NCCL all-gather of raw spectra, every rank derives every lag)
+    Order of the section: everything rank 0 does ALONE (the one-GPU reference, first launches and allocations of the H x rate
+    geometry) comes first, before the group's peer-memory windows exist and with the other ranks parked in a HOST barrier (gloo):
+    at 8 GPUs the same work done while seven GPUs sat in flag-waiting kernels once took longer than those kernels' patience."""
     from tempestsdr_b200 import superband
     from tempestsdr_b200.api import PostProcessFlags
     H = world
@@ -706,11 +746,80 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
     hop = hop_of(rank)
     hop0 = hop_of(0)                                      # the alignment reference, kept on every device (the pipeline copies hop 0 to all GPUs at ingest)
     flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")            # 256 MB > L2
-    grp = superband.SuperbGroup.for_process_group(gpu, hop_pairs)
     n_fft = gpu.fft_getrealsize(hop_pairs)
     out = torch.empty(H * n_fft, dtype=torch.float32, device="cuda") if rank == 0 else None
+    flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True, superresolution=True)
+    # ---- rank 0 alone: the same hops on one GPU (timing + the parity reference), buffers and first launches of the frames path
+    solo = torch.zeros(2, device="cuda", dtype=torch.float64)                      # [ok, one_gpu_ms]
+    r0 = {}
+    if rank == 0:
+        try:
+            hops = [hop_of(q) for q in range(H)]
+            for _ in range(2):
+                one_iq, one_offs = gpu.superb_stitch(hops, sif)
+            t1 = []
+            for _ in range(5):
+                flush.zero_(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); one_iq, one_offs = gpu.superb_stitch(hops, sif); b.record(); torch.cuda.synchronize()
+                t1.append(a.elapsed_time(b))
+            ref_mag = gpu.am_demod(one_iq)
+            r0["ref_mag"], r0["ref_peak"], r0["one_offs"] = ref_mag, float(ref_mag.abs().max()), list(one_offs)
+            r0["diff"] = torch.empty_like(ref_mag)
+            del one_iq, hops
+            # frames from the stitched stream: H x the rate, same lines
+            wH = int(2 * (H * FS / (FV * HEIGHT)))
+            blockH = int(0.1 * H * FS / FV)
+            nblk = (H * n_fft) // blockH
+            rs, pp = gpu.resampler(), gpu.post_processor()
+            upH = float(wH * HEIGHT) * FV
+            pix = torch.empty(int(rs.plan((blockH, nblk), upH, float(H * FS))) + 1024, dtype=torch.float32, device="cuda")
+            nH = wH * HEIGHT
+            frames_out = torch.empty(((pix.numel() // nH) + 1) * nH, dtype=torch.float32, device="cuda")
+
+            def frames_of(stream_mag):
+                px = rs.process(stream_mag, (blockH, nblk), upH, float(H * FS), in_is_iq=False, out=pix)
+                nf = px.numel() // nH
+                pp.process(px[: nf * nH], wH, HEIGHT, 0.0, 0.1, flags, out=frames_out[: nf * nH], want_results=False)
+                return nf
+            frames_of(ref_mag)                            # first launches and allocations happen here
+            pp.join(); torch.cuda.synchronize()
+            r0["frames_of"], r0["geometry"] = frames_of, [wH, HEIGHT]
+            solo[0], solo[1] = 1.0, sum(t1) / len(t1)
+        except Exception as e:
+            r0["error"] = repr(e)[:300]
+    host_barrier()
+    dist.all_reduce(solo)
+    if solo[0].item() != 1.0:
+        return {"hops": H, "n_per_hop": n_fft, "error": "rank 0's one-GPU reference failed: " + str(r0.get("error"))}
+    one_ms = solo[1].item()
+    # ---- the group: windows mapped into every rank (CUDA IPC)
+    grp = superband.SuperbGroup.for_process_group(gpu, hop_pairs)
+
+    def group_ok():
+        """Collective: did any rank's flag wait time out (the status word is sticky)?  Every rank gets the same answer, so the ranks
+        leave the section together instead of one raising while the others walk into the next collective."""
+        bad = 0
+        try:
+            grp.lags()
+        except Exception:
+            bad = 1
+        t = torch.tensor([bad], device="cuda", dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item()) == 0
+
+    def give_up(where, partial):
+        partial["error"] = f"a flag wait of the sharded stitch timed out {where}; the remaining superbandwidth measurements were skipped"
+        try:
+            grp.close()
+        except Exception:
+            pass
+        return partial
+
     for _ in range(3):
         grp.stitch(hop, sif, out=out, hop0=hop0)
+    if not group_ok():
+        return give_up("in the warm-up stitches", {"hops": H, "n_per_hop": n_fft, "one_gpu_ms": one_ms})
     lags = grp.lags()
     barrier()
     reps = 10
@@ -722,73 +831,39 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
     tms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / reps], device="cuda")
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     res = {"hops": H, "n_per_hop": n_fft, "ms_per_stitch": tms.item(), "stitched_MS_per_s": H * n_fft / (tms.item() * 1e-3) / 1e6,
+           "one_gpu_ms": one_ms, "speedup_vs_one_gpu": one_ms / tms.item(),
            "lags": lags, "l2_flushed_between_repetitions": True,
            "resident_before_the_timed_region": "hop q on GPU q, plus a copy of hop 0 (the alignment reference) on every GPU, as the pipeline leaves them",
            "exchange": "peer-memory windows (CUDA IPC over NVLink), flags in peer memory; no collective library on the data path",
            "nvlink_bytes_received_per_rank": int(8 * (n_fft // 2) * (1 if rank else 0) + 2 * 8 * n_fft * (H - 1) // H),
            "nvlink_bytes_received_by_root_for_stream": int(4 * n_fft * (H - 1))}
-    # ---- rank 0: the same hops on one GPU, parity, frames
-    one = torch.zeros(3, device="cuda", dtype=torch.float64)
+    if not group_ok():
+        return give_up("in the timed stitches", res)
+    # ---- parity of the sharded stream against the one-GPU path (rank 0; no new allocations while the windows are mapped)
     if rank == 0:
-        hops = [hop_of(q) for q in range(H)]
-        for _ in range(2):
-            one_iq, one_offs = gpu.superb_stitch(hops, sif)
-        t1 = []
-        for _ in range(5):
-            flush.zero_(); torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); one_iq, one_offs = gpu.superb_stitch(hops, sif); b.record(); torch.cuda.synchronize()
-            t1.append(a.elapsed_time(b))
-        one_ms = sum(t1) / len(t1)
-        ref_mag = gpu.am_demod(one_iq)
-        err = float((out - ref_mag).abs().max() / ref_mag.abs().max())
-        lags_equal = [2 * l for l in lags] == list(one_offs)
-        # frames from the stitched stream: H x the rate, same lines
-        wH = int(2 * (H * FS / (FV * HEIGHT)))
-        blockH = int(0.1 * H * FS / FV)
-        nblk = (H * n_fft) // blockH
-        rs, pp = gpu.resampler(), gpu.post_processor()
-        upH = float(wH * HEIGHT) * FV
-        pix = torch.empty(int(rs.plan((blockH, nblk), upH, float(H * FS))) + 1024, dtype=torch.float32, device="cuda")
-        nH = wH * HEIGHT
-        frames_out = torch.empty(((pix.numel() // nH) + 1) * nH, dtype=torch.float32, device="cuda")
-
-        def round_trip():
-            grp_out = grp.stitch(hop, sif, out=out, hop0=hop0)
-            px = rs.process(grp_out, (blockH, nblk), upH, float(H * FS), in_is_iq=False, out=pix)
-            nf = px.numel() // nH
-            pp.process(px[: nf * nH], wH, HEIGHT, 0.0, 0.1, PostProcessFlags(autoshift=True, lowpass_before_sync=True, superresolution=True),
-                       out=frames_out[: nf * nH], want_results=False)
-            return nf
-        res["_round_trip"] = round_trip
-        one[0], one[1], one[2] = one_ms, err, 1.0 if lags_equal else 0.0
-    # the frame rounds need every rank to take part in the stitch
+        torch.sub(out, r0["ref_mag"], out=r0["diff"])
+        err = float(r0["diff"].abs_().max()) / r0["ref_peak"]
+        res["parity_vs_one_gpu_path"] = {"max_err_over_peak": err, "lags_equal": [2 * l for l in lags] == r0["one_offs"], "bound": 1e-5}
+    # ---- frames: stitch + resample + frame stage of the stitched stream on the root; every rank takes part in the stitch
+    def round_trip():
+        so = grp.stitch(hop, sif, out=out, hop0=hop0)
+        return r0["frames_of"](so) if rank == 0 else 0
+    host_barrier()
     nf = 0
     for _ in range(2):
-        if rank == 0:
-            nf = res["_round_trip"]()
-        else:
-            grp.stitch(hop, sif, hop0=hop0)
+        nf = round_trip()
     barrier()
     fe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
     for a, b in fe:
         flush.zero_()
-        a.record()
-        if rank == 0:
-            nf = res["_round_trip"]()
-        else:
-            grp.stitch(hop, sif, hop0=hop0)
-        b.record()
+        a.record(); nf = round_trip(); b.record()
     barrier()
-    res.pop("_round_trip", None)
     ft = torch.tensor([sum(a.elapsed_time(b) for a, b in fe) / len(fe)], device="cuda")
     dist.all_reduce(ft, op=dist.ReduceOp.MAX)
-    dist.all_reduce(one)
-    res.update({"one_gpu_ms": one[0].item(), "speedup_vs_one_gpu": one[0].item() / tms.item(),
-                "parity_vs_one_gpu_path": {"max_err_over_peak": one[1].item(), "lags_equal": bool(one[2].item() == 1.0), "bound": 1e-5},
-                "frames": {"frames_per_round": int(nf) if rank == 0 else None, "ms_per_round_stitch_plus_frames": ft.item(),
-                           "frames_per_s": (nf / (ft.item() * 1e-3)) if rank == 0 else None, "geometry": [int(2 * (H * FS / (FV * HEIGHT))), HEIGHT]}})
-    grp.lags()                                            # raises if any wait timed out
+    res["frames"] = {"frames_per_round": int(nf) if rank == 0 else None, "ms_per_round_stitch_plus_frames": ft.item(),
+                     "frames_per_s": (nf / (ft.item() * 1e-3)) if rank == 0 else None, "geometry": r0.get("geometry")}
+    if not group_ok():
+        return give_up("in the stitch + frames rounds", res)
     # ---- where one stitch spends its time: CUDA events around every launch of 3 stitches on every rank (a flag-waiting kernel's
     # time is the wait for the slowest peer); informational, outside every timed region above
     try:
@@ -800,12 +875,14 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier):
         torch.cuda.synchronize()
         gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
         mine = {k: round(1e3 * t / 3, 2) for k, (t, c) in collect_profile(gpu).items()}
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine)
-        res["per_kernel_us_per_stitch"] = {"rank0_root": everyone[0], "rank1": everyone[1], "last_rank": everyone[-1]}
     except Exception as e:
-        res["per_kernel_us_per_stitch"] = {"error": repr(e)[:160]}
+        mine = {"error": repr(e)[:160]}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    res["per_kernel_us_per_stitch"] = {"rank0_root": everyone[0], "rank1": everyone[1], "last_rank": everyone[-1]}
     barrier()
+    if not group_ok():
+        return give_up("in the profiled stitches", res)
     # ---- round 1's formulation as the baseline: one NCCL all-gather of the raw spectra, every rank derives every lag
     try:
         for _ in range(2):

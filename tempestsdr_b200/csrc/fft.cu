@@ -45,6 +45,7 @@ struct FftPass {
 	int exact0;                                         // the first three layers of this pass have eps = 0: plain DFT-8
 	int conj_in, conj_out;                              // inverse transforms: conjugate on load (first pass) / on store (last pass)
 	float *abs_real;                                    // with out_abs: |.| goes here as float32 (same element index) instead of (|.|, 0) to `out` -- may be peer memory
+	int dbg;                                            // timing experiments only (TSDRGPU_FFT_DBG): 1 = no global loads, 2 = no global stores; results are garbage
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -230,7 +231,10 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	{
 		int c, i;
 		if (P.c_fast_in) { c = tid & (C - 1); i = tid >> log2C; } else { i = tid & (L8 - 1); c = tid >> LOG2L8; }
-		if (TMA) {
+		if (P.dbg & 1) {
+			#pragma unroll
+			for (int m = 0; m < 8; m++) v[m] = make_float2((float) tid, (float) m);
+		} else if (TMA) {
 			__shared__ __align__(8) unsigned long long bar_mem;
 			const unsigned bar = smem_addr(&bar_mem);
 			const unsigned landing = sbase + ((NSTAGES > 1) ? (unsigned) (C * L) * 8u : 0u);      // the half stage 0 does not write
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 		} else {
 			const float sy = P.conj_out ? -P.scale : P.scale;      // inverse transforms: the conjugate on the way out (see bf8)
 			#pragma unroll
-			for (int m = 0; m < RLAST; m++) o[(i + m * PL) * ks] = make_float2(w[m].x * P.scale, w[m].y * sy);
+			for (int m = 0; m < RLAST; m++) if (!(P.dbg & 2) || w[m].x == 1.2345e30f) o[(i + m * PL) * ks] = make_float2(w[m].x * P.scale, w[m].y * sy);
 		}
 	}
 }
@@ -719,6 +723,7 @@ int launch_pass(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, float
 		const unsigned ncols = P.G_lo * (unsigned) P.C;
 		if (ncols <= (1u << 20)) { int rc = step_table(ctx, P.tw_M, ncols, (unsigned) (L >> 3), &P.tw_step); if (rc) return rc; }
 	}
+	P.dbg = getenv("TSDRGPU_FFT_DBG") ? atoi(getenv("TSDRGPU_FFT_DBG")) : 0;
 	P.exact0 = 1;
 	for (int sidx = 0; sidx < 3 && sidx < P.log2L; sidx++) if (eps_all && l_base + sidx < 40 && fabs(eps_all[l_base + sidx]) > 1e-10) P.exact0 = 0;
 	// bulk copies (TMA) feed the passes whose lines are contiguous and 16-byte aligned; TSDRGPU_FFT_NO_TMA=1 keeps the plain loads

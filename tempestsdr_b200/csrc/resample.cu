@@ -239,8 +239,8 @@ __device__ __noinline__ bool rs_bank_walk(const float *__restrict__ in, unsigned
 	return true;
 }
 
-template <bool IQ>
-__global__ void __launch_bounds__(RS_THREADS) rs_main4(const float *__restrict__ in, float *__restrict__ out,
+template <bool IQ, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB) rs_main4(const float *__restrict__ in, float *__restrict__ out,
                                                        const RsBlock *__restrict__ blocks, const uint2 *__restrict__ tile_info,
                                                        float *__restrict__ mag_out) {
 	__shared__ __align__(16) float s_out[RS_OUT_CAP + 8];
@@ -637,8 +637,14 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
 			else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
 		} else {
-			if (in_is_iq) KL(ctx, "rs_main", stream, rs_main4<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
-			else KL(ctx, "rs_main", stream, rs_main4<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
+			// resident CTAs per SM the register allocation aims at (TSDRGPU_RS_MINB, experiments: 3 = 80 registers, 4 = 64, 5 = 48)
+			static const int minb = getenv("TSDRGPU_RS_MINB") ? atoi(getenv("TSDRGPU_RS_MINB")) : 3;
+			if (in_is_iq) {
+				if (minb >= 6) KL(ctx, "rs_main", stream, rs_main4<true, 6><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+				else if (minb == 5) KL(ctx, "rs_main", stream, rs_main4<true, 5><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+				else if (minb == 4) KL(ctx, "rs_main", stream, rs_main4<true, 4><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+				else KL(ctx, "rs_main", stream, rs_main4<true, 3><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
+			} else KL(ctx, "rs_main", stream, rs_main4<false, 3><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
 		}
 		if (in_is_iq) KL(ctx, "rs_fixup", stream, rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 		else KL(ctx, "rs_fixup", stream, rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));

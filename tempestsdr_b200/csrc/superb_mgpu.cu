@@ -228,7 +228,7 @@ int tsdrgpu_superb_mgpu_create(tsdrgpu_ctx_t *ctx, int nranks, int rank, int roo
 	CU_TRY(ctx, cudaDeviceSynchronize());
 	g->peers.win[rank] = g->win;
 	const char *to = getenv("TSDRGPU_SBM_TIMEOUT_MS");
-	g->timeout_cycles = (long long) ((to ? atof(to) : 4000.0) * 1.9e6);      // ~1.9 GHz SM clock
+	g->timeout_cycles = (long long) ((to ? atof(to) : 15000.0) * 1.9e6);      // ~1.9 GHz SM clock
 	*out = g;
 	return TSDRGPU_OK;
 }

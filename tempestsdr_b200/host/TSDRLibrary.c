@@ -64,6 +64,9 @@ struct tsdr_lib {
 	 * setters, the plugin's data callback) hold pipe_lock shared, the tear-down takes it exclusively before the object dies */
 	pthread_rwlock_t pipe_lock;
 	pthread_mutex_t err_mu;              /* errormsg is replaced from the plugin's thread too (GPU failures) */
+	/* optional timing of the data callback (TSDR_STATS_FILE=<path>): where a run's wall time goes, per block */
+	int stats_on; uint64_t cb_count; double cb_inside_s, cb_outside_s, cb_last_exit;
+	struct { double t, inside, outside; uint64_t n; } cb_log[1024]; int cb_nlog;   /* cumulative values every 128 callbacks (CLOCK_MONOTONIC) */
 };
 
 /* ---- error text: library-owned, NULL after a successful call (TSDRLibrary.c:136-159) ---------------------- */
@@ -279,11 +282,21 @@ static void on_retune(int32_t offset_hz, void *user) {
 }
 
 /* the plugin's data callback == the reference's process() (TSDRLibrary.c:264-298), on the plugin's thread */
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec; }
 static void process(float *buf, uint64_t items_count, void *ctx, int64_t samples_dropped) {
 	tsdr_lib_t *t = (tsdr_lib_t *) ctx;
 	if (t->gpu_failed) return;
 	int rc = TSDRGPU_OK;
+	double t_in = 0.0;
+	if (t->stats_on) { t_in = now_s(); if (t->cb_count) t->cb_outside_s += t_in - t->cb_last_exit; }
 	WITH_PIPE(t, rc = tsdrgpu_pipeline_process(t->pipe, buf, items_count, samples_dropped));
+	if (t->stats_on) {
+		t->cb_last_exit = now_s(); t->cb_inside_s += t->cb_last_exit - t_in; t->cb_count++;
+		if ((t->cb_count & 127u) == 0 && t->cb_nlog < 1024) {
+			t->cb_log[t->cb_nlog].t = t->cb_last_exit; t->cb_log[t->cb_nlog].inside = t->cb_inside_s;
+			t->cb_log[t->cb_nlog].outside = t->cb_outside_s; t->cb_log[t->cb_nlog].n = t->cb_count; t->cb_nlog++;
+		}
+	}
 	if (rc != TSDRGPU_OK) {
 		t->gpu_failed = 1;
 		fail(t, tsdrgpu_last_error(t->gpu), TSDR_CANNOT_OPEN_DEVICE);
@@ -381,8 +394,20 @@ int tsdr_readasync(tsdr_lib_t *t, tsdr_readasync_function cb, void *ctx) {
 		t->pipe = np;                                 /* published: setters on other threads reach the run from here on */
 		pthread_rwlock_unlock(&t->pipe_lock);
 	}
+	t->stats_on = getenv("TSDR_STATS_FILE") != NULL; t->cb_count = 0; t->cb_inside_s = t->cb_outside_s = 0.0; t->cb_nlog = 0;
 	status = t->plugin.readasync(process, t);                 /* blocks until tsdr_stop or a plugin error */
 	if (status != TSDR_OK) pluginsfault = 1;
+	if (t->stats_on) {                                         /* seconds inside process() vs. between two calls (= the plugin's own work) */
+		FILE *sf = fopen(getenv("TSDR_STATS_FILE"), "w");
+		if (sf) {
+			fprintf(sf, "{\"callbacks\": %llu, \"inside_callback_s\": %.6f, \"between_callbacks_s\": %.6f, \"log\": [",
+			        (unsigned long long) t->cb_count, t->cb_inside_s, t->cb_outside_s);
+			for (int i = 0; i < t->cb_nlog; i++)
+				fprintf(sf, "%s[%.6f, %.6f, %.6f, %llu]", i ? ", " : "", t->cb_log[i].t, t->cb_log[i].inside, t->cb_log[i].outside, (unsigned long long) t->cb_log[i].n);
+			fprintf(sf, "]}\n");
+			fclose(sf);
+		}
+	}
 	tsdrgpu_pipeline_flush(t->pipe);
 	{
 		pthread_rwlock_wrlock(&t->pipe_lock);        /* no setter is inside the object any more, none can enter */
