@@ -137,7 +137,13 @@ class DeviceStep:
         self.pix_fill = 0
         self.frames_out = [torch.empty((FRAMES_PER_BATCH + 2) * self.n, dtype=torch.float32, device=iq_dev.device) for _ in range(2)]
         self.pairs = self.block * self.nblocks
-        self.mag = torch.empty(self.cap + self.pairs, dtype=torch.float32, device=iq_dev.device)   # demodulated stream, capture-aligned
+        # demodulated stream, capture-aligned; two buffers: the transforms of step k (on the detector's own stream) read one
+        # while the resampler of step k+1 already fills the other
+        self.frd_overlap = not os.environ.get("BENCH_NO_FRD_OVERLAP")
+        self.frd.set_overlap(self.frd_overlap)
+        self.mags = [torch.empty(self.cap + self.pairs, dtype=torch.float32, device=iq_dev.device) for _ in range(2 if self.frd_overlap else 1)]
+        self.mag_sel = 0
+        self.mag = self.mags[0]
         self.mag_fill = 0
         self.frames = 0
         self.captures = 0
@@ -183,15 +189,27 @@ class DeviceStep:
         self.mag_fill += self.pairs
         ncap = self.mag_fill // self.cap
         if ncap:
-            self.frd.run_batch(FS, self.mag, self.cap, ncap, self.cap)
             rest = self.mag_fill - ncap * self.cap
-            if rest:
-                gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, self.mag.data_ptr(), self.mag.data_ptr() + 4 * ncap * self.cap, 4 * rest))
+            if self.frd_overlap:
+                # the samples behind the last complete capture move to the head of the OTHER buffer (once the transforms that
+                # last read it are done: they had a whole step), then this buffer's captures go to the detector's stream
+                other = self.mags[self.mag_sel ^ 1]
+                self.frd.join()
+                if rest:
+                    gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, other.data_ptr(), self.mag.data_ptr() + 4 * ncap * self.cap, 4 * rest))
+                self.frd.run_batch(FS, self.mag, self.cap, ncap, self.cap)
+                self.mag_sel ^= 1
+                self.mag = other
+            else:
+                self.frd.run_batch(FS, self.mag, self.cap, ncap, self.cap)
+                if rest:
+                    gpu.chk(gpu._lib.tsdrgpu_memcpy_d2d(gpu._h, gpu.stream, self.mag.data_ptr(), self.mag.data_ptr() + 4 * ncap * self.cap, 4 * rest))
             self.mag_fill = rest
             self.captures += ncap
 
     def join(self):
         self.pp.join()
+        self.frd.join()
 
 
 def collect_profile(gpu):
@@ -436,6 +454,7 @@ def run_ours(args):
     # (with it on, intervals on the main stream also contain the slowdown from sharing the chip with the sync search).
     batch.join(); torch.cuda.synchronize()
     batch.pp.set_overlap(False)
+    batch.frd.set_overlap(False)                          # (the two-buffer bookkeeping of DeviceStep stays; the runs are just not forked)
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
     collect_profile(gpu)
     prof_batches = 3
@@ -445,6 +464,7 @@ def run_ours(args):
     prof = collect_profile(gpu)
     gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
     batch.pp.set_overlap(not os.environ.get("BENCH_NO_OVERLAP"))
+    batch.frd.set_overlap(batch.frd_overlap)
     prof_caps = (batch.captures - caps_before_prof) / prof_batches          # captures autocorrelated per profiled batch
     acs = autocorr_sweep(gpu, torch) if (rank == 0 and not os.environ.get("BENCH_NO_SWEEP")) else None
     barrier()

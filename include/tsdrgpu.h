@@ -237,6 +237,11 @@ TSDRGPU_API int tsdrgpu_crosscorrelation(tsdrgpu_ctx_t *ctx, void *stream, float
 typedef struct tsdrgpu_frd tsdrgpu_frd_t;
 TSDRGPU_API int  tsdrgpu_frd_create(tsdrgpu_ctx_t *ctx, tsdrgpu_frd_t **frd);
 TSDRGPU_API void tsdrgpu_frd_destroy(tsdrgpu_frd_t *frd);
+/* Overlapped mode: a run's kernels go to an internal stream (behind what `stream` held at the call) with work buffers of the
+ * detector's own, so the transforms share the chip with what the caller enqueues next; the capture must stay untouched until
+ * tsdrgpu_frd_join(frd, s) has put stream s behind the run (plots / peaks readers join by themselves). */
+TSDRGPU_API int  tsdrgpu_frd_set_overlap(tsdrgpu_frd_t *frd, int on);
+TSDRGPU_API int  tsdrgpu_frd_join(tsdrgpu_frd_t *frd, void *stream);
 TSDRGPU_API int  tsdrgpu_frd_reset(tsdrgpu_frd_t *frd);                      /* extbuffer_cleartozero on all three */
 TSDRGPU_API uint32_t tsdrgpu_frd_capture_size(uint32_t samplerate);          /* frameratedetector.c:160 */
 TSDRGPU_API void tsdrgpu_frd_windows(uint32_t samplerate, int *frame_min, int *frame_max, int *line_min, int *line_max);

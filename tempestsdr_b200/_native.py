@@ -102,6 +102,8 @@ _SIGS = {
     "tsdrgpu_frd_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_frd_destroy": (None, [C.c_void_p]),
     "tsdrgpu_frd_reset": (C.c_int, [C.c_void_p]),
+    "tsdrgpu_frd_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "tsdrgpu_frd_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tsdrgpu_frd_capture_size": (C.c_uint32, [C.c_uint32]),
     "tsdrgpu_frd_windows": (None, [C.c_uint32] + [C.POINTER(C.c_int)] * 4),
     "tsdrgpu_frd_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,

@@ -316,6 +316,14 @@ class FrameRateDetector:
     def reset(self):
         self.ctx._lib.tsdrgpu_frd_reset(self._h)
 
+    def set_overlap(self, on: bool) -> None:
+        """Runs go to the detector's own stream and work buffers (tsdrgpu_frd_set_overlap); see :meth:`join`."""
+        self.ctx.chk(self.ctx._lib.tsdrgpu_frd_set_overlap(self._h, 1 if on else 0))
+
+    def join(self) -> None:
+        """The context's stream waits (on the device) for the last overlapped run: call before the capture memory is reused."""
+        self.ctx.chk(self.ctx._lib.tsdrgpu_frd_join(self._h, self.ctx.stream))
+
     @staticmethod
     def capture_size(samplerate: int) -> int:
         return N.lib().tsdrgpu_frd_capture_size(samplerate)

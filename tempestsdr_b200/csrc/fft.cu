@@ -859,6 +859,22 @@ int tsdrgpu_fft_oop_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const floa
 	o.cplx_in = in; o.cplx_bs = 0;
 	return fft_run(ctx, stream, out, (float2 *) scratch, ilog2(n_pow2), inverse, o);
 }
+// `batch` independent out-of-place transforms (transform b reads in + b*in_bs, writes out + b*out_bs) through a scratch area the
+// CALLER owns (batch * n_pow2 complex; NULL: the context's scratch slot 0) -- for callers that run transforms on two streams at once
+int tsdrgpu_fft_batch_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, const float2 *in, long long in_bs, float2 *out, long long out_bs,
+                               float2 *scratch, unsigned long long n_pow2, unsigned batch, int inverse) {
+	int rc = ensure_table(ctx, stream);
+	if (rc) return rc;
+	ARG_TRY(ctx, n_pow2 >= 2 && batch >= 1);
+	if (!scratch) {
+		void *sc;
+		if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * n_pow2 * batch, &sc))) return rc;
+		scratch = (float2 *) sc;
+	}
+	FftOpts o; memset(&o, 0, sizeof o); o.batch = batch; o.scale = inverse ? 1.0f : 1.0f / (float) n_pow2;
+	o.cplx_in = in; o.cplx_bs = in_bs; o.data_bs = out_bs; o.scratch_bs = (long long) n_pow2;
+	return fft_run(ctx, stream, out, scratch, ilog2(n_pow2), inverse, o);
+}
 // inverse transform of `data` (n_pow2 complex, clobbered) whose final pass stores |y| as float32 straight into real_out (n_pow2
 // floats; peer memory allowed: the stores of the last butterflies ARE the transfer)
 int tsdrgpu_ifft_abs_internal(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float *real_out, unsigned long long n_pow2) {
@@ -885,6 +901,12 @@ struct tsdrgpu_frd {
 	double *d_p1, *d_p2; size_t p1_cap, p2_cap;   // the two running means
 	uint64_t calls; int fresh;
 	int *d_peaks;                                 // first strict maximum of each plot (k_plot_peaks), refreshed with every run
+	// overlapped mode (tsdrgpu_frd_set_overlap): everything a run launches goes to an internal stream, behind what the caller's
+	// stream held at the call, with work buffers of its own -- the transforms then share the chip with whatever the caller
+	// enqueues next (the pass kernels are bound by issue slots, the resampler and the frame stage by other things)
+	int overlap, pending;
+	cudaStream_t s_side; cudaEvent_t ev_in, ev_done;
+	float2 *w0, *w1; size_t w0_cap, w1_cap;
 };
 
 extern "C" {
@@ -942,8 +964,9 @@ static unsigned autocorr_group(unsigned long long N, unsigned batch) {
 	return batch;
 }
 
+struct WorkBufs { float2 *w0, *w1; };                     // caller-owned work buffers (NULL: the context's scratch slots 0 and 1)
 static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *ans, long long ans_bs, const float *d_real,
-                                      long long real_stride, unsigned long long N, unsigned batch, LagWindows win) {
+                                      long long real_stride, unsigned long long N, unsigned batch, LagWindows win, WorkBufs wb) {
 	const unsigned log2N = ilog2(N), half = (unsigned) (N >> 1);
 	double eps_all[40];
 	tsdrgpu_fft_reference_eps((int) log2N, 0, eps_all);
@@ -952,9 +975,9 @@ static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, f
 	int rc = last_stage_table(ctx, half, exact_dft ? 0.0 : eps_all[log2N - 1], &last);
 	if (rc) return rc;
 	const unsigned G = autocorr_group(N, batch);
-	void *w0_, *w1_;
-	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * half * G, &w0_))) return rc;
-	if ((rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * half * G, &w1_))) return rc;
+	void *w0_ = wb.w0, *w1_ = wb.w1;
+	if (!w0_ && (rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * half * G, &w0_))) return rc;
+	if (!w1_ && (rc = tsdrgpu_scratch(ctx, 1, sizeof(float2) * half * G, &w1_))) return rc;
 	float2 *W0 = (float2 *) w0_, *W1 = (float2 *) w1_;
 	const bool windowed = win.hi0 > win.lo0 || win.hi1 > win.lo1;
 	for (unsigned g0 = 0; g0 < batch; g0 += G) {
@@ -983,7 +1006,8 @@ static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, f
 }
 
 static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float *d_answer, long long answer_stride,
-                                 const float *d_real, long long real_stride, uint32_t size, unsigned batch, bool skip_tail, LagWindows win = LagWindows{0, 0, 0, 0}) {
+                                 const float *d_real, long long real_stride, uint32_t size, unsigned batch, bool skip_tail, LagWindows win = LagWindows{0, 0, 0, 0},
+                                 WorkBufs wb = WorkBufs{NULL, NULL}) {
 	int rc = ensure_table(ctx, stream);
 	if (rc) return rc;
 	const unsigned long long N = tsdrgpu_fft_getrealsize(size);
@@ -1003,10 +1027,10 @@ static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float 
 	if (!full_size && N >= 16 && (real_stride & 1) == 0 && (answer_stride & 1) == 0
 	    && (reinterpret_cast<unsigned long long>(d_real) & 7ull) == 0) {
 		if (win.hi0 > (unsigned) (N >> 1) || win.hi1 > (unsigned) (N >> 1)) win = LagWindows{0, 0, 0, 0};      // a window beyond N/2: produce every lag
-		return autocorrelation_batch_half(ctx, stream, ans, answer_stride / 2, d_real, real_stride, N, batch, win);
+		return autocorrelation_batch_half(ctx, stream, ans, answer_stride / 2, d_real, real_stride, N, batch, win, wb);
 	}
-	void *scratch;
-	if ((rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N * batch, &scratch))) return rc;
+	void *scratch = wb.w0;                              // (sized for N * batch by the overlapped detector)
+	if (!scratch && (rc = tsdrgpu_scratch(ctx, 0, sizeof(float2) * N * batch, &scratch))) return rc;
 	// forward transform of the first N samples, real input widened on load, |X|/N on store
 	FftOpts f; memset(&f, 0, sizeof f);
 	f.real_in = d_real; f.out_abs = true; f.scale = 1.0f / (float) N; f.batch = batch;
@@ -1060,6 +1084,28 @@ int tsdrgpu_frd_create(tsdrgpu_ctx_t *ctx, tsdrgpu_frd_t **out) {
 	*out = f;
 	return TSDRGPU_OK;
 }
+// overlapped mode on/off (see struct tsdrgpu_frd).  While it is on, a capture handed to tsdrgpu_frd_run* must stay untouched
+// until tsdrgpu_frd_join (or the next synchronising call) has put the caller's stream behind the run.
+int tsdrgpu_frd_set_overlap(tsdrgpu_frd_t *f, int on) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
+	tsdrgpu_ctx_t *ctx = f->ctx;
+	BIND(ctx);
+	if (on && !f->s_side) {
+		CU_TRY(ctx, cudaStreamCreateWithFlags(&f->s_side, cudaStreamNonBlocking));
+		CU_TRY(ctx, cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+		CU_TRY(ctx, cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming));
+	}
+	if (!on && f->pending) { CU_TRY(ctx, cudaStreamSynchronize(f->s_side)); f->pending = 0; }
+	f->overlap = on ? 1 : 0;
+	return TSDRGPU_OK;
+}
+// `stream` waits (on the device) for the detector's last overlapped run; a no-op otherwise
+int tsdrgpu_frd_join(tsdrgpu_frd_t *f, void *stream) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
+	BIND(f->ctx);
+	if (f->pending) CU_TRY(f->ctx, cudaStreamWaitEvent((cudaStream_t) stream, f->ev_done, 0));
+	return TSDRGPU_OK;
+}
 void tsdrgpu_frd_destroy(tsdrgpu_frd_t *f) {
 	if (!f) return;
 	cudaSetDevice(f->ctx->device); cudaDeviceSynchronize();
@@ -1067,6 +1113,9 @@ void tsdrgpu_frd_destroy(tsdrgpu_frd_t *f) {
 	if (f->d_p1) cudaFree(f->d_p1);
 	if (f->d_p2) cudaFree(f->d_p2);
 	if (f->d_peaks) cudaFree(f->d_peaks);
+	if (f->w0) cudaFree(f->w0);
+	if (f->w1) cudaFree(f->w1);
+	if (f->s_side) { cudaStreamDestroy(f->s_side); cudaEventDestroy(f->ev_in); cudaEventDestroy(f->ev_done); }
 	delete f;
 }
 int tsdrgpu_frd_reset(tsdrgpu_frd_t *f) { if (!f) return TSDRGPU_EINVAL; f->fresh = 1; return TSDRGPU_OK; }
@@ -1085,7 +1134,7 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
 	tsdrgpu_ctx_t *ctx = f->ctx;
 	BIND(ctx); ARG_TRY(ctx, d_capture != NULL && size > 0 && batch > 0);
-	cudaStream_t stream = (cudaStream_t) stream_;
+	cudaStream_t caller = (cudaStream_t) stream_, stream = caller;
 	int fmin, fmax, lmin, lmax;
 	tsdrgpu_frd_windows(samplerate, &fmin, &fmax, &lmin, &lmax);
 	const int flen = fmax - fmin, llen = lmax - lmin;
@@ -1093,6 +1142,23 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 	ARG_TRY(ctx, (uint64_t) fmax <= (uint64_t) size && flen >= 0 && llen >= 0);
 	const bool skip_tail = (uint32_t) fmax <= N;               // always true for the detector's own capture size
 	const size_t big_need = 2ull * size * batch;
+	WorkBufs wb = WorkBufs{NULL, NULL};
+	if (f->overlap) {
+		// the internal stream picks up behind everything the caller's stream holds now (the capture is complete there)
+		stream = f->s_side;
+		const size_t need0 = (size_t) N * batch, need1 = (size_t) (N / 2) * batch + 16;
+		if (f->w0_cap < need0 || f->w1_cap < need1) {
+			CU_TRY(ctx, cudaStreamSynchronize(f->s_side));
+			if (f->w0) CU_TRY(ctx, cudaFree(f->w0));
+			if (f->w1) CU_TRY(ctx, cudaFree(f->w1));
+			f->w0 = f->w1 = NULL; f->w0_cap = f->w1_cap = 0;
+			CU_TRY(ctx, cudaMalloc(&f->w0, sizeof(float2) * need0)); f->w0_cap = need0;
+			CU_TRY(ctx, cudaMalloc(&f->w1, sizeof(float2) * need1)); f->w1_cap = need1;
+		}
+		wb = WorkBufs{f->w0, f->w1};
+		CU_TRY(ctx, cudaEventRecord(f->ev_in, caller));
+		CU_TRY(ctx, cudaStreamWaitEvent(f->s_side, f->ev_in, 0));
+	}
 	if (f->big_cap < big_need) {
 		CU_TRY(ctx, cudaStreamSynchronize(stream));
 		if (f->d_big) CU_TRY(ctx, cudaFree(f->d_big));
@@ -1113,7 +1179,7 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 	// only the two lag windows are ever read (frameratedetector.c:106-109): the last step writes nothing else
 	LagWindows win = LagWindows{0, 0, 0, 0};
 	if (skip_tail && !getenv("TSDRGPU_AUTOCORR_ALL_LAGS")) win = LagWindows{(unsigned) fmin, (unsigned) fmax, (unsigned) lmin, (unsigned) lmax};
-	if ((rc = autocorrelation_batch(ctx, stream, f->d_big, 2ll * size, d_capture, (long long) capture_stride, size, batch, skip_tail, win))) return rc;
+	if ((rc = autocorrelation_batch(ctx, stream, f->d_big, 2ll * size, d_capture, (long long) capture_stride, size, batch, skip_tail, win, wb))) return rc;
 	if (flen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) flen, ctx->sm_count), 256, 0, stream>>>(f->d_p1, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, fmin, flen));
 	if (llen) KL(ctx, "k_accumulate", stream, k_accumulate_batch<<<grid1d((unsigned long long) llen, ctx->sm_count), 256, 0, stream>>>(f->d_p2, first_calls, reinterpret_cast<const float2 *>(f->d_big), (long long) size, batch, lmin, llen));
 	KL(ctx, "k_plot_peaks", stream, k_plot_peaks<<<2, 1024, 0, stream>>>(f->d_p1, flen, f->d_p2, llen, f->d_peaks));
@@ -1123,6 +1189,7 @@ static int frd_run_impl(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, co
 		if (h_line_plot) CU_TRY(ctx, cudaMemcpyAsync(h_line_plot, f->d_p2, sizeof(double) * (size_t) (llen < line_cap ? llen : line_cap), cudaMemcpyDeviceToHost, stream));
 		if (synchronise) CU_TRY(ctx, cudaStreamSynchronize(stream));
 	}
+	if (f->overlap) { CU_TRY(ctx, cudaEventRecord(f->ev_done, f->s_side)); f->pending = 1; }
 	return TSDRGPU_OK;
 }
 
@@ -1149,6 +1216,7 @@ int tsdrgpu_frd_get_plots(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, 
 	tsdrgpu_frd_windows(samplerate, &fmin, &fmax, &lmin, &lmax);
 	const int flen = fmax - fmin, llen = lmax - lmin;
 	ARG_TRY(ctx, f->p1_cap >= (size_t) flen && f->p2_cap >= (size_t) llen);
+	if (f->pending) CU_TRY(ctx, cudaStreamWaitEvent(stream, f->ev_done, 0));
 	if (h_frame_plot) CU_TRY(ctx, cudaMemcpyAsync(h_frame_plot, f->d_p1, sizeof(double) * (size_t) (flen < frame_cap ? flen : frame_cap), cudaMemcpyDeviceToHost, stream));
 	if (h_line_plot) CU_TRY(ctx, cudaMemcpyAsync(h_line_plot, f->d_p2, sizeof(double) * (size_t) (llen < line_cap ? llen : line_cap), cudaMemcpyDeviceToHost, stream));
 	CU_TRY(ctx, cudaStreamSynchronize(stream));
@@ -1173,12 +1241,14 @@ int tsdrgpu_plot_peaks(tsdrgpu_ctx_t *ctx, void *stream_, const double *d_frame_
 int tsdrgpu_frd_peaks_async(tsdrgpu_frd_t *f, void *stream, int32_t *h_peaks_pinned) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL && h_peaks_pinned != NULL);
 	BIND(f->ctx);
+	if (f->pending) CU_TRY(f->ctx, cudaStreamWaitEvent((cudaStream_t) stream, f->ev_done, 0));
 	CU_TRY(f->ctx, cudaMemcpyAsync(h_peaks_pinned, f->d_peaks, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
 	return TSDRGPU_OK;
 }
 int tsdrgpu_frd_peaks(tsdrgpu_frd_t *f, void *stream, int32_t *h_peaks) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL && h_peaks != NULL);
 	BIND(f->ctx);
+	if (f->pending) CU_TRY(f->ctx, cudaStreamWaitEvent((cudaStream_t) stream, f->ev_done, 0));
 	CU_TRY(f->ctx, cudaMemcpyAsync(h_peaks, f->d_peaks, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
 	CU_TRY(f->ctx, cudaStreamSynchronize((cudaStream_t) stream));
 	return TSDRGPU_OK;

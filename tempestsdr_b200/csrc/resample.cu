@@ -637,14 +637,17 @@ int tsdrgpu_resampler_run(tsdrgpu_resampler_t *r, void *stream_, const float *d_
 			if (in_is_iq) KL(ctx, "rs_main", stream, rs_main<true><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
 			else KL(ctx, "rs_main", stream, rs_main<false><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
 		} else {
-			// resident CTAs per SM the register allocation aims at (TSDRGPU_RS_MINB, experiments: 3 = 80 registers, 4 = 64, 5 = 48)
-			static const int minb = getenv("TSDRGPU_RS_MINB") ? atoi(getenv("TSDRGPU_RS_MINB")) : 3;
+			// Resident CTAs per SM the register allocation aims at.  ncu (r02b): at 80 registers (3 CTAs, 37 % of the warp slots) the
+			// kernel was latency-bound -- issue slots 53 % busy, long-scoreboard stalls first.  Measured per launch of 640 blocks:
+			// 179.8 us at 3 CTAs (80 registers), 159.0 at 4 (64), 151.3 at 5 (48, 44 bytes of spills), 163.0 at 6 (40, 132 bytes).
+			// TSDRGPU_RS_MINB overrides for experiments.
+			static const int minb = getenv("TSDRGPU_RS_MINB") ? atoi(getenv("TSDRGPU_RS_MINB")) : 5;
 			if (in_is_iq) {
 				if (minb >= 6) KL(ctx, "rs_main", stream, rs_main4<true, 6><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
 				else if (minb == 5) KL(ctx, "rs_main", stream, rs_main4<true, 5><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
 				else if (minb == 4) KL(ctx, "rs_main", stream, rs_main4<true, 4><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
 				else KL(ctx, "rs_main", stream, rs_main4<true, 3><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, mag));
-			} else KL(ctx, "rs_main", stream, rs_main4<false, 3><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
+			} else KL(ctx, "rs_main", stream, rs_main4<false, 5><<<tiles, RS_THREADS, 0, stream>>>(d_in, d_out, db, dp, (float *) NULL));
 		}
 		if (in_is_iq) KL(ctx, "rs_fixup", stream, rs_fixup<true><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));
 		else KL(ctx, "rs_fixup", stream, rs_fixup<false><<<1, 256, 0, stream>>>(d_in, d_out, db, nblocks, r->d_bank, r->d_has_a, r->d_contrib));

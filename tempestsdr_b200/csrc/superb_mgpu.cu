@@ -97,6 +97,20 @@ __global__ void __launch_bounds__(256) sbm_abs_diff(const float2 *__restrict__ s
 	}
 }
 
+// the same for two signals in one launch (blockIdx.y picks the signal): dst = [ diff(src0) | diff(src1) ], n each
+__global__ void __launch_bounds__(256) sbm_abs_diff2(const float2 *__restrict__ src0, const float2 *__restrict__ src1, float2 *__restrict__ dst, unsigned n) {
+	const float2 *src = blockIdx.y ? src1 : src0;
+	float2 *d = dst + (size_t) blockIdx.y * n;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float2 v = src[i];
+		const float cur = mag_exact(v.x, v.y);
+		float prev;
+		if (i == 0) prev = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
+		else { const float2 u = src[i - 1]; prev = mag_exact(u.x, u.y); }
+		d[i] = make_float2(__fsub_rn(cur, prev), 0.0f);
+	}
+}
+
 // P = (aI bI + aQ bQ, aI bQ - aQ bI) (fft.c:80-89) with a = D_0 in RANK 0's window (NVLink loads), b = D_q local
 __global__ void __launch_bounds__(256) sbm_xcorr_pull(const float4 *__restrict__ d0_remote, const float4 *__restrict__ dq, float4 *__restrict__ out, unsigned n2 /* pairs of complex */) {
 	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
@@ -195,7 +209,9 @@ struct tsdrgpu_superb_mgpu {
 	unsigned char *win; size_t win_bytes;
 	size_t off_d, off_x, off_v, off_r;                // byte offsets in the window: D (difference spectrum), Xp (re-ordered spectrum), A (block transform), the root's stream
 	Peers peers; int connected; int ipc_opened[SBM_MAX_RANKS];
-	float2 *d_work, *d_p, *d_x; void *d_part; int *d_lag;   // local temporaries
+	float2 *d_work, *d_p, *d_x; void *d_part; int *d_lag;   // local temporaries (d_work, d_dd: 2 n_max complex -- the two difference signals / spectra side by side)
+	float2 *d_dd, *d_side;                            // d_side: the side stream's transform scratch
+	cudaStream_t s_side; cudaEvent_t ev_fork, ev_join; // the hop's own spectrum runs beside the lag search
 	unsigned epoch; unsigned last_n;
 	unsigned prep_n, prep_nd;                         // transform sizes whose kernels and twiddle tables are known to be resident
 	long long timeout_cycles;
@@ -219,9 +235,14 @@ int tsdrgpu_superb_mgpu_create(tsdrgpu_ctx_t *ctx, int nranks, int rank, int roo
 	g->win_bytes = g->off_r + sizeof(float) * n * (size_t) nranks;
 	CU_TRY(ctx, cudaMalloc(&g->win, g->win_bytes));
 	CU_TRY(ctx, cudaMemset(g->win, 0, sizeof(WinHeader)));
-	CU_TRY(ctx, cudaMalloc(&g->d_work, sizeof(float2) * n));
+	CU_TRY(ctx, cudaMalloc(&g->d_work, sizeof(float2) * 2 * n));
+	CU_TRY(ctx, cudaMalloc(&g->d_dd, sizeof(float2) * 2 * n));
+	CU_TRY(ctx, cudaMalloc(&g->d_side, sizeof(float2) * n));
 	CU_TRY(ctx, cudaMalloc(&g->d_p, sizeof(float2) * n));
 	CU_TRY(ctx, cudaMalloc(&g->d_x, sizeof(float2) * n));
+	CU_TRY(ctx, cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking));
+	CU_TRY(ctx, cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+	CU_TRY(ctx, cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
 	CU_TRY(ctx, cudaMalloc(&g->d_part, 8 * TSDRGPU_ARGMAX_PARTS));
 	CU_TRY(ctx, cudaMalloc(&g->d_lag, 256));
 	CU_TRY(ctx, cudaMemset(g->d_lag, 0, 256));
@@ -253,6 +274,10 @@ void tsdrgpu_superb_mgpu_destroy(tsdrgpu_superb_mgpu_t *g) {
 	cudaDeviceSynchronize();
 	for (int q = 0; q < g->H; q++) if (g->ipc_opened[q] && g->peers.win[q]) cudaIpcCloseMemHandle(g->peers.win[q]);
 	cudaFree(g->win); cudaFree(g->d_work); cudaFree(g->d_p); cudaFree(g->d_x); cudaFree(g->d_part); cudaFree(g->d_lag);
+	cudaFree(g->d_dd); cudaFree(g->d_side);
+	if (g->s_side) cudaStreamDestroy(g->s_side);
+	if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+	if (g->ev_join) cudaEventDestroy(g->ev_join);
 	delete g;
 }
 
@@ -325,6 +350,10 @@ static int sbm_prepare(tsdrgpu_superb_mgpu *g, cudaStream_t stream, unsigned N, 
 	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_x, N, 1))) return rc;
 	int *tmp_lag = g->d_lag + 8;
 	if ((rc = tsdrgpu_argmax_mag_internal(ctx, stream, g->d_p, nd, g->d_part, tmp_lag))) return rc;
+	if ((rc = tsdrgpu_fft_batch_internal(ctx, stream, g->d_work, (long long) nd, g->d_dd, (long long) nd, NULL, nd, 2, 0))) return rc;
+	if ((rc = tsdrgpu_fft_batch_internal(ctx, g->s_side, g->d_work, 0, g->d_x, 0, g->d_side, N, 1, 0))) return rc;
+	CU_TRY(ctx, cudaStreamSynchronize(g->s_side));
+	preload(sbm_abs_diff2);
 	preload(sbm_sync); preload(sbm_abs_diff); preload(sbm_xcorr_pull); preload(sbm_permute_ramp); preload(sbm_pull_blocks);
 	switch (g->H) {
 	case 2: preload(sbm_final<2>); break;
@@ -362,16 +391,26 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 	g->last_n = N;
 	float2 *D = reinterpret_cast<float2 *>(g->win + g->off_d), *Xp = reinterpret_cast<float2 *>(g->win + g->off_x), *Ablk = reinterpret_cast<float2 *>(g->win + g->off_v);
 	// ---- phase 1: this hop's spectrum, this hop's alignment lag, the spectrum re-ordered + ramped into the own window
-	if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, reinterpret_cast<const float2 *>(d_hop), g->d_x, N, 0))) return rc;
+	// The hop's own spectrum (N points) and the search for its lag (three nd-point transforms) do not depend on each other, and a
+	// single transform of this size fills the chip for little more than one wave of CTAs: on every rank but the first the spectrum
+	// runs on the group's side stream (own scratch) beside the lag search; the two meet again in front of sbm_permute_ramp.
+	const bool forked = rank != 0;
+	if (forked) {
+		CU_TRY(ctx, cudaEventRecord(g->ev_fork, stream));
+		CU_TRY(ctx, cudaStreamWaitEvent(g->s_side, g->ev_fork, 0));
+		if ((rc = tsdrgpu_fft_batch_internal(ctx, g->s_side, reinterpret_cast<const float2 *>(d_hop), 0, g->d_x, 0, g->d_side, N, 1, 0))) return rc;
+		CU_TRY(ctx, cudaEventRecord(g->ev_join, g->s_side));
+	} else if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, reinterpret_cast<const float2 *>(d_hop), g->d_x, N, 0))) return rc;
 	if (rank != 0) {
-		KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));
-		if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
 		const float4 *d0;
-		if (d_hop0) {                                         // the alignment reference is resident here: its difference spectrum locally
-			KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop0), g->d_work, nd));
-			if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, g->d_p, nd, 0))) return rc;
-			d0 = reinterpret_cast<const float4 *>(g->d_p);
+		if (d_hop0) {                                         // the alignment reference is resident here: both difference spectra in one batched transform
+			KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff2<<<dim3(grid_for(nd, ctx->sm_count), 2), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), reinterpret_cast<const float2 *>(d_hop0), g->d_work, nd));
+			if ((rc = tsdrgpu_fft_batch_internal(ctx, stream, g->d_work, (long long) nd, g->d_dd, (long long) nd, NULL, nd, 2, 0))) return rc;
+			D = g->d_dd;
+			d0 = reinterpret_cast<const float4 *>(g->d_dd + nd);
 		} else {                                              // pull it from rank 0 once its spectra are in place
+			KL(ctx, "sbm_abs_diff", stream, sbm_abs_diff<<<grid_for(nd, ctx->sm_count), 256, 0, stream>>>(reinterpret_cast<const float2 *>(d_hop), g->d_work, nd));
+			if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
 			KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
 			d0 = reinterpret_cast<const float4 *>(g->peers.win[0] + g->off_d);
 		}
@@ -383,6 +422,7 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 		if ((rc = tsdrgpu_fft_oop_internal(ctx, stream, g->d_work, D, nd, 0))) return rc;
 		KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_SPEC, epoch, all, all, (const int *) NULL, g->timeout_cycles));
 	}
+	if (forked) CU_TRY(ctx, cudaStreamWaitEvent(stream, g->ev_join, 0));
 	KL(ctx, "sbm_permute_ramp", stream, sbm_permute_ramp<<<grid_for(N, ctx->sm_count, 16), 256, 0, stream>>>(g->d_x, Xp, N, g->log2H, g->d_lag));
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_LAG, epoch, all, all, g->d_lag, g->timeout_cycles));
 	// ---- phase 2: all-to-all #1 (pull this rank's run from everybody), the block transform with the reference's stage angles

@@ -407,6 +407,33 @@ def test_accumulate_exact_and_framerate_plots(gpu, O):
         assert int(np.argmax(gp)) == int(np.argmax(fp))       # the lag the GUI would pick is the same
 
 
+def test_framerate_detector_overlapped_mode_gives_the_same_plots(gpu):
+    """tsdrgpu_frd_set_overlap: the same kernels on the detector's own stream with its own work buffers -- plots, peaks and call
+    counts must be bit-identical to the in-stream mode, also when the caller keeps its stream busy and reuses the capture
+    memory right after tsdrgpu_frd_join."""
+    fs = 2_000_000
+    from tempestsdr_b200.api import FrameRateDetector
+    size = FrameRateDetector.capture_size(fs)
+    caps = [torch.from_numpy(np.abs(synth.video_like_iq(3 * size, fs, 400, 200, 50.0, seed=40 + k).view(np.complex64)).astype(np.float32)).cuda() for k in range(3)]
+    plain, over = gpu.framerate_detector(), gpu.framerate_detector()
+    over.set_overlap(True)
+    busy = torch.empty(8 << 20, device="cuda")
+    for k, c in enumerate(caps):
+        work = c.clone()
+        plain.run_batch(fs, c, size, 3, size)
+        over.run_batch(fs, work, size, 3, size)
+        busy.normal_()                                     # the caller's stream has other things to do meanwhile
+        over.join()
+        work.zero_()                                       # after the join the capture memory may be reused
+        (fo, fp), (lo, lp) = plain.plots(fs)
+        (go, gp), (glo, glp) = over.plots(fs)
+        assert (fo, lo) == (go, glo)
+        assert np.array_equal(fp.view(np.uint64), gp.view(np.uint64)) and np.array_equal(lp.view(np.uint64), glp.view(np.uint64)), f"plots after batch {k}"
+    over.set_overlap(False)
+    plain.run_batch(fs, caps[0], size, 2, size); over.run_batch(fs, caps[0], size, 2, size)
+    assert np.array_equal(plain.plots(fs)[0][1].view(np.uint64), over.plots(fs)[0][1].view(np.uint64))
+
+
 def test_plot_peaks_on_the_device_match_the_gui_pick(gpu):
     """the first strict maximum of the two autocorrelation plots, reduced on the GPU (k_plot_peaks), against the
     GUI's pick restated on the host (tsdrgpu_detect_videomode <- PlotVisualizer.java:203-236): 120 seeded plots with ties,
