@@ -378,6 +378,12 @@ def run_ours(args):
     iq_host = make_iq(pairs, seed=1000 + rank)
     iq_pinned = torch.from_numpy(iq_host).pin_memory()
     iq_dev = iq_pinned.cuda(non_blocking=True)
+    # The pixel path is the critical chain of a batch (resampler -> auto-gain -> IIR -> collapse, then the sync search on the frame
+    # stage's own high-priority stream); the frame-rate detector's transforms are background work on a lowest-priority stream.
+    # BENCH_MAIN_STREAM_PRIO=<n> runs the step on a torch stream of that priority instead of the default stream (study knob).
+    if os.environ.get("BENCH_MAIN_STREAM_PRIO"):
+        torch.cuda.synchronize()                         # the resident IQ was copied on the default stream
+        torch.cuda.set_stream(torch.cuda.Stream(priority=int(os.environ["BENCH_MAIN_STREAM_PRIO"])))
     batch = DeviceStep(gpu, iq_dev, w)
 
     def step():

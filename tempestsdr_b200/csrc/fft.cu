@@ -1091,7 +1091,13 @@ int tsdrgpu_frd_set_overlap(tsdrgpu_frd_t *f, int on) {
 	tsdrgpu_ctx_t *ctx = f->ctx;
 	BIND(ctx);
 	if (on && !f->s_side) {
-		CU_TRY(ctx, cudaStreamCreateWithFlags(&f->s_side, cudaStreamNonBlocking));
+		// the detector's work is background work (a plot every few frames): lowest priority, so that the block scheduler hands free
+		// SM resources to the pixel path first and lets the transforms fill what is left (TSDRGPU_FRD_PRIO=high|default for studies)
+		int lo = 0, hi = 0;
+		CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		const char *pr = getenv("TSDRGPU_FRD_PRIO");
+		const int prio = (pr && !strcmp(pr, "high")) ? hi : ((pr && !strcmp(pr, "default")) ? 0 : lo);
+		CU_TRY(ctx, cudaStreamCreateWithPriority(&f->s_side, cudaStreamNonBlocking, prio));
 		CU_TRY(ctx, cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
 		CU_TRY(ctx, cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming));
 	}
