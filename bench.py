@@ -773,7 +773,8 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
     hop0 = hop_of(0)                                      # the alignment reference, kept on every device (the pipeline copies hop 0 to all GPUs at ingest)
     flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")            # 256 MB > L2
     n_fft = gpu.fft_getrealsize(hop_pairs)
-    out = torch.empty(H * n_fft, dtype=torch.float32, device="cuda") if rank == 0 else None
+    # the root consumes the stream where the last phase leaves it (its window; tsdrgpu_superb_mgpu_stream_window): no copy out
+    stitch = lambda: grp.stitch(hop, sif, hop0=hop0, in_place=True)
     flags = PostProcessFlags(autoshift=True, lowpass_before_sync=True, superresolution=True)
     # ---- rank 0 alone: the same hops on one GPU (timing + the parity reference), buffers and first launches of the frames path
     solo = torch.zeros(2, device="cuda", dtype=torch.float64)                      # [ok, one_gpu_ms]
@@ -843,7 +844,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
         return partial
 
     for _ in range(3):
-        grp.stitch(hop, sif, out=out, hop0=hop0)
+        stitch()
     if not group_ok():
         return give_up("in the warm-up stitches", {"hops": H, "n_per_hop": n_fft, "one_gpu_ms": one_ms})
     lags = grp.lags()
@@ -852,7 +853,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for a, b in evs:
         flush.zero_()
-        a.record(); grp.stitch(hop, sif, out=out, hop0=hop0); b.record()
+        a.record(); out = stitch(); b.record()
     barrier()
     tms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / reps], device="cuda")
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -860,6 +861,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
            "one_gpu_ms": one_ms, "speedup_vs_one_gpu": one_ms / tms.item(),
            "lags": lags, "l2_flushed_between_repetitions": True,
            "resident_before_the_timed_region": "hop q on GPU q, plus a copy of hop 0 (the alignment reference) on every GPU, as the pipeline leaves them",
+           "stream_lands": "in the root's window of the group (consumed in place by the resampler; no device-to-device copy)",
            "exchange": "peer-memory windows (CUDA IPC over NVLink), flags in peer memory; no collective library on the data path",
            "nvlink_bytes_received_per_rank": int(8 * (n_fft // 2) * (1 if rank else 0) + 2 * 8 * n_fft * (H - 1) // H),
            "nvlink_bytes_received_by_root_for_stream": int(4 * n_fft * (H - 1))}
@@ -872,7 +874,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
         res["parity_vs_one_gpu_path"] = {"max_err_over_peak": err, "lags_equal": [2 * l for l in lags] == r0["one_offs"], "bound": 1e-5}
     # ---- frames: stitch + resample + frame stage of the stitched stream on the root; every rank takes part in the stitch
     def round_trip():
-        so = grp.stitch(hop, sif, out=out, hop0=hop0)
+        so = stitch()
         return r0["frames_of"](so) if rank == 0 else 0
     host_barrier()
     nf = 0
@@ -897,7 +899,7 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
         gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 1))
         for _ in range(3):
             flush.zero_()
-            grp.stitch(hop, sif, out=out, hop0=hop0)
+            stitch()
         torch.cuda.synchronize()
         gpu.chk(gpu._lib.tsdrgpu_profile_enable(gpu._h, 0))
         mine = {k: round(1e3 * t / 3, 2) for k, (t, c) in collect_profile(gpu).items()}

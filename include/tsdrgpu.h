@@ -326,6 +326,8 @@ TSDRGPU_API int  tsdrgpu_superb_mgpu_disconnect(tsdrgpu_superb_mgpu_t *g);
 TSDRGPU_API int  tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream, const float *d_hop, const float *d_hop0, int count_pairs,
                                             int samples_in_frame, float *d_stream_out, uint32_t *h_n);
 /* lags (complex samples) of the last stitch as every rank published them, and the status word (0 = fine); synchronises `stream` */
+/* the root's stream inside its window: valid after a stitch called with d_stream_out = NULL, until the root's next stitch */
+TSDRGPU_API int  tsdrgpu_superb_mgpu_stream_window(tsdrgpu_superb_mgpu_t *g, float **d_stream);
 TSDRGPU_API int  tsdrgpu_superb_mgpu_lags(tsdrgpu_superb_mgpu_t *g, void *stream, int *h_lags, uint32_t *h_status);
 
 /* ---------------------------------------------------------------------------- a1, a3, a5, a16, a17  streaming pipeline

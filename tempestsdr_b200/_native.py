@@ -133,6 +133,7 @@ _SIGS = {
     "tsdrgpu_superb_mgpu_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "tsdrgpu_superb_mgpu_disconnect": (C.c_int, [C.c_void_p]),
     "tsdrgpu_superb_mgpu_stitch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "tsdrgpu_superb_mgpu_stream_window": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_superb_mgpu_lags": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "tsdrgpu_pipeline_create": (C.c_int, [C.c_void_p, C.POINTER(PipelineConfig), FRAME_CB, VALUE_CB, PLOT_CB, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tsdrgpu_pipeline_destroy": (None, [C.c_void_p]),

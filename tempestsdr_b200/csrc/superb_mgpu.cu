@@ -375,7 +375,6 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 	tsdrgpu_ctx_t *ctx = g->ctx;
 	BIND(ctx);
 	ARG_TRY(ctx, g->connected && d_hop != NULL && count_pairs > 0 && samples_in_frame > 0);
-	ARG_TRY(ctx, g->rank != g->root || d_stream_out != NULL);
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const unsigned N = tsdrgpu_fft_getrealsize((uint32_t) count_pairs);
 	int size = (int) ((2ull * N / (unsigned) samples_in_frame) * (unsigned) samples_in_frame);     // superbandwidth.c:84-86 with bufsize = 2N floats
@@ -450,8 +449,18 @@ int tsdrgpu_superb_mgpu_stitch(tsdrgpu_superb_mgpu_t *g, void *stream_, const fl
 	}
 	KL(ctx, "sbm_sync", stream, sbm_sync<<<1, 32, 0, stream>>>(g->peers, H, rank, PH_RES, epoch, 1u << g->root, rank == g->root ? all : 0u, (const int *) NULL, g->timeout_cycles));
 	// ---- phase 4 (root): the stream is complete and time-contiguous in the window; hand it to the caller
-	if (rank == g->root) CU_TRY(ctx, cudaMemcpyAsync(d_stream_out, g->win + g->off_r, sizeof(float) * (size_t) H * N, cudaMemcpyDeviceToDevice, stream));
+	// (d_stream_out == NULL: the caller reads it in place, tsdrgpu_superb_mgpu_stream_window -- on this stream, before its next stitch)
+	if (rank == g->root && d_stream_out) CU_TRY(ctx, cudaMemcpyAsync(d_stream_out, g->win + g->off_r, sizeof(float) * (size_t) H * N, cudaMemcpyDeviceToDevice, stream));
 	if (h_n) *h_n = N;
+	return TSDRGPU_OK;
+}
+
+// Where the root's stream lands inside its window (nranks * N floats after a stitch).  A root that passes d_stream_out = NULL to
+// tsdrgpu_superb_mgpu_stitch consumes the stream from here: on the stitch's stream and before its next stitch, whose last phase
+// overwrites it (the peers cannot get there earlier: they wait for the root's flags of the next stitch).
+int tsdrgpu_superb_mgpu_stream_window(tsdrgpu_superb_mgpu_t *g, float **d_stream) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, g != NULL && d_stream != NULL);
+	*d_stream = reinterpret_cast<float *>(g->win + g->off_r);
 	return TSDRGPU_OK;
 }
 

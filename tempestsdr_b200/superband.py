@@ -221,12 +221,23 @@ class SuperbGroup:
         gs[0].ctx.chk(gs[0].ctx._lib.tsdrgpu_superb_mgpu_connect_local(arr, len(gs)))
         return gs
 
-    def stitch(self, hop: torch.Tensor, samples_in_frame: int, out: Optional[torch.Tensor] = None, hop0: Optional[torch.Tensor] = None):
+    def stitch(self, hop: torch.Tensor, samples_in_frame: int, out: Optional[torch.Tensor] = None, hop0: Optional[torch.Tensor] = None,
+               in_place: bool = False):
         """This rank's share of one stitch, asynchronous on the current stream of the context's device.  On the root returns
         the magnitude stream (nranks * N floats, time-contiguous); elsewhere None.  hop0: this device's copy of hop 0 (the
-        alignment reference), passed by every rank or by none."""
+        alignment reference), passed by every rank or by none.  in_place (root): no copy out of the group's window -- the
+        returned tensor IS the window and is valid until this rank's next stitch."""
         pairs = hop.numel() // 2
         n = self.ctx.fft_getrealsize(pairs)
+        if in_place:
+            hn = C.c_uint32(0)
+            self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_stitch(self._h, self.ctx.stream, hop.data_ptr(), hop0.data_ptr() if hop0 is not None else None, pairs,
+                                                                  samples_in_frame, None, C.byref(hn)))
+            if self.rank != self.root:
+                return None
+            p = C.c_void_p()
+            self.ctx.chk(self.ctx._lib.tsdrgpu_superb_mgpu_stream_window(self._h, C.byref(p)))
+            return _device_view(p.value, self.nranks * hn.value)
         if self.rank == self.root and out is None:
             out = torch.empty(self.nranks * n, dtype=torch.float32, device=hop.device)
         hn = C.c_uint32(0)

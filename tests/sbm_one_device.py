@@ -36,7 +36,8 @@ def run(H: int, full: bool = False) -> None:
         for r in range(H):
             with torch.cuda.stream(streams[r]):
                 # round 0: every rank holds its own copy of hop 0 (the alignment reference); round 1: rank 0's difference spectrum is pulled
-                res = groups[r].stitch(d_hops[r], sif, hop0=d_hops[0] if rnd == 0 else None)
+                # round 1 also leaves the stream in the root's window (no copy out) and reads it from there
+                res = groups[r].stitch(d_hops[r], sif, hop0=d_hops[0] if rnd == 0 else None, in_place=(rnd == 1))
                 out = res if res is not None else out
         torch.cuda.synchronize()
         lags = groups[0].lags()

@@ -69,6 +69,15 @@ def _worker(rank, world, port, q):
         ok = ok and good
         msg += f" mgpu[{rnd}] lags_ok={good}"
         dist.barrier()
+    # the root reading the stream in place from its window (no copy out): the same floats
+    kept = out.clone() if rank == 0 else None
+    view = grp.stitch(torch.from_numpy(hops[rank]).cuda(), sif, hop0=None, in_place=True)
+    grp.lags()
+    if rank == 0:
+        same = bool(torch.equal(view, kept))
+        ok = ok and same
+        msg += f" in_place_same={same}"
+    dist.barrier()
     grp.close()
     q.put((rank, ok, msg))
     dist.destroy_process_group()
