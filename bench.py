@@ -614,7 +614,7 @@ def run_ours(args):
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
     ratio = w * HEIGHT * FV / FS
     n_pix = batch.n * FRAMES_PER_BATCH
-    NFFT = 1 << 20                                        # cfg2 capture 1 409 090 -> N = 2^20
+    NFFT = 1 << (int(3.1 * FS / 55.0).bit_length() - 1)   # the capture's transform size (fft_getrealsize): cfg2 capture 1 409 090 -> N = 2^20
     # ALGORITHMIC bytes per launch.  The autocorrelation of one capture runs at half size (N/2 complex
     # points per transform): per capture the fused passes move  fwd A: read 8*(N/2) write 8*(N/2);  fwd B (+ finish, |X|/N):
     # read 8*(N/2) write 4*N;  inv A: read 4*N write 8*(N/2);  inv B (+ finish): read 8*(N/2) write 8*N  = 40*N bytes in all

@@ -39,7 +39,7 @@ struct FftPass {
 	long long out_hi, out_lo, out_cs, out_ks;
 	unsigned long long tw_M; long long tw_lo, tw_cs;    // column index = g_lo*tw_lo + c*tw_cs ; tw_M == 0: none
 	float scale;
-	int in_real, out_abs;
+	int in_real, out_abs;                               // in_real: 1 = real input widened to (x, 0); 2 = complex input given as PAIRS OF FLOATS that are only 4-byte aligned (in_bs then counts floats)
 	const float2 *tw_step;                              // host-built W_M^(col (L/8) j), [col][8]; NULL: compute every twiddle
 	float2 *fan[16]; int nfan;                          // FAN kernels: the last stage stores to every fan[p] + offset instead of `out`
 	int exact0;                                         // the first three layers of this pass have eps = 0: plain DFT-8
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(32) fft_tiny_kernel(const float2 *in, float2 *
 	float2 v[L];
 	#pragma unroll
 	for (int j = 0; j < L; j++) {
-		v[j] = P.in_real ? make_float2(reinterpret_cast<const float *>(in)[ib + j], 0.0f) : in[ib + j];
+		if (P.in_real == 2) { const float *pr = reinterpret_cast<const float *>(in) + ib + 2 * j; v[j] = make_float2(pr[0], pr[1]); }
+		else v[j] = P.in_real ? make_float2(reinterpret_cast<const float *>(in)[ib + j], 0.0f) : in[ib + j];
 		if (P.conj_in) v[j].y = -v[j].y;
 	}
 	if (L == 2) dft2(v[0], v[1]); else dft4(v[0], v[1], v[2], v[3], false);
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 	const int C = P.C, log2C = P.log2C;
 	const int tid = threadIdx.x;
 	const unsigned g = blockIdx.x, g_hi = g / P.G_lo, g_lo = g - g_hi * P.G_lo;
-	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (long long) blockIdx.y * P.in_bs;
+	const long long in_base = (long long) g_hi * P.in_hi + (long long) g_lo * P.in_lo + (P.in_real == 2 ? 0ll : (long long) blockIdx.y * P.in_bs);
 	float2 *gout = out + ((long long) g_hi * P.out_hi + (long long) g_lo * P.out_lo + (long long) blockIdx.y * P.out_bs);
 	const bool active = tid < C * L8;                    // tiny bundles leave part of the last warp idle
 	// per-line slot constants (see above): xa for the buffer stage 0 writes, xb for the buffer the last stage reads
@@ -259,7 +260,15 @@ __global__ void __launch_bounds__(512, 3) fft_pass_kernel(const float2 *in, floa
 			}
 		} else if (active) {
 			const int off = c * (int) P.in_cs + i * (int) P.in_js, step = L8 * (int) P.in_js;
-			if (P.in_real) {
+			if (P.in_real == 2) {                             // pairs of floats, 4-byte aligned (a capture that starts on an odd sample)
+				const float *gr = reinterpret_cast<const float *>(in) + (long long) blockIdx.y * P.in_bs + 2 * (in_base + off);
+				#pragma unroll
+				for (int m = 0; m < 8; m++) v[m] = make_float2(__ldg(gr + 2 * m * step), __ldg(gr + 2 * m * step + 1));
+				if (P.conj_in) {
+					#pragma unroll
+					for (int m = 0; m < 8; m++) v[m].y = -v[m].y;
+				}
+			} else if (P.in_real) {
 				const float *gr = reinterpret_cast<const float *>(in) + in_base + off;
 				#pragma unroll
 				for (int m = 0; m < 8; m++) v[m] = make_float2(__ldg(gr + m * step), 0.0f);
@@ -748,6 +757,7 @@ struct FftOpts {
 	long long data_bs, scratch_bs, real_bs;   // distance between consecutive transforms in data (complex), scratch (complex), real_in (floats)
 	float2 *const *fan; int nfan;             // forward only: the final pass stores the result to every fan[p] (same layout as `data`) instead of `data`
 	const float2 *cplx_in; long long cplx_bs; // the first pass reads its (complex) input from here instead of `data` (which is then output only)
+	const float *pair_in; long long pair_bs;  // the same, but the input is pairs of floats with 4-byte alignment only; pair_bs in FLOATS
 	float *abs_real;                          // with out_abs (batch 1): the final pass stores |.| as float32 here (peer memory allowed) and leaves `data` alone
 };
 
@@ -755,8 +765,9 @@ struct FftOpts {
 // With opts.real_in the input is read from a real array instead (data is output only).
 int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scratch, unsigned log2N, int inverse, FftOpts o) {
 	const unsigned long long N = 1ull << log2N;
-	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : (o.cplx_in ? o.cplx_in : data);
-	const long long in0_bs = o.real_in ? o.real_bs : (o.cplx_in ? o.cplx_bs : o.data_bs);
+	const float2 *src0 = o.real_in ? reinterpret_cast<const float2 *>(o.real_in) : (o.pair_in ? reinterpret_cast<const float2 *>(o.pair_in) : (o.cplx_in ? o.cplx_in : data));
+	const long long in0_bs = o.real_in ? o.real_bs : (o.pair_in ? o.pair_bs : (o.cplx_in ? o.cplx_bs : o.data_bs));
+	const int in_mode = o.real_in ? 1 : (o.pair_in ? 2 : 0);
 	double eps_all[40];
 	tsdrgpu_fft_reference_eps((int) log2N < 40 ? (int) log2N : 40, inverse, eps_all);
 	FftPass P; memset(&P, 0, sizeof P);
@@ -766,7 +777,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 	};
 	if (log2N <= FFT_MAX_LOG2L) {                       // one pass, one CTA
 		P.log2L = (int) log2N; P.C = 1; P.G_lo = 1; P.in_js = 1; P.out_ks = 1; P.scale = o.scale;
-		P.in_real = o.real_in != NULL; P.out_abs = o.out_abs; P.abs_real = o.out_abs ? o.abs_real : NULL;
+		P.in_real = in_mode; P.out_abs = o.out_abs; P.abs_real = o.out_abs ? o.abs_real : NULL;
 		with_fan(P);
 		P.conj_in = P.conj_out = inverse ? 1 : 0;
 		return launch_pass(ctx, stream, src0, data, P, 1, inverse, o.batch, in0_bs, o.data_bs, eps_all, 0);
@@ -785,7 +796,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.G_lo = (unsigned) (N2 / P.C);
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N2;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N2;
-		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
+		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = in_mode;
 		P.conj_in = inverse ? 1 : 0;
 		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 		FftPass Q; memset(&Q, 0, sizeof Q);
@@ -807,7 +818,7 @@ int fft_run(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float2 *data, float2 *scrat
 		P.G_lo = (unsigned) (N23 / P.C);
 		P.in_lo = P.C; P.in_cs = 1; P.in_js = (long long) N23;
 		P.out_lo = P.C; P.out_cs = 1; P.out_ks = (long long) N23;
-		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = o.real_in != NULL;
+		P.tw_M = N; P.tw_lo = P.C; P.tw_cs = 1; P.scale = 1.0f; P.in_real = in_mode;
 		P.conj_in = inverse ? 1 : 0;
 		if ((rc = launch_pass(ctx, stream, src0, scratch, P, P.G_lo, inverse, o.batch, in0_bs, o.scratch_bs, eps_all, 0))) return rc;
 	}
@@ -986,7 +997,9 @@ static int autocorrelation_batch_half(tsdrgpu_ctx_t *ctx, cudaStream_t stream, f
 		// forward: Z = FFT_{N/2}(capture viewed as complex pairs), unscaled: capture -> W0 -> W1
 		FftOpts f; memset(&f, 0, sizeof f);
 		f.scale = 1.0f; f.batch = gb; f.data_bs = (long long) half; f.scratch_bs = (long long) half;
-		f.cplx_in = reinterpret_cast<const float2 *>(d_real + (long long) g0 * real_stride); f.cplx_bs = real_stride / 2;
+		const float *cap0 = d_real + (long long) g0 * real_stride;
+		if ((real_stride & 1) || (reinterpret_cast<unsigned long long>(cap0) & 7ull)) { f.pair_in = cap0; f.pair_bs = real_stride; }   // odd capture sizes: every other capture starts on an odd sample
+		else { f.cplx_in = reinterpret_cast<const float2 *>(cap0); f.cplx_bs = real_stride / 2; }
 		if ((rc = fft_run(ctx, stream, W1, W0, log2N - 1, 0, f))) return rc;
 		// R = |X| / N as N reals = N/2 complex: W1 -> W0
 		KL(ctx, "k_real_fwd_finish", stream, k_real_fwd_finish<<<grid, 256, 0, stream>>>(W1, (long long) half, last, half, 1.0f / (float) N,
@@ -1024,8 +1037,7 @@ static int autocorrelation_batch(tsdrgpu_ctx_t *ctx, cudaStream_t stream, float 
 	}
 	// default: both transforms at half size (autocorrelation_batch_half); TSDRGPU_AUTOCORR_FULL=1 keeps the N-point transforms
 	const bool full_size = getenv("TSDRGPU_AUTOCORR_FULL") != NULL;     // read per call: the tests flip it inside one process
-	if (!full_size && N >= 16 && (real_stride & 1) == 0 && (answer_stride & 1) == 0
-	    && (reinterpret_cast<unsigned long long>(d_real) & 7ull) == 0) {
+	if (!full_size && N >= 16 && (answer_stride & 1) == 0) {
 		if (win.hi0 > (unsigned) (N >> 1) || win.hi1 > (unsigned) (N >> 1)) win = LagWindows{0, 0, 0, 0};      // a window beyond N/2: produce every lag
 		return autocorrelation_batch_half(ctx, stream, ans, answer_stride / 2, d_real, real_stride, N, batch, win, wb);
 	}

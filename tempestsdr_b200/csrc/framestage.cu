@@ -56,27 +56,27 @@ __global__ void __launch_bounds__(256) fs_minmax(const float *__restrict__ in, s
 	const float *src = in + (size_t) f * n;
 	float lo = INFINITY, hi = -INFINITY;
 	double sum = 0.0;
-	if (((n & 3) == 0) && ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0)) {      // 16-byte loads
-		const float4 *src4 = reinterpret_cast<const float4 *>(src);
-		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (size_t) gridDim.x * blockDim.x) {
-			const float4 q = __ldg(src4 + i);
-			const float vv[4] = {q.x, q.y, q.z, q.w};
-			#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const float v = vv[u];
-				if (px_is_marker(v)) continue;
-				hi = (v > hi) ? v : hi;
-				lo = (v < lo) ? v : lo;
-				if (SNR) sum += (double) v;
-			}
-		}
-	} else
-	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-		const float v = __ldg(src + i);
-		if (px_is_marker(v)) continue;
+	// 16-byte loads on the ADDRESS: frames of an odd number of pixels (1481 x 1125, 507 x 525) start at any of the four alignments,
+	// so every frame is cut into a scalar head up to the next 16-byte boundary, a float4 body and a scalar tail (min / max and the
+	// SNR's tree-ordered sum do not care about the order)
+	auto take = [&](float v) {
+		if (px_is_marker(v)) return;
 		hi = (v > hi) ? v : hi;
 		lo = (v < lo) ? v : lo;
 		if (SNR) sum += (double) v;
+	};
+	{
+		const size_t gtid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t) gridDim.x * blockDim.x;
+		size_t head = (size_t) ((4u - (unsigned) ((reinterpret_cast<unsigned long long>(src) >> 2) & 3ull)) & 3u);
+		if (head > n) head = n;
+		const size_t nbody = (n - head) >> 2, tail0 = head + (nbody << 2);
+		if (gtid < head) take(__ldg(src + gtid));
+		if (gtid < n - tail0) take(__ldg(src + tail0 + gtid));
+		const float4 *src4 = reinterpret_cast<const float4 *>(src + head);
+		for (size_t i = gtid; i < nbody; i += gsz) {
+			const float4 q = __ldg(src4 + i);
+			take(q.x); take(q.y); take(q.z); take(q.w);
+		}
 	}
 	__shared__ float s_lo[8], s_hi[8];
 	__shared__ double s_sum[8];
@@ -191,14 +191,13 @@ __global__ void __launch_bounds__(256) fs_timelowpass(const float *__restrict__ 
 
 // auto-gain pass 2 fused with the temporal IIR (default stage order): out[f][i] = screen_f[i] where
 // screen_f = lowpass(screen_{f-1}, normalise_f(in[f][i])).  Saves one write + one read of the normalised frames.
+template <bool VEC>
 __global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__ in, float *out, float *screen, size_t n, int nframes,
                                                        const FrameParams *__restrict__ params, float coeff, double fresh) {
 	extern __shared__ float2 s_par[];                    // (lastmin, span) per frame
 	for (int f = threadIdx.x; f < nframes; f += blockDim.x) s_par[f] = make_float2(params[f].lastmin, params[f].span);
 	__syncthreads();
-	const bool vec = ((n & 3) == 0) && (((reinterpret_cast<unsigned long long>(in) | reinterpret_cast<unsigned long long>(out) |
-	                                       reinterpret_cast<unsigned long long>(screen)) & 15ull) == 0);
-	if (vec) {                                           // 4 pixels per thread, 16-byte loads and stores
+	if (VEC) {                                           // 4 pixels per thread, 16-byte loads and stores (n % 4 == 0, aligned bases: checked by the host)
 		const size_t n4 = n >> 2;
 		for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) {
 			float4 sc = reinterpret_cast<float4 *>(screen)[i];
@@ -226,16 +225,25 @@ __global__ void __launch_bounds__(256) fs_norm_lowpass(const float *__restrict__
 		}
 		return;
 	}
+	// frames of an odd number of pixels (1481 x 1125, 507 x 525) start at every alignment: one pixel per thread, and because a
+	// thread then has only 4 bytes per frame to ask for, SIXTEEN frames of loads are in flight before the ordered updates run
+	// (with four the kernel reached 40 % of the HBM roofline at 1481 x 1125 against 72 % for the 16-byte path at 740 x 1125)
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
 		float s = screen[i];
-		#pragma unroll 4
-		for (int f = 0; f < nframes; f++) {
-			const float raw = __ldg(in + (size_t) f * n + i);
-			const float2 p = s_par[f];
-			const float v = px_is_marker(raw) ? raw : __fdiv_rn(__fsub_rn(raw, p.x), p.y);
-			const float old = __fmul_rn(s, coeff);
-			s = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
-			out[(size_t) f * n + i] = s;
+		for (int f0 = 0; f0 < nframes; f0 += 16) {
+			float raw[16];
+			#pragma unroll
+			for (int g = 0; g < 16; g++) if (f0 + g < nframes) raw[g] = ldg_stream_f1(in + (size_t) (f0 + g) * n + i);
+			#pragma unroll
+			for (int g = 0; g < 16; g++) {
+				const int f = f0 + g;
+				if (f >= nframes) break;
+				const float2 p = s_par[f];
+				const float v = px_is_marker(raw[g]) ? raw[g] : __fdiv_rn(__fsub_rn(raw[g], p.x), p.y);
+				const float old = __fmul_rn(s, coeff);
+				s = __double2float_rn(__dadd_rn((double) old, __dmul_rn((double) v, fresh)));
+				out[(size_t) f * n + i] = s;
+			}
 		}
 		screen[i] = s;
 	}
@@ -1332,7 +1340,14 @@ static int framestage_run_impl(tsdrgpu_framestage_t *fs, void *stream_, const fl
 			lp_in = fs->d_t1;
 			KL(ctx, "fs_results_autogain", stream, fs_results_autogain<<<1, 256, 0, stream>>>(nframes, fs->d_params, fs->d_state, d_results));
 		}
-		if (fuse) KL(ctx, "fs_norm_lowpass", stream, fs_norm_lowpass<<<(unsigned) ((n / 4 + 255) / 256 ? (n / 4 + 255) / 256 : 1), 256, sizeof(float2) * nframes, stream>>>(d_in, T2, fs->d_screen, n, nframes, fs->d_params, motionblur, fresh));
+		if (fuse) {
+			// one thread per four pixels on the 16-byte path, one per pixel otherwise (odd frame sizes, unaligned input)
+			const bool vec = ((n & 3) == 0) && (((reinterpret_cast<unsigned long long>(d_in) | reinterpret_cast<unsigned long long>(T2) | reinterpret_cast<unsigned long long>(fs->d_screen)) & 15ull) == 0);
+			const size_t threads = vec ? n / 4 : n;
+			const unsigned grid = (unsigned) ((threads + 255) / 256 ? (threads + 255) / 256 : 1);
+			if (vec) KL(ctx, "fs_norm_lowpass", stream, fs_norm_lowpass<true><<<grid, 256, sizeof(float2) * nframes, stream>>>(d_in, T2, fs->d_screen, n, nframes, fs->d_params, motionblur, fresh));
+			else KL(ctx, "fs_norm_lowpass", stream, fs_norm_lowpass<false><<<grid, 256, sizeof(float2) * nframes, stream>>>(d_in, T2, fs->d_screen, n, nframes, fs->d_params, motionblur, fresh));
+		}
 		else KL(ctx, "fs_timelowpass", stream, fs_timelowpass<<<gx, 256, 0, stream>>>(lp_in, T2, fs->d_screen, n, nframes, motionblur, fresh));
 		if (overlapped) tail = fs->s_side;
 		if ((rc = collapse_sync(T2, tail))) return rc;
