@@ -9,7 +9,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 > gpurun_out/${TAG}_launches.log 2>&1
 for K in "$@"; do
   N=${K//[^a-zA-Z0-9_]/}
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:${K} -s 4 -c 4 -o gpurun_out/${TAG}_${N} \
-      python bench.py --steps 1 --warmup 3 > gpurun_out/${TAG}_${N}.log 2>&1
+  # skip the warm-up launches of the kernel (3 warm-up batches: 12 FFT passes, 3 of every once-per-batch kernel), capture the next ones
+  if [[ $K == fft* ]]; then S=12; C=4; else S=3; C=2; fi
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:${K} -s $S -c $C -o gpurun_out/${TAG}_${N} \
+      python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_${N}.log 2>&1
 done
 ls -la gpurun_out/${TAG}_* | tail -20
