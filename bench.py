@@ -5,15 +5,18 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 Workload (config.workload): BASELINE configs[1] -- 1080p60 geometry (1125 total lines, the GUI's convention;
-W = 740), 25 MS/s float32 IQ.  One step = one batch of 64 frames' worth of synthetic IQ (640 decimator blocks of
-41666 pairs = 26.7 M pairs = 213 MB, larger than L2) through the whole hot path:
+W = 740), 25 MS/s float32 IQ.  One BATCH = 64 frames' worth of synthetic IQ (640 decimator blocks of 41666 pairs = 26.7 M
+pairs = 213 MB, larger than L2) through the whole hot path:
     fused demod+resample -> pixel stream -> frame stage (auto-gain, temporal IIR, collapse, sync search, re-centre)
-    and, beside it, the frame-rate detector: every capture of 3.1*fs/55 samples is demodulated, autocorrelated
-    (2^20-point FFT + IFFT) and accumulated into the two lag plots.
+    and, beside it (on the detector's own stream), the frame-rate detector: every capture of 3.1*fs/55 samples is
+    autocorrelated (2^20-point FFT + IFFT at half size) and accumulated into the two lag plots.
+One STEP = 80 batches (~57 ms of device time), so that the default 20 steps time more than a second.
 `value`   MS/s with the IQ already resident in HBM (CUDA events around exactly K steps, max over ranks).
-`e2e`     the same metric through the reference-facing call: tsdrgpu_pipeline_process() == the plugin's process()
-          callback with HOST buffers (pinned), H2D of every block and D2H of every finished frame inside the timed
-          region (host wall clock bracketed by device synchronisation, max over ranks).
+`e2e`     the same metric through the reference-facing API end to end: this repo's libTSDRLibrary.so driven by the reference's
+          UNMODIFIED RawFile plugin through tsdr_init / tsdr_loadplugin / tsdr_readasync (pageable 2 MiB blocks, pacing off),
+          H2D of every block and D2H of every finished frame inside the timed region, frames counted in the host's callback --
+          the way the reference arm is measured.  `e2e.pinned_process` beside it: tsdrgpu_pipeline_process_raw_async() on
+          page-locked host IQ (a front end that owns page-locked buffers), `e2e_int8_transport`: the same with 8-bit samples.
 N > 1     N independent streams, one per GPU (the path has no cross-stream exchange: replicas, weak scaling).
 --impl reference   the reference's own threaded CPU pipeline (oracle/_ref: libTSDRLibrary.so + its RawFile plugin
           with pacing off) on this box's host cores, same geometry; falls back to the pinned C port when the
@@ -45,7 +48,7 @@ SHAPE = os.environ.get("BENCH_SHAPE", "cfg2")
 FS, HEIGHT, RASTER_W = SHAPES[SHAPE]
 FV = 60.0
 FRAMES_PER_BATCH = 256 if SHAPE == "cfg1" else 64         # frames per launch group (one pass over the resident 213 MB of IQ; cfg1's small frames: 256 -> 273 MB, still > L2)
-BATCHES_PER_STEP = int(os.environ.get("BENCH_BATCHES_PER_STEP", "48"))   # one step = 48 such passes = 3072 frames = 1.28 G IQ pairs (~40 ms)
+BATCHES_PER_STEP = int(os.environ.get("BENCH_BATCHES_PER_STEP", "80"))   # one step = 80 such passes = 5120 frames = 2.13 G IQ pairs (~57 ms): 20 steps time > 1 s
 FRAMES_PER_STEP = FRAMES_PER_BATCH * BATCHES_PER_STEP
 METRIC = "IQ MS/s ingested -> 1080p60 frames (demod+resample+frame stage+autocorrelation), whole job"
 
