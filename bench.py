@@ -475,8 +475,10 @@ def run_ours(args):
     batch.pp.set_overlap(not os.environ.get("BENCH_NO_OVERLAP"))
     batch.frd.set_overlap(batch.frd_overlap)
     prof_caps = (batch.captures - caps_before_prof) / prof_batches          # captures autocorrelated per profiled batch
+    # rank 0 alone (allocations, first launches of other transform sizes): the other ranks wait on the host, their GPUs idle
+    host_barrier()
     acs = autocorr_sweep(gpu, torch) if (rank == 0 and not os.environ.get("BENCH_NO_SWEEP")) else None
-    barrier()
+    host_barrier()
 
     # ---- e2e (headline): the reference-facing API end to end with an unmodified plugin, as the reference arm is measured
     e2e_seconds = float(os.environ.get("BENCH_E2E_SECONDS", "3.0"))
