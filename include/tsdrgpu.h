@@ -257,6 +257,8 @@ TSDRGPU_API int  tsdrgpu_frd_run_async(tsdrgpu_frd_t *frd, void *stream, uint32_
 TSDRGPU_API int  tsdrgpu_frd_run_batch(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_captures, uint32_t size,
                                        uint32_t batch, uint64_t capture_stride, uint64_t *calls);
 /* copies the current running means (device-resident) to host buffers; synchronises */
+/* dump_autocorrect (frameratedetector.c:64-85): CSV of (lag in ms, 10 log10 |r|) of one capture's autocorrelation; synchronises */
+TSDRGPU_API int  tsdrgpu_frd_dump_csv(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, const float *d_capture, uint32_t size, const char *path);
 TSDRGPU_API int  tsdrgpu_frd_get_plots(tsdrgpu_frd_t *frd, void *stream, uint32_t samplerate, double *h_frame_plot, int frame_cap,
                                        double *h_line_plot, int line_cap);
 /* SURVEY 8f-3 on the device: index of the first strict maximum of each plot (PlotVisualizer.java:203-236), reduced on the GPU

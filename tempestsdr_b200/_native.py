@@ -111,6 +111,7 @@ _SIGS = {
     "tsdrgpu_frd_run_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "tsdrgpu_frd_run_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "tsdrgpu_frd_dump_csv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_char_p]),
     "tsdrgpu_frd_get_plots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "tsdrgpu_frd_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "tsdrgpu_plot_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),

@@ -342,6 +342,10 @@ class FrameRateDetector:
                                                          stride if stride is not None else size, C.byref(calls)))
         return calls.value
 
+    def dump_csv(self, samplerate: int, capture: torch.Tensor, path: str) -> None:
+        """dump_autocorrect (frameratedetector.c:64-85) of one capture."""
+        self.ctx.chk(self.ctx._lib.tsdrgpu_frd_dump_csv(self._h, self.ctx.stream, samplerate, _f32(capture).data_ptr(), capture.numel(), path.encode()))
+
     def plots(self, samplerate: int):
         fmin, fmax, lmin, lmax = self.windows(samplerate)
         fp, lp = np.zeros(fmax - fmin), np.zeros(lmax - lmin)

@@ -1224,6 +1224,40 @@ int tsdrgpu_frd_run_async(tsdrgpu_frd_t *f, void *stream, uint32_t samplerate, c
 	return frd_run_impl(f, stream, samplerate, d_capture, size, 1, size, h_frame_plot_pinned, frame_cap, h_line_plot_pinned, line_cap, calls, false);
 }
 
+// dump_autocorrect (frameratedetector.c:64-85): the autocorrelation of ONE capture as a CSV of (lag in ms, 10 log10 |r|) for the
+// lags the reference writes (i < fft_getrealsize(2 size) / 2 floats, i.e. the first half of the transformed lags), same header and
+// "%f, %f" rows.  A debugging aid of the GUI (PARAM_AUTOCORR_DUMP): one extra autocorrelation with every lag produced, a device-to-
+// host copy and a synchronisation, only when asked for.  Does not touch the running means.
+int tsdrgpu_frd_dump_csv(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, const float *d_capture, uint32_t size, const char *path) {
+	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);
+	tsdrgpu_ctx_t *ctx = f->ctx;
+	BIND(ctx); ARG_TRY(ctx, d_capture != NULL && size > 0 && path != NULL && samplerate > 0);
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const uint32_t maxels = tsdrgpu_fft_getrealsize(2u * size) / 2u;           // floats of the answer the reference walks
+	float *d_ans = NULL;
+	CU_TRY(ctx, cudaMalloc(&d_ans, sizeof(float) * 2ull * size));
+	int rc = autocorrelation_batch(ctx, stream, d_ans, 2ll * size, d_capture, (long long) size, size, 1, false);
+	std::vector<float> h(maxels);
+	if (rc == TSDRGPU_OK) {
+		const cudaError_t e1 = cudaMemcpyAsync(h.data(), d_ans, sizeof(float) * maxels, cudaMemcpyDeviceToHost, stream);
+		const cudaError_t e2 = (e1 == cudaSuccess) ? cudaStreamSynchronize(stream) : e1;
+		if (e2 != cudaSuccess) rc = tsdrgpu_fail(ctx, TSDRGPU_ECUDA, "autocorrelation dump: copy", e2, __FILE__, __LINE__);
+	} else cudaStreamSynchronize(stream);
+	cudaFree(d_ans);
+	if (rc != TSDRGPU_OK) return rc;
+	FILE *fp = fopen(path, "w");
+	if (!fp) return tsdrgpu_fail(ctx, TSDRGPU_EINVAL, "autocorrelation dump: cannot open the file", cudaSuccess, __FILE__, __LINE__);
+	fprintf(fp, "%s, %s\n", "ms", "dB");
+	for (uint32_t i = 0; i < maxels; i += 2) {
+		const double I = (double) h[i], Q = (i + 1 < maxels) ? (double) h[i + 1] : 0.0;
+		const double db = 10.0 * log10(sqrt(I * I + Q * Q));
+		const double t = 1000.0 * (double) (i / 2) / (double) samplerate;
+		fprintf(fp, "%f, %f\n", t, db);
+	}
+	fclose(fp);
+	return TSDRGPU_OK;
+}
+
 int tsdrgpu_frd_get_plots(tsdrgpu_frd_t *f, void *stream_, uint32_t samplerate, double *h_frame_plot, int frame_cap,
                           double *h_line_plot, int line_cap) {
 	ARG_TRY((tsdrgpu_ctx_t *) NULL, f != NULL);

@@ -36,7 +36,7 @@ struct FrameJob {
 	int slot, nframes, w, h;
 	cudaEvent_t ev;
 	uint32_t samplerate;      // plots
-	int foff, flen, loff, llen; uint64_t calls; int reset_announce;
+	int foff, flen, loff, llen; uint64_t calls; int reset_announce, dump_announce;
 	int snr_valid;            // frames: results carry an SNR to announce
 	int pll_valid;            // frames: h_pll_rr holds the refresh rates the PLL set
 };
@@ -209,6 +209,7 @@ static void *delivery_main(void *arg) {
 			pthread_mutex_unlock(&p->mu);
 		} else if (j.kind == 1) {
 			if (j.reset_announce && p->value_cb) p->value_cb(1 /* VALUE_ID_AUTOCORRECT_RESET */, 0, 0, p->user);
+			if (j.dump_announce && p->value_cb) p->value_cb(5 /* VALUE_ID_AUTOCORRECT_DUMPED, frameratedetector.c:115 */, 0, 0, p->user);
 			if (p->plot_cb) {
 				p->plot_cb(0 /* PLOT_ID_FRAME */, j.foff, p->h_plot_frame[j.slot], j.flen, j.samplerate, p->user);
 				p->plot_cb(1 /* PLOT_ID_LINE */, j.loff, p->h_plot_line[j.slot], j.llen, j.samplerate, p->user);
@@ -375,6 +376,12 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 				}
 				p->plot_cap = need;
 			}
+			int dump_announce = 0;
+			if (p->params[TSDRGPU_PARAM_AUTOCORR_DUMP]) {                    // frameratedetector.c:110-116: "autocorr.csv" in the working directory
+				p->params[TSDRGPU_PARAM_AUTOCORR_DUMP] = 0;
+				if ((rc = tsdrgpu_frd_dump_csv(p->frd, p->s_main, p->samplerate, cap, (uint32_t) want, "autocorr.csv"))) return rc;
+				dump_announce = 1;
+			}
 			uint64_t calls = 0;
 			if ((rc = tsdrgpu_frd_run_async(p->frd, p->s_main, p->samplerate, cap, (uint32_t) want,
 			                                slot >= 0 ? p->h_plot_frame[slot] : NULL, fmax - fmin,
@@ -385,7 +392,7 @@ static int feed_capture(tsdrgpu_pipeline *p, const float *d_iq, uint64_t pairs, 
 			if (slot >= 0) {
 				FrameJob j; memset(&j, 0, sizeof j);
 				j.kind = 1; j.slot = slot; j.samplerate = p->samplerate; j.foff = fmin; j.flen = fmax - fmin; j.loff = lmin; j.llen = lmax - lmin;
-				j.calls = calls; j.reset_announce = reset_announce;
+				j.calls = calls; j.reset_announce = reset_announce; j.dump_announce = dump_announce;
 				if ((rc = submit(p, j, p->s_main))) return rc;
 			}
 		}

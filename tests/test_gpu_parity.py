@@ -407,6 +407,28 @@ def test_accumulate_exact_and_framerate_plots(gpu, O):
         assert int(np.argmax(gp)) == int(np.argmax(fp))       # the lag the GUI would pick is the same
 
 
+def test_autocorrelation_dump_csv(gpu, O, tmp_path):
+    """PARAM_AUTOCORR_DUMP (frameratedetector.c:64-85, 110-116): the CSV of one capture's autocorrelation -- same header, same
+    lags (the first fft_getrealsize(2 size) / 4 of them), same time column; the dB column against the reference's autocorrelation
+    within the FFT tolerance (2e-6 of the peak on |r|) plus the six printed decimals."""
+    fs, size = 2_000_000, 112_727                          # the detector's own (odd) capture size at 2 MS/s
+    x = np.abs(synth.video_like_iq(size, fs, 400, 200, 50.0, seed=77).view(np.complex64)).astype(np.float32)
+    path = str(tmp_path / "autocorr.csv")
+    gpu.framerate_detector().dump_csv(fs, dev(x), path)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "ms, dB"
+    rows = np.array([[float(v) for v in ln.split(",")] for ln in lines[1:]])
+    want = O.autocorrelation(x).astype(np.float64)
+    nreal = 1 << (int(2 * size).bit_length() - 1)
+    maxels = nreal // 2
+    assert rows.shape == (maxels // 2, 2)
+    k = np.arange(maxels // 2)
+    assert np.allclose(rows[:, 0], np.round(1000.0 * k / fs, 6), atol=1e-6)
+    mag = np.sqrt(want[0:maxels:2] ** 2 + want[1:maxels:2] ** 2)
+    got = 10.0 ** (rows[:, 1] / 10.0)
+    assert np.max(np.abs(got - mag)) <= 2e-6 * mag.max() + 3e-7 * mag.max()
+
+
 def test_framerate_detector_overlapped_mode_gives_the_same_plots(gpu):
     """tsdrgpu_frd_set_overlap: the same kernels on the detector's own stream with its own work buffers -- plots, peaks and call
     counts must be bit-identical to the in-stream mode, also when the caller keeps its stream busy and reuses the capture

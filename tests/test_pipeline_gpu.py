@@ -66,6 +66,31 @@ def test_pipeline_matches_stagewise_oracle():
     p.close()
 
 
+def test_pipeline_autocorr_dump_parameter(tmp_path, monkeypatch):
+    """PARAM_AUTOCORR_DUMP (frameratedetector.c:110-116): set once -> the next capture's autocorrelation lands in autocorr.csv in the
+    working directory, value id 5 (VALUE_ID_AUTOCORRECT_DUMPED) is announced once before that capture's plots, the parameter clears
+    itself, plots and frames go on as without it."""
+    from tempestsdr_b200 import pipeline
+    monkeypatch.chdir(tmp_path)
+    fs, h, fv = 2_000_000, 125, 60.0
+    iq_all = synth.video_like_iq(6 * 65536, fs, 533, h, fv, seed=5)
+    events = []
+    p = pipeline.Pipeline(samplerate=fs, height=h, refreshrate=fv, batch_frames=1, block_when_busy=True, params={"autoshift": 1, "lowpass_before_sync": 1},
+                          on_plot=lambda pid, off, v, sr: events.append(("plot", pid)), on_value=lambda vid, a, b: events.append(("value", vid)))
+    p.set_param("autocorr_dump", 1)
+    for k in range(12):
+        p.process(iq_all[k * 65536:(k + 1) * 65536].copy(), 0)
+    p.flush()
+    st = p.stats()
+    p.close()
+    assert st.captures >= 2
+    dumped = [i for i, e in enumerate(events) if e == ("value", 5)]
+    assert len(dumped) == 1 and dumped[0] < events.index(("plot", 0))
+    lines = (tmp_path / "autocorr.csv").read_text().splitlines()
+    cap = int(3.1 * fs / 55.0)
+    assert lines[0] == "ms, dB" and len(lines) - 1 == (1 << (int(2 * cap).bit_length() - 1)) // 4
+
+
 def run_oracle_stream_pll(O, iq_blocks, fs, h, fv):
     """The same single-threaded replay with the PLL switched on (syncdetector.c:133-153): after every frame the refresh rate
     the oracle's post-processor holds moves, and the NEXT group of ten decimator blocks is cut and resampled with it -- the
