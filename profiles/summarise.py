@@ -43,7 +43,22 @@ def main():
         if "autocorr_sweep" in d:
             for size, v in d["autocorr_sweep"].items():
                 print(f"  autocorr {size}: {v['us_per_autocorrelation']:.2f} us  {v['gbs_vs_bytes_moved']:.0f} GB/s moved ({100 * v['frac_vs_bytes_moved']:.0f} %)  {v['gbs_vs_28N']:.0f} GB/s vs 28N ({100 * v['frac_vs_28N']:.0f} %)")
-        for key in ("e2e_int8_transport", "superbandwidth", "variants"):
+        pt = e2e.get("plugin_thread_per_block_us")
+        if pt:
+            print(f"  plugin thread per 2 MiB block: {pt['in_the_plugin_between_callbacks']:.0f} us in the plugin, {pt['inside_the_library_callback']:.0f} us in the library's callback")
+        for name, v in (d.get("other_shapes") or {}).items():
+            if "value" in v:
+                print(f"  other shape {name}: {v['value'] / 1e3:.2f} GS/s  {v['ms_per_batch']:.4f} ms per batch  frame {v.get('frame')}")
+        sb = d.get("superbandwidth")
+        if sb and "ms_per_stitch" in sb:
+            fr = sb.get("frames") or {}
+            par = sb.get("parity_vs_one_gpu_path") or {}
+            print(f"  superbandwidth, {sb['hops']} hops of {sb['n_per_hop']}: {sb['ms_per_stitch']:.4f} ms per stitch, one GPU {sb.get('one_gpu_ms', float('nan')):.4f} ms "
+                  f"-> x{sb.get('speedup_vs_one_gpu', float('nan')):.2f}; stitch + frames {fr.get('ms_per_round_stitch_plus_frames')} ms; "
+                  f"max err / peak {par.get('max_err_over_peak')}, lags equal {par.get('lags_equal')}; NCCL all-gather formulation {sb.get('nccl_allgather_baseline_ms')} ms")
+        elif sb:
+            print(f"  superbandwidth: {json.dumps(sb)[:400]}")
+        for key in ("e2e_int8_transport", "variants"):
             if key in d:
                 print(f"  {key}: {json.dumps(d[key])[:400]}")
 
