@@ -34,3 +34,18 @@ def test_own_arm_needs_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and r.stdout.strip() == ""          # no number without the CUDA path
+
+
+def test_bench_shapes_are_the_baseline_geometries():
+    """BENCH_SHAPE selects BASELINE configs[1] (default), configs[4]'s per-GPU stream (cfg5) or configs[0] (cfg1): widths and
+    capture sizes as SURVEY section 8 lists them (the GUI's total-height convention)."""
+    code = ("import bench, json; print(json.dumps({'w': bench.geometry(), 'h': bench.HEIGHT, 'fs': bench.FS, 'cap': int(3.1 * bench.FS / 55.0), "
+            "'frames': bench.FRAMES_PER_BATCH}))")
+    want = {"cfg2": (740, 1125, 25_000_000, 1_409_090), "cfg5": (1481, 1125, 50_000_000, 2_818_181), "cfg1": (507, 525, 8_000_000, 450_909)}
+    for shape, (w, h, fs, cap) in want.items():
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, BENCH_SHAPE=shape))
+        assert r.returncode == 0, r.stderr[-1500:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert (d["w"], d["h"], d["fs"], d["cap"]) == (w, h, fs, cap), (shape, d)
+        # the resident IQ of a batch must exceed the 126 MB L2 (no L2 flush between timed iterations)
+        assert 8 * d["frames"] * int(d["fs"] / 60.0) > 200e6, (shape, d)
