@@ -825,7 +825,10 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
     if solo[0].item() != 1.0:
         return {"hops": H, "n_per_hop": n_fft, "error": "rank 0's one-GPU reference failed: " + str(r0.get("error"))}
     one_ms = solo[1].item()
-    # ---- the group: windows mapped into every rank (CUDA IPC)
+    # ---- the group: windows mapped into every rank (CUDA IPC); a flag wait gives up after 10 s here (a lost rank then costs the
+    # section at most a few tens of seconds before every rank leaves it together)
+    os.environ.setdefault("TSDRGPU_SBM_TIMEOUT_MS", "10000")
+    host_barrier()
     grp = superband.SuperbGroup.for_process_group(gpu, hop_pairs)
 
     def group_ok():
@@ -848,8 +851,10 @@ def superband_bench(gpu, torch, dist, iq_dev, world, rank, barrier, host_barrier
             pass
         return partial
 
-    for _ in range(3):
+    for k in range(3):
         stitch()
+        if k == 0 and not group_ok():                     # the first stitch (tables, first launches) is where ranks can drift apart: check at once
+            return give_up("in the first warm-up stitch", {"hops": H, "n_per_hop": n_fft, "one_gpu_ms": one_ms})
     if not group_ok():
         return give_up("in the warm-up stitches", {"hops": H, "n_per_hop": n_fft, "one_gpu_ms": one_ms})
     lags = grp.lags()
