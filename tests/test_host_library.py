@@ -93,6 +93,55 @@ def test_status_codes_and_error_text_match_the_reference(tmp_path):
 
 
 @needs_ref
+def test_more_setter_scenarios_match_the_reference(tmp_path):
+    """Second sweep of the boundary (TSDRLibrary.c:136-262, 420-560): every setter with in-range, edge and out-of-range values, before
+    and after a plugin is loaded, repeated loads / unloads -- status codes and error texts identical to the compiled reference."""
+    raw = tmp_path / "iq.raw"
+    synth.noise_iq(4096, seed=2).tofile(raw)
+    nv, npl = VALUE_CB(lambda *a: None), PLOT_CB(lambda *a: None)
+    results = {}
+    for name, path in (("mine", MINE), ("ref", orc.REF_LIB_SO)):
+        lib = bind(path)
+        t = C.c_void_p()
+        lib.tsdr_init(C.byref(t), nv, npl, None)
+        r = []
+        txt = lambda: lib.tsdr_getlasterrortext(t)
+        r.append(("fresh: error text", None, txt()))
+        r.append(("isrunning fresh", lib.tsdr_isrunning(t), None))
+        r.append(("setbasefreq without plugin", lib.tsdr_setbasefreq(t, 100_000_000), txt()))
+        r.append(("setgain without plugin", lib.tsdr_setgain(t, 0.5), txt()))
+        r.append(("sync before resolution", lib.tsdr_sync(t, 1, 0), txt()))
+        for h, fv in ((525, 60.0), (1125, 59.94), (-3, 60.0), (525, 0.0), (525, -1.0), (1, 1.0)):
+            r.append((f"setresolution {h} {fv}", lib.tsdr_setresolution(t, h, fv), txt()))
+        lib.tsdr_setresolution(t, 525, 60.0)
+        for mb in (0.0, 0.5, 1.0, -0.1, 1.0001):
+            r.append((f"motionblur {mb}", lib.tsdr_motionblur(t, mb), txt()))
+        for pid in range(-1, 11):
+            r.append((f"param_int {pid}", lib.tsdr_setparameter_int(t, pid, 1), txt()))
+            lib.tsdr_setparameter_int(t, pid, 0)
+        for pid in range(-1, 4):
+            r.append((f"param_double {pid}", lib.tsdr_setparameter_double(t, pid, 0.25), txt()))
+        r.append(("plugin ok", lib.tsdr_loadplugin(t, orc.REF_RAWFILE_SO.encode(), f'"{raw}" 8000000 float'.encode()), txt()))
+        r.append(("error text after success", None, txt()))
+        r.append(("plugin again", lib.tsdr_loadplugin(t, orc.REF_RAWFILE_SO.encode(), f'"{raw}" 2000000 int8'.encode()), txt()))
+        r.append(("getsamplerate", lib.tsdr_getsamplerate(t), txt()))
+        for g in (0.0, 1.0, -0.5, 1.5):
+            r.append((f"setgain {g}", lib.tsdr_setgain(t, g), txt()))
+        r.append(("setbasefreq", lib.tsdr_setbasefreq(t, 433_920_000), txt()))
+        for px, d in ((0, 0), (5, 0), (5, 1), (5, 2), (5, 3), (5, 4), (-5, 0), (10_000_000, 2), (10_000_000, 0)):
+            r.append((f"sync {px} {d}", lib.tsdr_sync(t, px, d), txt()))
+        r.append(("bad plugin params keep", lib.tsdr_loadplugin(t, orc.REF_RAWFILE_SO.encode(), b"nofile 0 float"), txt()))
+        r.append(("getsamplerate after failed load", lib.tsdr_getsamplerate(t), txt()))
+        r.append(("unload", lib.tsdr_unloadplugin(t), txt()))
+        r.append(("unload twice", lib.tsdr_unloadplugin(t), txt()))
+        r.append(("stop idle", lib.tsdr_stop(t), txt()))
+        lib.tsdr_free(C.byref(t))
+        results[name] = r
+    diff = [(a, b) for a, b in zip(results["mine"], results["ref"]) if a != b]
+    assert not diff, diff
+
+
+@needs_ref
 def test_readasync_without_gpu_fails_loudly(tmp_path):
     import torch
     if torch.cuda.is_available():
