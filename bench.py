@@ -311,6 +311,7 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
     for pid, v in ((0, 1), (1, 0), (6, 1)):          # AUTOSHIFT=1, PLL=0, LOW_PASS_BEFORE_SYNC=1: the reference arm's settings
         lib.tsdr_setparameter_int(t, pid, v)
     out = {"unavailable": None}
+    barriers = 0
     try:
         rc = lib.tsdr_loadplugin(t, plugin.encode(), params.encode())
         if rc != 0:
@@ -323,11 +324,11 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
             time.sleep(0.02)
         if not th.is_alive() or count["frames"] < 64:
             raise RuntimeError(f"no frames from tsdr_readasync (rc={rcs}): {lib.tsdr_getlasterrortext(t)}")
-        barrier()
+        barrier(); barriers += 1
         f0, t0, m0 = count["frames"], time.perf_counter(), time.monotonic()
         time.sleep(seconds)
         f1, t1, m1 = count["frames"], time.perf_counter(), time.monotonic()
-        barrier()
+        barrier(); barriers += 1
         lib.tsdr_stop(t)
         th.join(timeout=30)
         fps = (f1 - f0) / (t1 - t0)
@@ -349,6 +350,8 @@ def e2e_through_tsdr_api(local: int, rank: int, w: int, seconds: float, barrier)
     except Exception as e:
         out = {"unavailable": repr(e)[:300]}
     finally:
+        while barriers < 2:                               # a rank whose run failed still meets the others at both barriers
+            barrier(); barriers += 1
         try:
             lib.tsdr_free(C.byref(t))
         except Exception:
